@@ -1,0 +1,217 @@
+/*
+ * spfresh_b200.h — C ABI of libspfresh_b200.so, the B200 (sm_100a) implementation of the
+ * SPFresh/SPANN data-parallel hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry
+ * point replaces one batched seam of the reference (jairad26/spfresh, Rust); the reference
+ * interface it stands in for is cited as file:line next to it.  The binding a maintainer adds
+ * on the Rust side (an `extern "C"` block in a `spann-cuda-sys` crate) is in INTEGRATION.md.
+ *
+ * Conventions:
+ *  - every function returns SPF_OK (0) or a negative SPF_E_* code; the message is available
+ *    from spf_last_error() (thread-local).  No exception or abort crosses the boundary.
+ *  - host pointers passed in are only read during the call; nothing is retained.
+ *  - row / point ids are uint64_t (Rust usize); cluster slots are uint32_t.
+ *  - all floating point is IEEE f32; distances are computed exactly as the reference does
+ *    (sequential, un-fused accumulation), so results are bit-identical to it.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with
+ *    SPF_E_NO_DEVICE.
+ *  - a context may be used from several host threads; calls on one context are serialised.
+ */
+#ifndef SPFRESH_B200_H
+#define SPFRESH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define SPF_ABI_VERSION 1
+
+enum {
+  SPF_OK = 0,
+  SPF_E_INVALID = -1,    /* bad argument (null pointer, out-of-range row, k == 0, ...)      */
+  SPF_E_NO_DEVICE = -2,  /* no usable CUDA device / not an sm_100 part                      */
+  SPF_E_CUDA = -3,       /* a CUDA runtime or driver call failed                            */
+  SPF_E_OOM = -4,        /* host or device allocation failed                                */
+  SPF_E_IO = -5,         /* posting-list directory could not be read / written              */
+  SPF_E_STATE = -6       /* call order violated (e.g. k-means++ session exhausted)          */
+};
+
+/* src/spann/config.rs:92-100 — "Euclidean" | "Manhattan" | "Chebyshev"
+ * (src/distances/distance.rs:14-43).  Euclidean is the SQUARED L2 distance, as there. */
+enum { SPF_METRIC_EUCLIDEAN = 0, SPF_METRIC_MANHATTAN = 1, SPF_METRIC_CHEBYSHEV = 2 };
+
+/* spf_assign flags */
+enum {
+  SPF_ASSIGN_DEFAULT = 0,
+  SPF_ASSIGN_FORCE_EXACT = 1,   /* Euclidean only: skip the tcgen05 candidate GEMM and use the
+                                   CUDA-core direct-form kernel for all n*k distances          */
+  SPF_ASSIGN_NO_CSR = 2         /* only best/dmin are needed (no boundary replication, no CSR) */
+};
+
+typedef struct spf_ctx spf_ctx;                  /* one CUDA device + stream + scratch        */
+typedef struct spf_dataset spf_dataset;          /* n x d f32 rows resident in HBM            */
+typedef struct spf_assign_result spf_assign_result;
+typedef struct spf_kmpp spf_kmpp;                /* k-means++ session state in HBM            */
+typedef struct spf_index spf_index;              /* posting lists + centroids resident in HBM */
+
+/* ---- library / context ---------------------------------------------------------------- */
+int         spf_abi_version(void);
+const char* spf_last_error(void);
+int         spf_device_count(void);
+
+int  spf_ctx_create(int device, spf_ctx** out);
+void spf_ctx_destroy(spf_ctx* ctx);
+int  spf_ctx_device(const spf_ctx* ctx);
+/* cudaStream_t all work of this context is enqueued on (for CUDA-event timing by callers). */
+void* spf_ctx_stream(spf_ctx* ctx);
+int  spf_ctx_synchronize(spf_ctx* ctx);
+/* Per-kernel device timing: when enabled, the library brackets its dominant kernels with CUDA
+ * events on its stream; spf_ctx_kernel_ms returns the duration of the named kernel's last
+ * launch ("assign_tc", "assign_exact", "resolve", "csr", "scan", "probe", ...) or < 0. */
+int   spf_ctx_set_profiling(spf_ctx* ctx, int enabled);
+float spf_ctx_kernel_ms(spf_ctx* ctx, const char* name);
+/* Number of kernels this library launched on this context since creation. */
+uint64_t spf_ctx_launch_count(const spf_ctx* ctx);
+
+/* ---- dataset -------------------------------------------------------------------------- *
+ * Stands in for the borrowed ArrayView2<F> held by SpannIndexBuilder / HierarchicalClustering
+ * (src/spann/spann_builder.rs:10,20; src/clustering/hierarchical.rs:45).  `rows` is row-major
+ * with `row_stride` elements between rows (>= d).  The rows are copied to the device. */
+int  spf_dataset_upload(spf_ctx* ctx, const float* rows, uint64_t n, uint32_t d,
+                        uint64_t row_stride, spf_dataset** out);
+/* Same, but `dev_rows` already is device memory of this context's device (dense, stride d);
+ * it is copied device-to-device into the library's padded layout. */
+int  spf_dataset_from_device(spf_ctx* ctx, const void* dev_rows, uint64_t n, uint32_t d,
+                             spf_dataset** out);
+void spf_dataset_free(spf_dataset* ds);
+uint64_t spf_dataset_rows(const spf_dataset* ds);
+uint32_t spf_dataset_dim(const spf_dataset* ds);
+
+/* ---- single-pair distance (API-compat seam) --------------------------------------------- *
+ * DistanceMetric::compute, src/distances/distance.rs:7-43 — evaluated on the device for
+ * `pairs` pairs: out[i] = metric(a + i*d, b + i*d).  Present so the per-pair trait has a
+ * device-backed equivalent; batched callers use the entry points below. */
+int spf_distance_pairs(spf_ctx* ctx, int metric, const float* a, const float* b, uint32_t d,
+                       uint64_t pairs, float* out);
+
+/* ---- assignment ------------------------------------------------------------------------ *
+ * HierarchicalClustering::assign_points_to_clusters, src/clustering/hierarchical.rs:295-364
+ * (and assign_points :368-390 when point_idx == NULL).
+ *   point_idx     m dataset rows to assign, or NULL for rows 0..m-1 (m must equal n then)
+ *   centroid_rows k dataset rows acting as centroids (Cluster::centroid_idx)
+ *   boundary_factor  BOUNDARY_THRESHOLD, 1.1 in the reference (:55)
+ * Result (device resident until fetched): per listed point the nearest centroid slot and its
+ * distance, plus the cluster-major CSR of members (nearest + boundary replicas, input order
+ * preserved inside each cluster) — exactly the Vec<Vec<usize>> the reference returns. */
+int  spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
+                const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
+                spf_assign_result** out);
+uint64_t spf_assign_points(const spf_assign_result* r);        /* m                         */
+uint32_t spf_assign_clusters(const spf_assign_result* r);      /* k                         */
+uint64_t spf_assign_total(const spf_assign_result* r);         /* sum of cluster sizes      */
+/* Copies what is non-NULL: best[m], dmin[m], offsets[k+1], members[total] (dataset rows). */
+int  spf_assign_fetch(const spf_assign_result* r, uint32_t* best, float* dmin,
+                      uint64_t* offsets, uint64_t* members);
+void spf_assign_free(spf_assign_result* r);
+
+/* ---- centroid update ------------------------------------------------------------------- *
+ * HierarchicalClustering::update_centroids, src/clustering/hierarchical.rs:138-181, with
+ * compute_mean src/clustering/utils.rs:5-15: per cluster the f32 mean over all members
+ * (row-by-row sum in member order, then division) and the member nearest to it (leftmost on
+ * ties); an empty cluster keeps old_rows[c].  means_out (k*d) may be NULL.
+ * The CSR is either host arrays or a previous spf_assign result (no re-upload). */
+int spf_update_medoids(spf_dataset* ds, int metric, const uint64_t* offsets,
+                       const uint64_t* members, uint32_t k, const uint64_t* old_rows,
+                       uint64_t* new_rows, float* means_out);
+int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result* r,
+                            const uint64_t* old_rows, uint64_t* new_rows, float* means_out);
+
+/* ---- k-means++ ------------------------------------------------------------------------- *
+ * HierarchicalClustering::initialize_clusters_kmeans_plus_plus, hierarchical.rs:249-293.
+ * The host keeps the RNG (rand::SmallRng in the reference).  begin() takes the uniformly
+ * drawn first row (:253-256).  Each round() folds the newest centroid into the running
+ * minimum distance (bit-identical to the reference's per-round recomputation :260-276),
+ * forms sum and weights d^2/max(sum,1e-10) (:278-282) and performs the weighted pick of
+ * rand 0.9 WeightedIndex for the uniform draw u01 in [0,1) (:285-286).
+ * round() returns SPF_OK with *chosen set, or 1 (positive) when the weighted pick is
+ * impossible (all-zero or non-finite weights, the Err arm :287-290): the host then draws a
+ * uniform row itself and calls spf_kmpp_push(). */
+int  spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** out);
+int  spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen);
+int  spf_kmpp_push(spf_kmpp* s, uint64_t row);
+/* Diagnostics of the last round: the f32 sum (:278) and the f64 weight total. */
+int  spf_kmpp_last_sums(const spf_kmpp* s, float* sum, double* total);
+void spf_kmpp_free(spf_kmpp* s);
+
+/* ---- bisect seed ----------------------------------------------------------------------- *
+ * The fold of create_subclusters, hierarchical.rs:112-126: argmax over members != c1 of
+ * d(c1, member), strict >, identity (row 0, distance 0). */
+int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* members,
+                 uint64_t m, uint64_t* out_row);
+
+/* ---- index (posting lists in HBM) + query ---------------------------------------------- *
+ * spf_index_pack stands in for SpannIndex::create_posting_lists + build_kdtree,
+ * src/spann/spann_index.rs:56-114: list c holds the vectors of rows
+ * members[offsets[c]..offsets[c+1]) in that order and is represented by the dataset row
+ * centroid_rows[c].  Instead of one bincode file per cluster read per probe
+ * (src/spann/posting_lists.rs:98-106) the lists stay resident in HBM.
+ * Multi-GPU: each rank packs only the lists [list_begin, list_end) it owns but all centroids. */
+int  spf_index_pack(spf_dataset* ds, const uint64_t* offsets, const uint64_t* members,
+                    const uint64_t* centroid_rows, uint32_t nlists,
+                    uint32_t list_begin, uint32_t list_end, spf_index** out);
+/* Load an index saved in the reference's on-disk layout (posting_list_{id}.bin +
+ * cluster_ids.bin, bincode 1.3; src/spann/posting_lists.rs:42-45,64-129).  The reference
+ * keeps centroids only inside output.kdtree (kiddo internals); the dense centroid matrix is
+ * therefore passed in (nlists x d, list id order) — see INTEGRATION.md. */
+int  spf_index_load_dir(spf_ctx* ctx, const char* dir, const float* centroids, uint32_t nlists,
+                        uint32_t d, spf_index** out);
+/* Write the lists of this index in the reference's on-disk layout. */
+int  spf_index_save_dir(const spf_index* idx, const char* dir);
+void spf_index_free(spf_index* idx);
+uint32_t spf_index_lists(const spf_index* idx);
+uint64_t spf_index_vectors(const spf_index* idx);   /* total vectors stored on this rank */
+
+/* Batched SpannIndex::find_k_nearest_neighbor_spann, src/spann/spann_index.rs:148-197, for nq
+ * queries (row-major nq x d):
+ *   probe   the nprobe nearest centroids by squared L2, ascending (kiddo nearest_n :164);
+ *           nprobe == 0 means nprobe = k, the reference behaviour;
+ *   prune   thr = prune_factor * (d(q, c_nearest) + FLT_EPSILON), 1.2 in the reference (:165);
+ *   scan    every vector of every probed list, keep dist <= thr (:168-179);
+ *   top-k   stable sort by distance in encounter order, truncate to k, no de-duplication
+ *           (:188-193).
+ * Outputs: counts[q] <= k results per query (0 == the reference's None), ids / dists are
+ * nq x k (rows padded with UINT64_MAX / +inf), vectors (nq x k x d) may be NULL.
+ * keys (nq x k, may be NULL) receives the stable-order key of each result,
+ * (distance bits << 32 | encounter index), which is what a multi-GPU merge sorts on. */
+int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t k,
+                     uint32_t nprobe, float prune_factor, uint64_t* ids, float* dists,
+                     uint32_t* counts, float* vectors, uint64_t* keys);
+/* Bytes of posting-list vector payload the last spf_search_batch streamed
+ * (sum over queries and probed lists of |L| * d * 4): the roofline numerator of the scan. */
+uint64_t spf_index_last_scan_bytes(const spf_index* idx);
+
+/* Merge per-rank partial results of spf_search_batch (list-sharded index): `parts` rank-major
+ * arrays of nq x k keys / ids / dists, counts per rank and query; writes the global top-k. */
+int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys,
+                   const uint64_t* ids, const float* dists, const uint32_t* counts,
+                   uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
+
+/* ---- tuning knobs (not part of the drop-in surface; used by the tests to reach rare paths) -- *
+ * "cand_cap" candidate slots per point (default 128), "force_exact", "tc_min_k", "tc_min_m",
+ * "kmpp_exact_sum" (1: sequential f32 sum, bit-parity; 0: tree sum), "cc_matrix_max_k". */
+int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPFRESH_B200_H */

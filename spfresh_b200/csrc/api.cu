@@ -1,0 +1,220 @@
+// api.cu — context, dataset and error plumbing of the C ABI (include/spfresh_b200.h).
+#include <cuda.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace spf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace spf
+
+using namespace spf;
+
+extern "C" {
+
+int spf_abi_version(void) { return SPF_ABI_VERSION; }
+
+const char* spf_last_error(void) { return spf::g_err; }
+
+int spf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int spf_ctx_create(int device, spf_ctx** out) {
+  if (!out) return fail(SPF_E_INVALID, "spf_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = spf_device_count();
+  if (n <= 0) return fail(SPF_E_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(SPF_E_INVALID, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  SPF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SPF_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+  SPF_CUDA(cudaSetDevice(device));
+  spf_ctx* c = new (std::nothrow) spf_ctx();
+  if (!c) return fail(SPF_E_OOM, "out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev[0]);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev[1]);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(SPF_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+  }
+  // keep freed temporaries cached in the stream-ordered pool
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    fn = nullptr;
+  cudaGetLastError();
+  c->tma_encode = fn;
+  const char* env = getenv("SPF_FORCE_EXACT");
+  if (env && atoi(env)) c->params.force_exact = 1;
+  *out = c;
+  return SPF_OK;
+}
+
+void spf_ctx_destroy(spf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+  if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int spf_ctx_device(const spf_ctx* c) { return c ? c->device : -1; }
+void* spf_ctx_stream(spf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int spf_ctx_synchronize(spf_ctx* c) {
+  if (!c) return fail(SPF_E_INVALID, "ctx is NULL");
+  SPF_CUDA(cudaStreamSynchronize(c->stream));
+  return SPF_OK;
+}
+
+int spf_ctx_set_profiling(spf_ctx* c, int enabled) {
+  if (!c) return fail(SPF_E_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->profiling = enabled != 0;
+  return SPF_OK;
+}
+
+float spf_ctx_kernel_ms(spf_ctx* c, const char* name) {
+  if (!c || !name) return -1.0f;
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->kernel_ms.find(name);
+  return it == c->kernel_ms.end() ? -1.0f : it->second;
+}
+
+uint64_t spf_ctx_launch_count(const spf_ctx* c) { return c ? c->launches : 0; }
+
+// Internal tuning knobs (tests use them to force the rare paths; not part of the drop-in ABI).
+int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
+  if (!c || !name) return fail(SPF_E_INVALID, "ctx/name is NULL");
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::string s(name);
+  if (s == "cand_cap") {
+    if (value < 2 || value > 1024) return fail(SPF_E_INVALID, "cand_cap must be in [2,1024]");
+    c->params.cand_cap = value;
+  } else if (s == "force_exact") c->params.force_exact = value;
+  else if (s == "tc_min_k") c->params.tc_min_k = value;
+  else if (s == "tc_min_m") c->params.tc_min_m = value;
+  else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
+  else if (s == "cc_matrix_max_k") c->params.cc_matrix_max_k = value;
+  else return fail(SPF_E_INVALID, "unknown parameter '%s'", name);
+  return SPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dataset
+// ---------------------------------------------------------------------------------------------
+static int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out) {
+  if (!c || !out) return fail(SPF_E_INVALID, "ctx/out is NULL");
+  if (n == 0 || d == 0) return fail(SPF_E_INVALID, "dataset must have n > 0 and d > 0");
+  if (n >= (1ull << 32)) return fail(SPF_E_INVALID, "n must be < 2^32 rows per device shard");
+  SPF_CUDA(cudaSetDevice(c->device));
+  spf_dataset* ds = new (std::nothrow) spf_dataset();
+  if (!ds) return fail(SPF_E_OOM, "out of host memory");
+  ds->ctx = c;
+  ds->n = n;
+  ds->d = d;
+  ds->ld = round_up(d, 4);
+  size_t bytes = (size_t)n * ds->ld * sizeof(float);
+  cudaError_t e = cudaMalloc((void**)&ds->x, bytes);
+  if (e != cudaSuccess) {
+    delete ds;
+    return fail(SPF_E_OOM, "cudaMalloc of %zu bytes for the dataset failed: %s", bytes, cudaGetErrorString(e));
+  }
+  *out = ds;
+  return SPF_OK;
+}
+
+int spf_dataset_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride,
+                       spf_dataset** out) {
+  if (!rows) return fail(SPF_E_INVALID, "rows is NULL");
+  if (row_stride < d) return fail(SPF_E_INVALID, "row_stride (%llu) < d (%u)", (unsigned long long)row_stride, d);
+  spf_dataset* ds = nullptr;
+  SPF_TRY(dataset_alloc(c, n, d, &ds));
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaError_t e = cudaSuccess;
+  if (ds->ld != d) e = cudaMemsetAsync(ds->x, 0, (size_t)n * ds->ld * sizeof(float), c->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(ds->x, (size_t)ds->ld * sizeof(float), rows, (size_t)row_stride * sizeof(float),
+                          (size_t)d * sizeof(float), (size_t)n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    spf_dataset_free(ds);
+    return fail(SPF_E_CUDA, "dataset upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = ds;
+  return SPF_OK;
+}
+
+int spf_dataset_from_device(spf_ctx* c, const void* dev_rows, uint64_t n, uint32_t d, spf_dataset** out) {
+  if (!dev_rows) return fail(SPF_E_INVALID, "dev_rows is NULL");
+  spf_dataset* ds = nullptr;
+  SPF_TRY(dataset_alloc(c, n, d, &ds));
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaError_t e = cudaSuccess;
+  if (ds->ld != d) e = cudaMemsetAsync(ds->x, 0, (size_t)n * ds->ld * sizeof(float), c->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(ds->x, (size_t)ds->ld * sizeof(float), dev_rows, (size_t)d * sizeof(float),
+                          (size_t)d * sizeof(float), (size_t)n, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    spf_dataset_free(ds);
+    return fail(SPF_E_CUDA, "dataset device copy failed: %s", cudaGetErrorString(e));
+  }
+  *out = ds;
+  return SPF_OK;
+}
+
+void spf_dataset_free(spf_dataset* ds) {
+  if (!ds) return;
+  cudaSetDevice(ds->ctx->device);
+  cudaStreamSynchronize(ds->ctx->stream);
+  if (ds->x) cudaFree(ds->x);
+  if (ds->xnorm) cudaFree(ds->xnorm);
+  delete ds;
+}
+
+uint64_t spf_dataset_rows(const spf_dataset* ds) { return ds ? ds->n : 0; }
+uint32_t spf_dataset_dim(const spf_dataset* ds) { return ds ? ds->d : 0; }
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+// assign_tc.cu — tcgen05 / TMEM / TMA candidate GEMM for squared-Euclidean assignment (sm_100a).
+//
+// Replaces the Euclidean case of the n x k distance loop in assign_points_to_clusters,
+// src/clustering/hierarchical.rs:302-326 (reference).  d(x,c) = |x|^2 - 2 x.c + |c|^2 is a dense
+// contraction: X.C^T runs on the 5th-gen tensor cores as ONE TF32 pass with fp32 accumulation
+// in TMEM; the m x k matrix is never written.  The epilogue keeps, per point, a running
+// minimum and emits only the centroids that can still matter:
+//     d_tf32 < f * (runmin_tf32 + E) + E,      E = tc_err_bound(|x|^2, max|c|^2, ld)
+// which is a superset of {argmin candidates} U {j : d_ref(j) < f * dmin_ref} because E bounds
+// |d_tf32 - d_ref| and the running minimum only decreases.  resolve.cu then decides every
+// comparison on exact direct-form values, so the final result is bit-identical to the
+// reference while the O(n k d) work runs at tensor-core rate (1 pass instead of the 3 a
+// 3xTF32 split would need).
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0     TMA producer: the 128 x ld point tile (A, stationary for a whole row block) and a
+//              4-stage ring of 256 x 32 centroid tiles (B), both SWIZZLE_128B, K-major
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=8 per MMA)
+//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time from the double-buffered 2 x 256
+//              column accumulator, running min + candidate emission, one point per thread
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace spf {
+
+namespace {
+
+constexpr int BM = 128;            // points per CTA tile (TMEM lanes)
+constexpr int BN = 256;            // centroids per accumulator (TMEM columns)
+constexpr int BK = 32;             // floats per K block = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;          // tf32 MMA K (32 bytes)
+constexpr int KB_MAX = 4;          // stationary A supports ld <= 128
+constexpr int NSTAGE = 4;          // B ring depth
+constexpr int A_KB_BYTES = BM * BK * 4;       // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 4;    // 32 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_A = KB_MAX * A_KB_BYTES;                  // 64 KB
+constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
+constexpr int SMEM_BAR_OFF = SMEM_A + SMEM_B;
+constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;        // + barriers + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t receives lane (base + t), columns col .. col+31.
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024
+// bytes apart).  Matches the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256.
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)(BM >> 4) << 24);
+
+struct TcArgs {
+  uint32_t m, k, ld, kb;            // kb = ceil(ld / 32) K blocks
+  uint32_t ntiles;                  // ceil(k / 256)
+  uint32_t nrowblocks;              // ceil(m / 128)
+  float factor;
+  const float* xnorm; const float* cnorm; const float* cnmax;
+  uint2* cand; uint32_t* cand_cnt; int cap;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + SMEM_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
+  uint64_t* a_full = bars;                 // [KB_MAX]
+  uint64_t* a_empty = bars + KB_MAX;       // [KB_MAX]
+  uint64_t* b_full = bars + 2 * KB_MAX;    // [NSTAGE]
+  uint64_t* b_empty = b_full + NSTAGE;     // [NSTAGE]
+  uint64_t* t_full = b_empty + NSTAGE;     // [2]
+  uint64_t* t_empty = t_full + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int i = 0; i < KB_MAX; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===========================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x, ++it) {
+        for (uint32_t kb = 0; kb < a.kb; ++kb) {
+          mbar_wait(&a_empty[kb], (it & 1) ^ 1);          // previous row block's MMAs are done with it
+          mbar_expect_tx(&a_full[kb], A_KB_BYTES);
+          tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(rb * BM));
+        }
+        for (uint32_t t = 0; t < a.ntiles; ++t) {
+          for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);
+            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &b_full[stage], (int)(kb * BK), (int)(t * BN));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==============================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0, tcount = 0;
+      for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x, ++it) {
+        for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
+          const uint32_t buf = tcount & 1, use = tcount >> 1;
+          mbar_wait(&t_empty[buf], (use & 1) ^ 1);        // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            if (t == 0) mbar_wait(&a_full[kb], it & 1);
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + kb * A_KB_BYTES);
+            const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              tc_mma_tf32(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 4), make_smem_desc(b_addr + k * UMMA_K * 4),
+                          IDESC_TF32, (kb | (uint32_t)k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&b_empty[stage]);                   // frees the B stage once these MMAs retire
+            if (t + 1 == a.ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&t_full[buf]);                        // accumulator complete → epilogue
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ==========================================
+    const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const float INF = __int_as_float(0x7f800000);
+    const float cnmax = a.cnmax[0];
+    const float f1 = fmaxf(a.factor, 1.0f);
+    uint32_t tcount = 0;
+    for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
+      const uint32_t row = rb * BM + quarter * 32 + lane;
+      const bool row_ok = row < a.m;
+      const float xn = row_ok ? a.xnorm[row] : 0.0f;
+      const float E = tc_err_bound(xn, cnmax, a.ld);
+      const float xnE = xn + E, EmX = E - xn;
+      const float slop = 1e-6f * (xn + cnmax) + 1e-30f;
+      uint2* crow = a.cand + (size_t)row * a.cap;
+      float tmin = INF;
+      uint32_t cnt = 0;
+      for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
+        const uint32_t buf = tcount & 1, use = tcount >> 1;
+        mbar_wait(&t_full[buf], use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN;
+        const float4* cn4 = reinterpret_cast<const float4*>(a.cnorm + (size_t)t * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tc_ld32(taddr + c * 32, v);
+          if (c == BN / 32 - 1) {                         // accumulator fully read → hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+          }
+          float cmin = INF;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 cn = __ldg(cn4 + c * 8 + i4);
+            v[i4 * 4 + 0] = fmaf(-2.0f, v[i4 * 4 + 0], cn.x);
+            v[i4 * 4 + 1] = fmaf(-2.0f, v[i4 * 4 + 1], cn.y);
+            v[i4 * 4 + 2] = fmaf(-2.0f, v[i4 * 4 + 2], cn.z);
+            v[i4 * 4 + 3] = fmaf(-2.0f, v[i4 * 4 + 3], cn.w);
+            cmin = fminf(cmin, fminf(fminf(v[i4 * 4 + 0], v[i4 * 4 + 1]), fminf(v[i4 * 4 + 2], v[i4 * 4 + 3])));
+          }
+          tmin = fminf(tmin, cmin);
+          // d < f (dmin_run + E) + E   with d = t + |x|^2
+          const float thr_t = row_ok ? fmaf(f1, tmin + xnE, EmX) + slop : -INF;
+          const uint32_t jbase = t * BN + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (v[i] < thr_t) {
+              if (cnt < (uint32_t)a.cap) crow[cnt] = make_uint2(jbase + i, __float_as_uint(v[i] + xn));
+              ++cnt;
+            }
+          }
+        }
+      }
+      if (row_ok) a.cand_cnt[row] = cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {ld, rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(c->tma_encode)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SPF_E_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return SPF_OK;
+}
+
+}  // namespace
+
+bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) {
+  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= (uint32_t)(KB_MAX * BK) &&
+         (int64_t)k >= c->params.tc_min_k && (int64_t)m >= c->params.tc_min_m;
+}
+
+int launch_assign_tc(spf_ctx* c, const float* P, uint64_t m, const float* C, uint32_t k, uint32_t ld,
+                     const float* xnorm, const float* cnorm_pad, const float* d_cnmax, float factor,
+                     uint2* cand, uint32_t* cand_cnt, int cap) {
+  CUtensorMap map_a, map_b;
+  SPF_TRY(make_map(c, &map_a, P, m, ld, BM));
+  SPF_TRY(make_map(c, &map_b, C, k, ld, BN));
+  TcArgs a;
+  a.m = (uint32_t)m; a.k = k; a.ld = ld; a.kb = (ld + BK - 1) / BK;
+  a.ntiles = (k + BN - 1) / BN;
+  a.nrowblocks = (uint32_t)ceil_div(m, BM);
+  a.factor = factor;
+  a.xnorm = xnorm; a.cnorm = cnorm_pad; a.cnmax = d_cnmax;
+  a.cand = cand; a.cand_cnt = cand_cnt; a.cap = cap;
+  SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count;
+  assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, a);
+  return check_launch(c, "assign_tc_kernel");
+}
+
+}  // namespace spf

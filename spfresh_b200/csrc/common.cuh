@@ -1,0 +1,174 @@
+// common.cuh — shared host/device plumbing for libspfresh_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/spfresh_b200.h"
+
+namespace spf {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define SPF_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      return ::spf::fail(_e == cudaErrorMemoryAllocation ? SPF_E_OOM : SPF_E_CUDA,          \
+                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                         __LINE__);                                                         \
+    }                                                                                       \
+  } while (0)
+
+#define SPF_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc < 0) return _rc;     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct Params {
+  int cand_cap = 128;        // candidate slots per point kept by the assign kernels
+  int force_exact = 0;       // 1: never use the tcgen05 candidate GEMM
+  int tc_min_k = 64;         // use the tensor path only when k >= this
+  int tc_min_m = 1024;       // ... and m >= this
+  int kmpp_exact_sum = 1;    // 1: sequential f32 sum (bit-parity with the reference)
+  int cc_matrix_max_k = 16384;  // precompute the k x k centroid-centroid matrix up to this k
+  int scan_threads = 256;
+};
+
+}  // namespace spf
+
+struct spf_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  bool profiling = false;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::map<std::string, float> kernel_ms;
+  uint64_t launches = 0;
+  spf::Params params;
+  void* tma_encode = nullptr;  // cuTensorMapEncodeTiled, resolved at context creation
+};
+
+struct spf_dataset {
+  spf_ctx* ctx = nullptr;
+  float* x = nullptr;     // n x ld, rows zero-padded to ld (multiple of 4 floats)
+  float* xnorm = nullptr; // lazily computed squared norms (tensor path)
+  uint64_t n = 0;
+  uint32_t d = 0, ld = 0;
+};
+
+struct spf_assign_result {
+  spf_ctx* ctx = nullptr;
+  uint64_t m = 0;
+  uint32_t k = 0;
+  uint64_t total = 0;
+  bool has_csr = false;
+  uint32_t* best = nullptr;      // device, m
+  float* dmin = nullptr;         // device, m
+  uint64_t* offsets = nullptr;   // device, k+1
+  uint32_t* members = nullptr;   // device, total: positions into the point list
+  uint64_t* point_idx = nullptr; // device, m dataset rows, or NULL for identity
+};
+
+namespace spf {
+
+// RAII device temporaries on the context stream (stream-ordered pool).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(cudaStream_t stream, size_t count) {
+    release();
+    s = stream;
+    n = count;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMallocAsync((void**)&p, bytes, stream);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(SPF_E_OOM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return SPF_OK;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  T* take() { T* q = p; p = nullptr; return q; }
+};
+
+// Brackets a named kernel with events when profiling is on (adds two syncs: only for bench).
+struct KernelTimer {
+  spf_ctx* c;
+  const char* name;
+  KernelTimer(spf_ctx* ctx, const char* nm) : c(ctx), name(nm) {
+    if (c->profiling) cudaEventRecord(c->ev[0], c->stream);
+  }
+  ~KernelTimer() {
+    if (c->profiling) {
+      cudaEventRecord(c->ev[1], c->stream);
+      cudaEventSynchronize(c->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      c->kernel_ms[name] = ms;
+    }
+  }
+};
+
+inline int check_launch(spf_ctx* c, const char* what, int nlaunches = 1) {
+  c->launches += (uint64_t)nlaunches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SPF_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return SPF_OK;
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+}  // namespace spf
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace spf {
+
+// Exact, un-fused element update of the three metrics (src/distances/distance.rs:16-43 →
+// ndarray-stats sq_l2_dist / l1_dist / linf_dist).  The intrinsics stop nvcc from contracting
+// mul+add into FMA, which would change the rounding.
+template <int METRIC>
+__device__ __forceinline__ float dist_step(float acc, float a, float b) {
+  float df = __fsub_rn(a, b);
+  if (METRIC == SPF_METRIC_EUCLIDEAN) return __fadd_rn(acc, __fmul_rn(df, df));
+  if (METRIC == SPF_METRIC_MANHATTAN) return __fadd_rn(acc, fabsf(df));
+  return fmaxf(acc, fabsf(df));   // linf: `if |df| > max {max = |df|}`; NaN leaves max unchanged
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace spf
+#endif

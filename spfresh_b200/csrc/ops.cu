@@ -1,0 +1,520 @@
+// ops.cu — centroid update, k-means++ rounds, bisect seed and per-pair distances.
+#include <math.h>
+
+#include "kernels.cuh"
+#include "pairdist.cuh"
+
+using namespace spf;
+
+struct spf_kmpp {
+  spf_dataset* ds = nullptr;
+  int metric = 0;
+  uint64_t rounds = 0;       // centroids folded into mind so far
+  uint64_t newest = 0;       // row of the newest centroid (not yet folded)
+  bool pending = true;       // newest still has to be folded
+  float* mind = nullptr;     // n running minimum distances
+  double* block_sums = nullptr;
+  int* bad = nullptr;
+  uint64_t nblocks = 0;
+  // device result slots: [0]=status [1]=chosen ; sums
+  uint64_t* res = nullptr;
+  float* d_sum = nullptr;
+  double* d_total = nullptr;
+  float last_sum = 0.f;
+  double last_total = 0.0;
+};
+
+namespace spf {
+namespace {
+
+constexpr int WBLOCK = 1024;   // weights per block in the k-means++ pick
+
+// ---- compute_mean (src/clustering/utils.rs:5-15): row-by-row f32 sum in member order, then a
+// true division by m.  One thread owns 4 consecutive dimensions of one cluster.
+__global__ void cluster_mean_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t* __restrict__ offsets,
+                                    const uint64_t* __restrict__ rows, float* __restrict__ means) {
+  const uint32_t c = blockIdx.x;
+  const uint64_t b = offsets[c], e = offsets[c + 1];
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  for (uint32_t col = threadIdx.x; col < ld4; col += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint64_t t = b;
+    for (; t + 4 <= e; t += 4) {   // independent loads first, then the ordered adds
+      const float4 v0 = __ldg(X4 + (size_t)rows[t] * ld4 + col);
+      const float4 v1 = __ldg(X4 + (size_t)rows[t + 1] * ld4 + col);
+      const float4 v2 = __ldg(X4 + (size_t)rows[t + 2] * ld4 + col);
+      const float4 v3 = __ldg(X4 + (size_t)rows[t + 3] * ld4 + col);
+      acc.x = __fadd_rn(acc.x, v0.x); acc.y = __fadd_rn(acc.y, v0.y); acc.z = __fadd_rn(acc.z, v0.z); acc.w = __fadd_rn(acc.w, v0.w);
+      acc.x = __fadd_rn(acc.x, v1.x); acc.y = __fadd_rn(acc.y, v1.y); acc.z = __fadd_rn(acc.z, v1.z); acc.w = __fadd_rn(acc.w, v1.w);
+      acc.x = __fadd_rn(acc.x, v2.x); acc.y = __fadd_rn(acc.y, v2.y); acc.z = __fadd_rn(acc.z, v2.z); acc.w = __fadd_rn(acc.w, v2.w);
+      acc.x = __fadd_rn(acc.x, v3.x); acc.y = __fadd_rn(acc.y, v3.y); acc.z = __fadd_rn(acc.z, v3.z); acc.w = __fadd_rn(acc.w, v3.w);
+    }
+    for (; t < e; ++t) {
+      const float4 v = __ldg(X4 + (size_t)rows[t] * ld4 + col);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    if (e > b) {
+      const float fm = (float)(e - b);
+      acc.x = __fdiv_rn(acc.x, fm); acc.y = __fdiv_rn(acc.y, fm);
+      acc.z = __fdiv_rn(acc.z, fm); acc.w = __fdiv_rn(acc.w, fm);
+    }
+    reinterpret_cast<float4*>(means)[(size_t)c * ld4 + col] = acc;
+  }
+}
+
+__global__ void expand_cluster_ids_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ cid) {
+  const uint32_t c = blockIdx.x;
+  for (uint64_t t = offsets[c] + threadIdx.x; t < offsets[c + 1]; t += blockDim.x) cid[t] = c;
+}
+
+// ---- medoid (hierarchical.rs:155-171): argmin over members of d(row, mean), strict <, leftmost
+// wins, identity (0, +inf).  key = dist bits << 32 | position inside the member list.
+template <int METRIC>
+__global__ void __launch_bounds__(PD_THREADS)
+medoid_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restrict__ rows,
+              const uint32_t* __restrict__ cid, const uint64_t* __restrict__ offsets,
+              const float* __restrict__ means, uint64_t total, unsigned long long* __restrict__ keys) {
+  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
+  for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < total; base += nwarps * 32) {
+    const uint64_t t = base + lane;
+    const bool valid = t < total;
+    const float* pa = nullptr;
+    const float* pb = nullptr;
+    uint32_t c = 0;
+    if (valid) {
+      c = cid[t];
+      pa = X + (size_t)rows[t] * ld;
+      pb = means + (size_t)c * ld;
+    }
+    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    if (valid && dv < __int_as_float(0x7f800000)) {
+      const unsigned long long key = ((unsigned long long)__float_as_uint(dv) << 32) | (uint32_t)(t - offsets[c]);
+      atomicMin(&keys[c], key);
+    }
+  }
+}
+
+__global__ void medoid_finalize_kernel(const unsigned long long* __restrict__ keys, const uint64_t* __restrict__ offsets,
+                                       const uint64_t* __restrict__ rows, const uint64_t* __restrict__ old_rows,
+                                       uint32_t k, uint64_t* __restrict__ out) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  const uint64_t b = offsets[c], e = offsets[c + 1];
+  if (e == b) out[c] = old_rows[c];                                   // :146-149
+  else if (keys[c] == ~0ull) out[c] = 0;                              // identity (0, +inf)
+  else out[c] = rows[b + (keys[c] & 0xffffffffull)];
+}
+
+// ---- farthest point (hierarchical.rs:112-126): argmax over members != c1, strict >, identity
+// (0, 0.0): only distances > 0 compete, the earliest maximum wins.
+template <int METRIC>
+__global__ void __launch_bounds__(PD_THREADS)
+farthest_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restrict__ members, uint64_t m,
+                uint64_t c1, unsigned long long* __restrict__ key) {
+  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
+  for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < m; base += nwarps * 32) {
+    const uint64_t t = base + lane;
+    const bool valid = t < m && members[t] != c1;
+    const float* pa = valid ? X + (size_t)c1 * ld : nullptr;
+    const float* pb = valid ? X + (size_t)members[t] * ld : nullptr;
+    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    if (valid && dv > 0.0f) {
+      const unsigned long long kk = ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (uint32_t)t);
+      atomicMax(key, kk);
+    }
+  }
+}
+
+// ---- k-means++ ----------------------------------------------------------------------------
+// mind[i] = min(mind[i], d(x_i, newest))  (hierarchical.rs:260-276 restated as a running min)
+template <int METRIC>
+__global__ void __launch_bounds__(PD_THREADS)
+kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, uint64_t newest, int first,
+                   float* __restrict__ mind) {
+  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
+  for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < n; base += nwarps * 32) {
+    const uint64_t i = base + lane;
+    const bool valid = i < n;
+    const float* pa = valid ? X + (size_t)i * ld : nullptr;
+    const float* pb = valid ? X + (size_t)newest * ld : nullptr;
+    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    if (valid && (first || dv < mind[i])) mind[i] = dv;
+  }
+}
+
+// :278 `distances.iter().fold(F::zero(), |acc, &x| acc + x)` — a strictly sequential f32 sum.
+// One thread walks the array; loads are issued 16 ahead so only the add chain is serial.
+__global__ void seq_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float acc = 0.0f;
+  uint64_t i = 0;
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  for (; i + 16 <= n; i += 16) {
+    const float4 a = v4[i / 4], b = v4[i / 4 + 1], c = v4[i / 4 + 2], d = v4[i / 4 + 3];
+    acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
+    acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
+    acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
+    acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
+  }
+  for (; i < n; ++i) acc = __fadd_rn(acc, v[i]);
+  out[0] = acc;
+}
+
+// Deterministic tree sum (fast mode: picks equal the reference's only up to near-ties).
+__global__ void tree_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+  __shared__ double sm[1024];
+  double acc = 0.0;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)sm[0];
+}
+
+__device__ __forceinline__ float kmpp_weight(float d, float denom) {
+  return __fdiv_rn(__fmul_rn(d, d), denom);             // :281 (d * d) / max(sum, 1e-10)
+}
+
+// f64 block sums of the weights (rand 0.9 WeightedIndex accumulates f64 weights) + validity.
+__global__ void __launch_bounds__(256)
+kmpp_block_sums_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
+                       double* __restrict__ block_sums, int* __restrict__ bad) {
+  __shared__ double sm[256];
+  const float denom = fmaxf(d_sum[0], 1e-10f);
+  const uint64_t b0 = (uint64_t)blockIdx.x * WBLOCK;
+  double acc = 0.0;
+  bool isbad = false;
+#pragma unroll
+  for (int e = 0; e < WBLOCK / 256; ++e) {            // thread owns 4 consecutive weights
+    const uint64_t i = b0 + (uint64_t)threadIdx.x * (WBLOCK / 256) + e;
+    if (i < n) {
+      const double w = (double)kmpp_weight(mind[i], denom);
+      if (!(w >= 0.0)) isbad = true;
+      acc += w;
+    }
+  }
+  sm[threadIdx.x] = acc;
+  if (isbad) *bad = 1;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = sm[0];
+}
+
+// cumulative_weights.partition_point(|w| w <= u) with u = u01 * total (rand 0.9 WeightedIndex).
+__global__ void kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
+                                 const double* __restrict__ block_sums, uint64_t nblocks,
+                                 const int* __restrict__ bad, double u01, uint64_t* __restrict__ res,
+                                 double* __restrict__ d_total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double total = 0.0;
+  for (uint64_t b = 0; b < nblocks; ++b) total += block_sums[b];
+  d_total[0] = total;
+  if (*bad || total == 0.0 || !isfinite(total)) { res[0] = 1; res[1] = 0; return; }
+  const double u = u01 * total;
+  const float denom = fmaxf(d_sum[0], 1e-10f);
+  double cum = 0.0;
+  uint64_t b = 0;
+  for (; b + 1 < nblocks; ++b) {
+    if (!(cum + block_sums[b] <= u)) break;
+    cum += block_sums[b];
+  }
+  uint64_t idx = n - 1;
+  const uint64_t lo = b * WBLOCK;
+  uint64_t hi = lo + WBLOCK;
+  if (hi > n) hi = n;
+  bool found = false;
+  for (uint64_t i = lo; i < hi && i + 1 < n; ++i) {
+    cum += (double)kmpp_weight(mind[i], denom);
+    if (!(cum <= u)) { idx = i; found = true; break; }
+  }
+  if (!found) {       // rounding pushed the crossing into a later block: continue sequentially
+    for (uint64_t i = hi; i + 1 < n; ++i) {
+      cum += (double)kmpp_weight(mind[i], denom);
+      if (!(cum <= u)) { idx = i; break; }
+    }
+  }
+  res[0] = 0;
+  res[1] = idx;
+}
+
+template <typename F>
+int dispatch_metric(int metric, F&& f) {
+  switch (metric) {
+    case SPF_METRIC_EUCLIDEAN: return f(std::integral_constant<int, SPF_METRIC_EUCLIDEAN>());
+    case SPF_METRIC_MANHATTAN: return f(std::integral_constant<int, SPF_METRIC_MANHATTAN>());
+    case SPF_METRIC_CHEBYSHEV: return f(std::integral_constant<int, SPF_METRIC_CHEBYSHEV>());
+  }
+  return fail(SPF_E_INVALID, "unknown metric %d", metric);
+}
+
+unsigned pd_grid(spf_ctx* c, uint64_t count) {
+  uint64_t blocks = ceil_div(count, PD_THREADS);
+  const uint64_t cap = (uint64_t)c->sm_count * 32;
+  return (unsigned)(blocks > cap ? cap : (blocks ? blocks : 1));
+}
+
+// shared tail of the two spf_update_medoids entry points; d_offsets/d_rows are device arrays
+int update_medoids_dev(spf_dataset* ds, int metric, const uint64_t* d_offsets, const uint64_t* d_rows,
+                       uint64_t total, uint32_t k, const uint64_t* old_rows, uint64_t* new_rows,
+                       float* means_out) {
+  spf_ctx* c = ds->ctx;
+  cudaStream_t st = c->stream;
+  const uint32_t ld = ds->ld;
+  DevBuf<float> means;
+  DevBuf<uint32_t> cid;
+  DevBuf<unsigned long long> keys;
+  DevBuf<uint64_t> d_old, d_new;
+  SPF_TRY(means.alloc(st, (size_t)k * ld));
+  SPF_TRY(cid.alloc(st, total));
+  SPF_TRY(keys.alloc(st, k));
+  SPF_TRY(d_old.alloc(st, k));
+  SPF_TRY(d_new.alloc(st, k));
+  SPF_CUDA(cudaMemcpyAsync(d_old.p, old_rows, (size_t)k * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)k * sizeof(unsigned long long), st));
+  {
+    KernelTimer t(c, "cluster_mean");
+    unsigned threads = round_up(ld / 4, 32);
+    if (threads > 1024) threads = 1024;
+    cluster_mean_kernel<<<k, threads, 0, st>>>(ds->x, ld / 4, d_offsets, d_rows, means.p);
+    SPF_TRY(check_launch(c, "cluster_mean_kernel"));
+  }
+  expand_cluster_ids_kernel<<<k, 256, 0, st>>>(d_offsets, cid.p);
+  SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
+  if (total) {
+    KernelTimer t(c, "medoid");
+    SPF_TRY(dispatch_metric(metric, [&](auto M) {
+      medoid_kernel<decltype(M)::value><<<pd_grid(c, total), PD_THREADS, 0, st>>>(
+          ds->x, ld, d_rows, cid.p, d_offsets, means.p, total, keys.p);
+      return check_launch(c, "medoid_kernel");
+    }));
+  }
+  medoid_finalize_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys.p, d_offsets, d_rows, d_old.p, k, d_new.p);
+  SPF_TRY(check_launch(c, "medoid_finalize_kernel"));
+  SPF_CUDA(cudaMemcpyAsync(new_rows, d_new.p, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (means_out)
+    SPF_CUDA(cudaMemcpy2DAsync(means_out, (size_t)ds->d * sizeof(float), means.p, (size_t)ld * sizeof(float),
+                               (size_t)ds->d * sizeof(float), k, cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
+}
+
+}  // namespace
+}  // namespace spf
+
+extern "C" {
+
+int spf_update_medoids(spf_dataset* ds, int metric, const uint64_t* offsets, const uint64_t* members,
+                       uint32_t k, const uint64_t* old_rows, uint64_t* new_rows, float* means_out) {
+  if (!ds || !offsets || !old_rows || !new_rows) return fail(SPF_E_INVALID, "spf_update_medoids: NULL argument");
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  if (k == 0) return SPF_OK;
+  const uint64_t total = offsets[k];
+  if (total && !members) return fail(SPF_E_INVALID, "members is NULL");
+  for (uint32_t j = 0; j < k; ++j)
+    if (offsets[j] > offsets[j + 1]) return fail(SPF_E_INVALID, "offsets must be non-decreasing");
+  for (uint64_t t = 0; t < total; ++t)
+    if (members[t] >= ds->n) return fail(SPF_E_INVALID, "member row %llu >= n", (unsigned long long)members[t]);
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  DevBuf<uint64_t> d_off, d_rows;
+  SPF_TRY(d_off.alloc(st, (size_t)k + 1));
+  SPF_TRY(d_rows.alloc(st, total));
+  SPF_CUDA(cudaMemcpyAsync(d_off.p, offsets, ((size_t)k + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  if (total) SPF_CUDA(cudaMemcpyAsync(d_rows.p, members, total * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  return update_medoids_dev(ds, metric, d_off.p, d_rows.p, total, k, old_rows, new_rows, means_out);
+}
+
+int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result* r,
+                            const uint64_t* old_rows, uint64_t* new_rows, float* means_out) {
+  if (!ds || !r || !old_rows || !new_rows) return fail(SPF_E_INVALID, "spf_update_medoids_from: NULL argument");
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  if (!r->has_csr) return fail(SPF_E_STATE, "the assign result has no CSR (SPF_ASSIGN_NO_CSR)");
+  if (r->ctx != ds->ctx) return fail(SPF_E_INVALID, "result and dataset belong to different contexts");
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  DevBuf<uint64_t> d_rows;
+  SPF_TRY(d_rows.alloc(c->stream, r->total));
+  SPF_TRY(assign_members_as_rows(r, d_rows.p));
+  return update_medoids_dev(ds, metric, r->offsets, d_rows.p, r->total, r->k, old_rows, new_rows, means_out);
+}
+
+int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* members, uint64_t m,
+                 uint64_t* out_row) {
+  if (!ds || !out_row || (m && !members)) return fail(SPF_E_INVALID, "spf_farthest: NULL argument");
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  if (c1_row >= ds->n) return fail(SPF_E_INVALID, "c1_row >= n");
+  if (m >= (1ull << 32)) return fail(SPF_E_INVALID, "m must be < 2^32");
+  for (uint64_t t = 0; t < m; ++t)
+    if (members[t] >= ds->n) return fail(SPF_E_INVALID, "member row %llu >= n", (unsigned long long)members[t]);
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (m == 0) { *out_row = 0; return SPF_OK; }
+  DevBuf<uint64_t> d_mem;
+  DevBuf<unsigned long long> d_key;
+  SPF_TRY(d_mem.alloc(st, m));
+  SPF_TRY(d_key.alloc(st, 1));
+  SPF_CUDA(cudaMemcpyAsync(d_mem.p, members, m * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemsetAsync(d_key.p, 0, sizeof(unsigned long long), st));
+  {
+    KernelTimer t(c, "farthest");
+    SPF_TRY(dispatch_metric(metric, [&](auto M) {
+      farthest_kernel<decltype(M)::value><<<pd_grid(c, m), PD_THREADS, 0, st>>>(ds->x, ds->ld, d_mem.p, m, c1_row, d_key.p);
+      return check_launch(c, "farthest_kernel");
+    }));
+  }
+  unsigned long long key = 0;
+  SPF_CUDA(cudaMemcpyAsync(&key, d_key.p, sizeof(key), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  *out_row = key == 0 ? 0 : members[0xffffffffu - (uint32_t)(key & 0xffffffffull)];
+  return SPF_OK;
+}
+
+int spf_distance_pairs(spf_ctx* c, int metric, const float* a, const float* b, uint32_t d, uint64_t pairs,
+                       float* out) {
+  if (!c || !a || !b || !out) return fail(SPF_E_INVALID, "spf_distance_pairs: NULL argument");
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  // ndarray-stats returns Err(EmptyInput) for d == 0 and the reference unwraps it (panic)
+  if (d == 0) return fail(SPF_E_INVALID, "empty vectors (the reference panics on them)");
+  if (pairs == 0) return SPF_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint32_t ld = round_up(d, 4);
+  DevBuf<float> da, db, dout;
+  SPF_TRY(da.alloc(st, (size_t)pairs * ld));
+  SPF_TRY(db.alloc(st, (size_t)pairs * ld));
+  SPF_TRY(dout.alloc(st, pairs));
+  if (ld != d) {
+    SPF_CUDA(cudaMemsetAsync(da.p, 0, (size_t)pairs * ld * sizeof(float), st));
+    SPF_CUDA(cudaMemsetAsync(db.p, 0, (size_t)pairs * ld * sizeof(float), st));
+  }
+  SPF_CUDA(cudaMemcpy2DAsync(da.p, (size_t)ld * 4, a, (size_t)d * 4, (size_t)d * 4, pairs, cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemcpy2DAsync(db.p, (size_t)ld * 4, b, (size_t)d * 4, (size_t)d * 4, pairs, cudaMemcpyHostToDevice, st));
+  SPF_TRY(launch_pair_dist(c, metric, da.p, ld, nullptr, db.p, ld, nullptr, UINT64_MAX, ld, pairs, dout.p));
+  SPF_CUDA(cudaMemcpyAsync(out, dout.p, pairs * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
+}
+
+// ---- k-means++ session ----------------------------------------------------------------------
+int spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** out) {
+  if (!ds || !out) return fail(SPF_E_INVALID, "spf_kmpp_begin: NULL argument");
+  *out = nullptr;
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  if (first_row >= ds->n) return fail(SPF_E_INVALID, "first_row >= n");
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  spf_kmpp* s = new (std::nothrow) spf_kmpp();
+  if (!s) return fail(SPF_E_OOM, "out of host memory");
+  s->ds = ds;
+  s->metric = metric;
+  s->newest = first_row;
+  s->nblocks = ceil_div(ds->n, WBLOCK);
+  cudaError_t e = cudaMalloc((void**)&s->mind, ds->n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->block_sums, s->nblocks * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->bad, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->res, 2 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_sum, sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_total, sizeof(double));
+  if (e != cudaSuccess) {
+    spf_kmpp_free(s);
+    return fail(SPF_E_OOM, "k-means++ session allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return SPF_OK;
+}
+
+int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
+  if (!s || !chosen) return fail(SPF_E_INVALID, "spf_kmpp_round: NULL argument");
+  if (!(u01 >= 0.0 && u01 < 1.0)) return fail(SPF_E_INVALID, "u01 must be in [0,1)");
+  if (!s->pending) return fail(SPF_E_STATE, "previous round needs spf_kmpp_push() before the next one");
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint64_t n = ds->n;
+  {
+    KernelTimer t(c, "kmpp_update");
+    const int first = s->rounds == 0 ? 1 : 0;
+    SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
+      kmpp_update_kernel<decltype(M)::value><<<pd_grid(c, n), PD_THREADS, 0, st>>>(ds->x, ds->ld, n, s->newest, first, s->mind);
+      return check_launch(c, "kmpp_update_kernel");
+    }));
+  }
+  s->rounds += 1;
+  s->pending = false;
+  {
+    KernelTimer t(c, "kmpp_sum");
+    if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum);
+    else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
+    SPF_TRY(check_launch(c, "kmpp sum kernel"));
+  }
+  {
+    KernelTimer t(c, "kmpp_pick");
+    SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
+    kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->bad);
+    SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
+    kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, u01, s->res, s->d_total);
+    SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
+  }
+  uint64_t res[2] = {0, 0};
+  SPF_CUDA(cudaMemcpyAsync(res, s->res, sizeof(res), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(&s->last_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(&s->last_total, s->d_total, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  if (res[0] != 0) return 1;   // weighted pick impossible → host draws uniformly and pushes
+  s->newest = res[1];
+  s->pending = true;
+  *chosen = res[1];
+  return SPF_OK;
+}
+
+int spf_kmpp_push(spf_kmpp* s, uint64_t row) {
+  if (!s) return fail(SPF_E_INVALID, "session is NULL");
+  if (s->pending) return fail(SPF_E_STATE, "a centroid is already pending");
+  if (row >= s->ds->n) return fail(SPF_E_INVALID, "row >= n");
+  s->newest = row;
+  s->pending = true;
+  return SPF_OK;
+}
+
+int spf_kmpp_last_sums(const spf_kmpp* s, float* sum, double* total) {
+  if (!s) return fail(SPF_E_INVALID, "session is NULL");
+  if (sum) *sum = s->last_sum;
+  if (total) *total = s->last_total;
+  return SPF_OK;
+}
+
+void spf_kmpp_free(spf_kmpp* s) {
+  if (!s) return;
+  cudaSetDevice(s->ds->ctx->device);
+  cudaStreamSynchronize(s->ds->ctx->stream);
+  if (s->mind) cudaFree(s->mind);
+  if (s->block_sums) cudaFree(s->block_sums);
+  if (s->bad) cudaFree(s->bad);
+  if (s->res) cudaFree(s->res);
+  if (s->d_sum) cudaFree(s->d_sum);
+  if (s->d_total) cudaFree(s->d_total);
+  delete s;
+}
+
+}  // extern "C"

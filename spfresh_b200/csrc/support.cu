@@ -1,0 +1,156 @@
+// support.cu — small streaming kernels shared by the assign / update / k-means++ / query paths.
+#include "kernels.cuh"
+#include "pairdist.cuh"
+
+namespace spf {
+
+namespace {
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, uint32_t ld4, const uint64_t* __restrict__ idx,
+                                   uint64_t m, float* __restrict__ dst) {
+  // one float4 per thread; a row is ld4 float4s
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = m * ld4;
+  if (t >= total) return;
+  const uint64_t r = t / ld4;
+  const uint32_t c = (uint32_t)(t - r * ld4);
+  const float4* s = reinterpret_cast<const float4*>(src) + (size_t)idx[r] * ld4 + c;
+  reinterpret_cast<float4*>(dst)[t] = __ldg(s);
+}
+
+__global__ void row_sqnorm_kernel(const float* __restrict__ rows, uint32_t ld4, uint64_t m, float* __restrict__ out) {
+  // one warp per row: lanes stride over float4s, shuffle reduce (the norm only feeds the
+  // tensor-path error bound and approximate distances; its summation order is free).
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= m) return;
+  const float4* r = reinterpret_cast<const float4*>(rows) + (size_t)w * ld4;
+  float acc = 0.f;
+  for (uint32_t c = lane; c < ld4; c += 32) {
+    const float4 v = __ldg(r + c);
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[w] = acc;
+}
+
+__global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+__global__ void fill_u64_kernel(uint64_t* p, uint64_t n, uint64_t v) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+
+__global__ void max_f32_kernel(const float* __restrict__ p, uint64_t n, float* out) {
+  // single block; values are >= 0 (squared norms)
+  __shared__ float sm[32];
+  float v = 0.f;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) v = fmaxf(v, p[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+__global__ void check_rows_kernel(const uint64_t* __restrict__ idx, uint64_t m, uint64_t n, int* flag) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m && idx[t] >= n) *flag = 1;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(PD_THREADS)
+pair_dist_kernel(const float* __restrict__ A, uint32_t ldA, const uint64_t* __restrict__ idxA,
+                 const float* __restrict__ B, uint32_t ldB, const uint32_t* __restrict__ idxB32,
+                 uint64_t fixedB, uint32_t ld, uint64_t count, float* __restrict__ out) {
+  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
+  for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < count;
+       base += nwarps * 32) {
+    const uint64_t i = base + lane;
+    const bool valid = i < count;
+    const float* pa = nullptr;
+    const float* pb = nullptr;
+    if (valid) {
+      pa = A + (size_t)(idxA ? idxA[i] : i) * ldA;
+      pb = B + (size_t)(idxB32 ? (uint64_t)idxB32[i] : (fixedB == UINT64_MAX ? i : fixedB)) * ldB;
+    }
+    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    if (valid) out[i] = dv;
+  }
+}
+
+}  // namespace
+
+int launch_gather_rows(spf_ctx* c, const float* src, uint32_t ld, const uint64_t* d_idx, uint64_t m,
+                       float* dst) {
+  if (m == 0) return SPF_OK;
+  const uint32_t ld4 = ld / 4;
+  const uint64_t total = m * ld4;
+  gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, c->stream>>>(src, ld4, d_idx, m, dst);
+  return check_launch(c, "gather_rows_kernel");
+}
+
+int launch_row_sqnorm(spf_ctx* c, const float* rows, uint32_t ld, uint64_t m, float* out) {
+  if (m == 0) return SPF_OK;
+  row_sqnorm_kernel<<<(unsigned)ceil_div(m * 32, 256), 256, 0, c->stream>>>(rows, ld / 4, m, out);
+  return check_launch(c, "row_sqnorm_kernel");
+}
+
+int launch_fill_f32(spf_ctx* c, float* p, uint64_t n, float v) {
+  if (n == 0) return SPF_OK;
+  fill_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(p, n, v);
+  return check_launch(c, "fill_f32_kernel");
+}
+
+int launch_fill_u64(spf_ctx* c, uint64_t* p, uint64_t n, uint64_t v) {
+  if (n == 0) return SPF_OK;
+  fill_u64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(p, n, v);
+  return check_launch(c, "fill_u64_kernel");
+}
+
+int launch_max_f32(spf_ctx* c, const float* p, uint64_t n, float* out1) {
+  max_f32_kernel<<<1, 1024, 0, c->stream>>>(p, n, out1);
+  return check_launch(c, "max_f32_kernel");
+}
+
+int launch_check_rows(spf_ctx* c, const uint64_t* d_idx, uint64_t m, uint64_t n, int* d_flag) {
+  if (m == 0) return SPF_OK;
+  check_rows_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, c->stream>>>(d_idx, m, n, d_flag);
+  return check_launch(c, "check_rows_kernel");
+}
+
+int launch_pair_dist(spf_ctx* c, int metric, const float* A, uint32_t ldA, const uint64_t* idxA,
+                     const float* B, uint32_t ldB, const uint32_t* idxB32, uint64_t fixedB,
+                     uint32_t ld, uint64_t count, float* out) {
+  if (count == 0) return SPF_OK;
+  uint64_t blocks = ceil_div(count, PD_THREADS);   // 32 pairs per warp, 4 warps per block
+  if (blocks > (uint64_t)c->sm_count * 32) blocks = (uint64_t)c->sm_count * 32;
+  dim3 grid((unsigned)blocks), block(PD_THREADS);
+  switch (metric) {
+    case SPF_METRIC_EUCLIDEAN:
+      pair_dist_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(A, ldA, idxA, B, ldB, idxB32, fixedB, ld, count, out);
+      break;
+    case SPF_METRIC_MANHATTAN:
+      pair_dist_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(A, ldA, idxA, B, ldB, idxB32, fixedB, ld, count, out);
+      break;
+    case SPF_METRIC_CHEBYSHEV:
+      pair_dist_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(A, ldA, idxA, B, ldB, idxB32, fixedB, ld, count, out);
+      break;
+    default:
+      return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  }
+  return check_launch(c, "pair_dist_kernel");
+}
+
+}  // namespace spf

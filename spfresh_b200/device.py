@@ -1,0 +1,306 @@
+"""Object wrappers over the C ABI handles (context, dataset, assignment result, index)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import as_f32, as_u64, check, lib, ptr
+
+
+class Context:
+    """spf_ctx: one B200 + its stream.  `Context.default()` is a per-process singleton."""
+    _default = None
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        check(lib().spf_ctx_create(device, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def default(cls) -> "Context":
+        if cls._default is None:
+            cls._default = Context(0)
+        return cls._default
+
+    def close(self):
+        if self._h:
+            lib().spf_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return int(lib().spf_ctx_stream(self._h) or 0)
+
+    def synchronize(self):
+        check(lib().spf_ctx_synchronize(self._h))
+
+    def set_profiling(self, on: bool):
+        check(lib().spf_ctx_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_ms(self, name: str) -> float:
+        return float(lib().spf_ctx_kernel_ms(self._h, name.encode()))
+
+    def launch_count(self) -> int:
+        return int(lib().spf_ctx_launch_count(self._h))
+
+    def set_param(self, name: str, value: int):
+        check(lib().spf_ctx_set_param(self._h, name.encode(), int(value)))
+
+    def distance_pairs(self, metric: int, a, b) -> np.ndarray:
+        """Batched DistanceMetric::compute (distance.rs:7-43)."""
+        a, b = as_f32(a), as_f32(b)
+        if a.shape != b.shape:
+            raise ValueError("shape mismatch")   # the reference panics (ShapeMismatch.unwrap())
+        a2, b2 = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+        out = np.empty(a2.shape[0], np.float32)
+        check(lib().spf_distance_pairs(self._h, metric, ptr(a2), ptr(b2), a2.shape[1], a2.shape[0], ptr(out)))
+        return out
+
+
+class Dataset:
+    """spf_dataset: n x d f32 rows resident in HBM."""
+
+    def __init__(self, ctx: Context, rows=None, *, device_ptr: int | None = None, n: int = 0, d: int = 0):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if device_ptr is not None:
+            check(lib().spf_dataset_from_device(ctx.handle, C.c_void_p(device_ptr), n, d, C.byref(h)))
+            self.n, self.d = n, d
+        else:
+            rows = np.asarray(rows)
+            if rows.ndim != 2:
+                raise ValueError("rows must be 2-D")
+            if rows.dtype != np.float32 or rows.strides[1] != 4 or rows.strides[0] % 4 != 0 or rows.strides[0] < 4 * rows.shape[1]:
+                rows = np.ascontiguousarray(rows, dtype=np.float32)
+            self.n, self.d = rows.shape
+            check(lib().spf_dataset_upload(ctx.handle, ptr(rows), self.n, self.d, rows.strides[0] // 4, C.byref(h)))
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def free(self):
+        if self._h:
+            lib().spf_dataset_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ---- hot-path calls -------------------------------------------------------------------
+    def assign(self, metric: int, centroid_rows, point_idx=None, boundary_factor: float = 1.1,
+               flags: int = capi.ASSIGN_DEFAULT) -> "AssignResult":
+        cr = as_u64(centroid_rows)
+        if point_idx is None:
+            pi, m = None, self.n
+        else:
+            pi = as_u64(point_idx)
+            m = pi.size
+        h = C.c_void_p()
+        check(lib().spf_assign(self._h, metric, ptr(pi), m, ptr(cr), cr.size, boundary_factor, flags, C.byref(h)))
+        return AssignResult(self, h)
+
+    def update_medoids(self, metric: int, offsets, members, old_rows, want_means: bool = False):
+        offsets, members, old_rows = as_u64(offsets), as_u64(members), as_u64(old_rows)
+        k = old_rows.size
+        new_rows = np.zeros(k, np.uint64)
+        means = np.zeros((k, self.d), np.float32) if want_means else None
+        check(lib().spf_update_medoids(self._h, metric, ptr(offsets), ptr(members), k, ptr(old_rows),
+                                       ptr(new_rows), ptr(means)))
+        return (new_rows, means) if want_means else new_rows
+
+    def update_medoids_from(self, metric: int, result: "AssignResult", old_rows, want_means: bool = False):
+        old_rows = as_u64(old_rows)
+        k = old_rows.size
+        new_rows = np.zeros(k, np.uint64)
+        means = np.zeros((k, self.d), np.float32) if want_means else None
+        check(lib().spf_update_medoids_from(self._h, metric, result.handle, ptr(old_rows), ptr(new_rows), ptr(means)))
+        return (new_rows, means) if want_means else new_rows
+
+    def farthest(self, metric: int, c1_row: int, members) -> int:
+        members = as_u64(members)
+        out = C.c_uint64()
+        check(lib().spf_farthest(self._h, metric, int(c1_row), ptr(members), members.size, C.byref(out)))
+        return int(out.value)
+
+    def kmeanspp(self, metric: int, first_row: int) -> "KmppSession":
+        return KmppSession(self, metric, first_row)
+
+
+class AssignResult:
+    """spf_assign_result (device resident until fetched)."""
+
+    def __init__(self, ds: Dataset, h):
+        self.ds, self._h = ds, h
+        self.m = int(lib().spf_assign_points(h))
+        self.k = int(lib().spf_assign_clusters(h))
+        self.total = int(lib().spf_assign_total(h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def fetch(self, best=True, dmin=True, csr=True):
+        b = np.empty(self.m, np.uint32) if best else None
+        dm = np.empty(self.m, np.float32) if dmin else None
+        off = np.empty(self.k + 1, np.uint64) if csr else None
+        mem = np.empty(self.total, np.uint64) if csr else None
+        check(lib().spf_assign_fetch(self._h, ptr(b), ptr(dm), ptr(off), ptr(mem)))
+        return Fetched(off, mem, b, dm)
+
+    def free(self):
+        if self._h:
+            lib().spf_assign_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class Fetched:
+    offsets: np.ndarray | None
+    members: np.ndarray | None
+    best: np.ndarray | None
+    dmin: np.ndarray | None
+
+    def lists(self):
+        return [self.members[int(self.offsets[j]):int(self.offsets[j + 1])] for j in range(len(self.offsets) - 1)]
+
+
+class KmppSession:
+    """spf_kmpp: device state of initialize_clusters_kmeans_plus_plus (hierarchical.rs:249-293)."""
+
+    def __init__(self, ds: Dataset, metric: int, first_row: int):
+        self.ds = ds
+        h = C.c_void_p()
+        check(lib().spf_kmpp_begin(ds.handle, metric, int(first_row), C.byref(h)))
+        self._h = h
+
+    def round(self, u01: float):
+        """Returns the chosen row, or None when the weighted pick is impossible (caller then
+        draws uniformly and calls push)."""
+        out = C.c_uint64()
+        rc = check(lib().spf_kmpp_round(self._h, float(u01), C.byref(out)))
+        return None if rc == 1 else int(out.value)
+
+    def push(self, row: int):
+        check(lib().spf_kmpp_push(self._h, int(row)))
+
+    def last_sums(self):
+        s, t = C.c_float(), C.c_double()
+        check(lib().spf_kmpp_last_sums(self._h, C.byref(s), C.byref(t)))
+        return float(s.value), float(t.value)
+
+    def free(self):
+        if self._h:
+            lib().spf_kmpp_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceIndex:
+    """spf_index: posting lists + centroids resident in HBM."""
+
+    def __init__(self, ctx: Context, h, d: int):
+        self.ctx, self._h, self.d = ctx, h, d
+
+    @classmethod
+    def pack(cls, ds: Dataset, offsets, members, centroid_rows, list_range=None) -> "DeviceIndex":
+        offsets, members, cr = as_u64(offsets), as_u64(members), as_u64(centroid_rows)
+        lb, le = list_range if list_range is not None else (0, cr.size)
+        h = C.c_void_p()
+        check(lib().spf_index_pack(ds.handle, ptr(offsets), ptr(members), ptr(cr), cr.size, lb, le, C.byref(h)))
+        return cls(ds.ctx, h, ds.d)
+
+    @classmethod
+    def load_dir(cls, ctx: Context, directory: str, centroids) -> "DeviceIndex":
+        cen = as_f32(centroids)
+        h = C.c_void_p()
+        check(lib().spf_index_load_dir(ctx.handle, directory.encode(), ptr(cen), cen.shape[0], cen.shape[1], C.byref(h)))
+        return cls(ctx, h, cen.shape[1])
+
+    def save_dir(self, directory: str):
+        check(lib().spf_index_save_dir(self._h, directory.encode()))
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def nlists(self) -> int:
+        return int(lib().spf_index_lists(self._h))
+
+    @property
+    def nvectors(self) -> int:
+        return int(lib().spf_index_vectors(self._h))
+
+    def last_scan_bytes(self) -> int:
+        return int(lib().spf_index_last_scan_bytes(self._h))
+
+    def search(self, queries, k: int, nprobe: int = 0, prune_factor: float = 1.2, want_vectors=False,
+               want_keys=False):
+        q = as_f32(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.uint64)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        vec = np.empty((nq, k, self.d), np.float32) if want_vectors else None
+        keys = np.empty((nq, k), np.uint64) if want_keys else None
+        check(lib().spf_search_batch(self._h, ptr(q), nq, k, nprobe, prune_factor, ptr(ids), ptr(dists),
+                                     ptr(counts), ptr(vec), ptr(keys)))
+        out = [ids, dists, counts]
+        if want_vectors:
+            out.append(vec)
+        if want_keys:
+            out.append(keys)
+        return tuple(out)
+
+    def free(self):
+        if self._h:
+            lib().spf_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def topk_merge(keys, ids, dists, counts):
+    """Host merge of per-rank partial results: arrays are (parts, nq, k) / (parts, nq)."""
+    keys, ids = as_u64(keys), as_u64(ids)
+    dists = as_f32(dists)
+    counts = np.ascontiguousarray(counts, np.uint32)
+    parts, nq, k = keys.shape
+    o_ids = np.empty((nq, k), np.uint64)
+    o_d = np.empty((nq, k), np.float32)
+    o_c = np.empty(nq, np.uint32)
+    check(lib().spf_topk_merge(parts, nq, k, ptr(keys), ptr(ids), ptr(dists), ptr(counts), ptr(o_ids), ptr(o_d), ptr(o_c)))
+    return o_ids, o_d, o_c

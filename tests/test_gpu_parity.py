@@ -1,0 +1,425 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Integer / index outputs and all distances must be BIT-EXACT (the
+north-star tolerance is 1e-5 relative; the design delivers identity, so that is what is tested).
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+METRICS = [0, 1, 2]
+
+
+@pytest.fixture(scope="module")
+def spf():
+    import spfresh_b200 as s
+    from spfresh_b200 import build as b
+    b.build()
+    if s._capi.lib().spf_device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests need a B200 (there is no CPU fallback)")
+    return s
+
+
+@pytest.fixture(scope="module")
+def ctx(spf):
+    return spf.Context.default()
+
+
+def gauss(n, d, seed):
+    return np.random.Generator(np.random.Philox(key=seed)).standard_normal((n, d), dtype=np.float32)
+
+
+def clustered(n, d, ncent, seed):
+    g = np.random.Generator(np.random.Philox(key=seed))
+    cen = 2.0 * g.standard_normal((ncent, d), dtype=np.float32)
+    lab = g.integers(0, ncent, n)
+    return (cen[lab] + 0.5 * g.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+
+
+def check_assign(got, ref):
+    assert np.array_equal(got.offsets, ref.offsets)
+    assert np.array_equal(got.members, ref.members)
+    assert np.array_equal(got.best, ref.best)
+    assert np.array_equal(got.dmin.view(np.uint32), ref.dmin.view(np.uint32))
+
+
+# ----------------------------------------------------------------------------------------------
+# distances (distance.rs KATs) through the device
+# ----------------------------------------------------------------------------------------------
+def test_distance_kats_on_device(spf, ctx, kats, oracle):
+    name = {"Euclidean": 0, "Manhattan": 1, "Chebyshev": 2}
+    for kat in kats["distance"]:
+        got = ctx.distance_pairs(name[kat["metric"]], [kat["a"]], [kat["b"]])[0]
+        assert abs(float(got) - kat["expected"]) < kat["tol"], kat["cite"]
+    rng = np.random.default_rng(1)
+    for d in (1, 3, 31, 32, 33, 100, 128, 960):
+        a = rng.standard_normal((257, d)).astype(np.float32)
+        b = rng.standard_normal((257, d)).astype(np.float32)
+        for m in METRICS:
+            got = ctx.distance_pairs(m, a, b)
+            ref = np.array([oracle.distance(m, a[i], b[i]) for i in range(257)], np.float32)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (m, d)
+    with pytest.raises(ValueError):           # the reference panics on a shape mismatch
+        spf.SquaredEuclideanDistance().compute([1.0, 2.0], [1.0, 2.0, 3.0])
+
+
+# ----------------------------------------------------------------------------------------------
+# assignment — exact CUDA-core kernel (all metrics)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,d,k", [(6, 2, 2), (500, 7, 9), (3000, 33, 70), (4097, 128, 300)])
+def test_assign_exact_matches_oracle(spf, ctx, oracle, metric, n, d, k):
+    data = gauss(n, d, 10 + n)
+    data[n // 2] = data[1]                       # duplicate rows → exact ties
+    rng = np.random.default_rng(n + k)
+    cent = rng.choice(n, k, replace=False)
+    if k > 5:
+        cent[3], cent[4] = 1, n // 2             # identical centroids: lowest slot must win
+    ds = spf.Dataset(ctx, data)
+    got = ds.assign(metric, cent, flags=spf.ASSIGN_FORCE_EXACT).fetch()
+    check_assign(got, oracle.assign(data, metric, cent))
+
+
+def test_assign_toy_kat_all_inits(spf, ctx, kats):
+    """hierarchical.rs:466-486 on the device, for every ordered pair of distinct centroids."""
+    data = np.array(kats["toy_data"]["rows"], np.float32)
+    ds = spf.Dataset(ctx, data)
+    for c in itertools.permutations(range(6), 2):
+        r = ds.assign(0, c).fetch()
+        sizes = np.diff(r.offsets.astype(np.int64))
+        assert sizes.sum() == 6 and (sizes > 0).all()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_assign_subset_and_order(spf, ctx, oracle, metric):
+    data = clustered(5000, 24, 40, 3)
+    rng = np.random.default_rng(5)
+    sub = rng.permutation(5000)[:1777]           # arbitrary order must be preserved in the lists
+    cent = rng.choice(5000, 2, replace=False)    # the bisect shape (k = 2)
+    ds = spf.Dataset(ctx, data)
+    got = ds.assign(metric, cent, point_idx=sub).fetch()
+    check_assign(got, oracle.assign(data, metric, cent, point_idx=sub))
+
+
+def test_assign_candidate_overflow_path(spf, oracle):
+    """More candidates than slots → the brute-force rows must give the same answer."""
+    c2 = spf.Context(0)
+    try:
+        c2.set_param("cand_cap", 4)
+        data = gauss(2000, 16, 77)
+        cent = np.random.default_rng(2).choice(2000, 200, replace=False)
+        ds = spf.Dataset(c2, data)
+        for flags in (spf.ASSIGN_FORCE_EXACT, spf.ASSIGN_DEFAULT):
+            got = ds.assign(0, cent, boundary_factor=1.6, flags=flags).fetch()
+            check_assign(got, oracle.assign(data, 0, cent, boundary_factor=1.6))
+        ds.free()
+    finally:
+        c2.close()
+
+
+def test_assign_degenerate_inputs(spf, ctx, oracle):
+    # all points identical: every distance 0, thr 0, best = slot 0, nothing replicated
+    same = np.ones((300, 8), np.float32)
+    ds = spf.Dataset(ctx, same)
+    check_assign(ds.assign(0, [5, 9, 200]).fetch(), oracle.assign(same, 0, [5, 9, 200]))
+    # k == 1
+    data = gauss(100, 5, 1)
+    ds = spf.Dataset(ctx, data)
+    check_assign(ds.assign(1, [7]).fetch(), oracle.assign(data, 1, [7]))
+    # argument errors surface as status codes, not crashes
+    with pytest.raises(spf.SpfError):
+        ds.assign(0, [100])                      # centroid row out of range
+    with pytest.raises(spf.SpfError):
+        ds.assign(0, [])                         # k == 0
+    with pytest.raises(spf.SpfError):
+        ds.assign(0, [1], point_idx=[5, 1000])   # point row out of range
+
+
+# ----------------------------------------------------------------------------------------------
+# assignment — tcgen05 TF32 candidate GEMM + exact resolve (Euclidean)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,k,kind", [
+    (4096, 128, 256, "gauss"), (5000, 128, 300, "gauss"), (20000, 96, 1000, "clustered"),
+    (3000, 64, 513, "gauss"), (2500, 100, 64, "clustered"), (30000, 128, 4096, "clustered"),
+])
+def test_assign_tensor_path_matches_oracle(spf, ctx, oracle, n, d, k, kind):
+    data = gauss(n, d, n + d) if kind == "gauss" else clustered(n, d, max(k // 4, 2), n + d)
+    data[17] = data[3]
+    cent = np.random.default_rng(k).choice(n, k, replace=False)
+    cent[0], cent[1] = 3, 17                     # identical centroids
+    ds = spf.Dataset(ctx, data)
+    ctx.set_profiling(True)
+    got = ds.assign(0, cent).fetch()
+    assert ctx.kernel_ms("assign_tc") > 0, "the tcgen05 path did not run"
+    ctx.set_profiling(False)
+    check_assign(got, oracle.assign(data, 0, cent))
+
+
+def test_assign_tensor_path_large_norms(spf, ctx, oracle):
+    """SIFT-like data: all-positive, norms >> distances — the worst case for the TF32 slack."""
+    g = np.random.Generator(np.random.Philox(key=9))
+    data = np.floor(g.random((8000, 128), dtype=np.float32) * 128).astype(np.float32)
+    cent = np.random.default_rng(1).choice(8000, 512, replace=False)
+    ds = spf.Dataset(ctx, data)
+    check_assign(ds.assign(0, cent).fetch(), oracle.assign(data, 0, cent))
+
+
+def test_assign_tensor_equals_exact_at_scale(spf, ctx):
+    """Size-independent property at a size the oracle is too slow for: the tensor path and the
+    exact CUDA-core path (itself oracle-checked above) agree bit for bit."""
+    data = gauss(200_000, 128, 42)
+    cent = np.random.Generator(np.random.Philox(key=7)).choice(200_000, 2048, replace=False)
+    ds = spf.Dataset(ctx, data)
+    a = ds.assign(0, cent).fetch()
+    b = ds.assign(0, cent, flags=spf.ASSIGN_FORCE_EXACT).fetch()
+    check_assign(a, b)
+    sizes = np.diff(a.offsets.astype(np.int64))
+    assert sizes.sum() == a.members.size and sizes.sum() >= 200_000
+    for j in (0, 1, 1000, 2047):                 # members stay in input order inside a cluster
+        seg = a.members[int(a.offsets[j]):int(a.offsets[j + 1])]
+        assert np.all(np.diff(seg.astype(np.int64)) > 0)
+    nearest = np.bincount(a.best, minlength=2048)
+    assert nearest.sum() == 200_000
+
+
+# ----------------------------------------------------------------------------------------------
+# update_centroids / farthest / k-means++
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", METRICS)
+def test_update_medoids_matches_oracle(spf, ctx, oracle, metric):
+    data = clustered(6000, 40, 30, 21)
+    cent = np.random.default_rng(3).choice(6000, 50, replace=False)
+    ds = spf.Dataset(ctx, data)
+    res = ds.assign(metric, cent)
+    f = res.fetch()
+    ref_rows, ref_means = oracle.update_medoids(data, metric, f.offsets, f.members, cent, want_means=True)
+    rows, means = ds.update_medoids_from(metric, res, cent, want_means=True)
+    assert np.array_equal(rows, ref_rows)
+    assert np.array_equal(means.view(np.uint32), ref_means.view(np.uint32))
+    rows2 = ds.update_medoids(metric, f.offsets, f.members, cent)
+    assert np.array_equal(rows2, ref_rows)
+    # an empty cluster keeps its old centroid (hierarchical.rs:146-149)
+    off = np.array([0, 0, 3], np.uint64)
+    mem = np.array([5, 9, 5], np.uint64)
+    assert np.array_equal(ds.update_medoids(metric, off, mem, [77, 1]),
+                          oracle.update_medoids(data, metric, off, mem, [77, 1]))
+
+
+def test_mean_kat_on_device(spf, ctx, kats):
+    kat = kats["mean"][0]                          # utils.rs:24-32
+    data = np.array(kat["data"], np.float32)
+    ds = spf.Dataset(ctx, data)
+    _, means = ds.update_medoids(0, [0, 2], kat["indices"], [0], want_means=True)
+    assert np.all(np.abs(means[0] - np.array(kat["expected"])) < kat["tol"])
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_farthest_matches_oracle(spf, ctx, oracle, metric):
+    data = gauss(3000, 20, 4)
+    data[10] = data[11]
+    ds = spf.Dataset(ctx, data)
+    mem = np.random.default_rng(1).permutation(3000)[:1500]
+    for c1 in (int(mem[0]), int(mem[700]), 2999):
+        assert ds.farthest(metric, c1, mem) == oracle.farthest(data, metric, c1, mem)
+    assert ds.farthest(metric, 10, [10, 11]) == 0          # all distances 0 → identity row 0
+    assert ds.farthest(metric, 10, [10]) == 0
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_kmeanspp_matches_oracle(spf, ctx, oracle, metric):
+    data = clustered(20000, 32, 25, 8)
+    k = 24
+    u = np.random.default_rng(metric).random(k - 1)
+    ref, fell = oracle.kmeanspp(data, metric, k, 123, u)
+    assert not fell.any()
+    ds = spf.Dataset(ctx, data)
+    sess = ds.kmeanspp(metric, 123)
+    got = [123]
+    for r in range(k - 1):
+        got.append(sess.round(u[r]))
+    sess.free()
+    assert got == ref.tolist()
+    # degenerate: identical points → weighted pick impossible → host fallback is requested
+    same = np.ones((64, 4), np.float32)
+    sess = spf.Dataset(ctx, same).kmeanspp(0, 3)
+    assert sess.round(0.5) is None
+    sess.push(9)
+    assert sess.round(0.25) is None
+    sess.free()
+
+
+# ----------------------------------------------------------------------------------------------
+# fit() end to end through the host mirror
+# ----------------------------------------------------------------------------------------------
+def as_tuples(clusters):
+    return [(int(c.centroid_idx), np.asarray(c.points).tolist(), int(c.depth)) for c in clusters]
+
+
+@pytest.mark.parametrize("metric_cls", ["SquaredEuclideanDistance", "ManhattanDistance", "ChebyshevDistance"])
+def test_fit_matches_oracle(spf, ctx, oracle, metric_cls):
+    data = clustered(4000, 16, 12, 31)
+    init = np.random.default_rng(4).choice(4000, 5, replace=False).tolist()
+    pick = lambda n: (n * 5) // 7  # noqa: E731
+    metric = getattr(spf, metric_cls)()
+    params = spf.ClusteringParams(metric, spf.InitializationMethod.Random, 300, 5,
+                                  random_source=spf.ScriptedRandomSource(multiple=init, index=pick))
+    hc = spf.HierarchicalClustering(params, data, ctx=ctx)
+    hc.fit()
+    ref = oracle.fit(data, metric.kind, init, 300, pick=pick)
+    assert as_tuples(hc.clusters) == as_tuples(ref)
+    assert len(hc.clusters) > 5                       # the bisect did fire
+    lab = hc.labels()
+    assert lab.shape == (4000,) and lab.min() >= 0 and lab.max() < len(hc.clusters)
+
+
+def test_fit_kmeanspp_end_to_end(spf, ctx, oracle):
+    data = clustered(3000, 12, 9, 5)
+    u = np.random.default_rng(9).random(7).tolist()
+    params = spf.ClusteringParams(spf.SquaredEuclideanDistance(), spf.InitializationMethod.KMeansPlusPlus, 600, 8,
+                                  random_source=spf.ScriptedRandomSource(index=[17] + [0] * 50, u01=u))
+    hc = spf.HierarchicalClustering(params, data, ctx=ctx)
+    hc.fit()
+    init, _ = oracle.kmeanspp(data, 0, 8, 17, u)
+    ref = oracle.fit(data, 0, init, 600, pick=lambda n: 0)
+    assert as_tuples(hc.clusters) == as_tuples(ref)
+
+
+def test_reference_unit_tests_on_device(spf, ctx, kats):
+    """The reference's own hierarchical.rs tests, run against the device implementation."""
+    data = np.array(kats["toy_data"]["rows"], np.float32)
+    # test_subdivide_clusters (:444-463)
+    for init in range(6):
+        p = spf.ClusteringParams(spf.SquaredEuclideanDistance(), spf.InitializationMethod.Random, 2, 1,
+                                 random_source=spf.ScriptedRandomSource(multiple=[init], index=lambda n: n // 2))
+        hc = spf.HierarchicalClustering(p, data, ctx=ctx)
+        hc.initialize_clusters(1)
+        hc.assign_points()
+        hc.update_centroids()
+        hc.subdivide_clusters()
+        assert len(hc.clusters) > 1 and all(len(c.points) <= 2 for c in hc.clusters)
+    # test_initialize_clusters_randomly / kmeans_plus_plus (:405-441) with the default RNG
+    for meth in (spf.InitializationMethod.Random, spf.InitializationMethod.KMeansPlusPlus):
+        p = spf.ClusteringParams(spf.SquaredEuclideanDistance(), meth, 3, 2, rng_seed=42)
+        hc = spf.HierarchicalClustering(p, data, ctx=ctx)
+        hc.initialize_clusters(2)
+        assert len(hc.clusters) == 2 and all(c.centroid_idx is not None for c in hc.clusters)
+    # test_fit (:489-507) invariants with the default RNG: every cluster <= desired size
+    p = spf.ClusteringParams(spf.SquaredEuclideanDistance(), spf.InitializationMethod.KMeansPlusPlus, 2, 3, rng_seed=42)
+    hc = spf.HierarchicalClustering(p, data, ctx=ctx)
+    hc.fit()
+    assert all(len(c.points) <= 2 for c in hc.clusters)
+
+
+def test_example_build_index_kat_on_device(spf, ctx, kats, tmp_path):
+    """examples/build_index.rs through SpannIndexBuilder: point_id 0 / [1.0, 2.0] for any draws."""
+    kat = kats["example_query"][0]
+    data = np.array(kats["toy_data"]["rows"], np.float32)
+    for init in [(0, 1, 2, 3), (5, 3, 1, 0), (2, 4, 5, 1)]:
+        cfg = spf.Config(spf.ClusteringParamsConfig("Euclidean", "Random", 4), None, str(tmp_path / "idx"))
+        b = spf.SpannIndexBuilder(cfg, ctx=ctx,
+                                  random_source=spf.ScriptedRandomSource(multiple=list(init), index=lambda n: 0))
+        index = b.with_data(data).build(2)
+        res = index.find_k_nearest_neighbor_spann(np.array(kat["query"], np.float32), kat["k"])
+        assert res == [spf.PointData(kat["expected_point_id"], kat["expected_vector"])]
+        # load::<N>() from the files just written gives the same answer
+        loaded = spf.SpannIndexBuilder(cfg, ctx=ctx).load(2)
+        res2 = loaded.find_k_nearest_neighbor_spann(np.array(kat["query"], np.float32), kat["k"])
+        assert res2 == res
+    with pytest.raises(ValueError):
+        spf.SpannIndexBuilder(cfg, ctx=ctx).with_data(data).build(3)      # dimension mismatch
+
+
+# ----------------------------------------------------------------------------------------------
+# query path
+# ----------------------------------------------------------------------------------------------
+def build_lists(oracle, data, k, seed):
+    cent = np.random.default_rng(seed).choice(data.shape[0], k, replace=False)
+    r = oracle.assign(data, 0, cent)
+    return cent, r.offsets, r.members
+
+
+@pytest.mark.parametrize("n,d,nlists,topk,nprobe", [
+    (3000, 16, 40, 10, 0), (5000, 128, 64, 10, 0), (5000, 33, 50, 5, 20), (4000, 96, 30, 40, 8),
+    (2000, 8, 300, 100, 0),
+])
+def test_search_matches_oracle(spf, ctx, oracle, n, d, nlists, topk, nprobe):
+    data = clustered(n, d, 20, n + d)
+    cent, off, mem = build_lists(oracle, data, nlists, d)
+    ds = spf.Dataset(ctx, data)
+    idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+    q = clustered(200, d, 20, n + d)              # same centres → realistic probes
+    q[0] = data[cent[3]]                          # exact hit on a centroid: thr = 1.2 * eps
+    q[1] = 100.0                                  # far away
+    ids, dists, counts, vec = idx.search(q, topk, nprobe, want_vectors=True)
+    rid, rd, rc = oracle.search_batch(data, off, mem, cent, q, topk, nprobe)
+    assert np.array_equal(counts, rc)
+    for i in range(q.shape[0]):
+        c = int(rc[i])
+        assert np.array_equal(ids[i, :c], rid[i, :c]), i
+        assert np.array_equal(dists[i, :c].view(np.uint32), rd[i, :c].view(np.uint32)), i
+        assert np.array_equal(vec[i, :c], data[rid[i, :c].astype(np.int64)])
+    assert idx.last_scan_bytes() > 0
+    # no pruning at all
+    ids2, d2, c2 = idx.search(q, topk, nprobe, prune_factor=float("inf"))
+    rid2, rd2, rc2 = oracle.search_batch(data, off, mem, cent, q, topk, nprobe, prune_factor=float("inf"))
+    assert np.array_equal(c2, rc2)
+    for i in range(q.shape[0]):
+        assert np.array_equal(ids2[i, :rc2[i]], rid2[i, :rc2[i]])
+
+
+def test_search_duplicates_are_kept(spf, ctx, oracle):
+    """F7: a boundary-replicated point appears once per probed list it lives in."""
+    data = gauss(2000, 8, 12)
+    cent, off, mem = build_lists(oracle, data, 6, 1)
+    assert mem.size > 2000                         # replication did happen
+    ds = spf.Dataset(ctx, data)
+    idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+    q = gauss(300, 8, 13)
+    ids, dists, counts = idx.search(q, 6, 0, prune_factor=float("inf"))
+    rid, rd, rc = oracle.search_batch(data, off, mem, cent, q, 6, 0, prune_factor=float("inf"))
+    assert np.array_equal(ids, rid) and np.array_equal(counts, rc)
+    assert any(len(set(ids[i].tolist())) < 6 for i in range(300))
+
+
+def test_search_list_sharding_and_merge(spf, ctx, oracle):
+    """§8(e): lists sharded over ranks, per-rank top-k merged on the stable key == unsharded."""
+    data = clustered(6000, 24, 30, 2)
+    cent, off, mem = build_lists(oracle, data, 48, 7)
+    ds = spf.Dataset(ctx, data)
+    q = clustered(150, 24, 30, 2)
+    full = spf.DeviceIndex.pack(ds, off, mem, cent)
+    ids, dists, counts = full.search(q, 10)
+    parts = []
+    for lb, le in ((0, 11), (11, 30), (30, 48)):
+        part = spf.DeviceIndex.pack(ds, off, mem, cent, list_range=(lb, le))
+        parts.append(part.search(q, 10, want_keys=True))
+    mids, md, mc = spf.topk_merge(np.stack([p[3] for p in parts]), np.stack([p[0] for p in parts]),
+                                  np.stack([p[1] for p in parts]), np.stack([p[2] for p in parts]))
+    assert np.array_equal(mc, counts)
+    for i in range(150):
+        assert np.array_equal(mids[i, :mc[i]], ids[i, :mc[i]])
+        assert np.array_equal(md[i, :mc[i]], dists[i, :mc[i]])
+
+
+def test_index_files_interoperate_with_reference_layout(spf, ctx, oracle, tmp_path):
+    """posting_lists.rs:64-129: files written by the library are byte-identical to the oracle's
+    bincode writer, and an index loaded from oracle-written files answers identically."""
+    data = gauss(1500, 12, 3)
+    cent, off, mem = build_lists(oracle, data, 9, 2)
+    ds = spf.Dataset(ctx, data)
+    idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+    a, b = tmp_path / "ours", tmp_path / "ref"
+    b.mkdir()
+    idx.save_dir(str(a))
+    for j in range(9):
+        oracle.posting_list_write(str(b), j, data, mem[int(off[j]):int(off[j + 1])])
+        assert open(a / f"posting_list_{j}.bin", "rb").read() == open(b / f"posting_list_{j}.bin", "rb").read()
+    oracle.cluster_ids_write(str(b), [8, 3, 0, 1, 2, 4, 5, 6, 7])      # arbitrary hash-map order
+    loaded = spf.DeviceIndex.load_dir(ctx, str(b), data[cent.astype(np.int64)])
+    q = gauss(64, 12, 4)
+    r1, r2 = idx.search(q, 7), loaded.search(q, 7)
+    for x, y in zip(r1, r2):
+        assert np.array_equal(x, y)
