@@ -130,7 +130,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   std::lock_guard<std::mutex> lk(c->mu);
   std::string s(name);
   if (s == "cand_cap") {
-    if (value < 2 || value > 1024) return fail(SPF_E_INVALID, "cand_cap must be in [2,1024]");
+    if (value < 2 || value > 1024 || (value & 1)) return fail(SPF_E_INVALID, "cand_cap must be even and in [2,1024]");
     c->params.cand_cap = value;
   } else if (s == "force_exact") c->params.force_exact = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;

@@ -96,7 +96,7 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   DevBuf<uint2> cand;
   DevBuf<uint32_t> cand_cnt;
   SPF_TRY(cand.alloc(st, (size_t)m * cap));
-  SPF_TRY(cand_cnt.alloc(st, m));
+  SPF_TRY(cand_cnt.alloc(st, m * 2));
 
   const bool use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) &&
                       !c->params.force_exact && assign_tc_supported(c, m, k, ld);
@@ -149,7 +149,7 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   if (rc >= 0) {
     ResolveArgs a;
     a.metric = metric; a.P = P; a.m = m; a.C = Cg.p; a.k = k; a.ld = ld; a.factor = factor;
-    a.cand = cand.p; a.cand_cnt = cand_cnt.p; a.cap = cap;
+    a.cand = cand.p; a.cand_cnt = cand_cnt.p; a.cap = cap; a.nseg = use_tc ? 2 : 1;
     a.xnorm = use_tc ? xnorm : nullptr; a.d_cnmax = use_tc ? cnmax.p : nullptr;
     a.cc = cc.p; a.want_members = want_members;
     a.best = best.p; a.dmin = dmin.p; a.nmem = nmem.p;

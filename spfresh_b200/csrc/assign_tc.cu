@@ -12,12 +12,15 @@
 // reference while the O(n k d) work runs at tensor-core rate (1 pass instead of the 3 a
 // 3xTF32 split would need).
 //
-// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
 //   warp 0     TMA producer: the 128 x ld point tile (A, stationary for a whole row block) and a
 //              4-stage ring of 256 x 32 centroid tiles (B), both SWIZZLE_128B, K-major
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=8 per MMA)
-//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time from the double-buffered 2 x 256
-//              column accumulator, running min + candidate emission, one point per thread
+//   warps 2-9  epilogue (two warps per SM sub-partition so one hides the other's latencies):
+//              warp w reads TMEM lane quarter w%4 and column half (w-2)/4 of the double-buffered
+//              2 x 256 column accumulator, 32 columns per tcgen05.ld; one point x 128 columns
+//              per thread and tile: running minimum (shared between the two halves through
+//              shared memory) + candidate emission with predicated stores
 #include <cuda.h>
 
 #include "kernels.cuh"
@@ -34,12 +37,14 @@ constexpr int KB_MAX = 4;          // stationary A supports ld <= 128
 constexpr int NSTAGE = 4;          // B ring depth
 constexpr int A_KB_BYTES = BM * BK * 4;       // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 4;    // 32 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_A = KB_MAX * A_KB_BYTES;                  // 64 KB
 constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
 constexpr int SMEM_BAR_OFF = SMEM_A + SMEM_B;
-constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;        // + barriers + alignment slack
+constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [2][128]
+constexpr int SMEM_TOTAL = SMEM_PUB_OFF + 2 * BM * 8 + 1024; // + alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -95,8 +100,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 // 32 lanes x 32 consecutive columns: thread t receives lane (base + t), columns col .. col+31.
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// The load is asynchronous: tc_ld32_wait() must run before the registers are read.  The wait
+// lists the registers as in/out operands so the compiler cannot hoist their uses above it.
+#define SPF_R32(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], \
+                   r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -107,9 +115,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024
@@ -159,9 +173,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int i = 0; i < KB_MAX; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x >= 64) reinterpret_cast<unsigned long long*>(smem + SMEM_PUB_OFF)[threadIdx.x - 64] = ~0ull;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"((uint32_t)TMEM_COLS)
@@ -225,59 +240,113 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // =============================== epilogue warps ==========================================
     const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;      // column half of every accumulator
+    const uint32_t lrow = quarter * 32 + lane;
     const float INF = __int_as_float(0x7f800000);
     const float cnmax = a.cnmax[0];
     const float f1 = fmaxf(a.factor, 1.0f);
+    const uint32_t segcap = (uint32_t)a.cap >> 1;
+    volatile unsigned long long* pub = reinterpret_cast<volatile unsigned long long*>(smem + SMEM_PUB_OFF);
     uint32_t tcount = 0;
     for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
-      const uint32_t row = rb * BM + quarter * 32 + lane;
+      const uint32_t row = rb * BM + lrow;
       const bool row_ok = row < a.m;
       const float xn = row_ok ? a.xnorm[row] : 0.0f;
       const float E = tc_err_bound(xn, cnmax, a.ld);
       const float xnE = xn + E, EmX = E - xn;
       const float slop = 1e-6f * (xn + cnmax) + 1e-30f;
-      uint2* crow = a.cand + (size_t)row * a.cap;
+      uint2* const seg = a.cand + (size_t)row * a.cap + (size_t)half * segcap;
+      uint2* wp = seg;                                    // write pointer into this thread's segment
+      uint32_t overflow = 0;                              // hits that did not fit
       float tmin = INF;
-      uint32_t cnt = 0;
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(&t_full[buf], use & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN;
-        const float4* cn4 = reinterpret_cast<const float4*>(a.cnorm + (size_t)t * BN);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          tc_ld32(taddr + c * 32, v);
-          if (c == BN / 32 - 1) {                         // accumulator fully read → hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
-          }
-          float cmin = INF;
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
+        const float4* cn4 = reinterpret_cast<const float4*>(a.cnorm + (size_t)t * BN + half * (BN / 2));
+        const uint32_t jtile = t * BN + half * (BN / 2);
+
+        // one 32-column chunk: t = |c|^2 - 2 x.c, running minimum, candidate emission
+        auto process = [&](uint32_t (&rr)[32], int c) {
+          float v[32], q[8];
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
             const float4 cn = __ldg(cn4 + c * 8 + i4);
-            v[i4 * 4 + 0] = fmaf(-2.0f, v[i4 * 4 + 0], cn.x);
-            v[i4 * 4 + 1] = fmaf(-2.0f, v[i4 * 4 + 1], cn.y);
-            v[i4 * 4 + 2] = fmaf(-2.0f, v[i4 * 4 + 2], cn.z);
-            v[i4 * 4 + 3] = fmaf(-2.0f, v[i4 * 4 + 3], cn.w);
-            cmin = fminf(cmin, fminf(fminf(v[i4 * 4 + 0], v[i4 * 4 + 1]), fminf(v[i4 * 4 + 2], v[i4 * 4 + 3])));
+            v[i4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 0]), cn.x);
+            v[i4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 1]), cn.y);
+            v[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 2]), cn.z);
+            v[i4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 3]), cn.w);
+            q[i4] = fminf(fminf(v[i4 * 4 + 0], v[i4 * 4 + 1]), fminf(v[i4 * 4 + 2], v[i4 * 4 + 3]));
           }
-          tmin = fminf(tmin, cmin);
-          // d < f (dmin_run + E) + E   with d = t + |x|^2
+          tmin = fminf(tmin, fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])),
+                                   fminf(fminf(q[4], q[5]), fminf(q[6], q[7]))));
+          {   // exchange running minima with the partner half of the same row (tagged with the row
+              // block: any value published for this row block is a valid upper bound of the final
+              // minimum, so a stale one only makes the candidate set a little larger)
+            const unsigned long long pv = pub[(half ^ 1) * BM + lrow];
+            if ((uint32_t)(pv >> 32) == rb) tmin = fminf(tmin, __uint_as_float((uint32_t)pv));
+            pub[half * BM + lrow] = ((unsigned long long)rb << 32) | __float_as_uint(tmin);
+          }
+          // candidate test  d < f (dmin_run + E) + E  with d = t + |x|^2
           const float thr_t = row_ok ? fmaf(f1, tmin + xnE, EmX) + slop : -INF;
-          const uint32_t jbase = t * BN + c * 32;
+          const uint32_t jbase = jtile + c * 32;
+          const bool room = (uint32_t)(wp - seg) + 32u <= segcap;
+          if (__all_sync(0xffffffffu, room)) {
+            // fast path: one warp vote per 4 columns, predicated stores inside
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (v[i] < thr_t) {
-              if (cnt < (uint32_t)a.cap) crow[cnt] = make_uint2(jbase + i, __float_as_uint(v[i] + xn));
-              ++cnt;
+            for (int g = 0; g < 8; ++g) {
+              if (__any_sync(0xffffffffu, q[g] < thr_t)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float tv = v[g * 4 + e];
+                  asm volatile(
+                      "{\n\t.reg .pred p;\n\t"
+                      "setp.lt.f32 p, %1, %2;\n\t"
+                      "@p st.global.v2.b32 [%0], {%3, %4};\n\t"
+                      "@p add.u64 %0, %0, 8;\n\t}"
+                      : "+l"(wp)
+                      : "f"(tv), "f"(thr_t), "r"(jbase + g * 4 + e), "r"(__float_as_uint(tv + xn))
+                      : "memory");
+                }
+              }
+            }
+          } else {
+            // slow path: some thread of the warp is close to the end of its segment
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (v[i] < thr_t) {
+                if ((uint32_t)(wp - seg) < segcap) {
+                  *wp = make_uint2(jbase + i, __float_as_uint(v[i] + xn));
+                  ++wp;
+                } else {
+                  ++overflow;
+                }
+              }
             }
           }
-        }
+        };
+
+        // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
+        // c+1 is in flight while chunk c is processed
+        uint32_t ra[32], rbuf[32];
+        tc_ld32_issue(taddr, ra);
+        tc_ld32_wait(ra);
+        tc_ld32_issue(taddr + 32, rbuf);
+        process(ra, 0);
+        tc_ld32_wait(rbuf);
+        tc_ld32_issue(taddr + 64, ra);
+        process(rbuf, 1);
+        tc_ld32_wait(ra);
+        tc_ld32_issue(taddr + 96, rbuf);
+        process(ra, 2);
+        tc_ld32_wait(rbuf);
+        tc_fence_before();                                // this warp's part of the accumulator is read
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);
+        process(rbuf, 3);
       }
-      if (row_ok) a.cand_cnt[row] = cnt;
+      if (row_ok) a.cand_cnt[(size_t)row * 2 + half] = (uint32_t)(wp - seg) + overflow;
     }
   }
 

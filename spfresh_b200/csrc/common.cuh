@@ -39,7 +39,7 @@ int fail(int code, const char* fmt, ...);
 // context
 // ---------------------------------------------------------------------------------------------
 struct Params {
-  int cand_cap = 128;        // candidate slots per point kept by the assign kernels
+  int cand_cap = 256;        // candidate slots per point kept by the assign kernels
   int force_exact = 0;       // 1: never use the tcgen05 candidate GEMM
   int tc_min_k = 64;         // use the tensor path only when k >= this
   int tc_min_m = 1024;       // ... and m >= this

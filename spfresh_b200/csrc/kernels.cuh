@@ -57,6 +57,7 @@ struct ResolveArgs {
   const float* P; uint64_t m; const float* C; uint32_t k; uint32_t ld;
   float factor;
   uint2* cand; uint32_t* cand_cnt; int cap;
+  int nseg;                // segments per row buffer: 1 (exact kernel) or 2 (tensor kernel)
   const float* xnorm;      // NULL on the exact path (error bound 0)
   const float* d_cnmax;    // device scalar, tensor path only
   const float* cc;         // k x k exact centroid-centroid distances or NULL (computed on demand)
