@@ -49,7 +49,9 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   const bool prow_ok = (row0 + lrow) < m;
   const float* prow = P + (size_t)(row0 + lrow) * ld;
 
-  for (uint32_t c0 = 0; c0 < k; c0 += BN) {
+  // dense-only launches may split the centroid tiles over blockIdx.y (candidate mode keeps a
+  // CTA-wide running minimum per row and therefore uses gridDim.y == 1)
+  for (uint32_t c0 = blockIdx.y * BN; c0 < k; c0 += gridDim.y * BN) {
     const bool crow_ok = (c0 + lrow) < k;
     const float* crow = C + (size_t)(c0 + lrow) * ld;
 
@@ -151,6 +153,11 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
                         uint32_t ld, float factor, uint2* cand, uint32_t* cand_cnt, int cap, float* dense) {
   if (m == 0 || k == 0) return SPF_OK;
   dim3 grid((unsigned)ceil_div(m, BM)), block(NTHREADS);
+  if (cand == nullptr) {   // dense matrix only: fill the machine even when m is small
+    const uint64_t ctiles = ceil_div(k, BN);
+    uint64_t want = ceil_div((uint64_t)c->sm_count * 4, grid.x);
+    grid.y = (unsigned)(want < 1 ? 1 : (want > ctiles ? ctiles : want));
+  }
   switch (metric) {
     case SPF_METRIC_EUCLIDEAN:
       assign_exact_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(

@@ -29,7 +29,6 @@ struct ResolveDev {
   const float* xnorm; const float* cnmax; const float* cc;
   uint32_t* best; float* dmin; uint32_t* nmem;
   uint32_t* ovf_rows; uint32_t* ovf_count;
-  uint2* work; uint32_t* work_count; uint32_t work_cap;   // (row, slot) pairs needing an exact distance
   int want_members;
 };
 
@@ -37,209 +36,230 @@ __device__ __forceinline__ bool lex_less(float d1, uint32_t j1, float d2, uint32
   return d1 < d2 || (d1 == d2 && j1 < j2);
 }
 
-// Warp-aggregated append of (row, slot) to the work list; returns false when the list is full
-// (the caller then evaluates the distance inline, so the list is only an accelerator).
-__device__ __forceinline__ bool work_push(const ResolveDev& a, bool want, uint32_t row, uint32_t slot, int lane) {
-  const unsigned bal = __ballot_sync(0xffffffffu, want);
-  if (bal == 0) return true;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(a.work_count, (uint32_t)__popc(bal));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  const uint32_t pos = base + __popc(bal & ((1u << lane) - 1u));
-  if (want && pos < a.work_cap) a.work[pos] = make_uint2(row, slot);
-  return !want || pos < a.work_cap;
+constexpr int RS_WARPS = 8;           // warps per CTA of the resolve kernel
+constexpr int RS_CHUNK = 128;         // dimensions staged per step (one float4 per lane)
+constexpr int RS_PAIRS = 4;           // exact distances evaluated per cooperative round
+constexpr int RS_TB_STRIDE = RS_CHUNK + 4;
+
+struct ResolveSmem {
+  float xs[RS_CHUNK];
+  float tb[RS_PAIRS][RS_TB_STRIDE];
+};
+
+// Exact distances d(x, C[j]) for the lanes with `want` set (their centroid slot in `j`), four at
+// a time: the warp stages 128 dimensions of x and of the four centroid rows in shared memory
+// with coalesced float4 loads, then lanes 0..3 each walk one pair in dimension order, so every
+// value is the reference's sequential f32 sum (src/distances/distance.rs:16-43).  Returns the
+// distance to the owning lane (unchanged `dv` for lanes without `want`).
+template <int METRIC>
+__device__ __forceinline__ float coop_exact(bool want, uint32_t j, float dv, const float* __restrict__ x,
+                                            const float* __restrict__ C, uint32_t ld, ResolveSmem& sm, int lane,
+                                            const float4* x0 = nullptr) {
+  unsigned pending = __ballot_sync(0xffffffffu, want);
+  while (pending) {
+    int owner[RS_PAIRS];
+    uint32_t jj[RS_PAIRS];
+    int np = 0;
+#pragma unroll
+    for (int p = 0; p < RS_PAIRS; ++p) {
+      owner[p] = -1;
+      jj[p] = 0;
+      if (pending) {
+        owner[p] = __ffs(pending) - 1;
+        pending &= pending - 1;
+        np = p + 1;
+      }
+      jj[p] = __shfl_sync(0xffffffffu, j, owner[p] < 0 ? 0 : owner[p]);
+    }
+    float acc = 0.0f;
+    for (uint32_t c0 = 0; c0 < ld; c0 += RS_CHUNK) {
+      const uint32_t col = c0 + lane * 4;
+      const bool ok = col < ld;                      // ld is a multiple of 4
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xv = (x0 != nullptr && c0 == 0) ? *x0 : (ok ? __ldg(reinterpret_cast<const float4*>(x + col)) : z);
+      float4 cv[RS_PAIRS];
+#pragma unroll
+      for (int p = 0; p < RS_PAIRS; ++p)
+        cv[p] = (ok && p < np) ? __ldg(reinterpret_cast<const float4*>(C + (size_t)jj[p] * ld + col)) : z;
+      __syncwarp();
+      *reinterpret_cast<float4*>(&sm.xs[lane * 4]) = xv;
+#pragma unroll
+      for (int p = 0; p < RS_PAIRS; ++p) *reinterpret_cast<float4*>(&sm.tb[p][lane * 4]) = cv[p];
+      __syncwarp();
+      if (lane < np) {
+        const int nn = (ld - c0) < (uint32_t)RS_CHUNK ? (int)(ld - c0) : RS_CHUNK;
+#pragma unroll 8
+        for (int i = 0; i < nn; ++i) acc = dist_step<METRIC>(acc, sm.xs[i], sm.tb[lane][i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < RS_PAIRS; ++p) {
+      const float r = __shfl_sync(0xffffffffu, acc, p);
+      if (lane == owner[p]) dv = r;
+    }
+  }
+  return dv;
 }
 
-enum { MODE_MIN = 0, MODE_CLASSIFY = 1, MODE_FINAL = 2 };
-
-// One warp per listed point.
-//   MODE_MIN      (tensor path) approximate minimum, queue every candidate within 2E of it
-//   MODE_CLASSIFY (tensor path) exact (dmin, best); queue the boundary candidates whose
-//                 membership cannot be certified from the approximate distance
-//   MODE_FINAL    everything decided on exact values; members compacted to the row's front
-// Anything that should have been queued but did not fit is evaluated inline by its lane.
-template <int METRIC, int MODE>
-__global__ void __launch_bounds__(256) resolve_kernel(ResolveDev a) {
+// One warp per listed point; the whole of hierarchical.rs:317-346 for that point in one pass
+// over its candidate slots: approximate minimum → exact distances for everything within 2E of
+// it → exact (dmin, best) → boundary tests, recomputing exactly only where the approximate
+// value cannot certify the outcome → members compacted to the front of the row's buffer.
+template <int METRIC>
+__global__ void __launch_bounds__(RS_WARPS * 32, 3) resolve_kernel(ResolveDev a) {
+  __shared__ ResolveSmem smem[RS_WARPS];
   const int lane = threadIdx.x & 31;
+  ResolveSmem& sm = smem[threadIdx.x >> 5];
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const float INF = __int_as_float(0x7f800000);
   const uint32_t segcap = (uint32_t)a.cap / (uint32_t)a.nseg;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.m; r += warps_total) {
+  // Everything a row needs first (its counts, the first 32 slots of each segment, 128 dimensions
+  // of the point) is fetched one row ahead, so the dependent HBM round trips of row r+1 overlap
+  // the work on row r.  Slots past the live count are read speculatively and ignored.
+  struct Pre { uint32_t cnt0, cnt1; uint2 e0, e1; float4 xv; };
+  auto prefetch = [&](uint32_t r) {
+    Pre p;
+    p.cnt0 = p.cnt1 = 0;
+    p.e0 = p.e1 = make_uint2(0u, 0u);
+    p.xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < a.m) {
+      p.cnt0 = a.cand_cnt[(size_t)r * a.nseg];
+      if (a.nseg > 1) p.cnt1 = a.cand_cnt[(size_t)r * a.nseg + 1];
+      const uint2* cr = a.cand + (size_t)r * a.cap;
+      if ((uint32_t)lane < segcap) {
+        p.e0 = cr[lane];
+        if (a.nseg > 1) p.e1 = cr[segcap + lane];
+      }
+      if ((uint32_t)lane * 4 < a.ld) p.xv = __ldg(reinterpret_cast<const float4*>(a.P + (size_t)r * a.ld) + lane);
+    }
+    return p;
+  };
+  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  Pre nx = prefetch(r);
+  for (; r < a.m; r += warps_total) {
+    const Pre cur = nx;
+    nx = prefetch(r + warps_total);
     // the row's buffer holds nseg segments of segcap slots; cnt_s > segcap marks an overflow
-    uint32_t cnts[2];
-    cnts[0] = a.cand_cnt[(size_t)r * a.nseg];
-    cnts[1] = a.nseg > 1 ? a.cand_cnt[(size_t)r * a.nseg + 1] : 0;
-    if (cnts[0] > segcap || cnts[1] > segcap) {   // overflowed: the brute-force kernels own this row
-      if (MODE == MODE_MIN || (MODE == MODE_FINAL && a.work == nullptr)) {
-        if (lane == 0) {
-          const uint32_t pos = atomicAdd(a.ovf_count, 1u);
-          a.ovf_rows[pos] = r;
-          a.nmem[r] = NMEM_OVERFLOW_BIT;
-        }
+    const uint32_t cnt0 = cur.cnt0, cnt1 = cur.cnt1;
+    if (cnt0 > segcap || cnt1 > segcap) {   // overflowed: the brute-force kernels own this row
+      if (lane == 0) {
+        const uint32_t pos = atomicAdd(a.ovf_count, 1u);
+        a.ovf_rows[pos] = r;
+        a.nmem[r] = NMEM_OVERFLOW_BIT;
       }
       continue;
     }
+    const uint32_t total = cnt0 + cnt1;
+    auto slot_of = [&](uint32_t u) { return u < cnt0 ? u : segcap + (u - cnt0); };
     uint2* cr = a.cand + (size_t)r * a.cap;
     const float* x = a.P + (size_t)r * a.ld;
     const float E = a.xnorm ? tc_err_bound(a.xnorm[r], a.cnmax[0], a.ld) : 0.0f;
 
+    // 1. approximate minimum over all candidates
+    float ma = INF;
+    if ((uint32_t)lane < cnt0) ma = __uint_as_float(cur.e0.y);
+    if ((uint32_t)lane < cnt1) ma = fminf(ma, __uint_as_float(cur.e1.y));
+    for (uint32_t s2 = 32 + lane; s2 < cnt0; s2 += 32) ma = fminf(ma, __uint_as_float(cr[s2].y));
+    for (uint32_t s2 = 32 + lane; s2 < cnt1; s2 += 32) ma = fminf(ma, __uint_as_float(cr[segcap + s2].y));
+    ma = warp_min(ma);
+    const float min_band = ma + 2.0f * E;
+
+    // 2. exact distances for everything that could be the true minimum → exact (dmin, best)
     float bd = INF;
     uint32_t bj = 0xffffffffu;
-    if (MODE == MODE_MIN) {
-      float ma = INF;
-      for (int sg = 0; sg < a.nseg; ++sg)
-        for (uint32_t s = lane; s < cnts[sg]; s += 32) ma = fminf(ma, __uint_as_float(cr[sg * segcap + s].y));
-      ma = warp_min(ma);
-      const float min_band = ma + 2.0f * E;
-      for (int sg = 0; sg < a.nseg; ++sg)
-        for (uint32_t s0 = 0; s0 < cnts[sg]; s0 += 32) {
-          const uint32_t s = s0 + lane;
-          bool want = false;
-          if (s < cnts[sg]) {
-            const uint2 e = cr[sg * segcap + s];
-            want = !(e.x & CAND_EXACT_BIT) && __uint_as_float(e.y) <= min_band;
-          }
-          work_push(a, want, r, sg * segcap + s, lane);   // leftovers are caught inline in CLASSIFY
-        }
-      if (lane == 0) a.dmin[r] = min_band;                // handed to MODE_CLASSIFY
-      continue;
+    for (uint32_t u0 = 0; u0 < total; u0 += 32) {
+      const uint32_t u = u0 + lane;
+      const bool valid = u < total;
+      uint2 e = make_uint2(0u, 0u);
+      if (valid) e = cr[slot_of(u)];
+      float dv = __uint_as_float(e.y);
+      const bool exact = (e.x & CAND_EXACT_BIT) != 0;
+      const bool want = valid && !exact && dv <= min_band;
+      const uint32_t j = e.x & CAND_SLOT_MASK;
+      dv = coop_exact<METRIC>(want, j, dv, x, a.C, a.ld, sm, lane, &cur.xv);
+      if (want) cr[slot_of(u)] = make_uint2(e.x | CAND_EXACT_BIT, __float_as_uint(dv));
+      if (valid && (exact || want) && lex_less(dv, j, bd, bj)) { bd = dv; bj = j; }
     }
-
-    // ---- exact (dmin, best) -------------------------------------------------------------------
-    if (MODE == MODE_FINAL && a.work != nullptr) {
-      bd = a.dmin[r];
-      bj = a.best[r];
-    } else {
-      const float min_band = (MODE == MODE_CLASSIFY) ? a.dmin[r] : INF;   // exact path: all exact already
-      for (int sg = 0; sg < a.nseg; ++sg)
-        for (uint32_t s = lane; s < cnts[sg]; s += 32) {
-          uint2 e = cr[sg * segcap + s];
-          float dv = __uint_as_float(e.y);
-          if (!(e.x & CAND_EXACT_BIT)) {
-            if (!(dv <= min_band)) continue;
-            dv = thread_dist<METRIC>(x, a.C + (size_t)(e.x & CAND_SLOT_MASK) * a.ld, a.ld);   // list was full
-            e.x |= CAND_EXACT_BIT;
-            e.y = __float_as_uint(dv);
-            cr[sg * segcap + s] = e;
-          }
-          const uint32_t j = e.x & CAND_SLOT_MASK;
-          if (lex_less(dv, j, bd, bj)) { bd = dv; bj = j; }
-        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
-        if (lex_less(od, oj, bd, bj)) { bd = od; bj = oj; }
-      }
-      if (!(bd < INF)) { bd = INF; bj = 0; }   // fold identity (0, +inf): nothing was < inf
-      __syncwarp();
-      if (lane == 0) {
-        a.best[r] = bj;
-        a.dmin[r] = bd;
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (lex_less(od, oj, bd, bj)) { bd = od; bj = oj; }
+    }
+    if (!(bd < INF)) { bd = INF; bj = 0; }   // fold identity (0, +inf): nothing was < inf
+    if (lane == 0) {
+      a.best[r] = bj;
+      a.dmin[r] = bd;
     }
     if (!a.want_members) {
-      if (MODE == MODE_FINAL && lane == 0) a.nmem[r] = 1;
+      if (lane == 0) a.nmem[r] = 1;
       continue;
     }
+    __syncwarp();
 
-    // ---- boundary membership -------------------------------------------------------------------
+    // 3. boundary membership, decided on exact values
     const float thr = __fmul_rn(bd, a.factor);
     const float* cb = a.C + (size_t)bj * a.ld;
     bool best_listed = false;
-    for (int sg = 0; sg < a.nseg; ++sg)
-      for (uint32_t s0 = 0; s0 < cnts[sg]; s0 += 32) {
-        const uint32_t s = s0 + lane;
-        const bool valid = s < cnts[sg];
-        uint2 e = make_uint2(0u, 0u);
-        bool member = false, ambiguous = false;
-        float cc = 0.f;
-        if (valid) {
-          e = cr[sg * segcap + s];
-          const uint32_t j = e.x & CAND_SLOT_MASK;
-          const float dv = __uint_as_float(e.y);
-          if (j == bj) {
-            member = true;
-            best_listed = true;
-          } else {
-            const bool exact = (e.x & CAND_EXACT_BIT) != 0;
-            const float lo = exact ? dv : dv - E, hi = exact ? dv : dv + E;
-            if (lo < thr) {                         // otherwise certainly d >= thr → not a member
-              cc = a.cc ? a.cc[(size_t)bj * a.k + j] : thread_dist<METRIC>(cb, a.C + (size_t)j * a.ld, a.ld);
-              if (cc >= lo) {                       // otherwise certainly cc < d → not a member
-                if (hi < thr && cc >= hi) member = true;   // certain on both tests (exact ones end here)
-                else ambiguous = true;
-              }
-            }
-          }
-        }
-        if (MODE == MODE_CLASSIFY) {
-          work_push(a, ambiguous, r, sg * segcap + s, lane);
+    for (uint32_t u0 = 0; u0 < total; u0 += 32) {
+      const uint32_t u = u0 + lane;
+      const bool valid = u < total;
+      uint2 e = make_uint2(0u, 0u);
+      if (valid) e = cr[slot_of(u)];
+      const uint32_t j = e.x & CAND_SLOT_MASK;
+      float dv = __uint_as_float(e.y);
+      bool member = false, ambiguous = false, need_cc = false;
+      float cc = 0.f, lo = 0.f, hi = 0.f;
+      if (valid) {
+        if (j == bj) {
+          member = true;
+          best_listed = true;
         } else {
-          if (ambiguous) {                          // not queued (list full): decide inline
-            const float dv = thread_dist<METRIC>(x, a.C + (size_t)(e.x & CAND_SLOT_MASK) * a.ld, a.ld);
-            member = (dv < thr) && (cc >= dv);
-          }
-          if (valid) {
-            e.x = (e.x & ~CAND_MEMBER_BIT) | (member ? CAND_MEMBER_BIT : 0u);
-            cr[sg * segcap + s] = e;
-          }
+          const bool exact = (e.x & CAND_EXACT_BIT) != 0;
+          lo = exact ? dv : dv - E;
+          hi = exact ? dv : dv + E;
+          need_cc = lo < thr;                         // otherwise certainly d >= thr → not a member
         }
       }
-    if (MODE == MODE_CLASSIFY) continue;
+      if (a.cc) {
+        if (need_cc) cc = a.cc[(size_t)bj * a.k + j];
+      } else {
+        cc = coop_exact<METRIC>(need_cc, j, 0.f, cb, a.C, a.ld, sm, lane);   // no k x k matrix: on demand
+      }
+      if (need_cc && cc >= lo) {                      // otherwise certainly cc < d → not a member
+        if (hi < thr && cc >= hi) member = true;      // certain on both tests (exact values end here)
+        else ambiguous = true;
+      }
+      dv = coop_exact<METRIC>(ambiguous, j, dv, x, a.C, a.ld, sm, lane, &cur.xv);
+      if (ambiguous) member = (dv < thr) && (cc >= dv);
+      if (valid) cr[slot_of(u)] = make_uint2((e.x & ~CAND_MEMBER_BIT) | (member ? CAND_MEMBER_BIT : 0u), e.y);
+    }
     best_listed = __any_sync(0xffffffffu, best_listed);
     __syncwarp();
 
-    // ---- compact the member slots to the front of the row's buffer ------------------------------
+    // 4. compact the member slots to the front of the row's buffer
     uint32_t out = 0;
     if (!best_listed) {         // only when every distance was inf/NaN: members = {slot 0}
       if (lane == 0) cr[0] = make_uint2(0u, __float_as_uint(bd));
       out = 1;
       __syncwarp();
     } else {
-      for (int sg = 0; sg < a.nseg; ++sg)
-        for (uint32_t s0 = 0; s0 < cnts[sg]; s0 += 32) {
-          const uint32_t s = s0 + lane;
-          uint2 e = make_uint2(0u, 0u);
-          bool mem = false;
-          if (s < cnts[sg]) {
-            e = cr[sg * segcap + s];
-            mem = (e.x & CAND_MEMBER_BIT) != 0;
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, mem);
-          __syncwarp();
-          if (mem) cr[out + __popc(bal & ((1u << lane) - 1u))] = make_uint2(e.x & CAND_SLOT_MASK, e.y);
-          out += __popc(bal);
-          __syncwarp();
+      for (uint32_t u0 = 0; u0 < total; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        uint2 e = make_uint2(0u, 0u);
+        bool mem = false;
+        if (u < total) {
+          e = cr[slot_of(u)];
+          mem = (e.x & CAND_MEMBER_BIT) != 0;
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, mem);
+        __syncwarp();
+        if (mem) cr[out + __popc(bal & ((1u << lane) - 1u))] = make_uint2(e.x & CAND_SLOT_MASK, e.y);
+        out += __popc(bal);
+        __syncwarp();
+      }
     }
     if (lane == 0) a.nmem[r] = out;
-  }
-}
-
-// Exact distances for the queued (row, slot) pairs: 32 pairs per warp, rows fetched with
-// coalesced 128-byte requests (pairdist.cuh), result written back into the candidate record.
-template <int METRIC>
-__global__ void __launch_bounds__(PD_THREADS) work_exact_kernel(ResolveDev a) {
-  __shared__ PairDistSmem sm[PD_THREADS / 32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t count = *a.work_count;
-  if (count > a.work_cap) count = a.work_cap;
-  const uint32_t nwarps = gridDim.x * (PD_THREADS / 32);
-  for (uint32_t base = (blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < count; base += nwarps * 32) {
-    const uint32_t i = base + lane;
-    const bool valid = i < count;
-    const float* pa = nullptr;
-    const float* pb = nullptr;
-    uint2* rec = nullptr;
-    if (valid) {
-      const uint2 w = a.work[i];
-      rec = a.cand + (size_t)w.x * a.cap + w.y;
-      pa = a.P + (size_t)w.x * a.ld;
-      pb = a.C + (size_t)(rec->x & CAND_SLOT_MASK) * a.ld;
-    }
-    const float dv = warp_pair_dist<METRIC>(pa, pb, a.ld, sm[warp]);
-    if (valid) *rec = make_uint2(rec->x | CAND_EXACT_BIT, __float_as_uint(dv));
   }
 }
 
@@ -355,40 +375,15 @@ int run_resolve_t(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
   SPF_TRY(ovf_rows.alloc(st, a.m));
   SPF_TRY(ovf_count.alloc(st, 1));
   SPF_CUDA(cudaMemsetAsync(ovf_count.p, 0, sizeof(uint32_t), st));
-  // work list for exact re-evaluation (tensor path only)
-  DevBuf<uint2> work;
-  DevBuf<uint32_t> work_count;
-  const bool approx = a.xnorm != nullptr;
-  const uint32_t work_cap = approx ? (uint32_t)std::min<uint64_t>(a.m * 8ull + 1024, 1ull << 30) : 0;
-  if (approx) {
-    SPF_TRY(work.alloc(st, work_cap));
-    SPF_TRY(work_count.alloc(st, 1));
-  }
   ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, a.cand, a.cand_cnt, a.cap, a.nseg, a.xnorm,
-               a.d_cnmax, a.cc, a.best, a.dmin, a.nmem, ovf_rows.p, ovf_count.p,
-               approx ? work.p : nullptr, approx ? work_count.p : nullptr, work_cap, a.want_members ? 1 : 0};
+               a.d_cnmax, a.cc, a.best, a.dmin, a.nmem, ovf_rows.p, ovf_count.p, a.want_members ? 1 : 0};
   const unsigned ovf_grid = (unsigned)c->sm_count * 4;
   {
     KernelTimer t(c, "resolve");
-    uint64_t blocks = ceil_div(a.m * 32, 256);
+    uint64_t blocks = ceil_div(a.m, RS_WARPS);
     if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
-    const unsigned pgrid = (unsigned)c->sm_count * 16;
-    if (approx) {
-      SPF_CUDA(cudaMemsetAsync(work_count.p, 0, sizeof(uint32_t), st));
-      resolve_kernel<METRIC, MODE_MIN><<<(unsigned)blocks, 256, 0, st>>>(d);
-      SPF_TRY(check_launch(c, "resolve_kernel<MIN>"));
-      work_exact_kernel<METRIC><<<pgrid, PD_THREADS, 0, st>>>(d);
-      SPF_TRY(check_launch(c, "work_exact_kernel"));
-      SPF_CUDA(cudaMemsetAsync(work_count.p, 0, sizeof(uint32_t), st));
-      resolve_kernel<METRIC, MODE_CLASSIFY><<<(unsigned)blocks, 256, 0, st>>>(d);
-      SPF_TRY(check_launch(c, "resolve_kernel<CLASSIFY>"));
-      if (a.want_members) {
-        work_exact_kernel<METRIC><<<pgrid, PD_THREADS, 0, st>>>(d);
-        SPF_TRY(check_launch(c, "work_exact_kernel"));
-      }
-    }
-    resolve_kernel<METRIC, MODE_FINAL><<<(unsigned)blocks, 256, 0, st>>>(d);
-    SPF_TRY(check_launch(c, "resolve_kernel<FINAL>"));
+    resolve_kernel<METRIC><<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+    SPF_TRY(check_launch(c, "resolve_kernel"));
     resolve_overflow_kernel<METRIC, 0><<<ovf_grid, 256, 0, st>>>(d, nullptr, nullptr, nullptr);
     SPF_TRY(check_launch(c, "resolve_overflow_kernel<0>"));
   }
