@@ -337,8 +337,8 @@ def main():
     if not args.no_cpu and rank == 0:
         import oracle
         cores = oracle.online_cpus()
-        t_small = cpu_assign_sample(rows_np, 1024)
-        sample = int(min(200_000, max(1024, 1024 * 12.0 / max(t_small, 1e-3))))
+        t_small = cpu_assign_sample(rows_np, 8192)
+        sample = int(min(N_ROWS - K_CENT, max(8192, 8192 * 12.0 / max(t_small, 1e-3))))
         t_cpu = cpu_assign_sample(rows_np, sample)
         cpu = {"value": sample / t_cpu, "unit": "points/s", "cores": cores, "kind": "port",
                "sample": f"{sample} of 1e6 rows x all 4096 centroids in {t_cpu:.1f} s; C restatement of the Rust "
