@@ -268,11 +268,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t jtile = t * BN + half * (BN / 2);
 
         // one 32-column chunk: t = |c|^2 - 2 x.c, running minimum, candidate emission
-        auto process = [&](uint32_t (&rr)[32], int c) {
+        auto process = [&](uint32_t (&rr)[32], const float4 (&cnr)[8], int c) {
           float v[32], q[8];
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 cn = __ldg(cn4 + c * 8 + i4);
+            const float4 cn = cnr[i4];
             v[i4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 0]), cn.x);
             v[i4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 1]), cn.y);
             v[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 2]), cn.z);
@@ -330,21 +330,30 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
         // c+1 is in flight while chunk c is processed
         uint32_t ra[32], rbuf[32];
+        float4 cna[8], cnb[8];                            // |c|^2 of the chunk, fetched one chunk ahead
+        auto load_cn = [&](float4 (&cnr)[8], int c) {
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) cnr[i4] = __ldg(cn4 + c * 8 + i4);
+        };
         tc_ld32_issue(taddr, ra);
+        load_cn(cna, 0);
         tc_ld32_wait(ra);
         tc_ld32_issue(taddr + 32, rbuf);
-        process(ra, 0);
+        load_cn(cnb, 1);
+        process(ra, cna, 0);
         tc_ld32_wait(rbuf);
         tc_ld32_issue(taddr + 64, ra);
-        process(rbuf, 1);
+        load_cn(cna, 2);
+        process(rbuf, cnb, 1);
         tc_ld32_wait(ra);
         tc_ld32_issue(taddr + 96, rbuf);
-        process(ra, 2);
+        load_cn(cnb, 3);
+        process(ra, cna, 2);
         tc_ld32_wait(rbuf);
         tc_fence_before();                                // this warp's part of the accumulator is read
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[buf]);
-        process(rbuf, 3);
+        process(rbuf, cnb, 3);
       }
       if (row_ok) a.cand_cnt[(size_t)row * 2 + half] = (uint32_t)(wp - seg) + overflow;
     }
