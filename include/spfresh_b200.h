@@ -79,6 +79,9 @@ int   spf_ctx_set_profiling(spf_ctx* ctx, int enabled);
 float spf_ctx_kernel_ms(spf_ctx* ctx, const char* name);
 /* Number of kernels this library launched on this context since creation. */
 uint64_t spf_ctx_launch_count(const spf_ctx* ctx);
+/* Diagnostics: points of the last spf_assign whose candidate buffers overflowed and that were
+ * therefore resolved by the dense exact fallback (results are identical, only slower). */
+uint32_t spf_ctx_last_overflow_rows(const spf_ctx* ctx);
 
 /* ---- dataset -------------------------------------------------------------------------- *
  * Stands in for the borrowed ArrayView2<F> held by SpannIndexBuilder / HierarchicalClustering
@@ -204,7 +207,8 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
                    uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
 
 /* ---- tuning knobs (not part of the drop-in surface; used by the tests to reach rare paths) -- *
- * "cand_cap" candidate slots per point (default 128), "force_exact", "tc_min_k", "tc_min_m",
+ * "cand_cap" candidate group records per point (default 128), "short_cap" resolve short-list
+ * entries per point (power of two <= 64, default 64), "force_exact", "tc_min_k", "tc_min_m",
  * "kmpp_exact_sum" (1: sequential f32 sum, bit-parity; 0: tree sum), "cc_matrix_max_k". */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 

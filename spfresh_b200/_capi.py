@@ -33,6 +33,7 @@ SIGNATURES = {
     "spf_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
     "spf_ctx_kernel_ms": (C.c_float, [_vp, C.c_char_p]),
     "spf_ctx_launch_count": (C.c_uint64, [_vp]),
+    "spf_ctx_last_overflow_rows": (C.c_uint32, [_vp]),
     "spf_ctx_set_param": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "spf_dataset_upload": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, _vpp]),
     "spf_dataset_from_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, _vpp]),

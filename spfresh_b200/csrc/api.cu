@@ -123,6 +123,7 @@ float spf_ctx_kernel_ms(spf_ctx* c, const char* name) {
 }
 
 uint64_t spf_ctx_launch_count(const spf_ctx* c) { return c ? c->launches : 0; }
+uint32_t spf_ctx_last_overflow_rows(const spf_ctx* c) { return c ? c->last_overflow_rows : 0; }
 
 // Internal tuning knobs (tests use them to force the rare paths; not part of the drop-in ABI).
 int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
@@ -132,7 +133,11 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   if (s == "cand_cap") {
     if (value < 2 || value > 1024 || (value & 1)) return fail(SPF_E_INVALID, "cand_cap must be even and in [2,1024]");
     c->params.cand_cap = value;
+  } else if (s == "short_cap") {
+    if (value < 2 || value > 64 || (value & (value - 1))) return fail(SPF_E_INVALID, "short_cap must be a power of two in [2,64]");
+    c->params.short_cap = value;
   } else if (s == "force_exact") c->params.force_exact = value;
+  else if (s == "debug") c->params.debug = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
@@ -210,7 +215,9 @@ void spf_dataset_free(spf_dataset* ds) {
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
   if (ds->x) cudaFree(ds->x);
+  if (ds->xtf) cudaFree(ds->xtf);
   if (ds->xnorm) cudaFree(ds->xnorm);
+  if (ds->xres) cudaFree(ds->xres);
   delete ds;
 }
 

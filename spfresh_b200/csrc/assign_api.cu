@@ -29,15 +29,24 @@ int assign_members_as_rows(const spf_assign_result* r, uint64_t* d_out) {
   return check_launch(r->ctx, "positions_to_rows_kernel");
 }
 
-// Squared norms of all dataset rows, computed once per dataset (tensor path only).
-int dataset_norms(spf_dataset* ds) {
-  if (ds->xnorm) return SPF_OK;
+// Rounded copy, squared norms and rounding residuals of all dataset rows, computed once per
+// dataset (tensor path only).
+int dataset_prep(spf_dataset* ds) {
+  if (ds->xtf) return SPF_OK;
   spf_ctx* c = ds->ctx;
-  float* p = nullptr;
-  SPF_CUDA(cudaMalloc((void**)&p, (size_t)ds->n * sizeof(float)));
-  int rc = launch_row_sqnorm(c, ds->x, ds->ld, ds->n, p);
-  if (rc < 0) { cudaFree(p); return rc; }
-  ds->xnorm = p;
+  float *tf = nullptr, *nrm = nullptr, *res = nullptr;
+  cudaError_t e = cudaMalloc((void**)&tf, (size_t)ds->n * ds->ld * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&nrm, (size_t)ds->n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&res, (size_t)ds->n * sizeof(float));
+  int rc = e == cudaSuccess ? launch_row_prep(c, ds->x, ds->ld, nullptr, ds->n, tf, nrm, res)
+                            : fail(SPF_E_OOM, "cudaMalloc for the rounded dataset copy failed: %s", cudaGetErrorString(e));
+  if (rc < 0) {
+    cudaFree(tf); cudaFree(nrm); cudaFree(res);
+    return rc;
+  }
+  ds->xtf = tf;
+  ds->xnorm = nrm;
+  ds->xres = res;
   return SPF_OK;
 }
 
@@ -52,7 +61,7 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   *out = nullptr;
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
   if (k == 0) return fail(SPF_E_INVALID, "k must be > 0 (the reference indexes centroids[0])");
-  if (k > CAND_SLOT_MASK) return fail(SPF_E_INVALID, "k must be < 2^30");
+  if (k > (REC_G_MASK << 2)) return fail(SPF_E_INVALID, "k must be < 2^30");
   if (!point_idx && m != ds->n) return fail(SPF_E_INVALID, "point_idx == NULL requires m == n");
   if (m == 0) return fail(SPF_E_INVALID, "m must be > 0");
   if (m >= (1ull << 32)) return fail(SPF_E_INVALID, "m must be < 2^32");
@@ -92,39 +101,48 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
     P = Pg.p;
   }
 
-  const int cap = c->params.cand_cap;
-  DevBuf<uint2> cand;
-  DevBuf<uint32_t> cand_cnt;
-  SPF_TRY(cand.alloc(st, (size_t)m * cap));
-  SPF_TRY(cand_cnt.alloc(st, m * 2));
+  CandBuf cand;
+  cand.cap = c->params.cand_cap;
+  DevBuf<CandRec> cand_rec;
+  DevBuf<RowInfo> cand_info;
+  SPF_TRY(cand_rec.alloc(st, (size_t)m * cand.cap));
+  SPF_TRY(cand_info.alloc(st, m));
+  cand.rec = cand_rec.p;
+  cand.info = cand_info.p;
 
   const bool use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) &&
                       !c->params.force_exact && assign_tc_supported(c, m, k, ld);
-  DevBuf<float> xnorm_sub, cnorm, cnmax;
+  DevBuf<float> ptf_sub, xnorm_sub, xres_sub, ctf, cnorm, cres, cstat;
   const float* xnorm = nullptr;
+  const float* xres = nullptr;
   if (use_tc) {
-    if (point_idx) {
+    const float* Ptf = nullptr;
+    if (point_idx) {   // gather + round in one pass (P itself is only needed by resolve)
+      SPF_TRY(ptf_sub.alloc(st, (size_t)m * ld));
       SPF_TRY(xnorm_sub.alloc(st, m));
-      SPF_TRY(launch_row_sqnorm(c, P, ld, m, xnorm_sub.p));
-      xnorm = xnorm_sub.p;
+      SPF_TRY(xres_sub.alloc(st, m));
+      SPF_TRY(launch_row_prep(c, P, ld, nullptr, m, ptf_sub.p, xnorm_sub.p, xres_sub.p));
+      Ptf = ptf_sub.p; xnorm = xnorm_sub.p; xres = xres_sub.p;
     } else {
-      SPF_TRY(dataset_norms(ds));
-      xnorm = ds->xnorm;
+      SPF_TRY(dataset_prep(ds));
+      Ptf = ds->xtf; xnorm = ds->xnorm; xres = ds->xres;
     }
     const uint32_t kpad = round_up(k, 256);
+    SPF_TRY(ctf.alloc(st, (size_t)k * ld));
     SPF_TRY(cnorm.alloc(st, kpad));
-    SPF_TRY(cnmax.alloc(st, 1));
-    SPF_TRY(launch_row_sqnorm(c, Cg.p, ld, k, cnorm.p));
+    SPF_TRY(cres.alloc(st, k));
+    SPF_TRY(cstat.alloc(st, 2));
+    SPF_TRY(launch_row_prep(c, Cg.p, ld, nullptr, k, ctf.p, cnorm.p, cres.p));
+    SPF_TRY(launch_max2_f32(c, cnorm.p, cres.p, k, cstat.p));
     if (kpad > k) {
       pad_inf_kernel<<<(kpad - k + 255) / 256, 256, 0, st>>>(cnorm.p, k, kpad);
       SPF_TRY(check_launch(c, "pad_inf_kernel"));
     }
-    SPF_TRY(launch_max_f32(c, cnorm.p, k, cnmax.p));
     KernelTimer t(c, "assign_tc");
-    SPF_TRY(launch_assign_tc(c, P, m, Cg.p, k, ld, xnorm, cnorm.p, cnmax.p, factor, cand.p, cand_cnt.p, cap));
+    SPF_TRY(launch_assign_tc(c, Ptf, m, ctf.p, k, ld, xnorm, xres, cnorm.p, cstat.p, factor, cand));
   } else {
     KernelTimer t(c, "assign_exact");
-    SPF_TRY(launch_assign_exact(c, metric, P, m, Cg.p, k, ld, factor, cand.p, cand_cnt.p, cap, nullptr));
+    SPF_TRY(launch_assign_exact(c, metric, P, m, Cg.p, k, ld, factor, &cand, nullptr));
   }
 
   // exact centroid-centroid distances for the boundary rule `d(c_best, c_j) >= d_j` (:337-342)
@@ -132,7 +150,7 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   if (want_members && k > 1 && (int)k <= c->params.cc_matrix_max_k) {
     SPF_TRY(cc.alloc(st, (size_t)k * k));
     KernelTimer t(c, "cc_matrix");
-    SPF_TRY(launch_assign_exact(c, metric, Cg.p, k, Cg.p, k, ld, 1.0f, nullptr, nullptr, 0, cc.p));
+    SPF_TRY(launch_assign_exact(c, metric, Cg.p, k, Cg.p, k, ld, 1.0f, nullptr, cc.p));
   }
 
   spf_assign_result* r = new (std::nothrow) spf_assign_result();
@@ -149,8 +167,9 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   if (rc >= 0) {
     ResolveArgs a;
     a.metric = metric; a.P = P; a.m = m; a.C = Cg.p; a.k = k; a.ld = ld; a.factor = factor;
-    a.cand = cand.p; a.cand_cnt = cand_cnt.p; a.cap = cap; a.nseg = use_tc ? 2 : 1;
-    a.xnorm = use_tc ? xnorm : nullptr; a.d_cnmax = use_tc ? cnmax.p : nullptr;
+    a.cand = cand; a.nseg = use_tc ? 2 : 1;
+    a.xnorm = use_tc ? xnorm : nullptr; a.xres = use_tc ? xres : nullptr;
+    a.d_cstat = use_tc ? cstat.p : nullptr;
     a.cc = cc.p; a.want_members = want_members;
     a.best = best.p; a.dmin = dmin.p; a.nmem = nmem.p;
     rc = run_resolve(c, a, want_members ? &csr : nullptr);

@@ -24,7 +24,7 @@ constexpr int NTHREADS = 256;
 template <int METRIC>
 __global__ void __launch_bounds__(NTHREADS)
 assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __restrict__ C, uint32_t k,
-                    uint32_t ld, float factor, uint2* __restrict__ cand, uint32_t* __restrict__ cand_cnt,
+                    uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
                     int cap, float* __restrict__ dense) {
   __shared__ __align__(16) float Xs[2][BK][BM + PAD];
   __shared__ __align__(16) float Cs[2][BK][BN + PAD];
@@ -128,14 +128,19 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
         if (r >= m) continue;
         const float rm = __uint_as_float(rowmin[ty * 4 + i]);
         const float thr = __fmul_rn(rm, factor);
+        bool hit = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t cj = c0 + tx * 4 + j;
           const float dv = acc[i][j];
-          if (cj < k && (dv < thr || dv == rm)) {
-            const unsigned slot = atomicAdd(&rowcnt[ty * 4 + i], 1u);
-            if (slot < (unsigned)cap)
-              cand[(size_t)r * cap + slot] = make_uint2(cj | CAND_EXACT_BIT, __float_as_uint(dv));
+          hit = hit || (c0 + tx * 4 + j < k && (dv < thr || dv == rm));
+        }
+        if (hit) {   // one group record for the thread's 4 consecutive centroids (slots >= k are
+                     // ignored by index in resolve)
+          const unsigned slot = atomicAdd(&rowcnt[ty * 4 + i], 1u);
+          if (slot < (unsigned)cap) {
+            CandRec* w = cand + (size_t)r * cap + slot;
+            w->t = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            w->g = ((c0 >> 2) + tx) | REC_ALL_EXACT;
           }
         }
       }
@@ -143,15 +148,18 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   }
   if (cand != nullptr) {
     __syncthreads();
-    if (tid < BM && row0 + tid < m) cand_cnt[row0 + tid] = rowcnt[tid];
+    if (tid < BM && row0 + tid < m) info[row0 + tid] = make_uint4(rowcnt[tid], rowmin[tid], 0u, 0x7f800000u);
   }
 }
 
 }  // namespace
 
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, uint2* cand, uint32_t* cand_cnt, int cap, float* dense) {
+                        uint32_t ld, float factor, const CandBuf* cb, float* dense) {
   if (m == 0 || k == 0) return SPF_OK;
+  CandRec* cand = cb ? cb->rec : nullptr;
+  RowInfo* info = cb ? cb->info : nullptr;
+  const int cap = cb ? cb->cap : 0;
   dim3 grid((unsigned)ceil_div(m, BM)), block(NTHREADS);
   if (cand == nullptr) {   // dense matrix only: fill the machine even when m is small
     const uint64_t ctiles = ceil_div(k, BN);
@@ -161,15 +169,15 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   switch (metric) {
     case SPF_METRIC_EUCLIDEAN:
       assign_exact_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, cand_cnt, cap, dense);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense);
       break;
     case SPF_METRIC_MANHATTAN:
       assign_exact_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, cand_cnt, cap, dense);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense);
       break;
     case SPF_METRIC_CHEBYSHEV:
       assign_exact_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, cand_cnt, cap, dense);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense);
       break;
     default:
       return fail(SPF_E_INVALID, "unknown metric %d", metric);

@@ -12,6 +12,10 @@
 // reference while the O(n k d) work runs at tensor-core rate (1 pass instead of the 3 a
 // 3xTF32 split would need).
 //
+// Candidates leave the kernel as "group records" (kernels.cuh): when any of four consecutive
+// columns passes the test the thread stores all four t values with one 128-bit store, which keeps
+// the per-hit instruction cost low; resolve filters the bystanders.
+//
 // Kernel anatomy (persistent, one CTA per SM, 320 threads):
 //   warp 0     TMA producer: the 128 x ld point tile (A, stationary for a whole row block) and a
 //              4-stage ring of 256 x 32 centroid tiles (B), both SWIZZLE_128B, K-major
@@ -147,8 +151,8 @@ struct TcArgs {
   uint32_t ntiles;                  // ceil(k / 256)
   uint32_t nrowblocks;              // ceil(m / 128)
   float factor;
-  const float* xnorm; const float* cnorm; const float* cnmax;
-  uint2* cand; uint32_t* cand_cnt; int cap;
+  const float* xnorm; const float* xres; const float* cnorm; const float* cstat;
+  CandRec* rec; RowInfo* info; int cap;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -243,21 +247,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t half = (uint32_t)(warp - 2) >> 2;      // column half of every accumulator
     const uint32_t lrow = quarter * 32 + lane;
     const float INF = __int_as_float(0x7f800000);
-    const float cnmax = a.cnmax[0];
+    const float cnmax = a.cstat[0], dcmax = a.cstat[1];
     const float f1 = fmaxf(a.factor, 1.0f);
     const uint32_t segcap = (uint32_t)a.cap >> 1;
+    const uint32_t segbytes = segcap * (uint32_t)sizeof(CandRec);
     volatile unsigned long long* pub = reinterpret_cast<volatile unsigned long long*>(smem + SMEM_PUB_OFF);
     uint32_t tcount = 0;
     for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
       const uint32_t row = rb * BM + lrow;
       const bool row_ok = row < a.m;
       const float xn = row_ok ? a.xnorm[row] : 0.0f;
-      const float E = tc_err_bound(xn, cnmax, a.ld);
+      const float E = tc_err_bound(xn, row_ok ? a.xres[row] : 0.0f, cnmax, dcmax, a.ld);
+      // non-finite norms or bounds: no certified test exists, the brute-force kernels own the row
+      const bool hopeless = !(E < INF) || !(xn < INF);
       const float xnE = xn + E, EmX = E - xn;
       const float slop = 1e-6f * (xn + cnmax) + 1e-30f;
-      uint2* const seg = a.cand + (size_t)row * a.cap + (size_t)half * segcap;
-      uint2* wp = seg;                                    // write pointer into this thread's segment
-      uint32_t overflow = 0;                              // hits that did not fit
+      // this thread's segment of the row's records
+      CandRec* const seg = a.rec + ((size_t)row * a.cap + (size_t)half * segcap);
+      uint32_t wo = 0;                                    // write offset into the segment, bytes
+      uint32_t overflow = 0;                              // records that did not fit
       float tmin = INF;
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
@@ -265,60 +273,64 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
         const float4* cn4 = reinterpret_cast<const float4*>(a.cnorm + (size_t)t * BN + half * (BN / 2));
-        const uint32_t jtile = t * BN + half * (BN / 2);
+        const uint32_t gtile = (t * BN + half * (BN / 2)) >> 2;
 
         // one 32-column chunk: t = |c|^2 - 2 x.c, running minimum, candidate emission
         auto process = [&](uint32_t (&rr)[32], const float4 (&cnr)[8], int c) {
-          float v[32], q[8];
+          float4 v[8];
+          float q[8];
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 cn = cnr[i4];
-            v[i4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 0]), cn.x);
-            v[i4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 1]), cn.y);
-            v[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 2]), cn.z);
-            v[i4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(rr[i4 * 4 + 3]), cn.w);
-            q[i4] = fminf(fminf(v[i4 * 4 + 0], v[i4 * 4 + 1]), fminf(v[i4 * 4 + 2], v[i4 * 4 + 3]));
+          for (int g = 0; g < 8; ++g) {
+            const float4 cn = cnr[g];
+            v[g].x = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 0]), cn.x);
+            v[g].y = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 1]), cn.y);
+            v[g].z = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 2]), cn.z);
+            v[g].w = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 3]), cn.w);
+            q[g] = fminf(fminf(v[g].x, v[g].y), fminf(v[g].z, v[g].w));
           }
           tmin = fminf(tmin, fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])),
                                    fminf(fminf(q[4], q[5]), fminf(q[6], q[7]))));
+          float tshare = tmin;
           {   // exchange running minima with the partner half of the same row (tagged with the row
               // block: any value published for this row block is a valid upper bound of the final
               // minimum, so a stale one only makes the candidate set a little larger)
             const unsigned long long pv = pub[(half ^ 1) * BM + lrow];
-            if ((uint32_t)(pv >> 32) == rb) tmin = fminf(tmin, __uint_as_float((uint32_t)pv));
+            if ((uint32_t)(pv >> 32) == rb) tshare = fminf(tshare, __uint_as_float((uint32_t)pv));
             pub[half * BM + lrow] = ((unsigned long long)rb << 32) | __float_as_uint(tmin);
           }
           // candidate test  d < f (dmin_run + E) + E  with d = t + |x|^2
-          const float thr_t = row_ok ? fmaf(f1, tmin + xnE, EmX) + slop : -INF;
-          const uint32_t jbase = jtile + c * 32;
-          const bool room = (uint32_t)(wp - seg) + 32u <= segcap;
+          const float thr_t = row_ok ? fmaf(f1, tshare + xnE, EmX) + slop : -INF;
+          const uint32_t gbase = gtile + c * 8;
+          const bool room = wo + 8u * (uint32_t)sizeof(CandRec) <= segbytes;
           if (__all_sync(0xffffffffu, room)) {
-            // fast path: one warp vote per 4 columns, predicated stores inside
+            // fast path: one warp vote per group of 4 columns, predicated record store inside
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               if (__any_sync(0xffffffffu, q[g] < thr_t)) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float tv = v[g * 4 + e];
-                  asm volatile(
-                      "{\n\t.reg .pred p;\n\t"
-                      "setp.lt.f32 p, %1, %2;\n\t"
-                      "@p st.global.v2.b32 [%0], {%3, %4};\n\t"
-                      "@p add.u64 %0, %0, 8;\n\t}"
-                      : "+l"(wp)
-                      : "f"(tv), "f"(thr_t), "r"(jbase + g * 4 + e), "r"(__float_as_uint(tv + xn))
-                      : "memory");
-                }
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t"
+                    "setp.lt.f32 p, %2, %3;\n\t"
+                    "cvt.u64.u32 o, %0;\n\t"
+                    "add.u64 a, %1, o;\n\t"
+                    "@p st.global.v4.f32 [a], {%4, %5, %6, %7};\n\t"
+                    "@p st.global.u32 [a+16], %8;\n\t"
+                    "@p add.u32 %0, %0, 32;\n\t}"
+                    : "+r"(wo)
+                    : "l"(seg), "f"(q[g]), "f"(thr_t), "f"(v[g].x), "f"(v[g].y), "f"(v[g].z), "f"(v[g].w),
+                      "r"(gbase + g)
+                    : "memory");
               }
             }
           } else {
             // slow path: some thread of the warp is close to the end of its segment
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (v[i] < thr_t) {
-                if ((uint32_t)(wp - seg) < segcap) {
-                  *wp = make_uint2(jbase + i, __float_as_uint(v[i] + xn));
-                  ++wp;
+            for (int g = 0; g < 8; ++g) {
+              if (q[g] < thr_t) {
+                if (wo < segbytes) {
+                  CandRec* wp = reinterpret_cast<CandRec*>(reinterpret_cast<unsigned char*>(seg) + wo);
+                  wp->t = v[g];
+                  wp->g = gbase + g;
+                  wo += (uint32_t)sizeof(CandRec);
                 } else {
                   ++overflow;
                 }
@@ -355,7 +367,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) mbar_arrive(&t_empty[buf]);
         process(rbuf, cnb, 3);
       }
-      if (row_ok) a.cand_cnt[(size_t)row * 2 + half] = (uint32_t)(wp - seg) + overflow;
+      if (row_ok) {
+        uint2* const info2 = reinterpret_cast<uint2*>(a.info + row) + half;
+        *info2 = make_uint2(hopeless ? segcap + 1u : wo / (uint32_t)sizeof(CandRec) + overflow, __float_as_uint(tmin));
+      }
     }
   }
 
@@ -392,19 +407,19 @@ bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) 
          (int64_t)k >= c->params.tc_min_k && (int64_t)m >= c->params.tc_min_m;
 }
 
-int launch_assign_tc(spf_ctx* c, const float* P, uint64_t m, const float* C, uint32_t k, uint32_t ld,
-                     const float* xnorm, const float* cnorm_pad, const float* d_cnmax, float factor,
-                     uint2* cand, uint32_t* cand_cnt, int cap) {
+int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
+                     const float* xnorm, const float* xres, const float* cnorm_pad, const float* d_cstat,
+                     float factor, const CandBuf& cand) {
   CUtensorMap map_a, map_b;
-  SPF_TRY(make_map(c, &map_a, P, m, ld, BM));
-  SPF_TRY(make_map(c, &map_b, C, k, ld, BN));
+  SPF_TRY(make_map(c, &map_a, Ptf, m, ld, BM));
+  SPF_TRY(make_map(c, &map_b, Ctf, k, ld, BN));
   TcArgs a;
   a.m = (uint32_t)m; a.k = k; a.ld = ld; a.kb = (ld + BK - 1) / BK;
   a.ntiles = (k + BN - 1) / BN;
   a.nrowblocks = (uint32_t)ceil_div(m, BM);
   a.factor = factor;
-  a.xnorm = xnorm; a.cnorm = cnorm_pad; a.cnmax = d_cnmax;
-  a.cand = cand; a.cand_cnt = cand_cnt; a.cap = cap;
+  a.xnorm = xnorm; a.xres = xres; a.cnorm = cnorm_pad; a.cstat = d_cstat;
+  a.rec = cand.rec; a.info = cand.info; a.cap = cand.cap;
   SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count;
   assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, a);

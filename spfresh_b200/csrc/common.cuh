@@ -39,13 +39,15 @@ int fail(int code, const char* fmt, ...);
 // context
 // ---------------------------------------------------------------------------------------------
 struct Params {
-  int cand_cap = 256;        // candidate slots per point kept by the assign kernels
+  int cand_cap = 128;        // candidate group records per point kept by the assign kernels
+  int short_cap = 64;        // short-list entries per point kept by resolve (power of two, <= 64)
   int force_exact = 0;       // 1: never use the tcgen05 candidate GEMM
   int tc_min_k = 64;         // use the tensor path only when k >= this
   int tc_min_m = 1024;       // ... and m >= this
   int kmpp_exact_sum = 1;    // 1: sequential f32 sum (bit-parity with the reference)
   int cc_matrix_max_k = 16384;  // precompute the k x k centroid-centroid matrix up to this k
   int scan_threads = 256;
+  int debug = 0;             // development switches (timing experiments only)
 };
 
 }  // namespace spf
@@ -60,6 +62,7 @@ struct spf_ctx {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::map<std::string, float> kernel_ms;
   uint64_t launches = 0;
+  uint32_t last_overflow_rows = 0;   // rows the last assign resolved through the dense fallback
   spf::Params params;
   void* tma_encode = nullptr;  // cuTensorMapEncodeTiled, resolved at context creation
 };
@@ -67,7 +70,10 @@ struct spf_ctx {
 struct spf_dataset {
   spf_ctx* ctx = nullptr;
   float* x = nullptr;     // n x ld, rows zero-padded to ld (multiple of 4 floats)
-  float* xnorm = nullptr; // lazily computed squared norms (tensor path)
+  // tensor path only, made lazily once per dataset (row_prep_kernel):
+  float* xtf = nullptr;   // n x ld rows rounded to TF32 (the GEMM's A operand)
+  float* xnorm = nullptr; // squared norms |x|^2
+  float* xres = nullptr;  // rounding residual norms |x - xtf|
   uint64_t n = 0;
   uint32_t d = 0, ld = 0;
 };
@@ -117,21 +123,29 @@ struct DevBuf {
   T* take() { T* q = p; p = nullptr; return q; }
 };
 
-// Brackets a named kernel with events when profiling is on (adds two syncs: only for bench).
+// Brackets a named kernel (or group of kernels) with its own pair of events when profiling is
+// on, so timers may nest (adds a sync per timer: only for bench / profiling runs).
 struct KernelTimer {
   spf_ctx* c;
   const char* name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   KernelTimer(spf_ctx* ctx, const char* nm) : c(ctx), name(nm) {
-    if (c->profiling) cudaEventRecord(c->ev[0], c->stream);
+    if (c->profiling) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c->stream);
+    }
   }
   ~KernelTimer() {
-    if (c->profiling) {
-      cudaEventRecord(c->ev[1], c->stream);
-      cudaEventSynchronize(c->ev[1]);
+    if (c->profiling && e0 && e1) {
+      cudaEventRecord(e1, c->stream);
+      cudaEventSynchronize(e1);
       float ms = 0;
-      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      cudaEventElapsedTime(&ms, e0, e1);
       c->kernel_ms[name] = ms;
     }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
   }
 };
 

@@ -4,24 +4,62 @@
 
 namespace spf {
 
-// Candidate record written by the assign kernels: x = centroid slot (bit 31 set once the
-// distance has been recomputed exactly), y = distance bits.
-static constexpr uint32_t CAND_EXACT_BIT = 0x80000000u;
-static constexpr uint32_t CAND_MEMBER_BIT = 0x40000000u;
-static constexpr uint32_t CAND_SLOT_MASK = 0x3fffffffu;
+// Candidate records written by the assign kernels.  A record (32 bytes, one HBM sector) covers the
+// four consecutive centroid slots 4*g .. 4*g+3 of one point ("group record"): `t` holds one value
+// per slot, `g` holds the group index (bits 0-27) and one "exact" flag per slot (bits 28-31).
+//   exact flag set   : the value is the exact direct-form distance d(x, c)
+//   exact flag clear : the value is t = |c|^2 - 2 x.c from the TF32 GEMM; d ~ t + |x|^2 within E
+// Slots >= k carry no candidate (they are skipped by index).  A point owns `cap` records, split
+// into `nseg` segments (one per writer thread of the producing kernel).  After resolve the front
+// of the point's record area is reused for its member list (uint32 centroid slots).
+struct __align__(16) CandRec {
+  float4 t;
+  uint32_t g;
+  uint32_t pad[3];   // never written
+};
+static constexpr uint32_t REC_G_MASK = 0x0fffffffu;
+static constexpr int REC_EXACT_SHIFT = 28;
+static constexpr uint32_t REC_ALL_EXACT = 0xf0000000u;
 static constexpr uint32_t NMEM_OVERFLOW_BIT = 0x80000000u;
+// Per point: x = records in segment 0 (a value > segment capacity marks an overflow), y = bits of
+// the smallest t the producer saw in segment 0's columns, z / w = the same for segment 1.
+typedef uint4 RowInfo;
 
-// Certified bound on |d_tf32 - d_ref| for the tensor path, where d_tf32 = |x|^2 - 2 x.c + |c|^2
-// with the dot product taken on TF32 operands and d_ref is the reference's sequential f32 sum.
-//  * TF32 operands are off by < 2^-10 relative each, so every product by < 2^-9 (1 + 2^-11);
-//    Cauchy-Schwarz bounds the dot-product error by 2^-9 |x||c| and the distance error by twice
-//    that; 10 % head-room covers the fp32 accumulation inside the tensor core.
-//  * d_ref itself is within (ld + 2) 2^-24 D of the real distance D <= 2 (|x|^2 + |c|^2); the
-//    fp32 norms and epilogue adds contribute a few 2^-24 (|x|^2 + |c|^2) more.
+// Certified bound on |d_tf32 - d_ref| for the tensor path.  d_tf32 = |x|^2 - 2 x'.c' + |c|^2 where
+// x' = rn_tf32(x), c' = rn_tf32(c) are the operands the GEMM reads (rounded copies made by
+// row_prep_kernel, so the hardware's own treatment of the low mantissa bits never matters) and
+// d_ref is the reference's sequential f32 sum.
+//  * operands: x.c - x'.c' = dx.c + x'.dc with dx = x - x', dc = c - c'; by Cauchy-Schwarz
+//    |.| <= |dx| |c| + (|x| + |dx|) |dc|.  |dx| is known per point (xres), |c| and |dc| are
+//    bounded by their maxima over the centroids.  The distance error is twice that.
+//  * products of two TF32 values are exact in fp32; the fp32 accumulation inside the tensor core
+//    (16 MMA steps of 8 products, alignment truncation included) stays below
+//    (ld + 16) 2^-23 |x||c| for the dot product, i.e. (ld + 16) 2^-23 (|x|^2 + |c|^2) for the distance.
+//  * d_ref itself is within (ld + 2) 2^-24 D of the real distance, D <= 2 (|x|^2 + |c|^2); the
+//    fp32 norms and the epilogue adds contribute a few 2^-24 (|x|^2 + |c|^2) more.
 // Used identically by the GEMM epilogue (candidate slack) and by resolve (decision bands).
-__host__ __device__ inline float tc_err_bound(float xn, float cnmax, uint32_t ld) {
-  return 1.1f * 0.00390625f * sqrtf(xn * cnmax) + (float)(ld + 16) * 1.1920929e-7f * (xn + cnmax);
+__host__ __device__ inline float tc_err_bound(float xn, float xres, float cnmax, float dcmax, uint32_t ld) {
+  const float sx = sqrtf(xn), sc = sqrtf(cnmax);
+  const float op = 2.0f * (xres * sc + (sx + xres) * dcmax);
+  return 1.01f * op + 3.0f * (float)(ld + 16) * 1.1920929e-7f * (xn + cnmax);
 }
+
+// Candidate scratch of one assign call (device).
+struct CandBuf {
+  CandRec* rec = nullptr;    // m * cap records
+  RowInfo* info = nullptr;   // m
+  int cap = 0;               // records per point (all segments together)
+};
+
+// Rounded operands + norms for the tensor path: for every row r of `rows`
+//   tf[r]    = rn_tf32(rows[r])              (cvt.rna.tf32.f32, element-wise)
+//   norm[r]  = |rows[r]|^2                   (fp32, any order)
+//   res[r]   = |rows[r] - tf[r]|             (fp32)
+// idx == NULL: rows 0..m-1 of src; otherwise row idx[r] of src (gather fused in).
+int launch_row_prep(spf_ctx* c, const float* src, uint32_t ld, const uint64_t* d_idx, uint64_t m,
+                    float* tf, float* norm, float* res);
+// out2[0] = max(a[0..n)), out2[1] = max(b[0..n))   (values >= 0)
+int launch_max2_f32(spf_ctx* c, const float* a, const float* b, uint64_t n, float* out2);
 
 // ---- support.cu --------------------------------------------------------------------------
 int launch_gather_rows(spf_ctx* c, const float* src, uint32_t ld, const uint64_t* d_idx, uint64_t m,
@@ -39,27 +77,29 @@ int launch_check_rows(spf_ctx* c, const uint64_t* d_idx, uint64_t m, uint64_t n,
 
 // ---- assign_exact.cu ----------------------------------------------------------------------
 // CUDA-core direct-form kernel: every distance of the m x k problem, exact.  Emits boundary
-// candidates (cand != NULL) and/or the dense m x k matrix (dense != NULL).
+// candidates (cand != NULL, one segment, all records exact) and/or the dense m x k matrix.
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, uint2* cand, uint32_t* cand_cnt, int cap, float* dense);
+                        uint32_t ld, float factor, const CandBuf* cand, float* dense);
 
 // ---- assign_tc.cu -------------------------------------------------------------------------
 // tcgen05 (TF32) candidate GEMM for squared-Euclidean: approximate distances with a certified
-// error bound, candidates only.  cnorm_pad has round_up(k,256) entries (+inf padding).
+// error bound, candidates only (two segments per point).  Ptf / Ctf are the rounded operands;
+// cnorm_pad has round_up(k,256) entries (+inf padding); cstat = {max |c|^2, max |c - c'|}.
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld);
-int launch_assign_tc(spf_ctx* c, const float* P, uint64_t m, const float* C, uint32_t k, uint32_t ld,
-                     const float* xnorm, const float* cnorm_pad, const float* d_cnmax, float factor,
-                     uint2* cand, uint32_t* cand_cnt, int cap);
+int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
+                     const float* xnorm, const float* xres, const float* cnorm_pad, const float* d_cstat,
+                     float factor, const CandBuf& cand);
 
 // ---- resolve.cu ---------------------------------------------------------------------------
 struct ResolveArgs {
   int metric;
-  const float* P; uint64_t m; const float* C; uint32_t k; uint32_t ld;
+  const float* P; uint64_t m; const float* C; uint32_t k; uint32_t ld;   // exact (unrounded) rows
   float factor;
-  uint2* cand; uint32_t* cand_cnt; int cap;
-  int nseg;                // segments per row buffer: 1 (exact kernel) or 2 (tensor kernel)
+  CandBuf cand;
+  int nseg;                // segments per point: 1 (exact kernel) or 2 (tensor kernel)
   const float* xnorm;      // NULL on the exact path (error bound 0)
-  const float* d_cnmax;    // device scalar, tensor path only
+  const float* xres;       // tensor path only
+  const float* d_cstat;    // device {max |c|^2, max |c - c'|}, tensor path only
   const float* cc;         // k x k exact centroid-centroid distances or NULL (computed on demand)
   bool want_members;
   // outputs
@@ -75,7 +115,7 @@ struct CsrOut {
 int run_resolve(spf_ctx* c, const ResolveArgs& a, CsrOut* csr);
 
 // ---- assign_api.cu ------------------------------------------------------------------------
-int dataset_norms(spf_dataset* ds);
+int dataset_prep(spf_dataset* ds);   // rounded copy + norms of all rows, once per dataset
 int assign_members_as_rows(const spf_assign_result* r, uint64_t* d_out);   // positions → dataset rows
 
 }  // namespace spf

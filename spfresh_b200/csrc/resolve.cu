@@ -9,8 +9,19 @@
 // Candidates come from the exact kernel (distances already bit-exact) or from the tcgen05 TF32
 // GEMM (approximate, with a certified error bound E per point).  Every comparison above is
 // decided on exact values: an approximate candidate is only accepted or rejected without
-// recomputation when its whole interval [d-E, d+E] lies on one side of the test; otherwise the
-// lane recomputes the direct-form distance (same rounding sequence as the reference).
+// recomputation when its whole interval [d-E, d+E] lies on one side of the test; otherwise its
+// direct-form distance is recomputed (same rounding sequence as the reference).
+//
+// Three flat kernels (none of them serialises a warp on one point's dependent chain):
+//   classify   warp per point, one sweep over its group records: finds the elements that can be the
+//              argmin ("band": within 2E of the producer's approximate minimum), bounds the
+//              threshold from the band, and sorts every other element into certain member /
+//              certainly not / needs an exact value; survivors go to a short list (16 B entries)
+//   exact_eval gathers all short-list entries that need an exact distance and evaluates them 32 at
+//              a time per warp, one pair per lane (terms staged in parallel, one sequential chain
+//              per lane) — the only place distances are recomputed
+//   finalize   warp per point, lane per short-list entry: exact (dmin, best), the remaining tests
+//              on exact values, member list
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -22,163 +33,493 @@ namespace spf {
 
 namespace {
 
+// Short-list entry (classify → exact_eval → finalize).
+struct __align__(16) ShortEnt {
+  uint32_t j;       // centroid slot
+  float v;          // distance: exact when SE_EXACT, else approximate (within E)
+  float cc;         // d(c_best, c_j) when the kind is SE_TEST_CC
+  uint32_t flags;
+};
+constexpr uint32_t SE_EXACT = 1u;       // v is the exact direct-form distance
+constexpr uint32_t SE_NEED_EVAL = 2u;   // exact_eval must replace v
+constexpr uint32_t SE_KIND_MASK = 3u << 2;
+constexpr uint32_t SE_BAND = 0u << 2;       // can be the argmin (always exact after exact_eval)
+constexpr uint32_t SE_MEMBER = 1u << 2;     // certain boundary member whatever the exact values are
+constexpr uint32_t SE_TEST_CC = 2u << 2;    // d < thr and cc >= d still to be decided; cc stored
+constexpr uint32_t SE_TEST_NOCC = 3u << 2;  // same, best was not known yet: cc fetched by finalize
+
 struct ResolveDev {
   const float* P; uint32_t m; const float* C; uint32_t k; uint32_t ld;
   float factor;
-  uint2* cand; const uint32_t* cand_cnt; int cap; int nseg;
-  const float* xnorm; const float* cnmax; const float* cc;
+  CandRec* rec; const RowInfo* info; int cap; int nseg;
+  const float* xnorm; const float* xres; const float* cstat; const float* cc;
   uint32_t* best; float* dmin; uint32_t* nmem;
   uint32_t* ovf_rows; uint32_t* ovf_count;
   int want_members;
+  ShortEnt* sl; uint32_t* sl_cnt; int sl_shift;   // short list: 1 << sl_shift (<= 64) entries per point
+  // work list of exact evaluations: (short-list index, centroid slot) pairs appended by classify
+  uint2* work; uint32_t* work_count; uint32_t work_cap;
+  int debug;
 };
 
 __device__ __forceinline__ bool lex_less(float d1, uint32_t j1, float d2, uint32_t j2) {
   return d1 < d2 || (d1 == d2 && j1 < j2);
 }
 
-constexpr int RS_WARPS = 8;           // warps per CTA of the resolve kernel
-constexpr int RS_CHUNK = 128;         // dimensions staged per step (one float4 per lane)
-constexpr int RS_PAIRS = 4;           // exact distances evaluated per cooperative round
-constexpr int RS_TB_STRIDE = RS_CHUNK + 4;
+constexpr int RS_WARPS = 8;           // warps per CTA of classify / finalize
+constexpr int RS_EL = 8;              // candidate elements a lane holds per sweep step (2 records)
+constexpr int EV_WARPS = 2;           // warps per CTA of exact_eval (33 KB of staging each)
+constexpr int EV_CHUNK = 128;         // dimensions staged per step (one 16-byte cp.async per lane and row)
+constexpr int EV_STRIDE = EV_CHUNK + 4;
+constexpr int EV_QUEUE = 64;          // queued pairs per warp (32 are evaluated at a time)
 
-struct ResolveSmem {
-  float xs[RS_CHUNK];
-  float tb[RS_PAIRS][RS_TB_STRIDE];
-};
-
-// Exact distances d(x, C[j]) for the lanes with `want` set (their centroid slot in `j`), four at
-// a time: the warp stages 128 dimensions of x and of the four centroid rows in shared memory
-// with coalesced float4 loads, then lanes 0..3 each walk one pair in dimension order, so every
-// value is the reference's sequential f32 sum (src/distances/distance.rs:16-43).  Returns the
-// distance to the owning lane (unchanged `dv` for lanes without `want`).
+// The element term and the running combination of the three metrics, split so that the terms
+// of one pair can be produced by 32 lanes in parallel while ONE lane folds them in dimension
+// order: acc = comb(acc, term(a_i, b_i)) for i = 0, 1, ... is exactly the reference's sequential
+// f32 chain (src/distances/distance.rs:16-43; un-fused sub / mul / add).
 template <int METRIC>
-__device__ __forceinline__ float coop_exact(bool want, uint32_t j, float dv, const float* __restrict__ x,
-                                            const float* __restrict__ C, uint32_t ld, ResolveSmem& sm, int lane,
-                                            const float4* x0 = nullptr) {
-  unsigned pending = __ballot_sync(0xffffffffu, want);
-  while (pending) {
-    int owner[RS_PAIRS];
-    uint32_t jj[RS_PAIRS];
-    int np = 0;
-#pragma unroll
-    for (int p = 0; p < RS_PAIRS; ++p) {
-      owner[p] = -1;
-      jj[p] = 0;
-      if (pending) {
-        owner[p] = __ffs(pending) - 1;
-        pending &= pending - 1;
-        np = p + 1;
-      }
-      jj[p] = __shfl_sync(0xffffffffu, j, owner[p] < 0 ? 0 : owner[p]);
-    }
-    float acc = 0.0f;
-    for (uint32_t c0 = 0; c0 < ld; c0 += RS_CHUNK) {
-      const uint32_t col = c0 + lane * 4;
-      const bool ok = col < ld;                      // ld is a multiple of 4
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 xv = (x0 != nullptr && c0 == 0) ? *x0 : (ok ? __ldg(reinterpret_cast<const float4*>(x + col)) : z);
-      float4 cv[RS_PAIRS];
-#pragma unroll
-      for (int p = 0; p < RS_PAIRS; ++p)
-        cv[p] = (ok && p < np) ? __ldg(reinterpret_cast<const float4*>(C + (size_t)jj[p] * ld + col)) : z;
-      __syncwarp();
-      *reinterpret_cast<float4*>(&sm.xs[lane * 4]) = xv;
-#pragma unroll
-      for (int p = 0; p < RS_PAIRS; ++p) *reinterpret_cast<float4*>(&sm.tb[p][lane * 4]) = cv[p];
-      __syncwarp();
-      if (lane < np) {
-        const int nn = (ld - c0) < (uint32_t)RS_CHUNK ? (int)(ld - c0) : RS_CHUNK;
-#pragma unroll 8
-        for (int i = 0; i < nn; ++i) acc = dist_step<METRIC>(acc, sm.xs[i], sm.tb[lane][i]);
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < RS_PAIRS; ++p) {
-      const float r = __shfl_sync(0xffffffffu, acc, p);
-      if (lane == owner[p]) dv = r;
-    }
-  }
-  return dv;
+__device__ __forceinline__ float dist_term(float a, float b) {
+  const float df = __fsub_rn(a, b);
+  return METRIC == SPF_METRIC_EUCLIDEAN ? __fmul_rn(df, df) : fabsf(df);
+}
+template <int METRIC>
+__device__ __forceinline__ float dist_comb(float acc, float t) {
+  return METRIC == SPF_METRIC_CHEBYSHEV ? fmaxf(acc, t) : __fadd_rn(acc, t);
 }
 
-// One warp per listed point; the whole of hierarchical.rs:317-346 for that point in one pass
-// over its candidate slots: approximate minimum → exact distances for everything within 2E of
-// it → exact (dmin, best) → boundary tests, recomputing exactly only where the approximate
-// value cannot certify the outcome → members compacted to the front of the row's buffer.
-template <int METRIC>
-__global__ void __launch_bounds__(RS_WARPS * 32, 3) resolve_kernel(ResolveDev a) {
-  __shared__ ResolveSmem smem[RS_WARPS];
+// ---------------------------------------------------------------------------------------------
+// classify
+// ---------------------------------------------------------------------------------------------
+constexpr int CLS_STAGE = 96;         // records a point may keep after the coarse filter
+
+constexpr int CLS_QUEUE = 160;        // pending exact evaluations per warp (flushed 32 at a time)
+
+struct ClsSmem {
+  float4 t[CLS_STAGE];
+  uint32_t g[CLS_STAGE];
+  uint2 q[CLS_QUEUE];
+};
+struct El4 { uint32_t jb; float v[4]; uint32_t exact, valid; };
+
+__global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
+  __shared__ ClsSmem smem[RS_WARPS];
+  ClsSmem& sm = smem[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
-  ResolveSmem& sm = smem[threadIdx.x >> 5];
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const float INF = __int_as_float(0x7f800000);
   const uint32_t segcap = (uint32_t)a.cap / (uint32_t)a.nseg;
-  // Everything a row needs first (its counts, the first 32 slots of each segment, 128 dimensions
-  // of the point) is fetched one row ahead, so the dependent HBM round trips of row r+1 overlap
-  // the work on row r.  Slots past the live count are read speculatively and ignored.
-  struct Pre { uint32_t cnt0, cnt1; uint2 e0, e1; float4 xv; };
-  auto prefetch = [&](uint32_t r) {
-    Pre p;
-    p.cnt0 = p.cnt1 = 0;
-    p.e0 = p.e1 = make_uint2(0u, 0u);
-    p.xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < a.m) {
-      p.cnt0 = a.cand_cnt[(size_t)r * a.nseg];
-      if (a.nseg > 1) p.cnt1 = a.cand_cnt[(size_t)r * a.nseg + 1];
-      const uint2* cr = a.cand + (size_t)r * a.cap;
-      if ((uint32_t)lane < segcap) {
-        p.e0 = cr[lane];
-        if (a.nseg > 1) p.e1 = cr[segcap + lane];
+  const uint32_t slcap = 1u << a.sl_shift;
+  const bool approx = a.xnorm != nullptr;
+  const float cnmax = approx ? a.cstat[0] : 0.0f, dcmax = approx ? a.cstat[1] : 0.0f;
+
+  struct Rec2 { float4 t0, t1; uint32_t g0, g1; };
+  auto load_recs = [&](const CandRec* cr, uint32_t i, uint32_t n0, uint32_t n1) {
+    Rec2 rc;
+    rc.t0 = rc.t1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    rc.g0 = rc.g1 = 0;
+    if (i < n0 && i < segcap) { rc.t0 = cr[i].t; rc.g0 = cr[i].g; }
+    if (i < n1 && i < segcap) { rc.t1 = cr[segcap + i].t; rc.g1 = cr[segcap + i].g; }
+    return rc;
+  };
+  // Two-level prefetch: a row's info word and norms are fetched two rows ahead, its first 32
+  // records of each segment (only the live ones, the counts are known by then) one row ahead, so
+  // the dependent HBM round trips of the next rows overlap the work on the current one.
+  struct Pre1 { RowInfo info; float xn, xr; };
+  auto prefetch1 = [&](uint32_t rr) {
+    Pre1 p;
+    p.info = make_uint4(0u, 0u, 0u, 0u);
+    p.xn = p.xr = 0.f;
+    if (rr < a.m) {
+      p.info = a.info[rr];
+      if (approx) { p.xn = a.xnorm[rr]; p.xr = a.xres[rr]; }
+    }
+    return p;
+  };
+  auto prefetch2 = [&](uint32_t rr, const Pre1& p1) {
+    if (rr < a.m)
+      return load_recs(a.rec + (size_t)rr * a.cap, (uint32_t)lane, p1.info.x, a.nseg > 1 ? p1.info.z : 0u);
+    return Rec2{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), 0u, 0u};
+  };
+  uint32_t nq = 0;                                   // queued exact evaluations (warp-uniform)
+  // moves 32 queued items (or all of them when `all`) to the global work list
+  auto flush_queue = [&](bool all) {
+    while (nq >= 32u || (all && nq > 0)) {
+      const uint32_t take = nq < 32u ? nq : 32u;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(a.work_count, take);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      // items that do not fit stay flagged SE_NEED_EVAL: finalize recomputes those itself
+      if ((uint32_t)lane < take && base + lane < a.work_cap) a.work[base + lane] = sm.q[nq - take + lane];
+      nq -= take;
+      __syncwarp();
+    }
+  };
+  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  Pre1 cur1 = prefetch1(r);
+  Pre1 nx1 = prefetch1(r + warps_total);
+  Rec2 cur_rc = prefetch2(r, cur1);
+  for (; r < a.m; r += warps_total) {
+    struct { RowInfo info; Rec2 rc; float xn, xr; } cur;
+    cur.info = cur1.info; cur.xn = cur1.xn; cur.xr = cur1.xr; cur.rc = cur_rc;
+    cur1 = nx1;
+    nx1 = prefetch1(r + 2 * warps_total);
+    cur_rc = prefetch2(r + warps_total, cur1);
+    const uint32_t cnt0 = cur.info.x, cnt1 = a.nseg > 1 ? cur.info.z : 0u;
+    bool overflow = cnt0 > segcap || cnt1 > segcap;   // the dense fallback owns such rows
+    const uint32_t steps = overflow ? 0u : (max(cnt0, cnt1) + 31u) >> 5;
+    const CandRec* cr = a.rec + (size_t)r * a.cap;
+    const float xn = cur.xn;
+    const float E = approx ? tc_err_bound(xn, cur.xr, cnmax, dcmax, a.ld) : 0.0f;
+    // smallest distance the producer saw: approximate on the tensor path (the true minimum is
+    // within E of it, so only elements within 2E can be the argmin), exact otherwise
+    const float tmin = a.nseg > 1 ? fminf(__uint_as_float(cur.info.y), __uint_as_float(cur.info.w))
+                                  : __uint_as_float(cur.info.y);
+    const float ma = approx ? __fadd_rn(tmin, xn) : tmin;
+    const float band = __fadd_ru(ma, 2.0f * E);
+    // loosest possible threshold: thr = fl(dmin * factor) with dmin <= ma + E
+    const float thi_loose = a.want_members ? __fmul_ru(__fadd_ru(ma, E), a.factor) : 0.0f;
+    // an element matters only if it is in the band or its interval reaches below the threshold
+    const float vbound = fmaxf(band, __fadd_ru(thi_loose, E));
+
+    // ---- level A: coarse filter on the group minimum, survivors staged in shared memory ---------
+    uint32_t nrec = 0;
+    __syncwarp();
+    for (uint32_t st = 0; st < steps; ++st) {
+      const uint32_t i = st * 32 + lane;
+      const Rec2 rc = st == 0 ? cur.rc : load_recs(cr, i, cnt0, cnt1);
+      const float g0 = fminf(fminf(rc.t0.x, rc.t0.y), fminf(rc.t0.z, rc.t0.w));
+      const float g1 = fminf(fminf(rc.t1.x, rc.t1.y), fminf(rc.t1.z, rc.t1.w));
+      // (records are either all exact or all approximate per producer)
+      const bool k0 = i < cnt0 && (approx ? __fadd_rn(g0, xn) : g0) <= vbound;
+      const bool k1 = i < cnt1 && (approx ? __fadd_rn(g1, xn) : g1) <= vbound;
+      const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+      const unsigned below = (1u << lane) - 1u;
+      const uint32_t p0 = nrec + (uint32_t)__popc(b0 & below);
+      const uint32_t p1 = nrec + (uint32_t)__popc(b0) + (uint32_t)__popc(b1 & below);
+      if (k0 && p0 < (uint32_t)CLS_STAGE) { sm.t[p0] = rc.t0; sm.g[p0] = rc.g0; }
+      if (k1 && p1 < (uint32_t)CLS_STAGE) { sm.t[p1] = rc.t1; sm.g[p1] = rc.g1; }
+      nrec += (uint32_t)__popc(b0) + (uint32_t)__popc(b1);
+    }
+    __syncwarp();
+    if (nrec > (uint32_t)CLS_STAGE) { overflow = true; nrec = 0; }
+    const uint32_t steps2 = (nrec + 31u) >> 5;
+
+    // Unpacks a staged record into 4 elements: centroid slot, distance (approximate ones shifted
+    // by |x|^2), exact flag, valid flag.
+    auto unpack = [&](uint32_t i) {
+      El4 e;
+      e.jb = 0; e.exact = 0; e.valid = 0;
+      e.v[0] = e.v[1] = e.v[2] = e.v[3] = 0.f;
+      if (i < nrec) {
+        const float4 t = sm.t[i];
+        const uint32_t g = sm.g[i];
+        e.jb = (g & REC_G_MASK) << 2;
+        e.exact = g >> REC_EXACT_SHIFT;
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          e.valid |= (e.jb + (uint32_t)q < a.k) ? (1u << q) : 0u;
+          e.v[q] = ((e.exact >> q) & 1u) ? tv[q] : __fadd_rn(tv[q], xn);
+        }
       }
-      if ((uint32_t)lane * 4 < a.ld) p.xv = __ldg(reinterpret_cast<const float4*>(a.P + (size_t)r * a.ld) + lane);
+      return e;
+    };
+    auto band_mask = [&](const El4& e) {
+      uint32_t inb = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) inb |= (((e.valid >> q) & 1u) && e.v[q] <= band) ? (1u << q) : 0u;
+      return inb;
+    };
+
+    // ---- sweep 1: the band: how many elements, are they all exact, which one ----------------------
+    uint32_t n_in = 0, n_apx = 0, j_any = 0;
+    float bd = INF;
+    uint32_t bj = 0xffffffffu;
+    El4 e0 = unpack((uint32_t)lane);               // step 0 stays in registers for sweep 2
+    for (uint32_t st = 0; st < steps2; ++st) {
+      const El4 e = st == 0 ? e0 : unpack(st * 32 + lane);
+      const uint32_t inb = band_mask(e);
+      n_in += (uint32_t)__popc(inb);
+      n_apx += (uint32_t)__popc(inb & ~e.exact);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if ((inb >> q) & 1u) {
+          j_any = e.jb + (uint32_t)q;
+          if (((e.exact >> q) & 1u) && lex_less(e.v[q], e.jb + (uint32_t)q, bd, bj)) { bd = e.v[q]; bj = e.jb + (uint32_t)q; }
+        }
+      }
+    }
+    n_in = __reduce_add_sync(0xffffffffu, n_in);
+    n_apx = __reduce_add_sync(0xffffffffu, n_apx);
+    bool best_known, bd_known;
+    if (n_apx == 0) {          // every band element is exact (always so on the exact path)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (lex_less(od, oj, bd, bj)) { bd = od; bj = oj; }
+      }
+      if (!(bd < INF)) { bd = INF; bj = 0; }   // fold identity (0, +inf): nothing was < inf
+      best_known = bd_known = true;
+    } else if (n_in == 1) {    // a single approximate element can be the argmin: it is the best
+      bj = __reduce_max_sync(0xffffffffu, j_any);
+      best_known = true;
+      bd_known = false;
+    } else {
+      best_known = bd_known = false;
+    }
+    // bounds of thr = fl(dmin * factor): dmin lies in [max(ma - E, 0), ma + E]
+    const float tlo = bd_known ? __fmul_rn(bd, a.factor) : __fmul_rd(fmaxf(__fadd_rd(ma, -E), 0.0f), a.factor);
+    const float thi = bd_known ? tlo : thi_loose;
+    const float* ccrow = (best_known && a.cc) ? a.cc + (size_t)bj * a.k : nullptr;
+
+    // ---- sweep 2: classification, survivors appended to the short list --------------------------------
+    ShortEnt* sl = a.sl + ((size_t)r << a.sl_shift);
+    uint32_t out = 0;
+    for (uint32_t st = 0; st < steps2; ++st) {
+      const El4 e = st == 0 ? e0 : unpack(st * 32 + lane);
+      const uint32_t inb = band_mask(e);
+      uint32_t keep = inb, need_cc = 0, t1c = 0;
+      float ccv[4], lo[4], hi[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool ex = (e.exact >> q) & 1u;
+        lo[q] = ex ? e.v[q] : __fadd_rd(e.v[q], -E);
+        hi[q] = ex ? e.v[q] : __fadd_ru(e.v[q], E);
+        ccv[q] = 0.f;
+        if (a.want_members && (((e.valid & ~inb) >> q) & 1u) && lo[q] < thi) {   // else certainly d >= thr
+          need_cc |= 1u << q;
+          if (hi[q] < tlo) t1c |= 1u << q;          // certainly d < thr
+        }
+      }
+      if (ccrow != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if ((need_cc >> q) & 1u) ccv[q] = ccrow[e.jb + (uint32_t)q];
+      }
+      uint32_t fl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool ex = (e.exact >> q) & 1u;
+        fl[q] = SE_BAND | (ex ? SE_EXACT : SE_NEED_EVAL);
+        if ((need_cc >> q) & 1u) {
+          if (ccrow != nullptr) {
+            if (ccv[q] >= lo[q]) {                  // otherwise certainly cc < d → not a member
+              keep |= 1u << q;
+              const bool certain = ((t1c >> q) & 1u) && ccv[q] >= hi[q];
+              fl[q] = certain ? (SE_MEMBER | (ex ? SE_EXACT : 0u))
+                              : (SE_TEST_CC | (ex ? SE_EXACT : SE_NEED_EVAL));
+            }
+          } else {                                  // best (or the cc matrix) not available here
+            keep |= 1u << q;
+            fl[q] = SE_TEST_NOCC | (ex ? SE_EXACT : (((t1c >> q) & 1u) ? 0u : SE_NEED_EVAL));
+          }
+        }
+      }
+      // append: exclusive prefix of the per-lane survivor counts
+      const uint32_t mine = (uint32_t)__popc(keep);
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      uint32_t pos = out + incl - mine;
+      out += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if ((keep >> q) & 1u) {
+          if (pos < slcap) {
+            ShortEnt w;
+            w.j = e.jb + (uint32_t)q;
+            w.v = e.v[q];
+            w.cc = ccv[q];
+            w.flags = fl[q];
+            sl[pos] = w;
+          }
+          ++pos;
+        }
+      }
+      // queue the entries that need an exact value (warp-aggregated; at most 4 per lane and step)
+      uint32_t nd = 0;
+      {
+        uint32_t p2 = out - __shfl_sync(0xffffffffu, incl, 31) + incl - mine;   // this lane's first position
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if ((keep >> q) & 1u) {
+            if (p2 < slcap && (fl[q] & SE_NEED_EVAL)) nd |= 1u << q;
+            ++p2;
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, nd != 0)) {
+        const uint32_t nmine = (uint32_t)__popc(nd);
+        uint32_t ni = nmine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, ni, o);
+          if (lane >= o) ni += up;
+        }
+        const uint32_t ntot = __shfl_sync(0xffffffffu, ni, 31);
+        if (nq + ntot > (uint32_t)CLS_QUEUE) flush_queue(true);
+        uint32_t qp = nq + ni - nmine;
+        uint32_t p2 = out - __shfl_sync(0xffffffffu, incl, 31) + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if ((keep >> q) & 1u) {
+            if ((nd >> q) & 1u)   // slot (30 bits) + the entry kind (top 2 bits), so exact_eval can store the final flags
+              sm.q[qp++] = make_uint2((r << a.sl_shift) + p2, (e.jb + (uint32_t)q) | ((fl[q] & SE_KIND_MASK) << 28));
+            ++p2;
+          }
+        }
+        nq += ntot;
+        __syncwarp();
+        flush_queue(false);
+      }
+    }
+    overflow = overflow || out > slcap;
+    if (lane == 0) {
+      if (overflow) {
+        const uint32_t p2 = atomicAdd(a.ovf_count, 1u);
+        a.ovf_rows[p2] = r;
+        a.nmem[r] = NMEM_OVERFLOW_BIT;
+        a.sl_cnt[r] = 0;
+      } else {
+        a.sl_cnt[r] = out;
+      }
+    }
+  }
+  flush_queue(true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact_eval
+// ---------------------------------------------------------------------------------------------
+struct EvalSmem {
+  float xs[32][EV_STRIDE];   // staged point rows (one 128-dimension chunk), one row per queued pair
+  float cs[32][EV_STRIDE];   // staged centroid rows
+  uint32_t qd[EV_QUEUE];     // short-list index of the queued pair (point = qd >> sl_shift)
+  uint32_t qj[EV_QUEUE];     // centroid slot
+};
+
+// Evaluates the first np (<= 32) queued pairs.  The warp copies both rows of every pair into
+// shared memory with cp.async (one coalesced 512-byte request per row, all 2*np of them in flight
+// together, no registers held); then lane p walks pair p in dimension order, so every value is
+// the reference's sequential f32 sum, and stores the exact distance into the short-list entry.
+template <int METRIC>
+__device__ __forceinline__ void eval_queue(const ResolveDev& a, EvalSmem& sm, uint32_t np, int lane) {
+  float acc = 0.0f;
+  for (uint32_t c0 = 0; c0 < a.ld; c0 += EV_CHUNK) {
+    const uint32_t col = c0 + lane * 4;
+    if (col < a.ld) {                                // ld is a multiple of 4
+      for (uint32_t p = 0; p < np; ++p) {
+        const float* x = a.P + (size_t)(sm.qd[p] >> a.sl_shift) * a.ld + col;
+        const float* y = a.C + (size_t)(sm.qj[p] & 0x3fffffffu) * a.ld + col;
+        const uint32_t dx = (uint32_t)__cvta_generic_to_shared(&sm.xs[p][lane * 4]);
+        const uint32_t dy = (uint32_t)__cvta_generic_to_shared(&sm.cs[p][lane * 4]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dx), "l"(x) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dy), "l"(y) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if ((uint32_t)lane < np) {
+      const int n4 = (int)(((a.ld - c0) < (uint32_t)EV_CHUNK ? (a.ld - c0) : (uint32_t)EV_CHUNK) >> 2);
+      const float4* xp = reinterpret_cast<const float4*>(&sm.xs[lane][0]);
+      const float4* yp = reinterpret_cast<const float4*>(&sm.cs[lane][0]);
+#pragma unroll 8
+      for (int i = 0; i < n4; ++i) {
+        const float4 xv = xp[i], yv = yp[i];
+        acc = dist_step<METRIC>(acc, xv.x, yv.x);
+        acc = dist_step<METRIC>(acc, xv.y, yv.y);
+        acc = dist_step<METRIC>(acc, xv.z, yv.z);
+        acc = dist_step<METRIC>(acc, xv.w, yv.w);
+      }
+    }
+    __syncwarp();
+  }
+  if ((uint32_t)lane < np) {
+    ShortEnt* w = a.sl + sm.qd[lane];
+    w->v = acc;
+    w->flags = ((sm.qj[lane] >> 30) << 2) | SE_EXACT;
+  }
+  __syncwarp();
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(EV_WARPS * 32) exact_eval_kernel(ResolveDev a) {
+  extern __shared__ __align__(16) unsigned char ev_raw[];
+  EvalSmem& sm = reinterpret_cast<EvalSmem*>(ev_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t total = min(*a.work_count, a.work_cap);
+  // 32 work items per warp and round; the next round's items are fetched before this round runs
+  uint32_t base = warp_global * 32;
+  uint2 item = (base + lane < total) ? a.work[base + lane] : make_uint2(0u, 0u);
+  for (; base < total; base += warps_total * 32) {
+    const uint32_t np = min(32u, total - base);
+    sm.qd[lane] = item.x;
+    sm.qj[lane] = item.y;
+    const uint32_t nb = base + warps_total * 32;
+    item = (nb + lane < total) ? a.work[nb + lane] : make_uint2(0u, 0u);
+    __syncwarp();
+    eval_queue<METRIC>(a, sm, np, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize
+// ---------------------------------------------------------------------------------------------
+constexpr int FN_MAX = 2;             // short-list entries per lane (short list <= 64 entries)
+
+template <int METRIC>
+__global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const float INF = __int_as_float(0x7f800000);
+  const bool approx = a.xnorm != nullptr;
+  // two-level prefetch: a row's entry count and overflow mark two rows ahead, its live entries one
+  // row ahead
+  struct PreE { ShortEnt en[FN_MAX]; };
+  auto prefetch_n = [&](uint32_t rr) { return rr < a.m ? make_uint2(a.sl_cnt[rr], a.nmem[rr]) : make_uint2(0u, 0u); };
+  auto prefetch_e = [&](uint32_t rr, uint32_t n) {
+    PreE p;
+#pragma unroll
+    for (int u = 0; u < FN_MAX; ++u) { p.en[u].j = 0; p.en[u].v = 0.f; p.en[u].cc = 0.f; p.en[u].flags = SE_MEMBER; }
+    if (rr < a.m) {
+      const ShortEnt* sl = a.sl + ((size_t)rr << a.sl_shift);
+#pragma unroll
+      for (int u = 0; u < FN_MAX; ++u)
+        if ((uint32_t)(u * 32 + lane) < n) p.en[u] = sl[u * 32 + lane];
     }
     return p;
   };
   uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  Pre nx = prefetch(r);
+  uint2 cur_n = prefetch_n(r);
+  uint2 nx_n = prefetch_n(r + warps_total);
+  PreE cur_e = prefetch_e(r, cur_n.x);
   for (; r < a.m; r += warps_total) {
-    const Pre cur = nx;
-    nx = prefetch(r + warps_total);
-    // the row's buffer holds nseg segments of segcap slots; cnt_s > segcap marks an overflow
-    const uint32_t cnt0 = cur.cnt0, cnt1 = cur.cnt1;
-    if (cnt0 > segcap || cnt1 > segcap) {   // overflowed: the brute-force kernels own this row
-      if (lane == 0) {
-        const uint32_t pos = atomicAdd(a.ovf_count, 1u);
-        a.ovf_rows[pos] = r;
-        a.nmem[r] = NMEM_OVERFLOW_BIT;
-      }
-      continue;
-    }
-    const uint32_t total = cnt0 + cnt1;
-    auto slot_of = [&](uint32_t u) { return u < cnt0 ? u : segcap + (u - cnt0); };
-    uint2* cr = a.cand + (size_t)r * a.cap;
-    const float* x = a.P + (size_t)r * a.ld;
-    const float E = a.xnorm ? tc_err_bound(a.xnorm[r], a.cnmax[0], a.ld) : 0.0f;
-
-    // 1. approximate minimum over all candidates
-    float ma = INF;
-    if ((uint32_t)lane < cnt0) ma = __uint_as_float(cur.e0.y);
-    if ((uint32_t)lane < cnt1) ma = fminf(ma, __uint_as_float(cur.e1.y));
-    for (uint32_t s2 = 32 + lane; s2 < cnt0; s2 += 32) ma = fminf(ma, __uint_as_float(cr[s2].y));
-    for (uint32_t s2 = 32 + lane; s2 < cnt1; s2 += 32) ma = fminf(ma, __uint_as_float(cr[segcap + s2].y));
-    ma = warp_min(ma);
-    const float min_band = ma + 2.0f * E;
-
-    // 2. exact distances for everything that could be the true minimum → exact (dmin, best)
+    const uint32_t n = cur_n.x, nm = cur_n.y;
+    const PreE cur = cur_e;
+    cur_n = nx_n;
+    nx_n = prefetch_n(r + 2 * warps_total);
+    cur_e = prefetch_e(r + warps_total, cur_n.x);
+    if (nm & NMEM_OVERFLOW_BIT) continue;            // the dense fallback owns this row
+    ShortEnt* sl = a.sl + ((size_t)r << a.sl_shift);
+    ShortEnt en[FN_MAX];
     float bd = INF;
     uint32_t bj = 0xffffffffu;
-    for (uint32_t u0 = 0; u0 < total; u0 += 32) {
-      const uint32_t u = u0 + lane;
-      const bool valid = u < total;
-      uint2 e = make_uint2(0u, 0u);
-      if (valid) e = cr[slot_of(u)];
-      float dv = __uint_as_float(e.y);
-      const bool exact = (e.x & CAND_EXACT_BIT) != 0;
-      const bool want = valid && !exact && dv <= min_band;
-      const uint32_t j = e.x & CAND_SLOT_MASK;
-      dv = coop_exact<METRIC>(want, j, dv, x, a.C, a.ld, sm, lane, &cur.xv);
-      if (want) cr[slot_of(u)] = make_uint2(e.x | CAND_EXACT_BIT, __float_as_uint(dv));
-      if (valid && (exact || want) && lex_less(dv, j, bd, bj)) { bd = dv; bj = j; }
+#pragma unroll
+    for (int u = 0; u < FN_MAX; ++u) {
+      const uint32_t e = u * 32 + lane;
+      en[u] = cur.en[u];
+      if (e < n && (en[u].flags & SE_NEED_EVAL)) {   // did not fit the work list (rare): recompute here
+        en[u].v = thread_dist<METRIC>(a.P + (size_t)r * a.ld, a.C + (size_t)en[u].j * a.ld, a.ld);
+        en[u].flags = (en[u].flags & ~SE_NEED_EVAL) | SE_EXACT;
+      }
+      if (e < n && (en[u].flags & SE_KIND_MASK) == SE_BAND && lex_less(en[u].v, en[u].j, bd, bj)) { bd = en[u].v; bj = en[u].j; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -195,93 +536,92 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) resolve_kernel(ResolveDev a)
       if (lane == 0) a.nmem[r] = 1;
       continue;
     }
-    __syncwarp();
-
-    // 3. boundary membership, decided on exact values
     const float thr = __fmul_rn(bd, a.factor);
-    const float* cb = a.C + (size_t)bj * a.ld;
+    const float* x = a.P + (size_t)r * a.ld;
+    float E = 0.0f;
+    uint32_t member = 0;
     bool best_listed = false;
-    for (uint32_t u0 = 0; u0 < total; u0 += 32) {
-      const uint32_t u = u0 + lane;
-      const bool valid = u < total;
-      uint2 e = make_uint2(0u, 0u);
-      if (valid) e = cr[slot_of(u)];
-      const uint32_t j = e.x & CAND_SLOT_MASK;
-      float dv = __uint_as_float(e.y);
-      bool member = false, ambiguous = false, need_cc = false;
-      float cc = 0.f, lo = 0.f, hi = 0.f;
-      if (valid) {
-        if (j == bj) {
-          member = true;
-          best_listed = true;
-        } else {
-          const bool exact = (e.x & CAND_EXACT_BIT) != 0;
-          lo = exact ? dv : dv - E;
-          hi = exact ? dv : dv + E;
-          need_cc = lo < thr;                         // otherwise certainly d >= thr → not a member
+#pragma unroll
+    for (int u = 0; u < FN_MAX; ++u) {
+      const uint32_t e = u * 32 + lane;
+      if (e >= n) continue;
+      const uint32_t kind = en[u].flags & SE_KIND_MASK, j = en[u].j;
+      const bool ex = (en[u].flags & SE_EXACT) != 0;
+      float dv = en[u].v;
+      bool mem = false;
+      if (j == bj) {
+        mem = true;
+        best_listed = true;
+      } else if (kind == SE_MEMBER) {
+        mem = true;
+      } else if (kind == SE_TEST_CC) {               // exact by construction
+        mem = dv < thr && en[u].cc >= dv;
+      } else {                                       // a band element that lost, or best was unknown
+        bool t1 = true;                              // an approximate value reaching here was certified < thr
+        if (ex) t1 = dv < thr;
+        if (t1) {
+          const float cc = a.cc ? a.cc[(size_t)bj * a.k + j]
+                                : thread_dist<METRIC>(a.C + (size_t)bj * a.ld, a.C + (size_t)j * a.ld, a.ld);
+          if (ex) {
+            mem = cc >= dv;
+          } else {
+            if (E == 0.0f && approx) E = tc_err_bound(a.xnorm[r], a.xres[r], a.cstat[0], a.cstat[1], a.ld);
+            const float lo = __fadd_rd(dv, -E), hi = __fadd_ru(dv, E);
+            if (cc >= hi) mem = true;
+            else if (cc >= lo) {                     // undecidable on the interval: recompute (rare)
+              dv = thread_dist<METRIC>(x, a.C + (size_t)j * a.ld, a.ld);
+              mem = dv < thr && cc >= dv;
+            }
+          }
         }
       }
-      if (a.cc) {
-        if (need_cc) cc = a.cc[(size_t)bj * a.k + j];
-      } else {
-        cc = coop_exact<METRIC>(need_cc, j, 0.f, cb, a.C, a.ld, sm, lane);   // no k x k matrix: on demand
-      }
-      if (need_cc && cc >= lo) {                      // otherwise certainly cc < d → not a member
-        if (hi < thr && cc >= hi) member = true;      // certain on both tests (exact values end here)
-        else ambiguous = true;
-      }
-      dv = coop_exact<METRIC>(ambiguous, j, dv, x, a.C, a.ld, sm, lane, &cur.xv);
-      if (ambiguous) member = (dv < thr) && (cc >= dv);
-      if (valid) cr[slot_of(u)] = make_uint2((e.x & ~CAND_MEMBER_BIT) | (member ? CAND_MEMBER_BIT : 0u), e.y);
+      member |= mem ? (1u << u) : 0u;
     }
+    // member list (uint32 slots) at the front of the row's short list; all entries are in registers
+    const uint32_t mine = (uint32_t)__popc(member);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    uint32_t out = __shfl_sync(0xffffffffu, incl, 31);
     best_listed = __any_sync(0xffffffffu, best_listed);
     __syncwarp();
-
-    // 4. compact the member slots to the front of the row's buffer
-    uint32_t out = 0;
+    uint32_t* memlist = reinterpret_cast<uint32_t*>(sl);
+    uint32_t pos = incl - mine;
+#pragma unroll
+    for (int u = 0; u < FN_MAX; ++u)
+      if ((member >> u) & 1u) memlist[pos++] = en[u].j;
     if (!best_listed) {         // only when every distance was inf/NaN: members = {slot 0}
-      if (lane == 0) cr[0] = make_uint2(0u, __float_as_uint(bd));
+      if (lane == 0) memlist[0] = 0u;
       out = 1;
-      __syncwarp();
-    } else {
-      for (uint32_t u0 = 0; u0 < total; u0 += 32) {
-        const uint32_t u = u0 + lane;
-        uint2 e = make_uint2(0u, 0u);
-        bool mem = false;
-        if (u < total) {
-          e = cr[slot_of(u)];
-          mem = (e.x & CAND_MEMBER_BIT) != 0;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, mem);
-        __syncwarp();
-        if (mem) cr[out + __popc(bal & ((1u << lane) - 1u))] = make_uint2(e.x & CAND_SLOT_MASK, e.y);
-        out += __popc(bal);
-        __syncwarp();
-      }
     }
     if (lane == 0) a.nmem[r] = out;
   }
 }
 
-// Brute force for rows whose candidate buffer overflowed: one CTA per row, every distance
-// recomputed exactly.  PHASE 0 writes best/dmin/nmem; PHASE 1 writes the member slots.
+// Dense fallback for rows whose candidate or short-list buffers overflowed (or whose norms are
+// not finite): their exact distances to all k centroids come from the CUDA-core direct-form
+// kernel (dense mode), `drow` is that row of the batch.  One CTA per row; PHASE 0 writes
+// best / dmin / nmem, PHASE 1 writes the member slots as (key, val) pairs.
 template <int METRIC, int PHASE>
 __global__ void __launch_bounds__(256)
-resolve_overflow_kernel(ResolveDev a, const uint64_t* __restrict__ row_off, uint32_t* __restrict__ keys,
-                        uint32_t* __restrict__ vals) {
+overflow_rows_kernel(ResolveDev a, const float* __restrict__ dense, const uint32_t* __restrict__ rows,
+                     uint32_t nrows, const uint64_t* __restrict__ row_off, uint32_t* __restrict__ keys,
+                     uint32_t* __restrict__ vals) {
   __shared__ float s_bd[8];
   __shared__ uint32_t s_bj[8];
   __shared__ unsigned s_cnt;
   const float INF = __int_as_float(0x7f800000);
-  const uint32_t novf = *a.ovf_count;
-  for (uint32_t o = blockIdx.x; o < novf; o += gridDim.x) {
-    const uint32_t r = a.ovf_rows[o];
-    const float* x = a.P + (size_t)r * a.ld;
+  for (uint32_t o = blockIdx.x; o < nrows; o += gridDim.x) {
+    const uint32_t r = rows[o];
+    const float* drow = dense + (size_t)o * a.k;
     float bd = INF;
     uint32_t bj = 0xffffffffu;
     if (PHASE == 0) {
       for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) {
-        const float dv = thread_dist<METRIC>(x, a.C + (size_t)j * a.ld, a.ld);
+        const float dv = drow[j];
         if (lex_less(dv, j, bd, bj)) { bd = dv; bj = j; }
       }
 #pragma unroll
@@ -309,7 +649,7 @@ resolve_overflow_kernel(ResolveDev a, const uint64_t* __restrict__ row_off, uint
     for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) {
       bool member = (j == bj);
       if (!member && a.want_members) {
-        const float dv = thread_dist<METRIC>(x, a.C + (size_t)j * a.ld, a.ld);
+        const float dv = drow[j];
         if (dv < thr) {
           const float cc = a.cc ? a.cc[(size_t)bj * a.k + j]
                                 : thread_dist<METRIC>(cb, a.C + (size_t)j * a.ld, a.ld);
@@ -330,11 +670,45 @@ resolve_overflow_kernel(ResolveDev a, const uint64_t* __restrict__ row_off, uint
   }
 }
 
+__global__ void gather_rows32_kernel(const float* __restrict__ src, uint32_t ld4, const uint32_t* __restrict__ idx,
+                                     uint32_t m, float* __restrict__ dst) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)m * ld4) return;
+  const uint32_t r = (uint32_t)(t / ld4), c = (uint32_t)(t - (uint64_t)r * ld4);
+  reinterpret_cast<float4*>(dst)[t] = __ldg(reinterpret_cast<const float4*>(src) + (size_t)idx[r] * ld4 + c);
+}
+
+constexpr uint32_t OVF_BATCH = 4096;   // overflow rows per dense batch (4096 x k x 4 bytes of scratch)
+
+// Runs PHASE over all overflow rows, OVF_BATCH at a time (the dense block is recomputed per phase
+// so the scratch stays bounded whatever the number of overflow rows).
+template <int METRIC, int PHASE>
+int run_overflow(spf_ctx* c, const ResolveDev& d, uint32_t n_ovf, const uint64_t* row_off, uint32_t* keys,
+                 uint32_t* vals) {
+  if (n_ovf == 0) return SPF_OK;
+  cudaStream_t st = c->stream;
+  const uint32_t nb_max = n_ovf < OVF_BATCH ? n_ovf : OVF_BATCH;
+  DevBuf<float> rows, dense;
+  SPF_TRY(rows.alloc(st, (size_t)nb_max * d.ld));
+  SPF_TRY(dense.alloc(st, (size_t)nb_max * d.k));
+  for (uint32_t b0 = 0; b0 < n_ovf; b0 += OVF_BATCH) {
+    const uint32_t nb = (n_ovf - b0) < OVF_BATCH ? (n_ovf - b0) : OVF_BATCH;
+    const uint64_t total = (uint64_t)nb * (d.ld / 4);
+    gather_rows32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d.P, d.ld / 4, d.ovf_rows + b0, nb, rows.p);
+    SPF_TRY(check_launch(c, "gather_rows32_kernel"));
+    SPF_TRY(launch_assign_exact(c, METRIC, rows.p, nb, d.C, d.k, d.ld, 1.0f, nullptr, dense.p));
+    const unsigned grid = nb < (uint32_t)c->sm_count * 8 ? nb : (unsigned)c->sm_count * 8;
+    overflow_rows_kernel<METRIC, PHASE><<<grid, 256, 0, st>>>(d, dense.p, d.ovf_rows + b0, nb, row_off, keys, vals);
+    SPF_TRY(check_launch(c, "overflow_rows_kernel"));
+  }
+  return SPF_OK;
+}
+
 struct CountOp {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)(v & ~NMEM_OVERFLOW_BIT); }
 };
 
-__global__ void fill_pairs_kernel(const uint2* __restrict__ cand, int cap, const uint32_t* __restrict__ nmem,
+__global__ void fill_pairs_kernel(const ShortEnt* __restrict__ sl, int sl_shift, const uint32_t* __restrict__ nmem,
                                   const uint64_t* __restrict__ row_off, uint32_t m,
                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const int lane = threadIdx.x & 31;
@@ -343,9 +717,9 @@ __global__ void fill_pairs_kernel(const uint2* __restrict__ cand, int cap, const
     const uint32_t nm = nmem[r];
     if (nm & NMEM_OVERFLOW_BIT) continue;
     const uint64_t off = row_off[r];
-    const uint2* cr = cand + (size_t)r * cap;
+    const uint32_t* mem = reinterpret_cast<const uint32_t*>(sl + ((size_t)r << sl_shift));
     for (uint32_t s = lane; s < nm; s += 32) {
-      keys[off + s] = cr[s].x & CAND_SLOT_MASK;
+      keys[off + s] = mem[s];
       vals[off + s] = r;
     }
   }
@@ -375,18 +749,53 @@ int run_resolve_t(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
   SPF_TRY(ovf_rows.alloc(st, a.m));
   SPF_TRY(ovf_count.alloc(st, 1));
   SPF_CUDA(cudaMemsetAsync(ovf_count.p, 0, sizeof(uint32_t), st));
-  ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, a.cand, a.cand_cnt, a.cap, a.nseg, a.xnorm,
-               a.d_cnmax, a.cc, a.best, a.dmin, a.nmem, ovf_rows.p, ovf_count.p, a.want_members ? 1 : 0};
-  const unsigned ovf_grid = (unsigned)c->sm_count * 4;
+  int sl_shift = 0;
+  while ((1 << sl_shift) < c->params.short_cap) ++sl_shift;
+  if (((uint64_t)a.m << sl_shift) >= (1ull << 32))
+    return fail(SPF_E_INVALID, "assign: m * short_cap must be < 2^32 (m = %llu)", (unsigned long long)a.m);
+  DevBuf<ShortEnt> sl;
+  DevBuf<uint32_t> sl_cnt, work_count;
+  DevBuf<uint2> work;
+  const uint64_t work_cap64 = a.xnorm ? (uint64_t)a.m * 8 + 1024 : 32;   // the exact path never queues work
+  const uint32_t work_cap = work_cap64 > 0xffffff00ull ? 0xffffff00u : (uint32_t)work_cap64;
+  SPF_TRY(sl.alloc(st, (size_t)a.m << sl_shift));
+  SPF_TRY(sl_cnt.alloc(st, a.m));
+  SPF_TRY(work.alloc(st, work_cap));
+  SPF_TRY(work_count.alloc(st, 1));
+  SPF_CUDA(cudaMemsetAsync(work_count.p, 0, sizeof(uint32_t), st));
+  SPF_CUDA(cudaMemsetAsync(a.nmem, 0, a.m * sizeof(uint32_t), st));
+  ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, a.cand.rec, a.cand.info, a.cand.cap, a.nseg,
+               a.xnorm, a.xres, a.d_cstat, a.cc, a.best, a.dmin, a.nmem, ovf_rows.p, ovf_count.p,
+               a.want_members ? 1 : 0, sl.p, sl_cnt.p, sl_shift, work.p, work_count.p, work_cap, c->params.debug};
+  uint32_t n_ovf = 0;
   {
     KernelTimer t(c, "resolve");
     uint64_t blocks = ceil_div(a.m, RS_WARPS);
-    if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
-    resolve_kernel<METRIC><<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
-    SPF_TRY(check_launch(c, "resolve_kernel"));
-    resolve_overflow_kernel<METRIC, 0><<<ovf_grid, 256, 0, st>>>(d, nullptr, nullptr, nullptr);
-    SPF_TRY(check_launch(c, "resolve_overflow_kernel<0>"));
+    if (blocks > (uint64_t)c->sm_count * 8) blocks = (uint64_t)c->sm_count * 8;
+    {
+      KernelTimer t2(c, "classify");
+      classify_kernel<<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+      SPF_TRY(check_launch(c, "classify_kernel"));
+    }
+    const size_t ev_smem = EV_WARPS * sizeof(EvalSmem);
+    SPF_CUDA(cudaFuncSetAttribute(exact_eval_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev_smem));
+    uint64_t ev_blocks = a.xnorm ? (uint64_t)c->sm_count * 3 : 1;
+    {
+      KernelTimer t2(c, "exact_eval");
+      exact_eval_kernel<METRIC><<<(unsigned)ev_blocks, EV_WARPS * 32, ev_smem, st>>>(d);
+      SPF_TRY(check_launch(c, "exact_eval_kernel"));
+    }
+    {
+      KernelTimer t2(c, "finalize");
+      finalize_kernel<METRIC><<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+      SPF_TRY(check_launch(c, "finalize_kernel"));
+    }
+    SPF_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+    KernelTimer t2(c, "overflow");
+    SPF_TRY((run_overflow<METRIC, 0>(c, d, n_ovf, nullptr, nullptr, nullptr)));
   }
+  c->last_overflow_rows = n_ovf;
   if (!csr) return SPF_OK;
 
   KernelTimer t(c, "csr");
@@ -417,11 +826,10 @@ int run_resolve_t(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
   {
     uint64_t blocks = ceil_div(a.m * 32, 256);
     if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
-    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(a.cand, a.cap, a.nmem, row_off.p, (uint32_t)a.m,
+    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(sl.p, sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
                                                         keys.p, vals.p);
     SPF_TRY(check_launch(c, "fill_pairs_kernel"));
-    resolve_overflow_kernel<METRIC, 1><<<ovf_grid, 256, 0, st>>>(d, row_off.p, keys.p, vals.p);
-    SPF_TRY(check_launch(c, "resolve_overflow_kernel<1>"));
+    SPF_TRY((run_overflow<METRIC, 1>(c, d, n_ovf, row_off.p, keys.p, vals.p)));
   }
   // stable sort by cluster slot keeps the input order inside every cluster (:353-361)
   int end_bit = 1;

@@ -613,7 +613,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     for (uint64_t q0 = 0; q0 < nq; q0 += chunk) {
       const uint64_t nc = (nq - q0) < chunk ? (nq - q0) : chunk;
       SPF_TRY(launch_assign_exact(c, SPF_METRIC_EUCLIDEAN, Q.p + q0 * ld, nc, idx->centroids, nlists, ld, 1.0f,
-                                  nullptr, nullptr, 0, Dqc.p));
+                                  nullptr, Dqc.p));
       probe_select_kernel<<<(unsigned)nc, 128, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
                                                         probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
       SPF_TRY(check_launch(c, "probe_select_kernel"));

@@ -36,6 +36,70 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ rows, uint32_t ld4, 
   if (lane == 0) out[w] = acc;
 }
 
+// Rounded GEMM operands + norms (see launch_row_prep in kernels.cuh).  One warp per row.
+__global__ void row_prep_kernel(const float* __restrict__ src, uint32_t ld4, const uint64_t* __restrict__ idx,
+                                uint64_t m, float* __restrict__ tf, float* __restrict__ norm,
+                                float* __restrict__ res) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= m) return;
+  const float4* r = reinterpret_cast<const float4*>(src) + (size_t)(idx ? idx[w] : w) * ld4;
+  float4* o = reinterpret_cast<float4*>(tf) + (size_t)w * ld4;
+  float acc = 0.f, racc = 0.f;
+  auto rnd = [](float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+  };
+  for (uint32_t c = lane; c < ld4; c += 32) {
+    const float4 v = __ldg(r + c);
+    const float4 t = make_float4(rnd(v.x), rnd(v.y), rnd(v.z), rnd(v.w));
+    o[c] = t;
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    const float ex = v.x - t.x, ey = v.y - t.y, ez = v.z - t.z, ew = v.w - t.w;   // exact (Sterbenz)
+    racc = fmaf(ex, ex, racc); racc = fmaf(ey, ey, racc);
+    racc = fmaf(ez, ez, racc); racc = fmaf(ew, ew, racc);
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, of);
+    racc += __shfl_xor_sync(0xffffffffu, racc, of);
+  }
+  if (lane == 0) {
+    norm[w] = acc;
+    res[w] = sqrtf(racc);
+  }
+}
+
+__global__ void max2_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_t n,
+                                float* out2) {
+  // single block; values are >= 0
+  __shared__ float sa[32], sb[32];
+  float va = 0.f, vb = 0.f;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    va = fmaxf(va, a[i]);
+    vb = fmaxf(vb, b[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, o));
+    vb = fmaxf(vb, __shfl_xor_sync(0xffffffffu, vb, o));
+  }
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = va; sb[threadIdx.x >> 5] = vb; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    va = threadIdx.x < (blockDim.x >> 5) ? sa[threadIdx.x] : 0.f;
+    vb = threadIdx.x < (blockDim.x >> 5) ? sb[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, o));
+      vb = fmaxf(vb, __shfl_xor_sync(0xffffffffu, vb, o));
+    }
+    if (threadIdx.x == 0) { out2[0] = va; out2[1] = vb; }
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = v;
@@ -105,6 +169,18 @@ int launch_row_sqnorm(spf_ctx* c, const float* rows, uint32_t ld, uint64_t m, fl
   if (m == 0) return SPF_OK;
   row_sqnorm_kernel<<<(unsigned)ceil_div(m * 32, 256), 256, 0, c->stream>>>(rows, ld / 4, m, out);
   return check_launch(c, "row_sqnorm_kernel");
+}
+
+int launch_row_prep(spf_ctx* c, const float* src, uint32_t ld, const uint64_t* d_idx, uint64_t m,
+                    float* tf, float* norm, float* res) {
+  if (m == 0) return SPF_OK;
+  row_prep_kernel<<<(unsigned)ceil_div(m * 32, 256), 256, 0, c->stream>>>(src, ld / 4, d_idx, m, tf, norm, res);
+  return check_launch(c, "row_prep_kernel");
+}
+
+int launch_max2_f32(spf_ctx* c, const float* a, const float* b, uint64_t n, float* out2) {
+  max2_f32_kernel<<<1, 1024, 0, c->stream>>>(a, b, n, out2);
+  return check_launch(c, "max2_f32_kernel");
 }
 
 int launch_fill_f32(spf_ctx* c, float* p, uint64_t n, float v) {

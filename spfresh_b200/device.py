@@ -56,6 +56,9 @@ class Context:
     def launch_count(self) -> int:
         return int(lib().spf_ctx_launch_count(self._h))
 
+    def last_overflow_rows(self) -> int:
+        return int(lib().spf_ctx_last_overflow_rows(self._h))
+
     def set_param(self, name: str, value: int):
         check(lib().spf_ctx_set_param(self._h, name.encode(), int(value)))
 

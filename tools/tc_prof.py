@@ -24,5 +24,8 @@ ds = s.Dataset(ctx, data)
 for i in range(reps):
     r = ds.assign(0, cent)
     print(f"rep {i}: assign_tc {ctx.kernel_ms('assign_tc'):.3f} ms resolve {ctx.kernel_ms('resolve'):.3f} "
-          f"cc {ctx.kernel_ms('cc_matrix'):.3f} csr {ctx.kernel_ms('csr'):.3f} total members {r.total}", flush=True)
+          f"[classify {ctx.kernel_ms('classify'):.3f} eval {ctx.kernel_ms('exact_eval'):.3f} finalize {ctx.kernel_ms('finalize'):.3f} "
+          f"ovf {ctx.kernel_ms('overflow'):.3f}] "
+          f"cc {ctx.kernel_ms('cc_matrix'):.3f} csr {ctx.kernel_ms('csr'):.3f} total members {r.total} "
+          f"overflow rows {ctx.last_overflow_rows()}", flush=True)
     r.free()
