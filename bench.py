@@ -243,8 +243,8 @@ def main():
     e2e_bytes = {"h2d": 0, "d2h": 0}
 
     def step_e2e():
-        d2 = spf.Dataset(ctx, rows_pin)                       # host -> device, every step
-        r = d2.assign(spf.METRIC_EUCLIDEAN, cent)
+        # spf_assign_host: pinned host rows -> device (chunked, overlapped with the kernels), every step
+        d2, r = spf.Dataset.assign_from_host(ctx, rows_pin, spf.METRIC_EUCLIDEAN, cent)
         if members_cap["buf"] is None or members_cap["buf"].size < r.total:
             members_cap["buf"] = torch.empty(int(r.total * 1.05) + 1, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
         from spfresh_b200._capi import check, lib, ptr

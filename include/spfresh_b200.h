@@ -116,6 +116,16 @@ int spf_distance_pairs(spf_ctx* ctx, int metric, const float* a, const float* b,
 int  spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                 const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
                 spf_assign_result** out);
+/* The same for rows that are still in HOST memory (the borrowed ArrayView2 of
+ * src/spann/spann_builder.rs:20): uploads the n x d rows and assigns all of them to the k
+ * centroid rows in one call.  The upload is chunked and overlapped with the kernels of the
+ * previous chunk, so the call costs little more than the host-to-device copy itself (use pinned
+ * host memory for full PCIe rate).  `rows` is only read during the call.  When ds_out is not NULL
+ * it receives the resident dataset (for further spf_assign / spf_update_medoids_from calls);
+ * otherwise the device copy is dropped. */
+int  spf_assign_host(spf_ctx* ctx, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride,
+                     int metric, const uint64_t* centroid_rows, uint32_t k, float boundary_factor,
+                     int flags, spf_dataset** ds_out, spf_assign_result** out);
 uint64_t spf_assign_points(const spf_assign_result* r);        /* m                         */
 uint32_t spf_assign_clusters(const spf_assign_result* r);      /* k                         */
 uint64_t spf_assign_total(const spf_assign_result* r);         /* sum of cluster sizes      */
@@ -208,7 +218,8 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
 
 /* ---- tuning knobs (not part of the drop-in surface; used by the tests to reach rare paths) -- *
  * "cand_cap" candidate group records per point (default 128), "short_cap" resolve short-list
- * entries per point (power of two <= 64, default 64), "force_exact", "tc_min_k", "tc_min_m",
+ * entries per point (power of two <= 64, default 64), "chunk_rows" points per internal assign
+ * chunk (0 = automatic), "force_exact", "tc_min_k", "tc_min_m",
  * "kmpp_exact_sum" (1: sequential f32 sum, bit-parity; 0: tree sum), "cc_matrix_max_k". */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 

@@ -95,6 +95,7 @@ void spf_ctx_destroy(spf_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -137,7 +138,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
     if (value < 2 || value > 64 || (value & (value - 1))) return fail(SPF_E_INVALID, "short_cap must be a power of two in [2,64]");
     c->params.short_cap = value;
   } else if (s == "force_exact") c->params.force_exact = value;
-  else if (s == "debug") c->params.debug = value;
+  else if (s == "chunk_rows") c->params.chunk_rows = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
@@ -149,7 +150,9 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
 // ---------------------------------------------------------------------------------------------
 // dataset
 // ---------------------------------------------------------------------------------------------
-static int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out) {
+}  // extern "C"
+
+int spf::dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out) {
   if (!c || !out) return fail(SPF_E_INVALID, "ctx/out is NULL");
   if (n == 0 || d == 0) return fail(SPF_E_INVALID, "dataset must have n > 0 and d > 0");
   if (n >= (1ull << 32)) return fail(SPF_E_INVALID, "n must be < 2^32 rows per device shard");
@@ -161,21 +164,24 @@ static int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out) 
   ds->d = d;
   ds->ld = round_up(d, 4);
   size_t bytes = (size_t)n * ds->ld * sizeof(float);
-  cudaError_t e = cudaMalloc((void**)&ds->x, bytes);
+  // stream-ordered pool: re-uploading a dataset of the same size reuses the cached block
+  cudaError_t e = cudaMallocAsync((void**)&ds->x, bytes, c->stream);
   if (e != cudaSuccess) {
     delete ds;
-    return fail(SPF_E_OOM, "cudaMalloc of %zu bytes for the dataset failed: %s", bytes, cudaGetErrorString(e));
+    return fail(SPF_E_OOM, "allocation of %zu bytes for the dataset failed: %s", bytes, cudaGetErrorString(e));
   }
   *out = ds;
   return SPF_OK;
 }
+
+extern "C" {
 
 int spf_dataset_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride,
                        spf_dataset** out) {
   if (!rows) return fail(SPF_E_INVALID, "rows is NULL");
   if (row_stride < d) return fail(SPF_E_INVALID, "row_stride (%llu) < d (%u)", (unsigned long long)row_stride, d);
   spf_dataset* ds = nullptr;
-  SPF_TRY(dataset_alloc(c, n, d, &ds));
+  SPF_TRY(spf::dataset_alloc(c, n, d, &ds));
   std::lock_guard<std::mutex> lk(c->mu);
   cudaError_t e = cudaSuccess;
   if (ds->ld != d) e = cudaMemsetAsync(ds->x, 0, (size_t)n * ds->ld * sizeof(float), c->stream);
@@ -194,7 +200,7 @@ int spf_dataset_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, ui
 int spf_dataset_from_device(spf_ctx* c, const void* dev_rows, uint64_t n, uint32_t d, spf_dataset** out) {
   if (!dev_rows) return fail(SPF_E_INVALID, "dev_rows is NULL");
   spf_dataset* ds = nullptr;
-  SPF_TRY(dataset_alloc(c, n, d, &ds));
+  SPF_TRY(spf::dataset_alloc(c, n, d, &ds));
   std::lock_guard<std::mutex> lk(c->mu);
   cudaError_t e = cudaSuccess;
   if (ds->ld != d) e = cudaMemsetAsync(ds->x, 0, (size_t)n * ds->ld * sizeof(float), c->stream);
@@ -214,10 +220,11 @@ void spf_dataset_free(spf_dataset* ds) {
   if (!ds) return;
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
-  if (ds->x) cudaFree(ds->x);
-  if (ds->xtf) cudaFree(ds->xtf);
-  if (ds->xnorm) cudaFree(ds->xnorm);
-  if (ds->xres) cudaFree(ds->xres);
+  cudaStream_t st = ds->ctx->stream;
+  if (ds->x) cudaFreeAsync(ds->x, st);
+  if (ds->xtf) cudaFreeAsync(ds->xtf, st);
+  if (ds->xnorm) cudaFreeAsync(ds->xnorm, st);
+  if (ds->xres) cudaFreeAsync(ds->xres, st);
   delete ds;
 }
 

@@ -1,5 +1,9 @@
 // assign_api.cu — spf_assign: the batched replacement of
 // HierarchicalClustering::assign_points_to_clusters (src/clustering/hierarchical.rs:295-364).
+#include <string.h>
+
+#include <vector>
+
 #include "kernels.cuh"
 
 using namespace spf;
@@ -29,26 +33,164 @@ int assign_members_as_rows(const spf_assign_result* r, uint64_t* d_out) {
   return check_launch(r->ctx, "positions_to_rows_kernel");
 }
 
-// Rounded copy, squared norms and rounding residuals of all dataset rows, computed once per
-// dataset (tensor path only).
-int dataset_prep(spf_dataset* ds) {
+// Rounded copy, squared norms and rounding residuals of all dataset rows (tensor path only):
+// allocated by dataset_prep_alloc, filled once per dataset by dataset_prep (or chunk by chunk by
+// the host-streamed assign).
+int dataset_prep_alloc(spf_dataset* ds) {
   if (ds->xtf) return SPF_OK;
-  spf_ctx* c = ds->ctx;
+  cudaStream_t st = ds->ctx->stream;
   float *tf = nullptr, *nrm = nullptr, *res = nullptr;
-  cudaError_t e = cudaMalloc((void**)&tf, (size_t)ds->n * ds->ld * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&nrm, (size_t)ds->n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&res, (size_t)ds->n * sizeof(float));
-  int rc = e == cudaSuccess ? launch_row_prep(c, ds->x, ds->ld, nullptr, ds->n, tf, nrm, res)
-                            : fail(SPF_E_OOM, "cudaMalloc for the rounded dataset copy failed: %s", cudaGetErrorString(e));
-  if (rc < 0) {
-    cudaFree(tf); cudaFree(nrm); cudaFree(res);
-    return rc;
+  cudaError_t e = cudaMallocAsync((void**)&tf, (size_t)ds->n * ds->ld * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&nrm, (size_t)ds->n * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&res, (size_t)ds->n * sizeof(float), st);
+  if (e != cudaSuccess) {
+    if (tf) cudaFreeAsync(tf, st);
+    if (nrm) cudaFreeAsync(nrm, st);
+    if (res) cudaFreeAsync(res, st);
+    return fail(SPF_E_OOM, "allocation of the rounded dataset copy failed: %s", cudaGetErrorString(e));
   }
   ds->xtf = tf;
   ds->xnorm = nrm;
   ds->xres = res;
   return SPF_OK;
 }
+
+int dataset_prep(spf_dataset* ds) {
+  if (ds->prepped) return SPF_OK;
+  SPF_TRY(dataset_prep_alloc(ds));
+  SPF_TRY(launch_row_prep(ds->ctx, ds->x, ds->ld, nullptr, ds->n, ds->xtf, ds->xnorm, ds->xres));
+  ds->prepped = true;
+  return SPF_OK;
+}
+
+}  // namespace spf
+
+namespace spf {
+
+namespace {
+
+// One assign call: centroid-side operands prepared once, the point list processed in chunks
+// (bounded scratch; the host-streamed entry point overlaps uploads with the chunks' kernels).
+struct AssignCall {
+  spf_ctx* c = nullptr;
+  int metric = 0;
+  uint32_t k = 0, ld = 0;
+  float factor = 1.0f;
+  bool want_members = true, use_tc = false;
+  uint64_t m = 0, chunk_rows = 0;
+  DevBuf<float> Cg, ctf, cnorm, cres, cstat, cc;
+  DevBuf<CandRec> cand_rec;
+  DevBuf<RowInfo> cand_info;
+  CandBuf cand;
+  DevBuf<uint32_t> best, nmem;
+  DevBuf<float> dmin;
+  ResolveState* rs = nullptr;
+  ~AssignCall() { if (rs) resolve_free(rs); }
+};
+
+uint64_t pick_chunk_rows(const spf_ctx* c, uint64_t m, bool streamed) {
+  // multiples of one full wave of the tensor kernel (one 128-point row block per SM)
+  uint64_t rows = (uint64_t)c->sm_count * 128 * (streamed ? 4 : 16);
+  if (c->params.chunk_rows > 0) rows = (uint64_t)c->params.chunk_rows;
+  return rows < m ? rows : m;
+}
+
+// Everything that depends only on the centroids (Cg already holds the k gathered rows).
+int assign_setup(AssignCall& a) {
+  spf_ctx* c = a.c;
+  cudaStream_t st = c->stream;
+  a.cand.cap = c->params.cand_cap;
+  SPF_TRY(a.cand_rec.alloc(st, (size_t)a.chunk_rows * a.cand.cap));
+  SPF_TRY(a.cand_info.alloc(st, a.chunk_rows));
+  a.cand.rec = a.cand_rec.p;
+  a.cand.info = a.cand_info.p;
+  if (a.use_tc) {
+    const uint32_t kpad = round_up(a.k, 256);
+    SPF_TRY(a.ctf.alloc(st, (size_t)a.k * a.ld));
+    SPF_TRY(a.cnorm.alloc(st, kpad));
+    SPF_TRY(a.cres.alloc(st, a.k));
+    SPF_TRY(a.cstat.alloc(st, 2));
+    SPF_TRY(launch_row_prep(c, a.Cg.p, a.ld, nullptr, a.k, a.ctf.p, a.cnorm.p, a.cres.p));
+    SPF_TRY(launch_max2_f32(c, a.cnorm.p, a.cres.p, a.k, a.cstat.p));
+    if (kpad > a.k) {
+      pad_inf_kernel<<<(kpad - a.k + 255) / 256, 256, 0, st>>>(a.cnorm.p, a.k, kpad);
+      SPF_TRY(check_launch(c, "pad_inf_kernel"));
+    }
+  }
+  // exact centroid-centroid distances for the boundary rule `d(c_best, c_j) >= d_j` (:337-342)
+  if (a.want_members && a.k > 1 && (int)a.k <= c->params.cc_matrix_max_k) {
+    SPF_TRY(a.cc.alloc(st, (size_t)a.k * a.k));
+    KernelTimer t(c, "cc_matrix");
+    SPF_TRY(launch_assign_exact(c, a.metric, a.Cg.p, a.k, a.Cg.p, a.k, a.ld, 1.0f, nullptr, a.cc.p));
+  }
+  SPF_TRY(a.best.alloc(st, a.m));
+  SPF_TRY(a.dmin.alloc(st, a.m));
+  SPF_TRY(a.nmem.alloc(st, a.m));
+  SPF_TRY(resolve_begin(c, a.m, a.chunk_rows, a.use_tc, &a.rs));
+  return SPF_OK;
+}
+
+ResolveArgs resolve_args(const AssignCall& a, const float* P, uint64_t m, const float* xnorm, const float* xres,
+                         uint64_t r0) {
+  ResolveArgs r;
+  r.metric = a.metric; r.P = P; r.m = m; r.C = a.Cg.p; r.k = a.k; r.ld = a.ld; r.factor = a.factor;
+  r.cand = a.cand; r.nseg = a.use_tc ? 2 : 1;
+  r.xnorm = a.use_tc ? xnorm : nullptr; r.xres = a.use_tc ? xres : nullptr;
+  r.d_cstat = a.use_tc ? a.cstat.p : nullptr;
+  r.cc = a.cc.p; r.want_members = a.want_members;
+  r.best = a.best.p + r0; r.dmin = a.dmin.p + r0; r.nmem = a.nmem.p + r0;
+  return r;
+}
+
+// Candidate kernel + resolve for the points [r0, r0 + mc) of the list; all pointers chunk-relative.
+int assign_rows(AssignCall& a, const float* P, const float* Ptf, const float* xnorm, const float* xres,
+                uint64_t r0, uint64_t mc) {
+  spf_ctx* c = a.c;
+  if (a.use_tc) {
+    KernelTimer t(c, "assign_tc");
+    SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cnorm.p, a.cstat.p, a.factor, a.cand));
+  } else {
+    KernelTimer t(c, "assign_exact");
+    SPF_TRY(launch_assign_exact(c, a.metric, P, mc, a.Cg.p, a.k, a.ld, a.factor, &a.cand, nullptr));
+  }
+  return resolve_chunk(c, a.rs, resolve_args(a, P, mc, xnorm, xres, r0), r0);
+}
+
+// Overflow rows, CSR, and the result object (takes ownership of the output buffers).
+int assign_finish(AssignCall& a, const float* P_all, const float* xnorm_all, const float* xres_all,
+                  DevBuf<uint64_t>* d_pidx, spf_assign_result** out) {
+  spf_ctx* c = a.c;
+  cudaStream_t st = c->stream;
+  spf_assign_result* r = new (std::nothrow) spf_assign_result();
+  if (!r) return fail(SPF_E_OOM, "out of host memory");
+  r->ctx = c;
+  r->m = a.m;
+  r->k = a.k;
+  CsrOut csr;
+  ResolveArgs ra = resolve_args(a, P_all, a.m, xnorm_all, xres_all, 0);
+  int rc = resolve_finish(c, a.rs, ra, a.want_members ? &csr : nullptr);
+  if (rc >= 0) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(SPF_E_CUDA, "assign failed on the device: %s", cudaGetErrorString(e));
+  }
+  if (rc < 0) {
+    if (csr.offsets) cudaFreeAsync(csr.offsets, st);
+    if (csr.members) cudaFreeAsync(csr.members, st);
+    delete r;
+    return rc;
+  }
+  r->best = a.best.take();
+  r->dmin = a.dmin.take();
+  r->has_csr = a.want_members;
+  r->total = csr.total;
+  r->offsets = csr.offsets;
+  r->members = csr.members;
+  r->point_idx = (d_pidx && d_pidx->p) ? d_pidx->take() : nullptr;
+  *out = r;
+  return SPF_OK;
+}
+
+}  // namespace
 
 }  // namespace spf
 
@@ -69,9 +211,8 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  c->kernel_ms.clear();
   const uint32_t ld = ds->ld;
-  const bool want_members = !(flags & SPF_ASSIGN_NO_CSR);
-  const float factor = want_members ? boundary_factor : 1.0f;
 
   DevBuf<uint64_t> d_crow, d_pidx;
   DevBuf<int> d_flag;
@@ -90,34 +231,27 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   SPF_CUDA(cudaStreamSynchronize(st));
   if (h_flag) return fail(SPF_E_INVALID, "a point or centroid row index is >= n (%llu)", (unsigned long long)ds->n);
 
+  AssignCall a;
+  a.c = c; a.metric = metric; a.k = k; a.ld = ld; a.m = m;
+  a.want_members = !(flags & SPF_ASSIGN_NO_CSR);
+  a.factor = a.want_members ? boundary_factor : 1.0f;
+  a.use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) && !c->params.force_exact &&
+             assign_tc_supported(c, m, k, ld);
+  a.chunk_rows = pick_chunk_rows(c, m, false);
+
   // dense operands: centroids always gathered; points gathered only for a subset
-  DevBuf<float> Cg, Pg;
-  SPF_TRY(Cg.alloc(st, (size_t)k * ld));
-  SPF_TRY(launch_gather_rows(c, ds->x, ld, d_crow.p, k, Cg.p));
+  SPF_TRY(a.Cg.alloc(st, (size_t)k * ld));
+  SPF_TRY(launch_gather_rows(c, ds->x, ld, d_crow.p, k, a.Cg.p));
+  DevBuf<float> Pg, ptf_sub, xnorm_sub, xres_sub;
   const float* P = ds->x;
+  const float *Ptf = nullptr, *xnorm = nullptr, *xres = nullptr;
   if (point_idx) {
     SPF_TRY(Pg.alloc(st, (size_t)m * ld));
     SPF_TRY(launch_gather_rows(c, ds->x, ld, d_pidx.p, m, Pg.p));
     P = Pg.p;
   }
-
-  CandBuf cand;
-  cand.cap = c->params.cand_cap;
-  DevBuf<CandRec> cand_rec;
-  DevBuf<RowInfo> cand_info;
-  SPF_TRY(cand_rec.alloc(st, (size_t)m * cand.cap));
-  SPF_TRY(cand_info.alloc(st, m));
-  cand.rec = cand_rec.p;
-  cand.info = cand_info.p;
-
-  const bool use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) &&
-                      !c->params.force_exact && assign_tc_supported(c, m, k, ld);
-  DevBuf<float> ptf_sub, xnorm_sub, xres_sub, ctf, cnorm, cres, cstat;
-  const float* xnorm = nullptr;
-  const float* xres = nullptr;
-  if (use_tc) {
-    const float* Ptf = nullptr;
-    if (point_idx) {   // gather + round in one pass (P itself is only needed by resolve)
+  if (a.use_tc) {
+    if (point_idx) {
       SPF_TRY(ptf_sub.alloc(st, (size_t)m * ld));
       SPF_TRY(xnorm_sub.alloc(st, m));
       SPF_TRY(xres_sub.alloc(st, m));
@@ -127,71 +261,107 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
       SPF_TRY(dataset_prep(ds));
       Ptf = ds->xtf; xnorm = ds->xnorm; xres = ds->xres;
     }
-    const uint32_t kpad = round_up(k, 256);
-    SPF_TRY(ctf.alloc(st, (size_t)k * ld));
-    SPF_TRY(cnorm.alloc(st, kpad));
-    SPF_TRY(cres.alloc(st, k));
-    SPF_TRY(cstat.alloc(st, 2));
-    SPF_TRY(launch_row_prep(c, Cg.p, ld, nullptr, k, ctf.p, cnorm.p, cres.p));
-    SPF_TRY(launch_max2_f32(c, cnorm.p, cres.p, k, cstat.p));
-    if (kpad > k) {
-      pad_inf_kernel<<<(kpad - k + 255) / 256, 256, 0, st>>>(cnorm.p, k, kpad);
-      SPF_TRY(check_launch(c, "pad_inf_kernel"));
+  }
+  SPF_TRY(assign_setup(a));
+  for (uint64_t r0 = 0; r0 < m; r0 += a.chunk_rows) {
+    const uint64_t mc = (m - r0) < a.chunk_rows ? (m - r0) : a.chunk_rows;
+    SPF_TRY(assign_rows(a, P + r0 * ld, Ptf ? Ptf + r0 * ld : nullptr, xnorm ? xnorm + r0 : nullptr,
+                        xres ? xres + r0 : nullptr, r0, mc));
+  }
+  return assign_finish(a, P, xnorm, xres, &d_pidx, out);
+}
+
+int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride, int metric,
+                    const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
+                    spf_dataset** ds_out, spf_assign_result** out) {
+  if (!c || !rows || !out || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign_host: NULL argument");
+  *out = nullptr;
+  if (ds_out) *ds_out = nullptr;
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  if (k == 0) return fail(SPF_E_INVALID, "k must be > 0 (the reference indexes centroids[0])");
+  if (k > (REC_G_MASK << 2)) return fail(SPF_E_INVALID, "k must be < 2^30");
+  if (row_stride < d) return fail(SPF_E_INVALID, "row_stride (%llu) < d (%u)", (unsigned long long)row_stride, d);
+  for (uint32_t j = 0; j < k; ++j)
+    if (centroid_rows[j] >= n)
+      return fail(SPF_E_INVALID, "a point or centroid row index is >= n (%llu)", (unsigned long long)n);
+  spf_dataset* ds = nullptr;
+  SPF_TRY(dataset_alloc(c, n, d, &ds));
+  struct Guard {   // frees the dataset unless it is handed to the caller
+    spf_dataset* d;
+    ~Guard() { if (d) spf_dataset_free(d); }
+  } guard{ds};
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  c->kernel_ms.clear();
+  const uint32_t ld = ds->ld;
+  if (!c->copy_stream) SPF_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+
+  AssignCall a;
+  a.c = c; a.metric = metric; a.k = k; a.ld = ld; a.m = n;
+  a.want_members = !(flags & SPF_ASSIGN_NO_CSR);
+  a.factor = a.want_members ? boundary_factor : 1.0f;
+  a.use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) && !c->params.force_exact &&
+             assign_tc_supported(c, n, k, ld);
+  a.chunk_rows = pick_chunk_rows(c, n, true);
+  if (a.use_tc) SPF_TRY(dataset_prep_alloc(ds));
+
+  // the k centroid vectors come straight from the host rows (small gather + one copy)
+  {
+    std::vector<float> cg((size_t)k * ld, 0.0f);
+    for (uint32_t j = 0; j < k; ++j)
+      memcpy(&cg[(size_t)j * ld], rows + (size_t)centroid_rows[j] * row_stride, (size_t)d * sizeof(float));
+    SPF_TRY(a.Cg.alloc(st, (size_t)k * ld));
+    SPF_CUDA(cudaMemcpyAsync(a.Cg.p, cg.data(), cg.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    SPF_CUDA(cudaStreamSynchronize(st));   // cg goes out of scope
+  }
+  SPF_TRY(assign_setup(a));
+
+  // upload chunk by chunk on the copy stream; the compute stream follows one event behind
+  const uint64_t nchunks = ceil_div(n, a.chunk_rows);
+  std::vector<cudaEvent_t> evs(nchunks, nullptr);
+  struct EvGuard {
+    std::vector<cudaEvent_t>& v;
+    ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+  } evguard{evs};
+  // the copy stream must not overwrite memory the pool may still be recycling on the main stream
+  {
+    cudaEvent_t e0;
+    SPF_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    cudaEventRecord(e0, st);
+    cudaStreamWaitEvent(c->copy_stream, e0, 0);
+    cudaEventDestroy(e0);
+  }
+  for (uint64_t ci = 0; ci < nchunks; ++ci) {
+    const uint64_t r0 = ci * a.chunk_rows;
+    const uint64_t mc = (n - r0) < a.chunk_rows ? (n - r0) : a.chunk_rows;
+    float* dst = ds->x + r0 * ld;
+    const float* src = rows + r0 * row_stride;
+    if (ld == d && row_stride == d) {
+      SPF_CUDA(cudaMemcpyAsync(dst, src, (size_t)mc * d * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+      if (ld != d) SPF_CUDA(cudaMemsetAsync(dst, 0, (size_t)mc * ld * sizeof(float), c->copy_stream));
+      SPF_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)row_stride * sizeof(float),
+                                 (size_t)d * sizeof(float), (size_t)mc, cudaMemcpyHostToDevice, c->copy_stream));
     }
-    KernelTimer t(c, "assign_tc");
-    SPF_TRY(launch_assign_tc(c, Ptf, m, ctf.p, k, ld, xnorm, xres, cnorm.p, cstat.p, factor, cand));
-  } else {
-    KernelTimer t(c, "assign_exact");
-    SPF_TRY(launch_assign_exact(c, metric, P, m, Cg.p, k, ld, factor, &cand, nullptr));
+    SPF_CUDA(cudaEventCreateWithFlags(&evs[ci], cudaEventDisableTiming));
+    SPF_CUDA(cudaEventRecord(evs[ci], c->copy_stream));
   }
-
-  // exact centroid-centroid distances for the boundary rule `d(c_best, c_j) >= d_j` (:337-342)
-  DevBuf<float> cc;
-  if (want_members && k > 1 && (int)k <= c->params.cc_matrix_max_k) {
-    SPF_TRY(cc.alloc(st, (size_t)k * k));
-    KernelTimer t(c, "cc_matrix");
-    SPF_TRY(launch_assign_exact(c, metric, Cg.p, k, Cg.p, k, ld, 1.0f, nullptr, cc.p));
+  for (uint64_t ci = 0; ci < nchunks; ++ci) {
+    const uint64_t r0 = ci * a.chunk_rows;
+    const uint64_t mc = (n - r0) < a.chunk_rows ? (n - r0) : a.chunk_rows;
+    SPF_CUDA(cudaStreamWaitEvent(st, evs[ci], 0));
+    if (a.use_tc)
+      SPF_TRY(launch_row_prep(c, ds->x + r0 * ld, ld, nullptr, mc, ds->xtf + r0 * ld, ds->xnorm + r0, ds->xres + r0));
+    SPF_TRY(assign_rows(a, ds->x + r0 * ld, a.use_tc ? ds->xtf + r0 * ld : nullptr,
+                        a.use_tc ? ds->xnorm + r0 : nullptr, a.use_tc ? ds->xres + r0 : nullptr, r0, mc));
   }
-
-  spf_assign_result* r = new (std::nothrow) spf_assign_result();
-  if (!r) return fail(SPF_E_OOM, "out of host memory");
-  r->ctx = c;
-  r->m = m;
-  r->k = k;
-  DevBuf<uint32_t> best, nmem;
-  DevBuf<float> dmin;
-  int rc = best.alloc(st, m);
-  if (rc >= 0) rc = dmin.alloc(st, m);
-  if (rc >= 0) rc = nmem.alloc(st, m);
-  CsrOut csr;
-  if (rc >= 0) {
-    ResolveArgs a;
-    a.metric = metric; a.P = P; a.m = m; a.C = Cg.p; a.k = k; a.ld = ld; a.factor = factor;
-    a.cand = cand; a.nseg = use_tc ? 2 : 1;
-    a.xnorm = use_tc ? xnorm : nullptr; a.xres = use_tc ? xres : nullptr;
-    a.d_cstat = use_tc ? cstat.p : nullptr;
-    a.cc = cc.p; a.want_members = want_members;
-    a.best = best.p; a.dmin = dmin.p; a.nmem = nmem.p;
-    rc = run_resolve(c, a, want_members ? &csr : nullptr);
+  SPF_CUDA(cudaStreamSynchronize(c->copy_stream));   // `rows` is not read after the call returns
+  SPF_TRY(assign_finish(a, ds->x, ds->xnorm, ds->xres, nullptr, out));
+  if (ds_out) {
+    *ds_out = ds;
+    guard.d = nullptr;
   }
-  if (rc >= 0) {
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) rc = fail(SPF_E_CUDA, "assign failed on the device: %s", cudaGetErrorString(e));
-  }
-  if (rc < 0) {
-    if (csr.offsets) cudaFreeAsync(csr.offsets, st);
-    if (csr.members) cudaFreeAsync(csr.members, st);
-    delete r;
-    return rc;
-  }
-  r->best = best.take();
-  r->dmin = dmin.take();
-  r->has_csr = want_members;
-  r->total = csr.total;
-  r->offsets = csr.offsets;
-  r->members = csr.members;
-  r->point_idx = point_idx ? d_pidx.take() : nullptr;
-  *out = r;
   return SPF_OK;
 }
 

@@ -47,7 +47,7 @@ struct Params {
   int kmpp_exact_sum = 1;    // 1: sequential f32 sum (bit-parity with the reference)
   int cc_matrix_max_k = 16384;  // precompute the k x k centroid-centroid matrix up to this k
   int scan_threads = 256;
-  int debug = 0;             // development switches (timing experiments only)
+  int chunk_rows = 0;        // points per assign chunk (0: automatic)
 };
 
 }  // namespace spf
@@ -57,6 +57,7 @@ struct spf_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host-streamed assign: uploads overlap the main stream
   std::mutex mu;
   bool profiling = false;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -74,6 +75,7 @@ struct spf_dataset {
   float* xtf = nullptr;   // n x ld rows rounded to TF32 (the GEMM's A operand)
   float* xnorm = nullptr; // squared norms |x|^2
   float* xres = nullptr;  // rounding residual norms |x - xtf|
+  bool prepped = false;   // xtf / xnorm / xres hold valid data for all rows
   uint64_t n = 0;
   uint32_t d = 0, ld = 0;
 };
@@ -142,7 +144,7 @@ struct KernelTimer {
       cudaEventSynchronize(e1);
       float ms = 0;
       cudaEventElapsedTime(&ms, e0, e1);
-      c->kernel_ms[name] = ms;
+      c->kernel_ms[name] += ms;   // accumulates over the chunks of one call (cleared per call)
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);

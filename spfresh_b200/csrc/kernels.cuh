@@ -111,10 +111,23 @@ struct CsrOut {
   uint64_t* offsets = nullptr;   // device, k+1
   uint32_t* members = nullptr;   // device, total: positions 0..m-1 into the assign's point list
 };
-// Resolves best/dmin/members per row; csr == NULL skips the CSR build.
-int run_resolve(spf_ctx* c, const ResolveArgs& a, CsrOut* csr);
+// The point list of one assign is resolved in chunks (bounded scratch; lets the host-streamed
+// path overlap uploads with compute):
+//   resolve_begin   allocates the per-call state for m_total points, chunks of <= chunk_rows
+//   resolve_chunk   classify / exact_eval / finalize for one chunk; `a` holds chunk-relative
+//                   pointers (P, xnorm, xres, best, dmin, nmem, cand) and a.m = rows of the chunk,
+//                   r0 = first row of the chunk in the point list
+//   resolve_finish  dense fallback for the overflow rows of all chunks, then the CSR (csr == NULL
+//                   skips it); `a` describes the whole list (candidate fields unused)
+struct ResolveState;
+int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx, ResolveState** out);
+int resolve_chunk(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t r0);
+int resolve_finish(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* csr);
+void resolve_free(ResolveState* s);
 
 // ---- assign_api.cu ------------------------------------------------------------------------
+int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out);   // api.cu: device buffer only
+int dataset_prep_alloc(spf_dataset* ds);
 int dataset_prep(spf_dataset* ds);   // rounded copy + norms of all rows, once per dataset
 int assign_members_as_rows(const spf_assign_result* r, uint64_t* d_out);   // positions → dataset rows
 

@@ -31,7 +31,6 @@
 
 namespace spf {
 
-namespace {
 
 // Short-list entry (classify → exact_eval → finalize).
 struct __align__(16) ShortEnt {
@@ -48,6 +47,18 @@ constexpr uint32_t SE_MEMBER = 1u << 2;     // certain boundary member whatever 
 constexpr uint32_t SE_TEST_CC = 2u << 2;    // d < thr and cc >= d still to be decided; cc stored
 constexpr uint32_t SE_TEST_NOCC = 3u << 2;  // same, best was not known yet: cc fetched by finalize
 
+// Per-call state shared by the chunks of one assign (kernels.cuh: resolve_begin / _chunk / _finish).
+struct ResolveState {
+  DevBuf<uint32_t> ovf_rows, ovf_count, sl_cnt, work_count;
+  DevBuf<ShortEnt> sl;
+  DevBuf<uint2> work;
+  int sl_shift = 0;
+  uint32_t work_cap = 0;
+  uint64_t chunk_rows = 0;
+};
+
+namespace {
+
 struct ResolveDev {
   const float* P; uint32_t m; const float* C; uint32_t k; uint32_t ld;
   float factor;
@@ -59,7 +70,7 @@ struct ResolveDev {
   ShortEnt* sl; uint32_t* sl_cnt; int sl_shift;   // short list: 1 << sl_shift (<= 64) entries per point
   // work list of exact evaluations: (short-list index, centroid slot) pairs appended by classify
   uint2* work; uint32_t* work_count; uint32_t work_cap;
-  int debug;
+  uint32_t row_base;   // first row of this chunk in the whole point list (ovf_rows holds global rows)
 };
 
 __device__ __forceinline__ bool lex_less(float d1, uint32_t j1, float d2, uint32_t j2) {
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
     if (lane == 0) {
       if (overflow) {
         const uint32_t p2 = atomicAdd(a.ovf_count, 1u);
-        a.ovf_rows[p2] = r;
+        a.ovf_rows[p2] = a.row_base + r;
         a.nmem[r] = NMEM_OVERFLOW_BIT;
         a.sl_cnt[r] = 0;
       } else {
@@ -743,55 +754,51 @@ __global__ void offsets_kernel(const uint32_t* __restrict__ keys_sorted, uint64_
 }
 
 template <int METRIC>
-int run_resolve_t(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
+int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t r0) {
   cudaStream_t st = c->stream;
-  DevBuf<uint32_t> ovf_rows, ovf_count;
-  SPF_TRY(ovf_rows.alloc(st, a.m));
-  SPF_TRY(ovf_count.alloc(st, 1));
-  SPF_CUDA(cudaMemsetAsync(ovf_count.p, 0, sizeof(uint32_t), st));
-  int sl_shift = 0;
-  while ((1 << sl_shift) < c->params.short_cap) ++sl_shift;
-  if (((uint64_t)a.m << sl_shift) >= (1ull << 32))
-    return fail(SPF_E_INVALID, "assign: m * short_cap must be < 2^32 (m = %llu)", (unsigned long long)a.m);
-  DevBuf<ShortEnt> sl;
-  DevBuf<uint32_t> sl_cnt, work_count;
-  DevBuf<uint2> work;
-  const uint64_t work_cap64 = a.xnorm ? (uint64_t)a.m * 8 + 1024 : 32;   // the exact path never queues work
-  const uint32_t work_cap = work_cap64 > 0xffffff00ull ? 0xffffff00u : (uint32_t)work_cap64;
-  SPF_TRY(sl.alloc(st, (size_t)a.m << sl_shift));
-  SPF_TRY(sl_cnt.alloc(st, a.m));
-  SPF_TRY(work.alloc(st, work_cap));
-  SPF_TRY(work_count.alloc(st, 1));
-  SPF_CUDA(cudaMemsetAsync(work_count.p, 0, sizeof(uint32_t), st));
+  if (a.m > s->chunk_rows) return fail(SPF_E_INVALID, "resolve_chunk: chunk larger than planned");
+  SPF_CUDA(cudaMemsetAsync(s->work_count.p, 0, sizeof(uint32_t), st));
   SPF_CUDA(cudaMemsetAsync(a.nmem, 0, a.m * sizeof(uint32_t), st));
   ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, a.cand.rec, a.cand.info, a.cand.cap, a.nseg,
-               a.xnorm, a.xres, a.d_cstat, a.cc, a.best, a.dmin, a.nmem, ovf_rows.p, ovf_count.p,
-               a.want_members ? 1 : 0, sl.p, sl_cnt.p, sl_shift, work.p, work_count.p, work_cap, c->params.debug};
-  uint32_t n_ovf = 0;
+               a.xnorm, a.xres, a.d_cstat, a.cc, a.best, a.dmin, a.nmem, s->ovf_rows.p, s->ovf_count.p,
+               a.want_members ? 1 : 0, s->sl.p + ((size_t)r0 << s->sl_shift), s->sl_cnt.p + r0, s->sl_shift,
+               s->work.p, s->work_count.p, s->work_cap, (uint32_t)r0};
+  KernelTimer t(c, "resolve");
+  uint64_t blocks = ceil_div(a.m, RS_WARPS);
+  if (blocks > (uint64_t)c->sm_count * 8) blocks = (uint64_t)c->sm_count * 8;
   {
-    KernelTimer t(c, "resolve");
-    uint64_t blocks = ceil_div(a.m, RS_WARPS);
-    if (blocks > (uint64_t)c->sm_count * 8) blocks = (uint64_t)c->sm_count * 8;
-    {
-      KernelTimer t2(c, "classify");
-      classify_kernel<<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
-      SPF_TRY(check_launch(c, "classify_kernel"));
-    }
+    KernelTimer t2(c, "classify");
+    classify_kernel<<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+    SPF_TRY(check_launch(c, "classify_kernel"));
+  }
+  if (a.xnorm) {   // the exact path never queues work
+    KernelTimer t2(c, "exact_eval");
     const size_t ev_smem = EV_WARPS * sizeof(EvalSmem);
     SPF_CUDA(cudaFuncSetAttribute(exact_eval_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev_smem));
-    uint64_t ev_blocks = a.xnorm ? (uint64_t)c->sm_count * 3 : 1;
-    {
-      KernelTimer t2(c, "exact_eval");
-      exact_eval_kernel<METRIC><<<(unsigned)ev_blocks, EV_WARPS * 32, ev_smem, st>>>(d);
-      SPF_TRY(check_launch(c, "exact_eval_kernel"));
-    }
-    {
-      KernelTimer t2(c, "finalize");
-      finalize_kernel<METRIC><<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
-      SPF_TRY(check_launch(c, "finalize_kernel"));
-    }
-    SPF_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SPF_CUDA(cudaStreamSynchronize(st));
+    exact_eval_kernel<METRIC><<<(unsigned)c->sm_count * 3, EV_WARPS * 32, ev_smem, st>>>(d);
+    SPF_TRY(check_launch(c, "exact_eval_kernel"));
+  }
+  {
+    KernelTimer t2(c, "finalize");
+    finalize_kernel<METRIC><<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+    SPF_TRY(check_launch(c, "finalize_kernel"));
+  }
+  return SPF_OK;
+}
+
+// Overflow rows (all chunks) through the dense fallback, then the cluster-major CSR.  `a` describes
+// the whole point list (P, outputs); the candidate fields are not used.
+template <int METRIC>
+int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* csr) {
+  cudaStream_t st = c->stream;
+  ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, nullptr, nullptr, 0, 1,
+               a.xnorm, a.xres, a.d_cstat, a.cc, a.best, a.dmin, a.nmem, s->ovf_rows.p, s->ovf_count.p,
+               a.want_members ? 1 : 0, s->sl.p, s->sl_cnt.p, s->sl_shift, s->work.p, s->work_count.p,
+               s->work_cap, 0u};
+  uint32_t n_ovf = 0;
+  SPF_CUDA(cudaMemcpyAsync(&n_ovf, s->ovf_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  {
     KernelTimer t2(c, "overflow");
     SPF_TRY((run_overflow<METRIC, 0>(c, d, n_ovf, nullptr, nullptr, nullptr)));
   }
@@ -826,7 +833,7 @@ int run_resolve_t(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
   {
     uint64_t blocks = ceil_div(a.m * 32, 256);
     if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
-    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(sl.p, sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
+    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->sl.p, s->sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
                                                         keys.p, vals.p);
     SPF_TRY(check_launch(c, "fill_pairs_kernel"));
     SPF_TRY((run_overflow<METRIC, 1>(c, d, n_ovf, row_off.p, keys.p, vals.p)));
@@ -854,11 +861,46 @@ int run_resolve_t(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
 
 }  // namespace
 
-int run_resolve(spf_ctx* c, const ResolveArgs& a, CsrOut* csr) {
+int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx, ResolveState** out) {
+  cudaStream_t st = c->stream;
+  ResolveState* s = new (std::nothrow) ResolveState();
+  if (!s) return fail(SPF_E_OOM, "out of host memory");
+  s->chunk_rows = chunk_rows;
+  s->sl_shift = 0;
+  while ((1 << s->sl_shift) < c->params.short_cap) ++s->sl_shift;
+  const uint64_t work_cap64 = approx ? chunk_rows * 8 + 1024 : 32;
+  s->work_cap = work_cap64 > 0xffffff00ull ? 0xffffff00u : (uint32_t)work_cap64;
+  int rc = SPF_OK;
+  if ((chunk_rows << s->sl_shift) >= (1ull << 32)) rc = fail(SPF_E_INVALID, "assign: chunk too large");
+  if (rc >= 0) rc = s->ovf_rows.alloc(st, m_total);
+  if (rc >= 0) rc = s->ovf_count.alloc(st, 1);
+  if (rc >= 0) rc = s->sl.alloc(st, (size_t)m_total << s->sl_shift);
+  if (rc >= 0) rc = s->sl_cnt.alloc(st, m_total);
+  if (rc >= 0) rc = s->work.alloc(st, s->work_cap);
+  if (rc >= 0) rc = s->work_count.alloc(st, 1);
+  if (rc >= 0 && cudaMemsetAsync(s->ovf_count.p, 0, sizeof(uint32_t), st) != cudaSuccess)
+    rc = fail(SPF_E_CUDA, "cudaMemsetAsync failed");
+  if (rc < 0) { delete s; return rc; }
+  *out = s;
+  return SPF_OK;
+}
+
+void resolve_free(ResolveState* s) { delete s; }
+
+int resolve_chunk(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t r0) {
   switch (a.metric) {
-    case SPF_METRIC_EUCLIDEAN: return run_resolve_t<SPF_METRIC_EUCLIDEAN>(c, a, csr);
-    case SPF_METRIC_MANHATTAN: return run_resolve_t<SPF_METRIC_MANHATTAN>(c, a, csr);
-    case SPF_METRIC_CHEBYSHEV: return run_resolve_t<SPF_METRIC_CHEBYSHEV>(c, a, csr);
+    case SPF_METRIC_EUCLIDEAN: return resolve_chunk_t<SPF_METRIC_EUCLIDEAN>(c, s, a, r0);
+    case SPF_METRIC_MANHATTAN: return resolve_chunk_t<SPF_METRIC_MANHATTAN>(c, s, a, r0);
+    case SPF_METRIC_CHEBYSHEV: return resolve_chunk_t<SPF_METRIC_CHEBYSHEV>(c, s, a, r0);
+  }
+  return fail(SPF_E_INVALID, "unknown metric %d", a.metric);
+}
+
+int resolve_finish(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* csr) {
+  switch (a.metric) {
+    case SPF_METRIC_EUCLIDEAN: return resolve_finish_t<SPF_METRIC_EUCLIDEAN>(c, s, a, csr);
+    case SPF_METRIC_MANHATTAN: return resolve_finish_t<SPF_METRIC_MANHATTAN>(c, s, a, csr);
+    case SPF_METRIC_CHEBYSHEV: return resolve_finish_t<SPF_METRIC_CHEBYSHEV>(c, s, a, csr);
   }
   return fail(SPF_E_INVALID, "unknown metric %d", a.metric);
 }

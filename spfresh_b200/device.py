@@ -73,6 +73,13 @@ class Context:
         return out
 
 
+class _CtxHolder:
+    """Stands in for a Dataset as the owner reference of a result when the device copy was dropped."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+
 class Dataset:
     """spf_dataset: n x d f32 rows resident in HBM."""
 
@@ -95,6 +102,29 @@ class Dataset:
     @property
     def handle(self):
         return self._h
+
+    @classmethod
+    def assign_from_host(cls, ctx: Context, rows, metric: int, centroid_rows, boundary_factor: float = 1.1,
+                         flags: int = capi.ASSIGN_DEFAULT, keep_dataset: bool = True):
+        """spf_assign_host: upload (chunked, overlapped with compute) + assign of all rows in one call.
+        Returns (dataset or None, AssignResult)."""
+        rows = np.asarray(rows)
+        if rows.ndim != 2:
+            raise ValueError("rows must be 2-D")
+        if rows.dtype != np.float32 or rows.strides[1] != 4 or rows.strides[0] % 4 != 0 or rows.strides[0] < 4 * rows.shape[1]:
+            rows = np.ascontiguousarray(rows, dtype=np.float32)
+        cr = as_u64(centroid_rows)
+        hd, hr = C.c_void_p(), C.c_void_p()
+        check(lib().spf_assign_host(ctx.handle, ptr(rows), rows.shape[0], rows.shape[1], rows.strides[0] // 4, metric,
+                                    ptr(cr), cr.size, boundary_factor, flags,
+                                    C.byref(hd) if keep_dataset else None, C.byref(hr)))
+        ds = None
+        if keep_dataset:
+            ds = cls.__new__(cls)
+            ds.ctx, ds._h = ctx, hd
+            ds.n, ds.d = rows.shape
+        holder = ds if ds is not None else _CtxHolder(ctx)
+        return ds, AssignResult(holder, hr)
 
     def free(self):
         if self._h:

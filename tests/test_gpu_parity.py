@@ -185,6 +185,53 @@ def test_assign_tensor_equals_exact_at_scale(spf, ctx):
     assert nearest.sum() == 200_000
 
 
+def test_assign_is_chunk_invariant(spf, oracle):
+    """The point list is resolved in chunks; any chunk size must give the oracle's answer (tensor
+    and exact path, full list and subset)."""
+    c2 = spf.Context(0)
+    try:
+        data = clustered(9000, 64, 40, 5)
+        cent = np.random.default_rng(3).choice(9000, 130, replace=False)
+        ref = oracle.assign(data, 0, cent)
+        sub = np.random.default_rng(4).permutation(9000)[:5000]
+        ref_sub = oracle.assign(data, 0, cent, point_idx=sub)
+        ds = spf.Dataset(c2, data)
+        for chunk in (1000, 4096, 8999):
+            c2.set_param("chunk_rows", chunk)
+            for flags in (spf.ASSIGN_DEFAULT, spf.ASSIGN_FORCE_EXACT):
+                check_assign(ds.assign(0, cent, flags=flags).fetch(), ref)
+            check_assign(ds.assign(0, cent, point_idx=sub).fetch(), ref_sub)
+        ds.free()
+    finally:
+        c2.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_assign_host_streamed_matches_oracle(spf, oracle, metric):
+    """spf_assign_host: chunked upload overlapped with compute, rows with a stride, odd d (padding)."""
+    c2 = spf.Context(0)
+    try:
+        c2.set_param("chunk_rows", 3000)
+        wide = clustered(10000, 72, 30, 11 + metric)
+        data = wide[:, :67]                          # row stride 72 > d = 67, ld = 68
+        cent = np.random.default_rng(5).choice(10000, 96, replace=False)
+        ds, res = spf.Dataset.assign_from_host(c2, data, metric, cent)
+        ref = oracle.assign(np.ascontiguousarray(data), metric, cent)
+        check_assign(res.fetch(), ref)
+        # the returned dataset is fully resident and usable by the other entry points
+        check_assign(ds.assign(metric, cent).fetch(), ref)
+        rows = ds.update_medoids_from(metric, res, cent)
+        assert np.array_equal(rows, oracle.update_medoids(np.ascontiguousarray(data), metric, ref.offsets, ref.members, cent))
+        _, res2 = spf.Dataset.assign_from_host(c2, data, metric, cent, keep_dataset=False)
+        check_assign(res2.fetch(), ref)
+        with pytest.raises(spf.SpfError):
+            spf.Dataset.assign_from_host(c2, data, metric, [10000])
+        for obj in (res, res2, ds):              # handles must go before their context
+            obj.free()
+    finally:
+        c2.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # update_centroids / farthest / k-means++
 # ----------------------------------------------------------------------------------------------
