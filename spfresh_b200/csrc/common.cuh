@@ -47,6 +47,7 @@ struct Params {
   int kmpp_exact_sum = 1;    // 1: sequential f32 sum (bit-parity with the reference)
   int cc_matrix_max_k = 16384;  // precompute the k x k centroid-centroid matrix up to this k
   int scan_threads = 256;
+  int scan_list_major = 1;   // 0: query-major scan only, 1: automatic, 2: always list-major (k <= 32)
   int chunk_rows = 0;        // points per assign chunk (0: automatic)
 };
 

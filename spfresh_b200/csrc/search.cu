@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "kernels.cuh"
 
 using namespace spf;
@@ -256,6 +258,201 @@ scan_kernel(ScanArgs a) {
     }
   }
   if (lane == 0) a.out_counts[q] = count;
+}
+
+// ---- list-major scan ---------------------------------------------------------------------------
+// With many queries in flight most posting lists are probed by several of them.  Inverting the
+// probe table (sort of (list, query-probe) pairs) lets one CTA own one list and evaluate it
+// against batches of QB queries at a time: every vector chunk that is loaded is used QB times,
+// so the scan stops being bound by L2/HBM traffic and runs at the FP32 issue rate of the exact
+// (un-fused, sequential) distance.  Results are identical to the query-major kernel: the same
+// sequential f32 sums, the same `<= thr` filter, the same (distance, encounter index) keys.
+constexpr int LS_WARPS = 8;
+constexpr int LS_QB = 8;              // queries a warp evaluates per pass over the list
+
+struct ListScanArgs {
+  ScanArgs s;
+  const uint32_t* pair_sorted;        // (q * nprobe + p), grouped by probed list
+  const uint32_t* list_off;           // nlists + 1 offsets into pair_sorted
+  const uint32_t* unit_off;           // nlists + 1: first unit (= batch of LS_QB queries) of each list
+  unsigned long long* unit_keys;      // (nq * nprobe) x K per-(query, probe) partial top-k
+  unsigned long long* unit_slots;
+};
+
+// units per list = ceil(queries probing it / LS_QB), 0 for lists this rank does not hold
+__global__ void unit_counts_kernel(const uint32_t* __restrict__ list_off, const uint64_t* __restrict__ grp_off,
+                                   uint32_t nlists, uint32_t* __restrict__ counts) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > nlists) return;
+  uint32_t n = 0;
+  if (l < nlists && grp_off[l + 1] != grp_off[l]) n = (list_off[l + 1] - list_off[l] + LS_QB - 1) / LS_QB;
+  counts[l] = n;
+}
+
+// One CTA per unit = (list, batch of up to LS_QB queries probing it).  The batch's query vectors sit
+// in shared memory; the warps split the list's 32-vector groups round-robin, a lane computes the
+// exact squared L2 of its slot's vector to all LS_QB queries (spann_index.rs:172), and each warp
+// keeps the K smallest (distance, encounter index) keys per query; the warps' partial lists are
+// merged at the end, one query per warp.
+__global__ void __launch_bounds__(LS_WARPS * 32, 2)
+scan_lists_kernel(ListScanArgs la, uint32_t nlists) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ScanArgs& a = la.s;
+  // unit -> (list, batch): last list whose first unit is <= blockIdx.x
+  uint32_t lo = 0, hi = nlists;
+  if (blockIdx.x >= la.unit_off[nlists]) return;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (la.unit_off[mid] <= blockIdx.x) lo = mid; else hi = mid;
+  }
+  const uint32_t l = lo;
+  const uint32_t batch = blockIdx.x - la.unit_off[l];
+  const uint32_t ng = (uint32_t)(a.grp_off[l + 1] - a.grp_off[l]);
+  const uint32_t p0 = la.list_off[l] + batch * LS_QB;
+  const uint32_t nb = min((uint32_t)LS_QB, la.list_off[l + 1] - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ld4 = a.ld / 4;
+  float4* s_q = reinterpret_cast<float4*>(smem_raw);                               // LS_QB x ld4
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_q + (size_t)LS_QB * ld4);   // [warp][qi][K]
+  unsigned long long* s_pay = s_keys + (size_t)LS_WARPS * LS_QB * a.K;
+  const uint64_t G0 = a.grp_off[l];
+  const uint32_t len = a.lens[l];
+  const float4* V4 = reinterpret_cast<const float4*>(a.vecs);
+  if (threadIdx.x == 0) atomicAdd(a.bytes, (unsigned long long)nb * len * a.d * 4ull);
+
+  float thr[LS_QB];
+  uint32_t seq[LS_QB], pair[LS_QB];
+  unsigned long long key[LS_QB], pay[LS_QB], kth[LS_QB];
+#pragma unroll
+  for (int qi = 0; qi < LS_QB; ++qi) {
+    key[qi] = ~0ull; pay[qi] = ~0ull; kth[qi] = ~0ull;
+    thr[qi] = -1.0f; seq[qi] = 0; pair[qi] = 0;
+    const float4* src = nullptr;
+    if ((uint32_t)qi < nb) {
+      pair[qi] = la.pair_sorted[p0 + qi];
+      const uint32_t q = pair[qi] / a.nprobe;
+      thr[qi] = a.thr[q];
+      seq[qi] = a.seqbase[pair[qi]];
+      src = reinterpret_cast<const float4*>(a.Q + (size_t)q * a.ld);
+    }
+    for (uint32_t c = threadIdx.x; c < ld4; c += blockDim.x)
+      s_q[qi * ld4 + c] = src ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  for (uint32_t g = warp; g < ng; g += LS_WARPS) {
+    const float4* base = V4 + (G0 + g) * ld4 * 32 + lane;
+    float acc[LS_QB];
+#pragma unroll
+    for (int qi = 0; qi < LS_QB; ++qi) acc[qi] = 0.0f;
+#pragma unroll 4
+    for (uint32_t c = 0; c < ld4; ++c) {
+      const float4 v = __ldg(base + (size_t)c * 32);
+#pragma unroll
+      for (int qi = 0; qi < LS_QB; ++qi) {
+        const float4 qv = s_q[qi * ld4 + c];
+        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.x, v.x);
+        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.y, v.y);
+        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.z, v.z);
+        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.w, v.w);
+      }
+    }
+    const uint32_t pos = g * 32 + lane;
+    const bool valid = pos < len;
+#pragma unroll
+    for (int qi = 0; qi < LS_QB; ++qi) {
+      const unsigned long long ck =
+          ((unsigned long long)__float_as_uint(acc[qi]) << 32) | (unsigned long long)(seq[qi] + pos);
+      unsigned bal = __ballot_sync(0xffffffffu, valid && acc[qi] <= thr[qi] && ck < kth[qi]);
+      while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const unsigned long long k2 = __shfl_sync(0xffffffffu, ck, src);
+        if (k2 < kth[qi]) {
+          unsigned long long kk[1] = {key[qi]}, pp[1] = {pay[qi]};
+          topk_insert<1>(kk, pp, k2, (G0 + g) * 32 + src, lane);
+          key[qi] = kk[0]; pay[qi] = pp[0];
+          kth[qi] = __shfl_sync(0xffffffffu, key[qi], (a.K - 1) & 31);
+        }
+      }
+    }
+  }
+  // merge the warps' partial lists: warp w owns query w of the batch
+#pragma unroll
+  for (int qi = 0; qi < LS_QB; ++qi) {
+    if ((uint32_t)lane < a.K) {
+      s_keys[((size_t)warp * LS_QB + qi) * a.K + lane] = key[qi];
+      s_pay[((size_t)warp * LS_QB + qi) * a.K + lane] = pay[qi];
+    }
+  }
+  __syncthreads();
+  static_assert(LS_WARPS == LS_QB, "one query per warp in the final merge");
+  if ((uint32_t)warp >= nb) return;
+  unsigned long long mk[1] = {~0ull}, mp[1] = {~0ull};
+  unsigned long long mkth = ~0ull;
+  for (int w = 0; w < LS_WARPS; ++w) {
+    const unsigned long long* sk = s_keys + ((size_t)w * LS_QB + warp) * a.K;
+    const unsigned long long* sp = s_pay + ((size_t)w * LS_QB + warp) * a.K;
+    for (uint32_t e = 0; e < a.K; ++e) {
+      const unsigned long long k2 = sk[e];
+      if (k2 >= mkth) break;          // partial lists are ascending
+      topk_insert<1>(mk, mp, k2, sp[e], lane);
+      mkth = __shfl_sync(0xffffffffu, mk[0], (a.K - 1) & 31);
+    }
+  }
+  const uint32_t mypair = la.pair_sorted[p0 + warp];
+  if ((uint32_t)lane < a.K) {
+    la.unit_keys[(size_t)mypair * a.K + lane] = mk[0];
+    la.unit_slots[(size_t)mypair * a.K + lane] = mp[0];
+  }
+}
+
+// Per query: merge the (ascending) partial top-k of its nprobe probed lists.  One warp per query.
+__global__ void __launch_bounds__(256)
+merge_units_kernel(ListScanArgs la, uint64_t nq) {
+  const ScanArgs& a = la.s;
+  const int lane = threadIdx.x & 31;
+  const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  unsigned long long key[1] = {~0ull}, pay[1] = {~0ull};
+  unsigned long long kth = ~0ull;
+  for (uint32_t p = 0; p < a.nprobe; ++p) {
+    const uint32_t lst = a.probe[q * a.nprobe + p];
+    if (a.grp_off[lst + 1] == a.grp_off[lst]) continue;          // other rank's list (or empty): no unit ran
+    const unsigned long long* uk = la.unit_keys + ((size_t)q * a.nprobe + p) * a.K;
+    const unsigned long long* us = la.unit_slots + ((size_t)q * a.nprobe + p) * a.K;
+    for (uint32_t e = 0; e < a.K; ++e) {
+      const unsigned long long k2 = uk[e];
+      if (k2 >= kth) break;           // unit lists are ascending
+      topk_insert<1>(key, pay, k2, us[e], lane);
+      kth = __shfl_sync(0xffffffffu, key[0], (a.K - 1) & 31);
+    }
+  }
+  const bool ok = (uint32_t)lane < a.K && key[0] != ~0ull;
+  const uint32_t count = __popc(__ballot_sync(0xffffffffu, ok));
+  if ((uint32_t)lane < a.K) {
+    a.out_ids[q * a.K + lane] = ok ? a.slot_ids[pay[0]] : ~0ull;
+    a.out_dists[q * a.K + lane] = ok ? __uint_as_float((uint32_t)(key[0] >> 32)) : __int_as_float(0x7f800000);
+    a.out_keys[q * a.K + lane] = key[0];
+    a.out_slots[q * a.K + lane] = ok ? pay[0] : ~0ull;
+  }
+  if (lane == 0) a.out_counts[q] = count;
+}
+
+__global__ void iota_u32_kernel(uint32_t* p, uint64_t n) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = (uint32_t)t;
+}
+
+__global__ void list_offsets_kernel(const uint32_t* __restrict__ keys_sorted, uint64_t total, uint32_t nlists,
+                                    uint32_t* __restrict__ offsets) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nlists) return;
+  uint64_t lo = 0, hi = total;   // first position with key >= c
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (keys_sorted[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  offsets[c] = (uint32_t)lo;
 }
 
 __global__ void gather_vectors_kernel(const float* __restrict__ vecs, uint32_t ld, uint32_t d,
@@ -582,6 +779,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  c->kernel_ms.clear();
   const uint32_t ld = idx->ld, d = idx->d, nlists = idx->nlists;
 
   DevBuf<float> Q, thr, o_dists;
@@ -625,7 +823,56 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   a.nprobe = nprobe; a.K = k;
   a.out_ids = o_ids.p; a.out_dists = o_dists.p; a.out_counts = o_counts.p; a.out_keys = o_keys.p;
   a.out_slots = o_slots.p; a.bytes = d_bytes.p;
-  {
+  // list-major scan when the batch is large enough for lists to be shared between queries
+  const uint64_t npairs = nq * nprobe;
+  const bool list_major = k <= 32 && npairs < (1ull << 32) && c->params.scan_list_major != 0 &&
+                          (c->params.scan_list_major == 2 || npairs >= 2ull * nlists);
+  DevBuf<uint32_t> pk, pv, pk2, pv2, loff;
+  DevBuf<unsigned long long> ukeys, uslots;
+  DevBuf<uint8_t> stmp;
+  if (list_major) {
+    KernelTimer t(c, "scan");
+    SPF_TRY(pv.alloc(st, npairs));
+    SPF_TRY(pk2.alloc(st, npairs));
+    SPF_TRY(pv2.alloc(st, npairs));
+    SPF_TRY(loff.alloc(st, (size_t)nlists + 1));
+    SPF_TRY(ukeys.alloc(st, npairs * k));
+    SPF_TRY(uslots.alloc(st, npairs * k));
+    iota_u32_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(pv.p, npairs);
+    SPF_TRY(check_launch(c, "iota_u32_kernel"));
+    int end_bit = 1;
+    while (end_bit < 32 && (1ull << end_bit) < (uint64_t)nlists) ++end_bit;
+    size_t sort_bytes = 0;
+    SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, probe.p, pk2.p, pv.p, pv2.p, (int64_t)npairs, 0, end_bit, st));
+    SPF_TRY(stmp.alloc(st, sort_bytes));
+    SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sort_bytes, probe.p, pk2.p, pv.p, pv2.p, (int64_t)npairs, 0, end_bit, st));
+    c->launches += 3;
+    list_offsets_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(pk2.p, npairs, nlists, loff.p);
+    SPF_TRY(check_launch(c, "list_offsets_kernel"));
+    // units: batches of LS_QB queries per list; CTA -> unit through the scanned unit counts
+    DevBuf<uint32_t> ucnt, uoff;
+    SPF_TRY(ucnt.alloc(st, (size_t)nlists + 1));
+    SPF_TRY(uoff.alloc(st, (size_t)nlists + 1));
+    unit_counts_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(loff.p, idx->grp_off, nlists, ucnt.p);
+    SPF_TRY(check_launch(c, "unit_counts_kernel"));
+    size_t scan_bytes = 0;
+    SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
+    DevBuf<uint8_t> stmp2;
+    SPF_TRY(stmp2.alloc(st, scan_bytes));
+    SPF_CUDA(cub::DeviceScan::ExclusiveSum(stmp2.p, scan_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
+    c->launches += 2;
+    ListScanArgs la;
+    la.s = a; la.pair_sorted = pv2.p; la.list_off = loff.p; la.unit_off = uoff.p;
+    la.unit_keys = ukeys.p; la.unit_slots = uslots.p;
+    const size_t smem = (size_t)LS_QB * ld * sizeof(float) + (size_t)LS_WARPS * LS_QB * k * 16;
+    if (smem > 200 * 1024) return fail(SPF_E_INVALID, "dimension too large for the list-major scan");
+    SPF_CUDA(cudaFuncSetAttribute(scan_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t max_units = npairs / LS_QB + nlists + 1;   // upper bound; surplus CTAs exit at once
+    scan_lists_kernel<<<(unsigned)max_units, LS_WARPS * 32, smem, st>>>(la, nlists);
+    SPF_TRY(check_launch(c, "scan_lists_kernel"));
+    merge_units_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(la, nq);
+    SPF_TRY(check_launch(c, "merge_units_kernel"));
+  } else {
     KernelTimer t(c, "scan");
     if (k <= 32) SPF_TRY(launch_scan<1>(c, a, nq));
     else if (k <= 64) SPF_TRY(launch_scan<2>(c, a, nq));

@@ -417,6 +417,32 @@ def test_search_matches_oracle(spf, ctx, oracle, n, d, nlists, topk, nprobe):
         assert np.array_equal(ids2[i, :rc2[i]], rid2[i, :rc2[i]])
 
 
+def test_search_list_major_equals_query_major(spf, oracle):
+    """The list-major scan (lists shared by query batches) and the query-major scan are the same
+    function: identical ids, distance bits, counts and merge keys; the first is oracle-checked."""
+    c2 = spf.Context(0)
+    try:
+        data = clustered(20000, 64, 50, 21)
+        cent, off, mem = build_lists(oracle, data, 120, 3)
+        ds = spf.Dataset(c2, data)
+        idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+        q = clustered(1500, 64, 50, 22)
+        out = {}
+        for mode in (0, 2):
+            c2.set_param("scan_list_major", mode)
+            out[mode] = idx.search(q, 10, 16, want_keys=True)
+        for x, y in zip(out[0], out[2]):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+        rid, rd, rc = oracle.search_batch(data, off, mem, cent, q[:200], 10, 16)
+        assert np.array_equal(out[2][2][:200], rc)
+        for i in range(200):
+            assert np.array_equal(out[2][0][i, :rc[i]], rid[i, :rc[i]])
+        idx.free()
+        ds.free()
+    finally:
+        c2.close()
+
+
 def test_search_duplicates_are_kept(spf, ctx, oracle):
     """F7: a boundary-replicated point appears once per probed list it lives in."""
     data = gauss(2000, 8, 12)
