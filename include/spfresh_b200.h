@@ -116,6 +116,12 @@ int spf_distance_pairs(spf_ctx* ctx, int metric, const float* a, const float* b,
 int  spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                 const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
                 spf_assign_result** out);
+/* The same with the k centroids given as explicit vectors (k x d, row-major host memory) instead
+ * of dataset rows: the row-sharded build, where a centroid may be a row of
+ * another rank's shard. */
+int  spf_assign_vectors(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
+                        const float* centroids, uint32_t k, float boundary_factor, int flags,
+                        spf_assign_result** out);
 /* The same for rows that are still in HOST memory (the borrowed ArrayView2 of
  * src/spann/spann_builder.rs:20): uploads the n x d rows and assigns all of them to the k
  * centroid rows in one call.  The upload is chunked and overlapped with the kernels of the
@@ -145,6 +151,17 @@ int spf_update_medoids(spf_dataset* ds, int metric, const uint64_t* offsets,
                        uint64_t* new_rows, float* means_out);
 int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result* r,
                             const uint64_t* old_rows, uint64_t* new_rows, float* means_out);
+
+/* Row-sharded update_centroids (hierarchical.rs:138-181 split at its two reductions): every rank
+ * calls spf_cluster_sums on its shard's assignment, the sums / counts are all-reduced and divided
+ * (compute_mean, utils.rs:13-14), every rank calls spf_medoid_candidates with the global means,
+ * and the (distance, rank order) minimum over ranks names the new centroid (:155-171).
+ *   sums   k x d per-cluster f32 sums of this shard's member rows (member order), counts[k]
+ *   dist / row   per cluster the best local member for `means` (k x d): its distance and dataset
+ *                row, or (+inf, UINT64_MAX) when the shard has no candidate */
+int spf_cluster_sums(spf_dataset* ds, const spf_assign_result* r, float* sums, uint64_t* counts);
+int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* r, const float* means,
+                          float* dist, uint64_t* row);
 
 /* ---- k-means++ ------------------------------------------------------------------------- *
  * HierarchicalClustering::initialize_clusters_kmeans_plus_plus, hierarchical.rs:249-293.

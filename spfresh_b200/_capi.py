@@ -44,6 +44,9 @@ SIGNATURES = {
     "spf_assign": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, C.c_uint32, C.c_float, C.c_int, _vpp]),
     "spf_assign_host": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, _vp, C.c_uint32, C.c_float,
                                   C.c_int, _vpp, _vpp]),
+    "spf_assign_vectors": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, C.c_uint32, C.c_float, C.c_int, _vpp]),
+    "spf_cluster_sums": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "spf_medoid_candidates": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
     "spf_assign_points": (C.c_uint64, [_vp]),
     "spf_assign_clusters": (C.c_uint32, [_vp]),
     "spf_assign_total": (C.c_uint64, [_vp]),

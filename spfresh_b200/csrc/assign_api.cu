@@ -194,12 +194,12 @@ int assign_finish(AssignCall& a, const float* P_all, const float* xnorm_all, con
 
 }  // namespace spf
 
-extern "C" {
-
-int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
-               const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
-               spf_assign_result** out) {
-  if (!ds || !out || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
+// Shared body of spf_assign (centroids = dataset rows) and spf_assign_vectors (centroids = explicit
+// k x d host vectors, the sharded build where a centroid may live on another rank).
+static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
+                           const uint64_t* centroid_rows, const float* centroid_vecs, uint32_t k,
+                           float boundary_factor, int flags, spf_assign_result** out) {
+  if (!ds || !out || (!centroid_rows && !centroid_vecs)) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
   *out = nullptr;
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
   if (k == 0) return fail(SPF_E_INVALID, "k must be > 0 (the reference indexes centroids[0])");
@@ -216,11 +216,13 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
 
   DevBuf<uint64_t> d_crow, d_pidx;
   DevBuf<int> d_flag;
-  SPF_TRY(d_crow.alloc(st, k));
   SPF_TRY(d_flag.alloc(st, 1));
   SPF_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
-  SPF_CUDA(cudaMemcpyAsync(d_crow.p, centroid_rows, (size_t)k * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  SPF_TRY(launch_check_rows(c, d_crow.p, k, ds->n, d_flag.p));
+  if (centroid_rows) {
+    SPF_TRY(d_crow.alloc(st, k));
+    SPF_CUDA(cudaMemcpyAsync(d_crow.p, centroid_rows, (size_t)k * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    SPF_TRY(launch_check_rows(c, d_crow.p, k, ds->n, d_flag.p));
+  }
   if (point_idx) {
     SPF_TRY(d_pidx.alloc(st, m));
     SPF_CUDA(cudaMemcpyAsync(d_pidx.p, point_idx, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -239,9 +241,16 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
              assign_tc_supported(c, m, k, ld);
   a.chunk_rows = pick_chunk_rows(c, m, false);
 
-  // dense operands: centroids always gathered; points gathered only for a subset
+  // dense operands: centroids always materialised; points gathered only for a subset
   SPF_TRY(a.Cg.alloc(st, (size_t)k * ld));
-  SPF_TRY(launch_gather_rows(c, ds->x, ld, d_crow.p, k, a.Cg.p));
+  if (centroid_rows) {
+    SPF_TRY(launch_gather_rows(c, ds->x, ld, d_crow.p, k, a.Cg.p));
+  } else {
+    if (ld != ds->d) SPF_CUDA(cudaMemsetAsync(a.Cg.p, 0, (size_t)k * ld * sizeof(float), st));
+    SPF_CUDA(cudaMemcpy2DAsync(a.Cg.p, (size_t)ld * sizeof(float), centroid_vecs, (size_t)ds->d * sizeof(float),
+                               (size_t)ds->d * sizeof(float), k, cudaMemcpyHostToDevice, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+  }
   DevBuf<float> Pg, ptf_sub, xnorm_sub, xres_sub;
   const float* P = ds->x;
   const float *Ptf = nullptr, *xnorm = nullptr, *xres = nullptr;
@@ -269,6 +278,22 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
                         xres ? xres + r0 : nullptr, r0, mc));
   }
   return assign_finish(a, P, xnorm, xres, &d_pidx, out);
+}
+
+extern "C" {
+
+int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
+               const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
+               spf_assign_result** out) {
+  if (!centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
+  return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, k, boundary_factor, flags, out);
+}
+
+int spf_assign_vectors(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
+                       const float* centroids, uint32_t k, float boundary_factor, int flags,
+                       spf_assign_result** out) {
+  if (!centroids) return fail(SPF_E_INVALID, "spf_assign_vectors: NULL argument");
+  return assign_resident(ds, metric, point_idx, m, nullptr, centroids, k, boundary_factor, flags, out);
 }
 
 int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride, int metric,

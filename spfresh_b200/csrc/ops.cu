@@ -1,6 +1,8 @@
 // ops.cu — centroid update, k-means++ rounds, bisect seed and per-pair distances.
 #include <math.h>
 
+#include <vector>
+
 #include "kernels.cuh"
 #include "pairdist.cuh"
 
@@ -32,7 +34,7 @@ constexpr int WBLOCK = 1024;   // weights per block in the k-means++ pick
 // ---- compute_mean (src/clustering/utils.rs:5-15): row-by-row f32 sum in member order, then a
 // true division by m.  One thread owns 4 consecutive dimensions of one cluster.
 __global__ void cluster_mean_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t* __restrict__ offsets,
-                                    const uint64_t* __restrict__ rows, float* __restrict__ means) {
+                                    const uint64_t* __restrict__ rows, float* __restrict__ means, int divide) {
   const uint32_t c = blockIdx.x;
   const uint64_t b = offsets[c], e = offsets[c + 1];
   const float4* X4 = reinterpret_cast<const float4*>(X);
@@ -53,7 +55,7 @@ __global__ void cluster_mean_kernel(const float* __restrict__ X, uint32_t ld4, c
       const float4 v = __ldg(X4 + (size_t)rows[t] * ld4 + col);
       acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
     }
-    if (e > b) {
+    if (divide && e > b) {
       const float fm = (float)(e - b);
       acc.x = __fdiv_rn(acc.x, fm); acc.y = __fdiv_rn(acc.y, fm);
       acc.z = __fdiv_rn(acc.z, fm); acc.w = __fdiv_rn(acc.w, fm);
@@ -105,6 +107,22 @@ __global__ void medoid_finalize_kernel(const unsigned long long* __restrict__ ke
   if (e == b) out[c] = old_rows[c];                                   // :146-149
   else if (keys[c] == ~0ull) out[c] = 0;                              // identity (0, +inf)
   else out[c] = rows[b + (keys[c] & 0xffffffffull)];
+}
+
+// Sharded build: per cluster the best local member for a given mean, as (distance, dataset row);
+// (+inf, UINT64_MAX) when the shard holds no member of the cluster or no distance is < +inf.
+__global__ void medoid_candidates_kernel(const unsigned long long* __restrict__ keys,
+                                         const uint64_t* __restrict__ offsets, const uint64_t* __restrict__ rows,
+                                         uint32_t k, float* __restrict__ dist, uint64_t* __restrict__ row) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  if (keys[c] == ~0ull) {
+    dist[c] = __int_as_float(0x7f800000);
+    row[c] = ~0ull;
+  } else {
+    dist[c] = __uint_as_float((uint32_t)(keys[c] >> 32));
+    row[c] = rows[offsets[c] + (keys[c] & 0xffffffffull)];
+  }
 }
 
 // ---- farthest point (hierarchical.rs:112-126): argmax over members != c1, strict >, identity
@@ -287,7 +305,7 @@ int update_medoids_dev(spf_dataset* ds, int metric, const uint64_t* d_offsets, c
     KernelTimer t(c, "cluster_mean");
     unsigned threads = round_up(ld / 4, 32);
     if (threads > 1024) threads = 1024;
-    cluster_mean_kernel<<<k, threads, 0, st>>>(ds->x, ld / 4, d_offsets, d_rows, means.p);
+    cluster_mean_kernel<<<k, threads, 0, st>>>(ds->x, ld / 4, d_offsets, d_rows, means.p, 1);
     SPF_TRY(check_launch(c, "cluster_mean_kernel"));
   }
   expand_cluster_ids_kernel<<<k, 256, 0, st>>>(d_offsets, cid.p);
@@ -351,6 +369,78 @@ int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result
   SPF_TRY(d_rows.alloc(c->stream, r->total));
   SPF_TRY(assign_members_as_rows(r, d_rows.p));
   return update_medoids_dev(ds, metric, r->offsets, d_rows.p, r->total, r->k, old_rows, new_rows, means_out);
+}
+
+// ---- sharded build: the two halves of update_centroids, so that the mean can be
+// formed from the partial sums of all row shards and the medoid from the per-shard candidates ----
+int spf_cluster_sums(spf_dataset* ds, const spf_assign_result* r, float* sums, uint64_t* counts) {
+  if (!ds || !r || !sums || !counts) return fail(SPF_E_INVALID, "spf_cluster_sums: NULL argument");
+  if (!r->has_csr) return fail(SPF_E_STATE, "the assign result has no CSR (SPF_ASSIGN_NO_CSR)");
+  if (r->ctx != ds->ctx) return fail(SPF_E_INVALID, "result and dataset belong to different contexts");
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint32_t k = r->k, ld = ds->ld;
+  DevBuf<uint64_t> d_rows;
+  DevBuf<float> acc;
+  SPF_TRY(d_rows.alloc(st, r->total));
+  SPF_TRY(assign_members_as_rows(r, d_rows.p));
+  SPF_TRY(acc.alloc(st, (size_t)k * ld));
+  unsigned threads = round_up(ld / 4, 32);
+  if (threads > 1024) threads = 1024;
+  cluster_mean_kernel<<<k, threads, 0, st>>>(ds->x, ld / 4, r->offsets, d_rows.p, acc.p, 0);
+  SPF_TRY(check_launch(c, "cluster_mean_kernel"));
+  std::vector<uint64_t> off((size_t)k + 1);
+  SPF_CUDA(cudaMemcpy2DAsync(sums, (size_t)ds->d * sizeof(float), acc.p, (size_t)ld * sizeof(float),
+                             (size_t)ds->d * sizeof(float), k, cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(off.data(), r->offsets, ((size_t)k + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  for (uint32_t j = 0; j < k; ++j) counts[j] = off[j + 1] - off[j];
+  return SPF_OK;
+}
+
+int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* r, const float* means,
+                          float* dist, uint64_t* row) {
+  if (!ds || !r || !means || !dist || !row) return fail(SPF_E_INVALID, "spf_medoid_candidates: NULL argument");
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  if (!r->has_csr) return fail(SPF_E_STATE, "the assign result has no CSR (SPF_ASSIGN_NO_CSR)");
+  if (r->ctx != ds->ctx) return fail(SPF_E_INVALID, "result and dataset belong to different contexts");
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint32_t k = r->k, ld = ds->ld;
+  DevBuf<uint64_t> d_rows, d_row;
+  DevBuf<float> d_means, d_dist;
+  DevBuf<uint32_t> cid;
+  DevBuf<unsigned long long> keys;
+  SPF_TRY(d_rows.alloc(st, r->total));
+  SPF_TRY(assign_members_as_rows(r, d_rows.p));
+  SPF_TRY(d_means.alloc(st, (size_t)k * ld));
+  SPF_TRY(cid.alloc(st, r->total));
+  SPF_TRY(keys.alloc(st, k));
+  SPF_TRY(d_dist.alloc(st, k));
+  SPF_TRY(d_row.alloc(st, k));
+  if (ld != ds->d) SPF_CUDA(cudaMemsetAsync(d_means.p, 0, (size_t)k * ld * sizeof(float), st));
+  SPF_CUDA(cudaMemcpy2DAsync(d_means.p, (size_t)ld * sizeof(float), means, (size_t)ds->d * sizeof(float),
+                             (size_t)ds->d * sizeof(float), k, cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)k * sizeof(unsigned long long), st));
+  expand_cluster_ids_kernel<<<k, 256, 0, st>>>(r->offsets, cid.p);
+  SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
+  if (r->total) {
+    SPF_TRY(dispatch_metric(metric, [&](auto M) {
+      medoid_kernel<decltype(M)::value><<<pd_grid(c, r->total), PD_THREADS, 0, st>>>(
+          ds->x, ld, d_rows.p, cid.p, r->offsets, d_means.p, r->total, keys.p);
+      return check_launch(c, "medoid_kernel");
+    }));
+  }
+  medoid_candidates_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys.p, r->offsets, d_rows.p, k, d_dist.p, d_row.p);
+  SPF_TRY(check_launch(c, "medoid_candidates_kernel"));
+  SPF_CUDA(cudaMemcpyAsync(dist, d_dist.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(row, d_row.p, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
 }
 
 int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* members, uint64_t m,

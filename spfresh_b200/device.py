@@ -150,6 +150,33 @@ class Dataset:
         check(lib().spf_assign(self._h, metric, ptr(pi), m, ptr(cr), cr.size, boundary_factor, flags, C.byref(h)))
         return AssignResult(self, h)
 
+    def assign_vectors(self, metric: int, centroids, point_idx=None, boundary_factor: float = 1.1,
+                       flags: int = capi.ASSIGN_DEFAULT) -> "AssignResult":
+        """spf_assign_vectors: centroids as explicit k x d vectors (row-sharded build)."""
+        cv = as_f32(centroids).reshape(-1, self.d)
+        if point_idx is None:
+            pi, m = None, self.n
+        else:
+            pi = as_u64(point_idx)
+            m = pi.size
+        h = C.c_void_p()
+        check(lib().spf_assign_vectors(self._h, metric, ptr(pi), m, ptr(cv), cv.shape[0], boundary_factor, flags,
+                                       C.byref(h)))
+        return AssignResult(self, h)
+
+    def cluster_sums(self, result: "AssignResult"):
+        sums = np.zeros((result.k, self.d), np.float32)
+        counts = np.zeros(result.k, np.uint64)
+        check(lib().spf_cluster_sums(self._h, result.handle, ptr(sums), ptr(counts)))
+        return sums, counts
+
+    def medoid_candidates(self, metric: int, result: "AssignResult", means):
+        means = as_f32(means).reshape(result.k, self.d)
+        dist = np.zeros(result.k, np.float32)
+        row = np.zeros(result.k, np.uint64)
+        check(lib().spf_medoid_candidates(self._h, metric, result.handle, ptr(means), ptr(dist), ptr(row)))
+        return dist, row
+
     def update_medoids(self, metric: int, offsets, members, old_rows, want_means: bool = False):
         offsets, members, old_rows = as_u64(offsets), as_u64(members), as_u64(old_rows)
         k = old_rows.size

@@ -1,0 +1,191 @@
+"""Row-sharded k-means build step: one process per GPU, every rank owns a
+contiguous block of dataset rows, the k centroid vectors are replicated.
+
+    assign            local (no exchange): spf_assign_vectors on the rank's shard
+    update_centroids  hierarchical.rs:138-181 split at its two reductions
+                        C1  per-cluster partial sums + counts      -> all-gather, summed in rank order
+                        C2  per-cluster best local member (d, row) -> all-gather, minimum, lowest rank
+                            wins ties (= the leftmost member, shards being contiguous row ranges)
+                        the winners' vectors                       -> all-gather, selected per cluster
+
+All messages are k x d floats or smaller (2 MB at k = 4096, d = 128), so the exchange is latency
+bound; it goes through `torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU
+tests).  Partial sums are combined in rank order on every rank, which keeps the result identical
+on all ranks and reproducible; it differs from the single-process mean only by the f32 rounding
+of a different summation order (a documented near-tie class).
+
+The shard object only has to provide `n`, `d`, `assign_vectors`, `cluster_sums`,
+`medoid_candidates` and `rows` — `DeviceShard` wraps a `Dataset` on the GPU; the CPU tests plug an
+oracle-backed shard into the same exchange code.
+"""
+from __future__ import annotations
+
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------
+# communicators
+# ---------------------------------------------------------------------------------------------
+class Comm:
+    rank: int = 0
+    world: int = 1
+
+    def allgather(self, a: np.ndarray) -> List[np.ndarray]:
+        """Every rank contributes an array of the same shape / dtype; returns them in rank order."""
+        raise NotImplementedError
+
+
+class SingleComm(Comm):
+    def allgather(self, a):
+        return [np.array(a, copy=True)]
+
+
+class TorchComm(Comm):
+    """torch.distributed (NCCL: tensors staged on `device`; gloo: CPU tensors)."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device
+
+    def allgather(self, a):
+        import torch
+        a = np.ascontiguousarray(a)
+        view = a.view(np.uint8).reshape(-1)              # dtype-agnostic (uint64 has no torch dtype)
+        t = torch.from_numpy(view.copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t)
+        return [o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in outs]
+
+
+class ThreadComm(Comm):
+    """In-process ranks (threads) — used to exercise the exchange on one GPU / in CPU tests."""
+
+    class Group:
+        def __init__(self, world: int):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots: List[Optional[np.ndarray]] = [None] * world
+
+    def __init__(self, group: "ThreadComm.Group", rank: int):
+        self.g, self.rank, self.world = group, rank, group.world
+
+    def allgather(self, a):
+        self.g.slots[self.rank] = np.array(a, copy=True)
+        self.g.barrier.wait()
+        out = [np.array(x, copy=True) for x in self.g.slots]
+        self.g.barrier.wait()
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# shards
+# ---------------------------------------------------------------------------------------------
+class DeviceShard:
+    """A rank's rows resident on its B200 (spf_dataset) + the global id of its first row."""
+
+    def __init__(self, dataset, row0: int, host_rows: Optional[np.ndarray] = None):
+        self.ds, self.row0 = dataset, int(row0)
+        self.n, self.d = dataset.n, dataset.d
+        self._host = host_rows
+
+    def assign_vectors(self, metric, centroids, boundary_factor=1.1):
+        return self.ds.assign_vectors(metric, centroids, boundary_factor=boundary_factor)
+
+    def cluster_sums(self, res):
+        return self.ds.cluster_sums(res)
+
+    def medoid_candidates(self, metric, res, means):
+        return self.ds.medoid_candidates(metric, res, means)
+
+    def rows(self, local_rows: Sequence[int]) -> np.ndarray:
+        if self._host is None:
+            raise RuntimeError("DeviceShard needs host_rows to serve centroid vectors")
+        return np.asarray(self._host[np.asarray(local_rows, np.int64)], np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# the exchange
+# ---------------------------------------------------------------------------------------------
+def gather_rows(shard, comm: Comm, global_rows: np.ndarray, shard_starts: np.ndarray) -> np.ndarray:
+    """Vectors of arbitrary global rows: the owner of each row contributes it."""
+    global_rows = np.asarray(global_rows, np.int64)
+    owner = np.searchsorted(shard_starts, global_rows, side="right") - 1
+    mine = owner == comm.rank
+    part = np.zeros((global_rows.size, shard.d), np.float32)
+    if mine.any():
+        part[mine] = shard.rows(global_rows[mine] - int(shard_starts[comm.rank]))
+    parts = comm.allgather(part)
+    out = np.zeros_like(part)
+    for r in range(comm.world):
+        sel = owner == r
+        out[sel] = parts[r][sel]
+    return out
+
+
+def shard_layout(shard, comm: Comm) -> np.ndarray:
+    """Global id of every rank's first row (contiguous row sharding)."""
+    sizes = np.array([int(x[0]) for x in comm.allgather(np.array([shard.n], np.int64))], np.int64)
+    return np.concatenate([[0], np.cumsum(sizes)[:-1]])
+
+
+def update_centroids(shard, comm: Comm, metric: int, res, old_vectors: np.ndarray, old_rows: np.ndarray,
+                     shard_starts: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """One sharded update_centroids.  Returns (new global rows, new vectors, global means)."""
+    k, d = old_vectors.shape
+    sums, counts = shard.cluster_sums(res)                                   # C1, local part
+    all_sums = comm.allgather(np.ascontiguousarray(sums, np.float32))
+    all_counts = comm.allgather(np.ascontiguousarray(counts, np.uint64))
+    tot = np.zeros((k, d), np.float32)
+    cnt = np.zeros(k, np.uint64)
+    for r in range(comm.world):                                              # fixed (rank) order
+        tot = (tot + all_sums[r]).astype(np.float32)
+        cnt = cnt + all_counts[r]
+    means = np.zeros((k, d), np.float32)
+    nz = cnt > 0
+    means[nz] = (tot[nz] / cnt[nz].astype(np.float32)[:, None]).astype(np.float32)   # utils.rs:14
+
+    dist, row = shard.medoid_candidates(metric, res, means)                  # C2, local part
+    grow = np.where(row == np.uint64(np.iinfo(np.uint64).max), row, row + np.uint64(shard_starts[comm.rank]))
+    all_dist = comm.allgather(np.ascontiguousarray(dist, np.float32))
+    all_row = comm.allgather(np.ascontiguousarray(grow, np.uint64))
+    best_d = np.full(k, np.inf, np.float32)
+    best_row = np.zeros(k, np.uint64)                                        # identity (0, +inf) :163
+    for r in range(comm.world):                                              # strict <: lowest rank wins ties
+        better = all_dist[r] < best_d
+        best_d[better] = all_dist[r][better]
+        best_row[better] = all_row[r][better]
+    new_rows = np.where(nz, best_row, np.asarray(old_rows, np.uint64))       # empty cluster keeps its centroid :146-149
+    new_vecs = gather_rows(shard, comm, new_rows, shard_starts)
+    return new_rows, new_vecs, means
+
+
+class ShardedKMeans:
+    """Flat k-means iterations over row shards (the part of HierarchicalClustering.fit that is
+    data-parallel: assign_points + update_centroids)."""
+
+    def __init__(self, shard, comm: Comm, metric: int, boundary_factor: float = 1.1):
+        self.shard, self.comm, self.metric, self.factor = shard, comm, metric, boundary_factor
+        self.starts = shard_layout(shard, comm)
+        self.rows: Optional[np.ndarray] = None       # global centroid rows
+        self.vectors: Optional[np.ndarray] = None    # k x d centroid vectors
+        self.last = None                             # the rank's last assignment (device resident)
+
+    def init_rows(self, global_rows):
+        self.rows = np.asarray(global_rows, np.uint64)
+        self.vectors = gather_rows(self.shard, self.comm, self.rows, self.starts)
+
+    def step(self):
+        """assign + update; returns the cluster sizes over all shards."""
+        if self.last is not None and hasattr(self.last, "free"):
+            self.last.free()
+        self.last = self.shard.assign_vectors(self.metric, self.vectors, boundary_factor=self.factor)
+        self.rows, self.vectors, _ = update_centroids(self.shard, self.comm, self.metric, self.last,
+                                                      self.vectors, self.rows, self.starts)
+        return self.rows

@@ -232,6 +232,48 @@ def test_assign_host_streamed_matches_oracle(spf, oracle, metric):
         c2.close()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_sharded_build_step_matches_oracle_shards(spf, oracle, metric):
+    """§8(e) build: three row shards on one GPU exchanging partial sums / medoid candidates
+    in-process; every rank's device ops (spf_assign_vectors, spf_cluster_sums,
+    spf_medoid_candidates) against the oracle-backed shard, bit for bit."""
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_ref import OracleShard
+    from spfresh_b200.sharded import DeviceShard, ShardedKMeans, ThreadComm
+    data = clustered(2600, 20, 16, 77 + metric)
+    init = np.random.default_rng(8).choice(2600, 16, replace=False)
+    bounds = [0, 700, 1500, 2600]
+
+    def run_all(make_shard):
+        grp = ThreadComm.Group(3)
+        out = [None] * 3
+
+        def run(r):
+            km = ShardedKMeans(make_shard(r), ThreadComm(grp, r), metric)
+            km.init_rows(init)
+            rows = [np.array(km.step(), copy=True) for _ in range(2)]
+            out[r] = (rows, np.array(km.vectors, copy=True))
+        th = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return out
+    ctxs = [spf.Context(0) for _ in range(3)]
+    try:
+        dss = [spf.Dataset(ctxs[r], data[bounds[r]:bounds[r + 1]]) for r in range(3)]
+        got = run_all(lambda r: DeviceShard(dss[r], bounds[r], data[bounds[r]:bounds[r + 1]]))
+        ref = run_all(lambda r: OracleShard(data[bounds[r]:bounds[r + 1]], bounds[r]))
+        for r in range(3):
+            assert all(np.array_equal(a, b) for a, b in zip(got[r][0], ref[r][0]))
+            assert np.array_equal(got[r][1].view(np.uint32), ref[r][1].view(np.uint32))
+        for d_ in dss:
+            d_.free()
+    finally:
+        for c_ in ctxs:
+            c_.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # update_centroids / farthest / k-means++
 # ----------------------------------------------------------------------------------------------

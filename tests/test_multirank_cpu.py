@@ -75,3 +75,83 @@ def test_list_sharded_merge_over_gloo():
     ok = mp.get_context("spawn").Array("i", [0, 0])
     mp.spawn(worker, args=(2, port, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
+
+
+# ----------------------------------------------------------------------------------------------
+# row-sharded build: partial sums / counts and medoid candidates exchanged over gloo
+# ----------------------------------------------------------------------------------------------
+def sharded_inputs():
+    g = np.random.Generator(np.random.Philox(key=31))
+    cen = 3.0 * g.standard_normal((12, 10), dtype=np.float32)
+    data = (cen[g.integers(0, 12, 900)] + 0.4 * g.standard_normal((900, 10), dtype=np.float32)).astype(np.float32)
+    init = np.random.default_rng(2).choice(900, 12, replace=False)
+    return data, init
+
+
+def run_sharded(comm, data, init, bounds, metric, iters=3):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_ref import OracleShard
+    from spfresh_b200.sharded import ShardedKMeans
+    lo, hi = bounds[comm.rank], bounds[comm.rank + 1]
+    km = ShardedKMeans(OracleShard(data[lo:hi], lo), comm, metric)
+    km.init_rows(init)
+    hist = []
+    for _ in range(iters):
+        hist.append(np.array(km.step(), copy=True))
+    return hist, km.vectors
+
+
+def sharded_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spfresh_b200.sharded import TorchComm
+    data, init = sharded_inputs()
+    hist, vecs = run_sharded(TorchComm(), data, init, [0, 400, 900], 0)
+    out = np.concatenate([h.astype(np.float64) for h in hist] + [vecs.astype(np.float64).ravel()])
+    t = torch.from_numpy(out)
+    got = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(got, t)
+    same = all(torch.equal(got[0], g) for g in got)              # every rank ends with the same centroids
+    ok[rank] = 1 if same else 0
+    if rank == 0:
+        np.save(os.path.join(os.environ["SPF_TEST_TMP"], "gloo_rows.npy"), np.stack(hist))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_update_over_gloo(tmp_path):
+    """World size 2 over gloo == the same two shards exchanged in-process (ThreadComm), and the
+    sharded medoids agree with the single-process oracle on this well-separated data."""
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import oracle
+    from spfresh_b200.sharded import SingleComm, ThreadComm
+    oracle.build()
+    os.environ["SPF_TEST_TMP"] = str(tmp_path)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(sharded_worker, args=(2, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+    gloo_rows = np.load(tmp_path / "gloo_rows.npy")
+
+    data, init = sharded_inputs()
+    grp = ThreadComm.Group(2)
+    res = [None, None]
+
+    def run(r):
+        res[r] = run_sharded(ThreadComm(grp, r), data, init, [0, 400, 900], 0)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert np.array_equal(np.stack(res[0][0]), gloo_rows) and np.array_equal(np.stack(res[1][0]), gloo_rows)
+    # one shard holding everything == the reference's own update_centroids, bit for bit
+    single, _ = run_sharded(SingleComm(), data, init, [0, 900], 0, iters=1)
+    a = oracle.assign(data, 0, init)
+    assert np.array_equal(single[0], oracle.update_medoids(data, 0, a.offsets, a.members, init.astype(np.uint64)))
+    # two shards: same medoids (the mean differs only in f32 summation order; no near-tie here)
+    assert np.array_equal(gloo_rows[0], single[0])
