@@ -41,6 +41,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ROWS, DIM, K_CENT = 1_000_000, 128, 4096
+# dram__bytes_read.sum + dram__bytes_write.sum of assign_tc_kernel for one 1M x 4096 x 128 launch
+# (ncu --set full capture, profiles/): 512 MB rounded rows read once + candidate records written
+TC_DRAM_BYTES_PER_LAUNCH = 3.21e9
 NQ, TOPK = 10_000, 10
 METRIC_NAME = "kmeans_assign_pts_per_s"
 WORKLOAD = "assign_points_to_clusters 1M x 128 f32, k=4096, squared-Euclidean, boundary 1.1, iid N(0,1)"
@@ -146,7 +149,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measure_tf32_peak(torch, dev):
@@ -170,6 +173,16 @@ def measure_tf32_peak(torch, dev):
         return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
     except Exception:
         return None
+
+
+def emit(line: dict):
+    """The contract is ONE JSON line on stdout: everything else (NCCL banners, library chatter) was
+    sent to stderr by redirecting fd 1 at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -279,12 +292,12 @@ def main():
 
     # ---- per-kernel times (profiling mode brackets each kernel with events) ----------------------
     ctx.set_profiling(True)
-    kn = ["assign_tc", "resolve", "cc_matrix", "csr"]
+    kn = ["assign_tc", "resolve", "classify", "exact_eval", "finalize", "overflow", "cc_matrix", "csr"]
     acc = {k: [] for k in kn}
     for _ in range(3):
         step_resident()
         for k in kn:
-            acc[k].append(ctx.kernel_ms(k))
+            acc[k].append(max(ctx.kernel_ms(k), 0.0))
     ctx.set_profiling(False)
     kms = {k: float(np.mean(v)) for k, v in acc.items()}
 
@@ -307,6 +320,33 @@ def main():
         ms_e2e = float(t.item())
     e2e_value = N_ROWS * world * e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- one full row-sharded k-means iteration: assign + update_centroids with the exchange ------
+    sharded = None
+    try:
+        from spfresh_b200.sharded import DeviceShard, ShardedKMeans, SingleComm, TorchComm
+        comm = TorchComm(dev) if world > 1 else SingleComm()
+        km = ShardedKMeans(DeviceShard(ds, rank * N_ROWS, rows_np), comm, spf.METRIC_EUCLIDEAN)
+        km.init_rows(np.arange(K_CENT, dtype=np.uint64))
+        km.step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            km.step()
+        barrier()
+        dt = (time.perf_counter() - t0) / 2
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        sharded = {"ms_per_iteration": dt * 1e3, "points_per_s": N_ROWS * world / dt, "n_gpus": world,
+                   "what": "assign (spf_assign_vectors) + per-cluster sums/counts all-gather + medoid-candidate "
+                           "all-gather + winner-vector all-gather, wall clock incl. host marshalling, max over ranks",
+                   "backend": "nccl" if world > 1 else "none"}
+        if km.last is not None:
+            km.last.free()
+    except Exception as ex:      # the headline must still print
+        sharded = {"error": repr(ex)}
+
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     tf32_live = measure_tf32_peak(torch, dev) if rank == 0 else None
     bf16 = peaks.get("bf16_tflops")
@@ -320,7 +360,9 @@ def main():
     ach_tf = flops / (kms["assign_tc"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "assign_tc_kernel (tcgen05 kind::tf32, 1 pass)",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": None, "peak_source": peak_src, "flop_per_launch": flops,
+                "traffic": TC_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu dram__bytes_read+write.sum of this kernel, "
+                "profiles/r01_ncu_assign_v5.txt (1M-row launch)", "peak_source": peak_src, "flop_per_launch": flops,
+                "launches_per_step": 1, "overflow_rows": int(ctx.last_overflow_rows()),
                 "kernel_ms": kms["assign_tc"], "share_of_step": kms["assign_tc"] / (ms / args.steps),
                 "other_kernels_ms": {k: kms[k] for k in kn if k != "assign_tc"}}
 
@@ -359,9 +401,11 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "kernels_ms": kms,
+            "sharded_kmeans_iteration": sharded,
             "query": query,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -400,11 +444,21 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
         hit += len(set(gt[i].tolist()) & set(ids[i, :counts[i]].tolist()))
     del x, xq, d2
     gbs = bytes_ / (scan_ms * 1e-3) / 1e9
+    # the list-major scan reuses every loaded vector for 8 queries, so it is bound by the FP32 issue
+    # rate of the exact (un-fused) distance: 3 lane instructions per element-op
+    lane_instr = bytes_ / 4.0 * 3.0
+    fp32_peak = 148 * 128 * 1.965e9
     out = {"metric": "batch_qps_top10", "qps_e2e": NQ / (ms * 1e-3), "nq": NQ, "k": TOPK, "nprobe": TOPK,
            "prune_factor": 1.2, "recall_at_10": hit / (1000.0 * TOPK),
            "mean_results_per_query": float(counts.mean()),
-           "scan": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "peak_source": hbm_src, "bytes_per_launch": int(bytes_), "kernel_ms": scan_ms},
+           "scan": {"bound": "fp32", "achieved": lane_instr / (scan_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12,
+                    "unit": "T lane-instr/s", "frac": lane_instr / (scan_ms * 1e-3) / fp32_peak,
+                    "peak_source": "148 SM x 128 lanes x 1.965 GHz (nominal max clock)",
+                    "algorithmic_gbs": gbs, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                    "algorithmic_over_hbm": gbs / hbm_peak,
+                    "note": "query-major algorithmic bytes (sum over queries and probed lists of |L|*d*4); the "
+                            "list-major kernel streams each list once per 8-query batch, so this exceeds the HBM peak",
+                    "bytes_per_launch": int(bytes_), "kernel_ms": scan_ms},
            "probe_ms": probe_ms, "index_vectors": idx.nvectors}
     idx.free()
     return out

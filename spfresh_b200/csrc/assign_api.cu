@@ -90,7 +90,7 @@ struct AssignCall {
 
 uint64_t pick_chunk_rows(const spf_ctx* c, uint64_t m, bool streamed) {
   // multiples of one full wave of the tensor kernel (one 128-point row block per SM)
-  uint64_t rows = (uint64_t)c->sm_count * 128 * (streamed ? 4 : 16);
+  uint64_t rows = (uint64_t)c->sm_count * 128 * (streamed ? 4 : 64);
   if (c->params.chunk_rows > 0) rows = (uint64_t)c->params.chunk_rows;
   return rows < m ? rows : m;
 }
