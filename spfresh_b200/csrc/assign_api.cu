@@ -126,7 +126,7 @@ int assign_setup(AssignCall& a) {
   SPF_TRY(a.best.alloc(st, a.m));
   SPF_TRY(a.dmin.alloc(st, a.m));
   SPF_TRY(a.nmem.alloc(st, a.m));
-  SPF_TRY(resolve_begin(c, a.m, a.chunk_rows, a.use_tc, &a.rs));
+  SPF_TRY(resolve_begin(c, a.m, a.chunk_rows, a.use_tc, a.want_members, &a.rs));
   return SPF_OK;
 }
 

@@ -251,7 +251,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const float f1 = fmaxf(a.factor, 1.0f);
     const uint32_t segcap = (uint32_t)a.cap >> 1;
     const uint32_t segbytes = segcap * (uint32_t)sizeof(CandRec);
-    volatile unsigned long long* pub = reinterpret_cast<volatile unsigned long long*>(smem + SMEM_PUB_OFF);
+    const uint32_t pub_mine = smem_u32(smem + SMEM_PUB_OFF) + (half * BM + lrow) * 8u;
+    const uint32_t pub_other = smem_u32(smem + SMEM_PUB_OFF) + ((half ^ 1u) * BM + lrow) * 8u;
     uint32_t tcount = 0;
     for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
       const uint32_t row = rb * BM + lrow;
@@ -294,9 +295,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           {   // exchange running minima with the partner half of the same row (tagged with the row
               // block: any value published for this row block is a valid upper bound of the final
               // minimum, so a stale one only makes the candidate set a little larger)
-            const unsigned long long pv = pub[(half ^ 1) * BM + lrow];
-            if ((uint32_t)(pv >> 32) == rb) tshare = fminf(tshare, __uint_as_float((uint32_t)pv));
-            pub[half * BM + lrow] = ((unsigned long long)rb << 32) | __float_as_uint(tmin);
+            uint32_t pv_lo, pv_hi;
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pub_other) : "memory");
+            if (pv_hi == rb) tshare = fminf(tshare, __uint_as_float(pv_lo));
+            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(tmin)), "r"(rb) : "memory");
           }
           // candidate test  d < f (dmin_run + E) + E  with d = t + |x|^2
           const float thr_t = row_ok ? fmaf(f1, tshare + xnE, EmX) + slop : -INF;

@@ -120,7 +120,8 @@ struct CsrOut {
 //   resolve_finish  dense fallback for the overflow rows of all chunks, then the CSR (csr == NULL
 //                   skips it); `a` describes the whole list (candidate fields unused)
 struct ResolveState;
-int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx, ResolveState** out);
+int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx, bool want_members,
+                  ResolveState** out);
 int resolve_chunk(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t r0);
 int resolve_finish(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* csr);
 void resolve_free(ResolveState* s);

@@ -50,7 +50,8 @@ constexpr uint32_t SE_TEST_NOCC = 3u << 2;  // same, best was not known yet: cc 
 // Per-call state shared by the chunks of one assign (kernels.cuh: resolve_begin / _chunk / _finish).
 struct ResolveState {
   DevBuf<uint32_t> ovf_rows, ovf_count, sl_cnt, work_count;
-  DevBuf<ShortEnt> sl;
+  DevBuf<uint32_t> memlist;      // m_total x (1 << sl_shift) member slots, kept until the CSR is built
+  DevBuf<ShortEnt> sl;           // one chunk's short lists
   DevBuf<uint2> work;
   int sl_shift = 0;
   uint32_t work_cap = 0;
@@ -68,6 +69,7 @@ struct ResolveDev {
   uint32_t* ovf_rows; uint32_t* ovf_count;
   int want_members;
   ShortEnt* sl; uint32_t* sl_cnt; int sl_shift;   // short list: 1 << sl_shift (<= 64) entries per point
+  uint32_t* memlist;                              // member slots of this chunk's points, same stride
   // work list of exact evaluations: (short-list index, centroid slot) pairs appended by classify
   uint2* work; uint32_t* work_count; uint32_t work_cap;
   uint32_t row_base;   // first row of this chunk in the whole point list (ovf_rows holds global rows)
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
       }
       member |= mem ? (1u << u) : 0u;
     }
-    // member list (uint32 slots) at the front of the row's short list; all entries are in registers
+    // member list (uint32 slots) of the row
     const uint32_t mine = (uint32_t)__popc(member);
     uint32_t incl = mine;
 #pragma unroll
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
     uint32_t out = __shfl_sync(0xffffffffu, incl, 31);
     best_listed = __any_sync(0xffffffffu, best_listed);
     __syncwarp();
-    uint32_t* memlist = reinterpret_cast<uint32_t*>(sl);
+    uint32_t* memlist = a.memlist + ((size_t)r << a.sl_shift);
     uint32_t pos = incl - mine;
 #pragma unroll
     for (int u = 0; u < FN_MAX; ++u)
@@ -719,7 +721,7 @@ struct CountOp {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)(v & ~NMEM_OVERFLOW_BIT); }
 };
 
-__global__ void fill_pairs_kernel(const ShortEnt* __restrict__ sl, int sl_shift, const uint32_t* __restrict__ nmem,
+__global__ void fill_pairs_kernel(const uint32_t* __restrict__ memlist, int sl_shift, const uint32_t* __restrict__ nmem,
                                   const uint64_t* __restrict__ row_off, uint32_t m,
                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const int lane = threadIdx.x & 31;
@@ -728,7 +730,7 @@ __global__ void fill_pairs_kernel(const ShortEnt* __restrict__ sl, int sl_shift,
     const uint32_t nm = nmem[r];
     if (nm & NMEM_OVERFLOW_BIT) continue;
     const uint64_t off = row_off[r];
-    const uint32_t* mem = reinterpret_cast<const uint32_t*>(sl + ((size_t)r << sl_shift));
+    const uint32_t* mem = memlist + ((size_t)r << sl_shift);
     for (uint32_t s = lane; s < nm; s += 32) {
       keys[off + s] = mem[s];
       vals[off + s] = r;
@@ -761,7 +763,8 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   SPF_CUDA(cudaMemsetAsync(a.nmem, 0, a.m * sizeof(uint32_t), st));
   ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, a.cand.rec, a.cand.info, a.cand.cap, a.nseg,
                a.xnorm, a.xres, a.d_cstat, a.cc, a.best, a.dmin, a.nmem, s->ovf_rows.p, s->ovf_count.p,
-               a.want_members ? 1 : 0, s->sl.p + ((size_t)r0 << s->sl_shift), s->sl_cnt.p + r0, s->sl_shift,
+               a.want_members ? 1 : 0, s->sl.p, s->sl_cnt.p, s->sl_shift,
+               a.want_members ? s->memlist.p + ((size_t)r0 << s->sl_shift) : nullptr,
                s->work.p, s->work_count.p, s->work_cap, (uint32_t)r0};
   KernelTimer t(c, "resolve");
   uint64_t blocks = ceil_div(a.m, RS_WARPS);
@@ -793,8 +796,8 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   cudaStream_t st = c->stream;
   ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, nullptr, nullptr, 0, 1,
                a.xnorm, a.xres, a.d_cstat, a.cc, a.best, a.dmin, a.nmem, s->ovf_rows.p, s->ovf_count.p,
-               a.want_members ? 1 : 0, s->sl.p, s->sl_cnt.p, s->sl_shift, s->work.p, s->work_count.p,
-               s->work_cap, 0u};
+               a.want_members ? 1 : 0, s->sl.p, s->sl_cnt.p, s->sl_shift, s->memlist.p, s->work.p,
+               s->work_count.p, s->work_cap, 0u};
   uint32_t n_ovf = 0;
   SPF_CUDA(cudaMemcpyAsync(&n_ovf, s->ovf_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
@@ -833,7 +836,7 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   {
     uint64_t blocks = ceil_div(a.m * 32, 256);
     if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
-    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->sl.p, s->sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
+    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->memlist.p, s->sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
                                                         keys.p, vals.p);
     SPF_TRY(check_launch(c, "fill_pairs_kernel"));
     SPF_TRY((run_overflow<METRIC, 1>(c, d, n_ovf, row_off.p, keys.p, vals.p)));
@@ -861,7 +864,8 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
 
 }  // namespace
 
-int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx, ResolveState** out) {
+int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx, bool want_members,
+                  ResolveState** out) {
   cudaStream_t st = c->stream;
   ResolveState* s = new (std::nothrow) ResolveState();
   if (!s) return fail(SPF_E_OOM, "out of host memory");
@@ -874,8 +878,9 @@ int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx
   if ((chunk_rows << s->sl_shift) >= (1ull << 32)) rc = fail(SPF_E_INVALID, "assign: chunk too large");
   if (rc >= 0) rc = s->ovf_rows.alloc(st, m_total);
   if (rc >= 0) rc = s->ovf_count.alloc(st, 1);
-  if (rc >= 0) rc = s->sl.alloc(st, (size_t)m_total << s->sl_shift);
-  if (rc >= 0) rc = s->sl_cnt.alloc(st, m_total);
+  if (rc >= 0) rc = s->sl.alloc(st, (size_t)chunk_rows << s->sl_shift);
+  if (rc >= 0) rc = s->sl_cnt.alloc(st, chunk_rows);
+  if (rc >= 0 && want_members) rc = s->memlist.alloc(st, (size_t)m_total << s->sl_shift);
   if (rc >= 0) rc = s->work.alloc(st, s->work_cap);
   if (rc >= 0) rc = s->work_count.alloc(st, 1);
   if (rc >= 0 && cudaMemsetAsync(s->ovf_count.p, 0, sizeof(uint32_t), st) != cudaSuccess)
