@@ -94,6 +94,9 @@ int  spf_dataset_upload(spf_ctx* ctx, const float* rows, uint64_t n, uint32_t d,
 int  spf_dataset_from_device(spf_ctx* ctx, const void* dev_rows, uint64_t n, uint32_t d,
                              spf_dataset** out);
 void spf_dataset_free(spf_dataset* ds);
+/* Copies m dataset rows (m x d, row-major) back to the host: out[i] = row rows[i].  The reference
+ * indexes its host ArrayView2 directly; shards created on the device need this instead. */
+int  spf_dataset_fetch_rows(spf_dataset* ds, const uint64_t* rows, uint64_t m, float* out);
 uint64_t spf_dataset_rows(const spf_dataset* ds);
 uint32_t spf_dataset_dim(const spf_dataset* ds);
 

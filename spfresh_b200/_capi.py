@@ -38,6 +38,7 @@ SIGNATURES = {
     "spf_dataset_upload": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, _vpp]),
     "spf_dataset_from_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, _vpp]),
     "spf_dataset_free": (None, [_vp]),
+    "spf_dataset_fetch_rows": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "spf_dataset_rows": (C.c_uint64, [_vp]),
     "spf_dataset_dim": (C.c_uint32, [_vp]),
     "spf_distance_pairs": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint32, C.c_uint64, _vp]),

@@ -229,6 +229,27 @@ void spf_dataset_free(spf_dataset* ds) {
   delete ds;
 }
 
+int spf_dataset_fetch_rows(spf_dataset* ds, const uint64_t* rows, uint64_t m, float* out) {
+  if (!ds || (!rows && m) || (!out && m)) return fail(SPF_E_INVALID, "spf_dataset_fetch_rows: NULL argument");
+  if (m == 0) return SPF_OK;
+  for (uint64_t i = 0; i < m; ++i)
+    if (rows[i] >= ds->n) return fail(SPF_E_INVALID, "row %llu >= n", (unsigned long long)rows[i]);
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  spf::DevBuf<uint64_t> d_idx;
+  spf::DevBuf<float> g;
+  SPF_TRY(d_idx.alloc(st, m));
+  SPF_TRY(g.alloc(st, (size_t)m * ds->ld));
+  SPF_CUDA(cudaMemcpyAsync(d_idx.p, rows, m * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  SPF_TRY(spf::launch_gather_rows(c, ds->x, ds->ld, d_idx.p, m, g.p));
+  SPF_CUDA(cudaMemcpy2DAsync(out, (size_t)ds->d * sizeof(float), g.p, (size_t)ds->ld * sizeof(float),
+                             (size_t)ds->d * sizeof(float), m, cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
+}
+
 uint64_t spf_dataset_rows(const spf_dataset* ds) { return ds ? ds->n : 0; }
 uint32_t spf_dataset_dim(const spf_dataset* ds) { return ds ? ds->d : 0; }
 

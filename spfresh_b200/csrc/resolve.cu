@@ -693,25 +693,30 @@ __global__ void gather_rows32_kernel(const float* __restrict__ src, uint32_t ld4
 
 constexpr uint32_t OVF_BATCH = 4096;   // overflow rows per dense batch (4096 x k x 4 bytes of scratch)
 
-// Runs PHASE over all overflow rows, OVF_BATCH at a time (the dense block is recomputed per phase
-// so the scratch stays bounded whatever the number of overflow rows).
+// Runs PHASE over all overflow rows, OVF_BATCH at a time.  When `keep` is given (n_ovf x k floats,
+// used when that fits the budget) PHASE 0 stores every batch's dense block there and PHASE 1 reuses
+// it; otherwise the block is recomputed per phase so the scratch stays bounded.
 template <int METRIC, int PHASE>
-int run_overflow(spf_ctx* c, const ResolveDev& d, uint32_t n_ovf, const uint64_t* row_off, uint32_t* keys,
-                 uint32_t* vals) {
+int run_overflow(spf_ctx* c, const ResolveDev& d, uint32_t n_ovf, float* keep, const uint64_t* row_off,
+                 uint32_t* keys, uint32_t* vals) {
   if (n_ovf == 0) return SPF_OK;
   cudaStream_t st = c->stream;
   const uint32_t nb_max = n_ovf < OVF_BATCH ? n_ovf : OVF_BATCH;
   DevBuf<float> rows, dense;
-  SPF_TRY(rows.alloc(st, (size_t)nb_max * d.ld));
-  SPF_TRY(dense.alloc(st, (size_t)nb_max * d.k));
+  const bool compute = !(keep && PHASE == 1);
+  if (compute) SPF_TRY(rows.alloc(st, (size_t)nb_max * d.ld));
+  if (!keep) SPF_TRY(dense.alloc(st, (size_t)nb_max * d.k));
   for (uint32_t b0 = 0; b0 < n_ovf; b0 += OVF_BATCH) {
     const uint32_t nb = (n_ovf - b0) < OVF_BATCH ? (n_ovf - b0) : OVF_BATCH;
-    const uint64_t total = (uint64_t)nb * (d.ld / 4);
-    gather_rows32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d.P, d.ld / 4, d.ovf_rows + b0, nb, rows.p);
-    SPF_TRY(check_launch(c, "gather_rows32_kernel"));
-    SPF_TRY(launch_assign_exact(c, METRIC, rows.p, nb, d.C, d.k, d.ld, 1.0f, nullptr, dense.p));
+    float* blk = keep ? keep + (size_t)b0 * d.k : dense.p;
+    if (compute) {
+      const uint64_t total = (uint64_t)nb * (d.ld / 4);
+      gather_rows32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d.P, d.ld / 4, d.ovf_rows + b0, nb, rows.p);
+      SPF_TRY(check_launch(c, "gather_rows32_kernel"));
+      SPF_TRY(launch_assign_exact(c, METRIC, rows.p, nb, d.C, d.k, d.ld, 1.0f, nullptr, blk));
+    }
     const unsigned grid = nb < (uint32_t)c->sm_count * 8 ? nb : (unsigned)c->sm_count * 8;
-    overflow_rows_kernel<METRIC, PHASE><<<grid, 256, 0, st>>>(d, dense.p, d.ovf_rows + b0, nb, row_off, keys, vals);
+    overflow_rows_kernel<METRIC, PHASE><<<grid, 256, 0, st>>>(d, blk, d.ovf_rows + b0, nb, row_off, keys, vals);
     SPF_TRY(check_launch(c, "overflow_rows_kernel"));
   }
   return SPF_OK;
@@ -801,9 +806,13 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   uint32_t n_ovf = 0;
   SPF_CUDA(cudaMemcpyAsync(&n_ovf, s->ovf_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
+  // dense blocks of the overflow rows are kept between the two phases when they fit 16 GB
+  DevBuf<float> keep;
+  const bool keep_dense = csr != nullptr && n_ovf > 0 && (uint64_t)n_ovf * a.k * sizeof(float) <= (16ull << 30);
+  if (keep_dense) SPF_TRY(keep.alloc(st, (size_t)n_ovf * a.k));
   {
     KernelTimer t2(c, "overflow");
-    SPF_TRY((run_overflow<METRIC, 0>(c, d, n_ovf, nullptr, nullptr, nullptr)));
+    SPF_TRY((run_overflow<METRIC, 0>(c, d, n_ovf, keep.p, nullptr, nullptr, nullptr)));
   }
   c->last_overflow_rows = n_ovf;
   if (!csr) return SPF_OK;
@@ -839,7 +848,7 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
     fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->memlist.p, s->sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
                                                         keys.p, vals.p);
     SPF_TRY(check_launch(c, "fill_pairs_kernel"));
-    SPF_TRY((run_overflow<METRIC, 1>(c, d, n_ovf, row_off.p, keys.p, vals.p)));
+    SPF_TRY((run_overflow<METRIC, 1>(c, d, n_ovf, keep.p, row_off.p, keys.p, vals.p)));
   }
   // stable sort by cluster slot keeps the input order inside every cluster (:353-361)
   int end_bit = 1;

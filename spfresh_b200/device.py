@@ -126,6 +126,12 @@ class Dataset:
         holder = ds if ds is not None else _CtxHolder(ctx)
         return ds, AssignResult(holder, hr)
 
+    def fetch_rows(self, rows) -> np.ndarray:
+        rows = as_u64(rows)
+        out = np.empty((rows.size, self.d), np.float32)
+        check(lib().spf_dataset_fetch_rows(self._h, ptr(rows), rows.size, ptr(out)))
+        return out
+
     def free(self):
         if self._h:
             lib().spf_dataset_free(self._h)

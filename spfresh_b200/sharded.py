@@ -105,8 +105,8 @@ class DeviceShard:
         return self.ds.medoid_candidates(metric, res, means)
 
     def rows(self, local_rows: Sequence[int]) -> np.ndarray:
-        if self._host is None:
-            raise RuntimeError("DeviceShard needs host_rows to serve centroid vectors")
+        if self._host is None:                       # shard created on the device: read the rows back
+            return self.ds.fetch_rows(np.asarray(local_rows, np.uint64))
         return np.asarray(self._host[np.asarray(local_rows, np.int64)], np.float32)
 
 
