@@ -19,11 +19,6 @@ __global__ void positions_to_rows_kernel(const uint32_t* __restrict__ pos, const
   if (t < total) out[t] = pidx ? pidx[pos[t]] : (uint64_t)pos[t];
 }
 
-__global__ void pad_inf_kernel(float* p, uint32_t from, uint32_t to) {
-  const uint32_t t = from + blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < to) p[t] = __int_as_float(0x7f800000);
-}
-
 }  // namespace
 
 int assign_members_as_rows(const spf_assign_result* r, uint64_t* d_out) {
@@ -78,7 +73,7 @@ struct AssignCall {
   float factor = 1.0f;
   bool want_members = true, use_tc = false;
   uint64_t m = 0, chunk_rows = 0;
-  DevBuf<float> Cg, ctf, cnorm, cres, cstat, cc;
+  DevBuf<float> Cg, ctf, cnorm, cres, cstat, cext, cc;
   DevBuf<CandRec> cand_rec;
   DevBuf<RowInfo> cand_info;
   CandBuf cand;
@@ -112,10 +107,8 @@ int assign_setup(AssignCall& a) {
     SPF_TRY(a.cstat.alloc(st, 2));
     SPF_TRY(launch_row_prep(c, a.Cg.p, a.ld, nullptr, a.k, a.ctf.p, a.cnorm.p, a.cres.p));
     SPF_TRY(launch_max2_f32(c, a.cnorm.p, a.cres.p, a.k, a.cstat.p));
-    if (kpad > a.k) {
-      pad_inf_kernel<<<(kpad - a.k + 255) / 256, 256, 0, st>>>(a.cnorm.p, a.k, kpad);
-      SPF_TRY(check_launch(c, "pad_inf_kernel"));
-    }
+    SPF_TRY(a.cext.alloc(st, (size_t)kpad * 8));
+    SPF_TRY(launch_centroid_ext(c, a.cnorm.p, a.k, kpad, a.cext.p));
   }
   // exact centroid-centroid distances for the boundary rule `d(c_best, c_j) >= d_j` (:337-342)
   if (a.want_members && a.k > 1 && (int)a.k <= c->params.cc_matrix_max_k) {
@@ -148,7 +141,7 @@ int assign_rows(AssignCall& a, const float* P, const float* Ptf, const float* xn
   spf_ctx* c = a.c;
   if (a.use_tc) {
     KernelTimer t(c, "assign_tc");
-    SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cnorm.p, a.cstat.p, a.factor, a.cand));
+    SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cext.p, a.cstat.p, a.factor, a.cand));
   } else {
     KernelTimer t(c, "assign_exact");
     SPF_TRY(launch_assign_exact(c, a.metric, P, mc, a.Cg.p, a.k, a.ld, a.factor, &a.cand, nullptr));

@@ -3,8 +3,10 @@
 // Replaces the Euclidean case of the n x k distance loop in assign_points_to_clusters,
 // src/clustering/hierarchical.rs:302-326 (reference).  d(x,c) = |x|^2 - 2 x.c + |c|^2 is a dense
 // contraction: X.C^T runs on the 5th-gen tensor cores as ONE TF32 pass with fp32 accumulation
-// in TMEM; the m x k matrix is never written.  The epilogue keeps, per point, a running
-// minimum and emits only the centroids that can still matter:
+// in TMEM; the m x k matrix is never written.  |c|^2 rides along as an extra K = 8 block
+// (-|c|^2/2 split into three TF32 terms against ones), so the accumulator holds
+// s = x.c - |c|^2/2 and d = |x|^2 - 2 s.  The epilogue keeps, per point, a running minimum of d
+// (maximum of s) and emits only the centroids that can still matter:
 //     d_tf32 < f * (runmin_tf32 + E) + E,      E = tc_err_bound(|x|^2, max|c|^2, ld)
 // which is a superset of {argmin candidates} U {j : d_ref(j) < f * dmin_ref} because E bounds
 // |d_tf32 - d_ref| and the running minimum only decreases.  resolve.cu then decides every
@@ -46,7 +48,16 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_A = KB_MAX * A_KB_BYTES;                  // 64 KB
 constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
-constexpr int SMEM_BAR_OFF = SMEM_A + SMEM_B;
+// K extension: one extra K = 8 block per tile carries -|c|^2/2 (split into three TF32 terms), so
+// the accumulator holds s = x.c - |c|^2/2 and the epilogue needs neither |c|^2 nor an FMA per
+// element (d = |x|^2 - 2 s).  Rows of 8 floats = 32 bytes, SWIZZLE_32B.
+constexpr int EXT_K = 8;
+constexpr int NEXT = 2;                                      // ring depth of the extension tiles
+constexpr int AEXT_BYTES = BM * EXT_K * 4;                   // 4 KB, constant for the whole kernel
+constexpr int BEXT_BYTES = BN * EXT_K * 4;                   // 8 KB per tile
+constexpr int SMEM_AEXT_OFF = SMEM_A + SMEM_B;
+constexpr int SMEM_BEXT_OFF = SMEM_AEXT_OFF + AEXT_BYTES;
+constexpr int SMEM_BAR_OFF = SMEM_BEXT_OFF + NEXT * BEXT_BYTES;
 constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [2][128]
 constexpr int SMEM_TOTAL = SMEM_PUB_OFF + 2 * BM * 8 + 1024; // + alignment slack
 
@@ -142,6 +153,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// Same for rows of 32 bytes (SWIZZLE_32B, 8-row groups 256 bytes apart): the K-extension tiles.
+__device__ __forceinline__ uint64_t make_smem_desc32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(256 >> 4) << 32;                 // stride byte offset: 8 rows x 32 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)6 << 61;                          // SWIZZLE_32B
+  return d;
+}
+
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256.
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                 ((uint32_t)(BM >> 4) << 24);
@@ -151,12 +173,13 @@ struct TcArgs {
   uint32_t ntiles;                  // ceil(k / 256)
   uint32_t nrowblocks;              // ceil(m / 128)
   float factor;
-  const float* xnorm; const float* xres; const float* cnorm; const float* cstat;
+  const float* xnorm; const float* xres; const float* cstat;
   CandRec* rec; RowInfo* info; int cap;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_e, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
@@ -168,19 +191,30 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* b_empty = b_full + NSTAGE;     // [NSTAGE]
   uint64_t* t_full = b_empty + NSTAGE;     // [2]
   uint64_t* t_empty = t_full + 2;          // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* e_full = t_empty + 2;          // [NEXT]
+  uint64_t* e_empty = e_full + NEXT;       // [NEXT]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(e_empty + NEXT);
+  unsigned char* smem_aext = smem + SMEM_AEXT_OFF;
+  unsigned char* smem_bext = smem + SMEM_BEXT_OFF;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_e) : "memory");
     for (int i = 0; i < KB_MAX; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NEXT; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x >= 64) reinterpret_cast<unsigned long long*>(smem + SMEM_PUB_OFF)[threadIdx.x - 64] = ~0ull;
+  // A side of the K extension: every row {1,1,0,0, 1,1,0,0}.  Both 16-byte halves are equal, so the
+  // SWIZZLE_32B permutation leaves the tile unchanged and it can be written directly.
+  for (int i = threadIdx.x; i < BM * 2; i += NUM_THREADS)
+    reinterpret_cast<float4*>(smem_aext)[i] = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes → visible to the MMA
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"((uint32_t)TMEM_COLS)
@@ -195,20 +229,24 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // =============================== TMA producer ===========================================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, it = 0;
+      uint32_t stage = 0, phase = 0, it = 0, ecount = 0;
       for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x, ++it) {
         for (uint32_t kb = 0; kb < a.kb; ++kb) {
           mbar_wait(&a_empty[kb], (it & 1) ^ 1);          // previous row block's MMAs are done with it
           mbar_expect_tx(&a_full[kb], A_KB_BYTES);
           tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(rb * BM));
         }
-        for (uint32_t t = 0; t < a.ntiles; ++t) {
+        for (uint32_t t = 0; t < a.ntiles; ++t, ++ecount) {
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1);
             mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);
             tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &b_full[stage], (int)(kb * BK), (int)(t * BN));
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
+          const uint32_t es = ecount % NEXT, eu = ecount / NEXT;
+          mbar_wait(&e_empty[es], (eu & 1) ^ 1);
+          mbar_expect_tx(&e_full[es], BEXT_BYTES);
+          tma_load_2d(smem_bext + es * BEXT_BYTES, &map_e, &e_full[es], 0, (int)(t * BN));
         }
       }
     }
@@ -237,6 +275,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (t + 1 == a.ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
+          {   // K extension: accumulator += -|c|^2/2
+            const uint32_t es = tcount % NEXT, eu = tcount / NEXT;
+            mbar_wait(&e_full[es], eu & 1);
+            tc_fence_after();
+            tc_mma_tf32(tmem_d, make_smem_desc32(smem_u32(smem_aext)),
+                        make_smem_desc32(smem_u32(smem_bext + es * BEXT_BYTES)), IDESC_TF32, 1u);
+            tc_commit(&e_empty[es]);
+          }
           tc_commit(&t_full[buf]);                        // accumulator complete → epilogue
         }
       }
@@ -261,65 +307,60 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const float E = tc_err_bound(xn, row_ok ? a.xres[row] : 0.0f, cnmax, dcmax, a.ld);
       // non-finite norms or bounds: no certified test exists, the brute-force kernels own the row
       const bool hopeless = !(E < INF) || !(xn < INF);
-      const float xnE = xn + E, EmX = E - xn;
+      const float xnE = xn + E, xmE = xn - E;
       const float slop = 1e-6f * (xn + cnmax) + 1e-30f;
       // this thread's segment of the row's records
       CandRec* const seg = a.rec + ((size_t)row * a.cap + (size_t)half * segcap);
       uint32_t wo = 0;                                    // write offset into the segment, bytes
       uint32_t overflow = 0;                              // records that did not fit
-      float tmin = INF;
+      float smax = -INF;                                  // running maximum of s = x.c - |c|^2/2
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(&t_full[buf], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
-        const float4* cn4 = reinterpret_cast<const float4*>(a.cnorm + (size_t)t * BN + half * (BN / 2));
         const uint32_t gtile = (t * BN + half * (BN / 2)) >> 2;
 
-        // one 32-column chunk: t = |c|^2 - 2 x.c, running minimum, candidate emission
-        auto process = [&](uint32_t (&rr)[32], const float4 (&cnr)[8], int c) {
-          float4 v[8];
+        // one 32-column chunk of s: running maximum (= running minimum of d = |x|^2 - 2 s), candidate
+        // emission
+        auto process = [&](uint32_t (&rr)[32], int c) {
           float q[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 cn = cnr[g];
-            v[g].x = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 0]), cn.x);
-            v[g].y = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 1]), cn.y);
-            v[g].z = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 2]), cn.z);
-            v[g].w = fmaf(-2.0f, __uint_as_float(rr[g * 4 + 3]), cn.w);
-            q[g] = fminf(fminf(v[g].x, v[g].y), fminf(v[g].z, v[g].w));
-          }
-          tmin = fminf(tmin, fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])),
-                                   fminf(fminf(q[4], q[5]), fminf(q[6], q[7]))));
-          float tshare = tmin;
-          {   // exchange running minima with the partner half of the same row (tagged with the row
-              // block: any value published for this row block is a valid upper bound of the final
-              // minimum, so a stale one only makes the candidate set a little larger)
+          for (int g = 0; g < 8; ++g)
+            q[g] = fmaxf(fmaxf(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1])),
+                         fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
+          smax = fmaxf(smax, fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])),
+                                   fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7]))));
+          float sshare = smax;
+          {   // exchange running maxima with the partner half of the same row (tagged with the row
+              // block: any value published for this row block is a valid lower bound of the final
+              // maximum, so a stale one only makes the candidate set a little larger)
             uint32_t pv_lo, pv_hi;
             asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pub_other) : "memory");
-            if (pv_hi == rb) tshare = fminf(tshare, __uint_as_float(pv_lo));
-            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(tmin)), "r"(rb) : "memory");
+            if (pv_hi == rb) sshare = fmaxf(sshare, __uint_as_float(pv_lo));
+            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(smax)), "r"(rb) : "memory");
           }
-          // candidate test  d < f (dmin_run + E) + E  with d = t + |x|^2
-          const float thr_t = row_ok ? fmaf(f1, tshare + xnE, EmX) + slop : -INF;
+          // candidate test  d < f (dmin_run + E) + E  with d = |x|^2 - 2 s, dmin_run = |x|^2 - 2 smax:
+          //   s > ( |x|^2 - E - f (|x|^2 + E - 2 smax) ) / 2
+          const float thr_s = row_ok ? 0.5f * fmaf(-f1, fmaf(-2.0f, sshare, xnE), xmE) - slop : INF;
           const uint32_t gbase = gtile + c * 8;
           const bool room = wo + 8u * (uint32_t)sizeof(CandRec) <= segbytes;
           if (__all_sync(0xffffffffu, room)) {
             // fast path: one warp vote per group of 4 columns, predicated record store inside
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              if (__any_sync(0xffffffffu, q[g] < thr_t)) {
+              if (__any_sync(0xffffffffu, q[g] > thr_s)) {
                 asm volatile(
                     "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t"
-                    "setp.lt.f32 p, %2, %3;\n\t"
+                    "setp.gt.f32 p, %2, %3;\n\t"
                     "cvt.u64.u32 o, %0;\n\t"
                     "add.u64 a, %1, o;\n\t"
-                    "@p st.global.v4.f32 [a], {%4, %5, %6, %7};\n\t"
+                    "@p st.global.v4.b32 [a], {%4, %5, %6, %7};\n\t"
                     "@p st.global.u32 [a+16], %8;\n\t"
                     "@p add.u32 %0, %0, 32;\n\t}"
                     : "+r"(wo)
-                    : "l"(seg), "f"(q[g]), "f"(thr_t), "f"(v[g].x), "f"(v[g].y), "f"(v[g].z), "f"(v[g].w),
-                      "r"(gbase + g)
+                    : "l"(seg), "f"(q[g]), "f"(thr_s), "r"(rr[g * 4 + 0]), "r"(rr[g * 4 + 1]), "r"(rr[g * 4 + 2]),
+                      "r"(rr[g * 4 + 3]), "r"(gbase + g)
                     : "memory");
               }
             }
@@ -327,10 +368,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // slow path: some thread of the warp is close to the end of its segment
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              if (q[g] < thr_t) {
+              if (q[g] > thr_s) {
                 if (wo < segbytes) {
                   CandRec* wp = reinterpret_cast<CandRec*>(reinterpret_cast<unsigned char*>(seg) + wo);
-                  wp->t = v[g];
+                  wp->t = make_float4(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1]),
+                                      __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
                   wp->g = gbase + g;
                   wo += (uint32_t)sizeof(CandRec);
                 } else {
@@ -344,34 +386,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
         // c+1 is in flight while chunk c is processed
         uint32_t ra[32], rbuf[32];
-        float4 cna[8], cnb[8];                            // |c|^2 of the chunk, fetched one chunk ahead
-        auto load_cn = [&](float4 (&cnr)[8], int c) {
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) cnr[i4] = __ldg(cn4 + c * 8 + i4);
-        };
         tc_ld32_issue(taddr, ra);
-        load_cn(cna, 0);
         tc_ld32_wait(ra);
         tc_ld32_issue(taddr + 32, rbuf);
-        load_cn(cnb, 1);
-        process(ra, cna, 0);
+        process(ra, 0);
         tc_ld32_wait(rbuf);
         tc_ld32_issue(taddr + 64, ra);
-        load_cn(cna, 2);
-        process(rbuf, cnb, 1);
+        process(rbuf, 1);
         tc_ld32_wait(ra);
         tc_ld32_issue(taddr + 96, rbuf);
-        load_cn(cnb, 3);
-        process(ra, cna, 2);
+        process(ra, 2);
         tc_ld32_wait(rbuf);
         tc_fence_before();                                // this warp's part of the accumulator is read
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[buf]);
-        process(rbuf, cnb, 3);
+        process(rbuf, 3);
       }
       if (row_ok) {
         uint2* const info2 = reinterpret_cast<uint2*>(a.info + row) + half;
-        *info2 = make_uint2(hopeless ? segcap + 1u : wo / (uint32_t)sizeof(CandRec) + overflow, __float_as_uint(tmin));
+        *info2 = make_uint2(hopeless ? segcap + 1u : wo / (uint32_t)sizeof(CandRec) + overflow, __float_as_uint(smax));
       }
     }
   }
@@ -410,21 +443,33 @@ bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) 
 }
 
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
-                     const float* xnorm, const float* xres, const float* cnorm_pad, const float* d_cstat,
+                     const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
                      float factor, const CandBuf& cand) {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_e;
   SPF_TRY(make_map(c, &map_a, Ptf, m, ld, BM));
   SPF_TRY(make_map(c, &map_b, Ctf, k, ld, BN));
+  {   // K-extension rows: round_up(k, 256) x 8 floats, SWIZZLE_32B
+    const uint64_t kpad = (uint64_t)((k + BN - 1) / BN) * BN;
+    cuuint64_t gdim[2] = {EXT_K, kpad};
+    cuuint64_t gstride[1] = {EXT_K * sizeof(float)};
+    cuuint32_t box[2] = {EXT_K, BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(c->tma_encode)(
+        &map_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(cext_pad), gdim, gstride, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SPF_E_CUDA, "cuTensorMapEncodeTiled (extension) failed with code %d", (int)r);
+  }
   TcArgs a;
   a.m = (uint32_t)m; a.k = k; a.ld = ld; a.kb = (ld + BK - 1) / BK;
   a.ntiles = (k + BN - 1) / BN;
   a.nrowblocks = (uint32_t)ceil_div(m, BM);
   a.factor = factor;
-  a.xnorm = xnorm; a.xres = xres; a.cnorm = cnorm_pad; a.cstat = d_cstat;
+  a.xnorm = xnorm; a.xres = xres; a.cstat = d_cstat;
   a.rec = cand.rec; a.info = cand.info; a.cap = cand.cap;
   SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count;
-  assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, a);
+  assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
   return check_launch(c, "assign_tc_kernel");
 }
 

@@ -8,7 +8,7 @@ namespace spf {
 // four consecutive centroid slots 4*g .. 4*g+3 of one point ("group record"): `t` holds one value
 // per slot, `g` holds the group index (bits 0-27) and one "exact" flag per slot (bits 28-31).
 //   exact flag set   : the value is the exact direct-form distance d(x, c)
-//   exact flag clear : the value is t = |c|^2 - 2 x.c from the TF32 GEMM; d ~ t + |x|^2 within E
+//   exact flag clear : the value is s = x.c - |c|^2/2 from the TF32 GEMM; d ~ |x|^2 - 2 s within E
 // Slots >= k carry no candidate (they are skipped by index).  A point owns `cap` records, split
 // into `nseg` segments (one per writer thread of the producing kernel).  After resolve the front
 // of the point's record area is reused for its member list (uint32 centroid slots).
@@ -22,7 +22,8 @@ static constexpr int REC_EXACT_SHIFT = 28;
 static constexpr uint32_t REC_ALL_EXACT = 0xf0000000u;
 static constexpr uint32_t NMEM_OVERFLOW_BIT = 0x80000000u;
 // Per point: x = records in segment 0 (a value > segment capacity marks an overflow), y = bits of
-// the smallest t the producer saw in segment 0's columns, z / w = the same for segment 1.
+// the best value the producer saw in segment 0's columns (tensor kernel: largest s; exact kernel:
+// smallest distance), z / w = the same for segment 1.
 typedef uint4 RowInfo;
 
 // Certified bound on |d_tf32 - d_ref| for the tensor path.  d_tf32 = |x|^2 - 2 x'.c' + |c|^2 where
@@ -84,11 +85,15 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
 // ---- assign_tc.cu -------------------------------------------------------------------------
 // tcgen05 (TF32) candidate GEMM for squared-Euclidean: approximate distances with a certified
 // error bound, candidates only (two segments per point).  Ptf / Ctf are the rounded operands;
-// cnorm_pad has round_up(k,256) entries (+inf padding); cstat = {max |c|^2, max |c - c'|}.
+// cext_pad holds round_up(k,256) K-extension rows of 8 floats (launch_centroid_ext);
+// cstat = {max |c|^2, max |c - c'|}.  Record values are s = x.c - |c|^2/2 (d ~ |x|^2 - 2 s).
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld);
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
-                     const float* xnorm, const float* xres, const float* cnorm_pad, const float* d_cstat,
+                     const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
                      float factor, const CandBuf& cand);
+// K-extension rows for the tensor kernel: row j < k = {h, m, 0, 0, l, 0, 0, 0} with h + m + l =
+// -|c_j|^2 / 2 split into three TF32 values (residual < 2^-33 |c_j|^2); rows k .. kpad-1 = {-inf, 0, ...}.
+int launch_centroid_ext(spf_ctx* c, const float* cnorm, uint32_t k, uint32_t kpad, float* cext);
 
 // ---- resolve.cu ---------------------------------------------------------------------------
 struct ResolveArgs {

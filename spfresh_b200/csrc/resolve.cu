@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
     const float E = approx ? tc_err_bound(xn, cur.xr, cnmax, dcmax, a.ld) : 0.0f;
     // smallest distance the producer saw: approximate on the tensor path (the true minimum is
     // within E of it, so only elements within 2E can be the argmin), exact otherwise
-    const float tmin = a.nseg > 1 ? fminf(__uint_as_float(cur.info.y), __uint_as_float(cur.info.w))
-                                  : __uint_as_float(cur.info.y);
-    const float ma = approx ? __fadd_rn(tmin, xn) : tmin;
+    // tensor path: the info words hold the largest s = x.c - |c|^2/2 per column half, d = |x|^2 - 2 s
+    const float ma = approx ? fmaf(-2.0f, fmaxf(__uint_as_float(cur.info.y), __uint_as_float(cur.info.w)), xn)
+                            : __uint_as_float(cur.info.y);
     const float band = __fadd_ru(ma, 2.0f * E);
     // loosest possible threshold: thr = fl(dmin * factor) with dmin <= ma + E
     const float thi_loose = a.want_members ? __fmul_ru(__fadd_ru(ma, E), a.factor) : 0.0f;
@@ -200,11 +200,18 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
     for (uint32_t st = 0; st < steps; ++st) {
       const uint32_t i = st * 32 + lane;
       const Rec2 rc = st == 0 ? cur.rc : load_recs(cr, i, cnt0, cnt1);
-      const float g0 = fminf(fminf(rc.t0.x, rc.t0.y), fminf(rc.t0.z, rc.t0.w));
-      const float g1 = fminf(fminf(rc.t1.x, rc.t1.y), fminf(rc.t1.z, rc.t1.w));
-      // (records are either all exact or all approximate per producer)
-      const bool k0 = i < cnt0 && (approx ? __fadd_rn(g0, xn) : g0) <= vbound;
-      const bool k1 = i < cnt1 && (approx ? __fadd_rn(g1, xn) : g1) <= vbound;
+      // best element of each record (records are either all exact distances or all approximate s
+      // values per producer): smallest distance, i.e. largest s
+      float g0, g1;
+      if (approx) {
+        g0 = fmaf(-2.0f, fmaxf(fmaxf(rc.t0.x, rc.t0.y), fmaxf(rc.t0.z, rc.t0.w)), xn);
+        g1 = fmaf(-2.0f, fmaxf(fmaxf(rc.t1.x, rc.t1.y), fmaxf(rc.t1.z, rc.t1.w)), xn);
+      } else {
+        g0 = fminf(fminf(rc.t0.x, rc.t0.y), fminf(rc.t0.z, rc.t0.w));
+        g1 = fminf(fminf(rc.t1.x, rc.t1.y), fminf(rc.t1.z, rc.t1.w));
+      }
+      const bool k0 = i < cnt0 && g0 <= vbound;
+      const bool k1 = i < cnt1 && g1 <= vbound;
       const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
       const unsigned below = (1u << lane) - 1u;
       const uint32_t p0 = nrec + (uint32_t)__popc(b0 & below);
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           e.valid |= (e.jb + (uint32_t)q < a.k) ? (1u << q) : 0u;
-          e.v[q] = ((e.exact >> q) & 1u) ? tv[q] : __fadd_rn(tv[q], xn);
+          e.v[q] = ((e.exact >> q) & 1u) ? tv[q] : fmaf(-2.0f, tv[q], xn);
         }
       }
       return e;

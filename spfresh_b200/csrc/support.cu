@@ -100,6 +100,27 @@ __global__ void max2_f32_kernel(const float* __restrict__ a, const float* __rest
   }
 }
 
+__global__ void centroid_ext_kernel(const float* __restrict__ cnorm, uint32_t k, uint32_t kpad, float* __restrict__ cext) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kpad) return;
+  auto rnd = [](float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+  };
+  float h = -__int_as_float(0x7f800000), m = 0.f, l = 0.f;
+  if (j < k) {
+    const float v = -0.5f * cnorm[j];          // exact (power of two)
+    h = rnd(v);
+    const float r1 = v - h;                    // exact: |r1| <= 2^-11 |v|
+    m = rnd(r1);
+    l = rnd(r1 - m);                           // exact difference, then rounded once more
+  }
+  float4* o = reinterpret_cast<float4*>(cext + (size_t)j * 8);
+  o[0] = make_float4(h, m, 0.f, 0.f);
+  o[1] = make_float4(l, 0.f, 0.f, 0.f);
+}
+
 __global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = v;
@@ -176,6 +197,11 @@ int launch_row_prep(spf_ctx* c, const float* src, uint32_t ld, const uint64_t* d
   if (m == 0) return SPF_OK;
   row_prep_kernel<<<(unsigned)ceil_div(m * 32, 256), 256, 0, c->stream>>>(src, ld / 4, d_idx, m, tf, norm, res);
   return check_launch(c, "row_prep_kernel");
+}
+
+int launch_centroid_ext(spf_ctx* c, const float* cnorm, uint32_t k, uint32_t kpad, float* cext) {
+  centroid_ext_kernel<<<(kpad + 255) / 256, 256, 0, c->stream>>>(cnorm, k, kpad, cext);
+  return check_launch(c, "centroid_ext_kernel");
 }
 
 int launch_max2_f32(spf_ctx* c, const float* a, const float* b, uint64_t n, float* out2) {
