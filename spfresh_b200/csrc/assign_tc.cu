@@ -99,6 +99,31 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// Same load, delivered to the same shared-memory offsets (data and mbarrier) of every CTA in
+// `mask` of this cluster: the two CTAs of a pair each fetch half of a centroid tile from L2.
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -177,7 +202,7 @@ struct TcArgs {
   CandRec* rec; RowInfo* info; int cap;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_e, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -204,7 +229,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_e) : "memory");
     for (int i = 0; i < KB_MAX; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    // a centroid stage is written by both CTAs of the pair (multicast halves) and must be released
+    // by both MMA issuers before either producer may overwrite it
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
     for (int i = 0; i < NEXT; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -223,8 +250,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                      // the peer's barriers are initialised before anything remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t crank = cluster_ctarank();
 
   if (warp == 0) {
     // =============================== TMA producer ===========================================
@@ -238,9 +267,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (uint32_t t = 0; t < a.ntiles; ++t, ++ecount) {
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
-            mbar_wait(&b_empty[stage], phase ^ 1);
-            mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);
-            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &b_full[stage], (int)(kb * BK), (int)(t * BN));
+            mbar_wait(&b_empty[stage], phase ^ 1);          // both CTAs are done with this stage
+            mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);  // own half + the peer's multicast half
+            tma_load_2d_mc(smem_b + stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / 2), &map_b, &b_full[stage],
+                           (int)(kb * BK), (int)(t * BN + crank * (BN / 2)), (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           const uint32_t es = ecount % NEXT, eu = ecount / NEXT;
@@ -271,7 +301,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tc_mma_tf32(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 4), make_smem_desc(b_addr + k * UMMA_K * 4),
                           IDESC_TF32, (kb | (uint32_t)k) != 0 ? 1u : 0u);
             }
-            tc_commit(&b_empty[stage]);                   // frees the B stage once these MMAs retire
+            tc_commit_mc(&b_empty[stage], (uint16_t)0x3);   // frees the B stage in both CTAs once these MMAs retire
             if (t + 1 == a.ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
@@ -411,6 +441,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                      // no CTA leaves while its peer may still write into it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
@@ -447,7 +478,7 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
                      float factor, const CandBuf& cand) {
   CUtensorMap map_a, map_b, map_e;
   SPF_TRY(make_map(c, &map_a, Ptf, m, ld, BM));
-  SPF_TRY(make_map(c, &map_b, Ctf, k, ld, BN));
+  SPF_TRY(make_map(c, &map_b, Ctf, k, ld, BN / 2));   // each CTA of a pair fetches half a tile
   {   // K-extension rows: round_up(k, 256) x 8 floats, SWIZZLE_32B
     const uint64_t kpad = (uint64_t)((k + BN - 1) / BN) * BN;
     cuuint64_t gdim[2] = {EXT_K, kpad};
@@ -463,12 +494,12 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
   TcArgs a;
   a.m = (uint32_t)m; a.k = k; a.ld = ld; a.kb = (ld + BK - 1) / BK;
   a.ntiles = (k + BN - 1) / BN;
-  a.nrowblocks = (uint32_t)ceil_div(m, BM);
+  a.nrowblocks = (uint32_t)(ceil_div(m, 2 * BM) * 2);   // even: the CTAs of a pair walk the tiles in lockstep
   a.factor = factor;
   a.xnorm = xnorm; a.xres = xres; a.cstat = d_cstat;
   a.rec = cand.rec; a.info = cand.info; a.cap = cand.cap;
   SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-  unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count;
+  unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count & ~1u;
   assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
   return check_launch(c, "assign_tc_kernel");
 }
