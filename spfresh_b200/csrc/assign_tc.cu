@@ -344,6 +344,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t wo = 0;                                    // write offset into the segment, bytes
       uint32_t overflow = 0;                              // records that did not fit
       float smax = -INF;                                  // running maximum of s = x.c - |c|^2/2
+      float other = -INF;                                 // the partner half's maximum, one chunk old
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(&t_full[buf], use & 1);
@@ -361,13 +362,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                          fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
           smax = fmaxf(smax, fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])),
                                    fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7]))));
-          float sshare = smax;
-          {   // exchange running maxima with the partner half of the same row (tagged with the row
-              // block: any value published for this row block is a valid lower bound of the final
-              // maximum, so a stale one only makes the candidate set a little larger)
+          // Exchange running maxima with the partner half of the same row through shared memory
+          // (tagged with the row block: any value published for this row block is a valid lower
+          // bound of the final maximum, so a stale one only makes the candidate set a little
+          // larger).  The partner's value is read one chunk late (`other` was loaded while the
+          // previous chunk was processed) to keep the shared-memory round trip off the critical path.
+          const float sshare = fmaxf(smax, other);
+          {
             uint32_t pv_lo, pv_hi;
             asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pub_other) : "memory");
-            if (pv_hi == rb) sshare = fmaxf(sshare, __uint_as_float(pv_lo));
+            other = pv_hi == rb ? __uint_as_float(pv_lo) : -INF;
             asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(smax)), "r"(rb) : "memory");
           }
           // candidate test  d < f (dmin_run + E) + E  with d = |x|^2 - 2 s, dmin_run = |x|^2 - 2 smax:
@@ -375,24 +379,28 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const float thr_s = row_ok ? 0.5f * fmaf(-f1, fmaf(-2.0f, sshare, xnE), xmE) - slop : INF;
           const uint32_t gbase = gtile + c * 8;
           const bool room = wo + 8u * (uint32_t)sizeof(CandRec) <= segbytes;
-          if (__all_sync(0xffffffffu, room)) {
-            // fast path: one warp vote per group of 4 columns, predicated record store inside
+          bool anyhit = false;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) anyhit = anyhit || (q[g] > thr_s);
+          const unsigned votes = __ballot_sync(0xffffffffu, anyhit) | (__all_sync(0xffffffffu, room) ? 0u : 0x80000000u);
+          if (votes == 0) {
+            // no lane has a candidate in this chunk
+          } else if (__all_sync(0xffffffffu, room)) {
+            // fast path: straight-line predicated record stores (no per-group vote or branch)
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              if (__any_sync(0xffffffffu, q[g] > thr_s)) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t"
-                    "setp.gt.f32 p, %2, %3;\n\t"
-                    "cvt.u64.u32 o, %0;\n\t"
-                    "add.u64 a, %1, o;\n\t"
-                    "@p st.global.v4.b32 [a], {%4, %5, %6, %7};\n\t"
-                    "@p st.global.u32 [a+16], %8;\n\t"
-                    "@p add.u32 %0, %0, 32;\n\t}"
-                    : "+r"(wo)
-                    : "l"(seg), "f"(q[g]), "f"(thr_s), "r"(rr[g * 4 + 0]), "r"(rr[g * 4 + 1]), "r"(rr[g * 4 + 2]),
-                      "r"(rr[g * 4 + 3]), "r"(gbase + g)
-                    : "memory");
-              }
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t"
+                  "setp.gt.f32 p, %2, %3;\n\t"
+                  "cvt.u64.u32 o, %0;\n\t"
+                  "add.u64 a, %1, o;\n\t"
+                  "@p st.global.v4.b32 [a], {%4, %5, %6, %7};\n\t"
+                  "@p st.global.u32 [a+16], %8;\n\t"
+                  "@p add.u32 %0, %0, 32;\n\t}"
+                  : "+r"(wo)
+                  : "l"(seg), "f"(q[g]), "f"(thr_s), "r"(rr[g * 4 + 0]), "r"(rr[g * 4 + 1]), "r"(rr[g * 4 + 2]),
+                    "r"(rr[g * 4 + 3]), "r"(gbase + g)
+                  : "memory");
             }
           } else {
             // slow path: some thread of the warp is close to the end of its segment

@@ -130,8 +130,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
     Rec2 rc;
     rc.t0 = rc.t1 = make_float4(0.f, 0.f, 0.f, 0.f);
     rc.g0 = rc.g1 = 0;
-    if (i < n0 && i < segcap) { rc.t0 = cr[i].t; rc.g0 = cr[i].g; }
-    if (i < n1 && i < segcap) { rc.t1 = cr[segcap + i].t; rc.g1 = cr[segcap + i].g; }
+    // records are read exactly once: streaming loads keep them from evicting the k x k centroid
+    // matrix (read with a data-dependent pattern later in this kernel) out of L2
+    if (i < n0 && i < segcap) { rc.t0 = __ldcs(&cr[i].t); rc.g0 = __ldcs(&cr[i].g); }
+    if (i < n1 && i < segcap) { rc.t1 = __ldcs(&cr[segcap + i].t); rc.g1 = __ldcs(&cr[segcap + i].g); }
     return rc;
   };
   // Two-level prefetch: a row's info word and norms are fetched two rows ahead, its first 32
