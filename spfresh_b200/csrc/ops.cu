@@ -32,36 +32,125 @@ namespace {
 constexpr int WBLOCK = 1024;   // weights per block in the k-means++ pick
 
 // ---- compute_mean (src/clustering/utils.rs:5-15): row-by-row f32 sum in member order, then a
-// true division by m.  One thread owns 4 consecutive dimensions of one cluster.
+// true division by m.  One CTA per cluster, one thread per 4 consecutive dimensions.  The sum of
+// a dimension is a strictly sequential chain over the members, so the only parallelism inside a
+// cluster is memory-level: every thread keeps a ring of MEAN_RING rows of its own 16-byte column
+// in flight with cp.async (it consumes only what it copied itself, so no barrier is needed) and
+// the chain never waits for a gather.
+template <int RING>
 __global__ void cluster_mean_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t* __restrict__ offsets,
                                     const uint64_t* __restrict__ rows, float* __restrict__ means, int divide) {
+  extern __shared__ __align__(16) unsigned char mean_raw[];
+  float4* buf = reinterpret_cast<float4*>(mean_raw);       // [RING][blockDim.x]
   const uint32_t c = blockIdx.x;
   const uint64_t b = offsets[c], e = offsets[c + 1];
   const float4* X4 = reinterpret_cast<const float4*>(X);
-  for (uint32_t col = threadIdx.x; col < ld4; col += blockDim.x) {
+  for (uint32_t col0 = 0; col0 < ld4; col0 += blockDim.x) {
+    const uint32_t col = col0 + threadIdx.x;
+    const bool ok = col < ld4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint64_t t = b;
-    for (; t + 4 <= e; t += 4) {   // independent loads first, then the ordered adds
-      const float4 v0 = __ldg(X4 + (size_t)rows[t] * ld4 + col);
-      const float4 v1 = __ldg(X4 + (size_t)rows[t + 1] * ld4 + col);
-      const float4 v2 = __ldg(X4 + (size_t)rows[t + 2] * ld4 + col);
-      const float4 v3 = __ldg(X4 + (size_t)rows[t + 3] * ld4 + col);
-      acc.x = __fadd_rn(acc.x, v0.x); acc.y = __fadd_rn(acc.y, v0.y); acc.z = __fadd_rn(acc.z, v0.z); acc.w = __fadd_rn(acc.w, v0.w);
-      acc.x = __fadd_rn(acc.x, v1.x); acc.y = __fadd_rn(acc.y, v1.y); acc.z = __fadd_rn(acc.z, v1.z); acc.w = __fadd_rn(acc.w, v1.w);
-      acc.x = __fadd_rn(acc.x, v2.x); acc.y = __fadd_rn(acc.y, v2.y); acc.z = __fadd_rn(acc.z, v2.z); acc.w = __fadd_rn(acc.w, v2.w);
-      acc.x = __fadd_rn(acc.x, v3.x); acc.y = __fadd_rn(acc.y, v3.y); acc.z = __fadd_rn(acc.z, v3.z); acc.w = __fadd_rn(acc.w, v3.w);
+    // member indices are fetched 32 at a time (lane l of every warp holds rows[blk*32 + l], narrowed
+    // to 32 bits: n < 2^32) one block ahead of their use, so the gather address never waits for
+    // an index load
+    const int lane = threadIdx.x & 31;
+    auto load_idx = [&](uint64_t blk) {
+      const uint64_t t = b + blk * 32 + lane;
+      return t < e ? (uint32_t)rows[t] : 0u;
+    };
+    uint32_t idx_cur = load_idx(0), idx_nxt = load_idx(1);
+    uint64_t idx_blk = 0;                                     // block idx_cur belongs to
+    // rows are copied and consumed in groups of MEAN_G (one commit / wait per group, loads of a
+    // group issued back to back): the sum of a dimension is a serial chain over the cluster, so
+    // instructions per row are what bounds the largest cluster
+    constexpr int MEAN_G = 8;
+    static_assert(RING % MEAN_G == 0 && 32 % MEAN_G == 0, "ring and index blocks hold whole groups");
+    const uint64_t nrows = e - b;
+    auto issue = [&](uint64_t rel) {                          // rows rel .. rel + MEAN_G - 1 (relative), rel % MEAN_G == 0
+      if ((rel >> 5) != idx_blk) {                            // warp-uniform: advance to the next index block
+        idx_cur = idx_nxt;
+        idx_blk = rel >> 5;
+        idx_nxt = load_idx(idx_blk + 1);
+      }
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(&buf[(size_t)(rel % RING) * blockDim.x + threadIdx.x]);
+      if (rel + MEAN_G <= nrows) {                            // full group: no per-row guard
+#pragma unroll
+        for (int g = 0; g < MEAN_G; ++g) {
+          const uint32_t row = __shfl_sync(0xffffffffu, idx_cur, (int)((rel & 31) + g));
+          if (ok) {
+            const float4* src = X4 + (size_t)row * ld4 + col;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + g * blockDim.x * 16u), "l"(src) : "memory");
+          }
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < MEAN_G; ++g) {
+          const uint32_t row = __shfl_sync(0xffffffffu, idx_cur, (int)((rel & 31) + g));
+          if (rel + g < nrows && ok) {
+            const float4* src = X4 + (size_t)row * ld4 + col;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + g * blockDim.x * 16u), "l"(src) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // one group per MEAN_G rows
+    };
+    for (int i = 0; i < RING; i += MEAN_G) issue((uint64_t)i);
+    for (uint64_t rel = 0; rel < nrows; rel += MEAN_G) {
+      // RING / MEAN_G groups are in flight; the oldest has landed once at most RING / MEAN_G - 1 are pending
+      asm volatile("cp.async.wait_group %0;" ::"n"(RING / MEAN_G - 1) : "memory");
+      if (ok) {
+        const float4* slot = &buf[(size_t)(rel % RING) * blockDim.x + threadIdx.x];
+        if (rel + MEAN_G <= nrows) {
+          float4 v[MEAN_G];
+#pragma unroll
+          for (int g = 0; g < MEAN_G; ++g) v[g] = slot[(size_t)g * blockDim.x];
+#pragma unroll
+          for (int g = 0; g < MEAN_G; ++g) {
+            acc.x = __fadd_rn(acc.x, v[g].x); acc.y = __fadd_rn(acc.y, v[g].y);
+            acc.z = __fadd_rn(acc.z, v[g].z); acc.w = __fadd_rn(acc.w, v[g].w);
+          }
+        } else {
+          for (int g = 0; rel + g < nrows; ++g) {
+            const float4 v = slot[(size_t)g * blockDim.x];
+            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+            acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+          }
+        }
+      }
+      issue(rel + RING);                                      // reuses the slots just consumed
     }
-    for (; t < e; ++t) {
-      const float4 v = __ldg(X4 + (size_t)rows[t] * ld4 + col);
-      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (ok) {
+      if (divide && e > b) {
+        const float fm = (float)(e - b);
+        acc.x = __fdiv_rn(acc.x, fm); acc.y = __fdiv_rn(acc.y, fm);
+        acc.z = __fdiv_rn(acc.z, fm); acc.w = __fdiv_rn(acc.w, fm);
+      }
+      reinterpret_cast<float4*>(means)[(size_t)c * ld4 + col] = acc;
     }
-    if (divide && e > b) {
-      const float fm = (float)(e - b);
-      acc.x = __fdiv_rn(acc.x, fm); acc.y = __fdiv_rn(acc.y, fm);
-      acc.z = __fdiv_rn(acc.z, fm); acc.w = __fdiv_rn(acc.w, fm);
-    }
-    reinterpret_cast<float4*>(means)[(size_t)c * ld4 + col] = acc;
   }
+}
+
+// ring depth by row width: as many rows in flight as 64 KB of shared memory hold
+int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t* d_offsets, const uint64_t* d_rows,
+                        uint32_t k, float* means, int divide) {
+  unsigned threads = round_up(ld / 4, 32);
+  if (threads > 1024) threads = 1024;
+  cudaStream_t st = c->stream;
+  const size_t row_bytes = (size_t)threads * 16;
+  if (row_bytes * 128 <= 64 * 1024) {
+    const size_t smem = row_bytes * 128;
+    SPF_CUDA(cudaFuncSetAttribute(cluster_mean_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_mean_kernel<128><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
+  } else if (row_bytes * 32 <= 64 * 1024) {
+    const size_t smem = row_bytes * 32;
+    SPF_CUDA(cudaFuncSetAttribute(cluster_mean_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_mean_kernel<32><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
+  } else {
+    const size_t smem = row_bytes * 8;     // <= 128 KB (rows of up to 1024 float4 per pass)
+    SPF_CUDA(cudaFuncSetAttribute(cluster_mean_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_mean_kernel<8><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
+  }
+  return check_launch(c, "cluster_mean_kernel");
 }
 
 __global__ void expand_cluster_ids_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ cid) {
@@ -279,7 +368,7 @@ int dispatch_metric(int metric, F&& f) {
 
 unsigned pd_grid(spf_ctx* c, uint64_t count) {
   uint64_t blocks = ceil_div(count, PD_THREADS);
-  const uint64_t cap = (uint64_t)c->sm_count * 32;
+  const uint64_t cap = (uint64_t)c->sm_count * 12;   // 6 CTAs of 2 warps are resident per SM (35 KB of staging each)
   return (unsigned)(blocks > cap ? cap : (blocks ? blocks : 1));
 }
 
@@ -303,10 +392,7 @@ int update_medoids_dev(spf_dataset* ds, int metric, const uint64_t* d_offsets, c
   SPF_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)k * sizeof(unsigned long long), st));
   {
     KernelTimer t(c, "cluster_mean");
-    unsigned threads = round_up(ld / 4, 32);
-    if (threads > 1024) threads = 1024;
-    cluster_mean_kernel<<<k, threads, 0, st>>>(ds->x, ld / 4, d_offsets, d_rows, means.p, 1);
-    SPF_TRY(check_launch(c, "cluster_mean_kernel"));
+    SPF_TRY(launch_cluster_mean(c, ds->x, ld, d_offsets, d_rows, k, means.p, 1));
   }
   expand_cluster_ids_kernel<<<k, 256, 0, st>>>(d_offsets, cid.p);
   SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
@@ -387,10 +473,7 @@ int spf_cluster_sums(spf_dataset* ds, const spf_assign_result* r, float* sums, u
   SPF_TRY(d_rows.alloc(st, r->total));
   SPF_TRY(assign_members_as_rows(r, d_rows.p));
   SPF_TRY(acc.alloc(st, (size_t)k * ld));
-  unsigned threads = round_up(ld / 4, 32);
-  if (threads > 1024) threads = 1024;
-  cluster_mean_kernel<<<k, threads, 0, st>>>(ds->x, ld / 4, r->offsets, d_rows.p, acc.p, 0);
-  SPF_TRY(check_launch(c, "cluster_mean_kernel"));
+  SPF_TRY(launch_cluster_mean(c, ds->x, ld, r->offsets, d_rows.p, k, acc.p, 0));
   std::vector<uint64_t> off((size_t)k + 1);
   SPF_CUDA(cudaMemcpy2DAsync(sums, (size_t)ds->d * sizeof(float), acc.p, (size_t)ld * sizeof(float),
                              (size_t)ds->d * sizeof(float), k, cudaMemcpyDeviceToHost, st));

@@ -2,54 +2,62 @@
 //
 // The reference evaluates DistanceMetric::compute (src/distances/distance.rs:16-43) as one
 // sequential f32 chain per pair.  A lane therefore owns one pair and walks its dimensions in
-// order; the warp only cooperates on the memory side: the 32 lanes load 32 consecutive floats
-// of every pair's two rows (one coalesced 128-byte request per row chunk) into a padded shared
-// tile, then each lane reads its own pair's values back conflict-free.
+// order; the warp only cooperates on the memory side: for every pair the 32 lanes copy a
+// 64-dimension chunk of both rows into shared memory with cp.async (lanes 0-15 the first row,
+// lanes 16-31 the second, 16 bytes each — one coalesced 256-byte request per row chunk, all 64
+// requests of a step in flight together, no registers held), then each lane reads its own pair's
+// values back conflict-free.
 #pragma once
 #include "common.cuh"
 
 namespace spf {
 
-constexpr int PD_THREADS = 128;
+constexpr int PD_THREADS = 64;
+constexpr int PD_CHUNK = 64;              // dimensions staged per step
+constexpr int PD_STRIDE = PD_CHUNK + 4;   // floats per staged row (16-byte aligned, conflict-free)
 
 struct PairDistSmem {
-  float ta[32][33];
-  float tb[32][33];
-  const float* pa[32];
-  const float* pb[32];
+  float ta[32][PD_STRIDE];
+  float tb[32][PD_STRIDE];
 };
 
-// pa / pb: this lane's two rows (nullptr for an inactive lane).  All 32 lanes must call.
+// pa / pb: this lane's two rows (nullptr for an inactive lane), 16-byte aligned, ld a multiple of 4.
+// All 32 lanes must call.
 template <int METRIC>
 __device__ __forceinline__ float warp_pair_dist(const float* pa, const float* pb, uint32_t ld,
                                                 PairDistSmem& s) {
   const int lane = threadIdx.x & 31;
-  s.pa[lane] = pa;
-  s.pb[lane] = pb;
-  __syncwarp();
+  const int second = lane >> 4, l16 = lane & 15;
+  const unsigned long long ua = (unsigned long long)(uintptr_t)pa, ub = (unsigned long long)(uintptr_t)pb;
   float acc = 0.0f;
-  for (uint32_t chunk = 0; chunk < ld; chunk += 32) {
-    const uint32_t col = chunk + lane;
+  for (uint32_t c0 = 0; c0 < ld; c0 += PD_CHUNK) {
+    const uint32_t col = c0 + l16 * 4;
     const bool col_ok = col < ld;
 #pragma unroll 8
     for (int p = 0; p < 32; ++p) {
-      const float* qa = s.pa[p];
-      const float* qb = s.pb[p];
-      float va = 0.f, vb = 0.f;
-      if (qa != nullptr && col_ok) {
-        va = __ldg(qa + col);
-        vb = __ldg(qb + col);
+      const unsigned long long qa = __shfl_sync(0xffffffffu, ua, p);
+      const unsigned long long qb = __shfl_sync(0xffffffffu, ub, p);
+      if (qa != 0 && col_ok) {
+        const float* src = reinterpret_cast<const float*>((uintptr_t)(second ? qb : qa)) + col;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(second ? &s.tb[p][l16 * 4] : &s.ta[p][l16 * 4]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       }
-      s.ta[p][lane] = va;
-      s.tb[p][lane] = vb;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const int nn = (ld - chunk) < 32u ? (int)(ld - chunk) : 32;
-    if (nn == 32) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc = dist_step<METRIC>(acc, s.ta[lane][i], s.tb[lane][i]);
-    } else {
-      for (int i = 0; i < nn; ++i) acc = dist_step<METRIC>(acc, s.ta[lane][i], s.tb[lane][i]);
+    if (pa != nullptr) {
+      const int n4 = (int)(((ld - c0) < (uint32_t)PD_CHUNK ? (ld - c0) : (uint32_t)PD_CHUNK) >> 2);
+      const float4* xp = reinterpret_cast<const float4*>(&s.ta[lane][0]);
+      const float4* yp = reinterpret_cast<const float4*>(&s.tb[lane][0]);
+#pragma unroll 8
+      for (int i = 0; i < n4; ++i) {
+        const float4 xv = xp[i], yv = yp[i];
+        acc = dist_step<METRIC>(acc, xv.x, yv.x);
+        acc = dist_step<METRIC>(acc, xv.y, yv.y);
+        acc = dist_step<METRIC>(acc, xv.z, yv.z);
+        acc = dist_step<METRIC>(acc, xv.w, yv.w);
+      }
     }
     __syncwarp();
   }

@@ -236,7 +236,7 @@ int launch_pair_dist(spf_ctx* c, int metric, const float* A, uint32_t ldA, const
                      const float* B, uint32_t ldB, const uint32_t* idxB32, uint64_t fixedB,
                      uint32_t ld, uint64_t count, float* out) {
   if (count == 0) return SPF_OK;
-  uint64_t blocks = ceil_div(count, PD_THREADS);   // 32 pairs per warp, 4 warps per block
+  uint64_t blocks = ceil_div(count, PD_THREADS);   // 32 pairs per warp, 2 warps per block
   if (blocks > (uint64_t)c->sm_count * 32) blocks = (uint64_t)c->sm_count * 32;
   dim3 grid((unsigned)blocks), block(PD_THREADS);
   switch (metric) {
