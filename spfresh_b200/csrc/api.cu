@@ -139,6 +139,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
     c->params.short_cap = value;
   } else if (s == "force_exact") c->params.force_exact = value;
   else if (s == "chunk_rows") c->params.chunk_rows = value;
+  else if (s == "work_cap") c->params.work_cap = value;
   else if (s == "scan_list_major") c->params.scan_list_major = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;

@@ -49,6 +49,7 @@ struct Params {
   int scan_threads = 256;
   int scan_list_major = 1;   // 0: query-major scan only, 1: automatic, 2: always list-major (k <= 32)
   int chunk_rows = 0;        // points per assign chunk (0: automatic)
+  int work_cap = 0;          // exact-evaluation work-list entries per chunk (0: automatic, 8 per point)
 };
 
 }  // namespace spf

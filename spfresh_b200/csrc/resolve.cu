@@ -890,7 +890,8 @@ int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx
   s->chunk_rows = chunk_rows;
   s->sl_shift = 0;
   while ((1 << s->sl_shift) < c->params.short_cap) ++s->sl_shift;
-  const uint64_t work_cap64 = approx ? chunk_rows * 8 + 1024 : 32;
+  const uint64_t work_cap64 = c->params.work_cap > 0 ? (uint64_t)c->params.work_cap
+                                                     : (approx ? chunk_rows * 8 + 1024 : 32);
   s->work_cap = work_cap64 > 0xffffff00ull ? 0xffffff00u : (uint32_t)work_cap64;
   int rc = SPF_OK;
   if ((chunk_rows << s->sl_shift) >= (1ull << 32)) rc = fail(SPF_E_INVALID, "assign: chunk too large");

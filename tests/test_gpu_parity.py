@@ -185,6 +185,44 @@ def test_assign_tensor_equals_exact_at_scale(spf, ctx):
     assert nearest.sum() == 200_000
 
 
+@pytest.mark.parametrize("param,value", [("short_cap", 2), ("short_cap", 8), ("work_cap", 1), ("work_cap", 100),
+                                         ("cand_cap", 16)])
+def test_assign_small_buffers_fall_back_exactly(spf, oracle, param, value):
+    """Short list / work list / record buffers too small for the data: the dense fallback and the
+    inline recomputation in finalize must reproduce the oracle bit for bit (tensor path)."""
+    c2 = spf.Context(0)
+    try:
+        c2.set_param(param, value)
+        data = gauss(6000, 64, 91)
+        cent = np.random.default_rng(6).choice(6000, 192, replace=False)
+        ds = spf.Dataset(c2, data)
+        c2.set_profiling(True)
+        got = ds.assign(0, cent, boundary_factor=1.15).fetch()
+        assert c2.kernel_ms("assign_tc") > 0, "the tcgen05 path did not run"
+        check_assign(got, oracle.assign(data, 0, cent, boundary_factor=1.15))
+        if param != "work_cap":
+            assert c2.last_overflow_rows() > 0          # the fallback was exercised
+        ds.free()
+    finally:
+        c2.close()
+
+
+def test_assign_vectors_and_fetch_rows(spf, ctx, oracle):
+    """spf_assign_vectors with vectors that are not dataset rows (the sharded case) == oracle on the
+    augmented matrix; spf_dataset_fetch_rows returns the uploaded rows bit for bit."""
+    data = clustered(5000, 96, 24, 33)
+    g = np.random.default_rng(9)
+    cvec = (data[g.choice(5000, 80, replace=False)] + 0.05 * g.standard_normal((80, 96))).astype(np.float32)
+    ds = spf.Dataset(ctx, data)
+    aug = np.concatenate([data, cvec])
+    ref = oracle.assign(aug, 0, np.arange(5000, 5080, dtype=np.uint64), point_idx=np.arange(5000, dtype=np.uint64))
+    check_assign(ds.assign_vectors(0, cvec).fetch(), ref)
+    pick = g.choice(5000, 300)
+    assert np.array_equal(ds.fetch_rows(pick).view(np.uint32), data[pick].view(np.uint32))
+    with pytest.raises(spf.SpfError):
+        ds.fetch_rows([5000])
+
+
 def test_assign_is_chunk_invariant(spf, oracle):
     """The point list is resolved in chunks; any chunk size must give the oracle's answer (tensor
     and exact path, full list and subset)."""
