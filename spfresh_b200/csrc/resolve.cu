@@ -781,11 +781,15 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
                a.want_members ? s->memlist.p + ((size_t)r0 << s->sl_shift) : nullptr,
                s->work.p, s->work_count.p, s->work_cap, (uint32_t)r0};
   KernelTimer t(c, "resolve");
+  // persistent grids sized to exactly one resident wave (classify: 3 CTAs / SM by registers,
+  // finalize: 4), rows are taken grid-stride
   uint64_t blocks = ceil_div(a.m, RS_WARPS);
-  if (blocks > (uint64_t)c->sm_count * 8) blocks = (uint64_t)c->sm_count * 8;
+  uint64_t blocks_cls = blocks, blocks_fin = blocks;
+  if (blocks_cls > (uint64_t)c->sm_count * 3) blocks_cls = (uint64_t)c->sm_count * 3;
+  if (blocks_fin > (uint64_t)c->sm_count * 8) blocks_fin = (uint64_t)c->sm_count * 8;
   {
     KernelTimer t2(c, "classify");
-    classify_kernel<<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+    classify_kernel<<<(unsigned)blocks_cls, RS_WARPS * 32, 0, st>>>(d);
     SPF_TRY(check_launch(c, "classify_kernel"));
   }
   if (a.xnorm) {   // the exact path never queues work
@@ -797,7 +801,7 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   }
   {
     KernelTimer t2(c, "finalize");
-    finalize_kernel<METRIC><<<(unsigned)blocks, RS_WARPS * 32, 0, st>>>(d);
+    finalize_kernel<METRIC><<<(unsigned)blocks_fin, RS_WARPS * 32, 0, st>>>(d);
     SPF_TRY(check_launch(c, "finalize_kernel"));
   }
   return SPF_OK;
