@@ -109,6 +109,51 @@ probe_select_kernel(const float* __restrict__ Dqc, uint32_t nlists, uint32_t npr
   }
 }
 
+// The same selection by a full block-wide radix sort of the (distance bits << 32 | list id) keys of
+// one query (nlists <= 256 * ITEMS): O(nlists) work per query instead of O(nprobe * nlists), which
+// is what matters for nprobe in the tens to hundreds.  Same total order, same outputs.
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+probe_sort_kernel(const float* __restrict__ Dqc, uint32_t nlists, uint32_t nprobe, float prune_factor,
+                  const uint32_t* __restrict__ lens, uint32_t* __restrict__ probe, float* __restrict__ thr,
+                  uint32_t* __restrict__ seqbase) {
+  typedef cub::BlockRadixSort<unsigned long long, 256, ITEMS> Sort;
+  typedef cub::BlockScan<uint32_t, 256> Scan;
+  __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+  const uint64_t q = blockIdx.x;
+  const float* row = Dqc + q * nlists;
+  unsigned long long key[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t j = threadIdx.x * ITEMS + i;     // blocked arrangement
+    // (distance bits, list id) packed into 44 bits: fewer radix passes (list id < 256 * ITEMS <= 4096)
+    key[i] = j < nlists ? (((unsigned long long)__float_as_uint(row[j]) << 12) | j) : ~0ull;
+  }
+  Sort(tmp.sort).Sort(key, 0, 44);
+  __syncthreads();
+  // encounter-index base of every selected list = exclusive prefix of the lengths in probe order
+  uint32_t len[ITEMS], base[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t p = threadIdx.x * ITEMS + i;
+    len[i] = (p < nprobe && key[i] != ~0ull) ? lens[(uint32_t)(key[i] & 0xfffull)] : 0u;
+  }
+  Scan(tmp.scan).ExclusiveSum(len, base);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t p = threadIdx.x * ITEMS + i;
+    if (p < nprobe) {
+      probe[q * nprobe + p] = (uint32_t)(key[i] & 0xfffull);
+      seqbase[q * nprobe + p] = base[i];
+    }
+  }
+  if (threadIdx.x == 0) {
+    // :165  F::from(1.2) * (nearest.distance + F::epsilon())
+    const float d0 = __uint_as_float((uint32_t)(key[0] >> 12));
+    thr[q] = __fmul_rn(prune_factor, __fadd_rn(d0, 1.1920929e-7f));
+  }
+}
+
 template <int R>
 __device__ __forceinline__ void topk_insert(unsigned long long (&key)[R], unsigned long long (&pay)[R],
                                             unsigned long long ck, unsigned long long cp, int lane) {
@@ -812,8 +857,16 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
       const uint64_t nc = (nq - q0) < chunk ? (nq - q0) : chunk;
       SPF_TRY(launch_assign_exact(c, SPF_METRIC_EUCLIDEAN, Q.p + q0 * ld, nc, idx->centroids, nlists, ld, 1.0f,
                                   nullptr, Dqc.p));
-      probe_select_kernel<<<(unsigned)nc, 128, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
-                                                        probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+      if (nprobe > 16 && nlists <= 1024) {
+        probe_sort_kernel<4><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
+                                                          probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+      } else if (nprobe > 16 && nlists <= 4096) {
+        probe_sort_kernel<16><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
+                                                           probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+      } else {
+        probe_select_kernel<<<(unsigned)nc, 128, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
+                                                          probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+      }
       SPF_TRY(check_launch(c, "probe_select_kernel"));
     }
   }
