@@ -334,72 +334,105 @@ __global__ void unit_counts_kernel(const uint32_t* __restrict__ list_off, const 
   counts[l] = n;
 }
 
+// Sorted insertion of one key into a warp-distributed ascending list of 32 keys (lane = rank).
+__device__ __forceinline__ void topk_insert_key(unsigned long long& key, unsigned long long ck, int lane) {
+  const int pos = __popc(__ballot_sync(0xffffffffu, key < ck));
+  const unsigned long long uk = __shfl_up_sync(0xffffffffu, key, 1);
+  if (lane > pos) key = uk;
+  else if (lane == pos) key = ck;
+}
+
 // One CTA per unit = (list, batch of up to LS_QB queries probing it).  The batch's query vectors sit
 // in shared memory; the warps split the list's 32-vector groups round-robin, a lane computes the
 // exact squared L2 of its slot's vector to all LS_QB queries (spann_index.rs:172), and each warp
-// keeps the K smallest (distance, encounter index) keys per query; the warps' partial lists are
-// merged at the end, one query per warp.
+// keeps the K smallest (distance, encounter index) keys per query (the slot of a result follows
+// from its encounter index, so no payload is carried); the warps' partial lists are merged at
+// the end, one query per warp.  The vector chunks are double-buffered in registers: the loads of
+// the next four chunks are in flight while the current four are consumed.
+//
+// WARP_UNIT = true is the variant for short lists (a few groups each): every warp is a unit of its
+// own and walks all groups of its list, so there is no cross-warp merge and no block barrier.
+template <bool WARP_UNIT>
 __global__ void __launch_bounds__(LS_WARPS * 32, 2)
 scan_lists_kernel(ListScanArgs la, uint32_t nlists) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ScanArgs& a = la.s;
-  // unit -> (list, batch): last list whose first unit is <= blockIdx.x
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // unit -> (list, batch): last list whose first unit is <= unit
+  const uint32_t unit = WARP_UNIT ? blockIdx.x * LS_WARPS + warp : blockIdx.x;
   uint32_t lo = 0, hi = nlists;
-  if (blockIdx.x >= la.unit_off[nlists]) return;
+  if (unit >= la.unit_off[nlists]) return;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (la.unit_off[mid] <= blockIdx.x) lo = mid; else hi = mid;
+    if (la.unit_off[mid] <= unit) lo = mid; else hi = mid;
   }
   const uint32_t l = lo;
-  const uint32_t batch = blockIdx.x - la.unit_off[l];
+  const uint32_t batch = unit - la.unit_off[l];
   const uint32_t ng = (uint32_t)(a.grp_off[l + 1] - a.grp_off[l]);
   const uint32_t p0 = la.list_off[l] + batch * LS_QB;
   const uint32_t nb = min((uint32_t)LS_QB, la.list_off[l + 1] - p0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ld4 = a.ld / 4;
-  float4* s_q = reinterpret_cast<float4*>(smem_raw);                               // LS_QB x ld4
-  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_q + (size_t)LS_QB * ld4);   // [warp][qi][K]
-  unsigned long long* s_pay = s_keys + (size_t)LS_WARPS * LS_QB * a.K;
+  // query vectors: LS_QB x ld4 per unit (per CTA, or per warp in the WARP_UNIT variant)
+  float4* s_q = reinterpret_cast<float4*>(smem_raw) + (WARP_UNIT ? (size_t)warp * LS_QB * ld4 : 0);
+  unsigned long long* s_keys =
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<float4*>(smem_raw) + (size_t)LS_QB * ld4);   // [warp][qi][K]
   const uint64_t G0 = a.grp_off[l];
   const uint32_t len = a.lens[l];
   const float4* V4 = reinterpret_cast<const float4*>(a.vecs);
-  if (threadIdx.x == 0) atomicAdd(a.bytes, (unsigned long long)nb * len * a.d * 4ull);
+  if (WARP_UNIT ? lane == 0 : threadIdx.x == 0) atomicAdd(a.bytes, (unsigned long long)nb * len * a.d * 4ull);
+  const uint32_t tid = WARP_UNIT ? (uint32_t)lane : threadIdx.x, nthr = WARP_UNIT ? 32u : blockDim.x;
 
   float thr[LS_QB];
-  uint32_t seq[LS_QB], pair[LS_QB];
-  unsigned long long key[LS_QB], pay[LS_QB], kth[LS_QB];
+  uint32_t seq[LS_QB];
+  unsigned long long key[LS_QB], kth[LS_QB];
 #pragma unroll
   for (int qi = 0; qi < LS_QB; ++qi) {
-    key[qi] = ~0ull; pay[qi] = ~0ull; kth[qi] = ~0ull;
-    thr[qi] = -1.0f; seq[qi] = 0; pair[qi] = 0;
+    key[qi] = ~0ull; kth[qi] = ~0ull;
+    thr[qi] = -1.0f; seq[qi] = 0;
     const float4* src = nullptr;
     if ((uint32_t)qi < nb) {
-      pair[qi] = la.pair_sorted[p0 + qi];
-      const uint32_t q = pair[qi] / a.nprobe;
+      const uint32_t pair = la.pair_sorted[p0 + qi];
+      const uint32_t q = pair / a.nprobe;
       thr[qi] = a.thr[q];
-      seq[qi] = a.seqbase[pair[qi]];
+      seq[qi] = a.seqbase[pair];
       src = reinterpret_cast<const float4*>(a.Q + (size_t)q * a.ld);
     }
-    for (uint32_t c = threadIdx.x; c < ld4; c += blockDim.x)
+    for (uint32_t c = tid; c < ld4; c += nthr)
       s_q[qi * ld4 + c] = src ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __syncthreads();
-  for (uint32_t g = warp; g < ng; g += LS_WARPS) {
+  if (WARP_UNIT) __syncwarp(); else __syncthreads();
+  for (uint32_t g = WARP_UNIT ? 0u : (uint32_t)warp; g < ng; g += WARP_UNIT ? 1u : (uint32_t)LS_WARPS) {
     const float4* base = V4 + (G0 + g) * ld4 * 32 + lane;
     float acc[LS_QB];
 #pragma unroll
     for (int qi = 0; qi < LS_QB; ++qi) acc[qi] = 0.0f;
-#pragma unroll 4
-    for (uint32_t c = 0; c < ld4; ++c) {
-      const float4 v = __ldg(base + (size_t)c * 32);
+    float4 va[4], vb[4];
+    auto load4 = [&](float4 (&v)[4], uint32_t c0) {
 #pragma unroll
-      for (int qi = 0; qi < LS_QB; ++qi) {
-        const float4 qv = s_q[qi * ld4 + c];
-        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.x, v.x);
-        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.y, v.y);
-        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.z, v.z);
-        acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.w, v.w);
+      for (int u = 0; u < 4; ++u)
+        v[u] = (c0 + u < ld4) ? __ldg(base + (size_t)(c0 + u) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto use4 = [&](const float4 (&v)[4], uint32_t c0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c0 + u < ld4) {
+#pragma unroll
+          for (int qi = 0; qi < LS_QB; ++qi) {
+            const float4 qv = s_q[qi * ld4 + c0 + u];
+            acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.x, v[u].x);
+            acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.y, v[u].y);
+            acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.z, v[u].z);
+            acc[qi] = dist_step<SPF_METRIC_EUCLIDEAN>(acc[qi], qv.w, v[u].w);
+          }
+        }
       }
+    };
+    load4(va, 0);
+    for (uint32_t c0 = 0; c0 < ld4; c0 += 8) {
+      load4(vb, c0 + 4);
+      use4(va, c0);
+      load4(va, c0 + 8);
+      use4(vb, c0 + 4);
     }
     const uint32_t pos = g * 32 + lane;
     const bool valid = pos < len;
@@ -413,41 +446,47 @@ scan_lists_kernel(ListScanArgs la, uint32_t nlists) {
         bal &= bal - 1;
         const unsigned long long k2 = __shfl_sync(0xffffffffu, ck, src);
         if (k2 < kth[qi]) {
-          unsigned long long kk[1] = {key[qi]}, pp[1] = {pay[qi]};
-          topk_insert<1>(kk, pp, k2, (G0 + g) * 32 + src, lane);
-          key[qi] = kk[0]; pay[qi] = pp[0];
+          topk_insert_key(key[qi], k2, lane);
           kth[qi] = __shfl_sync(0xffffffffu, key[qi], (a.K - 1) & 31);
         }
       }
     }
   }
+  if (WARP_UNIT) {          // this warp saw the whole list: its lists are the unit results
+#pragma unroll
+    for (int qi = 0; qi < LS_QB; ++qi) {
+      if ((uint32_t)qi < nb && (uint32_t)lane < a.K) {
+        const uint32_t pair = la.pair_sorted[p0 + qi];
+        la.unit_keys[(size_t)pair * a.K + lane] = key[qi];
+        la.unit_slots[(size_t)pair * a.K + lane] =
+            key[qi] == ~0ull ? ~0ull : G0 * 32 + ((uint32_t)(key[qi] & 0xffffffffull) - seq[qi]);
+      }
+    }
+    return;
+  }
   // merge the warps' partial lists: warp w owns query w of the batch
 #pragma unroll
-  for (int qi = 0; qi < LS_QB; ++qi) {
-    if ((uint32_t)lane < a.K) {
-      s_keys[((size_t)warp * LS_QB + qi) * a.K + lane] = key[qi];
-      s_pay[((size_t)warp * LS_QB + qi) * a.K + lane] = pay[qi];
-    }
-  }
+  for (int qi = 0; qi < LS_QB; ++qi)
+    if ((uint32_t)lane < a.K) s_keys[((size_t)warp * LS_QB + qi) * a.K + lane] = key[qi];
   __syncthreads();
   static_assert(LS_WARPS == LS_QB, "one query per warp in the final merge");
   if ((uint32_t)warp >= nb) return;
-  unsigned long long mk[1] = {~0ull}, mp[1] = {~0ull};
-  unsigned long long mkth = ~0ull;
+  unsigned long long mk = ~0ull, mkth = ~0ull;
   for (int w = 0; w < LS_WARPS; ++w) {
     const unsigned long long* sk = s_keys + ((size_t)w * LS_QB + warp) * a.K;
-    const unsigned long long* sp = s_pay + ((size_t)w * LS_QB + warp) * a.K;
     for (uint32_t e = 0; e < a.K; ++e) {
       const unsigned long long k2 = sk[e];
       if (k2 >= mkth) break;          // partial lists are ascending
-      topk_insert<1>(mk, mp, k2, sp[e], lane);
-      mkth = __shfl_sync(0xffffffffu, mk[0], (a.K - 1) & 31);
+      topk_insert_key(mk, k2, lane);
+      mkth = __shfl_sync(0xffffffffu, mk, (a.K - 1) & 31);
     }
   }
   const uint32_t mypair = la.pair_sorted[p0 + warp];
   if ((uint32_t)lane < a.K) {
-    la.unit_keys[(size_t)mypair * a.K + lane] = mk[0];
-    la.unit_slots[(size_t)mypair * a.K + lane] = mp[0];
+    la.unit_keys[(size_t)mypair * a.K + lane] = mk;
+    // slot of a result: first slot of the list + (encounter index - encounter base of this probe)
+    la.unit_slots[(size_t)mypair * a.K + lane] =
+        mk == ~0ull ? ~0ull : G0 * 32 + ((uint32_t)(mk & 0xffffffffull) - a.seqbase[mypair]);
   }
 }
 
@@ -917,11 +956,21 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     ListScanArgs la;
     la.s = a; la.pair_sorted = pv2.p; la.list_off = loff.p; la.unit_off = uoff.p;
     la.unit_keys = ukeys.p; la.unit_slots = uslots.p;
-    const size_t smem = (size_t)LS_QB * ld * sizeof(float) + (size_t)LS_WARPS * LS_QB * k * 16;
-    if (smem > 200 * 1024) return fail(SPF_E_INVALID, "dimension too large for the list-major scan");
-    SPF_CUDA(cudaFuncSetAttribute(scan_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t max_units = npairs / LS_QB + nlists + 1;   // upper bound; surplus CTAs exit at once
-    scan_lists_kernel<<<(unsigned)max_units, LS_WARPS * 32, smem, st>>>(la, nlists);
+    const uint64_t max_units = npairs / LS_QB + nlists + 1;   // upper bound; surplus units exit at once
+    // short lists (a few 32-vector groups each): one warp per unit; long lists: one CTA per unit
+    const uint32_t nloc = idx->list_end - idx->list_begin;
+    const bool warp_units = nloc > 0 && idx->total_groups / nloc < 24;
+    if (warp_units) {
+      const size_t smem = (size_t)LS_WARPS * LS_QB * ld * sizeof(float);
+      if (smem > 200 * 1024) return fail(SPF_E_INVALID, "dimension too large for the list-major scan");
+      SPF_CUDA(cudaFuncSetAttribute(scan_lists_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scan_lists_kernel<true><<<(unsigned)ceil_div(max_units, LS_WARPS), LS_WARPS * 32, smem, st>>>(la, nlists);
+    } else {
+      const size_t smem = (size_t)LS_QB * ld * sizeof(float) + (size_t)LS_WARPS * LS_QB * k * 8;
+      if (smem > 200 * 1024) return fail(SPF_E_INVALID, "dimension too large for the list-major scan");
+      SPF_CUDA(cudaFuncSetAttribute(scan_lists_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scan_lists_kernel<false><<<(unsigned)max_units, LS_WARPS * 32, smem, st>>>(la, nlists);
+    }
     SPF_TRY(check_launch(c, "scan_lists_kernel"));
     merge_units_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(la, nq);
     SPF_TRY(check_launch(c, "merge_units_kernel"));

@@ -470,7 +470,7 @@ def build_lists(oracle, data, k, seed):
 
 @pytest.mark.parametrize("n,d,nlists,topk,nprobe", [
     (3000, 16, 40, 10, 0), (5000, 128, 64, 10, 0), (5000, 33, 50, 5, 20), (4000, 96, 30, 40, 8),
-    (2000, 8, 300, 100, 0), (6000, 16, 1500, 10, 40),
+    (2000, 8, 300, 100, 0), (6000, 16, 1500, 10, 40), (40000, 16, 30, 10, 6),
 ])
 def test_search_matches_oracle(spf, ctx, oracle, n, d, nlists, topk, nprobe):
     data = clustered(n, d, 20, n + d)
