@@ -25,7 +25,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(NTHREADS)
 assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __restrict__ C, uint32_t k,
                     uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
-                    int cap, float* __restrict__ dense) {
+                    int cap, float* __restrict__ dense, int symmetric) {
   __shared__ __align__(16) float Xs[2][BK][BM + PAD];
   __shared__ __align__(16) float Cs[2][BK][BN + PAD];
   __shared__ unsigned rowmin[BM];
@@ -52,6 +52,9 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   // dense-only launches may split the centroid tiles over blockIdx.y (candidate mode keeps a
   // CTA-wide running minimum per row and therefore uses gridDim.y == 1)
   for (uint32_t c0 = blockIdx.y * BN; c0 < k; c0 += gridDim.y * BN) {
+    // symmetric mode (P == C, e.g. the k x k centroid matrix): d(a,b) == d(b,a) bit for bit for all
+    // three metrics, so tiles strictly below the diagonal are skipped and mirrored from above
+    if (symmetric && c0 + BN <= row0) continue;
     const bool crow_ok = (c0 + lrow) < k;
     const float* crow = C + (size_t)(c0 + lrow) * ld;
 
@@ -107,7 +110,10 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t cj = c0 + tx * 4 + j;
-            if (cj < k) dense[(size_t)r * k + cj] = acc[i][j];
+            if (cj < k) {
+              dense[(size_t)r * k + cj] = acc[i][j];
+              if (symmetric && cj >= row0 + BM) dense[(size_t)cj * k + r] = acc[i][j];   // mirror (off-diagonal tiles)
+            }
           }
         }
       }
@@ -156,6 +162,8 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
 
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
                         uint32_t ld, float factor, const CandBuf* cb, float* dense) {
+  // a dense P x P request is the symmetric centroid matrix: half the tiles
+  const int symmetric = (cb == nullptr && dense != nullptr && P == C && m == k) ? 1 : 0;
   if (m == 0 || k == 0) return SPF_OK;
   CandRec* cand = cb ? cb->rec : nullptr;
   RowInfo* info = cb ? cb->info : nullptr;
@@ -169,15 +177,15 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   switch (metric) {
     case SPF_METRIC_EUCLIDEAN:
       assign_exact_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric);
       break;
     case SPF_METRIC_MANHATTAN:
       assign_exact_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric);
       break;
     case SPF_METRIC_CHEBYSHEV:
       assign_exact_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric);
       break;
     default:
       return fail(SPF_E_INVALID, "unknown metric %d", metric);

@@ -103,7 +103,7 @@ def sweep(args):
     ctx.set_profiling(True)
     for prune in (1.2, float("inf")):
         for nprobe in (8, 10, 16, 32, 64, 128, 256):
-            idx.search(q[:2000], topk, nprobe, prune_factor=prune)
+            idx.search(q, topk, nprobe, prune_factor=prune)     # warm-up at full size (scratch allocation)
             t0 = time.perf_counter()
             ids, dists, counts = idx.search(q, topk, nprobe, prune_factor=prune)
             dt = time.perf_counter() - t0
@@ -118,6 +118,83 @@ def sweep(args):
                               "scan_algorithmic_gbs": b / (scan_ms * 1e-3) / 1e9,
                               "scan_fp32_frac": lane / (scan_ms * 1e-3) / FP32_PEAK,
                               "index_vectors": idx.nvectors}), flush=True)
+
+
+def qshard(args):
+    """Config 5 at N GPUs: posting lists sharded by list (balanced by vectors), queries and centroids
+    replicated, every rank scans its own lists, partial top-k all-gathered and merged on the stable
+    key (spf_topk_merge).  Run under torchrun."""
+    import torch
+    import torch.distributed as dist
+
+    import spfresh_b200 as s
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, k, topk = 1_000_000, 128, 4096, 10
+    rows = clustered_rows(n, d, 1024, 44) if args.kind == "clustered" else \
+        np.random.Generator(np.random.Philox(key=42)).standard_normal((n, d), dtype=np.float32)
+    q = (clustered_rows(args.nq, d, 1024, 44)[::-1].copy() if args.kind == "clustered" else
+         np.random.Generator(np.random.Philox(key=46)).standard_normal((args.nq, d), dtype=np.float32))
+    ctx = s.Context(local)
+    ds = s.Dataset(ctx, rows)
+    cent = np.random.Generator(np.random.Philox(key=7)).choice(n, k, replace=False)
+    res = ds.assign(0, cent)
+    med = ds.update_medoids_from(0, res, cent)
+    res.free()
+    res = ds.assign(0, med)
+    f = res.fetch(best=False, dmin=False)
+    res.free()
+    # contiguous list ranges with (nearly) equal numbers of vectors
+    cum = f.offsets.astype(np.int64)
+    cuts = [int(np.searchsorted(cum, cum[-1] * r // world)) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, k
+    idx = s.DeviceIndex.pack(ds, f.offsets, f.members, med, list_range=(cuts[rank], cuts[rank + 1]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.set_profiling(True)
+    for nprobe in (8, 32, 128):
+        idx.search(q, topk, nprobe, want_keys=True)
+        barrier()
+        t0 = time.perf_counter()
+        ids, dists, counts, keys = idx.search(q, topk, nprobe, want_keys=True)
+        t_scan = time.perf_counter() - t0
+        scan_ms = ctx.kernel_ms("scan")
+        if world > 1:
+            def gather(a):
+                t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+                outs = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(outs, t)
+                return np.stack([o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in outs])
+            gk, gi, gd, gc = gather(keys), gather(ids), gather(dists), gather(counts)
+            t_x = time.perf_counter() - t0
+            if rank == 0:
+                s.topk_merge(gk, gi, gd, gc)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt, t_scan, scan_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, t_scan, scan_ms = float(t[0]), float(t[1]), float(t[2])
+        if rank == 0:
+            print(json.dumps({"config": "qshard", "data": args.kind, "n_gpus": world, "nq": args.nq, "k": topk,
+                              "nprobe": nprobe, "qps_merged": args.nq / dt, "qps_scan_only": args.nq / t_scan,
+                              "scan_kernel_ms_max": scan_ms, "call_ms": t_scan * 1e3, "total_ms": dt * 1e3,
+                              "lists_rank0": cuts[1] - cuts[0], "vectors_rank0": idx.nvectors,
+                              "merge": "host spf_topk_merge on rank 0 after an NCCL all-gather of keys/ids/dists/counts"}),
+                  flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def deep(args):
@@ -205,13 +282,13 @@ def deep(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["gist", "sweep", "deep"])
+    ap.add_argument("what", choices=["gist", "sweep", "deep", "qshard"])
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--rows-total", type=int, default=100_000_000)
     ap.add_argument("--nq", type=int, default=100_000)
     ap.add_argument("--kind", default="gauss", choices=["gauss", "clustered"])
     args = ap.parse_args()
-    {"gist": gist, "sweep": sweep, "deep": deep}[args.what](args)
+    {"gist": gist, "sweep": sweep, "deep": deep, "qshard": qshard}[args.what](args)
 
 
 if __name__ == "__main__":
