@@ -170,15 +170,32 @@ def qshard(args):
         t_scan = time.perf_counter() - t0
         scan_ms = ctx.kernel_ms("scan")
         if world > 1:
-            def gather(a):
-                t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
-                outs = [torch.empty_like(t) for _ in range(world)]
-                dist.all_gather(outs, t)
-                return np.stack([o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in outs])
-            gk, gi, gd, gc = gather(keys), gather(ids), gather(dists), gather(counts)
-            t_x = time.perf_counter() - t0
+            # exchange on the device: all-gather of the (key, id) pairs, k smallest keys per query
+            # (keys are globally consistent; distances and counts follow from them)
+            sent = np.iinfo(np.int64).max
+            kt = torch.from_numpy(keys.view(np.int64)).to(dev)
+            kt = torch.where(kt == -1, torch.full_like(kt, sent), kt)          # empty slots sort last
+            it = torch.from_numpy(ids.view(np.int64)).to(dev)
+            gk = [torch.empty_like(kt) for _ in range(world)]
+            gi = [torch.empty_like(it) for _ in range(world)]
+            dist.all_gather(gk, kt)
+            dist.all_gather(gi, it)
+            allk, alli = torch.cat(gk, dim=1), torch.cat(gi, dim=1)
+            topv, topi = torch.topk(allk, topk, dim=1, largest=False, sorted=True)
+            m_ids = torch.gather(alli, 1, topi)
+            m_counts = (topv != sent).sum(dim=1)
             if rank == 0:
-                s.topk_merge(gk, gi, gd, gc)
+                m_ids_h, m_keys_h, m_counts_h = m_ids.cpu().numpy(), topv.cpu().numpy(), m_counts.cpu().numpy()
+                if nprobe == 8:                  # cross-check the device merge against spf_topk_merge once
+                    gkh = np.stack([g.cpu().numpy() for g in gk]).view(np.uint64)
+                    gkh[gkh == np.uint64(sent)] = np.uint64(np.iinfo(np.uint64).max)
+                    gih = np.stack([g.cpu().numpy() for g in gi]).view(np.uint64)
+                    gdh = (gkh >> np.uint64(32)).astype(np.uint32).view(np.float32)
+                    gch = (gkh != np.uint64(np.iinfo(np.uint64).max)).sum(axis=2).astype(np.uint32)
+                    r_ids, _, r_counts = s.topk_merge(gkh, gih, gdh, gch)
+                    assert np.array_equal(r_counts, m_counts_h.astype(np.uint32))
+                    for qi in range(0, args.nq, 997):
+                        assert np.array_equal(r_ids[qi, :r_counts[qi]], m_ids_h[qi, :r_counts[qi]].view(np.uint64))
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -190,7 +207,7 @@ def qshard(args):
                               "nprobe": nprobe, "qps_merged": args.nq / dt, "qps_scan_only": args.nq / t_scan,
                               "scan_kernel_ms_max": scan_ms, "call_ms": t_scan * 1e3, "total_ms": dt * 1e3,
                               "lists_rank0": cuts[1] - cuts[0], "vectors_rank0": idx.nvectors,
-                              "merge": "host spf_topk_merge on rank 0 after an NCCL all-gather of keys/ids/dists/counts"}),
+                              "merge": "NCCL all-gather of (key, id) + per-query k smallest keys on the device (checked against spf_topk_merge)"}),
                   flush=True)
     if world > 1:
         dist.barrier()
