@@ -181,6 +181,19 @@ int  spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen);
 int  spf_kmpp_push(spf_kmpp* s, uint64_t row);
 /* Diagnostics of the last round: the f32 sum (:278) and the f64 weight total. */
 int  spf_kmpp_last_sums(const spf_kmpp* s, float* sum, double* total);
+/* Row-sharded form (one session per rank over its shard): the newest centroid
+ * arrives as an explicit vector, the reductions of :278 and of WeightedIndex are done by the host
+ * over the ranks:
+ *   fold_vector   folds the centroid into the shard's running minimum, returns the shard's f32
+ *                 sum of minimum distances (:260-278); the ranks' sums are added in rank order
+ *   weight_total  with the global sum as denominator (:279-282): the shard's f64 weight total;
+ *                 returns 1 when a weight of this shard is invalid (the Err arm, :287-290)
+ *   pick_local    partition point of the shard's cumulative weights for a target already made
+ *                 relative to the shard (u * total - sum of the lower ranks' totals) */
+int  spf_kmpp_begin_sharded(spf_dataset* ds, int metric, spf_kmpp** out);
+int  spf_kmpp_fold_vector(spf_kmpp* s, const float* centroid, float* local_sum);
+int  spf_kmpp_weight_total(spf_kmpp* s, float global_sum, double* local_total);
+int  spf_kmpp_pick_local(spf_kmpp* s, double target, uint64_t* row);
 void spf_kmpp_free(spf_kmpp* s);
 
 /* ---- bisect seed ----------------------------------------------------------------------- *

@@ -59,6 +59,10 @@ SIGNATURES = {
     "spf_kmpp_round": (C.c_int, [_vp, C.c_double, _u64p]),
     "spf_kmpp_push": (C.c_int, [_vp, C.c_uint64]),
     "spf_kmpp_last_sums": (C.c_int, [_vp, _f32p, C.POINTER(C.c_double)]),
+    "spf_kmpp_begin_sharded": (C.c_int, [_vp, C.c_int, _vpp]),
+    "spf_kmpp_fold_vector": (C.c_int, [_vp, _vp, _f32p]),
+    "spf_kmpp_weight_total": (C.c_int, [_vp, C.c_float, C.POINTER(C.c_double)]),
+    "spf_kmpp_pick_local": (C.c_int, [_vp, C.c_double, _u64p]),
     "spf_kmpp_free": (None, [_vp]),
     "spf_farthest": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "spf_index_pack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vpp]),

@@ -24,6 +24,7 @@ struct spf_kmpp {
   double* d_total = nullptr;
   float last_sum = 0.f;
   double last_total = 0.0;
+  float* d_vec = nullptr;    // sharded sessions: the newest centroid as an explicit vector (ld floats)
 };
 
 namespace spf {
@@ -240,7 +241,7 @@ farthest_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __rest
 // mind[i] = min(mind[i], d(x_i, newest))  (hierarchical.rs:260-276 restated as a running min)
 template <int METRIC>
 __global__ void __launch_bounds__(PD_THREADS)
-kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, uint64_t newest, int first,
+kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const float* __restrict__ cvec, int first,
                    float* __restrict__ mind) {
   __shared__ PairDistSmem sm[PD_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,7 +250,7 @@ kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, uint64_
     const uint64_t i = base + lane;
     const bool valid = i < n;
     const float* pa = valid ? X + (size_t)i * ld : nullptr;
-    const float* pb = valid ? X + (size_t)newest * ld : nullptr;
+    const float* pb = valid ? cvec : nullptr;       // the newest centroid (a dataset row or an explicit vector)
     const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
     if (valid && (first || dv < mind[i])) mind[i] = dv;
   }
@@ -322,14 +323,14 @@ kmpp_block_sums_kernel(const float* __restrict__ mind, uint64_t n, const float* 
 // cumulative_weights.partition_point(|w| w <= u) with u = u01 * total (rand 0.9 WeightedIndex).
 __global__ void kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
                                  const double* __restrict__ block_sums, uint64_t nblocks,
-                                 const int* __restrict__ bad, double u01, uint64_t* __restrict__ res,
+                                 const int* __restrict__ bad, double u01, double target, uint64_t* __restrict__ res,
                                  double* __restrict__ d_total) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double total = 0.0;
   for (uint64_t b = 0; b < nblocks; ++b) total += block_sums[b];
   d_total[0] = total;
   if (*bad || total == 0.0 || !isfinite(total)) { res[0] = 1; res[1] = 0; return; }
-  const double u = u01 * total;
+  const double u = target >= 0.0 ? target : u01 * total;   // sharded pick: target already relative to this shard
   const float denom = fmaxf(d_sum[0], 1e-10f);
   double cum = 0.0;
   uint64_t b = 0;
@@ -629,7 +630,8 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
     KernelTimer t(c, "kmpp_update");
     const int first = s->rounds == 0 ? 1 : 0;
     SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
-      kmpp_update_kernel<decltype(M)::value><<<pd_grid(c, n), PD_THREADS, 0, st>>>(ds->x, ds->ld, n, s->newest, first, s->mind);
+      kmpp_update_kernel<decltype(M)::value><<<pd_grid(c, n), PD_THREADS, 0, st>>>(
+          ds->x, ds->ld, n, ds->x + (size_t)s->newest * ds->ld, first, s->mind);
       return check_launch(c, "kmpp_update_kernel");
     }));
   }
@@ -646,7 +648,7 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
     SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
     kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->bad);
     SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
-    kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, u01, s->res, s->d_total);
+    kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, u01, -1.0, s->res, s->d_total);
     SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
   }
   uint64_t res[2] = {0, 0};
@@ -658,6 +660,85 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
   s->newest = res[1];
   s->pending = true;
   *chosen = res[1];
+  return SPF_OK;
+}
+
+// ---- row-sharded k-means++: hierarchical.rs:249-293 split at its reductions ----
+int spf_kmpp_begin_sharded(spf_dataset* ds, int metric, spf_kmpp** out) {
+  SPF_TRY(spf_kmpp_begin(ds, metric, 0, out));
+  spf_kmpp* s = *out;
+  s->pending = false;      // no centroid yet: the first one arrives through spf_kmpp_fold_vector
+  if (cudaMalloc((void**)&s->d_vec, (size_t)ds->ld * sizeof(float)) != cudaSuccess) {
+    spf_kmpp_free(s);
+    *out = nullptr;
+    return fail(SPF_E_OOM, "k-means++ session allocation failed");
+  }
+  return SPF_OK;
+}
+
+int spf_kmpp_fold_vector(spf_kmpp* s, const float* centroid, float* local_sum) {
+  if (!s || !centroid || !local_sum || !s->d_vec) return fail(SPF_E_INVALID, "spf_kmpp_fold_vector: bad argument");
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint64_t n = ds->n;
+  SPF_CUDA(cudaMemsetAsync(s->d_vec, 0, (size_t)ds->ld * sizeof(float), st));
+  SPF_CUDA(cudaMemcpyAsync(s->d_vec, centroid, (size_t)ds->d * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int first = s->rounds == 0 ? 1 : 0;
+  SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
+    kmpp_update_kernel<decltype(M)::value><<<pd_grid(c, n), PD_THREADS, 0, st>>>(ds->x, ds->ld, n, s->d_vec, first, s->mind);
+    return check_launch(c, "kmpp_update_kernel");
+  }));
+  s->rounds += 1;
+  if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum);
+  else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
+  SPF_TRY(check_launch(c, "kmpp sum kernel"));
+  SPF_CUDA(cudaMemcpyAsync(local_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
+}
+
+int spf_kmpp_weight_total(spf_kmpp* s, float global_sum, double* local_total) {
+  if (!s || !local_total) return fail(SPF_E_INVALID, "spf_kmpp_weight_total: NULL argument");
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  SPF_CUDA(cudaMemcpyAsync(s->d_sum, &global_sum, sizeof(float), cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
+  kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->bad);
+  SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
+  // total + validity through the pick kernel (target beyond the total: the pick itself is discarded)
+  kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, 0.0, s->res, s->d_total);
+  SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
+  uint64_t res[2] = {0, 0};
+  SPF_CUDA(cudaMemcpyAsync(res, s->res, sizeof(res), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(local_total, s->d_total, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  int bad = 0;
+  SPF_CUDA(cudaMemcpy(&bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost));
+  return bad ? 1 : SPF_OK;   // 1: an invalid weight on this shard (the Err arm of WeightedIndex::new)
+}
+
+int spf_kmpp_pick_local(spf_kmpp* s, double target, uint64_t* row) {
+  if (!s || !row) return fail(SPF_E_INVALID, "spf_kmpp_pick_local: NULL argument");
+  if (!(target >= 0.0)) return fail(SPF_E_INVALID, "target must be >= 0");
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // block sums and the global denominator are those of the preceding spf_kmpp_weight_total
+  kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, target, s->res, s->d_total);
+  SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
+  uint64_t res[2] = {0, 0};
+  SPF_CUDA(cudaMemcpyAsync(res, s->res, sizeof(res), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  if (res[0] != 0) return 1;
+  *row = res[1];
   return SPF_OK;
 }
 
@@ -687,6 +768,7 @@ void spf_kmpp_free(spf_kmpp* s) {
   if (s->res) cudaFree(s->res);
   if (s->d_sum) cudaFree(s->d_sum);
   if (s->d_total) cudaFree(s->d_total);
+  if (s->d_vec) cudaFree(s->d_vec);
   delete s;
 }
 

@@ -290,6 +290,45 @@ class KmppSession:
             pass
 
 
+class KmppShardSession:
+    """Row-sharded k-means++ state of one rank (spf_kmpp_begin_sharded / fold_vector / weight_total /
+    pick_local)."""
+
+    def __init__(self, ds: Dataset, metric: int):
+        self.ds = ds
+        h = C.c_void_p()
+        check(lib().spf_kmpp_begin_sharded(ds.handle, metric, C.byref(h)))
+        self._h = h
+
+    def fold_vector(self, centroid) -> float:
+        v = as_f32(centroid).reshape(self.ds.d)
+        out = C.c_float()
+        check(lib().spf_kmpp_fold_vector(self._h, ptr(v), C.byref(out)))
+        return float(out.value)
+
+    def weight_total(self, global_sum: float):
+        """Returns (local f64 total, ok); ok is False when a local weight is invalid."""
+        out = C.c_double()
+        rc = check(lib().spf_kmpp_weight_total(self._h, float(np.float32(global_sum)), C.byref(out)))
+        return float(out.value), rc == 0
+
+    def pick_local(self, target: float):
+        out = C.c_uint64()
+        rc = check(lib().spf_kmpp_pick_local(self._h, float(target), C.byref(out)))
+        return None if rc == 1 else int(out.value)
+
+    def free(self):
+        if self._h:
+            lib().spf_kmpp_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceIndex:
     """spf_index: posting lists + centroids resident in HBM."""
 

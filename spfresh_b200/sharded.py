@@ -37,6 +37,21 @@ class Comm:
         """Every rank contributes an array of the same shape / dtype; returns them in rank order."""
         raise NotImplementedError
 
+    def allgather_many(self, arrays: Sequence[np.ndarray]) -> List[List[np.ndarray]]:
+        """Several arrays in ONE message (the exchange is latency bound): result[r][i] is rank r's
+        i-th array."""
+        arrays = [np.ascontiguousarray(a) for a in arrays]
+        flat = [a.view(np.uint8).reshape(-1) for a in arrays]
+        outs = self.allgather(np.concatenate(flat))
+        res = []
+        for o in outs:
+            parts, pos = [], 0
+            for a, f in zip(arrays, flat):
+                parts.append(o[pos:pos + f.size].view(a.dtype).reshape(a.shape))
+                pos += f.size
+            res.append(parts)
+        return res
+
 
 class SingleComm(Comm):
     def allgather(self, a):
@@ -104,6 +119,10 @@ class DeviceShard:
     def medoid_candidates(self, metric, res, means):
         return self.ds.medoid_candidates(metric, res, means)
 
+    def kmpp_session(self, metric):
+        from .device import KmppShardSession
+        return KmppShardSession(self.ds, metric)
+
     def rows(self, local_rows: Sequence[int]) -> np.ndarray:
         if self._host is None:                       # shard created on the device: read the rows back
             return self.ds.fetch_rows(np.asarray(local_rows, np.uint64))
@@ -140,30 +159,81 @@ def update_centroids(shard, comm: Comm, metric: int, res, old_vectors: np.ndarra
     """One sharded update_centroids.  Returns (new global rows, new vectors, global means)."""
     k, d = old_vectors.shape
     sums, counts = shard.cluster_sums(res)                                   # C1, local part
-    all_sums = comm.allgather(np.ascontiguousarray(sums, np.float32))
-    all_counts = comm.allgather(np.ascontiguousarray(counts, np.uint64))
+    parts = comm.allgather_many([np.asarray(sums, np.float32), np.asarray(counts, np.uint64)])
     tot = np.zeros((k, d), np.float32)
     cnt = np.zeros(k, np.uint64)
     for r in range(comm.world):                                              # fixed (rank) order
-        tot = (tot + all_sums[r]).astype(np.float32)
-        cnt = cnt + all_counts[r]
+        tot = (tot + parts[r][0]).astype(np.float32)
+        cnt = cnt + parts[r][1]
     means = np.zeros((k, d), np.float32)
     nz = cnt > 0
     means[nz] = (tot[nz] / cnt[nz].astype(np.float32)[:, None]).astype(np.float32)   # utils.rs:14
 
     dist, row = shard.medoid_candidates(metric, res, means)                  # C2, local part
     grow = np.where(row == np.uint64(np.iinfo(np.uint64).max), row, row + np.uint64(shard_starts[comm.rank]))
-    all_dist = comm.allgather(np.ascontiguousarray(dist, np.float32))
-    all_row = comm.allgather(np.ascontiguousarray(grow, np.uint64))
+    cands = comm.allgather_many([np.asarray(dist, np.float32), np.asarray(grow, np.uint64)])
     best_d = np.full(k, np.inf, np.float32)
     best_row = np.zeros(k, np.uint64)                                        # identity (0, +inf) :163
     for r in range(comm.world):                                              # strict <: lowest rank wins ties
-        better = all_dist[r] < best_d
-        best_d[better] = all_dist[r][better]
-        best_row[better] = all_row[r][better]
+        better = cands[r][0] < best_d
+        best_d[better] = cands[r][0][better]
+        best_row[better] = cands[r][1][better]
     new_rows = np.where(nz, best_row, np.asarray(old_rows, np.uint64))       # empty cluster keeps its centroid :146-149
     new_vecs = gather_rows(shard, comm, new_rows, shard_starts)
     return new_rows, new_vecs, means
+
+
+def kmeans_plus_plus(shard, comm: Comm, metric: int, k: int, rng, shard_starts: Optional[np.ndarray] = None):
+    """Row-sharded initialize_clusters_kmeans_plus_plus (hierarchical.rs:249-293).  `rng` is a
+    RandomSource (clustering.py) that every rank seeds identically, so the draws need no exchange:
+    choose_index(n_total) for the first centroid (:253-255) and the uniform fallback (:287-290),
+    uniform01() for the weighted pick (:285-286).  Per round: every rank folds the newest centroid
+    into its running minimum (local), the f32 sums are added in rank order (:278), every rank forms
+    its f64 weight total with the global denominator (:279-282), and the rank whose weight range
+    holds u * total picks inside its shard.  Returns the k global centroid rows."""
+    starts = shard_layout(shard, comm) if shard_starts is None else shard_starts
+    sizes = np.array([int(x[0]) for x in comm.allgather(np.array([shard.n], np.int64))], np.int64)
+    n_total = int(sizes.sum())
+    sess = shard.kmpp_session(metric)
+    try:
+        chosen = [int(rng.choose_index(n_total))]
+        for _ in range(1, k):
+            vec = gather_rows(shard, comm, np.array([chosen[-1]], np.uint64), starts)[0]
+            s_local = np.float32(sess.fold_vector(vec))
+            s = np.float32(0.0)
+            for part in comm.allgather(np.array([s_local], np.float32)):          # rank order
+                s = np.float32(s + part[0])
+            t_local, ok = sess.weight_total(float(s))
+            info = comm.allgather(np.array([t_local, 1.0 if ok else 0.0], np.float64))
+            totals = np.array([x[0] for x in info], np.float64)
+            total = np.float64(0.0)
+            for t in totals:
+                total = np.float64(total + t)
+            all_ok = all(x[1] == 1.0 for x in info)
+            row = None
+            if all_ok and total > 0.0 and np.isfinite(total):
+                u = np.float64(rng.uniform01()) * total
+                prefix = np.float64(0.0)
+                owner = comm.world - 1
+                for r in range(comm.world - 1):
+                    if u < prefix + totals[r]:
+                        owner = r
+                        break
+                    prefix = np.float64(prefix + totals[r])
+                else:
+                    prefix = np.float64(sum(totals[:comm.world - 1], np.float64(0.0)))
+                mine = -1
+                if comm.rank == owner:
+                    loc = sess.pick_local(float(u - prefix))
+                    mine = -1 if loc is None else int(loc) + int(starts[owner])
+                got = [int(x[0]) for x in comm.allgather(np.array([mine], np.int64))]
+                row = got[owner] if got[owner] >= 0 else None
+            if row is None:                                                       # Err arm: uniform draw
+                row = int(rng.choose_index(n_total))
+            chosen.append(row)
+        return np.array(chosen, np.uint64)
+    finally:
+        sess.free()
 
 
 class ShardedKMeans:

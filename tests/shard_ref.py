@@ -52,3 +52,73 @@ class OracleShard:
 
     def rows(self, local_rows):
         return self.x[np.asarray(local_rows, np.int64)]
+
+
+class OracleKmpp:
+    """The shard-local half of the sharded k-means++ (same interface as KmppShardSession)."""
+
+    def __init__(self, shard, metric):
+        self.x, self.metric = shard.x, metric
+        self.mind = None
+        self.w = None
+
+    def fold_vector(self, centroid):
+        c = np.ascontiguousarray(centroid, np.float32)
+        d = np.array([oracle.distance(self.metric, self.x[i], c) for i in range(self.x.shape[0])], np.float32)
+        self.mind = d if self.mind is None else np.where(d < self.mind, d, self.mind)
+        acc = np.float32(0.0)
+        for v in self.mind:                                   # sequential f32 fold (:278)
+            acc = np.float32(acc + v)
+        return float(acc)
+
+    def weight_total(self, global_sum):
+        denom = np.float32(max(np.float32(global_sum), np.float32(1e-10)))
+        self.w = ((self.mind * self.mind).astype(np.float32) / denom).astype(np.float32).astype(np.float64)
+        ok = bool(np.all(self.w >= 0.0))
+        # the device adds 1024-weight blocks (256 threads x 4 consecutive weights, tree over threads),
+        # then the blocks in order: mirror it so the f64 totals agree bit for bit
+        tot = np.float64(0.0)
+        self.block_sums = []
+        for b0 in range(0, self.w.size, 1024):
+            blk = np.zeros(1024, np.float64)
+            seg = self.w[b0:b0 + 1024]
+            blk[:seg.size] = seg
+            t = blk.reshape(256, 4)
+            per_thread = np.zeros(256, np.float64)
+            for e in range(4):
+                per_thread = per_thread + t[:, e]
+            sarr = per_thread.copy()
+            step = 128
+            while step > 0:
+                sarr[:step] = sarr[:step] + sarr[step:2 * step]
+                step //= 2
+            self.block_sums.append(np.float64(sarr[0]))
+            tot = np.float64(tot + sarr[0])
+        return float(tot), ok
+
+    def pick_local(self, target):
+        u = np.float64(target)
+        cum = np.float64(0.0)
+        b = 0
+        nb = len(self.block_sums)
+        while b + 1 < nb:
+            if not (cum + self.block_sums[b] <= u):
+                break
+            cum = np.float64(cum + self.block_sums[b])
+            b += 1
+        n = self.w.size
+        for i in range(b * 1024, n - 1):
+            cum = np.float64(cum + self.w[i])
+            if not (cum <= u):
+                return i
+        return n - 1
+
+    def free(self):
+        pass
+
+
+def _kmpp_session(self, metric):
+    return OracleKmpp(self, metric)
+
+
+OracleShard.kmpp_session = _kmpp_session

@@ -312,6 +312,52 @@ def test_sharded_build_step_matches_oracle_shards(spf, oracle, metric):
             c_.close()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_sharded_kmeanspp_matches_oracle_shards(spf, oracle, metric):
+    """Sharded k-means++ on three device shards == the oracle-backed shards, and (one shard) == the
+    single-process device k-means++ session."""
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_ref import OracleShard
+    from spfresh_b200.sharded import DeviceShard, SingleComm, ThreadComm, kmeans_plus_plus
+    data = clustered(2300, 12, 9, 55 + metric)
+    bounds = [0, 900, 1500, 2300]
+    u01 = [0.37, 0.91, 0.08, 0.55, 0.73, 0.21, 0.66]
+
+    def run_all(make_shard):
+        grp = ThreadComm.Group(3)
+        out = [None] * 3
+
+        def run(r):
+            out[r] = kmeans_plus_plus(make_shard(r), ThreadComm(grp, r), metric, 8,
+                                      spf.ScriptedRandomSource(index=[1234], u01=u01))
+        th = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return out
+    ctxs = [spf.Context(0) for _ in range(3)]
+    try:
+        dss = [spf.Dataset(ctxs[r], data[bounds[r]:bounds[r + 1]]) for r in range(3)]
+        got = run_all(lambda r: DeviceShard(dss[r], bounds[r], data[bounds[r]:bounds[r + 1]]))
+        ref = run_all(lambda r: OracleShard(data[bounds[r]:bounds[r + 1]], bounds[r]))
+        for r in range(3):
+            assert np.array_equal(got[r], ref[r])
+        whole = spf.Dataset(ctxs[0], data)
+        one = kmeans_plus_plus(DeviceShard(whole, 0, data), SingleComm(), metric, 8,
+                               spf.ScriptedRandomSource(index=[1234], u01=u01))
+        sess = whole.kmeanspp(metric, 1234)
+        rows = [1234] + [sess.round(u) for u in u01]
+        sess.free()
+        assert np.array_equal(one, np.array(rows, np.uint64))
+        whole.free()
+        for d_ in dss:
+            d_.free()
+    finally:
+        for c_ in ctxs:
+            c_.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # update_centroids / farthest / k-means++
 # ----------------------------------------------------------------------------------------------

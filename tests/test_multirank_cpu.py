@@ -155,3 +155,65 @@ def test_sharded_update_over_gloo(tmp_path):
     assert np.array_equal(single[0], oracle.update_medoids(data, 0, a.offsets, a.members, init.astype(np.uint64)))
     # two shards: same medoids (the mean differs only in f32 summation order; no near-tie here)
     assert np.array_equal(gloo_rows[0], single[0])
+
+
+def run_sharded_kmpp(comm, data, bounds, metric, k, first, u01):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_ref import OracleShard
+    from spfresh_b200.clustering import ScriptedRandomSource
+    from spfresh_b200.sharded import kmeans_plus_plus
+    lo, hi = bounds[comm.rank], bounds[comm.rank + 1]
+    return kmeans_plus_plus(OracleShard(data[lo:hi], lo), comm, metric, k,
+                            ScriptedRandomSource(index=[first], u01=u01))
+
+
+KMPP_U = [0.11, 0.93, 0.5, 0.27, 0.68, 0.04, 0.81, 0.39, 0.99]
+
+
+def kmpp_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spfresh_b200.sharded import TorchComm
+    data, _ = sharded_inputs()
+    rows = run_sharded_kmpp(TorchComm(), data, [0, 400, 900], 0, 10, 321, KMPP_U)
+    if rank == 0:
+        np.save(os.path.join(os.environ["SPF_TEST_TMP"], "kmpp_rows.npy"), rows)
+    ok[rank] = 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_kmeanspp_over_gloo(tmp_path):
+    """Sharded k-means++: world size 2 over gloo == two in-process shards; one shard == the oracle's
+    k-means++ for the same draws; two shards pick the same rows on this data (only the f32 sum
+    order differs)."""
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import oracle
+    from spfresh_b200.sharded import SingleComm, ThreadComm
+    oracle.build()
+    os.environ["SPF_TEST_TMP"] = str(tmp_path)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(kmpp_worker, args=(2, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+    gloo_rows = np.load(tmp_path / "kmpp_rows.npy")
+    data, _ = sharded_inputs()
+    grp = ThreadComm.Group(2)
+    res = [None, None]
+
+    def run(r):
+        res[r] = run_sharded_kmpp(ThreadComm(grp, r), data, [0, 400, 900], 0, 10, 321, KMPP_U)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert np.array_equal(res[0], gloo_rows) and np.array_equal(res[1], gloo_rows)
+    single = run_sharded_kmpp(SingleComm(), data, [0, 900], 0, 10, 321, KMPP_U)
+    ref, _ = oracle.kmeanspp(data, 0, 10, 321, KMPP_U)
+    assert np.array_equal(single, ref)
+    assert np.array_equal(gloo_rows, ref)
