@@ -103,26 +103,33 @@ __device__ __forceinline__ float dist_comb(float acc, float t) {
 // ---------------------------------------------------------------------------------------------
 // classify
 // ---------------------------------------------------------------------------------------------
-constexpr int CLS_STAGE = 96;         // records a point may keep after the coarse filter
-
-constexpr int CLS_QUEUE = 160;        // pending exact evaluations per warp (flushed 32 at a time)
+constexpr int CLS_STAGE = 256;        // candidate elements a point may keep after the coarse filter
+constexpr int CLS_QUEUE = 96;         // pending exact evaluations per warp (flushed 32 at a time)
 
 struct ClsSmem {
-  float4 t[CLS_STAGE];
-  uint32_t g[CLS_STAGE];
+  uint32_t j[CLS_STAGE];              // centroid slot of a staged element
+  float v[CLS_STAGE];                 // its distance (approximate ones already shifted by |x|^2)
   uint2 q[CLS_QUEUE];
 };
-struct El4 { uint32_t jb; float v[4]; uint32_t exact, valid; };
 
-__global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
+// Warp per point.  Level A walks the point's group records (a lane holds one record of each
+// segment per step) and keeps the ELEMENTS that can matter — in the band of possible minima or
+// with an interval reaching below the loosest possible threshold — compacted into shared memory.
+// Level B then works lane-per-element on the survivors (a dozen or two): band statistics, the
+// threshold interval, the centroid-centroid test, and the short-list entry of every element that
+// is not certainly out.  Records are either all exact (CUDA-core producer) or all approximate
+// (tensor producer), so exactness is a property of the call, not of the element.
+__global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a) {
   __shared__ ClsSmem smem[RS_WARPS];
   ClsSmem& sm = smem[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const float INF = __int_as_float(0x7f800000);
   const uint32_t segcap = (uint32_t)a.cap / (uint32_t)a.nseg;
   const uint32_t slcap = 1u << a.sl_shift;
   const bool approx = a.xnorm != nullptr;
+  const uint32_t ent_flags = approx ? 0u : SE_EXACT;
   const float cnmax = approx ? a.cstat[0] : 0.0f, dcmax = approx ? a.cstat[1] : 0.0f;
 
   struct Rec2 { float4 t0, t1; uint32_t g0, g1; };
@@ -174,107 +181,89 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
   Pre1 nx1 = prefetch1(r + warps_total);
   Rec2 cur_rc = prefetch2(r, cur1);
   for (; r < a.m; r += warps_total) {
-    struct { RowInfo info; Rec2 rc; float xn, xr; } cur;
-    cur.info = cur1.info; cur.xn = cur1.xn; cur.xr = cur1.xr; cur.rc = cur_rc;
+    const RowInfo info = cur1.info;
+    const float xn = cur1.xn, xr = cur1.xr;
+    const Rec2 rc0 = cur_rc;
     cur1 = nx1;
     nx1 = prefetch1(r + 2 * warps_total);
     cur_rc = prefetch2(r + warps_total, cur1);
-    const uint32_t cnt0 = cur.info.x, cnt1 = a.nseg > 1 ? cur.info.z : 0u;
+    const uint32_t cnt0 = info.x, cnt1 = a.nseg > 1 ? info.z : 0u;
     bool overflow = cnt0 > segcap || cnt1 > segcap;   // the dense fallback owns such rows
     const uint32_t steps = overflow ? 0u : (max(cnt0, cnt1) + 31u) >> 5;
     const CandRec* cr = a.rec + (size_t)r * a.cap;
-    const float xn = cur.xn;
-    const float E = approx ? tc_err_bound(xn, cur.xr, cnmax, dcmax, a.ld) : 0.0f;
-    // smallest distance the producer saw: approximate on the tensor path (the true minimum is
-    // within E of it, so only elements within 2E can be the argmin), exact otherwise
-    // tensor path: the info words hold the largest s = x.c - |c|^2/2 per column half, d = |x|^2 - 2 s
-    const float ma = approx ? fmaf(-2.0f, fmaxf(__uint_as_float(cur.info.y), __uint_as_float(cur.info.w)), xn)
-                            : __uint_as_float(cur.info.y);
+    const float E = approx ? tc_err_bound(xn, xr, cnmax, dcmax, a.ld) : 0.0f;
+    // smallest distance the producer saw: approximate on the tensor path (the info words hold the
+    // largest s = x.c - |c|^2/2 per column half, d = |x|^2 - 2 s; the true minimum is within E of
+    // it, so only elements within 2E can be the argmin), exact otherwise
+    const float ma = approx ? fmaf(-2.0f, fmaxf(__uint_as_float(info.y), __uint_as_float(info.w)), xn)
+                            : __uint_as_float(info.y);
     const float band = __fadd_ru(ma, 2.0f * E);
     // loosest possible threshold: thr = fl(dmin * factor) with dmin <= ma + E
     const float thi_loose = a.want_members ? __fmul_ru(__fadd_ru(ma, E), a.factor) : 0.0f;
     // an element matters only if it is in the band or its interval reaches below the threshold
     const float vbound = fmaxf(band, __fadd_ru(thi_loose, E));
 
-    // ---- level A: coarse filter on the group minimum, survivors staged in shared memory ---------
-    uint32_t nrec = 0;
+    // ---- level A: element filter, survivors compacted into shared memory ----------------------
+    uint32_t nel = 0;
     __syncwarp();
     for (uint32_t st = 0; st < steps; ++st) {
       const uint32_t i = st * 32 + lane;
-      const Rec2 rc = st == 0 ? cur.rc : load_recs(cr, i, cnt0, cnt1);
-      // best element of each record (records are either all exact distances or all approximate s
-      // values per producer): smallest distance, i.e. largest s
-      float g0, g1;
-      if (approx) {
-        g0 = fmaf(-2.0f, fmaxf(fmaxf(rc.t0.x, rc.t0.y), fmaxf(rc.t0.z, rc.t0.w)), xn);
-        g1 = fmaf(-2.0f, fmaxf(fmaxf(rc.t1.x, rc.t1.y), fmaxf(rc.t1.z, rc.t1.w)), xn);
-      } else {
-        g0 = fminf(fminf(rc.t0.x, rc.t0.y), fminf(rc.t0.z, rc.t0.w));
-        g1 = fminf(fminf(rc.t1.x, rc.t1.y), fminf(rc.t1.z, rc.t1.w));
+      const Rec2 rc = st == 0 ? rc0 : load_recs(cr, i, cnt0, cnt1);
+      const float tv[8] = {rc.t0.x, rc.t0.y, rc.t0.z, rc.t0.w, rc.t1.x, rc.t1.y, rc.t1.z, rc.t1.w};
+      const uint32_t jb0 = (rc.g0 & REC_G_MASK) << 2, jb1 = (rc.g1 & REC_G_MASK) << 2;
+      float v[8];
+      uint32_t pass = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[q] = approx ? fmaf(-2.0f, tv[q], xn) : tv[q];
+        const bool live = (q < 4 ? i < cnt0 : i < cnt1) && ((q < 4 ? jb0 : jb1) + (uint32_t)(q & 3)) < a.k;
+        pass |= (live && v[q] <= vbound) ? (1u << q) : 0u;      // NaN never passes (never a member)
       }
-      const bool k0 = i < cnt0 && g0 <= vbound;
-      const bool k1 = i < cnt1 && g1 <= vbound;
-      const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
-      const unsigned below = (1u << lane) - 1u;
-      const uint32_t p0 = nrec + (uint32_t)__popc(b0 & below);
-      const uint32_t p1 = nrec + (uint32_t)__popc(b0) + (uint32_t)__popc(b1 & below);
-      if (k0 && p0 < (uint32_t)CLS_STAGE) { sm.t[p0] = rc.t0; sm.g[p0] = rc.g0; }
-      if (k1 && p1 < (uint32_t)CLS_STAGE) { sm.t[p1] = rc.t1; sm.g[p1] = rc.g1; }
-      nrec += (uint32_t)__popc(b0) + (uint32_t)__popc(b1);
+      const uint32_t mine = (uint32_t)__popc(pass);
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      uint32_t pos = nel + incl - mine;
+      nel += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if ((pass >> q) & 1u) {
+          if (pos < (uint32_t)CLS_STAGE) {
+            sm.j[pos] = (q < 4 ? jb0 : jb1) + (uint32_t)(q & 3);
+            sm.v[pos] = v[q];
+          }
+          ++pos;
+        }
+      }
     }
     __syncwarp();
-    if (nrec > (uint32_t)CLS_STAGE) { overflow = true; nrec = 0; }
-    const uint32_t steps2 = (nrec + 31u) >> 5;
+    if (nel > (uint32_t)CLS_STAGE) { overflow = true; nel = 0; }
+    const uint32_t steps2 = (nel + 31u) >> 5;
 
-    // Unpacks a staged record into 4 elements: centroid slot, distance (approximate ones shifted
-    // by |x|^2), exact flag, valid flag.
-    auto unpack = [&](uint32_t i) {
-      El4 e;
-      e.jb = 0; e.exact = 0; e.valid = 0;
-      e.v[0] = e.v[1] = e.v[2] = e.v[3] = 0.f;
-      if (i < nrec) {
-        const float4 t = sm.t[i];
-        const uint32_t g = sm.g[i];
-        e.jb = (g & REC_G_MASK) << 2;
-        e.exact = g >> REC_EXACT_SHIFT;
-        const float tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          e.valid |= (e.jb + (uint32_t)q < a.k) ? (1u << q) : 0u;
-          e.v[q] = ((e.exact >> q) & 1u) ? tv[q] : fmaf(-2.0f, tv[q], xn);
-        }
-      }
-      return e;
-    };
-    auto band_mask = [&](const El4& e) {
-      uint32_t inb = 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) inb |= (((e.valid >> q) & 1u) && e.v[q] <= band) ? (1u << q) : 0u;
-      return inb;
-    };
-
-    // ---- sweep 1: the band: how many elements, are they all exact, which one ----------------------
-    uint32_t n_in = 0, n_apx = 0, j_any = 0;
+    // ---- level B, sweep 1: the band: how many elements, are they all exact, which one ------------
+    uint32_t n_in = 0, j_any = 0;
     float bd = INF;
     uint32_t bj = 0xffffffffu;
-    El4 e0 = unpack((uint32_t)lane);               // step 0 stays in registers for sweep 2
+    // the first 32 staged elements stay in registers for sweep 2
+    const uint32_t j0 = (uint32_t)lane < nel ? sm.j[lane] : 0u;
+    const float v0 = (uint32_t)lane < nel ? sm.v[lane] : INF;
     for (uint32_t st = 0; st < steps2; ++st) {
-      const El4 e = st == 0 ? e0 : unpack(st * 32 + lane);
-      const uint32_t inb = band_mask(e);
-      n_in += (uint32_t)__popc(inb);
-      n_apx += (uint32_t)__popc(inb & ~e.exact);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if ((inb >> q) & 1u) {
-          j_any = e.jb + (uint32_t)q;
-          if (((e.exact >> q) & 1u) && lex_less(e.v[q], e.jb + (uint32_t)q, bd, bj)) { bd = e.v[q]; bj = e.jb + (uint32_t)q; }
-        }
+      const uint32_t e = st * 32 + lane;
+      const bool have = e < nel;
+      const uint32_t j = st == 0 ? j0 : (have ? sm.j[e] : 0u);
+      const float v = st == 0 ? v0 : (have ? sm.v[e] : INF);
+      const bool inb = have && v <= band;
+      n_in += (uint32_t)__popc(__ballot_sync(0xffffffffu, inb));
+      if (inb) {
+        j_any = j;
+        if (!approx && lex_less(v, j, bd, bj)) { bd = v; bj = j; }
       }
     }
-    n_in = __reduce_add_sync(0xffffffffu, n_in);
-    n_apx = __reduce_add_sync(0xffffffffu, n_apx);
     bool best_known, bd_known;
-    if (n_apx == 0) {          // every band element is exact (always so on the exact path)
+    if (!approx) {             // every band element is exact: the best and its distance are known
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float od = __shfl_xor_sync(0xffffffffu, bd, o);
@@ -287,6 +276,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
       bj = __reduce_max_sync(0xffffffffu, j_any);
       best_known = true;
       bd_known = false;
+    } else if (n_in == 0) {    // no finite candidate at all: the fold identity
+      bd = INF; bj = 0;
+      best_known = bd_known = true;
     } else {
       best_known = bd_known = false;
     }
@@ -295,109 +287,54 @@ __global__ void __launch_bounds__(RS_WARPS * 32) classify_kernel(ResolveDev a) {
     const float thi = bd_known ? tlo : thi_loose;
     const float* ccrow = (best_known && a.cc) ? a.cc + (size_t)bj * a.k : nullptr;
 
-    // ---- sweep 2: classification, survivors appended to the short list --------------------------------
+    // ---- level B, sweep 2: classification, survivors appended to the short list --------------------
     ShortEnt* sl = a.sl + ((size_t)r << a.sl_shift);
     uint32_t out = 0;
     for (uint32_t st = 0; st < steps2; ++st) {
-      const El4 e = st == 0 ? e0 : unpack(st * 32 + lane);
-      const uint32_t inb = band_mask(e);
-      uint32_t keep = inb, need_cc = 0, t1c = 0;
-      float ccv[4], lo[4], hi[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const bool ex = (e.exact >> q) & 1u;
-        lo[q] = ex ? e.v[q] : __fadd_rd(e.v[q], -E);
-        hi[q] = ex ? e.v[q] : __fadd_ru(e.v[q], E);
-        ccv[q] = 0.f;
-        if (a.want_members && (((e.valid & ~inb) >> q) & 1u) && lo[q] < thi) {   // else certainly d >= thr
-          need_cc |= 1u << q;
-          if (hi[q] < tlo) t1c |= 1u << q;          // certainly d < thr
-        }
-      }
-      if (ccrow != nullptr) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if ((need_cc >> q) & 1u) ccv[q] = ccrow[e.jb + (uint32_t)q];
-      }
-      uint32_t fl[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const bool ex = (e.exact >> q) & 1u;
-        fl[q] = SE_BAND | (ex ? SE_EXACT : SE_NEED_EVAL);
-        if ((need_cc >> q) & 1u) {
-          if (ccrow != nullptr) {
-            if (ccv[q] >= lo[q]) {                  // otherwise certainly cc < d → not a member
-              keep |= 1u << q;
-              const bool certain = ((t1c >> q) & 1u) && ccv[q] >= hi[q];
-              fl[q] = certain ? (SE_MEMBER | (ex ? SE_EXACT : 0u))
-                              : (SE_TEST_CC | (ex ? SE_EXACT : SE_NEED_EVAL));
-            }
-          } else {                                  // best (or the cc matrix) not available here
-            keep |= 1u << q;
-            fl[q] = SE_TEST_NOCC | (ex ? SE_EXACT : (((t1c >> q) & 1u) ? 0u : SE_NEED_EVAL));
+      const uint32_t e = st * 32 + lane;
+      const bool have = e < nel;
+      const uint32_t j = st == 0 ? j0 : (have ? sm.j[e] : 0u);
+      const float v = st == 0 ? v0 : (have ? sm.v[e] : INF);
+      const bool inb = have && v <= band;
+      const float lo = approx ? __fadd_rd(v, -E) : v, hi = approx ? __fadd_ru(v, E) : v;
+      bool keep = inb;
+      uint32_t fl = SE_BAND | (approx ? SE_NEED_EVAL : SE_EXACT);
+      float ccv = 0.f;
+      if (a.want_members && have && !inb && lo < thi) {      // else certainly d >= thr → not a member
+        const bool t1c = hi < tlo;                            // certainly d < thr
+        if (ccrow != nullptr) {
+          ccv = ccrow[j];
+          if (ccv >= lo) {                                    // otherwise certainly cc < d → not a member
+            keep = true;
+            const bool certain = t1c && ccv >= hi;
+            fl = certain ? (SE_MEMBER | ent_flags) : (SE_TEST_CC | (approx ? SE_NEED_EVAL : SE_EXACT));
           }
+        } else {                                              // best (or the cc matrix) not available here
+          keep = true;
+          fl = SE_TEST_NOCC | (approx ? (t1c ? 0u : SE_NEED_EVAL) : SE_EXACT);
         }
       }
-      // append: exclusive prefix of the per-lane survivor counts
-      const uint32_t mine = (uint32_t)__popc(keep);
-      uint32_t incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
+      // append: lane-per-entry, ballot compaction
+      const unsigned kb = __ballot_sync(0xffffffffu, keep);
+      const uint32_t pos = out + (uint32_t)__popc(kb & below);
+      if (keep && pos < slcap) {
+        ShortEnt w;
+        w.j = j; w.v = v; w.cc = ccv; w.flags = fl;
+        sl[pos] = w;
       }
-      uint32_t pos = out + incl - mine;
-      out += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if ((keep >> q) & 1u) {
-          if (pos < slcap) {
-            ShortEnt w;
-            w.j = e.jb + (uint32_t)q;
-            w.v = e.v[q];
-            w.cc = ccv[q];
-            w.flags = fl[q];
-            sl[pos] = w;
-          }
-          ++pos;
-        }
-      }
-      // queue the entries that need an exact value (warp-aggregated; at most 4 per lane and step)
-      uint32_t nd = 0;
-      {
-        uint32_t p2 = out - __shfl_sync(0xffffffffu, incl, 31) + incl - mine;   // this lane's first position
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if ((keep >> q) & 1u) {
-            if (p2 < slcap && (fl[q] & SE_NEED_EVAL)) nd |= 1u << q;
-            ++p2;
-          }
-        }
-      }
-      if (__any_sync(0xffffffffu, nd != 0)) {
-        const uint32_t nmine = (uint32_t)__popc(nd);
-        uint32_t ni = nmine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t up = __shfl_up_sync(0xffffffffu, ni, o);
-          if (lane >= o) ni += up;
-        }
-        const uint32_t ntot = __shfl_sync(0xffffffffu, ni, 31);
+      // queue the entries that need an exact value: slot (30 bits) + the entry kind (top 2 bits),
+      // so exact_eval can store the final flags
+      const bool need = keep && pos < slcap && (fl & SE_NEED_EVAL);
+      const unsigned nbal = __ballot_sync(0xffffffffu, need);
+      if (nbal) {
+        const uint32_t ntot = (uint32_t)__popc(nbal);
         if (nq + ntot > (uint32_t)CLS_QUEUE) flush_queue(true);
-        uint32_t qp = nq + ni - nmine;
-        uint32_t p2 = out - __shfl_sync(0xffffffffu, incl, 31) + incl - mine;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if ((keep >> q) & 1u) {
-            if ((nd >> q) & 1u)   // slot (30 bits) + the entry kind (top 2 bits), so exact_eval can store the final flags
-              sm.q[qp++] = make_uint2((r << a.sl_shift) + p2, (e.jb + (uint32_t)q) | ((fl[q] & SE_KIND_MASK) << 28));
-            ++p2;
-          }
-        }
+        if (need) sm.q[nq + (uint32_t)__popc(nbal & below)] = make_uint2((r << a.sl_shift) + pos, j | ((fl & SE_KIND_MASK) << 28));
         nq += ntot;
         __syncwarp();
         flush_queue(false);
       }
+      out += (uint32_t)__popc(kb);
     }
     overflow = overflow || out > slcap;
     if (lane == 0) {
@@ -785,7 +722,10 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   // finalize: 4), rows are taken grid-stride
   uint64_t blocks = ceil_div(a.m, RS_WARPS);
   uint64_t blocks_cls = blocks, blocks_fin = blocks;
-  if (blocks_cls > (uint64_t)c->sm_count * 3) blocks_cls = (uint64_t)c->sm_count * 3;
+  int cls_per_sm = 2;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cls_per_sm, classify_kernel, RS_WARPS * 32, 0);
+  if (cls_per_sm < 1) cls_per_sm = 1;
+  if (blocks_cls > (uint64_t)c->sm_count * cls_per_sm) blocks_cls = (uint64_t)c->sm_count * cls_per_sm;
   if (blocks_fin > (uint64_t)c->sm_count * 8) blocks_fin = (uint64_t)c->sm_count * 8;
   {
     KernelTimer t2(c, "classify");
