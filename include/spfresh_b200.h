@@ -253,7 +253,9 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
  * "cand_cap" candidate group records per point (default 128), "short_cap" resolve short-list
  * entries per point (power of two <= 64, default 64), "chunk_rows" points per internal assign
  * chunk (0 = automatic), "work_cap" exact-evaluation work-list entries per chunk (0 = automatic),
- * "scan_list_major" (0 query-major, 1 automatic, 2 list-major), "force_exact", "tc_min_k", "tc_min_m",
+ * "scan_list_major" (0 query-major, 1 automatic, 2 list-major), "scan_tc" (tensor-core candidate
+ * scan: 0 never, 1 automatic, 2 whenever supported), "scan_tc_bucket" (candidates per query, default
+ * 256), "scan_tc_tau_probes" (0 = all), "force_exact", "tc_min_k", "tc_min_m",
  * "kmpp_exact_sum" (1: sequential f32 sum, bit-parity; 0: tree sum), "cc_matrix_max_k". */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 

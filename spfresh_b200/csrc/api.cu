@@ -141,6 +141,11 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "chunk_rows") c->params.chunk_rows = value;
   else if (s == "work_cap") c->params.work_cap = value;
   else if (s == "scan_list_major") c->params.scan_list_major = value;
+  else if (s == "scan_tc") c->params.scan_tc = value;
+  else if (s == "scan_tc_bucket") {
+    if (value < 1 || value > 65536) return fail(SPF_E_INVALID, "scan_tc_bucket must be in [1,65536]");
+    c->params.scan_tc_bucket = value;
+  } else if (s == "scan_tc_tau_probes") c->params.scan_tc_tau_probes = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;

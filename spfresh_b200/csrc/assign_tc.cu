@@ -27,18 +27,14 @@
 //              2 x 256 column accumulator, 32 columns per tcgen05.ld; one point x 128 columns
 //              per thread and tile: running minimum (shared between the two halves through
 //              shared memory) + candidate emission with predicated stores
-#include <cuda.h>
-
-#include "kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace spf {
 
+using namespace tc;
+
 namespace {
 
-constexpr int BM = 128;            // points per CTA tile (TMEM lanes)
-constexpr int BN = 256;            // centroids per accumulator (TMEM columns)
-constexpr int BK = 32;             // floats per K block = 128 bytes = one SWIZZLE_128B row
-constexpr int UMMA_K = 8;          // tf32 MMA K (32 bytes)
 constexpr int KB_MAX = 4;          // stationary A supports ld <= 128
 constexpr int NSTAGE = 4;          // B ring depth
 constexpr int A_KB_BYTES = BM * BK * 4;       // 16 KB
@@ -51,7 +47,6 @@ constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
 // K extension: one extra K = 8 block per tile carries -|c|^2/2 (split into three TF32 terms), so
 // the accumulator holds s = x.c - |c|^2/2 and the epilogue needs neither |c|^2 nor an FMA per
 // element (d = |x|^2 - 2 s).  Rows of 8 floats = 32 bytes, SWIZZLE_32B.
-constexpr int EXT_K = 8;
 constexpr int NEXT = 2;                                      // ring depth of the extension tiles
 constexpr int AEXT_BYTES = BM * EXT_K * 4;                   // 4 KB, constant for the whole kernel
 constexpr int BEXT_BYTES = BN * EXT_K * 4;                   // 8 KB per tile
@@ -60,138 +55,6 @@ constexpr int SMEM_BEXT_OFF = SMEM_AEXT_OFF + AEXT_BYTES;
 constexpr int SMEM_BAR_OFF = SMEM_BEXT_OFF + NEXT * BEXT_BYTES;
 constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [2][128]
 constexpr int SMEM_TOTAL = SMEM_PUB_OFF + 2 * BM * 8 + 1024; // + alignment slack
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-// Same load, delivered to the same shared-memory offsets (data and mbarrier) of every CTA in
-// `mask` of this cluster: the two CTAs of a pair each fetch half of a centroid tile from L2.
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 32 consecutive columns: thread t receives lane (base + t), columns col .. col+31.
-// The load is asynchronous: tc_ld32_wait() must run before the registers are read.  The wait
-// lists the registers as in/out operands so the compiler cannot hoist their uses above it.
-#define SPF_R32(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], \
-                   r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
-__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024
-// bytes apart).  Matches the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);        // start address
-  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-  return d;
-}
-
-// Same for rows of 32 bytes (SWIZZLE_32B, 8-row groups 256 bytes apart): the K-extension tiles.
-__device__ __forceinline__ uint64_t make_smem_desc32(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);        // start address
-  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(256 >> 4) << 32;                 // stride byte offset: 8 rows x 32 B
-  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-  d |= (uint64_t)6 << 61;                          // SWIZZLE_32B
-  return d;
-}
-
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256.
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                ((uint32_t)(BM >> 4) << 24);
 
 struct TcArgs {
   uint32_t m, k, ld, kb;            // kb = ceil(ld / 32) K blocks
@@ -457,23 +320,6 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
-  cuuint64_t gdim[2] = {ld, rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {BK, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(c->tma_encode)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(SPF_E_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
-  return SPF_OK;
-}
-
 }  // namespace
 
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) {
@@ -485,20 +331,10 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
                      float factor, const CandBuf& cand) {
   CUtensorMap map_a, map_b, map_e;
-  SPF_TRY(make_map(c, &map_a, Ptf, m, ld, BM));
-  SPF_TRY(make_map(c, &map_b, Ctf, k, ld, BN / 2));   // each CTA of a pair fetches half a tile
-  {   // K-extension rows: round_up(k, 256) x 8 floats, SWIZZLE_32B
-    const uint64_t kpad = (uint64_t)((k + BN - 1) / BN) * BN;
-    cuuint64_t gdim[2] = {EXT_K, kpad};
-    cuuint64_t gstride[1] = {EXT_K * sizeof(float)};
-    cuuint32_t box[2] = {EXT_K, BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = reinterpret_cast<EncodeTiledFn>(c->tma_encode)(
-        &map_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(cext_pad), gdim, gstride, box, estr,
-        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SPF_E_CUDA, "cuTensorMapEncodeTiled (extension) failed with code %d", (int)r);
-  }
+  SPF_TRY(make_map_k128(c, &map_a, Ptf, m, ld, BM));
+  SPF_TRY(make_map_k128(c, &map_b, Ctf, k, ld, BN / 2));   // each CTA of a pair fetches half a tile
+  // K-extension rows: round_up(k, 256) x 8 floats
+  SPF_TRY(make_map_ext(c, &map_e, cext_pad, (uint64_t)((k + BN - 1) / BN) * BN, BN));
   TcArgs a;
   a.m = (uint32_t)m; a.k = k; a.ld = ld; a.kb = (ld + BK - 1) / BK;
   a.ntiles = (k + BN - 1) / BN;

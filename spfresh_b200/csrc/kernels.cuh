@@ -131,6 +131,49 @@ int resolve_chunk(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t r0
 int resolve_finish(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* csr);
 void resolve_free(ResolveState* s);
 
+// ---- search.cu / scan_tc.cu -----------------------------------------------------------------
+// Arguments shared by the posting-list scan kernels (see search.cu).
+struct ScanArgs {
+  const float* vecs; const uint64_t* slot_ids; const uint64_t* grp_off; const uint32_t* lens;
+  uint32_t ld; uint32_t d;
+  const float* Q; const uint32_t* probe; const float* thr; const uint32_t* seqbase;
+  uint32_t nprobe; uint32_t K;
+  uint64_t* out_ids; float* out_dists; uint32_t* out_counts; unsigned long long* out_keys;
+  unsigned long long* out_slots;   // nq x K slot index of each result (vector gather)
+  unsigned long long* bytes;
+  const uint8_t* only;             // query-major kernel: when set, only queries with only[q] != 0 run
+};
+
+// TF32 side structures of an index for the tensor-core candidate scan (scan_tc.cu), made lazily
+// from the slot layout: row-major rounded copies of the slot vectors (row = slot), their
+// K-extension rows {h, m, 0, 0, l, 0, 0, 0} (h + m + l = -|v|^2/2; {-inf, 0, ...} for pad slots)
+// and vstat = {max |v|^2, max |v - v'|}.
+struct ScanTcSide {
+  float* vtf = nullptr;
+  float* vext = nullptr;
+  float* vstat = nullptr;
+  uint64_t nslots = 0;
+  bool ready = false;
+};
+int scan_tc_prepare(spf_ctx* c, const float* vecs, const uint64_t* slot_ids, uint64_t nslots, uint32_t ld,
+                    ScanTcSide* side);
+void scan_tc_release(ScanTcSide* side);
+bool scan_tc_supported(const spf_ctx* c, uint32_t ld, uint64_t nslots, uint32_t K, uint64_t npairs);
+// Tensor-core candidate scan of all (query, probe) pairs: TF32 GEMM of the probing queries of a list
+// against the list's vectors, certified candidate filter, exact re-evaluation and top-k per query.
+// Fills the out_* arrays of `s` for every query with qflag[q] == 0; the flagged ones (no certified
+// bound, or more candidates than the bucket holds) must be re-run by the exact query-major kernel.
+struct ScanTcCall {
+  ScanArgs s;
+  const ScanTcSide* side;
+  const uint32_t* pair_sorted;     // (q * nprobe + p) grouped by probed list
+  const uint32_t* list_off;        // nlists + 1 offsets into pair_sorted
+  uint32_t nlists;
+  uint64_t nq;
+  uint8_t* qflag;                  // nq, out
+};
+int scan_tc_run(spf_ctx* c, const ScanTcCall& call);
+
 // ---- assign_api.cu ------------------------------------------------------------------------
 int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out);   // api.cu: device buffer only
 int dataset_prep_alloc(spf_dataset* ds);

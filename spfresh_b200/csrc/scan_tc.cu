@@ -1,0 +1,717 @@
+// scan_tc.cu — tcgen05 / TMEM / TMA candidate scan of the posting lists (sm_100a).
+//
+// Replaces the per-point distance loop of SpannIndex::find_k_nearest_neighbor_spann,
+// src/spann/spann_index.rs:168-181 (reference), for batches large enough that a posting list is
+// probed by many queries.  d(q, v) = |q|^2 - 2 q.v + |v|^2 is a dense contraction between the
+// queries probing a list and the list's vectors: it runs on the 5th-gen tensor cores as one TF32
+// pass (fp32 accumulation in TMEM) whose only job is to SELECT.  With E = tc_err_bound a certified
+// bound on |d_tf32 - d_ref| (kernels.cuh), two passes over the same (list, 128-query) units give
+// the reference's result bit for bit:
+//
+//   phase A  per (query, probe) pair the 16 largest 32-column chunk maxima of s = q'.v' - |v|^2/2.
+//            Chunk maxima belong to distinct vectors, so the K-th largest over a query's pairs,
+//            s_K, certifies that K probed vectors have d_ref <= |q|^2 - 2 s_K + E.
+//   phase B  emits every (query, slot) with d_tf32 - E <= min(thr_q, |q|^2 - 2 s_K + E): a superset
+//            of everything that can be among the K smallest keys that pass `dist <= threshold`
+//            (:176), typically K plus a handful.
+//   refine   evaluates the emitted pairs exactly (the reference's sequential f32 sum, :172), applies
+//            `dist <= threshold` and keeps the K smallest (distance, encounter index) keys — the
+//            stable sort + truncate of :188-193.
+//
+// Queries without a certified bound (non-finite norms) or with more candidates than their bucket
+// holds are flagged and re-run by the exact query-major kernel (search.cu), so the tensor path never
+// decides a comparison on an approximate value.
+//
+// Kernel anatomy (persistent, one CTA per SM, 320 threads), per unit = (list, <= 128 probing pairs):
+//   warp 0     TMA producer: the unit's 128 gathered query rows (A, stationary for the unit) and a
+//              4-stage ring of 256-slot x 32-float tiles of the list (B), SWIZZLE_128B, K-major,
+//              plus the K-extension rows that carry -|v|^2/2
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=8 per MMA)
+//   warps 2-9  epilogue: warp w reads TMEM lane quarter w%4 and column half (w-2)/4 of the
+//              double-buffered 2 x 256 column accumulator, 32 columns per tcgen05.ld
+#include <cub/cub.cuh>
+
+#include "tc_ptx.cuh"
+
+namespace spf {
+
+using namespace tc;
+
+namespace {
+
+constexpr int KB_MAX = 4;          // stationary A supports ld <= 128
+constexpr int NSTAGE = 4;          // B ring depth
+constexpr int A_KB_BYTES = BM * BK * 4;       // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 4;    // 32 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_A = KB_MAX * A_KB_BYTES;                  // 64 KB
+constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
+constexpr int NEXT = 2;                                      // ring depth of the extension tiles
+constexpr int AEXT_BYTES = BM * EXT_K * 4;                   // 4 KB, constant for the whole kernel
+constexpr int BEXT_BYTES = BN * EXT_K * 4;                   // 8 KB per tile
+constexpr int SMEM_AEXT_OFF = SMEM_A + SMEM_B;
+constexpr int SMEM_BEXT_OFF = SMEM_AEXT_OFF + AEXT_BYTES;
+constexpr int SMEM_BAR_OFF = SMEM_BEXT_OFF + NEXT * BEXT_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;        // + alignment slack
+
+constexpr int TOPR = 16;           // chunk maxima kept per (pair, column half) in phase A; K <= TOPR
+constexpr int UNIT_ROWS = BM;      // pairs per unit
+constexpr uint32_t NOPAIR = 0xffffffffu;
+
+struct UnitDesc { uint32_t slot0, nslots; };
+
+struct ScanTcArgs {
+  uint32_t nunits, kb, nprobe, cap;
+  const UnitDesc* desc;            // per unit of this launch
+  const float* rowthr;             // per row: threshold on s (phase B), -inf / +inf = enabled / disabled (phase A)
+  const uint32_t* rowseq;          // per row: encounter base of the pair - slot0 (mod 2^32)
+  const uint32_t* rowpair;         // per row: q * nprobe + p, NOPAIR for padding rows
+  float* pairtop;                  // phase A out: (pair, half) x TOPR chunk maxima, descending
+  uint32_t* qcnt; uint2* bucket;   // phase B out: per query candidate count and (slot, encounter index) entries
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_e, ScanTcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + SMEM_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
+  uint64_t* a_full = bars;                 // [KB_MAX]
+  uint64_t* a_empty = bars + KB_MAX;       // [KB_MAX]
+  uint64_t* b_full = bars + 2 * KB_MAX;    // [NSTAGE]
+  uint64_t* b_empty = b_full + NSTAGE;     // [NSTAGE]
+  uint64_t* t_full = b_empty + NSTAGE;     // [2]
+  uint64_t* t_empty = t_full + 2;          // [2]
+  uint64_t* e_full = t_empty + 2;          // [NEXT]
+  uint64_t* e_empty = e_full + NEXT;       // [NEXT]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(e_empty + NEXT);
+  unsigned char* smem_aext = smem + SMEM_AEXT_OFF;
+  unsigned char* smem_bext = smem + SMEM_BEXT_OFF;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_e) : "memory");
+    for (int i = 0; i < KB_MAX; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NEXT; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // A side of the K extension: every row {1,1,0,0, 1,1,0,0}.  Both 16-byte halves are equal, so the
+  // SWIZZLE_32B permutation leaves the tile unchanged and it can be written directly.
+  for (int i = threadIdx.x; i < BM * 2; i += NUM_THREADS)
+    reinterpret_cast<float4*>(smem_aext)[i] = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes → visible to the MMA
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===========================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0, ecount = 0;
+      for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        const UnitDesc ud = a.desc[u];
+        const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
+        if (ntiles == 0) continue;
+        for (uint32_t kb = 0; kb < a.kb; ++kb) {
+          mbar_wait(&a_empty[kb], (it & 1) ^ 1);          // previous unit's MMAs are done with it
+          mbar_expect_tx(&a_full[kb], A_KB_BYTES);
+          tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(u * UNIT_ROWS));
+        }
+        for (uint32_t t = 0; t < ntiles; ++t, ++ecount) {
+          const int row0 = (int)(ud.slot0 + t * BN);
+          for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);
+            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &b_full[stage], (int)(kb * BK), row0);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          const uint32_t es = ecount % NEXT, eu = ecount / NEXT;
+          mbar_wait(&e_empty[es], (eu & 1) ^ 1);
+          mbar_expect_tx(&e_full[es], BEXT_BYTES);
+          tma_load_2d(smem_bext + es * BEXT_BYTES, &map_e, &e_full[es], 0, row0);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==============================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0, tcount = 0;
+      for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        const UnitDesc ud = a.desc[u];
+        const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
+        if (ntiles == 0) continue;
+        for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
+          const uint32_t buf = tcount & 1, use = tcount >> 1;
+          mbar_wait(&t_empty[buf], (use & 1) ^ 1);        // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            if (t == 0) mbar_wait(&a_full[kb], it & 1);
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + kb * A_KB_BYTES);
+            const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              tc_mma_tf32(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 4), make_smem_desc(b_addr + k * UMMA_K * 4),
+                          IDESC_TF32, (kb | (uint32_t)k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&b_empty[stage]);                     // frees the B stage once these MMAs retire
+            if (t + 1 == ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          {   // K extension: accumulator += -|v|^2/2
+            const uint32_t es = tcount % NEXT, eu = tcount / NEXT;
+            mbar_wait(&e_full[es], eu & 1);
+            tc_fence_after();
+            tc_mma_tf32(tmem_d, make_smem_desc32(smem_u32(smem_aext)),
+                        make_smem_desc32(smem_u32(smem_bext + es * BEXT_BYTES)), IDESC_TF32, 1u);
+            tc_commit(&e_empty[es]);
+          }
+          tc_commit(&t_full[buf]);                        // accumulator complete → epilogue
+        }
+        ++it;
+      }
+    }
+  } else {
+    // =============================== epilogue warps ==========================================
+    const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;      // column half of every accumulator
+    const uint32_t lrow = quarter * 32 + lane;
+    const float INF = __int_as_float(0x7f800000);
+    uint32_t tcount = 0;
+    for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+      const UnitDesc ud = a.desc[u];
+      const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
+      if (ntiles == 0) continue;
+      const size_t row = (size_t)u * UNIT_ROWS + lrow;
+      const float thr_s = a.rowthr[row];
+      const bool enabled = thr_s < INF;
+      const bool warp_enabled = __any_sync(0xffffffffu, enabled);
+      const uint32_t rseq = a.rowseq[row];
+      const uint32_t pair = a.rowpair[row];
+      float top[TOPR];
+#pragma unroll
+      for (int i = 0; i < TOPR; ++i) top[i] = -INF;
+
+      for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
+        const uint32_t buf = tcount & 1, use = tcount >> 1;
+        mbar_wait(&t_full[buf], use & 1);
+        tc_fence_after();
+        if (!warp_enabled) {                              // no live row in this lane quarter
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+          continue;
+        }
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
+        const uint32_t colbase = t * BN + half * (BN / 2);   // first slot of this half tile, relative to slot0
+
+        // One 32-column chunk of s.  Chunks are aligned with the 32-slot groups of the list, so a
+        // chunk lies either inside the list or entirely behind its end (where the tile holds the
+        // next list's vectors).
+        auto process = [&](uint32_t (&rr)[32], int c) {
+          const uint32_t cb = colbase + (uint32_t)c * 32u;
+          if (cb >= ud.nslots || !enabled) return;
+          float q[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            q[g] = fmaxf(fmaxf(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1])),
+                         fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
+          float m = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
+          m = fmaxf(m, -INF);                             // an all-NaN chunk counts as empty
+          if (EMIT) {
+            if (m > thr_s) {
+              const uint32_t qi = pair / a.nprobe;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                if (__uint_as_float(rr[e]) > thr_s) {
+                  const uint32_t slot = ud.slot0 + cb + (uint32_t)e;
+                  const uint32_t pos = atomicAdd(a.qcnt + qi, 1u);
+                  if (pos < a.cap) a.bucket[(size_t)qi * a.cap + pos] = make_uint2(slot, rseq + slot);
+                }
+              }
+            }
+          } else {
+            float v = m;
+#pragma unroll
+            for (int i = 0; i < TOPR; ++i) {
+              const float hi = fmaxf(top[i], v);
+              v = fminf(top[i], v);
+              top[i] = hi;
+            }
+          }
+        };
+
+        // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
+        // c+1 is in flight while chunk c is processed
+        uint32_t ra[32], rbuf[32];
+        tc_ld32_issue(taddr, ra);
+        tc_ld32_wait(ra);
+        tc_ld32_issue(taddr + 32, rbuf);
+        process(ra, 0);
+        tc_ld32_wait(rbuf);
+        tc_ld32_issue(taddr + 64, ra);
+        process(rbuf, 1);
+        tc_ld32_wait(ra);
+        tc_ld32_issue(taddr + 96, rbuf);
+        process(ra, 2);
+        tc_ld32_wait(rbuf);
+        tc_fence_before();                                // this warp's part of the accumulator is read
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);
+        process(rbuf, 3);
+      }
+      if (!EMIT && enabled) {
+        float4* o = reinterpret_cast<float4*>(a.pairtop + ((size_t)pair * 2 + half) * TOPR);
+#pragma unroll
+        for (int i = 0; i < TOPR / 4; ++i) o[i] = make_float4(top[4 * i], top[4 * i + 1], top[4 * i + 2], top[4 * i + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// index side: slot layout → row-major TF32 rows + K-extension rows + norms
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+// One warp per 32-slot group, lane = slot.
+__global__ void slot_prep_kernel(const float* __restrict__ vecs, const uint64_t* __restrict__ slot_ids, uint64_t ngroups,
+                                 uint32_t ld4, float* __restrict__ vtf, float* __restrict__ vext,
+                                 float* __restrict__ vnorm, float* __restrict__ vres) {
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= ngroups) return;
+  const float4* V4 = reinterpret_cast<const float4*>(vecs) + g * ld4 * 32 + lane;
+  const uint64_t slot = g * 32 + lane;
+  float4* o = reinterpret_cast<float4*>(vtf) + slot * ld4;
+  float acc = 0.f, racc = 0.f;
+  for (uint32_t c = 0; c < ld4; ++c) {
+    const float4 v = __ldg(V4 + (size_t)c * 32);
+    const float4 t = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+    o[c] = t;
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    const float ex = v.x - t.x, ey = v.y - t.y, ez = v.z - t.z, ew = v.w - t.w;   // exact (Sterbenz)
+    racc = fmaf(ex, ex, racc); racc = fmaf(ey, ey, racc);
+    racc = fmaf(ez, ez, racc); racc = fmaf(ew, ew, racc);
+  }
+  const bool valid = slot_ids[slot] != ~0ull;
+  vnorm[slot] = valid ? acc : 0.f;
+  vres[slot] = valid ? sqrtf(racc) : 0.f;
+  float h = -__int_as_float(0x7f800000), m = 0.f, l = 0.f;
+  if (valid) {
+    const float v = -0.5f * acc;               // exact (power of two)
+    h = rna_tf32(v);
+    const float r1 = v - h;                    // exact: |r1| <= 2^-11 |v|
+    m = rna_tf32(r1);
+    l = rna_tf32(r1 - m);
+  }
+  float4* e = reinterpret_cast<float4*>(vext + slot * 8);
+  e[0] = make_float4(h, m, 0.f, 0.f);
+  e[1] = make_float4(l, 0.f, 0.f, 0.f);
+}
+
+// out2[0] = max(a), out2[1] = max(b) over n values >= 0; out2 must be zeroed.  Non-negative floats
+// order like their bit patterns, so an integer atomicMax does it.
+__global__ void max2_atomic_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_t n, float* out2) {
+  float va = 0.f, vb = 0.f;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    va = fmaxf(va, a[i]);
+    vb = fmaxf(vb, b[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, o));
+    vb = fmaxf(vb, __shfl_xor_sync(0xffffffffu, vb, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned int*>(out2), __float_as_uint(va));
+    atomicMax(reinterpret_cast<unsigned int*>(out2) + 1, __float_as_uint(vb));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per call: units, gathered query rows, bounds, refinement
+// ---------------------------------------------------------------------------------------------
+// units per list = ceil(pairs probing it / 128), 0 for lists this rank does not hold
+__global__ void tc_unit_counts_kernel(const uint32_t* __restrict__ list_off, const uint64_t* __restrict__ grp_off,
+                                      uint32_t nlists, uint32_t* __restrict__ counts) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > nlists) return;
+  uint32_t n = 0;
+  if (l < nlists && grp_off[l + 1] != grp_off[l]) n = (list_off[l + 1] - list_off[l] + UNIT_ROWS - 1) / UNIT_ROWS;
+  counts[l] = n;
+}
+
+struct GatherArgs {
+  const uint32_t* pair_sorted; const uint32_t* list_off; const uint32_t* unit_off; uint32_t nlists;
+  const uint64_t* grp_off; const uint32_t* lens; const uint32_t* seqbase;
+  uint32_t nprobe, ld4, d;
+  uint32_t u0;                     // first unit of this launch
+  const float* qtf;                // nq x ld rounded queries
+  const float* qthr;               // nq thresholds on s (phase B) or NULL (phase A)
+  uint32_t tau_probes;             // phase A: pairs with p < tau_probes take part
+  int copy_rows;                   // 0: the gathered rows of this chunk are already in place
+  float* A; UnitDesc* desc; float* rowthr; uint32_t* rowseq; uint32_t* rowpair;
+  unsigned long long* bytes;       // algorithmic scan bytes (counted when != NULL)
+};
+
+// One CTA (8 warps) per unit: unit descriptor, the unit's query rows (TF32 copies) gathered into
+// a contiguous 128 x ld tile for TMA, and the per-row scalars of the epilogue.
+__global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
+  const uint32_t u = g.u0 + blockIdx.x;
+  uint32_t lo = 0, hi = g.nlists;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (g.unit_off[mid] <= u) lo = mid; else hi = mid;
+  }
+  const uint32_t l = lo;
+  const uint32_t batch = u - g.unit_off[l];
+  const uint32_t p0 = g.list_off[l] + batch * UNIT_ROWS;
+  const uint32_t nb = min((uint32_t)UNIT_ROWS, g.list_off[l + 1] - p0);
+  const uint32_t slot0 = (uint32_t)(g.grp_off[l] * 32);
+  const float INF = __int_as_float(0x7f800000);
+  if (threadIdx.x == 0) {
+    UnitDesc ud;
+    ud.slot0 = slot0;
+    ud.nslots = (uint32_t)((g.grp_off[l + 1] - g.grp_off[l]) * 32);
+    g.desc[blockIdx.x] = ud;
+    if (g.bytes) atomicAdd(g.bytes, (unsigned long long)nb * g.lens[l] * g.d * 4ull);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t r = warp; r < (uint32_t)UNIT_ROWS; r += 8) {
+    const size_t row = (size_t)blockIdx.x * UNIT_ROWS + r;
+    uint32_t pair = NOPAIR, q = 0;
+    if (r < nb) { pair = g.pair_sorted[p0 + r]; q = pair / g.nprobe; }
+    if (g.copy_rows) {
+      float4* dst = reinterpret_cast<float4*>(g.A) + row * g.ld4;
+      const float4* src = reinterpret_cast<const float4*>(g.qtf) + (size_t)q * g.ld4;
+      for (uint32_t c = lane; c < g.ld4; c += 32) dst[c] = pair != NOPAIR ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (lane == 0) {
+      float th = INF;
+      if (pair != NOPAIR) {
+        if (g.qthr) th = g.qthr[q];
+        else th = (pair - q * g.nprobe) < g.tau_probes ? -INF : INF;
+      }
+      g.rowthr[row] = th;
+      g.rowseq[row] = pair != NOPAIR ? g.seqbase[pair] - slot0 : 0u;
+      g.rowpair[row] = pair;
+    }
+  }
+}
+
+struct TauArgs {
+  uint64_t nq; uint32_t nprobe, tau_probes, K, ld;
+  const uint32_t* probe; const uint64_t* grp_off;
+  const float* pairtop; const float* qnorm; const float* qres; const float* thr; const float* vstat;
+  float* qthr; uint8_t* qflag;
+};
+
+// Sorted insertion of one value into a warp-distributed descending list of 32 floats (lane = rank).
+__device__ __forceinline__ void top_insert_desc(float& val, float v, int lane) {
+  const int pos = __popc(__ballot_sync(0xffffffffu, val >= v));
+  const float up = __shfl_up_sync(0xffffffffu, val, 1);
+  if (lane > pos) val = up;
+  else if (lane == pos) val = v;
+}
+
+// One warp per query: s_K = K-th largest chunk maximum over the query's pairs, then the phase-B
+// threshold on s.  A candidate can matter only if d_ref <= B = min(thr_q, |q|^2 - 2 s_K + E), and
+// d_ref >= d_tf32 - E = |q|^2 - 2 s - E, i.e. only if  s >= (|q|^2 - E - B) / 2.
+__global__ void __launch_bounds__(256) tau_kernel(TauArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= a.nq) return;
+  const float INF = __int_as_float(0x7f800000);
+  float val = -INF, kth = -INF;
+  const uint32_t np = min(a.nprobe, a.tau_probes);
+  for (uint32_t p = 0; p < np; ++p) {
+    const uint32_t pair = (uint32_t)(q * a.nprobe + p);
+    const uint32_t l = a.probe[pair];
+    if (a.grp_off[l + 1] == a.grp_off[l]) continue;       // not held here: no unit ran
+    const float mine = a.pairtop[(size_t)pair * 2 * TOPR + lane];   // lanes 0-15: half 0, 16-31: half 1
+    for (int h = 0; h < 2; ++h) {
+      for (int i = 0; i < TOPR; ++i) {
+        const float v = __shfl_sync(0xffffffffu, mine, h * TOPR + i);
+        if (!(v > kth)) break;                              // each array is descending
+        top_insert_desc(val, v, lane);
+        kth = __shfl_sync(0xffffffffu, val, (int)a.K - 1);
+      }
+    }
+  }
+  if (lane == 0) {
+    const float qn = a.qnorm[q];
+    const float cnmax = a.vstat[0], dcmax = a.vstat[1];
+    const float E = tc_err_bound(qn, a.qres[q], cnmax, dcmax, a.ld);
+    const bool hopeless = !(E < INF) || !(qn < INF);
+    const float slop = 1e-6f * (qn + cnmax) + 1e-30f;
+    const float by_thr = 0.5f * ((qn - E) - a.thr[q]);    // -inf when pruning is off; NaN thr: below
+    const float by_tau = kth - E;                          // = (|q|^2 - E - (|q|^2 - 2 s_K + E)) / 2
+    float th = fmaxf(by_thr, by_tau) - slop;
+    if (!(a.thr[q] == a.thr[q])) th = INF;                 // NaN threshold: `dist <= thr` never holds
+    a.qthr[q] = hopeless ? INF : th;
+    a.qflag[q] = hopeless ? 1 : 0;
+  }
+}
+
+struct RefineArgs {
+  ScanArgs s; uint64_t nq; uint32_t cap;
+  const uint32_t* qcnt; const uint2* bucket; uint8_t* qflag;
+};
+
+// One warp per query: exact distance of every emitted (query, slot) pair — the reference's
+// sequential f32 sum — then `<= thr` and the K smallest (distance, encounter index) keys.
+__global__ void __launch_bounds__(256) refine_kernel(RefineArgs r) {
+  const ScanArgs& a = r.s;
+  const int lane = threadIdx.x & 31;
+  const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= r.nq) return;
+  const uint32_t n = r.qcnt[q];
+  if (r.qflag[q] || n > r.cap) {                 // the exact query-major kernel owns this query
+    if (lane == 0) r.qflag[q] = 1;
+    return;
+  }
+  const uint32_t ld4 = a.ld / 4;
+  const float4* V4 = reinterpret_cast<const float4*>(a.vecs);
+  const float4* Q4 = reinterpret_cast<const float4*>(a.Q) + q * ld4;
+  const float thr = a.thr[q];
+  unsigned long long key = ~0ull, pay = ~0ull, kth = ~0ull;
+  for (uint32_t b = 0; b < n; b += 32) {
+    const uint32_t i = b + lane;
+    const bool have = i < n;
+    const uint2 ent = have ? r.bucket[q * r.cap + i] : make_uint2(0u, 0u);
+    const float4* base = V4 + ((size_t)(ent.x >> 5) * ld4) * 32 + (ent.x & 31u);
+    float acc = 0.0f;
+    if (have) {
+#pragma unroll 4
+      for (uint32_t c = 0; c < ld4; ++c) {
+        const float4 v = __ldg(base + (size_t)c * 32);
+        const float4 qv = __ldg(Q4 + c);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+      }
+    }
+    const unsigned long long ck = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned long long)ent.y;
+    unsigned bal = __ballot_sync(0xffffffffu, have && acc <= thr && ck < kth);
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const unsigned long long k2 = __shfl_sync(0xffffffffu, ck, src);
+      const unsigned long long p2 = __shfl_sync(0xffffffffu, (unsigned long long)ent.x, src);
+      if (k2 < kth) {
+        const int pos = __popc(__ballot_sync(0xffffffffu, key < k2));
+        const unsigned long long uk = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, pay, 1);
+        if (lane > pos) { key = uk; pay = up; }
+        else if (lane == pos) { key = k2; pay = p2; }
+        kth = __shfl_sync(0xffffffffu, key, (int)a.K - 1);
+      }
+    }
+  }
+  const bool ok = (uint32_t)lane < a.K && key != ~0ull;
+  const uint32_t count = __popc(__ballot_sync(0xffffffffu, ok));
+  if ((uint32_t)lane < a.K) {
+    a.out_ids[q * a.K + lane] = ok ? a.slot_ids[pay] : ~0ull;
+    a.out_dists[q * a.K + lane] = ok ? __uint_as_float((uint32_t)(key >> 32)) : __int_as_float(0x7f800000);
+    a.out_keys[q * a.K + lane] = key;
+    a.out_slots[q * a.K + lane] = ok ? pay : ~0ull;
+  }
+  if (lane == 0) a.out_counts[q] = count;
+}
+
+}  // namespace
+
+bool scan_tc_supported(const spf_ctx* c, uint32_t ld, uint64_t nslots, uint32_t K, uint64_t npairs) {
+  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= (uint32_t)(KB_MAX * BK) && K <= (uint32_t)TOPR &&
+         nslots > 0 && nslots + BN < (1ull << 31) && npairs < (1ull << 32) - 1;
+}
+
+void scan_tc_release(ScanTcSide* side) {
+  if (!side) return;
+  if (side->vtf) cudaFree(side->vtf);
+  if (side->vext) cudaFree(side->vext);
+  if (side->vstat) cudaFree(side->vstat);
+  *side = ScanTcSide();
+}
+
+int scan_tc_prepare(spf_ctx* c, const float* vecs, const uint64_t* slot_ids, uint64_t nslots, uint32_t ld,
+                    ScanTcSide* side) {
+  if (side->ready) return SPF_OK;
+  cudaStream_t st = c->stream;
+  scan_tc_release(side);
+  if (cudaMalloc((void**)&side->vtf, nslots * ld * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&side->vext, nslots * 8 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&side->vstat, 2 * sizeof(float)) != cudaSuccess) {
+    scan_tc_release(side);
+    cudaGetLastError();
+    return fail(SPF_E_OOM, "tensor-scan side structures for %llu slots do not fit", (unsigned long long)nslots);
+  }
+  DevBuf<float> vnorm, vres;
+  SPF_TRY(vnorm.alloc(st, nslots));
+  SPF_TRY(vres.alloc(st, nslots));
+  SPF_CUDA(cudaMemsetAsync(side->vstat, 0, 2 * sizeof(float), st));
+  slot_prep_kernel<<<(unsigned)ceil_div(nslots, 256), 256, 0, st>>>(vecs, slot_ids, nslots / 32, ld / 4, side->vtf,
+                                                                    side->vext, vnorm.p, vres.p);
+  SPF_TRY(check_launch(c, "slot_prep_kernel"));
+  max2_atomic_kernel<<<(unsigned)(c->sm_count * 4), 256, 0, st>>>(vnorm.p, vres.p, nslots, side->vstat);
+  SPF_TRY(check_launch(c, "max2_atomic_kernel"));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  side->nslots = nslots;
+  side->ready = true;
+  return SPF_OK;
+}
+
+int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
+  cudaStream_t st = c->stream;
+  const ScanArgs& s = call.s;
+  const ScanTcSide& side = *call.side;
+  const uint64_t nq = call.nq, npairs = nq * s.nprobe;
+  const uint32_t ld = s.ld, nlists = call.nlists;
+  const uint32_t cap = (uint32_t)(c->params.scan_tc_bucket > 0 ? c->params.scan_tc_bucket : 256);
+  const uint32_t tau_probes = c->params.scan_tc_tau_probes > 0 ? (uint32_t)c->params.scan_tc_tau_probes : s.nprobe;
+
+  // rounded queries + norms
+  DevBuf<float> qtf, qnorm, qres, qthr;
+  SPF_TRY(qtf.alloc(st, (size_t)nq * ld));
+  SPF_TRY(qnorm.alloc(st, nq));
+  SPF_TRY(qres.alloc(st, nq));
+  SPF_TRY(qthr.alloc(st, nq));
+  SPF_TRY(launch_row_prep(c, s.Q, ld, nullptr, nq, qtf.p, qnorm.p, qres.p));
+
+  // units
+  DevBuf<uint32_t> ucnt, uoff;
+  DevBuf<uint8_t> tmp;
+  SPF_TRY(ucnt.alloc(st, (size_t)nlists + 1));
+  SPF_TRY(uoff.alloc(st, (size_t)nlists + 1));
+  tc_unit_counts_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(call.list_off, s.grp_off, nlists, ucnt.p);
+  SPF_TRY(check_launch(c, "tc_unit_counts_kernel"));
+  size_t tmp_bytes = 0;
+  SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
+  SPF_TRY(tmp.alloc(st, tmp_bytes));
+  SPF_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
+  c->launches += 1;
+  uint32_t nunits = 0;
+  SPF_CUDA(cudaMemcpyAsync(&nunits, uoff.p + nlists, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+
+  DevBuf<uint32_t> qcnt;
+  DevBuf<uint2> bucket;
+  SPF_TRY(qcnt.alloc(st, nq));
+  SPF_TRY(bucket.alloc(st, (size_t)nq * cap));
+  SPF_CUDA(cudaMemsetAsync(qcnt.p, 0, nq * sizeof(uint32_t), st));
+  SPF_CUDA(cudaMemsetAsync(call.qflag, 0, nq, st));
+
+  if (nunits > 0) {
+    const uint32_t chunk_units = nunits < 16384u ? nunits : 16384u;     // <= 1 GB of gathered rows
+    const bool single = chunk_units == nunits;
+    DevBuf<float> A, rowthr, pairtop;
+    DevBuf<uint32_t> rowseq, rowpair;
+    DevBuf<UnitDesc> desc;
+    SPF_TRY(A.alloc(st, (size_t)chunk_units * UNIT_ROWS * ld));
+    SPF_TRY(rowthr.alloc(st, (size_t)chunk_units * UNIT_ROWS));
+    SPF_TRY(rowseq.alloc(st, (size_t)chunk_units * UNIT_ROWS));
+    SPF_TRY(rowpair.alloc(st, (size_t)chunk_units * UNIT_ROWS));
+    SPF_TRY(desc.alloc(st, chunk_units));
+    SPF_TRY(pairtop.alloc(st, npairs * 2 * TOPR));
+
+    CUtensorMap map_a, map_b, map_e;
+    SPF_TRY(make_map_k128(c, &map_a, A.p, (uint64_t)chunk_units * UNIT_ROWS, ld, BM));
+    SPF_TRY(make_map_k128(c, &map_b, side.vtf, side.nslots, ld, BN));
+    SPF_TRY(make_map_ext(c, &map_e, side.vext, side.nslots, BN));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+
+    GatherArgs g;
+    g.pair_sorted = call.pair_sorted; g.list_off = call.list_off; g.unit_off = uoff.p; g.nlists = nlists;
+    g.grp_off = s.grp_off; g.lens = s.lens; g.seqbase = s.seqbase;
+    g.nprobe = s.nprobe; g.ld4 = ld / 4; g.d = s.d;
+    g.qtf = qtf.p; g.tau_probes = tau_probes;
+    g.A = A.p; g.desc = desc.p; g.rowthr = rowthr.p; g.rowseq = rowseq.p; g.rowpair = rowpair.p;
+
+    ScanTcArgs k;
+    k.kb = (ld + BK - 1) / BK; k.nprobe = s.nprobe; k.cap = cap;
+    k.desc = desc.p; k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
+    k.pairtop = pairtop.p; k.qcnt = qcnt.p; k.bucket = bucket.p;
+
+    {
+      KernelTimer t(c, "scan_tc_a");
+      for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
+        const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
+        g.u0 = u0; g.qthr = nullptr; g.copy_rows = 1; g.bytes = s.bytes;
+        unit_gather_kernel<<<nu, 256, 0, st>>>(g);
+        SPF_TRY(check_launch(c, "unit_gather_kernel"));
+        k.nunits = nu;
+        const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
+        scan_tc_kernel<false><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        SPF_TRY(check_launch(c, "scan_tc_kernel<A>"));
+      }
+    }
+    {
+      KernelTimer t(c, "scan_tc_tau");
+      TauArgs ta;
+      ta.nq = nq; ta.nprobe = s.nprobe; ta.tau_probes = tau_probes; ta.K = s.K; ta.ld = ld;
+      ta.probe = s.probe; ta.grp_off = s.grp_off; ta.pairtop = pairtop.p; ta.qnorm = qnorm.p; ta.qres = qres.p;
+      ta.thr = s.thr; ta.vstat = side.vstat; ta.qthr = qthr.p; ta.qflag = call.qflag;
+      tau_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(ta);
+      SPF_TRY(check_launch(c, "tau_kernel"));
+    }
+    {
+      KernelTimer t(c, "scan_tc_b");
+      for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
+        const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
+        g.u0 = u0; g.qthr = qthr.p; g.copy_rows = single ? 0 : 1; g.bytes = nullptr;
+        unit_gather_kernel<<<nu, 256, 0, st>>>(g);
+        SPF_TRY(check_launch(c, "unit_gather_kernel"));
+        k.nunits = nu;
+        const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
+        scan_tc_kernel<true><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        SPF_TRY(check_launch(c, "scan_tc_kernel<B>"));
+      }
+    }
+  }
+  {
+    KernelTimer t(c, "scan_tc_refine");
+    RefineArgs r;
+    r.s = s; r.nq = nq; r.cap = cap; r.qcnt = qcnt.p; r.bucket = bucket.p; r.qflag = call.qflag;
+    refine_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(r);
+    SPF_TRY(check_launch(c, "refine_kernel"));
+  }
+  return SPF_OK;
+}
+
+}  // namespace spf

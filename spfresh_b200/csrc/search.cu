@@ -37,6 +37,7 @@ struct spf_index {
   std::vector<uint32_t> h_lens;
   uint64_t total_groups = 0, total_vectors = 0;
   uint64_t last_scan_bytes = 0;
+  spf::ScanTcSide tc;            // TF32 side structures of the tensor-core scan, made on first use
 };
 
 namespace spf {
@@ -186,15 +187,6 @@ __device__ __forceinline__ unsigned long long topk_kth(const unsigned long long 
   return v;
 }
 
-struct ScanArgs {
-  const float* vecs; const uint64_t* slot_ids; const uint64_t* grp_off; const uint32_t* lens;
-  uint32_t ld; uint32_t d;
-  const float* Q; const uint32_t* probe; const float* thr; const uint32_t* seqbase;
-  uint32_t nprobe; uint32_t K;
-  uint64_t* out_ids; float* out_dists; uint32_t* out_counts; unsigned long long* out_keys;
-  unsigned long long* out_slots;   // nq x K slot index of each result (vector gather)
-  unsigned long long* bytes;
-};
 
 constexpr int SCAN_WARPS = 8;
 
@@ -212,6 +204,7 @@ scan_kernel(ScanArgs a) {
   unsigned long long* s_pay = s_keys + SCAN_WARPS * a.K;
 
   const uint64_t q = blockIdx.x;
+  if (a.only != nullptr && a.only[q] == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ld4 = a.ld / 4;
   const uint32_t* probe = a.probe + q * a.nprobe;
@@ -843,6 +836,7 @@ void spf_index_free(spf_index* idx) {
   if (idx->slot_ids) cudaFree(idx->slot_ids);
   if (idx->grp_off) cudaFree(idx->grp_off);
   if (idx->lens) cudaFree(idx->lens);
+  spf::scan_tc_release(&idx->tc);
   delete idx;
 }
 
@@ -914,22 +908,25 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   a.ld = ld; a.d = d; a.Q = Q.p; a.probe = probe.p; a.thr = thr.p; a.seqbase = seqbase.p;
   a.nprobe = nprobe; a.K = k;
   a.out_ids = o_ids.p; a.out_dists = o_dists.p; a.out_counts = o_counts.p; a.out_keys = o_keys.p;
-  a.out_slots = o_slots.p; a.bytes = d_bytes.p;
-  // list-major scan when the batch is large enough for lists to be shared between queries
+  a.out_slots = o_slots.p; a.bytes = d_bytes.p; a.only = nullptr;
+  // list-major scan when the batch is large enough for lists to be shared between queries; with
+  // tens of probing queries per list the TF32 candidate scan (scan_tc.cu) takes over
   const uint64_t npairs = nq * nprobe;
-  const bool list_major = k <= 32 && npairs < (1ull << 32) && c->params.scan_list_major != 0 &&
+  const uint32_t nloc = idx->list_end - idx->list_begin;
+  const bool use_tc = c->params.scan_tc != 0 && scan_tc_supported(c, ld, idx->total_groups * 32, k, npairs) &&
+                      (c->params.scan_tc == 2 || npairs >= 16ull * (nloc ? nloc : 1));
+  const bool list_major = !use_tc && k <= 32 && npairs < (1ull << 32) && c->params.scan_list_major != 0 &&
                           (c->params.scan_list_major == 2 || npairs >= 2ull * nlists);
   DevBuf<uint32_t> pk, pv, pk2, pv2, loff;
   DevBuf<unsigned long long> ukeys, uslots;
-  DevBuf<uint8_t> stmp;
-  if (list_major) {
-    KernelTimer t(c, "scan");
+  DevBuf<uint8_t> stmp, qflag;
+  if (use_tc) SPF_TRY(scan_tc_prepare(c, idx->vecs, idx->slot_ids, idx->total_groups * 32, ld, &idx->tc));
+  if (list_major || use_tc) {
+    // invert the probe table: (q * nprobe + p) grouped by probed list
     SPF_TRY(pv.alloc(st, npairs));
     SPF_TRY(pk2.alloc(st, npairs));
     SPF_TRY(pv2.alloc(st, npairs));
     SPF_TRY(loff.alloc(st, (size_t)nlists + 1));
-    SPF_TRY(ukeys.alloc(st, npairs * k));
-    SPF_TRY(uslots.alloc(st, npairs * k));
     iota_u32_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(pv.p, npairs);
     SPF_TRY(check_launch(c, "iota_u32_kernel"));
     int end_bit = 1;
@@ -941,6 +938,23 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     c->launches += 3;
     list_offsets_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(pk2.p, npairs, nlists, loff.p);
     SPF_TRY(check_launch(c, "list_offsets_kernel"));
+  }
+  if (use_tc) {
+    KernelTimer t(c, "scan");
+    SPF_TRY(qflag.alloc(st, nq));
+    ScanTcCall tc;
+    tc.s = a; tc.side = &idx->tc; tc.pair_sorted = pv2.p; tc.list_off = loff.p; tc.nlists = nlists; tc.nq = nq;
+    tc.qflag = qflag.p;
+    SPF_TRY(scan_tc_run(c, tc));
+    // flagged queries (no certified bound / bucket overflow): exact query-major scan
+    KernelTimer t2(c, "scan_tc_fallback");
+    ScanArgs fa = a;
+    fa.only = qflag.p;
+    SPF_TRY(launch_scan<1>(c, fa, nq));
+  } else if (list_major) {
+    KernelTimer t(c, "scan");
+    SPF_TRY(ukeys.alloc(st, npairs * k));
+    SPF_TRY(uslots.alloc(st, npairs * k));
     // units: batches of LS_QB queries per list; CTA -> unit through the scanned unit counts
     DevBuf<uint32_t> ucnt, uoff;
     SPF_TRY(ucnt.alloc(st, (size_t)nlists + 1));
@@ -958,7 +972,6 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     la.unit_keys = ukeys.p; la.unit_slots = uslots.p;
     const uint64_t max_units = npairs / LS_QB + nlists + 1;   // upper bound; surplus units exit at once
     // short lists (a few 32-vector groups each): one warp per unit; long lists: one CTA per unit
-    const uint32_t nloc = idx->list_end - idx->list_begin;
     const bool warp_units = nloc > 0 && idx->total_groups / nloc < 24;
     if (warp_units) {
       const size_t smem = (size_t)LS_WARPS * LS_QB * ld * sizeof(float);

@@ -569,6 +569,105 @@ def test_search_list_major_equals_query_major(spf, oracle):
         c2.close()
 
 
+@pytest.mark.parametrize("n,d,nlists,topk,nprobe,kind", [
+    (6000, 16, 12, 10, 4, "clustered"), (20000, 128, 40, 10, 8, "clustered"), (8000, 33, 20, 5, 20, "gauss"),
+    (12000, 96, 30, 16, 6, "gauss"), (5000, 8, 10, 1, 3, "gauss"), (30000, 64, 150, 10, 32, "clustered"),
+    (3000, 100, 7, 3, 0, "gauss"),
+])
+def test_search_tensor_scan_matches_oracle(spf, oracle, n, d, nlists, topk, nprobe, kind):
+    """scan_tc.cu: the TF32 candidate scan + exact refinement is the same function as the exact
+    scans — identical ids, distance bits, counts and merge keys — and matches the oracle."""
+    c2 = spf.Context(0)
+    try:
+        data = clustered(n, d, 20, n + d) if kind == "clustered" else gauss(n, d, n + d)
+        cent, off, mem = build_lists(oracle, data, nlists, d)
+        ds = spf.Dataset(c2, data)
+        idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+        q = (clustered(700, d, 20, n + d) if kind == "clustered" else gauss(700, d, 5)).copy()
+        q[0] = data[cent[3]]                          # exact hit on a centroid: thr = 1.2 * eps
+        q[1] = 100.0                                  # far away
+        q[2] = data[int(mem[0])]                      # exact hit on a member
+        for pf in (1.2, float("inf")):
+            out = {}
+            for mode in (0, 2):
+                c2.set_param("scan_tc", mode)
+                c2.set_profiling(True)
+                out[mode] = idx.search(q, topk, nprobe, prune_factor=pf, want_keys=True)
+                assert (c2.kernel_ms("scan_tc_b") > 0) == (mode == 2)
+                c2.set_profiling(False)
+            for x, y in zip(out[0], out[2]):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+            rid, rd, rc = oracle.search_batch(data, off, mem, cent, q[:150], topk, nprobe, prune_factor=pf)
+            assert np.array_equal(out[2][2][:150], rc)
+            for i in range(150):
+                assert np.array_equal(out[2][0][i, :rc[i]], rid[i, :rc[i]]), i
+                assert np.array_equal(out[2][1][i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32)), i
+        idx.free()
+        ds.free()
+    finally:
+        c2.close()
+
+
+def test_search_tensor_scan_fallbacks(spf, oracle):
+    """Bucket overflow, a bound pass over a subset of the probes, non-finite queries and huge norms
+    all end in the exact result (flagged queries re-run on the exact query-major kernel)."""
+    c2 = spf.Context(0)
+    try:
+        data = gauss(9000, 48, 77)
+        data[17] *= 3.0e4                             # large norm: loose bound for everybody
+        cent, off, mem = build_lists(oracle, data, 16, 5)
+        ds = spf.Dataset(c2, data)
+        idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+        q = gauss(400, 48, 78).copy()
+        q[3, 5] = np.inf
+        q[4, 7] = np.nan
+        q[5] = 1.0e18                                 # |q|^2 overflows
+        q[6] = 0.0
+        c2.set_param("scan_tc", 0)
+        want = idx.search(q, 10, 6, want_keys=True)
+        for name, value in (("scan_tc_bucket", 4), ("scan_tc_bucket", 256), ("scan_tc_tau_probes", 1),
+                            ("scan_tc_tau_probes", 3)):
+            c2.set_param("scan_tc", 2)
+            c2.set_param(name, value)
+            got = idx.search(q, 10, 6, want_keys=True)
+            for x, y in zip(want, got):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (name, value)
+        idx.free()
+        ds.free()
+    finally:
+        c2.close()
+
+
+def test_search_tensor_scan_sharded_lists(spf, oracle):
+    """List shards scanned by the tensor path merge to the unsharded exact answer."""
+    c2 = spf.Context(0)
+    try:
+        data = clustered(15000, 32, 25, 9)
+        cent, off, mem = build_lists(oracle, data, 24, 7)
+        ds = spf.Dataset(c2, data)
+        q = clustered(900, 32, 25, 9)
+        c2.set_param("scan_tc", 0)
+        full = spf.DeviceIndex.pack(ds, off, mem, cent)
+        ids, dists, counts = full.search(q, 10, 8)
+        c2.set_param("scan_tc", 2)
+        parts, handles = [], [full]
+        for lb, le in ((0, 5), (5, 17), (17, 24)):
+            part = spf.DeviceIndex.pack(ds, off, mem, cent, list_range=(lb, le))
+            handles.append(part)
+            parts.append(part.search(q, 10, 8, want_keys=True))
+        mids, md, mc = spf.topk_merge(np.stack([p[3] for p in parts]), np.stack([p[0] for p in parts]),
+                                      np.stack([p[1] for p in parts]), np.stack([p[2] for p in parts]))
+        assert np.array_equal(mc, counts)
+        for i in range(q.shape[0]):
+            assert np.array_equal(mids[i, :mc[i]], ids[i, :mc[i]])
+            assert np.array_equal(md[i, :mc[i]], dists[i, :mc[i]])
+        for h in handles:
+            h.free()
+        ds.free()
+    finally:
+        c2.close()
+
+
 def test_search_duplicates_are_kept(spf, ctx, oracle):
     """F7: a boundary-replicated point appears once per probed list it lives in."""
     data = gauss(2000, 8, 12)
