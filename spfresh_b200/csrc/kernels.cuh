@@ -171,6 +171,7 @@ struct ScanTcCall {
   uint32_t nlists;
   uint64_t nq;
   uint8_t* qflag;                  // nq, out
+  bool is_probe = false;           // the centroid probe (names of the timers only)
 };
 int scan_tc_run(spf_ctx* c, const ScanTcCall& call);
 

@@ -56,7 +56,7 @@ constexpr int SMEM_BEXT_OFF = SMEM_AEXT_OFF + AEXT_BYTES;
 constexpr int SMEM_BAR_OFF = SMEM_BEXT_OFF + NEXT * BEXT_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;        // + alignment slack
 
-constexpr int TOPR = 16;           // chunk maxima kept per (pair, column half) in phase A; K <= TOPR
+constexpr int TOPR_MAX = 32;       // chunk maxima kept per (pair, column half) in phase A: 16 or 32, >= K
 constexpr int UNIT_ROWS = BM;      // pairs per unit
 constexpr uint32_t NOPAIR = 0xffffffffu;
 
@@ -68,11 +68,11 @@ struct ScanTcArgs {
   const float* rowthr;             // per row: threshold on s (phase B), -inf / +inf = enabled / disabled (phase A)
   const uint32_t* rowseq;          // per row: encounter base of the pair - slot0 (mod 2^32)
   const uint32_t* rowpair;         // per row: q * nprobe + p, NOPAIR for padding rows
-  float* pairtop;                  // phase A out: (pair, half) x TOPR chunk maxima, descending
+  float* pairtop;                  // phase A out: (pair, half) x TOPR (16 or 32) chunk maxima, descending
   uint32_t* qcnt; uint2* bucket;   // phase B out: per query candidate count and (slot, encounter index) entries
 };
 
-template <bool EMIT>
+template <bool EMIT, int TOPR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_e, ScanTcArgs a) {
@@ -375,11 +375,28 @@ __global__ void tc_unit_counts_kernel(const uint32_t* __restrict__ list_off, con
   counts[l] = n;
 }
 
+// Sort key of a unit: longest list first (stable, so the units of one list stay adjacent and share
+// the list through L2).  Dealing the sorted units round-robin to the persistent CTAs balances them.
+__global__ void tc_unit_keys_kernel(const uint32_t* __restrict__ unit_off, const uint64_t* __restrict__ grp_off,
+                                    uint32_t nlists, uint32_t nunits, uint32_t* __restrict__ keys,
+                                    uint32_t* __restrict__ vals) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nunits) return;
+  uint32_t lo = 0, hi = nlists;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (unit_off[mid] <= u) lo = mid; else hi = mid;
+  }
+  keys[u] = 0xffffffffu - (uint32_t)(grp_off[lo + 1] - grp_off[lo]);
+  vals[u] = u;
+}
+
 struct GatherArgs {
   const uint32_t* pair_sorted; const uint32_t* list_off; const uint32_t* unit_off; uint32_t nlists;
   const uint64_t* grp_off; const uint32_t* lens; const uint32_t* seqbase;
   uint32_t nprobe, ld4, d;
-  uint32_t u0;                     // first unit of this launch
+  uint32_t u0;                     // first unit (rank in `order`) of this launch
+  const uint32_t* order;           // unit ids, longest list first
   const float* qtf;                // nq x ld rounded queries
   const float* qthr;               // nq thresholds on s (phase B) or NULL (phase A)
   uint32_t tau_probes;             // phase A: pairs with p < tau_probes take part
@@ -391,7 +408,7 @@ struct GatherArgs {
 // One CTA (8 warps) per unit: unit descriptor, the unit's query rows (TF32 copies) gathered into
 // a contiguous 128 x ld tile for TMA, and the per-row scalars of the epilogue.
 __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
-  const uint32_t u = g.u0 + blockIdx.x;
+  const uint32_t u = g.order[g.u0 + blockIdx.x];
   uint32_t lo = 0, hi = g.nlists;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
@@ -434,7 +451,7 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
 }
 
 struct TauArgs {
-  uint64_t nq; uint32_t nprobe, tau_probes, K, ld;
+  uint64_t nq; uint32_t nprobe, tau_probes, K, ld, topr;
   const uint32_t* probe; const uint64_t* grp_off;
   const float* pairtop; const float* qnorm; const float* qres; const float* thr; const float* vstat;
   float* qthr; uint8_t* qflag;
@@ -462,13 +479,16 @@ __global__ void __launch_bounds__(256) tau_kernel(TauArgs a) {
     const uint32_t pair = (uint32_t)(q * a.nprobe + p);
     const uint32_t l = a.probe[pair];
     if (a.grp_off[l + 1] == a.grp_off[l]) continue;       // not held here: no unit ran
-    const float mine = a.pairtop[(size_t)pair * 2 * TOPR + lane];   // lanes 0-15: half 0, 16-31: half 1
-    for (int h = 0; h < 2; ++h) {
-      for (int i = 0; i < TOPR; ++i) {
-        const float v = __shfl_sync(0xffffffffu, mine, h * TOPR + i);
-        if (!(v > kth)) break;                              // each array is descending
-        top_insert_desc(val, v, lane);
-        kth = __shfl_sync(0xffffffffu, val, (int)a.K - 1);
+    // the pair's two arrays (column halves) of topr descending values, 32 values per load
+    for (uint32_t base = 0; base < 2 * a.topr; base += 32) {
+      const float mine = a.pairtop[(size_t)pair * 2 * a.topr + base + lane];
+      for (uint32_t a0 = 0; a0 < 32; a0 += a.topr) {       // the arrays inside this load (topr = 16: two)
+        for (uint32_t j = 0; j < a.topr && j < 32; ++j) {
+          const float v = __shfl_sync(0xffffffffu, mine, (int)(a0 + j));
+          if (!(v > kth)) break;                            // each array is descending
+          top_insert_desc(val, v, lane);
+          kth = __shfl_sync(0xffffffffu, val, (int)a.K - 1);
+        }
       }
     }
   }
@@ -490,6 +510,7 @@ __global__ void __launch_bounds__(256) tau_kernel(TauArgs a) {
 struct RefineArgs {
   ScanArgs s; uint64_t nq; uint32_t cap;
   const uint32_t* qcnt; const uint2* bucket; uint8_t* qflag;
+  unsigned long long* stats;       // [0] candidates emitted, [1] queries handed to the exact fallback
 };
 
 // One warp per query: exact distance of every emitted (query, slot) pair — the reference's
@@ -500,8 +521,9 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineArgs r) {
   const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= r.nq) return;
   const uint32_t n = r.qcnt[q];
+  if (lane == 0) atomicAdd(r.stats, (unsigned long long)n);
   if (r.qflag[q] || n > r.cap) {                 // the exact query-major kernel owns this query
-    if (lane == 0) r.qflag[q] = 1;
+    if (lane == 0) { r.qflag[q] = 1; atomicAdd(r.stats + 1, 1ull); }
     return;
   }
   const uint32_t ld4 = a.ld / 4;
@@ -557,7 +579,7 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineArgs r) {
 }  // namespace
 
 bool scan_tc_supported(const spf_ctx* c, uint32_t ld, uint64_t nslots, uint32_t K, uint64_t npairs) {
-  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= (uint32_t)(KB_MAX * BK) && K <= (uint32_t)TOPR &&
+  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= (uint32_t)(KB_MAX * BK) && K <= (uint32_t)TOPR_MAX &&
          nslots > 0 && nslots + BN < (1ull << 31) && npairs < (1ull << 32) - 1;
 }
 
@@ -604,6 +626,13 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   const uint32_t ld = s.ld, nlists = call.nlists;
   const uint32_t cap = (uint32_t)(c->params.scan_tc_bucket > 0 ? c->params.scan_tc_bucket : 256);
   const uint32_t tau_probes = c->params.scan_tc_tau_probes > 0 ? (uint32_t)c->params.scan_tc_tau_probes : s.nprobe;
+  const uint32_t topr = s.K <= 16 ? 16u : 32u;
+  // timer / counter names of this call (the centroid probe runs through the same code)
+  const bool pr = call.is_probe;
+  const char* n_a = pr ? "probe_tc_a" : "scan_tc_a";
+  const char* n_tau = pr ? "probe_tc_tau" : "scan_tc_tau";
+  const char* n_b = pr ? "probe_tc_b" : "scan_tc_b";
+  const char* n_ref = pr ? "probe_tc_refine" : "scan_tc_refine";
 
   // rounded queries + norms
   DevBuf<float> qtf, qnorm, qres, qthr;
@@ -629,8 +658,27 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   SPF_CUDA(cudaMemcpyAsync(&nunits, uoff.p + nlists, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
 
+  DevBuf<uint32_t> ukey, uval, ukey2, order;
+  if (nunits > 0) {
+    SPF_TRY(ukey.alloc(st, nunits));
+    SPF_TRY(uval.alloc(st, nunits));
+    SPF_TRY(ukey2.alloc(st, nunits));
+    SPF_TRY(order.alloc(st, nunits));
+    tc_unit_keys_kernel<<<(unsigned)ceil_div(nunits, 256), 256, 0, st>>>(uoff.p, s.grp_off, nlists, nunits, ukey.p, uval.p);
+    SPF_TRY(check_launch(c, "tc_unit_keys_kernel"));
+    size_t sb = 0;
+    SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sb, ukey.p, ukey2.p, uval.p, order.p, (int)nunits, 0, 32, st));
+    DevBuf<uint8_t> stmp;
+    SPF_TRY(stmp.alloc(st, sb));
+    SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sb, ukey.p, ukey2.p, uval.p, order.p, (int)nunits, 0, 32, st));
+    c->launches += 1;
+  }
+
   DevBuf<uint32_t> qcnt;
   DevBuf<uint2> bucket;
+  DevBuf<unsigned long long> stats;
+  SPF_TRY(stats.alloc(st, 2));
+  SPF_CUDA(cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), st));
   SPF_TRY(qcnt.alloc(st, nq));
   SPF_TRY(bucket.alloc(st, (size_t)nq * cap));
   SPF_CUDA(cudaMemsetAsync(qcnt.p, 0, nq * sizeof(uint32_t), st));
@@ -647,20 +695,21 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_TRY(rowseq.alloc(st, (size_t)chunk_units * UNIT_ROWS));
     SPF_TRY(rowpair.alloc(st, (size_t)chunk_units * UNIT_ROWS));
     SPF_TRY(desc.alloc(st, chunk_units));
-    SPF_TRY(pairtop.alloc(st, npairs * 2 * TOPR));
+    SPF_TRY(pairtop.alloc(st, npairs * 2 * topr));
 
     CUtensorMap map_a, map_b, map_e;
     SPF_TRY(make_map_k128(c, &map_a, A.p, (uint64_t)chunk_units * UNIT_ROWS, ld, BM));
     SPF_TRY(make_map_k128(c, &map_b, side.vtf, side.nslots, ld, BN));
     SPF_TRY(make_map_ext(c, &map_e, side.vext, side.nslots, BN));
-    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
 
     GatherArgs g;
     g.pair_sorted = call.pair_sorted; g.list_off = call.list_off; g.unit_off = uoff.p; g.nlists = nlists;
     g.grp_off = s.grp_off; g.lens = s.lens; g.seqbase = s.seqbase;
     g.nprobe = s.nprobe; g.ld4 = ld / 4; g.d = s.d;
-    g.qtf = qtf.p; g.tau_probes = tau_probes;
+    g.qtf = qtf.p; g.tau_probes = tau_probes; g.order = order.p;
     g.A = A.p; g.desc = desc.p; g.rowthr = rowthr.p; g.rowseq = rowseq.p; g.rowpair = rowpair.p;
 
     ScanTcArgs k;
@@ -669,7 +718,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     k.pairtop = pairtop.p; k.qcnt = qcnt.p; k.bucket = bucket.p;
 
     {
-      KernelTimer t(c, "scan_tc_a");
+      KernelTimer t(c, n_a);
       for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
         const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
         g.u0 = u0; g.qthr = nullptr; g.copy_rows = 1; g.bytes = s.bytes;
@@ -677,21 +726,22 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
         k.nunits = nu;
         const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
-        scan_tc_kernel<false><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        if (topr == 16) scan_tc_kernel<false, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        else scan_tc_kernel<false, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
         SPF_TRY(check_launch(c, "scan_tc_kernel<A>"));
       }
     }
     {
-      KernelTimer t(c, "scan_tc_tau");
+      KernelTimer t(c, n_tau);
       TauArgs ta;
-      ta.nq = nq; ta.nprobe = s.nprobe; ta.tau_probes = tau_probes; ta.K = s.K; ta.ld = ld;
+      ta.nq = nq; ta.nprobe = s.nprobe; ta.tau_probes = tau_probes; ta.K = s.K; ta.ld = ld; ta.topr = topr;
       ta.probe = s.probe; ta.grp_off = s.grp_off; ta.pairtop = pairtop.p; ta.qnorm = qnorm.p; ta.qres = qres.p;
       ta.thr = s.thr; ta.vstat = side.vstat; ta.qthr = qthr.p; ta.qflag = call.qflag;
       tau_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(ta);
       SPF_TRY(check_launch(c, "tau_kernel"));
     }
     {
-      KernelTimer t(c, "scan_tc_b");
+      KernelTimer t(c, n_b);
       for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
         const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
         g.u0 = u0; g.qthr = qthr.p; g.copy_rows = single ? 0 : 1; g.bytes = nullptr;
@@ -699,17 +749,26 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
         k.nunits = nu;
         const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
-        scan_tc_kernel<true><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        scan_tc_kernel<true, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
         SPF_TRY(check_launch(c, "scan_tc_kernel<B>"));
       }
     }
   }
   {
-    KernelTimer t(c, "scan_tc_refine");
+    KernelTimer t(c, n_ref);
     RefineArgs r;
     r.s = s; r.nq = nq; r.cap = cap; r.qcnt = qcnt.p; r.bucket = bucket.p; r.qflag = call.qflag;
+    r.stats = stats.p;
     refine_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(r);
     SPF_TRY(check_launch(c, "refine_kernel"));
+  }
+  if (c->profiling) {   // counters for bench / profiling runs, reported through spf_ctx_kernel_ms
+    unsigned long long h[2] = {0, 0};
+    SPF_CUDA(cudaMemcpyAsync(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+    c->kernel_ms[pr ? "probe_tc_candidates" : "scan_tc_candidates"] = (float)h[0];
+    c->kernel_ms[pr ? "probe_tc_flagged" : "scan_tc_flagged"] = (float)h[1];
+    c->kernel_ms[pr ? "probe_tc_units" : "scan_tc_units"] = (float)nunits;
   }
   return SPF_OK;
 }

@@ -38,6 +38,12 @@ struct spf_index {
   uint64_t total_groups = 0, total_vectors = 0;
   uint64_t last_scan_bytes = 0;
   spf::ScanTcSide tc;            // TF32 side structures of the tensor-core scan, made on first use
+  // the centroids as one posting list (slot layout) for the tensor-core probe, made on first use
+  float* cvecs = nullptr;
+  uint64_t* cids = nullptr;
+  uint64_t* cgrp = nullptr;      // device {0, groups}
+  uint32_t* clens = nullptr;     // device {nlists}
+  spf::ScanTcSide ctc;
 };
 
 namespace spf {
@@ -515,6 +521,39 @@ merge_units_kernel(ListScanArgs la, uint64_t nq) {
   if (lane == 0) a.out_counts[q] = count;
 }
 
+// Row-major rows → one posting list in slot layout (ids = row numbers, pad slots zero / UINT64_MAX).
+__global__ void rows_to_slots_kernel(const float* __restrict__ X, uint32_t ld4, uint32_t nrows, uint32_t nslots,
+                                     float* __restrict__ vecs, uint64_t* __restrict__ slot_ids) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (uint64_t)nslots * ld4) return;
+  const uint32_t pos = (uint32_t)(w / ld4), c = (uint32_t)(w - (uint64_t)pos * ld4);
+  const float4 v = pos < nrows ? __ldg(reinterpret_cast<const float4*>(X) + (size_t)pos * ld4 + c)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+  reinterpret_cast<float4*>(vecs)[((size_t)(pos >> 5) * ld4 + c) * 32 + (pos & 31)] = v;
+  if (c == 0) slot_ids[pos] = pos < nrows ? (uint64_t)pos : ~0ull;
+}
+
+// Probe table from the sorted (distance, list id) keys of the tensor-core probe: the probed lists,
+// the prune threshold (:165) and the encounter-index base of every probe.  A query with fewer than
+// nprobe keys (non-finite distances) raises `redo`: the exact probe kernels own such batches.
+__global__ void probe_from_keys_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                       uint64_t nq, uint32_t nprobe, float prune_factor,
+                                       const uint32_t* __restrict__ lens, uint32_t* __restrict__ probe,
+                                       float* __restrict__ thr, uint32_t* __restrict__ seqbase, int* __restrict__ redo) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  if (counts[q] < nprobe) { *redo = 1; return; }
+  uint32_t seq = 0;
+  for (uint32_t p = 0; p < nprobe; ++p) {
+    const unsigned long long k = keys[q * nprobe + p];
+    const uint32_t j = (uint32_t)(k & 0xffffffffull);
+    probe[q * nprobe + p] = j;
+    seqbase[q * nprobe + p] = seq;
+    seq += lens[j];
+    if (p == 0) thr[q] = __fmul_rn(prune_factor, __fadd_rn(__uint_as_float((uint32_t)(k >> 32)), 1.1920929e-7f));
+  }
+}
+
 __global__ void iota_u32_kernel(uint32_t* p, uint64_t n) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = (uint32_t)t;
@@ -837,6 +876,11 @@ void spf_index_free(spf_index* idx) {
   if (idx->grp_off) cudaFree(idx->grp_off);
   if (idx->lens) cudaFree(idx->lens);
   spf::scan_tc_release(&idx->tc);
+  spf::scan_tc_release(&idx->ctc);
+  if (idx->cvecs) cudaFree(idx->cvecs);
+  if (idx->cids) cudaFree(idx->cids);
+  if (idx->cgrp) cudaFree(idx->cgrp);
+  if (idx->clens) cudaFree(idx->clens);
   delete idx;
 }
 
@@ -878,13 +922,80 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   if (ld != d) SPF_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)nq * ld * sizeof(float), st));
   SPF_CUDA(cudaMemcpy2DAsync(Q.p, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq, cudaMemcpyHostToDevice, st));
 
-  // centroid probe in query chunks (dense nq_chunk x nlists exact distances, then selection)
-  uint64_t chunk = (256ull << 20) / nlists;
-  if (chunk == 0) chunk = 1;
-  if (chunk > nq) chunk = nq;
-  DevBuf<float> Dqc;
-  SPF_TRY(Dqc.alloc(st, (size_t)chunk * nlists));
-  {
+  // centroid probe.  Large batches with nprobe <= 32: the centroids are one posting list that every
+  // query probes, so the tensor-core candidate scan (scan_tc.cu) with K = nprobe yields the sorted
+  // (distance, list id) keys; otherwise, and for batches with non-finite distances, dense exact
+  // distances in query chunks followed by a selection kernel.
+  bool probed = false;
+  const uint32_t cslots = round_up(nlists, 32);
+  if (c->params.scan_tc != 0 && nprobe <= 32 && scan_tc_supported(c, ld, cslots, nprobe, nq) &&
+      (c->params.scan_tc == 2 || (nq >= 2048 && nlists >= 512))) {
+    KernelTimer t(c, "probe");
+    if (!idx->ctc.ready) {
+      const uint64_t hg[2] = {0, cslots / 32};
+      SPF_CUDA(cudaMalloc((void**)&idx->cvecs, (size_t)cslots * ld * sizeof(float)));
+      SPF_CUDA(cudaMalloc((void**)&idx->cids, (size_t)cslots * sizeof(uint64_t)));
+      SPF_CUDA(cudaMalloc((void**)&idx->cgrp, 2 * sizeof(uint64_t)));
+      SPF_CUDA(cudaMalloc((void**)&idx->clens, sizeof(uint32_t)));
+      SPF_CUDA(cudaMemcpyAsync(idx->cgrp, hg, sizeof(hg), cudaMemcpyHostToDevice, st));
+      SPF_CUDA(cudaMemcpyAsync(idx->clens, &nlists, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+      rows_to_slots_kernel<<<(unsigned)ceil_div((uint64_t)cslots * (ld / 4), 256), 256, 0, st>>>(
+          idx->centroids, ld / 4, nlists, cslots, idx->cvecs, idx->cids);
+      SPF_TRY(check_launch(c, "rows_to_slots_kernel"));
+      SPF_CUDA(cudaStreamSynchronize(st));     // hg / nlists are stack variables
+      SPF_TRY(scan_tc_prepare(c, idx->cvecs, idx->cids, cslots, ld, &idx->ctc));
+    }
+    DevBuf<uint32_t> zero, pairs, loff2, p_counts;
+    DevBuf<float> thr_inf, p_dists;
+    DevBuf<uint64_t> p_ids;
+    DevBuf<unsigned long long> p_keys, p_slots, p_bytes;
+    DevBuf<uint8_t> p_flag;
+    DevBuf<int> redo;
+    SPF_TRY(zero.alloc(st, nq));
+    SPF_TRY(pairs.alloc(st, nq));
+    SPF_TRY(loff2.alloc(st, 2));
+    SPF_TRY(thr_inf.alloc(st, nq));
+    SPF_TRY(p_ids.alloc(st, (size_t)nq * nprobe));
+    SPF_TRY(p_dists.alloc(st, (size_t)nq * nprobe));
+    SPF_TRY(p_keys.alloc(st, (size_t)nq * nprobe));
+    SPF_TRY(p_slots.alloc(st, (size_t)nq * nprobe));
+    SPF_TRY(p_counts.alloc(st, nq));
+    SPF_TRY(p_bytes.alloc(st, 1));
+    SPF_TRY(p_flag.alloc(st, nq));
+    SPF_TRY(redo.alloc(st, 1));
+    const uint32_t h_loff[2] = {0u, (uint32_t)nq};
+    SPF_CUDA(cudaMemsetAsync(zero.p, 0, nq * sizeof(uint32_t), st));
+    SPF_CUDA(cudaMemsetAsync(redo.p, 0, sizeof(int), st));
+    SPF_CUDA(cudaMemcpyAsync(loff2.p, h_loff, sizeof(h_loff), cudaMemcpyHostToDevice, st));
+    SPF_TRY(launch_fill_f32(c, thr_inf.p, nq, __builtin_inff()));
+    iota_u32_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(pairs.p, nq);
+    SPF_TRY(check_launch(c, "iota_u32_kernel"));
+    ScanTcCall pc;
+    pc.s.vecs = idx->cvecs; pc.s.slot_ids = idx->cids; pc.s.grp_off = idx->cgrp; pc.s.lens = idx->clens;
+    pc.s.ld = ld; pc.s.d = d; pc.s.Q = Q.p; pc.s.probe = zero.p; pc.s.thr = thr_inf.p; pc.s.seqbase = zero.p;
+    pc.s.nprobe = 1; pc.s.K = nprobe;
+    pc.s.out_ids = p_ids.p; pc.s.out_dists = p_dists.p; pc.s.out_counts = p_counts.p; pc.s.out_keys = p_keys.p;
+    pc.s.out_slots = p_slots.p; pc.s.bytes = p_bytes.p; pc.s.only = nullptr;
+    pc.side = &idx->ctc; pc.pair_sorted = pairs.p; pc.list_off = loff2.p; pc.nlists = 1; pc.nq = nq;
+    pc.qflag = p_flag.p; pc.is_probe = true;
+    SPF_TRY(scan_tc_run(c, pc));
+    ScanArgs fa = pc.s;
+    fa.only = p_flag.p;
+    SPF_TRY(launch_scan<1>(c, fa, nq));
+    probe_from_keys_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(p_keys.p, p_counts.p, nq, nprobe, prune_factor,
+                                                                        idx->lens, probe.p, thr.p, seqbase.p, redo.p);
+    SPF_TRY(check_launch(c, "probe_from_keys_kernel"));
+    int h_redo = 0;
+    SPF_CUDA(cudaMemcpyAsync(&h_redo, redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+    probed = h_redo == 0;
+  }
+  if (!probed) {
+    uint64_t chunk = (256ull << 20) / nlists;
+    if (chunk == 0) chunk = 1;
+    if (chunk > nq) chunk = nq;
+    DevBuf<float> Dqc;
+    SPF_TRY(Dqc.alloc(st, (size_t)chunk * nlists));
     KernelTimer t(c, "probe");
     for (uint64_t q0 = 0; q0 < nq; q0 += chunk) {
       const uint64_t nc = (nq - q0) < chunk ? (nq - q0) : chunk;

@@ -594,6 +594,7 @@ def test_search_tensor_scan_matches_oracle(spf, oracle, n, d, nlists, topk, npro
                 c2.set_profiling(True)
                 out[mode] = idx.search(q, topk, nprobe, prune_factor=pf, want_keys=True)
                 assert (c2.kernel_ms("scan_tc_b") > 0) == (mode == 2)
+                assert (c2.kernel_ms("probe_tc_b") > 0) == (mode == 2)      # tensor-core probe (nprobe <= 32)
                 c2.set_profiling(False)
             for x, y in zip(out[0], out[2]):
                 assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
