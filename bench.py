@@ -44,6 +44,9 @@ N_ROWS, DIM, K_CENT = 1_000_000, 128, 4096
 # dram__bytes_read.sum + dram__bytes_write.sum of assign_tc_kernel for one 1M x 4096 x 128 launch
 # (ncu --set full capture, profiles/): 512 MB rounded rows read once + candidate records written
 TC_DRAM_BYTES_PER_LAUNCH = 3.21e9
+# the same for one bound-pass launch of scan_tc_kernel on the bench's 10k-query batch (None until captured)
+SCAN_TC_DRAM_BYTES_PER_LAUNCH = None
+SCAN_TC_DRAM_SOURCE = None
 NQ, TOPK = 10_000, 10
 METRIC_NAME = "kmeans_assign_pts_per_s"
 WORKLOAD = "assign_points_to_clusters 1M x 128 f32, k=4096, squared-Euclidean, boundary 1.1, iid N(0,1)"
@@ -447,8 +450,19 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
     ctx.set_profiling(True)
     idx.search(q, TOPK)
     scan_ms, probe_ms = ctx.kernel_ms("scan"), ctx.kernel_ms("probe")
+    tc = {n: ctx.kernel_ms("scan_tc_" + n) for n in ("a", "tau", "b", "refine", "fallback", "candidates", "flagged",
+                                                      "units", "stream_mb", "unique_mb")}
     ctx.set_profiling(False)
     bytes_ = idx.last_scan_bytes()
+    # the same batch on the exact CUDA-core scan (what the tensor-core candidate scan replaces): identical results
+    ctx.set_param("scan_tc", 0)
+    ctx.set_profiling(True)
+    ids0, dists0, counts0 = idx.search(q, TOPK)
+    exact_scan_ms, exact_probe_ms = ctx.kernel_ms("scan"), ctx.kernel_ms("probe")
+    ctx.set_profiling(False)
+    ctx.set_param("scan_tc", 1)
+    same = bool(np.array_equal(ids, ids0) and np.array_equal(dists.view(np.uint32), dists0.view(np.uint32))
+                and np.array_equal(counts, counts0))
     # recall@10 against exact brute force on the device (fp32, torch) for the first 1000 queries
     xq = torch.from_numpy(q[:1000]).to(dev)
     x = torch.from_numpy(rows_np).to(dev)
@@ -459,22 +473,38 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
         hit += len(set(gt[i].tolist()) & set(ids[i, :counts[i]].tolist()))
     del x, xq, d2
     gbs = bytes_ / (scan_ms * 1e-3) / 1e9
-    # the list-major scan reuses every loaded vector for 8 queries, so it is bound by the FP32 issue
-    # rate of the exact (un-fused) distance: 3 lane instructions per element-op
-    lane_instr = bytes_ / 4.0 * 3.0
-    fp32_peak = 148 * 128 * 1.965e9
     out = {"metric": "batch_qps_top10", "qps_e2e": NQ / (ms * 1e-3), "nq": NQ, "k": TOPK, "nprobe": TOPK,
            "prune_factor": 1.2, "recall_at_10": hit / (1000.0 * TOPK),
            "mean_results_per_query": float(counts.mean()),
-           "scan": {"bound": "fp32", "achieved": lane_instr / (scan_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12,
-                    "unit": "T lane-instr/s", "frac": lane_instr / (scan_ms * 1e-3) / fp32_peak,
-                    "peak_source": "148 SM x 128 lanes x 1.965 GHz (nominal max clock)",
-                    "algorithmic_gbs": gbs, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
-                    "algorithmic_over_hbm": gbs / hbm_peak,
-                    "note": "query-major algorithmic bytes (sum over queries and probed lists of |L|*d*4); the "
-                            "list-major kernel streams each list once per 8-query batch, so this exceeds the HBM peak",
-                    "bytes_per_launch": int(bytes_), "kernel_ms": scan_ms},
-           "probe_ms": probe_ms, "index_vectors": idx.nvectors}
+           "probe_ms": probe_ms, "scan_ms": scan_ms, "index_vectors": idx.nvectors,
+           "exact_cuda_core_path": {"scan_ms": exact_scan_ms, "probe_ms": exact_probe_ms, "identical_results": same}}
+    if tc["a"] > 0:
+        # tensor-core candidate scan: every pass streams the probed lists' TF32 tiles once per
+        # (list, 128 probing queries) unit — the kernel is bound by HBM
+        stream, unique = tc["stream_mb"] * 1e6, tc["unique_mb"] * 1e6
+        ach = unique / (tc["a"] * 1e-3) / 1e9
+        out["scan"] = {"bound": "hbm", "kernel": "scan_tc_kernel (tcgen05 kind::tf32), bound pass",
+                       "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                       "peak_source": hbm_src, "bytes_per_launch": int(unique), "requested_bytes_per_launch": int(stream),
+                       "traffic": SCAN_TC_DRAM_BYTES_PER_LAUNCH, "traffic_source": SCAN_TC_DRAM_SOURCE,
+                       "kernel_ms": tc["a"],
+                       "passes_ms": {"bound": tc["a"], "tau": tc["tau"], "emit": tc["b"], "refine": tc["refine"],
+                                     "fallback": tc["fallback"]},
+                       "units": int(tc["units"]), "candidates_per_query": tc["candidates"] / NQ,
+                       "queries_on_exact_fallback": int(tc["flagged"]),
+                       "query_major_algorithmic_gbs": gbs, "query_major_algorithmic_over_hbm": gbs / hbm_peak,
+                       "note": "bytes_per_launch = TF32 rows + K-extension rows of every probed list once (algorithmic HBM "
+                               "traffic of a pass); requested = the same per unit (hot lists have several units, served by L2); "
+                               "query_major_algorithmic = sum over queries and probed lists of |L|*d*4 (SURVEY 8d), "
+                               "which the unit-major kernel serves with one read per 128 probing queries"}
+    else:
+        lane_instr = bytes_ / 4.0 * 3.0
+        fp32_peak = 148 * 128 * 1.965e9
+        out["scan"] = {"bound": "fp32", "achieved": lane_instr / (scan_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12,
+                       "unit": "T lane-instr/s", "frac": lane_instr / (scan_ms * 1e-3) / fp32_peak,
+                       "peak_source": "148 SM x 128 lanes x 1.965 GHz (nominal max clock)",
+                       "algorithmic_gbs": gbs, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                       "bytes_per_launch": int(bytes_), "kernel_ms": scan_ms}
     idx.free()
     return out
 

@@ -240,14 +240,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           m = fmaxf(m, -INF);                             // an all-NaN chunk counts as empty
           if (EMIT) {
             if (m > thr_s) {
-              const uint32_t qi = pair / a.nprobe;
+              // which of the 32 columns pass: straight-line mask, then one iteration per hit (only the
+              // column index is needed, so the registers are never indexed dynamically)
+              uint32_t hits = 0;
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                if (__uint_as_float(rr[e]) > thr_s) {
-                  const uint32_t slot = ud.slot0 + cb + (uint32_t)e;
-                  const uint32_t pos = atomicAdd(a.qcnt + qi, 1u);
-                  if (pos < a.cap) a.bucket[(size_t)qi * a.cap + pos] = make_uint2(slot, rseq + slot);
-                }
+              for (int e = 0; e < 32; ++e) hits |= __uint_as_float(rr[e]) > thr_s ? (1u << e) : 0u;
+              const uint32_t qi = pair / a.nprobe;
+              while (hits) {
+                const uint32_t slot = ud.slot0 + cb + (uint32_t)(__ffs(hits) - 1);
+                hits &= hits - 1;
+                const uint32_t pos = atomicAdd(a.qcnt + qi, 1u);
+                if (pos < a.cap) a.bucket[(size_t)qi * a.cap + pos] = make_uint2(slot, rseq + slot);
               }
             }
           } else {
@@ -403,6 +406,7 @@ struct GatherArgs {
   int copy_rows;                   // 0: the gathered rows of this chunk are already in place
   float* A; UnitDesc* desc; float* rowthr; uint32_t* rowseq; uint32_t* rowpair;
   unsigned long long* bytes;       // algorithmic scan bytes (counted when != NULL)
+  unsigned long long* stream_bytes;   // [0] bytes of list tiles one pass requests, [1] the same counting every list once
 };
 
 // One CTA (8 warps) per unit: unit descriptor, the unit's query rows (TF32 copies) gathered into
@@ -425,7 +429,11 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
     ud.slot0 = slot0;
     ud.nslots = (uint32_t)((g.grp_off[l + 1] - g.grp_off[l]) * 32);
     g.desc[blockIdx.x] = ud;
-    if (g.bytes) atomicAdd(g.bytes, (unsigned long long)nb * g.lens[l] * g.d * 4ull);
+    if (g.bytes) {
+      atomicAdd(g.bytes, (unsigned long long)nb * g.lens[l] * g.d * 4ull);
+      atomicAdd(g.stream_bytes, (unsigned long long)ud.nslots * (g.ld4 * 16ull + EXT_K * 4ull));
+      if (batch == 0) atomicAdd(g.stream_bytes + 1, (unsigned long long)ud.nslots * (g.ld4 * 16ull + EXT_K * 4ull));
+    }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t r = warp; r < (uint32_t)UNIT_ROWS; r += 8) {
@@ -677,8 +685,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   DevBuf<uint32_t> qcnt;
   DevBuf<uint2> bucket;
   DevBuf<unsigned long long> stats;
-  SPF_TRY(stats.alloc(st, 2));
-  SPF_CUDA(cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), st));
+  SPF_TRY(stats.alloc(st, 4));
+  SPF_CUDA(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), st));
   SPF_TRY(qcnt.alloc(st, nq));
   SPF_TRY(bucket.alloc(st, (size_t)nq * cap));
   SPF_CUDA(cudaMemsetAsync(qcnt.p, 0, nq * sizeof(uint32_t), st));
@@ -711,6 +719,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     g.nprobe = s.nprobe; g.ld4 = ld / 4; g.d = s.d;
     g.qtf = qtf.p; g.tau_probes = tau_probes; g.order = order.p;
     g.A = A.p; g.desc = desc.p; g.rowthr = rowthr.p; g.rowseq = rowseq.p; g.rowpair = rowpair.p;
+    g.stream_bytes = stats.p + 2;
 
     ScanTcArgs k;
     k.kb = (ld + BK - 1) / BK; k.nprobe = s.nprobe; k.cap = cap;
@@ -763,12 +772,14 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_TRY(check_launch(c, "refine_kernel"));
   }
   if (c->profiling) {   // counters for bench / profiling runs, reported through spf_ctx_kernel_ms
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[4] = {0, 0, 0, 0};
     SPF_CUDA(cudaMemcpyAsync(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     SPF_CUDA(cudaStreamSynchronize(st));
     c->kernel_ms[pr ? "probe_tc_candidates" : "scan_tc_candidates"] = (float)h[0];
     c->kernel_ms[pr ? "probe_tc_flagged" : "scan_tc_flagged"] = (float)h[1];
     c->kernel_ms[pr ? "probe_tc_units" : "scan_tc_units"] = (float)nunits;
+    c->kernel_ms[pr ? "probe_tc_stream_mb" : "scan_tc_stream_mb"] = (float)((double)h[2] / 1e6);
+    c->kernel_ms[pr ? "probe_tc_unique_mb" : "scan_tc_unique_mb"] = (float)((double)h[3] / 1e6);
   }
   return SPF_OK;
 }

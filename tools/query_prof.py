@@ -46,6 +46,9 @@ for i in range(reps):
     if ctx.kernel_ms("scan_tc_b") > 0:
         print("   tensor scan: " + " ".join(f"{n} {ctx.kernel_ms('scan_tc_' + n):.3f}" for n in
                                             ("a", "tau", "b", "refine", "fallback", "candidates", "flagged", "units")), flush=True)
+    if ctx.kernel_ms("probe_tc_b") > 0:
+        print("   tensor probe: " + " ".join(f"{n} {ctx.kernel_ms('probe_tc_' + n):.3f}" for n in
+                                             ("a", "tau", "b", "refine", "candidates", "flagged", "units")), flush=True)
 if tc and len(sys.argv) > 7:          # cross-check against the exact scan
     ctx.set_param("scan_tc", 0)
     i2, d2, c2 = idx.search(q, 10, nprobe)
