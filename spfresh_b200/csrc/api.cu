@@ -146,6 +146,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
     if (value < 1 || value > 65536) return fail(SPF_E_INVALID, "scan_tc_bucket must be in [1,65536]");
     c->params.scan_tc_bucket = value;
   } else if (s == "scan_tc_tau_probes") c->params.scan_tc_tau_probes = value;
+  else if (s == "scan_tc_cmax_mb") c->params.scan_tc_cmax_mb = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;

@@ -60,11 +60,13 @@ constexpr int TOPR_MAX = 32;       // chunk maxima kept per (pair, column half) 
 constexpr int UNIT_ROWS = BM;      // pairs per unit
 constexpr uint32_t NOPAIR = 0xffffffffu;
 
-struct UnitDesc { uint32_t slot0, nslots; };
+struct UnitDesc { uint32_t slot0, nslots, tile0, pad; };   // tile0: first tile of the unit in the chunk-maxima array
 
 struct ScanTcArgs {
   uint32_t nunits, kb, nprobe, cap;
+  uint32_t u0;                     // rank of this launch's first unit (row scalars are kept for all units)
   const UnitDesc* desc;            // per unit of this launch
+  float4* cmax;                    // bound pass out (optional): per (tile, column half, row) its 4 chunk maxima
   const float* rowthr;             // per row: threshold on s (phase B), -inf / +inf = enabled / disabled (phase A)
   const uint32_t* rowseq;          // per row: encounter base of the pair - slot0 (mod 2^32)
   const uint32_t* rowpair;         // per row: q * nprobe + p, NOPAIR for padding rows
@@ -202,7 +204,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const UnitDesc ud = a.desc[u];
       const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
       if (ntiles == 0) continue;
-      const size_t row = (size_t)u * UNIT_ROWS + lrow;
+      const size_t row = (size_t)(a.u0 + u) * UNIT_ROWS + lrow;
       const float thr_s = a.rowthr[row];
       const bool enabled = thr_s < INF;
       const bool warp_enabled = __any_sync(0xffffffffu, enabled);
@@ -228,9 +230,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // One 32-column chunk of s.  Chunks are aligned with the 32-slot groups of the list, so a
         // chunk lies either inside the list or entirely behind its end (where the tile holds the
         // next list's vectors).
-        auto process = [&](uint32_t (&rr)[32], int c) {
+        auto process = [&](uint32_t (&rr)[32], int c) -> float {
           const uint32_t cb = colbase + (uint32_t)c * 32u;
-          if (cb >= ud.nslots || !enabled) return;
+          if (cb >= ud.nslots || !enabled) return -INF;
           float q[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -262,6 +264,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               top[i] = hi;
             }
           }
+          return m;
         };
 
         // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
@@ -270,18 +273,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_ld32_issue(taddr, ra);
         tc_ld32_wait(ra);
         tc_ld32_issue(taddr + 32, rbuf);
-        process(ra, 0);
+        const float m0 = process(ra, 0);
         tc_ld32_wait(rbuf);
         tc_ld32_issue(taddr + 64, ra);
-        process(rbuf, 1);
+        const float m1 = process(rbuf, 1);
         tc_ld32_wait(ra);
         tc_ld32_issue(taddr + 96, rbuf);
-        process(ra, 2);
+        const float m2 = process(ra, 2);
         tc_ld32_wait(rbuf);
         tc_fence_before();                                // this warp's part of the accumulator is read
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[buf]);
-        process(rbuf, 3);
+        const float m3 = process(rbuf, 3);
+        if (!EMIT && a.cmax != nullptr)                   // one coalesced 512-byte store per warp and tile
+          a.cmax[((size_t)(ud.tile0 + t) * 2 + half) * UNIT_ROWS + lrow] = make_float4(m0, m1, m2, m3);
       }
       if (!EMIT && enabled) {
         float4* o = reinterpret_cast<float4*>(a.pairtop + ((size_t)pair * 2 + half) * TOPR);
@@ -400,11 +405,13 @@ struct GatherArgs {
   uint32_t nprobe, ld4, d;
   uint32_t u0;                     // first unit (rank in `order`) of this launch
   const uint32_t* order;           // unit ids, longest list first
+  const uint32_t* tile_off;        // first chunk-maxima tile of every unit rank, or NULL
   const float* qtf;                // nq x ld rounded queries
   const float* qthr;               // nq thresholds on s (phase B) or NULL (phase A)
   uint32_t tau_probes;             // phase A: pairs with p < tau_probes take part
   int copy_rows;                   // 0: the gathered rows of this chunk are already in place
   float* A; UnitDesc* desc; float* rowthr; uint32_t* rowseq; uint32_t* rowpair;
+  uint32_t* unit_slot0;            // per unit rank: first slot of its list
   unsigned long long* bytes;       // algorithmic scan bytes (counted when != NULL)
   unsigned long long* stream_bytes;   // [0] bytes of list tiles one pass requests, [1] the same counting every list once
 };
@@ -428,7 +435,10 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
     UnitDesc ud;
     ud.slot0 = slot0;
     ud.nslots = (uint32_t)((g.grp_off[l + 1] - g.grp_off[l]) * 32);
+    ud.tile0 = g.tile_off ? g.tile_off[g.u0 + blockIdx.x] : 0u;
+    ud.pad = 0;
     g.desc[blockIdx.x] = ud;
+    g.unit_slot0[g.u0 + blockIdx.x] = slot0;
     if (g.bytes) {
       atomicAdd(g.bytes, (unsigned long long)nb * g.lens[l] * g.d * 4ull);
       atomicAdd(g.stream_bytes, (unsigned long long)ud.nslots * (g.ld4 * 16ull + EXT_K * 4ull));
@@ -437,7 +447,8 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t r = warp; r < (uint32_t)UNIT_ROWS; r += 8) {
-    const size_t row = (size_t)blockIdx.x * UNIT_ROWS + r;
+    const size_t row = (size_t)blockIdx.x * UNIT_ROWS + r;        // in the gathered tile buffer of this launch
+    const size_t grow = (size_t)(g.u0 + blockIdx.x) * UNIT_ROWS + r;  // in the per-row scalars (all units)
     uint32_t pair = NOPAIR, q = 0;
     if (r < nb) { pair = g.pair_sorted[p0 + r]; q = pair / g.nprobe; }
     if (g.copy_rows) {
@@ -451,9 +462,9 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
         if (g.qthr) th = g.qthr[q];
         else th = (pair - q * g.nprobe) < g.tau_probes ? -INF : INF;
       }
-      g.rowthr[row] = th;
-      g.rowseq[row] = pair != NOPAIR ? g.seqbase[pair] - slot0 : 0u;
-      g.rowpair[row] = pair;
+      g.rowthr[grow] = th;
+      g.rowseq[grow] = pair != NOPAIR ? g.seqbase[pair] - slot0 : 0u;
+      g.rowpair[grow] = pair;
     }
   }
 }
@@ -462,7 +473,7 @@ struct TauArgs {
   uint64_t nq; uint32_t nprobe, tau_probes, K, ld, topr;
   const uint32_t* probe; const uint64_t* grp_off;
   const float* pairtop; const float* qnorm; const float* qres; const float* thr; const float* vstat;
-  float* qthr; uint8_t* qflag;
+  float* qthr; float* qbound; uint8_t* qflag;
 };
 
 // Sorted insertion of one value into a warp-distributed descending list of 32 floats (lane = rank).
@@ -511,18 +522,133 @@ __global__ void __launch_bounds__(256) tau_kernel(TauArgs a) {
     float th = fmaxf(by_thr, by_tau) - slop;
     if (!(a.thr[q] == a.thr[q])) th = INF;                 // NaN threshold: `dist <= thr` never holds
     a.qthr[q] = hopeless ? INF : th;
+    // exact-side filter of the group refinement: the K-th smallest probed distance is <= this
+    a.qbound[q] = (fmaf(-2.0f, kth, qn) + E) + slop;
     a.qflag[q] = hopeless ? 1 : 0;
+  }
+}
+
+// Tiles of every unit rank (from its sort key = 0xffffffff - groups of the list).
+__global__ void tc_unit_tiles_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t nunits, uint32_t* __restrict__ ntiles) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nunits) return;
+  ntiles[r] = r < nunits ? ((0xffffffffu - keys_sorted[r]) * 32u + BN - 1) / BN : 0u;
+}
+
+struct WorkItem { uint32_t pair, group; };   // group = 32-slot group of the index
+
+struct FlagArgs {
+  const uint32_t* keys_sorted;     // unit ranks: 0xffffffff - groups of the list
+  const uint32_t* tile_off; const float4* cmax;
+  const uint32_t* rowpair; const uint32_t* unit_slot0;  // per row: pair; per unit rank: first slot of its list
+  const float* qthr; uint32_t nprobe;
+  WorkItem* work; uint32_t work_cap; uint32_t* nwork; uint8_t* qflag;
+};
+
+// One CTA per unit rank, thread = (column half, row): walks the unit's chunk maxima and queues
+// every (pair, 32-slot group) whose maximum passes the pair's threshold on s.  Items that do not
+// fit flag their query for the exact fallback.
+__global__ void __launch_bounds__(256) chunk_flag_kernel(FlagArgs f) {
+  // items are staged in shared memory and appended with one global atomic per CTA (a single
+  // global counter bumped once per item serialises in L2)
+  constexpr uint32_t SQ = 2048;
+  __shared__ WorkItem sq[SQ];
+  __shared__ uint32_t sn, sbase;
+  if (threadIdx.x == 0) sn = 0;
+  __syncthreads();
+  const uint32_t r = blockIdx.x;
+  const uint32_t half = threadIdx.x >> 7, lrow = threadIdx.x & 127;
+  const size_t row = (size_t)r * UNIT_ROWS + lrow;
+  const uint32_t pair = f.rowpair[row];
+  if (pair != NOPAIR) {
+    const uint32_t q = pair / f.nprobe;
+    const float th = f.qthr[q];
+    const uint32_t groups = 0xffffffffu - f.keys_sorted[r];
+    const uint32_t ntiles = (groups * 32u + BN - 1) / BN;
+    const uint32_t g0 = f.unit_slot0[r] >> 5;
+    const float4* cm = f.cmax + ((size_t)f.tile_off[r] * 2 + half) * UNIT_ROWS + lrow;
+#pragma unroll 4
+    for (uint32_t t = 0; t < ntiles; ++t) {
+      const float4 m = cm[(size_t)t * 2 * UNIT_ROWS];
+      const float mv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t grp = t * 8 + half * 4 + c;          // chunk = 32-slot group of the list
+        if (grp < groups && mv[c] > th) {
+          WorkItem w;
+          w.pair = pair; w.group = g0 + grp;
+          const uint32_t sp = atomicAdd(&sn, 1u);
+          if (sp < SQ) {
+            sq[sp] = w;
+          } else {                                            // staging full: straight to the global list
+            const uint32_t pos = atomicAdd(f.nwork, 1u);
+            if (pos < f.work_cap) f.work[pos] = w; else f.qflag[q] = 1;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n = min(sn, SQ);
+  if (threadIdx.x == 0 && n) sbase = atomicAdd(f.nwork, n);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t pos = sbase + i;
+    if (pos < f.work_cap) f.work[pos] = sq[i]; else f.qflag[sq[i].pair / f.nprobe] = 1;
+  }
+}
+
+struct GroupArgs {
+  ScanArgs s; const WorkItem* work; const uint32_t* nwork; uint32_t work_cap;
+  const float* qbound; uint32_t cap; uint32_t* qcnt; uint4* ebucket;   // exact entries: key lo, key hi, slot
+};
+
+// One warp per queued (pair, group): the lane's vector against the pair's query, exact (the
+// reference's sequential f32 sum, :172); vectors passing `dist <= threshold` (:176) and the certified
+// bound on the K-th smallest distance go to the query's bucket with their (distance, encounter) key.
+__global__ void __launch_bounds__(256) group_refine_kernel(GroupArgs g) {
+  const ScanArgs& a = g.s;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nw = min(*g.nwork, g.work_cap);
+  const uint32_t ld4 = a.ld / 4;
+  const float4* V4 = reinterpret_cast<const float4*>(a.vecs);
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nw; w += (gridDim.x * blockDim.x) >> 5) {
+    const WorkItem it = g.work[w];
+    const uint32_t q = it.pair / a.nprobe;
+    const float4* Q4 = reinterpret_cast<const float4*>(a.Q) + (size_t)q * ld4;
+    const float4* base = V4 + (size_t)it.group * ld4 * 32 + lane;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (uint32_t c = 0; c < ld4; ++c) {
+      const float4 v = __ldg(base + (size_t)c * 32);
+      const float4 qv = __ldg(Q4 + c);
+      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
+      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
+      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
+      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+    }
+    const uint32_t slot = it.group * 32 + lane;
+    const bool valid = a.slot_ids[slot] != ~0ull;
+    if (valid && acc <= a.thr[q] && acc <= g.qbound[q]) {
+      const uint32_t l = a.probe[it.pair];
+      // encounter index: base of this probe + position in the list
+      const uint32_t seq = a.seqbase[it.pair] + (slot - (uint32_t)(a.grp_off[l] * 32));
+      const uint32_t pos = atomicAdd(g.qcnt + q, 1u);
+      if (pos < g.cap) g.ebucket[(size_t)q * g.cap + pos] = make_uint4(seq, __float_as_uint(acc), slot, 0u);
+    }
   }
 }
 
 struct RefineArgs {
   ScanArgs s; uint64_t nq; uint32_t cap;
   const uint32_t* qcnt; const uint2* bucket; uint8_t* qflag;
+  const uint4* ebucket;            // EXACT: entries already hold the exact key (group refinement)
   unsigned long long* stats;       // [0] candidates emitted, [1] queries handed to the exact fallback
 };
 
 // One warp per query: exact distance of every emitted (query, slot) pair — the reference's
 // sequential f32 sum — then `<= thr` and the K smallest (distance, encounter index) keys.
+template <bool EXACT>
 __global__ void __launch_bounds__(256) refine_kernel(RefineArgs r) {
   const ScanArgs& a = r.s;
   const int lane = threadIdx.x & 31;
@@ -542,18 +668,27 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineArgs r) {
   for (uint32_t b = 0; b < n; b += 32) {
     const uint32_t i = b + lane;
     const bool have = i < n;
-    const uint2 ent = have ? r.bucket[q * r.cap + i] : make_uint2(0u, 0u);
-    const float4* base = V4 + ((size_t)(ent.x >> 5) * ld4) * 32 + (ent.x & 31u);
+    uint2 ent = make_uint2(0u, 0u);               // slot, encounter index
     float acc = 0.0f;
-    if (have) {
+    if (EXACT) {
+      if (have) {
+        const uint4 e = r.ebucket[q * r.cap + i];
+        ent = make_uint2(e.z, e.x);
+        acc = __uint_as_float(e.y);
+      }
+    } else {
+      if (have) ent = r.bucket[q * r.cap + i];
+      const float4* base = V4 + ((size_t)(ent.x >> 5) * ld4) * 32 + (ent.x & 31u);
+      if (have) {
 #pragma unroll 4
-      for (uint32_t c = 0; c < ld4; ++c) {
-        const float4 v = __ldg(base + (size_t)c * 32);
-        const float4 qv = __ldg(Q4 + c);
-        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
-        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
-        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
-        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+        for (uint32_t c = 0; c < ld4; ++c) {
+          const float4 v = __ldg(base + (size_t)c * 32);
+          const float4 qv = __ldg(Q4 + c);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+        }
       }
     }
     const unsigned long long ck = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned long long)ent.y;
@@ -684,6 +819,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
 
   DevBuf<uint32_t> qcnt;
   DevBuf<uint2> bucket;
+  DevBuf<uint4> ebucket;
+  bool exact_entries = false;
   DevBuf<unsigned long long> stats;
   SPF_TRY(stats.alloc(st, 4));
   SPF_CUDA(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), st));
@@ -692,18 +829,45 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   SPF_CUDA(cudaMemsetAsync(qcnt.p, 0, nq * sizeof(uint32_t), st));
   SPF_CUDA(cudaMemsetAsync(call.qflag, 0, nq, st));
 
+  // One GEMM pass or two?  When the chunk maxima of the bound pass fit in the budget they are kept
+  // (4 KB per tile) and the candidates come from an exact re-evaluation of the few 32-slot groups
+  // whose maximum passes ("group refinement"); otherwise — and for the centroid probe, where every
+  // query has nprobe hits in one short list — a second GEMM pass emits the candidates.
+  uint32_t total_tiles = 0;
+  DevBuf<uint32_t> utiles, tile_off;
+  bool keep_cmax = false;
+  if (nunits > 0 && !call.is_probe && c->params.scan_tc_cmax_mb > 0) {
+    SPF_TRY(utiles.alloc(st, (size_t)nunits + 1));
+    SPF_TRY(tile_off.alloc(st, (size_t)nunits + 1));
+    tc_unit_tiles_kernel<<<(unsigned)ceil_div((uint64_t)nunits + 1, 256), 256, 0, st>>>(ukey2.p, nunits, utiles.p);
+    SPF_TRY(check_launch(c, "tc_unit_tiles_kernel"));
+    size_t sb = 0;
+    SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, utiles.p, tile_off.p, (int)(nunits + 1), st));
+    DevBuf<uint8_t> stmp;
+    SPF_TRY(stmp.alloc(st, sb));
+    SPF_CUDA(cub::DeviceScan::ExclusiveSum(stmp.p, sb, utiles.p, tile_off.p, (int)(nunits + 1), st));
+    c->launches += 1;
+    SPF_CUDA(cudaMemcpyAsync(&total_tiles, tile_off.p + nunits, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+    keep_cmax = (uint64_t)total_tiles * 4096ull <= (uint64_t)c->params.scan_tc_cmax_mb << 20;
+  }
+
   if (nunits > 0) {
     const uint32_t chunk_units = nunits < 16384u ? nunits : 16384u;     // <= 1 GB of gathered rows
     const bool single = chunk_units == nunits;
-    DevBuf<float> A, rowthr, pairtop;
-    DevBuf<uint32_t> rowseq, rowpair;
+    DevBuf<float> A, rowthr, pairtop, qbound;
+    DevBuf<uint32_t> rowseq, rowpair, unit_slot0;
     DevBuf<UnitDesc> desc;
+    DevBuf<float4> cmax;
     SPF_TRY(A.alloc(st, (size_t)chunk_units * UNIT_ROWS * ld));
-    SPF_TRY(rowthr.alloc(st, (size_t)chunk_units * UNIT_ROWS));
-    SPF_TRY(rowseq.alloc(st, (size_t)chunk_units * UNIT_ROWS));
-    SPF_TRY(rowpair.alloc(st, (size_t)chunk_units * UNIT_ROWS));
+    SPF_TRY(rowthr.alloc(st, (size_t)nunits * UNIT_ROWS));
+    SPF_TRY(rowseq.alloc(st, (size_t)nunits * UNIT_ROWS));
+    SPF_TRY(rowpair.alloc(st, (size_t)nunits * UNIT_ROWS));
+    SPF_TRY(unit_slot0.alloc(st, nunits));
     SPF_TRY(desc.alloc(st, chunk_units));
     SPF_TRY(pairtop.alloc(st, npairs * 2 * topr));
+    SPF_TRY(qbound.alloc(st, nq));
+    if (keep_cmax) SPF_TRY(cmax.alloc(st, (size_t)total_tiles * 2 * UNIT_ROWS));
 
     CUtensorMap map_a, map_b, map_e;
     SPF_TRY(make_map_k128(c, &map_a, A.p, (uint64_t)chunk_units * UNIT_ROWS, ld, BM));
@@ -717,14 +881,17 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     g.pair_sorted = call.pair_sorted; g.list_off = call.list_off; g.unit_off = uoff.p; g.nlists = nlists;
     g.grp_off = s.grp_off; g.lens = s.lens; g.seqbase = s.seqbase;
     g.nprobe = s.nprobe; g.ld4 = ld / 4; g.d = s.d;
-    g.qtf = qtf.p; g.tau_probes = tau_probes; g.order = order.p;
+    g.qtf = qtf.p; g.tau_probes = keep_cmax ? s.nprobe : tau_probes; g.order = order.p;
+    g.tile_off = keep_cmax ? tile_off.p : nullptr;
     g.A = A.p; g.desc = desc.p; g.rowthr = rowthr.p; g.rowseq = rowseq.p; g.rowpair = rowpair.p;
+    g.unit_slot0 = unit_slot0.p;
     g.stream_bytes = stats.p + 2;
 
     ScanTcArgs k;
     k.kb = (ld + BK - 1) / BK; k.nprobe = s.nprobe; k.cap = cap;
     k.desc = desc.p; k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
     k.pairtop = pairtop.p; k.qcnt = qcnt.p; k.bucket = bucket.p;
+    k.cmax = keep_cmax ? cmax.p : nullptr;
 
     {
       KernelTimer t(c, n_a);
@@ -733,7 +900,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
         g.u0 = u0; g.qthr = nullptr; g.copy_rows = 1; g.bytes = s.bytes;
         unit_gather_kernel<<<nu, 256, 0, st>>>(g);
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
-        k.nunits = nu;
+        k.nunits = nu; k.u0 = u0;
         const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
         if (topr == 16) scan_tc_kernel<false, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
         else scan_tc_kernel<false, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
@@ -743,20 +910,49 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     {
       KernelTimer t(c, n_tau);
       TauArgs ta;
-      ta.nq = nq; ta.nprobe = s.nprobe; ta.tau_probes = tau_probes; ta.K = s.K; ta.ld = ld; ta.topr = topr;
+      ta.nq = nq; ta.nprobe = s.nprobe; ta.tau_probes = g.tau_probes; ta.K = s.K; ta.ld = ld; ta.topr = topr;
       ta.probe = s.probe; ta.grp_off = s.grp_off; ta.pairtop = pairtop.p; ta.qnorm = qnorm.p; ta.qres = qres.p;
-      ta.thr = s.thr; ta.vstat = side.vstat; ta.qthr = qthr.p; ta.qflag = call.qflag;
+      ta.thr = s.thr; ta.vstat = side.vstat; ta.qthr = qthr.p; ta.qbound = qbound.p; ta.qflag = call.qflag;
       tau_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(ta);
       SPF_TRY(check_launch(c, "tau_kernel"));
     }
-    {
+    if (keep_cmax) {
+      // group refinement: queue the (pair, group) items whose chunk maximum passes, evaluate them exactly
+      KernelTimer t(c, n_b);
+      const uint64_t want = nq * 64ull > (1ull << 20) ? nq * 64ull : (1ull << 20);
+      const uint32_t work_cap = (uint32_t)(want < (1ull << 30) ? want : (1ull << 30));
+      DevBuf<WorkItem> work;
+      DevBuf<uint32_t> nwork;
+      SPF_TRY(work.alloc(st, work_cap));
+      SPF_TRY(nwork.alloc(st, 1));
+      SPF_TRY(ebucket.alloc(st, (size_t)nq * cap));
+      SPF_CUDA(cudaMemsetAsync(nwork.p, 0, sizeof(uint32_t), st));
+      FlagArgs f;
+      f.keys_sorted = ukey2.p; f.tile_off = tile_off.p; f.cmax = cmax.p; f.rowpair = rowpair.p;
+      f.unit_slot0 = unit_slot0.p; f.qthr = qthr.p; f.nprobe = s.nprobe;
+      f.work = work.p; f.work_cap = work_cap; f.nwork = nwork.p; f.qflag = call.qflag;
+      chunk_flag_kernel<<<nunits, 256, 0, st>>>(f);
+      SPF_TRY(check_launch(c, "chunk_flag_kernel"));
+      GroupArgs ga;
+      ga.s = s; ga.work = work.p; ga.nwork = nwork.p; ga.work_cap = work_cap; ga.qbound = qbound.p; ga.cap = cap;
+      ga.qcnt = qcnt.p; ga.ebucket = ebucket.p;
+      group_refine_kernel<<<(unsigned)(c->sm_count * 8), 256, 0, st>>>(ga);
+      SPF_TRY(check_launch(c, "group_refine_kernel"));
+      exact_entries = true;
+      if (c->profiling) {
+        uint32_t h = 0;
+        SPF_CUDA(cudaMemcpyAsync(&h, nwork.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        SPF_CUDA(cudaStreamSynchronize(st));
+        c->kernel_ms["scan_tc_groups"] = (float)h;
+      }
+    } else {
       KernelTimer t(c, n_b);
       for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
         const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
         g.u0 = u0; g.qthr = qthr.p; g.copy_rows = single ? 0 : 1; g.bytes = nullptr;
         unit_gather_kernel<<<nu, 256, 0, st>>>(g);
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
-        k.nunits = nu;
+        k.nunits = nu; k.u0 = u0;
         const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
         scan_tc_kernel<true, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
         SPF_TRY(check_launch(c, "scan_tc_kernel<B>"));
@@ -767,8 +963,9 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     KernelTimer t(c, n_ref);
     RefineArgs r;
     r.s = s; r.nq = nq; r.cap = cap; r.qcnt = qcnt.p; r.bucket = bucket.p; r.qflag = call.qflag;
-    r.stats = stats.p;
-    refine_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(r);
+    r.ebucket = ebucket.p; r.stats = stats.p;
+    if (exact_entries) refine_kernel<true><<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(r);
+    else refine_kernel<false><<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(r);
     SPF_TRY(check_launch(c, "refine_kernel"));
   }
   if (c->profiling) {   // counters for bench / profiling runs, reported through spf_ctx_kernel_ms

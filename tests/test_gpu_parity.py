@@ -589,15 +589,20 @@ def test_search_tensor_scan_matches_oracle(spf, oracle, n, d, nlists, topk, npro
         q[2] = data[int(mem[0])]                      # exact hit on a member
         for pf in (1.2, float("inf")):
             out = {}
-            for mode in (0, 2):
+            # exact scans / one GEMM pass + group refinement / two GEMM passes
+            for mode, cmax_mb in ((0, 0), (2, 16384), (2, 0)):
                 c2.set_param("scan_tc", mode)
+                c2.set_param("scan_tc_cmax_mb", cmax_mb)
                 c2.set_profiling(True)
-                out[mode] = idx.search(q, topk, nprobe, prune_factor=pf, want_keys=True)
+                out[(mode, cmax_mb)] = idx.search(q, topk, nprobe, prune_factor=pf, want_keys=True)
                 assert (c2.kernel_ms("scan_tc_b") > 0) == (mode == 2)
                 assert (c2.kernel_ms("probe_tc_b") > 0) == (mode == 2)      # tensor-core probe (nprobe <= 32)
+                assert (c2.kernel_ms("scan_tc_groups") > 0) == (mode == 2 and cmax_mb > 0)
                 c2.set_profiling(False)
-            for x, y in zip(out[0], out[2]):
-                assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+            for key in ((2, 16384), (2, 0)):
+                for x, y in zip(out[(0, 0)], out[key]):
+                    assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), key
+            out[2] = out[(2, 16384)]
             rid, rd, rc = oracle.search_batch(data, off, mem, cent, q[:150], topk, nprobe, prune_factor=pf)
             assert np.array_equal(out[2][2][:150], rc)
             for i in range(150):
@@ -626,13 +631,15 @@ def test_search_tensor_scan_fallbacks(spf, oracle):
         q[6] = 0.0
         c2.set_param("scan_tc", 0)
         want = idx.search(q, 10, 6, want_keys=True)
-        for name, value in (("scan_tc_bucket", 4), ("scan_tc_bucket", 256), ("scan_tc_tau_probes", 1),
-                            ("scan_tc_tau_probes", 3)):
-            c2.set_param("scan_tc", 2)
-            c2.set_param(name, value)
-            got = idx.search(q, 10, 6, want_keys=True)
-            for x, y in zip(want, got):
-                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (name, value)
+        for cmax_mb in (16384, 0):
+            for name, value in (("scan_tc_bucket", 4), ("scan_tc_bucket", 256), ("scan_tc_tau_probes", 1),
+                                ("scan_tc_tau_probes", 3)):
+                c2.set_param("scan_tc", 2)
+                c2.set_param("scan_tc_cmax_mb", cmax_mb)
+                c2.set_param(name, value)
+                got = idx.search(q, 10, 6, want_keys=True)
+                for x, y in zip(want, got):
+                    assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (cmax_mb, name, value)
         idx.free()
         ds.free()
     finally:
