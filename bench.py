@@ -19,8 +19,10 @@ reference's own benches/clustering_benchmark.rs:11-15.
             CUDA-event duration, against the TF32 dense peak measured live with cuBLAS
   cpu_baseline  the C oracle (restatement of the reference CPU path, all host cores) on a
             bounded row sample, same centroids
-  query     batched find_k_nearest_neighbor_spann (10k queries, top-10, nprobe = k): QPS, scan
-            GB/s against the measured HBM peak, recall@10 vs brute force
+  query     batched find_k_nearest_neighbor_spann (10k queries, top-10, nprobe = k): QPS through the
+            C ABI with host buffers, the tensor-core candidate scan's bound pass against the measured
+            HBM peak, the same batch on the exact CUDA-core scan (identical results), recall@10 vs
+            brute force
 
 --impl reference times the CPU restatement (the Rust reference cannot be built here: no
 cargo/rustc) on the host cores, on a bounded sample per step.
@@ -45,8 +47,9 @@ N_ROWS, DIM, K_CENT = 1_000_000, 128, 4096
 # (ncu --set full capture, profiles/): 512 MB rounded rows read once + candidate records written
 TC_DRAM_BYTES_PER_LAUNCH = 3.21e9
 # the same for one bound-pass launch of scan_tc_kernel on the bench's 10k-query batch (None until captured)
-SCAN_TC_DRAM_BYTES_PER_LAUNCH = None
-SCAN_TC_DRAM_SOURCE = None
+SCAN_TC_DRAM_BYTES_PER_LAUNCH = 5.76e9
+SCAN_TC_DRAM_SOURCE = ("ncu dram__bytes_read+write.sum of the bound-pass launch on this batch, profiles/r01_ncu_scan_tc_v2.txt "
+                       "(5.61 GB read = lists once + gathered query rows, 0.15 GB chunk maxima written)")
 NQ, TOPK = 10_000, 10
 METRIC_NAME = "kmeans_assign_pts_per_s"
 WORKLOAD = "assign_points_to_clusters 1M x 128 f32, k=4096, squared-Euclidean, boundary 1.1, iid N(0,1)"
@@ -488,7 +491,7 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
                        "peak_source": hbm_src, "bytes_per_launch": int(unique), "requested_bytes_per_launch": int(stream),
                        "traffic": SCAN_TC_DRAM_BYTES_PER_LAUNCH, "traffic_source": SCAN_TC_DRAM_SOURCE,
                        "kernel_ms": tc["a"],
-                       "passes_ms": {"bound": tc["a"], "tau": tc["tau"], "emit": tc["b"], "refine": tc["refine"],
+                       "passes_ms": {"bound_incl_gather": tc["a"], "tau": tc["tau"], "group_refine": tc["b"], "select": tc["refine"],
                                      "fallback": tc["fallback"]},
                        "units": int(tc["units"]), "candidates_per_query": tc["candidates"] / NQ,
                        "queries_on_exact_fallback": int(tc["flagged"]),

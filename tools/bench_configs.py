@@ -111,13 +111,21 @@ def sweep(args):
             b = idx.last_scan_bytes()
             hit = sum(len(set(gt[i].tolist()) & set(ids[i, :counts[i]].tolist())) for i in range(1000))
             lane = b / 4.0 * 3.0
-            print(json.dumps({"config": "sweep", "data": args.kind, "nq": args.nq, "k": topk, "nprobe": nprobe,
-                              "prune_factor": prune if prune < 1e30 else "inf", "qps": args.nq / dt,
-                              "recall_at_10": hit / 10000.0, "mean_results": float(counts.mean()),
-                              "scan_ms": scan_ms, "probe_ms": probe_ms, "call_ms": dt * 1e3,
-                              "scan_algorithmic_gbs": b / (scan_ms * 1e-3) / 1e9,
-                              "scan_fp32_frac": lane / (scan_ms * 1e-3) / FP32_PEAK,
-                              "index_vectors": idx.nvectors}), flush=True)
+            rec = {"config": "sweep", "data": args.kind, "nq": args.nq, "k": topk, "nprobe": nprobe,
+                   "prune_factor": prune if prune < 1e30 else "inf", "qps": args.nq / dt,
+                   "recall_at_10": hit / 10000.0, "mean_results": float(counts.mean()),
+                   "scan_ms": scan_ms, "probe_ms": probe_ms, "call_ms": dt * 1e3,
+                   "scan_algorithmic_gbs": b / (scan_ms * 1e-3) / 1e9, "index_vectors": idx.nvectors}
+            if ctx.kernel_ms("scan_tc_a") > 0:          # tensor-core candidate scan (scan_tc.cu)
+                rec["scan_path"] = "tcgen05 candidate scan + exact refinement"
+                rec["scan_passes_ms"] = {n: ctx.kernel_ms("scan_tc_" + n) for n in ("a", "tau", "b", "refine", "fallback")}
+                rec["candidates_per_query"] = ctx.kernel_ms("scan_tc_candidates") / args.nq
+                rec["queries_on_exact_fallback"] = int(ctx.kernel_ms("scan_tc_flagged"))
+            else:
+                rec["scan_path"] = "exact CUDA-core scan"
+                rec["scan_fp32_frac"] = lane / (scan_ms * 1e-3) / FP32_PEAK
+            rec["probe_path"] = "tcgen05" if ctx.kernel_ms("probe_tc_a") > 0 else "exact CUDA-core"
+            print(json.dumps(rec), flush=True)
 
 
 def qshard(args):
