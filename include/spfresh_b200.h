@@ -201,6 +201,13 @@ void spf_kmpp_free(spf_kmpp* s);
  * d(c1, member), strict >, identity (row 0, distance 0). */
 int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* members,
                  uint64_t m, uint64_t* out_row);
+/* Row-sharded form ("for bisects, every GPU processes its slice of the member
+ * list"): c1 arrives as an explicit vector (it may be a row of another rank's shard); skip_row is
+ * the shard-local row of c1 when this rank owns it, UINT64_MAX otherwise.  Returns the largest
+ * distance over this shard's members and the earliest member attaining it, or (0, UINT64_MAX) when
+ * no member has a distance > 0; the ranks' answers are combined with strict > in rank order. */
+int spf_farthest_from(spf_dataset* ds, int metric, const float* c1_vector, uint64_t skip_row,
+                      const uint64_t* members, uint64_t m, float* out_dist, uint64_t* out_row);
 
 /* ---- index (posting lists in HBM) + query ---------------------------------------------- *
  * spf_index_pack stands in for SpannIndex::create_posting_lists + build_kdtree,

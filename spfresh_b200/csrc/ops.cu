@@ -3,6 +3,8 @@
 
 #include <vector>
 
+#include <string.h>
+
 #include "kernels.cuh"
 #include "pairdist.cuh"
 
@@ -220,14 +222,14 @@ __global__ void medoid_candidates_kernel(const unsigned long long* __restrict__ 
 template <int METRIC>
 __global__ void __launch_bounds__(PD_THREADS)
 farthest_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restrict__ members, uint64_t m,
-                uint64_t c1, unsigned long long* __restrict__ key) {
+                const float* __restrict__ c1vec, uint64_t c1, unsigned long long* __restrict__ key) {
   __shared__ PairDistSmem sm[PD_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
   for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < m; base += nwarps * 32) {
     const uint64_t t = base + lane;
     const bool valid = t < m && members[t] != c1;
-    const float* pa = valid ? X + (size_t)c1 * ld : nullptr;
+    const float* pa = valid ? c1vec : nullptr;      // c1 as a dataset row or an explicit vector (c1 = UINT64_MAX)
     const float* pb = valid ? X + (size_t)members[t] * ld : nullptr;
     const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
     if (valid && dv > 0.0f) {
@@ -527,11 +529,11 @@ int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* 
   return SPF_OK;
 }
 
-int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* members, uint64_t m,
-                 uint64_t* out_row) {
-  if (!ds || !out_row || (m && !members)) return fail(SPF_E_INVALID, "spf_farthest: NULL argument");
+// Shared by spf_farthest (c1 is a dataset row) and spf_farthest_from (c1 is an explicit vector, the
+// row-sharded bisect): packed (distance, earliest position) maximum over the members != skip_row.
+static int farthest_impl(spf_dataset* ds, int metric, const float* h_c1vec, uint64_t c1_row, const uint64_t* members,
+                         uint64_t m, unsigned long long* out_key) {
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
-  if (c1_row >= ds->n) return fail(SPF_E_INVALID, "c1_row >= n");
   if (m >= (1ull << 32)) return fail(SPF_E_INVALID, "m must be < 2^32");
   for (uint64_t t = 0; t < m; ++t)
     if (members[t] >= ds->n) return fail(SPF_E_INVALID, "member row %llu >= n", (unsigned long long)members[t]);
@@ -539,24 +541,56 @@ int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* m
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  if (m == 0) { *out_row = 0; return SPF_OK; }
+  *out_key = 0;
+  if (m == 0) return SPF_OK;
   DevBuf<uint64_t> d_mem;
   DevBuf<unsigned long long> d_key;
+  DevBuf<float> d_vec;
   SPF_TRY(d_mem.alloc(st, m));
   SPF_TRY(d_key.alloc(st, 1));
+  const float* c1vec = nullptr;
+  if (h_c1vec) {
+    SPF_TRY(d_vec.alloc(st, ds->ld));
+    SPF_CUDA(cudaMemsetAsync(d_vec.p, 0, ds->ld * sizeof(float), st));
+    SPF_CUDA(cudaMemcpyAsync(d_vec.p, h_c1vec, ds->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    c1vec = d_vec.p;
+  } else {
+    c1vec = ds->x + (size_t)c1_row * ds->ld;
+  }
   SPF_CUDA(cudaMemcpyAsync(d_mem.p, members, m * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   SPF_CUDA(cudaMemsetAsync(d_key.p, 0, sizeof(unsigned long long), st));
   {
     KernelTimer t(c, "farthest");
     SPF_TRY(dispatch_metric(metric, [&](auto M) {
-      farthest_kernel<decltype(M)::value><<<pd_grid(c, m), PD_THREADS, 0, st>>>(ds->x, ds->ld, d_mem.p, m, c1_row, d_key.p);
+      farthest_kernel<decltype(M)::value><<<pd_grid(c, m), PD_THREADS, 0, st>>>(ds->x, ds->ld, d_mem.p, m, c1vec, c1_row, d_key.p);
       return check_launch(c, "farthest_kernel");
     }));
   }
-  unsigned long long key = 0;
-  SPF_CUDA(cudaMemcpyAsync(&key, d_key.p, sizeof(key), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(out_key, d_key.p, sizeof(*out_key), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
+}
+
+int spf_farthest(spf_dataset* ds, int metric, uint64_t c1_row, const uint64_t* members, uint64_t m,
+                 uint64_t* out_row) {
+  if (!ds || !out_row || (m && !members)) return fail(SPF_E_INVALID, "spf_farthest: NULL argument");
+  if (c1_row >= ds->n) return fail(SPF_E_INVALID, "c1_row >= n");
+  unsigned long long key = 0;
+  SPF_TRY(farthest_impl(ds, metric, nullptr, c1_row, members, m, &key));
   *out_row = key == 0 ? 0 : members[0xffffffffu - (uint32_t)(key & 0xffffffffull)];
+  return SPF_OK;
+}
+
+int spf_farthest_from(spf_dataset* ds, int metric, const float* c1_vector, uint64_t skip_row, const uint64_t* members,
+                      uint64_t m, float* out_dist, uint64_t* out_row) {
+  if (!ds || !c1_vector || !out_dist || !out_row || (m && !members))
+    return fail(SPF_E_INVALID, "spf_farthest_from: NULL argument");
+  unsigned long long key = 0;
+  SPF_TRY(farthest_impl(ds, metric, c1_vector, skip_row, members, m, &key));
+  if (key == 0) { *out_dist = 0.0f; *out_row = ~0ull; return SPF_OK; }
+  const uint32_t bits = (uint32_t)(key >> 32);
+  memcpy(out_dist, &bits, sizeof(float));
+  *out_row = members[0xffffffffu - (uint32_t)(key & 0xffffffffull)];
   return SPF_OK;
 }
 

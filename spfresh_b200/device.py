@@ -206,6 +206,18 @@ class Dataset:
         check(lib().spf_farthest(self._h, metric, int(c1_row), ptr(members), members.size, C.byref(out)))
         return int(out.value)
 
+    def farthest_from(self, metric: int, c1_vector, members, skip_row=None):
+        """spf_farthest_from (row-sharded bisect): (largest distance, earliest local member), or
+        (0.0, None) when no member of this shard has a distance > 0."""
+        members = as_u64(members)
+        v = as_f32(c1_vector).reshape(self.d)
+        dist, row = C.c_float(), C.c_uint64()
+        skip = np.iinfo(np.uint64).max if skip_row is None else int(skip_row)
+        check(lib().spf_farthest_from(self._h, metric, ptr(v), skip, ptr(members), members.size, C.byref(dist),
+                                      C.byref(row)))
+        r = int(row.value)
+        return float(dist.value), (None if r == int(np.iinfo(np.uint64).max) else r)
+
     def kmeanspp(self, metric: int, first_row: int) -> "KmppSession":
         return KmppSession(self, metric, first_row)
 
@@ -369,12 +381,21 @@ class DeviceIndex:
         return int(lib().spf_index_last_scan_bytes(self._h))
 
     def search(self, queries, k: int, nprobe: int = 0, prune_factor: float = 1.2, want_vectors=False,
-               want_keys=False):
+               want_keys=False, out=None):
+        """Batched find_k_nearest_neighbor_spann.  `out` = (ids, dists, counts) lets the caller supply
+        the result arrays (e.g. views of pinned host memory); they are filled in place."""
         q = as_f32(queries).reshape(-1, self.d)
         nq = q.shape[0]
-        ids = np.empty((nq, k), np.uint64)
-        dists = np.empty((nq, k), np.float32)
-        counts = np.empty(nq, np.uint32)
+        if out is not None:
+            ids, dists, counts = out
+            if (ids.shape != (nq, k) or ids.dtype != np.uint64 or dists.shape != (nq, k) or dists.dtype != np.float32
+                    or counts.shape != (nq,) or counts.dtype != np.uint32
+                    or not (ids.flags.c_contiguous and dists.flags.c_contiguous and counts.flags.c_contiguous)):
+                raise ValueError("out must be C-contiguous (nq,k) uint64, (nq,k) float32, (nq,) uint32")
+        else:
+            ids = np.empty((nq, k), np.uint64)
+            dists = np.empty((nq, k), np.float32)
+            counts = np.empty(nq, np.uint32)
         vec = np.empty((nq, k, self.d), np.float32) if want_vectors else None
         keys = np.empty((nq, k), np.uint64) if want_keys else None
         check(lib().spf_search_batch(self._h, ptr(q), nq, k, nprobe, prune_factor, ptr(ids), ptr(dists),

@@ -14,8 +14,13 @@ tests).  Partial sums are combined in rank order on every rank, which keeps the 
 on all ranks and reproducible; it differs from the single-process mean only by the f32 rounding
 of a different summation order (a documented near-tie class).
 
+    subdivide_clusters / create_subclusters   hierarchical.rs:74-135: the serial work-list runs
+                        identically on every rank from the global cluster sizes; a bisect draws c1
+                        from the global member list, folds the farthest point per shard (combined
+                        with strict > in rank order) and assigns the local slice to (c1, c2)
+
 The shard object only has to provide `n`, `d`, `assign_vectors`, `cluster_sums`,
-`medoid_candidates` and `rows` — `DeviceShard` wraps a `Dataset` on the GPU; the CPU tests plug an
+`medoid_candidates`, `farthest_from`, `member_lists` and `rows` — `DeviceShard` wraps a `Dataset` on the GPU; the CPU tests plug an
 oracle-backed shard into the same exchange code.
 """
 from __future__ import annotations
@@ -110,8 +115,15 @@ class DeviceShard:
         self.n, self.d = dataset.n, dataset.d
         self._host = host_rows
 
-    def assign_vectors(self, metric, centroids, boundary_factor=1.1):
-        return self.ds.assign_vectors(metric, centroids, boundary_factor=boundary_factor)
+    def assign_vectors(self, metric, centroids, boundary_factor=1.1, point_idx=None):
+        return self.ds.assign_vectors(metric, centroids, point_idx=point_idx, boundary_factor=boundary_factor)
+
+    def farthest_from(self, metric, c1_vector, members, skip_row=None):
+        return self.ds.farthest_from(metric, c1_vector, members, skip_row)
+
+    def member_lists(self, res):
+        """Per cluster the shard-local rows assigned to it (input order)."""
+        return res.fetch(best=False, dmin=False).lists()
 
     def cluster_sums(self, res):
         return self.ds.cluster_sums(res)
@@ -234,6 +246,85 @@ def kmeans_plus_plus(shard, comm: Comm, metric: int, k: int, rng, shard_starts: 
         return np.array(chosen, np.uint64)
     finally:
         sess.free()
+
+
+class ShardedCluster:
+    """A cluster of the row-sharded build: the global row of its centroid, this rank's slice of the
+    member list (shard-local rows, input order), the member count of every rank, the depth."""
+
+    def __init__(self, centroid_row: int, local_points: np.ndarray, counts: np.ndarray, depth: int):
+        self.centroid_idx = int(centroid_row)
+        self.local_points = np.asarray(local_points, np.uint64)
+        self.counts = np.asarray(counts, np.int64)
+        self.depth = int(depth)
+
+    @property
+    def size(self) -> int:
+        return int(self.counts.sum())
+
+
+def create_subclusters(shard, comm: Comm, metric: int, cluster: ShardedCluster, rng, shard_starts: np.ndarray,
+                       boundary_factor: float = 1.1):
+    """Row-sharded create_subclusters (hierarchical.rs:107-135): every rank works on its slice of the
+    member list.  Shards are contiguous row ranges and member lists are in input order, so the
+    global member list is the concatenation of the slices in rank order.
+      c1   points.choose(rng) (:111): an index into the global list (identical draw on every rank);
+           the owning rank turns it into a global row, its vector is gathered
+      c2   the farthest-point fold (:112-126): local (max distance, earliest member) per rank,
+           combined with strict > in rank order; no distance > 0 anywhere -> global row 0
+      then assign_points_to_clusters with the two centroids on the local slice (:129)"""
+    j = int(rng.choose_index(cluster.size))                                   # :111
+    prefix = np.concatenate([[0], np.cumsum(cluster.counts)])
+    owner = int(np.searchsorted(prefix, j, side="right") - 1)
+    mine = -1
+    if comm.rank == owner:
+        mine = int(cluster.local_points[j - int(prefix[owner])]) + int(shard_starts[owner])
+    c1 = [int(x[0]) for x in comm.allgather(np.array([mine], np.int64))][owner]
+    v1 = gather_rows(shard, comm, np.array([c1], np.uint64), shard_starts)[0]
+    skip = c1 - int(shard_starts[comm.rank]) if comm.rank == owner else None
+    dist, row = shard.farthest_from(metric, v1, cluster.local_points, skip)
+    grow = -1 if row is None else int(row) + int(shard_starts[comm.rank])
+    cands = comm.allgather_many([np.array([dist], np.float32), np.array([grow], np.int64)])
+    best_d, c2 = np.float32(0.0), 0                                            # identity (0, 0.0) :115
+    for r in range(comm.world):                                                # strict >: lowest rank wins ties
+        if int(cands[r][1][0]) >= 0 and cands[r][0][0] > best_d:
+            best_d, c2 = cands[r][0][0], int(cands[r][1][0])
+    vecs = gather_rows(shard, comm, np.array([c1, c2], np.uint64), shard_starts)
+    res = shard.assign_vectors(metric, vecs, boundary_factor=boundary_factor, point_idx=cluster.local_points)
+    try:
+        lists = shard.member_lists(res)
+    finally:
+        res.free()
+    sizes = comm.allgather(np.array([len(lists[0]), len(lists[1])], np.int64))
+    cnt = np.stack(sizes)                                                      # world x 2
+    return (ShardedCluster(c1, lists[0], cnt[:, 0], cluster.depth + 1),
+            ShardedCluster(c2, lists[1], cnt[:, 1], cluster.depth + 1))
+
+
+def subdivide_clusters(shard, comm: Comm, metric: int, clusters: List[ShardedCluster], desired: int, rng,
+                       shard_starts: np.ndarray, boundary_factor: float = 1.1, max_splits: int = 1_000_000):
+    """Row-sharded subdivide_clusters (hierarchical.rs:74-105): the reference's serial work-list,
+    driven identically on every rank by the global cluster sizes."""
+    i, splits = 0, 0
+    while i < len(clusters):
+        if clusters[i].size > desired:
+            splits += 1
+            if splits > max_splits:
+                raise RuntimeError("subdivide_clusters: split limit reached (the reference would loop forever here)")
+            s1, s2 = create_subclusters(shard, comm, metric, clusters[i], rng, shard_starts, boundary_factor)
+            clusters[i] = s1                                                   # :95
+            clusters.append(s2)                                                # :98
+        else:
+            i += 1
+    return clusters
+
+
+def clusters_from_assignment(shard, comm: Comm, res, centroid_rows) -> List[ShardedCluster]:
+    """The sharded form of assign_points' result (hierarchical.rs:368-390): per cluster the local
+    member slice and every rank's member count."""
+    lists = shard.member_lists(res)
+    counts = np.stack(comm.allgather(np.array([len(x) for x in lists], np.int64)))   # world x k
+    return [ShardedCluster(int(centroid_rows[c]), lists[c], counts[:, c], 0) for c in range(len(lists))]
 
 
 class ShardedKMeans:

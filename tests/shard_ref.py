@@ -19,13 +19,27 @@ class OracleShard:
         self.n, self.d = self.x.shape
         self.row0 = row0
 
-    def assign_vectors(self, metric, centroids, boundary_factor=1.1):
+    def assign_vectors(self, metric, centroids, boundary_factor=1.1, point_idx=None):
         cv = np.ascontiguousarray(centroids, np.float32)
         aug = np.concatenate([self.x, cv], axis=0)            # centroids appended as extra rows
         cent = np.arange(self.n, self.n + cv.shape[0], dtype=np.uint64)
-        res = oracle.assign(aug, metric, cent, point_idx=np.arange(self.n, dtype=np.uint64),
-                            boundary_factor=boundary_factor)
+        pts = np.arange(self.n, dtype=np.uint64) if point_idx is None else np.asarray(point_idx, np.uint64)
+        res = oracle.assign(aug, metric, cent, point_idx=pts, boundary_factor=boundary_factor)
         return OracleAssign(res, cv.shape[0])
+
+    def member_lists(self, res):
+        return [res.members[int(res.offsets[c]):int(res.offsets[c + 1])].copy() for c in range(res.k)]
+
+    def farthest_from(self, metric, c1_vector, members, skip_row=None):
+        best_d, best_row = np.float32(0.0), None              # strict >, identity (0, 0.0) (:112-126)
+        v = np.asarray(c1_vector, np.float32)
+        for r in np.asarray(members, np.int64):
+            if skip_row is not None and int(r) == int(skip_row):
+                continue
+            dv = np.float32(oracle.distance(metric, v, self.x[r]))
+            if dv > best_d:
+                best_d, best_row = dv, int(r)
+        return float(best_d), best_row
 
     def cluster_sums(self, res):
         sums = np.zeros((res.k, self.d), np.float32)

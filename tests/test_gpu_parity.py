@@ -313,6 +313,46 @@ def test_sharded_build_step_matches_oracle_shards(spf, oracle, metric):
 
 
 @pytest.mark.parametrize("metric", METRICS)
+def test_sharded_bisect_matches_oracle(spf, oracle, metric):
+    """§8(e) bisect: three device shards run assign + update + the bisect work-list
+    (spf_farthest_from, spf_assign_vectors on the local member slices) == the oracle-backed shards
+    == the single-process oracle fit."""
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_multirank_cpu import run_sharded_fit
+    from spfresh_b200.sharded import DeviceShard, ThreadComm
+    data = clustered(3000, 14, 10, 91 + metric)
+    init = np.random.default_rng(5).choice(3000, 4, replace=False)
+    bounds = [0, 800, 1900, 3000]
+
+    def run_all(make_shard):
+        grp = ThreadComm.Group(3)
+        out = [None] * 3
+
+        def run(r):
+            out[r] = run_sharded_fit(ThreadComm(grp, r), data, init, bounds, metric, 250, make_shard)
+        th = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return out
+    ctxs = [spf.Context(0) for _ in range(3)]
+    try:
+        dss = [spf.Dataset(ctxs[r], data[bounds[r]:bounds[r + 1]]) for r in range(3)]
+        got = run_all(lambda r: DeviceShard(dss[r], bounds[r], data[bounds[r]:bounds[r + 1]]))
+        ref = run_all(None)
+        assert got[0] == got[1] == got[2] and got[0] == ref[0]
+        full = oracle.fit(data, metric, init, 250, pick=lambda m: (m * 5) // 7)
+        assert got[0] == [(int(c.centroid_idx), np.asarray(c.points).tolist(), int(c.depth)) for c in full]
+        assert len(full) > 4
+        for d_ in dss:
+            d_.free()
+    finally:
+        for c_ in ctxs:
+            c_.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
 def test_sharded_kmeanspp_matches_oracle_shards(spf, oracle, metric):
     """Sharded k-means++ on three device shards == the oracle-backed shards, and (one shard) == the
     single-process device k-means++ session."""

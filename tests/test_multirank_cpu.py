@@ -217,3 +217,86 @@ def test_sharded_kmeanspp_over_gloo(tmp_path):
     ref, _ = oracle.kmeanspp(data, 0, 10, 321, KMPP_U)
     assert np.array_equal(single, ref)
     assert np.array_equal(gloo_rows, ref)
+
+
+# ----------------------------------------------------------------------------------------------
+# row-sharded fit: assign + update + bisect work-list (hierarchical.rs:65-135)
+# ----------------------------------------------------------------------------------------------
+def run_sharded_fit(comm, data, init, bounds, metric, desired, make_shard=None):
+    """initialize (given rows) -> assign_points -> update_centroids -> subdivide_clusters on row
+    shards; returns the clusters with GLOBAL member lists (slices concatenated in rank order)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_ref import OracleShard
+    from spfresh_b200.clustering import ScriptedRandomSource
+    from spfresh_b200.sharded import ShardedKMeans, clusters_from_assignment, subdivide_clusters
+    lo, hi = bounds[comm.rank], bounds[comm.rank + 1]
+    shard = make_shard(comm.rank) if make_shard else OracleShard(data[lo:hi], lo)
+    km = ShardedKMeans(shard, comm, metric)
+    km.init_rows(init)
+    km.step()                                            # assign (old centroids) + update (new rows)
+    clusters = clusters_from_assignment(shard, comm, km.last, km.rows)
+    rng = ScriptedRandomSource(index=lambda m: (m * 5) // 7)
+    clusters = subdivide_clusters(shard, comm, metric, clusters, desired, rng, km.starts)
+    out = []
+    for c in clusters:
+        width = int(c.counts.max()) if c.counts.size else 0
+        pad = np.full(max(width, 1), -1, np.int64)
+        pad[:c.local_points.size] = c.local_points.astype(np.int64) + int(km.starts[comm.rank])
+        parts = comm.allgather(pad)
+        pts = np.concatenate([p[p >= 0] for p in parts])
+        out.append((c.centroid_idx, pts.tolist(), c.depth))
+    return out
+
+
+def fit_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spfresh_b200.sharded import TorchComm
+    import pickle
+    data, init = sharded_inputs()
+    out = run_sharded_fit(TorchComm(), data, init[:4], [0, 400, 900], 0, 60)
+    with open(os.path.join(os.environ["SPF_TEST_TMP"], f"fit_{rank}.pkl"), "wb") as f:
+        pickle.dump(out, f)
+    ok[rank] = 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_bisect_over_gloo(tmp_path):
+    """Row-sharded fit (assign, update, bisect work-list): world size 2 over gloo == two in-process
+    shards == one shard == the single-process oracle fit for the same random decisions."""
+    import pickle
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import oracle
+    from spfresh_b200.sharded import SingleComm, ThreadComm
+    oracle.build()
+    os.environ["SPF_TEST_TMP"] = str(tmp_path)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(fit_worker, args=(2, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+    gloo = [pickle.load(open(tmp_path / f"fit_{r}.pkl", "rb")) for r in range(2)]
+    assert gloo[0] == gloo[1]                            # every rank ends with the same global clusters
+
+    data, init = sharded_inputs()
+    grp = ThreadComm.Group(2)
+    res = [None, None]
+
+    def run(r):
+        res[r] = run_sharded_fit(ThreadComm(grp, r), data, init[:4], [0, 400, 900], 0, 60)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert res[0] == gloo[0] and res[1] == gloo[0]
+    single = run_sharded_fit(SingleComm(), data, init[:4], [0, 900], 0, 60)
+    ref = oracle.fit(data, 0, init[:4], 60, pick=lambda m: (m * 5) // 7)
+    ref_t = [(int(c.centroid_idx), np.asarray(c.points).tolist(), int(c.depth)) for c in ref]
+    assert single == ref_t                               # one shard: the reference's fit, bit for bit
+    assert len(ref_t) > 4                                # the bisect did fire
+    assert gloo[0] == ref_t                              # two shards: same clusters on this data
