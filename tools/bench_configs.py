@@ -173,7 +173,7 @@ def qshard(args):
     if world > 1:                                    # NCCL communicator set-up outside the timed region
         w = torch.zeros(1, device=dev)
         dist.all_gather([torch.empty_like(w) for _ in range(world)], w)
-    for nprobe in (8, 32, 128):
+    for it, nprobe in enumerate((8, 8, 32, 128)):        # the first pass warms the merge path up and is not reported
         idx.search(q, topk, nprobe, want_keys=True)
         barrier()
         t0 = time.perf_counter()
@@ -213,7 +213,7 @@ def qshard(args):
             t = torch.tensor([dt, t_scan, scan_ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt, t_scan, scan_ms = float(t[0]), float(t[1]), float(t[2])
-        if rank == 0:
+        if rank == 0 and it > 0:
             print(json.dumps({"config": "qshard", "data": args.kind, "n_gpus": world, "nq": args.nq, "k": topk,
                               "nprobe": nprobe, "qps_merged": args.nq / dt, "qps_scan_only": args.nq / t_scan,
                               "scan_kernel_ms_max": scan_ms, "call_ms": t_scan * 1e3, "total_ms": dt * 1e3,
