@@ -654,6 +654,46 @@ def test_search_tensor_scan_matches_oracle(spf, oracle, n, d, nlists, topk, npro
         c2.close()
 
 
+def test_search_tensor_scan_random_shapes(spf, oracle):
+    """Randomised shapes (tiny and empty lists, k larger than a list, one list, nprobe = all lists,
+    duplicate rows, ragged dimensions): tensor scan + tensor probe == exact kernels, bit for bit."""
+    rng = np.random.default_rng(2024)
+    c2 = spf.Context(0)
+    try:
+        for case in range(14):
+            n = int(rng.integers(40, 4000))
+            d = int(rng.choice([1, 2, 3, 7, 16, 31, 64, 100, 128]))
+            nlists = int(rng.integers(1, min(n, 70) + 1))
+            topk = int(rng.integers(1, 17))
+            nprobe = int(rng.choice([0, 1, 2, 5, nlists]))
+            data = clustered(n, d, 5, 1000 + case) if case % 2 else gauss(n, d, 1000 + case)
+            if case % 3 == 0:
+                data[n // 2:] = data[:n - n // 2]            # duplicate rows: exact ties everywhere
+            cent = rng.choice(n, nlists, replace=False)
+            r = oracle.assign(data, 0, cent)
+            off, mem = r.offsets.copy(), r.members.copy()
+            if nlists > 2:                                    # empty a list: its members vanish from the index
+                lo, hi = int(off[1]), int(off[2])
+                mem = np.concatenate([mem[:lo], mem[hi:]])
+                off[2:] -= np.uint64(hi - lo)
+            ds = spf.Dataset(c2, data)
+            idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+            q = np.concatenate([data[rng.integers(0, n, 150)], gauss(150, d, 77 + case)]).astype(np.float32)
+            pf = float(rng.choice([1.0, 1.2, 3.0, np.inf]))
+            out = {}
+            for mode, cmax_mb in ((0, 0), (2, 16384), (2, 0)):
+                c2.set_param("scan_tc", mode)
+                c2.set_param("scan_tc_cmax_mb", cmax_mb)
+                out[(mode, cmax_mb)] = idx.search(q, topk, nprobe, prune_factor=pf, want_keys=True)
+            for key in ((2, 16384), (2, 0)):
+                for x, y in zip(out[(0, 0)], out[key]):
+                    assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (case, n, d, nlists, topk, nprobe, pf, key)
+            idx.free()
+            ds.free()
+    finally:
+        c2.close()
+
+
 def test_search_tensor_scan_fallbacks(spf, oracle):
     """Bucket overflow, a bound pass over a subset of the probes, non-finite queries and huge norms
     all end in the exact result (flagged queries re-run on the exact query-major kernel)."""
