@@ -451,10 +451,12 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
     const size_t grow = (size_t)(g.u0 + blockIdx.x) * UNIT_ROWS + r;  // in the per-row scalars (all units)
     uint32_t pair = NOPAIR, q = 0;
     if (r < nb) { pair = g.pair_sorted[p0 + r]; q = pair / g.nprobe; }
-    if (g.copy_rows) {
+    // Padding rows are left as they are: a row of the GEMM only feeds its own accumulator lane,
+    // and the epilogue never looks at a row whose threshold is +inf.
+    if (g.copy_rows && pair != NOPAIR) {
       float4* dst = reinterpret_cast<float4*>(g.A) + row * g.ld4;
       const float4* src = reinterpret_cast<const float4*>(g.qtf) + (size_t)q * g.ld4;
-      for (uint32_t c = lane; c < g.ld4; c += 32) dst[c] = pair != NOPAIR ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (uint32_t c = lane; c < g.ld4; c += 32) dst[c] = __ldg(src + c);
     }
     if (lane == 0) {
       float th = INF;
