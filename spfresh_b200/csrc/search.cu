@@ -161,6 +161,138 @@ probe_sort_kernel(const float* __restrict__ Dqc, uint32_t nlists, uint32_t nprob
   }
 }
 
+// The same outputs for nprobe << nlists without sorting everything: a bitwise search finds the
+// nprobe-th smallest (distance bits, list id) key of the query (one counting step over the keys in
+// registers per differing distance bit, 12 more over the list ids only when equal distances straddle
+// the cut), the nprobe keys up to it are compacted into shared memory and only those are sorted.
+// Keys are unique, so exactly nprobe keys are selected.  ITEMS: keys per thread (nlists <= 256 *
+// ITEMS), OUT: selected keys per thread (nprobe <= 256 * OUT).
+template <int ITEMS, int OUT>
+__global__ void __launch_bounds__(256)
+probe_topn_kernel(const float* __restrict__ Dqc, uint32_t nlists, uint32_t nprobe, float prune_factor,
+                  const uint32_t* __restrict__ lens, uint32_t* __restrict__ probe, float* __restrict__ thr,
+                  uint32_t* __restrict__ seqbase) {
+  typedef cub::BlockRadixSort<unsigned long long, 256, OUT> Sort;
+  typedef cub::BlockScan<uint32_t, 256> Scan;
+  __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+  __shared__ unsigned long long s_sel[256 * OUT];
+  __shared__ uint32_t s_cnt[2][8];
+  const uint64_t q = blockIdx.x;
+  const float* row = Dqc + q * nlists;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // striped keys (coalesced loads; the order is irrelevant here): distance bits in registers, the
+  // list id j = i * 256 + threadIdx.x implicit.  Pad keys (j >= nlists) are (0xffffffff, j): last.
+  uint32_t dv[ITEMS];
+  uint32_t vo = 0u, va = ~0u;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t j = i * 256 + threadIdx.x;
+    dv[i] = j < nlists ? __float_as_uint(row[j]) : ~0u;
+    vo |= dv[i];
+    va &= dv[i];
+  }
+  auto block_sum = [&](uint32_t c, int slot) {       // sum over the block; slots alternate between calls
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_cnt[slot][warp] = c;
+    __syncthreads();
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_cnt[slot][w];
+    return tot;
+  };
+  // bits that all keys share need no counting
+  vo = __reduce_or_sync(0xffffffffu, vo);
+  va = __reduce_and_sync(0xffffffffu, va);
+  if (lane == 0) { s_cnt[0][warp] = vo; s_cnt[1][warp] = va; }
+  __syncthreads();
+  vo = 0u; va = ~0u;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { vo |= s_cnt[0][w]; va &= s_cnt[1][w]; }
+  __syncthreads();
+  const uint32_t diff = vo ^ va;
+  const int hb = diff ? 31 - __clz((int)diff) : -1;
+  // distance bits of the nprobe-th smallest key, most significant differing bit first: with the bits
+  // above `bit` fixed to `prefix`, count the keys whose bit is 0; the wanted key is among them if at
+  // least `want` keys are
+  uint32_t prefix = hb >= 31 ? 0u : (hb < 0 ? va : (va & ~((2u << hb) - 1u)));
+  uint32_t want = nprobe;
+  for (int bit = hb; bit >= 0; --bit) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) c += ((dv[i] ^ prefix) >> bit) == 0u ? 1u : 0u;
+    const uint32_t tot = block_sum(c, bit & 1);
+    if (want > tot) { want -= tot; prefix |= 1u << bit; }
+  }
+  // keys with smaller distance bits are all selected; of the `ties` keys with equal bits the `want`
+  // smallest list ids are (usually ties == want == 1)
+  uint32_t tc = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) tc += dv[i] == prefix ? 1u : 0u;
+  __syncthreads();
+  const uint32_t ties = block_sum(tc, 0);
+  uint32_t jmax = 0xffffffffu;
+  if (ties != want) {                                 // the want-th smallest id among the ties, bitwise again
+    uint32_t jp = 0;
+    __syncthreads();
+    for (int bit = 11; bit >= 0; --bit) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t j = i * 256 + threadIdx.x;
+        c += (dv[i] == prefix && ((j ^ jp) >> bit) == 0u) ? 1u : 0u;
+      }
+      const uint32_t tot = block_sum(c, bit & 1);
+      if (want > tot) { want -= tot; jp |= 1u << bit; }
+    }
+    jmax = jp;
+  }
+  // compact the selected keys (exactly nprobe of them) and sort those
+  uint32_t mine = 0, base0 = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t j = i * 256 + threadIdx.x;
+    mine += (dv[i] < prefix || (dv[i] == prefix && j <= jmax)) ? 1u : 0u;
+  }
+  __syncthreads();
+  Scan(tmp.scan).ExclusiveSum(mine, base0);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t j = i * 256 + threadIdx.x;
+    if (dv[i] < prefix || (dv[i] == prefix && j <= jmax))
+      s_sel[base0++] = j < nlists ? (((unsigned long long)dv[i] << 12) | j) : ~0ull;
+  }
+  __syncthreads();
+  unsigned long long sk[OUT];
+#pragma unroll
+  for (int i = 0; i < OUT; ++i) {
+    const uint32_t p = threadIdx.x * OUT + i;       // blocked arrangement
+    sk[i] = p < nprobe ? s_sel[p] : ~0ull;
+  }
+  __syncthreads();
+  Sort(tmp.sort).Sort(sk, 0, 44);
+  __syncthreads();
+  uint32_t len[OUT], base[OUT];
+#pragma unroll
+  for (int i = 0; i < OUT; ++i) {
+    const uint32_t p = threadIdx.x * OUT + i;
+    len[i] = (p < nprobe && sk[i] != ~0ull) ? lens[(uint32_t)(sk[i] & 0xfffull)] : 0u;
+  }
+  Scan(tmp.scan).ExclusiveSum(len, base);
+#pragma unroll
+  for (int i = 0; i < OUT; ++i) {
+    const uint32_t p = threadIdx.x * OUT + i;
+    if (p < nprobe) {
+      probe[q * nprobe + p] = (uint32_t)(sk[i] & 0xfffull);
+      seqbase[q * nprobe + p] = base[i];
+    }
+  }
+  if (threadIdx.x == 0) {
+    // :165  F::from(1.2) * (nearest.distance + F::epsilon())
+    const float d0 = __uint_as_float((uint32_t)(sk[0] >> 12));
+    thr[q] = __fmul_rn(prune_factor, __fadd_rn(d0, 1.1920929e-7f));
+  }
+}
+
 template <int R>
 __device__ __forceinline__ void topk_insert(unsigned long long (&key)[R], unsigned long long (&pay)[R],
                                             unsigned long long ck, unsigned long long cp, int lane) {
@@ -1004,9 +1136,12 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
       if (nprobe > 16 && nlists <= 1024) {
         probe_sort_kernel<4><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
                                                           probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+      } else if (nprobe > 16 && nprobe <= 256 && nlists <= 4096) {        // select the nprobe smallest, sort only those
+        probe_topn_kernel<16, 1><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
+                                                              probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
       } else if (nprobe > 16 && nlists <= 4096) {
-        probe_sort_kernel<16><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
-                                                           probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+        probe_topn_kernel<16, 4><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
+                                                              probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
       } else {
         probe_select_kernel<<<(unsigned)nc, 128, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
                                                           probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);

@@ -583,6 +583,33 @@ def test_search_matches_oracle(spf, ctx, oracle, n, d, nlists, topk, nprobe):
         assert np.array_equal(ids2[i, :rc2[i]], rid2[i, :rc2[i]])
 
 
+@pytest.mark.parametrize("nprobe", [17, 64, 256, 300, 1024])
+def test_search_probe_selection_large_nprobe(spf, oracle, nprobe):
+    """probe_topn_kernel (select the nprobe smallest (distance, list id) keys, sort only those) ==
+    the oracle's full stable sort of the centroid distances, for 1024 < nlists <= 4096."""
+    c2 = spf.Context(0)
+    try:
+        data = clustered(9000, 8, 30, 404)
+        data[100:140] = data[60:100]                       # duplicated centroid vectors: equal distances, id order
+        nlists = 3000
+        cent = np.arange(nlists, dtype=np.uint64) * 3 % 9000
+        r = oracle.assign(data, 0, cent)
+        ds = spf.Dataset(c2, data)
+        idx = spf.DeviceIndex.pack(ds, r.offsets, r.members, cent)
+        q = clustered(64, 8, 30, 404)
+        c2.set_param("scan_tc", 0)
+        ids, dists, counts, keys = idx.search(q, 10, nprobe, prune_factor=float("inf"), want_keys=True)
+        rid, rd, rc = oracle.search_batch(data, r.offsets, r.members, cent, q, 10, nprobe, prune_factor=float("inf"))
+        assert np.array_equal(counts, rc)
+        for i in range(64):
+            assert np.array_equal(ids[i, :rc[i]], rid[i, :rc[i]]), i
+            assert np.array_equal(dists[i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32)), i
+        idx.free()
+        ds.free()
+    finally:
+        c2.close()
+
+
 def test_search_list_major_equals_query_major(spf, oracle):
     """The list-major scan (lists shared by query batches) and the query-major scan are the same
     function: identical ids, distance bits, counts and merge keys; the first is oracle-checked."""
