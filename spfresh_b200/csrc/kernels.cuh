@@ -174,6 +174,12 @@ struct ScanTcCall {
   bool is_probe = false;           // the centroid probe (names of the timers only)
 };
 int scan_tc_run(spf_ctx* c, const ScanTcCall& call);
+// Dense tensor-core centroid probe for 32 < nprobe <= 1024, nlists <= 4096: TF32 s of every query
+// against every centroid, nprobe-th largest s per query, exact evaluation of everything within the
+// certified bound, sort.  Writes probe / thr / seqbase; sets *d_redo when the exact probe must run.
+int probe_tc_dense(spf_ctx* c, const ScanTcSide& side, const float* centroids, const float* Q, uint64_t nq, uint32_t ld,
+                   uint32_t nlists, uint32_t nprobe, float prune_factor, const uint32_t* lens, uint32_t* probe,
+                   float* thr, uint32_t* seqbase, int* d_redo);
 
 // ---- assign_api.cu ------------------------------------------------------------------------
 int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out);   // api.cu: device buffer only

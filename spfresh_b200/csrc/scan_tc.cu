@@ -72,9 +72,11 @@ struct ScanTcArgs {
   const uint32_t* rowpair;         // per row: q * nprobe + p, NOPAIR for padding rows
   float* pairtop;                  // phase A out: (pair, half) x TOPR (16 or 32) chunk maxima, descending
   uint32_t* qcnt; uint2* bucket;   // phase B out: per query candidate count and (slot, encounter index) entries
+  float* dense; uint32_t dense_ld; // MODE 2 out: s of row `pair` against every slot, dense_ld floats per row
 };
 
-template <bool EMIT, int TOPR>
+// MODE 0: bound pass, 1: emit pass, 2: dense store of s (centroid probe with nprobe > 32)
+template <int MODE, int TOPR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_e, ScanTcArgs a) {
@@ -233,6 +235,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         auto process = [&](uint32_t (&rr)[32], int c) -> float {
           const uint32_t cb = colbase + (uint32_t)c * 32u;
           if (cb >= ud.nslots || !enabled) return -INF;
+          if (MODE == 2) {                                // 128 contiguous bytes per thread: four full sectors
+            float4* o = reinterpret_cast<float4*>(a.dense + (size_t)pair * a.dense_ld + cb);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              o[g] = make_float4(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1]),
+                                 __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
+            return -INF;
+          }
           float q[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -240,7 +250,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                          fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
           float m = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
           m = fmaxf(m, -INF);                             // an all-NaN chunk counts as empty
-          if (EMIT) {
+          if (MODE == 1) {
             if (m > thr_s) {
               // which of the 32 columns pass: straight-line mask, then one iteration per hit (only the
               // column index is needed, so the registers are never indexed dynamically)
@@ -285,10 +295,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[buf]);
         const float m3 = process(rbuf, 3);
-        if (!EMIT && a.cmax != nullptr)                   // one coalesced 512-byte store per warp and tile
+        if (MODE == 0 && a.cmax != nullptr)                   // one coalesced 512-byte store per warp and tile
           a.cmax[((size_t)(ud.tile0 + t) * 2 + half) * UNIT_ROWS + lrow] = make_float4(m0, m1, m2, m3);
       }
-      if (!EMIT && enabled) {
+      if (MODE == 0 && enabled) {
         float4* o = reinterpret_cast<float4*>(a.pairtop + ((size_t)pair * 2 + half) * TOPR);
 #pragma unroll
         for (int i = 0; i < TOPR / 4; ++i) o[i] = make_float4(top[4 * i], top[4 * i + 1], top[4 * i + 2], top[4 * i + 3]);
@@ -721,6 +731,151 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineArgs r) {
   if (lane == 0) a.out_counts[q] = count;
 }
 
+// ---------------------------------------------------------------------------------------------
+// dense centroid probe (nprobe > 32): s of every query against every centroid, then selection
+// ---------------------------------------------------------------------------------------------
+// Per-unit / per-row scalars of a dense launch over the queries [0, nq) of one chunk: unit u holds the
+// queries u*128 .. u*128+127, every unit scans the whole centroid list.
+__global__ void dense_setup_kernel(uint32_t nunits, uint32_t nq, uint32_t nslots, UnitDesc* __restrict__ desc,
+                                   float* __restrict__ rowthr, uint32_t* __restrict__ rowseq,
+                                   uint32_t* __restrict__ rowpair) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nunits * UNIT_ROWS) return;
+  if ((r % UNIT_ROWS) == 0) { UnitDesc ud; ud.slot0 = 0; ud.nslots = nslots; ud.tile0 = 0; ud.pad = 0; desc[r / UNIT_ROWS] = ud; }
+  rowthr[r] = r < nq ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+  rowseq[r] = 0;
+  rowpair[r] = r < nq ? r : NOPAIR;
+}
+
+struct DenseSelArgs {
+  const float* S; uint32_t s_ld;                 // nq x s_ld approximate s = q'.c' - |c|^2/2
+  const float* Q; const float* C; uint32_t ld;   // exact queries (chunk) and centroids, row-major
+  const float* qnorm; const float* qres; const float* vstat;
+  uint32_t nlists, nprobe; float prune_factor;
+  const uint32_t* lens; uint32_t* probe; float* thr; uint32_t* seqbase; int* redo;
+};
+
+// One CTA per query.  With s_T the nprobe-th largest approximate s, nprobe centroids have
+// d_ref <= |q|^2 - 2 s_T + E, so every centroid among the nprobe nearest has s >= s_T - E: those
+// (nprobe plus a few) are evaluated exactly (the reference's sequential f32 sum), sorted by
+// (distance bits, list id) and the first nprobe are the probe — kiddo's nearest_n (:164).  Queries
+// without a certified bound, with a non-finite s, or with more candidates than 256 * OUT raise `redo`.
+template <int ITEMS, int OUT>
+__global__ void __launch_bounds__(256) probe_dense_select_kernel(DenseSelArgs a) {
+  typedef cub::BlockRadixSort<unsigned long long, 256, OUT> Sort;
+  typedef cub::BlockScan<uint32_t, 256> Scan;
+  __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+  __shared__ uint32_t s_sel[256 * OUT];
+  __shared__ uint32_t s_cnt[2][8];
+  const uint64_t q = blockIdx.x;
+  const float* row = a.S + q * a.s_ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float INF = __int_as_float(0x7f800000);
+  // keys ascending with DEscending s: bits flipped into unsigned order, then inverted
+  auto to_key = [](float s) {
+    const uint32_t b = __float_as_uint(s);
+    return ~((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+  };
+  auto block_sum = [&](uint32_t c, int slot) {
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_cnt[slot][warp] = c;
+    __syncthreads();
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_cnt[slot][w];
+    return tot;
+  };
+  uint32_t dv[ITEMS];
+  uint32_t bad = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t j = i * 256 + threadIdx.x;
+    const float s = j < a.nlists ? row[j] : -INF;
+    bad |= (j < a.nlists && !(fabsf(s) < INF)) ? 1u : 0u;      // NaN or infinite
+    dv[i] = j < a.nlists ? to_key(s) : ~0u;
+  }
+  const float qn = a.qnorm[q], cnmax = a.vstat[0];
+  const float E = tc_err_bound(qn, a.qres[q], cnmax, a.vstat[1], a.ld);
+  if (!(E < INF) || !(qn < INF)) bad = 1;
+  if (block_sum(bad, 0) != 0) {                   // uniform: the exact probe owns such batches
+    if (threadIdx.x == 0) *a.redo = 1;
+    return;
+  }
+  // nprobe-th smallest key, most significant bit first (see probe_topn_kernel, search.cu)
+  uint32_t prefix = 0, want = a.nprobe;
+  for (int bit = 31; bit >= 0; --bit) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) c += ((dv[i] ^ prefix) >> bit) == 0u ? 1u : 0u;
+    const uint32_t tot = block_sum(c, bit & 1);
+    if (want > tot) { want -= tot; prefix |= 1u << bit; }
+  }
+  // s_T back from the key; candidates: s >= s_T - E (E in distance units is 2E on d = |q|^2 - 2 s)
+  const uint32_t fb = ~prefix;
+  const float s_t = __uint_as_float((fb & 0x80000000u) ? (fb & 0x7fffffffu) : ~fb);
+  const float slop = 1e-6f * (qn + cnmax) + 1e-30f;
+  const uint32_t cut = to_key((s_t - E) - slop);  // keys <= cut are candidates
+  uint32_t mine = 0, base0 = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) mine += dv[i] <= cut ? 1u : 0u;
+  __syncthreads();
+  Scan(tmp.scan).ExclusiveSum(mine, base0);
+  const uint32_t total = block_sum(mine, 0);
+  if (total > 256u * OUT) {
+    if (threadIdx.x == 0) *a.redo = 1;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i)
+    if (dv[i] <= cut) s_sel[base0++] = i * 256 + threadIdx.x;
+  __syncthreads();
+  // exact distances of the candidates, (distance bits, list id) keys
+  const uint32_t ld4 = a.ld / 4;
+  const float4* Q4 = reinterpret_cast<const float4*>(a.Q) + q * ld4;
+  unsigned long long sk[OUT];
+#pragma unroll
+  for (int i = 0; i < OUT; ++i) {
+    const uint32_t p = threadIdx.x * OUT + i;       // blocked arrangement
+    sk[i] = ~0ull;
+    if (p < total) {
+      const uint32_t j = s_sel[p];
+      const float4* C4 = reinterpret_cast<const float4*>(a.C) + (size_t)j * ld4;
+      float acc = 0.0f;
+      for (uint32_t c = 0; c < ld4; ++c) {
+        const float4 v = __ldg(C4 + c), qv = __ldg(Q4 + c);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
+        acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+      }
+      sk[i] = ((unsigned long long)__float_as_uint(acc) << 12) | j;
+    }
+  }
+  __syncthreads();
+  Sort(tmp.sort).Sort(sk, 0, 44);
+  __syncthreads();
+  uint32_t len[OUT], base[OUT];
+#pragma unroll
+  for (int i = 0; i < OUT; ++i) {
+    const uint32_t p = threadIdx.x * OUT + i;
+    len[i] = (p < a.nprobe && sk[i] != ~0ull) ? a.lens[(uint32_t)(sk[i] & 0xfffull)] : 0u;
+  }
+  Scan(tmp.scan).ExclusiveSum(len, base);
+#pragma unroll
+  for (int i = 0; i < OUT; ++i) {
+    const uint32_t p = threadIdx.x * OUT + i;
+    if (p < a.nprobe) {
+      a.probe[q * a.nprobe + p] = (uint32_t)(sk[i] & 0xfffull);
+      a.seqbase[q * a.nprobe + p] = base[i];
+    }
+  }
+  if (threadIdx.x == 0) {
+    // :165  F::from(1.2) * (nearest.distance + F::epsilon())
+    const float d0 = __uint_as_float((uint32_t)(sk[0] >> 12));
+    a.thr[q] = __fmul_rn(a.prune_factor, __fadd_rn(d0, 1.1920929e-7f));
+  }
+}
+
 }  // namespace
 
 bool scan_tc_supported(const spf_ctx* c, uint32_t ld, uint64_t nslots, uint32_t K, uint64_t npairs) {
@@ -875,9 +1030,9 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_TRY(make_map_k128(c, &map_a, A.p, (uint64_t)chunk_units * UNIT_ROWS, ld, BM));
     SPF_TRY(make_map_k128(c, &map_b, side.vtf, side.nslots, ld, BN));
     SPF_TRY(make_map_ext(c, &map_e, side.vext, side.nslots, BN));
-    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<0, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
 
     GatherArgs g;
     g.pair_sorted = call.pair_sorted; g.list_off = call.list_off; g.unit_off = uoff.p; g.nlists = nlists;
@@ -894,6 +1049,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     k.desc = desc.p; k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
     k.pairtop = pairtop.p; k.qcnt = qcnt.p; k.bucket = bucket.p;
     k.cmax = keep_cmax ? cmax.p : nullptr;
+    k.dense = nullptr; k.dense_ld = 0;
 
     {
       KernelTimer t(c, n_a);
@@ -904,8 +1060,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
         k.nunits = nu; k.u0 = u0;
         const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
-        if (topr == 16) scan_tc_kernel<false, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
-        else scan_tc_kernel<false, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        if (topr == 16) scan_tc_kernel<0, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        else scan_tc_kernel<0, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
         SPF_TRY(check_launch(c, "scan_tc_kernel<A>"));
       }
     }
@@ -956,7 +1112,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
         k.nunits = nu; k.u0 = u0;
         const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
-        scan_tc_kernel<true, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+        scan_tc_kernel<1, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
         SPF_TRY(check_launch(c, "scan_tc_kernel<B>"));
       }
     }
@@ -979,6 +1135,66 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     c->kernel_ms[pr ? "probe_tc_units" : "scan_tc_units"] = (float)nunits;
     c->kernel_ms[pr ? "probe_tc_stream_mb" : "scan_tc_stream_mb"] = (float)((double)h[2] / 1e6);
     c->kernel_ms[pr ? "probe_tc_unique_mb" : "scan_tc_unique_mb"] = (float)((double)h[3] / 1e6);
+  }
+  return SPF_OK;
+}
+
+// Dense tensor-core probe for 32 < nprobe <= 1024 and nlists <= 4096 (see probe_dense_select_kernel).
+// `side` / `centroids`: the centroid list's TF32 side structures and the exact row-major centroids.
+// Sets *redo (device) when some query must go through the exact probe instead.
+int probe_tc_dense(spf_ctx* c, const ScanTcSide& side, const float* centroids, const float* Q, uint64_t nq, uint32_t ld,
+                   uint32_t nlists, uint32_t nprobe, float prune_factor, const uint32_t* lens, uint32_t* probe,
+                   float* thr, uint32_t* seqbase, int* d_redo) {
+  cudaStream_t st = c->stream;
+  const uint32_t cslots = (uint32_t)side.nslots;
+  const uint64_t chunk = nq < 32768 ? nq : 32768;          // 512 MB of s per chunk at 4096 lists
+  const uint32_t cunits = (uint32_t)ceil_div(chunk, UNIT_ROWS);
+  DevBuf<float> qtf, qnorm, qres, S, rowthr;
+  DevBuf<uint32_t> rowseq, rowpair;
+  DevBuf<UnitDesc> desc;
+  SPF_TRY(qtf.alloc(st, (size_t)nq * ld));
+  SPF_TRY(qnorm.alloc(st, nq));
+  SPF_TRY(qres.alloc(st, nq));
+  SPF_TRY(S.alloc(st, (size_t)chunk * cslots));
+  SPF_TRY(rowthr.alloc(st, (size_t)cunits * UNIT_ROWS));
+  SPF_TRY(rowseq.alloc(st, (size_t)cunits * UNIT_ROWS));
+  SPF_TRY(rowpair.alloc(st, (size_t)cunits * UNIT_ROWS));
+  SPF_TRY(desc.alloc(st, cunits));
+  SPF_TRY(launch_row_prep(c, Q, ld, nullptr, nq, qtf.p, qnorm.p, qres.p));
+  CUtensorMap map_a, map_b, map_e;
+  SPF_TRY(make_map_k128(c, &map_b, side.vtf, side.nslots, ld, BN));
+  SPF_TRY(make_map_ext(c, &map_e, side.vext, side.nslots, BN));
+  SPF_CUDA(cudaFuncSetAttribute(scan_tc_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  for (uint64_t q0 = 0; q0 < nq; q0 += chunk) {
+    const uint32_t nc = (uint32_t)((nq - q0) < chunk ? (nq - q0) : chunk);
+    const uint32_t nu = (uint32_t)ceil_div(nc, UNIT_ROWS);
+    SPF_TRY(make_map_k128(c, &map_a, qtf.p + q0 * ld, nc, ld, BM));   // the chunk's rounded queries, no gather needed
+    dense_setup_kernel<<<(unsigned)ceil_div((uint64_t)nu * UNIT_ROWS, 256), 256, 0, st>>>(nu, nc, cslots, desc.p, rowthr.p,
+                                                                                          rowseq.p, rowpair.p);
+    SPF_TRY(check_launch(c, "dense_setup_kernel"));
+    ScanTcArgs k;
+    k.nunits = nu; k.kb = (ld + BK - 1) / BK; k.nprobe = 1; k.cap = 0; k.u0 = 0;
+    k.desc = desc.p; k.cmax = nullptr; k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
+    k.pairtop = nullptr; k.qcnt = nullptr; k.bucket = nullptr;
+    k.dense = S.p; k.dense_ld = cslots;
+    {
+      KernelTimer t(c, "probe_tc_dense");
+      const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
+      scan_tc_kernel<2, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+      SPF_TRY(check_launch(c, "scan_tc_kernel<dense>"));
+    }
+    DenseSelArgs a;
+    a.S = S.p; a.s_ld = cslots; a.Q = Q + q0 * ld; a.C = centroids; a.ld = ld;
+    a.qnorm = qnorm.p + q0; a.qres = qres.p + q0; a.vstat = side.vstat;
+    a.nlists = nlists; a.nprobe = nprobe; a.prune_factor = prune_factor;
+    a.lens = lens; a.probe = probe + q0 * nprobe; a.thr = thr + q0; a.seqbase = seqbase + q0 * nprobe; a.redo = d_redo;
+    {
+      KernelTimer t(c, "probe_tc_select");
+      if (nprobe <= 192) probe_dense_select_kernel<16, 1><<<nc, 256, 0, st>>>(a);
+      else if (nprobe <= 448) probe_dense_select_kernel<16, 2><<<nc, 256, 0, st>>>(a);
+      else probe_dense_select_kernel<16, 5><<<nc, 256, 0, st>>>(a);
+      SPF_TRY(check_launch(c, "probe_dense_select_kernel"));
+    }
   }
   return SPF_OK;
 }

@@ -1060,23 +1060,39 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   // distances in query chunks followed by a selection kernel.
   bool probed = false;
   const uint32_t cslots = round_up(nlists, 32);
-  if (c->params.scan_tc != 0 && nprobe <= 32 && scan_tc_supported(c, ld, cslots, nprobe, nq) &&
-      (c->params.scan_tc == 2 || (nq >= 2048 && nlists >= 512))) {
+  const bool tc_probe_ok = c->params.scan_tc != 0 && scan_tc_supported(c, ld, cslots, nprobe <= 32 ? nprobe : 1, nq) &&
+                           (c->params.scan_tc == 2 || (nq >= 2048 && nlists >= 512));
+  auto centroid_side = [&]() -> int {      // the centroids as one posting list + TF32 side structures, once
+    if (idx->ctc.ready) return SPF_OK;
+    const uint64_t hg[2] = {0, cslots / 32};
+    SPF_CUDA(cudaMalloc((void**)&idx->cvecs, (size_t)cslots * ld * sizeof(float)));
+    SPF_CUDA(cudaMalloc((void**)&idx->cids, (size_t)cslots * sizeof(uint64_t)));
+    SPF_CUDA(cudaMalloc((void**)&idx->cgrp, 2 * sizeof(uint64_t)));
+    SPF_CUDA(cudaMalloc((void**)&idx->clens, sizeof(uint32_t)));
+    SPF_CUDA(cudaMemcpyAsync(idx->cgrp, hg, sizeof(hg), cudaMemcpyHostToDevice, st));
+    SPF_CUDA(cudaMemcpyAsync(idx->clens, &nlists, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    rows_to_slots_kernel<<<(unsigned)ceil_div((uint64_t)cslots * (ld / 4), 256), 256, 0, st>>>(
+        idx->centroids, ld / 4, nlists, cslots, idx->cvecs, idx->cids);
+    SPF_TRY(check_launch(c, "rows_to_slots_kernel"));
+    SPF_CUDA(cudaStreamSynchronize(st));     // hg / nlists are stack variables
+    return scan_tc_prepare(c, idx->cvecs, idx->cids, cslots, ld, &idx->ctc);
+  };
+  if (tc_probe_ok && nprobe > 32 && nlists <= 4096) {
+    // dense TF32 s of every query against every centroid, selection with the certified bound
     KernelTimer t(c, "probe");
-    if (!idx->ctc.ready) {
-      const uint64_t hg[2] = {0, cslots / 32};
-      SPF_CUDA(cudaMalloc((void**)&idx->cvecs, (size_t)cslots * ld * sizeof(float)));
-      SPF_CUDA(cudaMalloc((void**)&idx->cids, (size_t)cslots * sizeof(uint64_t)));
-      SPF_CUDA(cudaMalloc((void**)&idx->cgrp, 2 * sizeof(uint64_t)));
-      SPF_CUDA(cudaMalloc((void**)&idx->clens, sizeof(uint32_t)));
-      SPF_CUDA(cudaMemcpyAsync(idx->cgrp, hg, sizeof(hg), cudaMemcpyHostToDevice, st));
-      SPF_CUDA(cudaMemcpyAsync(idx->clens, &nlists, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-      rows_to_slots_kernel<<<(unsigned)ceil_div((uint64_t)cslots * (ld / 4), 256), 256, 0, st>>>(
-          idx->centroids, ld / 4, nlists, cslots, idx->cvecs, idx->cids);
-      SPF_TRY(check_launch(c, "rows_to_slots_kernel"));
-      SPF_CUDA(cudaStreamSynchronize(st));     // hg / nlists are stack variables
-      SPF_TRY(scan_tc_prepare(c, idx->cvecs, idx->cids, cslots, ld, &idx->ctc));
-    }
+    SPF_TRY(centroid_side());
+    DevBuf<int> redo;
+    SPF_TRY(redo.alloc(st, 1));
+    SPF_CUDA(cudaMemsetAsync(redo.p, 0, sizeof(int), st));
+    SPF_TRY(probe_tc_dense(c, idx->ctc, idx->centroids, Q.p, nq, ld, nlists, nprobe, prune_factor, idx->lens, probe.p,
+                           thr.p, seqbase.p, redo.p));
+    int h_redo = 0;
+    SPF_CUDA(cudaMemcpyAsync(&h_redo, redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+    probed = h_redo == 0;
+  } else if (tc_probe_ok && nprobe <= 32) {
+    KernelTimer t(c, "probe");
+    SPF_TRY(centroid_side());
     DevBuf<uint32_t> zero, pairs, loff2, p_counts;
     DevBuf<float> thr_inf, p_dists;
     DevBuf<uint64_t> p_ids;

@@ -597,13 +597,17 @@ def test_search_probe_selection_large_nprobe(spf, oracle, nprobe):
         ds = spf.Dataset(c2, data)
         idx = spf.DeviceIndex.pack(ds, r.offsets, r.members, cent)
         q = clustered(64, 8, 30, 404)
-        c2.set_param("scan_tc", 0)
-        ids, dists, counts, keys = idx.search(q, 10, nprobe, prune_factor=float("inf"), want_keys=True)
         rid, rd, rc = oracle.search_batch(data, r.offsets, r.members, cent, q, 10, nprobe, prune_factor=float("inf"))
-        assert np.array_equal(counts, rc)
-        for i in range(64):
-            assert np.array_equal(ids[i, :rc[i]], rid[i, :rc[i]]), i
-            assert np.array_equal(dists[i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32)), i
+        for mode in (0, 2):              # exact selection kernel / tensor-core probe (dense variant for nprobe > 32)
+            c2.set_param("scan_tc", mode)
+            c2.set_profiling(True)
+            ids, dists, counts, keys = idx.search(q, 10, nprobe, prune_factor=float("inf"), want_keys=True)
+            assert (c2.kernel_ms("probe_tc_select") > 0) == (mode == 2 and nprobe > 32)
+            c2.set_profiling(False)
+            assert np.array_equal(counts, rc)
+            for i in range(64):
+                assert np.array_equal(ids[i, :rc[i]], rid[i, :rc[i]]), (mode, i)
+                assert np.array_equal(dists[i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32)), (mode, i)
         idx.free()
         ds.free()
     finally:
