@@ -124,7 +124,9 @@ def sweep(args):
             else:
                 rec["scan_path"] = "exact CUDA-core scan"
                 rec["scan_fp32_frac"] = lane / (scan_ms * 1e-3) / FP32_PEAK
-            rec["probe_path"] = "tcgen05" if ctx.kernel_ms("probe_tc_a") > 0 else "exact CUDA-core"
+            rec["probe_path"] = ("tcgen05 candidate scan over the centroid list" if ctx.kernel_ms("probe_tc_a") > 0 else
+                                 "tcgen05 dense s matrix + certified selection" if ctx.kernel_ms("probe_tc_select") > 0 else
+                                 "exact CUDA-core")
             print(json.dumps(rec), flush=True)
 
 
