@@ -258,22 +258,104 @@ kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const f
   }
 }
 
-// :278 `distances.iter().fold(F::zero(), |acc, &x| acc + x)` — a strictly sequential f32 sum.
-// One thread walks the array; loads are issued 16 ahead so only the add chain is serial.
-__global__ void seq_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float acc = 0.0f;
-  uint64_t i = 0;
-  const float4* v4 = reinterpret_cast<const float4*>(v);
-  for (; i + 16 <= n; i += 16) {
-    const float4 a = v4[i / 4], b = v4[i / 4 + 1], c = v4[i / 4 + 2], d = v4[i / 4 + 3];
-    acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
-    acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
-    acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
-    acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
+// The same update for ld <= 448 at HBM rate: a CTA stages 128 rows in shared memory with coalesced
+// 16-byte cp.async copies (row pitch ld + 4 floats: conflict-free 128-bit reads per quarter warp),
+// then thread r walks row r in dimension order — the reference's sequential f32 chain — against the
+// centroid held in shared memory.
+constexpr int KU_ROWS = 128;
+template <int METRIC>
+__global__ void __launch_bounds__(KU_ROWS)
+kmpp_update_tiled_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const float* __restrict__ cvec, int first,
+                         float* __restrict__ mind) {
+  extern __shared__ __align__(16) float ku_smem[];
+  const uint32_t ld4 = ld / 4, pitch4 = ld4 + 1;           // in float4 units
+  float4* s_c = reinterpret_cast<float4*>(ku_smem);         // the centroid, ld4 float4
+  float4* s_x = s_c + ld4;                                  // KU_ROWS x pitch4
+  for (uint32_t c = threadIdx.x; c < ld4; c += KU_ROWS) s_c[c] = reinterpret_cast<const float4*>(cvec)[c];
+  const uint64_t ntiles = (n + KU_ROWS - 1) / KU_ROWS;
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint64_t row0 = t * KU_ROWS;
+    const uint32_t rows = (uint32_t)((n - row0) < (uint64_t)KU_ROWS ? (n - row0) : (uint64_t)KU_ROWS);
+    __syncthreads();                                        // the previous tile is consumed (and s_c is written)
+    const float4* src = reinterpret_cast<const float4*>(X) + row0 * ld4;
+    for (uint32_t w = threadIdx.x; w < rows * ld4; w += KU_ROWS) {
+      const uint32_t r = w / ld4, c = w - r * ld4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_x + r * pitch4 + c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + w) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < rows) {
+      const float4* xr = s_x + threadIdx.x * pitch4;
+      float acc = 0.0f;
+#pragma unroll 4
+      for (uint32_t c = 0; c < ld4; ++c) {
+        const float4 a = xr[c], b = s_c[c];
+        acc = dist_step<METRIC>(acc, a.x, b.x);
+        acc = dist_step<METRIC>(acc, a.y, b.y);
+        acc = dist_step<METRIC>(acc, a.z, b.z);
+        acc = dist_step<METRIC>(acc, a.w, b.w);
+      }
+      const uint64_t i = row0 + threadIdx.x;
+      if (first || acc < mind[i]) mind[i] = acc;
+    }
   }
-  for (; i < n; ++i) acc = __fadd_rn(acc, v[i]);
-  out[0] = acc;
+}
+
+unsigned pd_grid(spf_ctx* c, uint64_t count);
+
+// Launches the tiled kernel when the row fits its shared-memory tile, the generic one otherwise.
+template <int METRIC>
+int launch_kmpp_update(spf_ctx* c, const float* X, uint32_t ld, uint64_t n, const float* cvec, int first, float* mind) {
+  const size_t smem = ((size_t)(ld / 4) + (size_t)KU_ROWS * (ld / 4 + 1)) * sizeof(float4);
+  if (smem <= 72 * 1024) {                                  // three CTAs per SM
+    SPF_CUDA(cudaFuncSetAttribute(kmpp_update_tiled_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t ntiles = (n + KU_ROWS - 1) / KU_ROWS;
+    const uint64_t cap = (uint64_t)c->sm_count * 3 * 4;
+    kmpp_update_tiled_kernel<METRIC><<<(unsigned)(ntiles < cap ? ntiles : cap), KU_ROWS, smem, c->stream>>>(X, ld, n, cvec, first, mind);
+  } else {
+    kmpp_update_kernel<METRIC><<<pd_grid(c, n), PD_THREADS, 0, c->stream>>>(X, ld, n, cvec, first, mind);
+  }
+  return check_launch(c, "kmpp_update_kernel");
+}
+
+// :278 `distances.iter().fold(F::zero(), |acc, &x| acc + x)` — a strictly sequential f32 sum.
+// Only the add chain is serial: the other threads of the block stage the next tile in shared
+// memory (double buffered) while thread 0 folds the current one, so the cost is the 4-cycle FADD
+// latency per element, not a global-memory round trip per 16 elements.
+constexpr int SEQ_TILE = 4096;       // floats per tile
+constexpr int SEQ_THREADS = 256;
+__global__ void __launch_bounds__(SEQ_THREADS) seq_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+  __shared__ __align__(16) float buf[2][SEQ_TILE];
+  const uint64_t ntiles = (n + SEQ_TILE - 1) / SEQ_TILE;
+  auto stage = [&](uint64_t t, int b) {            // threads 1.. load tile t (the fold only reads the valid part)
+    const uint64_t base = t * SEQ_TILE;
+    for (uint32_t i = threadIdx.x - 1; i < (uint32_t)SEQ_TILE; i += SEQ_THREADS - 1)
+      buf[b][i] = base + i < n ? v[base + i] : 0.0f;
+  };
+  if (threadIdx.x != 0 && ntiles) stage(0, 0);
+  __syncthreads();
+  float acc = 0.0f;
+  for (uint64_t t = 0; t < ntiles; ++t) {
+    const int b = (int)(t & 1);
+    if (threadIdx.x != 0) {
+      if (t + 1 < ntiles) stage(t + 1, b ^ 1);
+    } else {
+      const uint64_t left = n - t * SEQ_TILE;
+      const uint32_t cnt = left < (uint64_t)SEQ_TILE ? (uint32_t)left : (uint32_t)SEQ_TILE;
+      const float4* b4 = reinterpret_cast<const float4*>(buf[b]);
+      uint32_t i = 0;
+#pragma unroll 4
+      for (; i + 4 <= cnt; i += 4) {
+        const float4 x = b4[i / 4];
+        acc = __fadd_rn(acc, x.x); acc = __fadd_rn(acc, x.y); acc = __fadd_rn(acc, x.z); acc = __fadd_rn(acc, x.w);
+      }
+      for (; i < cnt; ++i) acc = __fadd_rn(acc, buf[b][i]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = acc;
 }
 
 // Deterministic tree sum (fast mode: picks equal the reference's only up to near-ties).
@@ -323,30 +405,84 @@ kmpp_block_sums_kernel(const float* __restrict__ mind, uint64_t n, const float* 
 }
 
 // cumulative_weights.partition_point(|w| w <= u) with u = u01 * total (rand 0.9 WeightedIndex).
-__global__ void kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
-                                 const double* __restrict__ block_sums, uint64_t nblocks,
-                                 const int* __restrict__ bad, double u01, double target, uint64_t* __restrict__ res,
-                                 double* __restrict__ d_total) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// The three walks (total of the block sums, the block where the cumulative sum crosses u, the
+// element inside that block) are strictly sequential f64 chains on thread 0; the other threads of
+// the block stage what it reads next in shared memory, so no step waits for global memory.
+constexpr int PICK_THREADS = 256;
+constexpr int PICK_TILE = 1024;      // block sums per staged tile
+__global__ void __launch_bounds__(PICK_THREADS)
+kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
+                 const double* __restrict__ block_sums, uint64_t nblocks,
+                 const int* __restrict__ bad, double u01, double target, uint64_t* __restrict__ res,
+                 double* __restrict__ d_total) {
+  __shared__ double sd[2][PICK_TILE];
+  __shared__ float sf[WBLOCK];
+  __shared__ int s_stop;
+  __shared__ double s_u, s_cum;
+  __shared__ unsigned long long s_b;
+  const uint64_t ntiles = (nblocks + PICK_TILE - 1) / PICK_TILE;
+  auto stage = [&](uint64_t t, int b) {
+    const uint64_t base = t * PICK_TILE;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)PICK_TILE; i += PICK_THREADS)
+      sd[b][i] = base + i < nblocks ? block_sums[base + i] : 0.0;
+  };
+  // ---- total = block sums added in order
   double total = 0.0;
-  for (uint64_t b = 0; b < nblocks; ++b) total += block_sums[b];
-  d_total[0] = total;
-  if (*bad || total == 0.0 || !isfinite(total)) { res[0] = 1; res[1] = 0; return; }
-  const double u = target >= 0.0 ? target : u01 * total;   // sharded pick: target already relative to this shard
-  const float denom = fmaxf(d_sum[0], 1e-10f);
-  double cum = 0.0;
-  uint64_t b = 0;
-  for (; b + 1 < nblocks; ++b) {
-    if (!(cum + block_sums[b] <= u)) break;
-    cum += block_sums[b];
+  if (ntiles) stage(0, 0);
+  __syncthreads();
+  for (uint64_t t = 0; t < ntiles; ++t) {
+    const int b = (int)(t & 1);
+    if (t + 1 < ntiles) stage(t + 1, b ^ 1);
+    if (threadIdx.x == 0) {
+      const uint64_t left = nblocks - t * PICK_TILE;
+      const uint32_t cnt = left < (uint64_t)PICK_TILE ? (uint32_t)left : (uint32_t)PICK_TILE;
+      for (uint32_t i = 0; i < cnt; ++i) total += sd[b][i];
+    }
+    __syncthreads();
   }
-  uint64_t idx = n - 1;
-  const uint64_t lo = b * WBLOCK;
+  if (threadIdx.x == 0) {
+    d_total[0] = total;
+    s_stop = 0;
+    if (*bad || total == 0.0 || !isfinite(total)) { res[0] = 1; res[1] = 0; s_stop = 2; }
+    s_u = target >= 0.0 ? target : u01 * total;   // sharded pick: target already relative to this shard
+    s_cum = 0.0;
+    s_b = 0;
+  }
+  __syncthreads();
+  if (s_stop == 2) return;
+  const double u = s_u;
+  // ---- the block where the cumulative sum crosses u (the last block takes what is left)
+  if (ntiles) stage(0, 0);
+  __syncthreads();
+  for (uint64_t t = 0; t < ntiles && s_stop == 0; ++t) {
+    const int b = (int)(t & 1);
+    if (t + 1 < ntiles) stage(t + 1, b ^ 1);
+    if (threadIdx.x == 0) {
+      double cum = s_cum;
+      uint64_t bi = t * PICK_TILE;
+      const uint64_t end = bi + PICK_TILE < nblocks ? bi + PICK_TILE : nblocks;
+      for (; bi < end; ++bi) {
+        if (bi + 1 >= nblocks || !(cum + sd[b][bi - t * PICK_TILE] <= u)) { s_stop = 1; break; }
+        cum += sd[b][bi - t * PICK_TILE];
+      }
+      s_cum = cum;
+      s_b = bi;
+    }
+    __syncthreads();
+  }
+  // ---- the element inside that block
+  const uint64_t lo = (uint64_t)s_b * WBLOCK;
   uint64_t hi = lo + WBLOCK;
   if (hi > n) hi = n;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += PICK_THREADS) sf[i - lo] = mind[i];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const float denom = fmaxf(d_sum[0], 1e-10f);
+  double cum = s_cum;
+  uint64_t idx = n - 1;
   bool found = false;
   for (uint64_t i = lo; i < hi && i + 1 < n; ++i) {
-    cum += (double)kmpp_weight(mind[i], denom);
+    cum += (double)kmpp_weight(sf[i - lo], denom);
     if (!(cum <= u)) { idx = i; found = true; break; }
   }
   if (!found) {       // rounding pushed the crossing into a later block: continue sequentially
@@ -664,16 +800,14 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
     KernelTimer t(c, "kmpp_update");
     const int first = s->rounds == 0 ? 1 : 0;
     SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
-      kmpp_update_kernel<decltype(M)::value><<<pd_grid(c, n), PD_THREADS, 0, st>>>(
-          ds->x, ds->ld, n, ds->x + (size_t)s->newest * ds->ld, first, s->mind);
-      return check_launch(c, "kmpp_update_kernel");
+      return launch_kmpp_update<decltype(M)::value>(c, ds->x, ds->ld, n, ds->x + (size_t)s->newest * ds->ld, first, s->mind);
     }));
   }
   s->rounds += 1;
   s->pending = false;
   {
     KernelTimer t(c, "kmpp_sum");
-    if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum);
+    if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
     else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
     SPF_TRY(check_launch(c, "kmpp sum kernel"));
   }
@@ -682,7 +816,7 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
     SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
     kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->bad);
     SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
-    kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, u01, -1.0, s->res, s->d_total);
+    kmpp_pick_kernel<<<1, PICK_THREADS, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, u01, -1.0, s->res, s->d_total);
     SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
   }
   uint64_t res[2] = {0, 0};
@@ -722,11 +856,10 @@ int spf_kmpp_fold_vector(spf_kmpp* s, const float* centroid, float* local_sum) {
   SPF_CUDA(cudaMemcpyAsync(s->d_vec, centroid, (size_t)ds->d * sizeof(float), cudaMemcpyHostToDevice, st));
   const int first = s->rounds == 0 ? 1 : 0;
   SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
-    kmpp_update_kernel<decltype(M)::value><<<pd_grid(c, n), PD_THREADS, 0, st>>>(ds->x, ds->ld, n, s->d_vec, first, s->mind);
-    return check_launch(c, "kmpp_update_kernel");
+    return launch_kmpp_update<decltype(M)::value>(c, ds->x, ds->ld, n, s->d_vec, first, s->mind);
   }));
   s->rounds += 1;
-  if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, 32, 0, st>>>(s->mind, n, s->d_sum);
+  if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
   else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
   SPF_TRY(check_launch(c, "kmpp sum kernel"));
   SPF_CUDA(cudaMemcpyAsync(local_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -746,7 +879,7 @@ int spf_kmpp_weight_total(spf_kmpp* s, float global_sum, double* local_total) {
   kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->bad);
   SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
   // total + validity through the pick kernel (target beyond the total: the pick itself is discarded)
-  kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, 0.0, s->res, s->d_total);
+  kmpp_pick_kernel<<<1, PICK_THREADS, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, 0.0, s->res, s->d_total);
   SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
   uint64_t res[2] = {0, 0};
   SPF_CUDA(cudaMemcpyAsync(res, s->res, sizeof(res), cudaMemcpyDeviceToHost, st));
@@ -766,7 +899,7 @@ int spf_kmpp_pick_local(spf_kmpp* s, double target, uint64_t* row) {
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   // block sums and the global denominator are those of the preceding spf_kmpp_weight_total
-  kmpp_pick_kernel<<<1, 32, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, target, s->res, s->d_total);
+  kmpp_pick_kernel<<<1, PICK_THREADS, 0, st>>>(s->mind, ds->n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, target, s->res, s->d_total);
   SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
   uint64_t res[2] = {0, 0};
   SPF_CUDA(cudaMemcpyAsync(res, s->res, sizeof(res), cudaMemcpyDeviceToHost, st));
