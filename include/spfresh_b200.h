@@ -263,8 +263,13 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
  * "scan_list_major" (0 query-major, 1 automatic, 2 list-major), "scan_tc" (tensor-core candidate
  * scan: 0 never, 1 automatic, 2 whenever supported), "scan_tc_bucket" (candidates per query, default
  * 256), "scan_tc_tau_probes" (0 = all), "scan_tc_cmax_mb" (budget for the one-pass variant, 0 = two GEMM passes), "force_exact", "tc_min_k", "tc_min_m",
- * "kmpp_exact_sum" (1: sequential f32 sum, bit-parity; 0: tree sum), "cc_matrix_max_k". */
+ * "kmpp_exact_sum" (1: sequential f32 sum by scan, 2: by the serial add chain — same bits; 0: tree sum), "cc_matrix_max_k". */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
+
+/* Test hook: the strictly sequential f32 fold of hierarchical.rs:278 over n host values.  mode 1 is
+ * the scan-based kernel the k-means++ rounds use ("kmpp_exact_sum" = 1), mode 2 the serial add
+ * chain it must equal bit for bit. */
+int spf_seq_sum_f32(spf_ctx* ctx, const float* values, uint64_t n, int mode, float* out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -64,6 +64,7 @@ SIGNATURES = {
     "spf_kmpp_weight_total": (C.c_int, [_vp, C.c_float, C.POINTER(C.c_double)]),
     "spf_kmpp_pick_local": (C.c_int, [_vp, C.c_double, _u64p]),
     "spf_kmpp_free": (None, [_vp]),
+    "spf_seq_sum_f32": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _f32p]),
     "spf_farthest": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, _u64p]),
     "spf_farthest_from": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, C.c_uint64, _f32p, _u64p]),
     "spf_index_pack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vpp]),

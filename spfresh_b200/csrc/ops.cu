@@ -358,6 +358,215 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_sum_kernel(const float* __res
   if (threadIdx.x == 0) out[0] = acc;
 }
 
+// The same sequential f32 sum, bit for bit, without a serial chain over the elements.
+//
+// For finite x >= 0 the running sum acc only grows.  While acc stays inside one binade
+// [2^e, 2^(e+1)) it is an integer multiple A of u = ulp(acc), and fl(acc + x) = u * (A + k) where k
+// is x / u rounded to an integer (round-half-to-even on A + floor(x/u)).  k depends on acc only
+// through the parity of A, so a run of elements is a two-state transducer (parity in -> sum of k,
+// parity out); transducers compose associatively, which turns the fold into a scan.  The element
+// whose addition reaches the next binade is added with the hardware FADD and the scan restarts
+// behind it with the new ulp: the sum crosses ~25 binades, so a 1 M element fold costs ~150 block
+// iterations instead of 1 M dependent adds.  Anything else (negative or non-finite input) drops to
+// the serial fold from the current position, and so does a sum that is already infinite.
+constexpr int FS_THREADS = 1024;
+constexpr int FS_RUN = 16;                              // consecutive elements per thread
+constexpr int FS_WINDOW = FS_THREADS * FS_RUN;
+constexpr int FS_SMEM = (FS_WINDOW + FS_WINDOW / 32) * 4;   // dynamic shared memory of the staging buffer
+
+struct FsSumm { unsigned long long k0, k1; uint32_t po; };   // po: bit p = parity out for parity in p
+
+__device__ __forceinline__ FsSumm fs_compose(const FsSumm& a, const FsSumm& b) {   // a first, then b
+  FsSumm r;
+  const uint32_t m0 = a.po & 1u, m1 = (a.po >> 1) & 1u;
+  r.k0 = a.k0 + (m0 ? b.k1 : b.k0);
+  r.k1 = a.k1 + (m1 ? b.k1 : b.k0);
+  r.po = ((b.po >> m0) & 1u) | (((b.po >> m1) & 1u) << 1);
+  return r;
+}
+
+__global__ void __launch_bounds__(FS_THREADS) seq_sum_scan_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+  extern __shared__ float fs_buf[];                     // FS_WINDOW + FS_WINDOW / 32 staged values
+  __shared__ FsSumm s_lane[FS_THREADS];                 // per thread: its exclusive prefix inside the warp
+  __shared__ FsSumm s_warp[FS_THREADS / 32];
+  __shared__ unsigned long long s_wk[FS_THREADS / 32];  // prefix of the warps for the actual parity
+  __shared__ uint32_t s_wp[FS_THREADS / 32];
+  __shared__ unsigned long long s_cross, s_ktotal;
+  __shared__ unsigned long long s_pos;
+  __shared__ uint32_t s_acc;                            // bits of the running sum
+  __shared__ int s_bad;
+  const uint32_t LIMIT = 1u << 24;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { s_pos = 0; s_acc = 0; s_bad = 0; }
+  __syncthreads();
+  while (true) {
+    const uint64_t pos = s_pos;
+    const uint32_t accb = s_acc;
+    if (pos >= n || s_bad || (accb >> 23) == 255u) break;
+    // the binade of acc: A = acc / u as an integer, ulp exponent from max(E, 1)
+    const uint32_t Ea = accb >> 23;
+    const uint32_t Eeff = Ea ? Ea : 1u;
+    const uint32_t A0 = Ea ? ((accb & 0x7fffffu) | 0x800000u) : accb;
+    // ---- my run: floor(x/u), rounding direction / tie flag per element
+    uint32_t F[FS_RUN];
+    uint32_t gt = 0, tie = 0;
+    bool bad = false;
+    // the window goes through shared memory: coalesced global loads, then every thread reads its
+    // run (one pad word per 32 keeps the 16-float runs on distinct banks)
+#pragma unroll
+    for (int r = 0; r < FS_RUN; ++r) {
+      const uint32_t w = (uint32_t)r * FS_THREADS + threadIdx.x;
+      const uint64_t i = pos + w;
+      fs_buf[w + (w >> 5)] = i < n ? v[i] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < FS_RUN; ++r) {
+      const uint32_t w = threadIdx.x * FS_RUN + (uint32_t)r;
+      const uint32_t xb = __float_as_uint(fs_buf[w + (w >> 5)]);
+      const uint32_t Ex = (xb >> 23) & 0xffu;
+      if ((xb >> 31) && (xb << 1)) bad = true;          // negative (−0 counts as 0)
+      if (Ex == 255u) bad = true;                       // inf / NaN
+      const uint32_t mx = Ex ? ((xb & 0x7fffffu) | 0x800000u) : (xb & 0x7fffffu);
+      const uint32_t Exeff = Ex ? Ex : 1u;
+      uint32_t f = 0;
+      if (Exeff > Eeff) {
+        f = LIMIT;                                      // x alone reaches the next binade
+      } else if (Exeff == Eeff) {
+        f = mx;
+      } else {
+        const uint32_t sh = Eeff - Exeff;
+        if (sh <= 25u) {
+          f = mx >> sh;
+          const uint32_t rem = mx & ((1u << sh) - 1u), half = 1u << (sh - 1u);
+          gt |= (rem > half ? 1u : 0u) << r;
+          tie |= (rem == half ? 1u : 0u) << r;
+        }
+      }
+      F[r] = f;
+    }
+    if (bad) s_bad = 1;
+    FsSumm me;
+    if (tie == 0) {                                     // no half-way case in the run: k does not depend on the parity
+      unsigned long long K = (unsigned long long)__popc(gt);
+#pragma unroll
+      for (int r = 0; r < FS_RUN; ++r) K += F[r];
+      me.k0 = K; me.k1 = K;
+      me.po = (uint32_t)(K & 1ull) | ((uint32_t)((K + 1ull) & 1ull) << 1);
+    } else {
+      unsigned long long k[2];
+      uint32_t po = 0;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        unsigned long long K = 0;
+        uint32_t par = (uint32_t)p;
+#pragma unroll
+        for (int r = 0; r < FS_RUN; ++r) {
+          const uint32_t kk = F[r] + (((tie >> r) & 1u) ? ((par + F[r]) & 1u) : ((gt >> r) & 1u));
+          K += kk;
+          par = (par + kk) & 1u;
+        }
+        k[p] = K;
+        po |= par << p;
+      }
+      me.k0 = k[0]; me.k1 = k[1]; me.po = po;
+    }
+    if (threadIdx.x == 0) s_cross = ~0ull;
+    __syncthreads();
+    if (s_bad) break;
+    // ---- exclusive prefixes: a shuffle scan of the transducers inside each warp, then over the warps
+    {
+      FsSumm inc = me;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        FsSumm l;
+        l.k0 = __shfl_up_sync(0xffffffffu, inc.k0, d);
+        l.k1 = __shfl_up_sync(0xffffffffu, inc.k1, d);
+        l.po = __shfl_up_sync(0xffffffffu, inc.po, d);
+        if (lane >= d) inc = fs_compose(l, inc);
+      }
+      FsSumm ex;                                           // exclusive = inclusive of the lane before
+      ex.k0 = __shfl_up_sync(0xffffffffu, inc.k0, 1);
+      ex.k1 = __shfl_up_sync(0xffffffffu, inc.k1, 1);
+      ex.po = __shfl_up_sync(0xffffffffu, inc.po, 1);
+      if (lane == 0) { ex.k0 = 0; ex.k1 = 0; ex.po = 2u; }  // identity: parity out = parity in
+      s_lane[threadIdx.x] = ex;
+      if (lane == 31) s_warp[warp] = inc;
+    }
+    __syncthreads();
+    if (warp == 0) {                                        // the 32 warp totals: one more shuffle scan
+      static_assert(FS_THREADS / 32 == 32, "one lane per warp total");
+      FsSumm inc = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        FsSumm l;
+        l.k0 = __shfl_up_sync(0xffffffffu, inc.k0, d);
+        l.k1 = __shfl_up_sync(0xffffffffu, inc.k1, d);
+        l.po = __shfl_up_sync(0xffffffffu, inc.po, d);
+        if (lane >= d) inc = fs_compose(l, inc);
+      }
+      FsSumm ex;
+      ex.k0 = __shfl_up_sync(0xffffffffu, inc.k0, 1);
+      ex.k1 = __shfl_up_sync(0xffffffffu, inc.k1, 1);
+      ex.po = __shfl_up_sync(0xffffffffu, inc.po, 1);
+      if (lane == 0) { ex.k0 = 0; ex.k1 = 0; ex.po = 2u; }
+      const uint32_t p0 = A0 & 1u;                          // evaluated for the parity the window starts with
+      s_wk[lane] = p0 ? ex.k1 : ex.k0;
+      s_wp[lane] = (ex.po >> p0) & 1u;
+      if (lane == 31) s_ktotal = p0 ? inc.k1 : inc.k0;
+    }
+    __syncthreads();
+    // ---- second walk with the actual A: the first element whose addition reaches the next binade
+    {
+      const uint32_t wp = s_wp[warp];
+      const FsSumm pre = s_lane[threadIdx.x];
+      unsigned long long A = (unsigned long long)A0 + s_wk[warp] + (wp ? pre.k1 : pre.k0);
+      // k >= 0, so the run can only reach the next binade if its end does
+      const unsigned long long mine = ((uint32_t)A & 1u) ? me.k1 : me.k0;
+      if (A < LIMIT && A + mine >= LIMIT) {
+#pragma unroll
+      for (int r = 0; r < FS_RUN; ++r) {
+        const uint32_t kk = F[r] + (((tie >> r) & 1u) ? (((uint32_t)A + F[r]) & 1u) : ((gt >> r) & 1u));
+        if (A + kk >= LIMIT) {
+          if (A < LIMIT)                                  // prefixes behind an earlier crossing are meaningless
+            atomicMin(&s_cross, ((unsigned long long)(threadIdx.x * FS_RUN + r) << 32) | A);
+          break;
+        }
+        A += kk;
+      }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long cr = s_cross;
+      auto to_bits = [&](uint32_t A) { return A < 0x800000u ? A : ((Eeff << 23) | (A & 0x7fffffu)); };
+      if (cr == ~0ull) {                                  // the whole window stays in this binade
+        s_acc = to_bits((uint32_t)(A0 + s_ktotal));
+        s_pos = pos + FS_WINDOW;
+      } else {
+        const uint32_t ci = (uint32_t)(cr >> 32);
+        const float before = __uint_as_float(to_bits((uint32_t)(cr & 0xffffffffull)));
+        s_acc = __float_as_uint(__fadd_rn(before, fs_buf[ci + (ci >> 5)]));
+        s_pos = pos + ci + 1;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // serial tail (empty in the normal case): negative / non-finite input or an infinite sum
+  if (threadIdx.x == 0) {
+    float acc = __uint_as_float(s_acc);
+    for (uint64_t i = s_pos; i < n; ++i) acc = __fadd_rn(acc, v[i]);
+    out[0] = acc;
+  }
+}
+
+int launch_seq_sum_scan(spf_ctx* c, const float* v, uint64_t n, float* out) {
+  SPF_CUDA(cudaFuncSetAttribute(seq_sum_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+  seq_sum_scan_kernel<<<1, FS_THREADS, FS_SMEM, c->stream>>>(v, n, out);
+  return SPF_OK;
+}
+
 // Deterministic tree sum (fast mode: picks equal the reference's only up to near-ties).
 __global__ void tree_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
   __shared__ double sm[1024];
@@ -757,6 +966,29 @@ int spf_distance_pairs(spf_ctx* c, int metric, const float* a, const float* b, u
   return SPF_OK;
 }
 
+// The fold of hierarchical.rs:278 on its own (test hook for the scan-based kernel): mode 1 = scan,
+// 2 = serial chain.  Both must return the same bits for any input.
+int spf_seq_sum_f32(spf_ctx* c, const float* values, uint64_t n, int mode, float* out) {
+  if (!c || !out || (n && !values)) return fail(SPF_E_INVALID, "spf_seq_sum_f32: NULL argument");
+  if (mode != 1 && mode != 2) return fail(SPF_E_INVALID, "mode must be 1 (scan) or 2 (serial)");
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  DevBuf<float> d_v, d_out;
+  SPF_TRY(d_v.alloc(st, n));
+  SPF_TRY(d_out.alloc(st, 1));
+  if (n) SPF_CUDA(cudaMemcpyAsync(d_v.p, values, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  {
+    KernelTimer t(c, "seq_sum");
+    if (mode == 1) SPF_TRY(launch_seq_sum_scan(c, d_v.p, n, d_out.p));
+    else seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(d_v.p, n, d_out.p);
+    SPF_TRY(check_launch(c, "seq_sum kernel"));
+  }
+  SPF_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  return SPF_OK;
+}
+
 // ---- k-means++ session ----------------------------------------------------------------------
 int spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** out) {
   if (!ds || !out) return fail(SPF_E_INVALID, "spf_kmpp_begin: NULL argument");
@@ -807,7 +1039,8 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
   s->pending = false;
   {
     KernelTimer t(c, "kmpp_sum");
-    if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
+    if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_seq_sum_scan(c, s->mind, n, s->d_sum));
+    else if (c->params.kmpp_exact_sum == 2) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
     else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
     SPF_TRY(check_launch(c, "kmpp sum kernel"));
   }
@@ -859,7 +1092,8 @@ int spf_kmpp_fold_vector(spf_kmpp* s, const float* centroid, float* local_sum) {
     return launch_kmpp_update<decltype(M)::value>(c, ds->x, ds->ld, n, s->d_vec, first, s->mind);
   }));
   s->rounds += 1;
-  if (c->params.kmpp_exact_sum) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
+  if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_seq_sum_scan(c, s->mind, n, s->d_sum));
+    else if (c->params.kmpp_exact_sum == 2) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
   else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
   SPF_TRY(check_launch(c, "kmpp sum kernel"));
   SPF_CUDA(cudaMemcpyAsync(local_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -59,6 +59,13 @@ class Context:
     def last_overflow_rows(self) -> int:
         return int(lib().spf_ctx_last_overflow_rows(self._h))
 
+    def seq_sum_f32(self, values, mode: int = 1) -> np.float32:
+        """spf_seq_sum_f32 (test hook): the sequential f32 fold, mode 1 = scan kernel, 2 = serial chain."""
+        v = as_f32(values).reshape(-1)
+        out = C.c_float()
+        check(lib().spf_seq_sum_f32(self._h, ptr(v), v.size, int(mode), C.byref(out)))
+        return np.float32(out.value)
+
     def set_param(self, name: str, value: int):
         check(lib().spf_ctx_set_param(self._h, name.encode(), int(value)))
 

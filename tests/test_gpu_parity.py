@@ -464,6 +464,39 @@ def test_kmeanspp_matches_oracle(spf, ctx, oracle, metric):
     sess.free()
 
 
+def test_sequential_sum_scan_is_bit_exact(spf, ctx):
+    """hierarchical.rs:278 is a strictly sequential f32 fold.  The scan-based kernel (two-state
+    transducers per binade) must return the bits of the serial add chain and of numpy's sequential
+    cumsum for every input: ties, zeros, denormals, huge dynamic range, overflow, invalid values."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for n in (0, 1, 2, 3, 7, 8, 9, 1023, 8192, 8193, 100_000, 1_000_003):
+        cases.append(rng.random(n, dtype=np.float32) * 300.0)                       # distances of the bench shape
+    cases.append((rng.integers(0, 4096, 300_000) * 0.25).astype(np.float32))           # many exact ties
+    cases.append((rng.integers(0, 3, 200_000)).astype(np.float32))                      # zeros and small integers
+    cases.append(np.exp(rng.normal(0, 12, 200_000)).astype(np.float32))                 # 30 binades of range
+    cases.append(np.concatenate([np.zeros(5000, np.float32), rng.random(50_000, dtype=np.float32) * 1e-41]))   # denormals
+    cases.append(np.concatenate([rng.random(10_000, dtype=np.float32) * 1e-40, rng.random(10_000, dtype=np.float32)]))
+    cases.append(np.full(70_000, 16777216.0, np.float32))                               # 2^24: every add is a tie or exact
+    cases.append(np.concatenate([[1.0], np.full(100_000, 2.0 ** -24, np.float32)]).astype(np.float32))   # half-ulp ties: never grows
+    cases.append(np.concatenate([[1.0], np.full(100_000, 2.0 ** -24 * 1.5, np.float32)]).astype(np.float32))
+    cases.append(np.full(3000, 3.0e38, np.float32))                                     # overflows to +inf
+    cases.append(np.concatenate([rng.random(20_000, dtype=np.float32), [-1.0], rng.random(20_000, dtype=np.float32)]).astype(np.float32))
+    cases.append(np.concatenate([rng.random(9000, dtype=np.float32), [np.inf], rng.random(100, dtype=np.float32)]).astype(np.float32))
+    cases.append(np.concatenate([rng.random(9000, dtype=np.float32), [np.nan], rng.random(100, dtype=np.float32)]).astype(np.float32))
+    cases.append(np.concatenate([[0.0, -0.0, 0.0], rng.random(5000, dtype=np.float32)]).astype(np.float32))
+    for i, v in enumerate(cases):
+        v = np.ascontiguousarray(v, np.float32)
+        with np.errstate(over="ignore", invalid="ignore"):
+            want = np.cumsum(v, dtype=np.float32)[-1] if v.size else np.float32(0.0)
+        serial = ctx.seq_sum_f32(v, 2)
+        scan = ctx.seq_sum_f32(v, 1)
+        assert np.array_equal(np.array([serial]).view(np.uint32), np.array([want]).view(np.uint32)) or \
+            (np.isnan(serial) and np.isnan(want)), (i, serial, want)
+        assert np.array_equal(np.array([scan]).view(np.uint32), np.array([serial]).view(np.uint32)) or \
+            (np.isnan(scan) and np.isnan(serial)), (i, v.size, scan, serial)
+
+
 # ----------------------------------------------------------------------------------------------
 # fit() end to end through the host mirror
 # ----------------------------------------------------------------------------------------------
