@@ -143,7 +143,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "scan_list_major") c->params.scan_list_major = value;
   else if (s == "scan_tc") c->params.scan_tc = value;
   else if (s == "scan_tc_bucket") {
-    if (value < 1 || value > 65536) return fail(SPF_E_INVALID, "scan_tc_bucket must be in [1,65536]");
+    if (value < 0 || value > 65536) return fail(SPF_E_INVALID, "scan_tc_bucket must be in [0,65536]");
     c->params.scan_tc_bucket = value;
   } else if (s == "scan_tc_tau_probes") c->params.scan_tc_tau_probes = value;
   else if (s == "scan_tc_cmax_mb") c->params.scan_tc_cmax_mb = value;

@@ -49,7 +49,7 @@ struct Params {
   int scan_threads = 256;
   int scan_list_major = 1;   // 0: query-major scan only, 1: automatic, 2: always list-major (k <= 32)
   int scan_tc = 1;           // tensor-core candidate scan: 0 never, 1 automatic, 2 whenever supported (k <= 16, d <= 128)
-  int scan_tc_bucket = 256;  // candidate entries per query kept by the tensor scan (overflow: exact fallback)
+  int scan_tc_bucket = 0;    // candidate entries per query kept by the tensor scan (overflow: exact fallback); 0: 256, or 1024 for d > 256
   int scan_tc_cmax_mb = 40960; // keep the bound pass's chunk maxima (one GEMM pass) while they fit in this many MB; 0: always two passes
   int scan_tc_tau_probes = 0;  // probes per query that take part in the bound pass (0: all)
   int chunk_rows = 0;        // points per assign chunk (0: automatic)

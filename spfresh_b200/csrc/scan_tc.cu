@@ -124,6 +124,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // ld <= 128: the unit's query tile (<= 4 K blocks) stays in shared memory for the whole unit.
+  // Longer rows: the query K block is streamed with the list's K block, one ring stage for both
+  // (the 64 KB that hold the stationary tile are then four 16 KB stages).
+  const bool stream_a = a.kb > (uint32_t)KB_MAX;
+  static_assert(KB_MAX == NSTAGE, "the stationary A tile and the streamed A stages share one region");
 
   if (warp == 0) {
     // =============================== TMA producer ===========================================
@@ -133,16 +138,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const UnitDesc ud = a.desc[u];
         const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
         if (ntiles == 0) continue;
-        for (uint32_t kb = 0; kb < a.kb; ++kb) {
-          mbar_wait(&a_empty[kb], (it & 1) ^ 1);          // previous unit's MMAs are done with it
-          mbar_expect_tx(&a_full[kb], A_KB_BYTES);
-          tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(u * UNIT_ROWS));
+        if (!stream_a) {
+          for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            mbar_wait(&a_empty[kb], (it & 1) ^ 1);        // previous unit's MMAs are done with it
+            mbar_expect_tx(&a_full[kb], A_KB_BYTES);
+            tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(u * UNIT_ROWS));
+          }
         }
         for (uint32_t t = 0; t < ntiles; ++t, ++ecount) {
           const int row0 = (int)(ud.slot0 + t * BN);
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1);
-            mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);
+            if (stream_a) {                               // the query K block rides in the same ring stage
+              mbar_expect_tx(&b_full[stage], A_KB_BYTES + B_STAGE_BYTES);
+              tma_load_2d(smem_a + stage * A_KB_BYTES, &map_a, &b_full[stage], (int)(kb * BK), (int)(u * UNIT_ROWS));
+            } else {
+              mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);
+            }
             tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &b_full[stage], (int)(kb * BK), row0);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
@@ -168,10 +180,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
-            if (t == 0) mbar_wait(&a_full[kb], it & 1);
+            if (!stream_a && t == 0) mbar_wait(&a_full[kb], it & 1);
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + kb * A_KB_BYTES);
+            const uint32_t a_addr = smem_u32(smem_a + (stream_a ? stage : kb) * A_KB_BYTES);
             const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -179,7 +191,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                           IDESC_TF32, (kb | (uint32_t)k) != 0 ? 1u : 0u);
             }
             tc_commit(&b_empty[stage]);                     // frees the B stage once these MMAs retire
-            if (t + 1 == ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
+            if (!stream_a && t + 1 == ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           {   // K extension: accumulator += -|v|^2/2
@@ -879,7 +891,7 @@ __global__ void __launch_bounds__(256) probe_dense_select_kernel(DenseSelArgs a)
 }  // namespace
 
 bool scan_tc_supported(const spf_ctx* c, uint32_t ld, uint64_t nslots, uint32_t K, uint64_t npairs) {
-  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= (uint32_t)(KB_MAX * BK) && K <= (uint32_t)TOPR_MAX &&
+  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= 1024u && K <= (uint32_t)TOPR_MAX &&
          nslots > 0 && nslots + BN < (1ull << 31) && npairs < (1ull << 32) - 1;
 }
 
@@ -924,7 +936,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   const ScanTcSide& side = *call.side;
   const uint64_t nq = call.nq, npairs = nq * s.nprobe;
   const uint32_t ld = s.ld, nlists = call.nlists;
-  const uint32_t cap = (uint32_t)(c->params.scan_tc_bucket > 0 ? c->params.scan_tc_bucket : 256);
+  // candidate entries per query; long rows have a wider error bound and therefore more candidates
+  const uint32_t cap = (uint32_t)(c->params.scan_tc_bucket > 0 ? c->params.scan_tc_bucket : (s.ld <= 256 ? 256 : 1024));
   const uint32_t tau_probes = c->params.scan_tc_tau_probes > 0 ? (uint32_t)c->params.scan_tc_tau_probes : s.nprobe;
   const uint32_t topr = s.K <= 16 ? 16u : 32u;
   // timer / counter names of this call (the centroid probe runs through the same code)
@@ -993,7 +1006,9 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   uint32_t total_tiles = 0;
   DevBuf<uint32_t> utiles, tile_off;
   bool keep_cmax = false;
-  if (nunits > 0 && !call.is_probe && c->params.scan_tc_cmax_mb > 0) {
+  // (a flagged group costs 32 exact vectors = 128 * ld bytes: beyond ld = 256 the second GEMM pass,
+  // which pins down the single candidates, is cheaper than re-evaluating whole groups)
+  if (nunits > 0 && !call.is_probe && c->params.scan_tc_cmax_mb > 0 && ld <= 256) {
     SPF_TRY(utiles.alloc(st, (size_t)nunits + 1));
     SPF_TRY(tile_off.alloc(st, (size_t)nunits + 1));
     tc_unit_tiles_kernel<<<(unsigned)ceil_div((uint64_t)nunits + 1, 256), 256, 0, st>>>(ukey2.p, nunits, utiles.p);
@@ -1010,7 +1025,9 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   }
 
   if (nunits > 0) {
-    const uint32_t chunk_units = nunits < 16384u ? nunits : 16384u;     // <= 1 GB of gathered rows
+    uint32_t max_units = (uint32_t)((1ull << 30) / ((uint64_t)UNIT_ROWS * ld * sizeof(float)));   // <= 1 GB of gathered rows
+    if (max_units < 64u) max_units = 64u;
+    const uint32_t chunk_units = nunits < max_units ? nunits : max_units;
     const bool single = chunk_units == nunits;
     DevBuf<float> A, rowthr, pairtop, qbound;
     DevBuf<uint32_t> rowseq, rowpair, unit_slot0;

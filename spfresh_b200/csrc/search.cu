@@ -1234,10 +1234,11 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     la.unit_keys = ukeys.p; la.unit_slots = uslots.p;
     const uint64_t max_units = npairs / LS_QB + nlists + 1;   // upper bound; surplus units exit at once
     // short lists (a few 32-vector groups each): one warp per unit; long lists: one CTA per unit
-    const bool warp_units = nloc > 0 && idx->total_groups / nloc < 24;
+    // (the per-warp query tiles of the first variant must fit in shared memory: d <= 800)
+    const bool warp_units = nloc > 0 && idx->total_groups / nloc < 24 &&
+                            (size_t)LS_WARPS * LS_QB * ld * sizeof(float) <= 200 * 1024;
     if (warp_units) {
       const size_t smem = (size_t)LS_WARPS * LS_QB * ld * sizeof(float);
-      if (smem > 200 * 1024) return fail(SPF_E_INVALID, "dimension too large for the list-major scan");
       SPF_CUDA(cudaFuncSetAttribute(scan_lists_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       scan_lists_kernel<true><<<(unsigned)ceil_div(max_units, LS_WARPS), LS_WARPS * 32, smem, st>>>(la, nlists);
     } else {
