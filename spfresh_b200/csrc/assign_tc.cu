@@ -117,21 +117,33 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t crank = cluster_ctarank();
+  // ld <= 128: the point tile (<= 4 K blocks) stays in shared memory for the whole row block.
+  // Longer rows: the point K block is streamed with the centroid K block, one ring stage for both
+  // (the 64 KB of the stationary tile are then four 16 KB stages).
+  const bool stream_a = a.kb > (uint32_t)KB_MAX;
+  static_assert(KB_MAX == NSTAGE, "the stationary A tile and the streamed A stages share one region");
 
   if (warp == 0) {
     // =============================== TMA producer ===========================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0, ecount = 0;
       for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x, ++it) {
-        for (uint32_t kb = 0; kb < a.kb; ++kb) {
-          mbar_wait(&a_empty[kb], (it & 1) ^ 1);          // previous row block's MMAs are done with it
-          mbar_expect_tx(&a_full[kb], A_KB_BYTES);
-          tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(rb * BM));
+        if (!stream_a) {
+          for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            mbar_wait(&a_empty[kb], (it & 1) ^ 1);        // previous row block's MMAs are done with it
+            mbar_expect_tx(&a_full[kb], A_KB_BYTES);
+            tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(rb * BM));
+          }
         }
         for (uint32_t t = 0; t < a.ntiles; ++t, ++ecount) {
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1);          // both CTAs are done with this stage
-            mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);  // own half + the peer's multicast half
+            if (stream_a) {                                 // own point K block in the same ring stage (not multicast)
+              mbar_expect_tx(&b_full[stage], A_KB_BYTES + B_STAGE_BYTES);
+              tma_load_2d(smem_a + stage * A_KB_BYTES, &map_a, &b_full[stage], (int)(kb * BK), (int)(rb * BM));
+            } else {
+              mbar_expect_tx(&b_full[stage], B_STAGE_BYTES);  // own half + the peer's multicast half
+            }
             tma_load_2d_mc(smem_b + stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / 2), &map_b, &b_full[stage],
                            (int)(kb * BK), (int)(t * BN + crank * (BN / 2)), (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -154,10 +166,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
-            if (t == 0) mbar_wait(&a_full[kb], it & 1);
+            if (!stream_a && t == 0) mbar_wait(&a_full[kb], it & 1);
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + kb * A_KB_BYTES);
+            const uint32_t a_addr = smem_u32(smem_a + (stream_a ? stage : kb) * A_KB_BYTES);
             const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -165,7 +177,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                           IDESC_TF32, (kb | (uint32_t)k) != 0 ? 1u : 0u);
             }
             tc_commit_mc(&b_empty[stage], (uint16_t)0x3);   // frees the B stage in both CTAs once these MMAs retire
-            if (t + 1 == a.ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
+            if (!stream_a && t + 1 == a.ntiles) tc_commit(&a_empty[kb]);   // last use of this A block
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           {   // K extension: accumulator += -|c|^2/2
@@ -323,7 +335,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }  // namespace
 
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) {
-  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= (uint32_t)(KB_MAX * BK) &&
+  return c->tma_encode != nullptr && ld % 4 == 0 && ld <= 1024u &&
          (int64_t)k >= c->params.tc_min_k && (int64_t)m >= c->params.tc_min_m;
 }
 

@@ -144,6 +144,7 @@ def test_assign_degenerate_inputs(spf, ctx, oracle):
 @pytest.mark.parametrize("n,d,k,kind", [
     (4096, 128, 256, "gauss"), (5000, 128, 300, "gauss"), (20000, 96, 1000, "clustered"),
     (3000, 64, 513, "gauss"), (2500, 100, 64, "clustered"), (30000, 128, 4096, "clustered"),
+    (4000, 200, 300, "clustered"), (3000, 960, 256, "clustered"), (2048, 516, 128, "gauss"),   # streamed point K blocks
 ])
 def test_assign_tensor_path_matches_oracle(spf, ctx, oracle, n, d, k, kind):
     data = gauss(n, d, n + d) if kind == "gauss" else clustered(n, d, max(k // 4, 2), n + d)
