@@ -83,9 +83,19 @@ struct AssignCall {
   ~AssignCall() { if (rs) resolve_free(rs); }
 };
 
-uint64_t pick_chunk_rows(const spf_ctx* c, uint64_t m, bool streamed) {
+// Candidate group records per point.  Long rows have concentrated distances (the 1.1 boundary band
+// covers far more centroids until the running minimum has tightened) and a wider TF32 bound, so the
+// tensor path keeps four times as many records per point there unless the knob was set explicitly.
+int effective_cand_cap(const spf_ctx* c, bool use_tc, uint32_t ld) {
+  if (c->params.cand_cap == 128 && use_tc && ld > 256) return 512;
+  return c->params.cand_cap;
+}
+
+uint64_t pick_chunk_rows(const spf_ctx* c, uint64_t m, bool streamed, int cand_cap) {
   // multiples of one full wave of the tensor kernel (one 128-point row block per SM)
   uint64_t rows = (uint64_t)c->sm_count * 128 * (streamed ? 4 : 64);
+  // candidate scratch of a chunk stays below ~5 GB
+  while (rows > (uint64_t)c->sm_count * 128 && rows * (uint64_t)cand_cap * sizeof(CandRec) > (5ull << 30)) rows /= 2;
   if (c->params.chunk_rows > 0) rows = (uint64_t)c->params.chunk_rows;
   return rows < m ? rows : m;
 }
@@ -94,7 +104,7 @@ uint64_t pick_chunk_rows(const spf_ctx* c, uint64_t m, bool streamed) {
 int assign_setup(AssignCall& a) {
   spf_ctx* c = a.c;
   cudaStream_t st = c->stream;
-  a.cand.cap = c->params.cand_cap;
+  a.cand.cap = effective_cand_cap(c, a.use_tc, a.ld);
   SPF_TRY(a.cand_rec.alloc(st, (size_t)a.chunk_rows * a.cand.cap));
   SPF_TRY(a.cand_info.alloc(st, a.chunk_rows));
   a.cand.rec = a.cand_rec.p;
@@ -232,7 +242,7 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
   a.factor = a.want_members ? boundary_factor : 1.0f;
   a.use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) && !c->params.force_exact &&
              assign_tc_supported(c, m, k, ld);
-  a.chunk_rows = pick_chunk_rows(c, m, false);
+  a.chunk_rows = pick_chunk_rows(c, m, false, effective_cand_cap(c, a.use_tc, ld));
 
   // dense operands: centroids always materialised; points gathered only for a subset
   SPF_TRY(a.Cg.alloc(st, (size_t)k * ld));
@@ -321,7 +331,7 @@ int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint6
   a.factor = a.want_members ? boundary_factor : 1.0f;
   a.use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) && !c->params.force_exact &&
              assign_tc_supported(c, n, k, ld);
-  a.chunk_rows = pick_chunk_rows(c, n, true);
+  a.chunk_rows = pick_chunk_rows(c, n, true, effective_cand_cap(c, a.use_tc, ld));
   if (a.use_tc) SPF_TRY(dataset_prep_alloc(ds));
 
   // the k centroid vectors come straight from the host rows (small gather + one copy)
