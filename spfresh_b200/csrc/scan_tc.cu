@@ -5,22 +5,27 @@
 // probed by many queries.  d(q, v) = |q|^2 - 2 q.v + |v|^2 is a dense contraction between the
 // queries probing a list and the list's vectors: it runs on the 5th-gen tensor cores as one TF32
 // pass (fp32 accumulation in TMEM) whose only job is to SELECT.  With E = tc_err_bound a certified
-// bound on |d_tf32 - d_ref| (kernels.cuh), two passes over the same (list, 128-query) units give
-// the reference's result bit for bit:
+// bound on |d_tf32 - d_ref| (kernels.cuh) the result is the reference's, bit for bit:
 //
-//   phase A  per (query, probe) pair the 16 largest 32-column chunk maxima of s = q'.v' - |v|^2/2.
-//            Chunk maxima belong to distinct vectors, so the K-th largest over a query's pairs,
-//            s_K, certifies that K probed vectors have d_ref <= |q|^2 - 2 s_K + E.
-//   phase B  emits every (query, slot) with d_tf32 - E <= min(thr_q, |q|^2 - 2 s_K + E): a superset
-//            of everything that can be among the K smallest keys that pass `dist <= threshold`
-//            (:176), typically K plus a handful.
-//   refine   evaluates the emitted pairs exactly (the reference's sequential f32 sum, :172), applies
-//            `dist <= threshold` and keeps the K smallest (distance, encounter index) keys — the
-//            stable sort + truncate of :188-193.
+//   bound pass   per (query, probe) pair the 16 (or 32) largest 32-column chunk maxima of
+//                s = q'.v' - |v|^2/2.  Chunk maxima belong to distinct vectors, so the K-th largest
+//                over a query's pairs, s_K, certifies that K probed vectors have
+//                d_ref <= |q|^2 - 2 s_K + E.  A vector can be among the K smallest keys that pass
+//                `dist <= threshold` (:176) only if d_tf32 - E <= min(thr_q, |q|^2 - 2 s_K + E).
+//   candidates   either the bound pass also stores every chunk maximum (4 KB per 128 x 256 tile) and
+//                the few (pair, 32-slot group) items whose maximum passes are re-evaluated exactly
+//                ("group refinement": no second GEMM), or — centroid probe, rows longer than 256
+//                floats, chunk maxima over the memory budget — a second GEMM pass emits the single
+//                (query, slot) hits: typically K plus a handful per query.
+//   select       exact distances (the reference's sequential f32 sum, :172), `dist <= threshold`,
+//                the K smallest (distance, encounter index) keys — the stable sort + truncate of
+//                :188-193.
 //
 // Queries without a certified bound (non-finite norms) or with more candidates than their bucket
 // holds are flagged and re-run by the exact query-major kernel (search.cu), so the tensor path never
-// decides a comparison on an approximate value.
+// decides a comparison on an approximate value.  The centroid probe is the same computation with the
+// centroids as one posting list (K = nprobe <= 32), or, for larger nprobe, a dense store of s
+// followed by a certified bitwise selection (probe_dense_select_kernel).
 //
 // Kernel anatomy (persistent, one CTA per SM, 320 threads), per unit = (list, <= 128 probing pairs):
 //   warp 0     TMA producer: the unit's 128 gathered query rows (A, stationary for the unit) and a
