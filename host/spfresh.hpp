@@ -10,6 +10,7 @@
 //   src/spann/spann_builder.rs           SpannIndexBuilder::{new, with_data, build, load}
 //   src/spann/spann_index.rs             SpannIndex::{find_k_nearest_neighbor_spann, ...}
 //   src/spann/posting_lists.rs           PointData
+//   src/spann/lire/operations.rs         Split, Reassign (the parts that are distance work)
 // Every distance, mean, argmin and scan runs on the B200 through the C ABI; this header only
 // sequences the calls (fit(), the bisect work-list) and owns the random decisions.  Rust
 // `Result::Err` / `expect` / `unwrap` panics become `spfresh::Error`.  Header-only, C++17.
@@ -615,4 +616,120 @@ class SpannIndexBuilder {
 };
 
 }  // namespace spann
+
+// ---------------------------------------------------------------------------------------------
+// src/spann/lire/operations.rs — the two operations that sit on the hot path's kernels
+// ---------------------------------------------------------------------------------------------
+namespace lire {
+
+using VectorList = std::vector<std::pair<size_t, std::vector<float>>>;   // (vector_id, vector_data)
+
+// operations.rs:8-120.  Tie rules of the reference: `max_by` keeps the LAST maximum (second centroid),
+// `dist1 <= dist2` sends ties to the first partition.
+class Split {
+ public:
+  size_t posting_id;
+  VectorList vectors;
+  std::shared_ptr<distances::DistanceMetric> distance_metric;
+  std::pair<size_t, size_t> new_posting_ids;
+
+  Split(size_t posting, VectorList vecs, std::shared_ptr<distances::DistanceMetric> metric,
+        std::pair<size_t, size_t> new_ids, std::shared_ptr<Context> ctx = nullptr)
+      : posting_id(posting), vectors(std::move(vecs)), distance_metric(std::move(metric)), new_posting_ids(new_ids),
+        ctx_(ctx ? std::move(ctx) : Context::shared()) {}
+
+  // operations.rs:33-58: (vectors[0], the farthest of vectors[1..] from it)
+  std::pair<std::vector<float>, std::vector<float>> select_initial_centroids() {
+    if (vectors.size() < 2) throw Error("Not enough vectors to split");
+    upload();
+    // the fold keeps the earliest maximum, so it runs over the members in reverse order
+    std::vector<uint64_t> members;
+    for (size_t i = vectors.size() - 1; i >= 1; --i) members.push_back(i);
+    float dist = 0.f;
+    uint64_t row = 0;
+    check(spf_farthest_from(ds_->handle(), distance_metric->kind(), vectors[0].second.data(), UINT64_MAX, members.data(),
+                            members.size(), &dist, &row));
+    if (row == UINT64_MAX) row = vectors.size() - 1;    // every distance is 0: max_by returns the last element
+    return {vectors[0].second, vectors[(size_t)row].second};
+  }
+
+  // operations.rs:61-82
+  std::pair<VectorList, VectorList> assign_vectors(const std::vector<float>& c1, const std::vector<float>& c2) {
+    upload();
+    std::vector<float> cen(c1);
+    cen.insert(cen.end(), c2.begin(), c2.end());
+    spf_assign_result* r = nullptr;
+    check(spf_assign_vectors(ds_->handle(), distance_metric->kind(), nullptr, vectors.size(), cen.data(), 2, 1.0f,
+                             SPF_ASSIGN_NO_CSR, &r));
+    std::vector<uint32_t> best(vectors.size());
+    const int rc = spf_assign_fetch(r, best.data(), nullptr, nullptr, nullptr);
+    spf_assign_free(r);
+    check(rc);
+    std::pair<VectorList, VectorList> out;
+    for (size_t i = 0; i < vectors.size(); ++i) (best[i] == 0 ? out.first : out.second).push_back(vectors[i]);
+    return out;
+  }
+
+  std::vector<size_t> execute() {                         // operations.rs:86-101
+    auto c = select_initial_centroids();
+    partitions = assign_vectors(c.first, c.second);
+    return get_affected_partitions();
+  }
+  bool validate() const {                                 // operations.rs:103-112
+    return vectors.size() >= 2 && new_posting_ids.first != posting_id && new_posting_ids.second != posting_id &&
+           new_posting_ids.first != new_posting_ids.second;
+  }
+  std::vector<size_t> get_affected_partitions() const { return {posting_id, new_posting_ids.first, new_posting_ids.second}; }
+
+  std::pair<VectorList, VectorList> partitions;          // what execute() computed (the reference drops it)
+
+ private:
+  void upload() {
+    if (ds_) return;
+    const size_t d = vectors[0].second.size();
+    std::vector<float> rows(vectors.size() * d);
+    for (size_t i = 0; i < vectors.size(); ++i) {
+      if (vectors[i].second.size() != d) throw Error("vectors of different length");
+      std::copy(vectors[i].second.begin(), vectors[i].second.end(), rows.begin() + i * d);
+    }
+    ds_ = std::make_shared<DeviceDataset>(ctx_, ArrayView2(rows.data(), vectors.size(), d));
+  }
+  std::shared_ptr<Context> ctx_;
+  std::shared_ptr<DeviceDataset> ds_;
+};
+
+// operations.rs:222-300: the nearest candidate centroid, `min_by` keeps the FIRST minimum.
+class Reassign {
+ public:
+  size_t vector_id, from_posting;
+  std::vector<float> vector;
+  VectorList candidate_postings;                          // (posting_id, centroid)
+  std::shared_ptr<distances::DistanceMetric> distance_metric;
+  uint64_t version;
+
+  Reassign(size_t id, std::vector<float> vec, size_t from, VectorList candidates,
+           std::shared_ptr<distances::DistanceMetric> metric, uint64_t ver, std::shared_ptr<Context> ctx = nullptr)
+      : vector_id(id), from_posting(from), vector(std::move(vec)), candidate_postings(std::move(candidates)),
+        distance_metric(std::move(metric)), version(ver), ctx_(ctx ? std::move(ctx) : Context::shared()) {}
+
+  size_t find_best_posting() const {                      // operations.rs:253-276
+    if (candidate_postings.empty()) throw Error("No candidate postings available");
+    const size_t d = vector.size(), m = candidate_postings.size();
+    std::vector<float> a(m * d), b(m * d), dist(m);
+    for (size_t j = 0; j < m; ++j) {
+      std::copy(vector.begin(), vector.end(), a.begin() + j * d);
+      std::copy(candidate_postings[j].second.begin(), candidate_postings[j].second.end(), b.begin() + j * d);
+    }
+    check(spf_distance_pairs(ctx_->handle(), distance_metric->kind(), a.data(), b.data(), (uint32_t)d, m, dist.data()));
+    size_t best = 0;
+    for (size_t j = 1; j < m; ++j)
+      if (dist[j] < dist[best]) best = j;
+    return candidate_postings[best].first;
+  }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+};
+
+}  // namespace lire
 }  // namespace spfresh

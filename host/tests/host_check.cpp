@@ -32,8 +32,36 @@ int main(int argc, char** argv) {
     printf("%d\n", spf_abi_version());
     return 0;
   }
+  if (argc == 6 && !strcmp(argv[1], "--lire")) {
+    // host_check --lire <vectors.f32> <n> <d> <out.txt>: Split over the n vectors (ids = row numbers,
+    // squared L2) and Reassign of vector 1 against vectors 2..9 as candidate centroids
+    try {
+      const size_t n = std::stoull(argv[3]), d = std::stoull(argv[4]);
+      const std::vector<float> rows = read_f32(argv[2], n * d);
+      lire::VectorList vl;
+      for (size_t i = 0; i < n; ++i) vl.push_back({i, std::vector<float>(rows.begin() + i * d, rows.begin() + (i + 1) * d)});
+      auto metric = std::make_shared<distances::SquaredEuclideanDistance>();
+      lire::Split sp(7, vl, metric, {8, 9});
+      auto cen = sp.select_initial_centroids();
+      auto parts = sp.assign_vectors(cen.first, cen.second);
+      std::ofstream out(argv[5]);
+      size_t far = 0;
+      for (size_t i = 1; i < n; ++i) if (vl[i].second == cen.second) far = i;    // last vector equal to c2
+      out << "far " << far << "\npartition1 " << parts.first.size();
+      for (auto& p : parts.first) out << " " << p.first;
+      out << "\npartition2 " << parts.second.size();
+      for (auto& p : parts.second) out << " " << p.first;
+      lire::VectorList cands(vl.begin() + 2, vl.begin() + 10);
+      lire::Reassign re(1, vl[1].second, 0, cands, metric, 1);
+      out << "\nbest " << re.find_best_posting() << "\n";
+      return 0;
+    } catch (const std::exception& e) {
+      fprintf(stderr, "host_check: %s\n", e.what());
+      return 1;
+    }
+  }
   if (argc != 3) {
-    fprintf(stderr, "usage: host_check <scenario.txt> <out.txt> | --abi\n");
+    fprintf(stderr, "usage: host_check <scenario.txt> <out.txt> | --lire <vectors.f32> <n> <d> <out.txt> | --abi\n");
     return 2;
   }
   try {

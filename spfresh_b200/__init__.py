@@ -13,6 +13,7 @@ from .clustering import (BOUNDARY_THRESHOLD, ChebyshevDistance, Cluster, Cluster
                          HierarchicalClustering, InitializationMethod, ManhattanDistance, NumpyRandomSource,
                          RandomSource, ScriptedRandomSource, SquaredEuclideanDistance)
 from .device import AssignResult, Context, Dataset, DeviceIndex, KmppSession, KmppShardSession, topk_merge
+from .lire import LireError, Reassign, Split, reassign_batch
 from .spann import ClusteringParamsConfig, Config, PointData, SpannIndex, SpannIndexBuilder
 
 __all__ = [n for n in dir() if not n.startswith("_")]

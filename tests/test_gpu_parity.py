@@ -875,3 +875,54 @@ def test_index_files_interoperate_with_reference_layout(spf, ctx, oracle, tmp_pa
     r1, r2 = idx.search(q, 7), loaded.search(q, 7)
     for x, y in zip(r1, r2):
         assert np.array_equal(x, y)
+
+
+# ----------------------------------------------------------------------------------------------
+# LIRE operations on the hot-path kernels (src/spann/lire/operations.rs)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric_cls,kind", [("SquaredEuclideanDistance", 0), ("ManhattanDistance", 1),
+                                             ("ChebyshevDistance", 2)])
+def test_lire_split_and_reassign(spf, ctx, oracle, metric_cls, kind):
+    """Split: c1 = vectors[0], c2 = LAST maximum of d(c1, v) over vectors[1..] (Rust max_by),
+    `dist1 <= dist2` -> partition 1.  Reassign: FIRST minimum over the candidate centroids (min_by).
+    Compared with a per-pair restatement on the oracle's distance function."""
+    metric = getattr(spf, metric_cls)()
+    rng = np.random.default_rng(11 + kind)
+    vecs = clustered(700, 24, 3, 50 + kind)
+    vecs[400] = vecs[0]                                   # distance 0 to c1
+    vecs[650] = vecs[123]                                 # a duplicated vector: equal distances, ties on both rules
+    ids = rng.permutation(10_000)[:700]
+    vectors = [(int(i), v) for i, v in zip(ids, vecs)]
+    op = spf.Split(7, vectors, metric, (8, 9), ctx=ctx)
+    assert op.validate() and not spf.Split(7, vectors, metric, (7, 9), ctx=ctx).validate()
+    c1, c2 = op.select_initial_centroids()
+    d1 = np.array([oracle.distance(kind, vecs[0], v) for v in vecs], np.float32)
+    far = 1 + int(np.flatnonzero(d1[1:] == d1[1:].max())[-1])            # last maximum over skip(1)
+    assert np.array_equal(c1, vecs[0]) and np.array_equal(c2, vecs[far])
+    p1, p2 = op.assign_vectors(c1, c2)
+    d2 = np.array([oracle.distance(kind, vecs[far], v) for v in vecs], np.float32)
+    want1 = [int(i) for i, a, b in zip(ids, d1, d2) if a <= b]
+    want2 = [int(i) for i, a, b in zip(ids, d1, d2) if not a <= b]
+    assert [i for i, _ in p1] == want1 and [i for i, _ in p2] == want2
+    assert op.execute() == {7, 8, 9} and op.get_affected_partitions() == {7, 8, 9}
+    # all vectors identical: every distance is 0 and max_by returns the last element
+    same = spf.Split(1, [(k, vecs[5]) for k in range(6)], metric, (2, 3), ctx=ctx)
+    s1, s2 = same.select_initial_centroids()
+    assert np.array_equal(s1, vecs[5]) and np.array_equal(s2, vecs[5])
+    assert [i for i, _ in same.assign_vectors(s1, s2)[0]] == list(range(6))
+    with pytest.raises(spf.LireError):
+        spf.Split(1, vectors[:1], metric, (2, 3), ctx=ctx).select_initial_centroids()
+    op.free()
+    same.free()
+    # Reassign
+    cands = [(100 + j, vecs[50 + 7 * j]) for j in range(9)] + [(300, vecs[50])]   # posting 300 duplicates posting 100
+    for t in (3, 50, 57, 600):
+        r = spf.Reassign(t, vecs[t], 5, cands, metric, 1, ctx=ctx)
+        dc = np.array([oracle.distance(kind, vecs[t], c) for _, c in cands], np.float32)
+        assert r.find_best_posting() == cands[int(np.argmin(dc))][0]
+        assert r.get_affected_partitions() == {5, cands[int(np.argmin(dc))][0]}
+    with pytest.raises(spf.LireError):
+        spf.Reassign(1, vecs[1], 5, [], metric, 1, ctx=ctx).find_best_posting()
+    best = spf.reassign_batch(ctx, metric, vecs, np.stack([c for _, c in cands]))
+    full = np.array([[oracle.distance(kind, v, c) for _, c in cands] for v in vecs[:200]], np.float32)
+    assert np.array_equal(best[:200], full.argmin(axis=1))

@@ -121,3 +121,28 @@ def test_cpp_example_build_and_load_index(host_bin):
     r = subprocess.run([os.path.join(HOST, "build", "load_index")], capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == "Nearest neighbour: point_id:0 and vector:[1.0, 2.0]"
+
+
+@pytest.mark.gpu
+def test_cpp_lire_split_and_reassign(host_bin, tmp_path):
+    """lire::Split / lire::Reassign on the C++ layer against a per-pair restatement."""
+    import oracle
+    oracle.build()
+    n, d = 500, 20
+    vecs = clustered(n, d, 3, 77)
+    vecs[300] = vecs[0]
+    vecs[450] = vecs[200]
+    vecs.tofile(tmp_path / "v.f32")
+    out = tmp_path / "lire.txt"
+    r = subprocess.run([host_bin, "--lire", str(tmp_path / "v.f32"), str(n), str(d), str(out)], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = {ln.split()[0]: [int(x) for x in ln.split()[1:]] for ln in out.read_text().splitlines()}
+    d1 = np.array([oracle.distance(0, vecs[0], v) for v in vecs], np.float32)
+    far = 1 + int(np.flatnonzero(d1[1:] == d1[1:].max())[-1])
+    assert rows["far"] == [far]
+    d2 = np.array([oracle.distance(0, vecs[far], v) for v in vecs], np.float32)
+    assert rows["partition1"][1:] == [i for i in range(n) if d1[i] <= d2[i]]
+    assert rows["partition2"][1:] == [i for i in range(n) if not d1[i] <= d2[i]]
+    dc = np.array([oracle.distance(0, vecs[1], vecs[j]) for j in range(2, 10)], np.float32)
+    assert rows["best"] == [2 + int(np.argmin(dc))]
