@@ -460,7 +460,7 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
     ctx.set_profiling(True)
     idx.search(q, TOPK)
     scan_ms, probe_ms = ctx.kernel_ms("scan"), ctx.kernel_ms("probe")
-    tc = {n: ctx.kernel_ms("scan_tc_" + n) for n in ("a", "tau", "b", "refine", "fallback", "candidates", "flagged",
+    tc = {n: ctx.kernel_ms("scan_tc_" + n) for n in ("a", "gather", "tau", "b", "refine", "fallback", "candidates", "flagged",
                                                       "units", "stream_mb", "unique_mb")}
     ctx.set_profiling(False)
     bytes_ = idx.last_scan_bytes()
@@ -500,7 +500,7 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
                        "peak_source": hbm_src, "bytes_per_launch": int(unique), "requested_bytes_per_launch": int(stream),
                        "traffic": SCAN_TC_DRAM_BYTES_PER_LAUNCH, "traffic_source": SCAN_TC_DRAM_SOURCE,
                        "kernel_ms": tc["a"],
-                       "passes_ms": {"bound_incl_gather": tc["a"], "tau": tc["tau"], "group_refine": tc["b"], "select": tc["refine"],
+                       "passes_ms": {"gather": tc["gather"], "bound": tc["a"], "tau": tc["tau"], "group_refine": tc["b"], "select": tc["refine"],
                                      "fallback": tc["fallback"]},
                        "units": int(tc["units"]), "candidates_per_query": tc["candidates"] / NQ,
                        "queries_on_exact_fallback": int(tc["flagged"]),

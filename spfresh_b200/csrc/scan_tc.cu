@@ -948,6 +948,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   // timer / counter names of this call (the centroid probe runs through the same code)
   const bool pr = call.is_probe;
   const char* n_a = pr ? "probe_tc_a" : "scan_tc_a";
+  const char* n_gather = pr ? "probe_tc_gather" : "scan_tc_gather";
   const char* n_tau = pr ? "probe_tc_tau" : "scan_tc_tau";
   const char* n_b = pr ? "probe_tc_b" : "scan_tc_b";
   const char* n_ref = pr ? "probe_tc_refine" : "scan_tc_refine";
@@ -1073,19 +1074,20 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     k.cmax = keep_cmax ? cmax.p : nullptr;
     k.dense = nullptr; k.dense_ld = 0;
 
-    {
-      KernelTimer t(c, n_a);
-      for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
-        const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
+    for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
+      const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
+      {
+        KernelTimer t(c, n_gather);
         g.u0 = u0; g.qthr = nullptr; g.copy_rows = 1; g.bytes = s.bytes;
         unit_gather_kernel<<<nu, 256, 0, st>>>(g);
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
-        k.nunits = nu; k.u0 = u0;
-        const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
-        if (topr == 16) scan_tc_kernel<0, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
-        else scan_tc_kernel<0, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
-        SPF_TRY(check_launch(c, "scan_tc_kernel<A>"));
       }
+      KernelTimer t(c, n_a);                              // the bound pass alone (the roofline's kernel time)
+      k.nunits = nu; k.u0 = u0;
+      const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
+      if (topr == 16) scan_tc_kernel<0, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+      else scan_tc_kernel<0, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
+      SPF_TRY(check_launch(c, "scan_tc_kernel<A>"));
     }
     {
       KernelTimer t(c, n_tau);
