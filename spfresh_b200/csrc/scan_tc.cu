@@ -646,15 +646,25 @@ __global__ void __launch_bounds__(256) group_refine_kernel(GroupArgs g) {
     const uint32_t q = it.pair / a.nprobe;
     const float4* Q4 = reinterpret_cast<const float4*>(a.Q) + (size_t)q * ld4;
     const float4* base = V4 + (size_t)it.group * ld4 * 32 + lane;
+    // The sum only grows (or turns NaN), so a lane whose partial sum is already above the bound can
+    // stop reading: it could not pass the tests below anyway.  31 of the 32 vectors of a flagged
+    // group usually drop out this way, and with them most of the group's sectors.
+    const float bound = fminf(a.thr[q], g.qbound[q]);
     float acc = 0.0f;
-#pragma unroll 4
-    for (uint32_t c = 0; c < ld4; ++c) {
-      const float4 v = __ldg(base + (size_t)c * 32);
-      const float4 qv = __ldg(Q4 + c);
-      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
-      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
-      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
-      acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+    for (uint32_t c0 = 0; c0 < ld4; c0 += 4) {
+      if (!(acc <= bound)) break;
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u;
+        if (c < ld4) {
+          const float4 v = __ldg(base + (size_t)c * 32);
+          const float4 qv = __ldg(Q4 + c);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.x, v.x);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.y, v.y);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.z, v.z);
+          acc = dist_step<SPF_METRIC_EUCLIDEAN>(acc, qv.w, v.w);
+        }
+      }
     }
     const uint32_t slot = it.group * 32 + lane;
     const bool valid = a.slot_ids[slot] != ~0ull;
