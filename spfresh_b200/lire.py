@@ -32,11 +32,13 @@ class Split:
         self.vectors = [(int(i), np.asarray(v, np.float32)) for i, v in vectors]
         self.distance_metric = distance_metric
         self.new_posting_ids = (int(new_posting_ids[0]), int(new_posting_ids[1]))
-        self.ctx = ctx or Context.default()
+        self.ctx = ctx                       # resolved on first device use (validate() needs no GPU)
         self._ds: Optional[Dataset] = None
 
     def _dataset(self) -> Dataset:
         if self._ds is None:
+            if self.ctx is None:
+                self.ctx = Context.default()
             self._ds = Dataset(self.ctx, np.stack([v for _, v in self.vectors]))
         return self._ds
 
@@ -93,11 +95,13 @@ class Reassign:
         self.vector = np.asarray(vector, np.float32)
         self.candidate_postings = [(int(p), np.asarray(c, np.float32)) for p, c in candidate_postings]
         self.distance_metric = distance_metric
-        self.ctx = ctx or Context.default()
+        self.ctx = ctx
 
     def find_best_posting(self) -> int:                                    # operations.rs:253-276
         if not self.candidate_postings:
             raise LireError("No candidate postings available")
+        if self.ctx is None:
+            self.ctx = Context.default()
         cen = np.stack([c for _, c in self.candidate_postings])
         d = self.ctx.distance_pairs(self.distance_metric.kind, np.broadcast_to(self.vector, cen.shape), cen)
         return self.candidate_postings[int(np.argmin(d))][0]               # min_by: the first minimum

@@ -112,3 +112,17 @@ def test_config_mirror(tmp_path):
     p.write_text('clustering_params:\n  distance_metric: "Euclidean"\n  initialization_method: "Random"\n  initial_k: 0\n')
     with pytest.raises(ValueError):
         s.Config.from_file(str(p))
+
+
+def test_lire_bookkeeping_needs_no_device():
+    """validate() / get_affected_partitions() of the LIRE mirror are host logic (operations.rs:103-120)."""
+    import spfresh_b200 as s
+    vecs = [(3, [0.0, 1.0]), (9, [2.0, 2.0])]
+    op = s.Split(7, vecs, s.SquaredEuclideanDistance(), (8, 9))
+    assert op.validate() and op.get_affected_partitions() == {7, 8, 9}
+    assert not s.Split(7, vecs, s.SquaredEuclideanDistance(), (8, 8)).validate()
+    assert not s.Split(7, vecs[:1], s.SquaredEuclideanDistance(), (8, 9)).validate()
+    with pytest.raises(s.LireError):
+        s.Split(7, vecs[:1], s.SquaredEuclideanDistance(), (8, 9)).select_initial_centroids()
+    with pytest.raises(s.LireError):
+        s.Reassign(1, [0.0, 1.0], 5, [], s.SquaredEuclideanDistance(), 1).find_best_posting()
