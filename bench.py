@@ -115,15 +115,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_assign_sample(rows: np.ndarray, sample: int, threads: int = 0):
+def cpu_assign_sample(rows: np.ndarray, sample: int, threads: int = 0, want_result: bool = False):
     """Oracle (C restatement of the reference CPU path) on the first `sample` rows, all centroids."""
     import oracle
     oracle.build()
     cent = np.arange(K_CENT, dtype=np.uint64)
     idx = np.arange(K_CENT, K_CENT + sample, dtype=np.uint64)      # real shard rows, not the centroids
     t0 = time.perf_counter()
-    oracle.assign(rows, oracle.EUCLIDEAN, cent, point_idx=idx, threads=threads)
-    return time.perf_counter() - t0
+    res = oracle.assign(rows, oracle.EUCLIDEAN, cent, point_idx=idx, threads=threads)
+    dt = time.perf_counter() - t0
+    return (dt, res) if want_result else dt
+
+
+def parity_of_timed_step(gpu, ref, sample: int) -> dict:
+    """Full-size parity of the step that was timed: the oracle's answer for the sampled rows
+    [K_CENT, K_CENT + sample) against the GPU result of the same 1M x 4096 assign — nearest slot,
+    distance bits, and every cluster's member list restricted to those rows (order included)."""
+    lo, hi = K_CENT, K_CENT + sample
+    ok_best = bool(np.array_equal(gpu.best[lo:hi], ref.best))
+    ok_dmin = bool(np.array_equal(gpu.dmin[lo:hi].view(np.uint32), ref.dmin.view(np.uint32)))
+    mask = (gpu.members >= lo) & (gpu.members < hi)
+    ok_members = bool(np.array_equal(gpu.members[mask], ref.members))
+    cum = np.concatenate([[0], np.cumsum(mask, dtype=np.int64)])
+    ok_offsets = bool(np.array_equal(cum[gpu.offsets.astype(np.int64)], ref.offsets.astype(np.int64)))
+    return {"parity_checked_rows": int(sample), "parity_ok": ok_best and ok_dmin and ok_members and ok_offsets,
+            "parity_detail": {"best": ok_best, "dmin_bits": ok_dmin, "member_lists": ok_members, "offsets": ok_offsets,
+                              "memberships_compared": int(ref.members.size)}}
 
 
 def run_reference(args, rank, world):
@@ -306,6 +323,12 @@ def main():
             acc[k].append(max(ctx.kernel_ms(k), 0.0))
     ctx.set_profiling(False)
     kms = {k: float(np.mean(v)) for k, v in acc.items()}
+    # the result of the timed step, kept for the full-size parity check against the CPU leg below
+    gpu_fetched = None
+    if not args.no_cpu and rank == 0:
+        r_keep = ds.assign(spf.METRIC_EUCLIDEAN, cent)
+        gpu_fetched = r_keep.fetch()
+        r_keep.free()
 
     # ---- e2e -------------------------------------------------------------------------------------
     for _ in range(2):
@@ -393,15 +416,18 @@ def main():
 
     # ---- CPU side-by-side (rank 0, bounded sample) -------------------------------------------------
     cpu = None
+    parity = {"parity_checked_rows": 0, "parity_ok": None}
     if not args.no_cpu and rank == 0:
         import oracle
         cores = oracle.online_cpus()
         t_small = cpu_assign_sample(rows_np, 8192)
         sample = int(min(N_ROWS - K_CENT, max(8192, 8192 * 12.0 / max(t_small, 1e-3))))
-        t_cpu = cpu_assign_sample(rows_np, sample)
+        t_cpu, ref_res = cpu_assign_sample(rows_np, sample, want_result=True)
         cpu = {"value": sample / t_cpu, "unit": "points/s", "cores": cores, "kind": "port",
                "sample": f"{sample} of 1e6 rows x all 4096 centroids in {t_cpu:.1f} s; C restatement of the Rust "
                          "reference CPU path (cargo/rustc absent), gcc -O2 -ffp-contract=off, one task per point on all cores"}
+        parity = parity_of_timed_step(gpu_fetched, ref_res, sample)
+        del ref_res
 
     if rank == 0:
         line = {
@@ -422,6 +448,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_checked_rows": parity["parity_checked_rows"], "parity_ok": parity["parity_ok"],
+            "parity_detail": parity.get("parity_detail"),
             "kernels_ms": kms,
             "sharded_kmeans_iteration": sharded,
             "query": query,
@@ -430,6 +458,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity["parity_ok"] is False:
+        raise SystemExit("bench.py: the GPU result of the timed step differs from the CPU oracle")
 
 
 def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src):

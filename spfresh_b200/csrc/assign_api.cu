@@ -72,8 +72,11 @@ struct AssignCall {
   uint32_t k = 0, ld = 0;
   float factor = 1.0f;
   bool want_members = true, use_tc = false;
+  int nsplit = 2;                // column parts / record segments per point of the tensor kernel
+  const float* seed = nullptr;   // optional device array (m): upper bounds of the minimum distances
   uint64_t m = 0, chunk_rows = 0;
-  DevBuf<float> Cg, ctf, cnorm, cres, cstat, cext, cc;
+  DevBuf<float> Cg, ctf, cnorm, cres, cstat, cext, cc_own;
+  const float* cc = nullptr;     // k x k exact centroid-centroid distances (own buffer or the context's cache)
   DevBuf<CandRec> cand_rec;
   DevBuf<RowInfo> cand_info;
   CandBuf cand;
@@ -86,8 +89,17 @@ struct AssignCall {
 // Candidate group records per point.  Long rows have concentrated distances (the 1.1 boundary band
 // covers far more centroids until the running minimum has tightened) and a wider TF32 bound, so the
 // tensor path keeps four times as many records per point there unless the knob was set explicitly.
+int effective_nsplit(const spf_ctx* c, uint32_t ld) {
+  // 16 epilogue warps pay off when the epilogue is exposed (short rows); long rows hide it behind
+  // the MMAs of their many K blocks and keep the wider segments of the 8-warp variant
+  if (c->params.tc_epi_split == 2 || c->params.tc_epi_split == 4) return c->params.tc_epi_split;
+  return ld <= 256 ? 4 : 2;
+}
+
 int effective_cand_cap(const spf_ctx* c, bool use_tc, uint32_t ld) {
   if (c->params.cand_cap == 128 && use_tc && ld > 256) return 512;
+  // four segments per point: a segment holds a quarter of the records, keep 48 per segment
+  if (c->params.cand_cap == 128 && use_tc && effective_nsplit(c, ld) == 4) return 192;
   return c->params.cand_cap;
 }
 
@@ -105,6 +117,8 @@ int assign_setup(AssignCall& a) {
   spf_ctx* c = a.c;
   cudaStream_t st = c->stream;
   a.cand.cap = effective_cand_cap(c, a.use_tc, a.ld);
+  a.nsplit = effective_nsplit(c, a.ld);
+  if (a.cand.cap % a.nsplit) a.nsplit = 2;
   SPF_TRY(a.cand_rec.alloc(st, (size_t)a.chunk_rows * a.cand.cap));
   SPF_TRY(a.cand_info.alloc(st, a.chunk_rows));
   a.cand.rec = a.cand_rec.p;
@@ -122,9 +136,42 @@ int assign_setup(AssignCall& a) {
   }
   // exact centroid-centroid distances for the boundary rule `d(c_best, c_j) >= d_j` (:337-342)
   if (a.want_members && a.k > 1 && (int)a.k <= c->params.cc_matrix_max_k) {
-    SPF_TRY(a.cc.alloc(st, (size_t)a.k * a.k));
     KernelTimer t(c, "cc_matrix");
-    SPF_TRY(launch_assign_exact(c, a.metric, a.Cg.p, a.k, a.Cg.p, a.k, a.ld, 1.0f, nullptr, a.cc.p));
+    if (c->params.cc_cache != 0 && a.k >= 64 && a.k <= 8192) {
+      // The matrix depends only on the centroid vectors: keep it in the context and recompute it
+      // only when they changed.  The comparison runs on the device (no host round trip): the
+      // matrix kernel itself looks at the flag and returns at once when the cache is current.
+      spf_ctx::CcCache& cc = c->cc_cache;
+      const size_t nC = (size_t)a.k * a.ld;
+      if (cc.k != a.k || cc.ld != a.ld || !cc.cc) {
+        SPF_CUDA(cudaStreamSynchronize(st));
+        if (cc.cc) cudaFree(cc.cc);
+        if (cc.C) cudaFree(cc.C);
+        cc.cc = cc.C = nullptr;
+        cc.valid = false;
+        cc.k = a.k; cc.ld = a.ld;
+        if (!cc.same) SPF_CUDA(cudaMalloc((void**)&cc.same, sizeof(int)));
+        cudaError_t e = cudaMalloc((void**)&cc.cc, (size_t)a.k * a.k * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&cc.C, nC * sizeof(float));
+        if (e != cudaSuccess) {
+          if (cc.cc) cudaFree(cc.cc);
+          cc.cc = nullptr; cc.k = 0;
+          return fail(SPF_E_OOM, "allocation of the centroid matrix failed: %s", cudaGetErrorString(e));
+        }
+      }
+      const int init = (cc.valid && cc.metric == a.metric) ? 1 : 0;
+      SPF_CUDA(cudaMemsetAsync(cc.same, init, sizeof(int), st));
+      if (init) SPF_TRY(launch_rows_equal(c, a.Cg.p, cc.C, nC, cc.same));
+      SPF_TRY(launch_assign_exact(c, a.metric, a.Cg.p, a.k, a.Cg.p, a.k, a.ld, 1.0f, nullptr, cc.cc, cc.same));
+      SPF_CUDA(cudaMemcpyAsync(cc.C, a.Cg.p, nC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      cc.metric = a.metric;
+      cc.valid = true;
+      a.cc = cc.cc;
+    } else {
+      SPF_TRY(a.cc_own.alloc(st, (size_t)a.k * a.k));
+      SPF_TRY(launch_assign_exact(c, a.metric, a.Cg.p, a.k, a.Cg.p, a.k, a.ld, 1.0f, nullptr, a.cc_own.p));
+      a.cc = a.cc_own.p;
+    }
   }
   SPF_TRY(a.best.alloc(st, a.m));
   SPF_TRY(a.dmin.alloc(st, a.m));
@@ -137,10 +184,11 @@ ResolveArgs resolve_args(const AssignCall& a, const float* P, uint64_t m, const 
                          uint64_t r0) {
   ResolveArgs r;
   r.metric = a.metric; r.P = P; r.m = m; r.C = a.Cg.p; r.k = a.k; r.ld = a.ld; r.factor = a.factor;
-  r.cand = a.cand; r.nseg = a.use_tc ? 2 : 1;
+  r.cand = a.cand; r.nseg = a.use_tc ? a.nsplit : 1;
+  r.seed = (a.use_tc && a.seed) ? a.seed + r0 : nullptr;
   r.xnorm = a.use_tc ? xnorm : nullptr; r.xres = a.use_tc ? xres : nullptr;
   r.d_cstat = a.use_tc ? a.cstat.p : nullptr;
-  r.cc = a.cc.p; r.want_members = a.want_members;
+  r.cc = a.cc; r.want_members = a.want_members;
   r.best = a.best.p + r0; r.dmin = a.dmin.p + r0; r.nmem = a.nmem.p + r0;
   return r;
 }
@@ -151,7 +199,8 @@ int assign_rows(AssignCall& a, const float* P, const float* Ptf, const float* xn
   spf_ctx* c = a.c;
   if (a.use_tc) {
     KernelTimer t(c, "assign_tc");
-    SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cext.p, a.cstat.p, a.factor, a.cand));
+    SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cext.p, a.cstat.p,
+                             a.seed ? a.seed + r0 : nullptr, a.factor, a.cand, a.nsplit));
   } else {
     KernelTimer t(c, "assign_exact");
     SPF_TRY(launch_assign_exact(c, a.metric, P, mc, a.Cg.p, a.k, a.ld, a.factor, &a.cand, nullptr));

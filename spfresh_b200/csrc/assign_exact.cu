@@ -25,7 +25,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(NTHREADS)
 assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __restrict__ C, uint32_t k,
                     uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
-                    int cap, float* __restrict__ dense, int symmetric) {
+                    int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;   // the caller already holds this result (cached centroid matrix)
   __shared__ __align__(16) float Xs[2][BK][BM + PAD];
   __shared__ __align__(16) float Cs[2][BK][BN + PAD];
   __shared__ unsigned rowmin[BM];
@@ -154,14 +155,19 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   }
   if (cand != nullptr) {
     __syncthreads();
-    if (tid < BM && row0 + tid < m) info[row0 + tid] = make_uint4(rowcnt[tid], rowmin[tid], 0u, 0x7f800000u);
+    if (tid < BM && row0 + tid < m) {
+      RowInfo ri;
+      ri.cnt[0] = rowcnt[tid]; ri.best[0] = rowmin[tid];
+      for (int s = 1; s < MAX_SEG; ++s) { ri.cnt[s] = 0u; ri.best[s] = 0x7f800000u; }
+      info[row0 + tid] = ri;
+    }
   }
 }
 
 }  // namespace
 
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, const CandBuf* cb, float* dense) {
+                        uint32_t ld, float factor, const CandBuf* cb, float* dense, const int* d_skip) {
   // a dense P x P request is the symmetric centroid matrix: half the tiles
   const int symmetric = (cb == nullptr && dense != nullptr && P == C && m == k) ? 1 : 0;
   if (m == 0 || k == 0) return SPF_OK;
@@ -177,15 +183,15 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   switch (metric) {
     case SPF_METRIC_EUCLIDEAN:
       assign_exact_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip);
       break;
     case SPF_METRIC_MANHATTAN:
       assign_exact_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip);
       break;
     case SPF_METRIC_CHEBYSHEV:
       assign_exact_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip);
       break;
     default:
       return fail(SPF_E_INVALID, "unknown metric %d", metric);

@@ -18,15 +18,21 @@
 // columns passes the test the thread stores all four t values with one 128-bit store, which keeps
 // the per-hit instruction cost low; resolve filters the bystanders.
 //
-// Kernel anatomy (persistent, one CTA per SM, 320 threads):
+// Kernel anatomy (persistent, one CTA per SM, 64 + 128 * NSPLIT threads):
 //   warp 0     TMA producer: the 128 x ld point tile (A, stationary for a whole row block) and a
 //              4-stage ring of 256 x 32 centroid tiles (B), both SWIZZLE_128B, K-major
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=8 per MMA)
-//   warps 2-9  epilogue (two warps per SM sub-partition so one hides the other's latencies):
-//              warp w reads TMEM lane quarter w%4 and column half (w-2)/4 of the double-buffered
-//              2 x 256 column accumulator, 32 columns per tcgen05.ld; one point x 128 columns
-//              per thread and tile: running minimum (shared between the two halves through
-//              shared memory) + candidate emission with predicated stores
+//   warps 2..  epilogue, 4 * NSPLIT warps (NSPLIT = 2 or 4 warps per SM sub-partition, so that the
+//              latencies of one — tcgen05.ld round trips, dependent min chains — hide behind the
+//              others): warp w reads TMEM lane quarter w%4 and column part (w-2)/4 of the
+//              double-buffered 2 x 256 column accumulator, 32 columns per tcgen05.ld; one point x
+//              256/NSPLIT columns per thread and tile: running minimum (shared between the parts
+//              of a row through shared memory) + candidate emission with predicated stores.
+//              The K = 128 epilogue is latency-bound, not issue-bound (round 1: 35 % issue
+//              utilisation with 8 warps), which is what the 16-warp variant addresses.
+// An optional per-point seed (a certified upper bound of the point's minimum distance, e.g. the
+// running minimum of the k-means++ rounds or the distance to the previous iteration's centroid)
+// tightens the candidate test from the first column on; resolve validates it a posteriori.
 #include "tc_ptx.cuh"
 
 namespace spf {
@@ -39,8 +45,6 @@ constexpr int KB_MAX = 4;          // stationary A supports ld <= 128
 constexpr int NSTAGE = 4;          // B ring depth
 constexpr int A_KB_BYTES = BM * BK * 4;       // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 4;    // 32 KB
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_A = KB_MAX * A_KB_BYTES;                  // 64 KB
 constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
@@ -53,8 +57,8 @@ constexpr int BEXT_BYTES = BN * EXT_K * 4;                   // 8 KB per tile
 constexpr int SMEM_AEXT_OFF = SMEM_A + SMEM_B;
 constexpr int SMEM_BEXT_OFF = SMEM_AEXT_OFF + AEXT_BYTES;
 constexpr int SMEM_BAR_OFF = SMEM_BEXT_OFF + NEXT * BEXT_BYTES;
-constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [2][128]
-constexpr int SMEM_TOTAL = SMEM_PUB_OFF + 2 * BM * 8 + 1024; // + alignment slack
+constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [NSPLIT][128]
+constexpr int SMEM_TOTAL = SMEM_PUB_OFF + MAX_SEG * BM * 8 + 1024; // + alignment slack
 
 struct TcArgs {
   uint32_t m, k, ld, kb;            // kb = ceil(ld / 32) K blocks
@@ -62,10 +66,14 @@ struct TcArgs {
   uint32_t nrowblocks;              // ceil(m / 128)
   float factor;
   const float* xnorm; const float* xres; const float* cstat;
+  const float* seed;                // optional: per point an upper bound of its minimum distance
   CandRec* rec; RowInfo* info; int cap;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// (__maxnreg__ instead of __launch_bounds__: for the 576-thread variant the latter would allot 96
+// registers, 18 warps x 112 fit the register file)
+template <int NSPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(NSPLIT == 4 ? 112 : 200)
 assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_e, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -85,6 +93,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* smem_aext = smem + SMEM_AEXT_OFF;
   unsigned char* smem_bext = smem + SMEM_BEXT_OFF;
 
+  constexpr int NUM_EPI_WARPS = 4 * NSPLIT;
+  constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+  constexpr int PART_COLS = BN / NSPLIT;       // accumulator columns per epilogue thread and tile
+  constexpr int NCHUNK = PART_COLS / 32;       // tcgen05.ld chunks per thread and tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -99,7 +111,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int i = 0; i < NEXT; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x >= 64) reinterpret_cast<unsigned long long*>(smem + SMEM_PUB_OFF)[threadIdx.x - 64] = ~0ull;
+  for (int i = threadIdx.x; i < MAX_SEG * BM; i += NUM_THREADS)
+    reinterpret_cast<unsigned long long*>(smem + SMEM_PUB_OFF)[i] = ~0ull;
   // A side of the K extension: every row {1,1,0,0, 1,1,0,0}.  Both 16-byte halves are equal, so the
   // SWIZZLE_32B permutation leaves the tile unchanged and it can be written directly.
   for (int i = threadIdx.x; i < BM * 2; i += NUM_THREADS)
@@ -195,15 +208,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // =============================== epilogue warps ==========================================
     const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
-    const uint32_t half = (uint32_t)(warp - 2) >> 2;      // column half of every accumulator
+    const uint32_t part = (uint32_t)(warp - 2) >> 2;      // column part of every accumulator
     const uint32_t lrow = quarter * 32 + lane;
     const float INF = __int_as_float(0x7f800000);
     const float cnmax = a.cstat[0], dcmax = a.cstat[1];
     const float f1 = fmaxf(a.factor, 1.0f);
-    const uint32_t segcap = (uint32_t)a.cap >> 1;
+    const uint32_t segcap = (uint32_t)a.cap / (uint32_t)NSPLIT;
     const uint32_t segbytes = segcap * (uint32_t)sizeof(CandRec);
-    const uint32_t pub_mine = smem_u32(smem + SMEM_PUB_OFF) + (half * BM + lrow) * 8u;
-    const uint32_t pub_other = smem_u32(smem + SMEM_PUB_OFF) + ((half ^ 1u) * BM + lrow) * 8u;
+    const uint32_t pub_base = smem_u32(smem + SMEM_PUB_OFF) + lrow * 8u;
+    const uint32_t pub_mine = pub_base + part * (BM * 8u);
+    uint32_t rot = 1;                                     // partner whose published maximum is read next
     uint32_t tcount = 0;
     for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
       const uint32_t row = rb * BM + lrow;
@@ -214,18 +228,26 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool hopeless = !(E < INF) || !(xn < INF);
       const float xnE = xn + E, xmE = xn - E;
       const float slop = 1e-6f * (xn + cnmax) + 1e-30f;
+      // seed: some centroid has d_ref <= seed, hence d_tf32 <= seed + E and the final maximum of s
+      // is at least (|x|^2 - seed - E) / 2 (minus rounding slop).  resolve checks that the observed
+      // maximum really reaches it and hands the row to the dense fallback otherwise.
+      float sseed = -INF;
+      if (a.seed != nullptr && row_ok) {
+        const float sd = a.seed[row];
+        if (sd < INF) sseed = tc_seed_bound(xn, sd, E, cnmax);
+      }
       // this thread's segment of the row's records
-      CandRec* const seg = a.rec + ((size_t)row * a.cap + (size_t)half * segcap);
+      CandRec* const seg = a.rec + ((size_t)row * a.cap + (size_t)part * segcap);
       uint32_t wo = 0;                                    // write offset into the segment, bytes
       uint32_t overflow = 0;                              // records that did not fit
-      float smax = -INF;                                  // running maximum of s = x.c - |c|^2/2
-      float other = -INF;                                 // the partner half's maximum, one chunk old
+      float smax = -INF;                                  // running maximum of s = x.c - |c|^2/2 over this part
+      float other = sseed;                                // best lower bound of the row's final maximum seen elsewhere
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(&t_full[buf], use & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
-        const uint32_t gtile = (t * BN + half * (BN / 2)) >> 2;
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + part * PART_COLS;
+        const uint32_t gtile = (t * BN + part * PART_COLS) >> 2;
 
         // one 32-column chunk of s: running maximum (= running minimum of d = |x|^2 - 2 s), candidate
         // emission
@@ -237,17 +259,22 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                          fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
           smax = fmaxf(smax, fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])),
                                    fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7]))));
-          // Exchange running maxima with the partner half of the same row through shared memory
-          // (tagged with the row block: any value published for this row block is a valid lower
-          // bound of the final maximum, so a stale one only makes the candidate set a little
-          // larger).  The partner's value is read one chunk late (`other` was loaded while the
-          // previous chunk was processed) to keep the shared-memory round trip off the critical path.
+          // Exchange running maxima with the other parts of the same row through shared memory
+          // (tagged with the row block: any value published for this row block is a lower bound of
+          // the row's final maximum, so a stale one only makes the candidate set a little larger).
+          // The partner's value is read one chunk late (`other` was loaded while the previous
+          // chunk was processed) to keep the shared-memory round trip off the critical path; with
+          // more than two parts the partners are read in rotation and every thread publishes the
+          // best bound it knows, so a new maximum reaches all parts within NSPLIT - 1 chunks.
           const float sshare = fmaxf(smax, other);
           {
             uint32_t pv_lo, pv_hi;
-            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pub_other) : "memory");
-            other = pv_hi == rb ? __uint_as_float(pv_lo) : -INF;
-            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(smax)), "r"(rb) : "memory");
+            const uint32_t pp = pub_base + ((part + rot) & (uint32_t)(NSPLIT - 1)) * (BM * 8u);
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pp) : "memory");
+            other = fmaxf(other, pv_hi == rb ? __uint_as_float(pv_lo) : -INF);
+            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(sshare)), "r"(rb)
+                         : "memory");
+            if (NSPLIT > 2) rot = rot == (uint32_t)(NSPLIT - 1) ? 1u : rot + 1u;
           }
           // candidate test  d < f (dmin_run + E) + E  with d = |x|^2 - 2 s, dmin_run = |x|^2 - 2 smax:
           //   s > ( |x|^2 - E - f (|x|^2 + E - 2 smax) ) / 2
@@ -261,16 +288,18 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (votes == 0) {
             // no lane has a candidate in this chunk
           } else if (__all_sync(0xffffffffu, room)) {
-            // fast path: straight-line predicated record stores (no per-group vote or branch)
+            // fast path: straight-line predicated record stores (no per-group vote or branch); both
+            // 16-byte halves of the record are written, so the 32-byte sector never needs a fill
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               asm volatile(
-                  "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t"
+                  "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t.reg .b32 z;\n\t"
                   "setp.gt.f32 p, %2, %3;\n\t"
                   "cvt.u64.u32 o, %0;\n\t"
                   "add.u64 a, %1, o;\n\t"
+                  "mov.b32 z, 0;\n\t"
                   "@p st.global.v4.b32 [a], {%4, %5, %6, %7};\n\t"
-                  "@p st.global.u32 [a+16], %8;\n\t"
+                  "@p st.global.v4.b32 [a+16], {%8, z, z, z};\n\t"
                   "@p add.u32 %0, %0, 32;\n\t}"
                   : "+r"(wo)
                   : "l"(seg), "f"(q[g]), "f"(thr_s), "r"(rr[g * 4 + 0]), "r"(rr[g * 4 + 1]), "r"(rr[g * 4 + 2]),
@@ -286,7 +315,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   CandRec* wp = reinterpret_cast<CandRec*>(reinterpret_cast<unsigned char*>(seg) + wo);
                   wp->t = make_float4(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1]),
                                       __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
-                  wp->g = gbase + g;
+                  *reinterpret_cast<uint4*>(&wp->g) = make_uint4(gbase + g, 0u, 0u, 0u);
                   wo += (uint32_t)sizeof(CandRec);
                 } else {
                   ++overflow;
@@ -296,28 +325,44 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         };
 
-        // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
-        // c+1 is in flight while chunk c is processed
         uint32_t ra[32], rbuf[32];
-        tc_ld32_issue(taddr, ra);
-        tc_ld32_wait(ra);
-        tc_ld32_issue(taddr + 32, rbuf);
-        process(ra, 0);
-        tc_ld32_wait(rbuf);
-        tc_ld32_issue(taddr + 64, ra);
-        process(rbuf, 1);
-        tc_ld32_wait(ra);
-        tc_ld32_issue(taddr + 96, rbuf);
-        process(ra, 2);
-        tc_ld32_wait(rbuf);
-        tc_fence_before();                                // this warp's part of the accumulator is read
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[buf]);
-        process(rbuf, 3);
+        if (NCHUNK == 2) {
+          // both chunks of this warp's columns are fetched at once and the accumulator is released
+          // before they are processed: the next MMA into this buffer never waits for the epilogue
+          // arithmetic, only for the TMEM reads
+          tc_ld32_issue(taddr, ra);
+          tc_ld32_issue(taddr + 32, rbuf);
+          tc_ld32_wait(ra);
+          tc_ld32_wait(rbuf);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+          process(ra, 0);
+          process(rbuf, 1);
+        } else {
+          // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
+          // c+1 is in flight while chunk c is processed
+          tc_ld32_issue(taddr, ra);
+          tc_ld32_wait(ra);
+          tc_ld32_issue(taddr + 32, rbuf);
+          process(ra, 0);
+          tc_ld32_wait(rbuf);
+          tc_ld32_issue(taddr + 64, ra);
+          process(rbuf, 1);
+          tc_ld32_wait(ra);
+          tc_ld32_issue(taddr + 96, rbuf);
+          process(ra, 2);
+          tc_ld32_wait(rbuf);
+          tc_fence_before();                                // this warp's part of the accumulator is read
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+          process(rbuf, 3);
+        }
       }
       if (row_ok) {
-        uint2* const info2 = reinterpret_cast<uint2*>(a.info + row) + half;
-        *info2 = make_uint2(hopeless ? segcap + 1u : wo / (uint32_t)sizeof(CandRec) + overflow, __float_as_uint(smax));
+        RowInfo* const ri = a.info + row;
+        ri->cnt[part] = hopeless ? segcap + 1u : wo / (uint32_t)sizeof(CandRec) + overflow;
+        ri->best[part] = __float_as_uint(smax);
       }
     }
   }
@@ -341,7 +386,7 @@ bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) 
 
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
-                     float factor, const CandBuf& cand) {
+                     const float* seed, float factor, const CandBuf& cand, int nsplit) {
   CUtensorMap map_a, map_b, map_e;
   SPF_TRY(make_map_k128(c, &map_a, Ptf, m, ld, BM));
   SPF_TRY(make_map_k128(c, &map_b, Ctf, k, ld, BN / 2));   // each CTA of a pair fetches half a tile
@@ -352,11 +397,16 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
   a.ntiles = (k + BN - 1) / BN;
   a.nrowblocks = (uint32_t)(ceil_div(m, 2 * BM) * 2);   // even: the CTAs of a pair walk the tiles in lockstep
   a.factor = factor;
-  a.xnorm = xnorm; a.xres = xres; a.cstat = d_cstat;
+  a.xnorm = xnorm; a.xres = xres; a.cstat = d_cstat; a.seed = seed;
   a.rec = cand.rec; a.info = cand.info; a.cap = cand.cap;
-  SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count & ~1u;
-  assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
+  if (nsplit == 4) {
+    SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    assign_tc_kernel<4><<<grid, 64 + 128 * 4, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
+  } else {
+    SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    assign_tc_kernel<2><<<grid, 64 + 128 * 2, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
+  }
   return check_launch(c, "assign_tc_kernel");
 }
 

@@ -52,6 +52,9 @@ struct Params {
   int scan_tc_bucket = 0;    // candidate entries per query kept by the tensor scan (overflow: exact fallback); 0: 256, or 1024 for d > 256
   int scan_tc_cmax_mb = 40960; // keep the bound pass's chunk maxima (one GEMM pass) while they fit in this many MB; 0: always two passes
   int scan_tc_tau_probes = 0;  // probes per query that take part in the bound pass (0: all)
+  int tc_epi_split = 0;      // column parts per point of the tensor assign kernel: 2 (8 epilogue warps), 4 (16), 0 automatic
+  int csr_sort = 1;          // CSR build: 1 single-pass counting sort (k <= 8192), 0 library radix sort
+  int cc_cache = 1;          // keep the k x k centroid matrix while the centroid vectors do not change
   int chunk_rows = 0;        // points per assign chunk (0: automatic)
   int work_cap = 0;          // exact-evaluation work-list entries per chunk (0: automatic, 8 per point)
 };
@@ -72,6 +75,16 @@ struct spf_ctx {
   uint32_t last_overflow_rows = 0;   // rows the last assign resolved through the dense fallback
   spf::Params params;
   void* tma_encode = nullptr;  // cuTensorMapEncodeTiled, resolved at context creation
+  // k x k centroid-centroid matrix of the last assign, kept while the centroid vectors stay the
+  // same bit for bit (checked on the device each call: assign_api.cu)
+  struct CcCache {
+    float* cc = nullptr;   // k x k
+    float* C = nullptr;    // k x ld centroid vectors the matrix was computed from
+    int* same = nullptr;   // device flag: 1 = this call's centroids equal the cached ones
+    uint32_t k = 0, ld = 0;
+    int metric = -1;
+    bool valid = false;
+  } cc_cache;
 };
 
 struct spf_dataset {

@@ -15,16 +15,20 @@ namespace spf {
 struct __align__(16) CandRec {
   float4 t;
   uint32_t g;
-  uint32_t pad[3];   // never written
+  uint32_t pad[3];   // written as zeros by the tensor kernel (whole 32-byte sector per record: no DRAM read-fill)
 };
 static constexpr uint32_t REC_G_MASK = 0x0fffffffu;
 static constexpr int REC_EXACT_SHIFT = 28;
 static constexpr uint32_t REC_ALL_EXACT = 0xf0000000u;
 static constexpr uint32_t NMEM_OVERFLOW_BIT = 0x80000000u;
-// Per point: x = records in segment 0 (a value > segment capacity marks an overflow), y = bits of
-// the best value the producer saw in segment 0's columns (tensor kernel: largest s; exact kernel:
-// smallest distance), z / w = the same for segment 1.
-typedef uint4 RowInfo;
+// Per point: cnt[s] = records in segment s (a value > segment capacity marks an overflow),
+// best[s] = bits of the best value the producer saw in segment s's columns (tensor kernel:
+// largest s; exact kernel: smallest distance).  The exact kernel uses segment 0 only.
+constexpr int MAX_SEG = 4;
+struct __align__(16) RowInfo {
+  uint32_t cnt[MAX_SEG];
+  uint32_t best[MAX_SEG];
+};
 
 // Certified bound on |d_tf32 - d_ref| for the tensor path.  d_tf32 = |x|^2 - 2 x'.c' + |c|^2 where
 // x' = rn_tf32(x), c' = rn_tf32(c) are the operands the GEMM reads (rounded copies made by
@@ -43,6 +47,16 @@ __host__ __device__ inline float tc_err_bound(float xn, float xres, float cnmax,
   const float sx = sqrtf(xn), sc = sqrtf(cnmax);
   const float op = 2.0f * (xres * sc + (sx + xres) * dcmax);
   return 1.01f * op + 3.0f * (float)(ld + 16) * 1.1920929e-7f * (xn + cnmax);
+}
+
+// Seeded candidate pass: `seed` is an upper bound of the point's minimum reference distance, so some
+// centroid has d_tf32 <= seed + E and the final maximum of s = x.c - |c|^2/2 is at least this value.
+// Evaluated with the same operations by the GEMM epilogue (initial bound) and by resolve (which
+// checks that the observed maximum reaches it; otherwise the seed was not a valid bound and the
+// point goes to the dense fallback).
+__device__ __forceinline__ float tc_seed_bound(float xn, float seed, float E, float cnmax) {
+  const float slop = __fadd_rn(__fmul_rn(1e-6f, __fadd_rn(xn, cnmax)), 1e-30f);
+  return __fsub_rn(__fmul_rn(0.5f, __fsub_rn(__fsub_rn(xn, seed), E)), slop);
 }
 
 // Candidate scratch of one assign call (device).
@@ -74,23 +88,28 @@ int launch_max_f32(spf_ctx* c, const float* p, uint64_t n, float* out1);   // ou
 int launch_pair_dist(spf_ctx* c, int metric, const float* A, uint32_t ldA, const uint64_t* idxA,
                      const float* B, uint32_t ldB, const uint32_t* idxB32, uint64_t fixedB,
                      uint32_t ld, uint64_t count, float* out);
+// *d_flag = 0 when a[0..n) and b[0..n) differ in any bit (left untouched otherwise)
+int launch_rows_equal(spf_ctx* c, const float* a, const float* b, uint64_t n, int* d_flag);
 int launch_check_rows(spf_ctx* c, const uint64_t* d_idx, uint64_t m, uint64_t n, int* d_flag);
 
 // ---- assign_exact.cu ----------------------------------------------------------------------
 // CUDA-core direct-form kernel: every distance of the m x k problem, exact.  Emits boundary
 // candidates (cand != NULL, one segment, all records exact) and/or the dense m x k matrix.
+// d_skip (optional device flag): when it is non-zero at run time the kernel does nothing.
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, const CandBuf* cand, float* dense);
+                        uint32_t ld, float factor, const CandBuf* cand, float* dense, const int* d_skip = nullptr);
 
 // ---- assign_tc.cu -------------------------------------------------------------------------
 // tcgen05 (TF32) candidate GEMM for squared-Euclidean: approximate distances with a certified
 // error bound, candidates only (two segments per point).  Ptf / Ctf are the rounded operands;
 // cext_pad holds round_up(k,256) K-extension rows of 8 floats (launch_centroid_ext);
 // cstat = {max |c|^2, max |c - c'|}.  Record values are s = x.c - |c|^2/2 (d ~ |x|^2 - 2 s).
+// seed (optional, m floats): per point an upper bound of its minimum distance.  nsplit = column
+// parts (= record segments) per point: 2 (8 epilogue warps) or 4 (16 epilogue warps).
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld);
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
-                     float factor, const CandBuf& cand);
+                     const float* seed, float factor, const CandBuf& cand, int nsplit);
 // K-extension rows for the tensor kernel: row j < k = {h, m, 0, 0, l, 0, 0, 0} with h + m + l =
 // -|c_j|^2 / 2 split into three TF32 values (residual < 2^-33 |c_j|^2); rows k .. kpad-1 = {-inf, 0, ...}.
 int launch_centroid_ext(spf_ctx* c, const float* cnorm, uint32_t k, uint32_t kpad, float* cext);
@@ -101,7 +120,8 @@ struct ResolveArgs {
   const float* P; uint64_t m; const float* C; uint32_t k; uint32_t ld;   // exact (unrounded) rows
   float factor;
   CandBuf cand;
-  int nseg;                // segments per point: 1 (exact kernel) or 2 (tensor kernel)
+  int nseg;                // segments per point: 1 (exact kernel), 2 or 4 (tensor kernel)
+  const float* seed;       // tensor path, optional: the seeds the candidate kernel used (validated here)
   const float* xnorm;      // NULL on the exact path (error bound 0)
   const float* xres;       // tensor path only
   const float* d_cstat;    // device {max |c|^2, max |c - c'|}, tensor path only

@@ -226,6 +226,22 @@ int launch_max_f32(spf_ctx* c, const float* p, uint64_t n, float* out1) {
   return check_launch(c, "max_f32_kernel");
 }
 
+__global__ void rows_equal_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint64_t n, int* flag) {
+  bool diff = false;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    diff = diff || a[i] != b[i];
+  if (__syncthreads_or(diff) && threadIdx.x == 0) *flag = 0;
+}
+
+int launch_rows_equal(spf_ctx* c, const float* a, const float* b, uint64_t n, int* d_flag) {
+  if (n == 0) return SPF_OK;
+  uint64_t blocks = ceil_div(n, 256 * 8);
+  if (blocks > (uint64_t)c->sm_count * 8) blocks = (uint64_t)c->sm_count * 8;
+  rows_equal_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(a),
+                                                             reinterpret_cast<const uint32_t*>(b), n, d_flag);
+  return check_launch(c, "rows_equal_kernel");
+}
+
 int launch_check_rows(spf_ctx* c, const uint64_t* d_idx, uint64_t m, uint64_t n, int* d_flag) {
   if (m == 0) return SPF_OK;
   check_rows_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, c->stream>>>(d_idx, m, n, d_flag);
