@@ -154,10 +154,6 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
   else if (s == "cc_matrix_max_k") c->params.cc_matrix_max_k = value;
-  else if (s == "tc_epi_split") {
-    if (value != 0 && value != 2 && value != 4) return fail(SPF_E_INVALID, "tc_epi_split must be 0, 2 or 4");
-    c->params.tc_epi_split = value;
-  } else if (s == "csr_sort") c->params.csr_sort = value;
   else if (s == "cc_cache") c->params.cc_cache = value;
   else return fail(SPF_E_INVALID, "unknown parameter '%s'", name);
   return SPF_OK;

@@ -72,7 +72,6 @@ struct AssignCall {
   uint32_t k = 0, ld = 0;
   float factor = 1.0f;
   bool want_members = true, use_tc = false;
-  int nsplit = 2;                // column parts / record segments per point of the tensor kernel
   const float* seed = nullptr;   // optional device array (m): upper bounds of the minimum distances
   uint64_t m = 0, chunk_rows = 0;
   DevBuf<float> Cg, ctf, cnorm, cres, cstat, cext, cc_own;
@@ -89,17 +88,8 @@ struct AssignCall {
 // Candidate group records per point.  Long rows have concentrated distances (the 1.1 boundary band
 // covers far more centroids until the running minimum has tightened) and a wider TF32 bound, so the
 // tensor path keeps four times as many records per point there unless the knob was set explicitly.
-int effective_nsplit(const spf_ctx* c, uint32_t ld) {
-  // 16 epilogue warps pay off when the epilogue is exposed (short rows); long rows hide it behind
-  // the MMAs of their many K blocks and keep the wider segments of the 8-warp variant
-  if (c->params.tc_epi_split == 2 || c->params.tc_epi_split == 4) return c->params.tc_epi_split;
-  return ld <= 256 ? 4 : 2;
-}
-
 int effective_cand_cap(const spf_ctx* c, bool use_tc, uint32_t ld) {
   if (c->params.cand_cap == 128 && use_tc && ld > 256) return 512;
-  // four segments per point: a segment holds a quarter of the records, keep 48 per segment
-  if (c->params.cand_cap == 128 && use_tc && effective_nsplit(c, ld) == 4) return 192;
   return c->params.cand_cap;
 }
 
@@ -117,8 +107,6 @@ int assign_setup(AssignCall& a) {
   spf_ctx* c = a.c;
   cudaStream_t st = c->stream;
   a.cand.cap = effective_cand_cap(c, a.use_tc, a.ld);
-  a.nsplit = effective_nsplit(c, a.ld);
-  if (a.cand.cap % a.nsplit) a.nsplit = 2;
   SPF_TRY(a.cand_rec.alloc(st, (size_t)a.chunk_rows * a.cand.cap));
   SPF_TRY(a.cand_info.alloc(st, a.chunk_rows));
   a.cand.rec = a.cand_rec.p;
@@ -184,7 +172,7 @@ ResolveArgs resolve_args(const AssignCall& a, const float* P, uint64_t m, const 
                          uint64_t r0) {
   ResolveArgs r;
   r.metric = a.metric; r.P = P; r.m = m; r.C = a.Cg.p; r.k = a.k; r.ld = a.ld; r.factor = a.factor;
-  r.cand = a.cand; r.nseg = a.use_tc ? a.nsplit : 1;
+  r.cand = a.cand; r.nseg = a.use_tc ? 2 : 1;
   r.seed = (a.use_tc && a.seed) ? a.seed + r0 : nullptr;
   r.xnorm = a.use_tc ? xnorm : nullptr; r.xres = a.use_tc ? xres : nullptr;
   r.d_cstat = a.use_tc ? a.cstat.p : nullptr;
@@ -200,7 +188,7 @@ int assign_rows(AssignCall& a, const float* P, const float* Ptf, const float* xn
   if (a.use_tc) {
     KernelTimer t(c, "assign_tc");
     SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cext.p, a.cstat.p,
-                             a.seed ? a.seed + r0 : nullptr, a.factor, a.cand, a.nsplit));
+                             a.seed ? a.seed + r0 : nullptr, a.factor, a.cand));
   } else {
     KernelTimer t(c, "assign_exact");
     SPF_TRY(launch_assign_exact(c, a.metric, P, mc, a.Cg.p, a.k, a.ld, a.factor, &a.cand, nullptr));
@@ -248,10 +236,14 @@ int assign_finish(AssignCall& a, const float* P_all, const float* xnorm_all, con
 
 // Shared body of spf_assign (centroids = dataset rows) and spf_assign_vectors (centroids = explicit
 // k x d host vectors, the sharded build where a centroid may live on another rank).
+// centroid_dev: the vectors already on the device (k x ld, padded); d_seed: optional device array of
+// m per-point upper bounds of the minimum distance.  The caller holds the context lock.
 static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
-                           const uint64_t* centroid_rows, const float* centroid_vecs, uint32_t k,
-                           float boundary_factor, int flags, spf_assign_result** out) {
-  if (!ds || !out || (!centroid_rows && !centroid_vecs)) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
+                           const uint64_t* centroid_rows, const float* centroid_vecs, const float* centroid_dev,
+                           uint32_t k, float boundary_factor, int flags, const float* d_seed,
+                           spf_assign_result** out) {
+  if (!ds || !out || (!centroid_rows && !centroid_vecs && !centroid_dev))
+    return fail(SPF_E_INVALID, "spf_assign: NULL argument");
   *out = nullptr;
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
   if (k == 0) return fail(SPF_E_INVALID, "k must be > 0 (the reference indexes centroids[0])");
@@ -260,7 +252,6 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
   if (m == 0) return fail(SPF_E_INVALID, "m must be > 0");
   if (m >= (1ull << 32)) return fail(SPF_E_INVALID, "m must be < 2^32");
   spf_ctx* c = ds->ctx;
-  std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   c->kernel_ms.clear();
@@ -292,11 +283,14 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
   a.use_tc = metric == SPF_METRIC_EUCLIDEAN && !(flags & SPF_ASSIGN_FORCE_EXACT) && !c->params.force_exact &&
              assign_tc_supported(c, m, k, ld);
   a.chunk_rows = pick_chunk_rows(c, m, false, effective_cand_cap(c, a.use_tc, ld));
+  a.seed = a.use_tc ? d_seed : nullptr;
 
   // dense operands: centroids always materialised; points gathered only for a subset
   SPF_TRY(a.Cg.alloc(st, (size_t)k * ld));
   if (centroid_rows) {
     SPF_TRY(launch_gather_rows(c, ds->x, ld, d_crow.p, k, a.Cg.p));
+  } else if (centroid_dev) {
+    SPF_CUDA(cudaMemcpyAsync(a.Cg.p, centroid_dev, (size_t)k * ld * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
     if (ld != ds->d) SPF_CUDA(cudaMemsetAsync(a.Cg.p, 0, (size_t)k * ld * sizeof(float), st));
     SPF_CUDA(cudaMemcpy2DAsync(a.Cg.p, (size_t)ld * sizeof(float), centroid_vecs, (size_t)ds->d * sizeof(float),
@@ -332,20 +326,28 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
   return assign_finish(a, P, xnorm, xres, &d_pidx, out);
 }
 
+int spf::assign_device_centroids(spf_dataset* ds, int metric, const float* d_centroids, uint32_t k,
+                                 float boundary_factor, int flags, const float* d_seed, spf_assign_result** out) {
+  return assign_resident(ds, metric, nullptr, ds ? ds->n : 0, nullptr, nullptr, d_centroids, k, boundary_factor, flags,
+                         d_seed, out);
+}
+
 extern "C" {
 
 int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
                spf_assign_result** out) {
-  if (!centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
-  return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, k, boundary_factor, flags, out);
+  if (!ds || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
+  std::lock_guard<std::mutex> lk(ds->ctx->mu);
+  return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, nullptr, k, boundary_factor, flags, nullptr, out);
 }
 
 int spf_assign_vectors(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                        const float* centroids, uint32_t k, float boundary_factor, int flags,
                        spf_assign_result** out) {
-  if (!centroids) return fail(SPF_E_INVALID, "spf_assign_vectors: NULL argument");
-  return assign_resident(ds, metric, point_idx, m, nullptr, centroids, k, boundary_factor, flags, out);
+  if (!ds || !centroids) return fail(SPF_E_INVALID, "spf_assign_vectors: NULL argument");
+  std::lock_guard<std::mutex> lk(ds->ctx->mu);
+  return assign_resident(ds, metric, point_idx, m, nullptr, centroids, nullptr, k, boundary_factor, flags, nullptr, out);
 }
 
 int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride, int metric,

@@ -155,12 +155,7 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   }
   if (cand != nullptr) {
     __syncthreads();
-    if (tid < BM && row0 + tid < m) {
-      RowInfo ri;
-      ri.cnt[0] = rowcnt[tid]; ri.best[0] = rowmin[tid];
-      for (int s = 1; s < MAX_SEG; ++s) { ri.cnt[s] = 0u; ri.best[s] = 0x7f800000u; }
-      info[row0 + tid] = ri;
-    }
+    if (tid < BM && row0 + tid < m) info[row0 + tid] = make_uint4(rowcnt[tid], rowmin[tid], 0u, 0x7f800000u);
   }
 }
 

@@ -18,18 +18,20 @@
 // columns passes the test the thread stores all four t values with one 128-bit store, which keeps
 // the per-hit instruction cost low; resolve filters the bystanders.
 //
-// Kernel anatomy (persistent, one CTA per SM, 64 + 128 * NSPLIT threads):
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
 //   warp 0     TMA producer: the 128 x ld point tile (A, stationary for a whole row block) and a
 //              4-stage ring of 256 x 32 centroid tiles (B), both SWIZZLE_128B, K-major
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=8 per MMA)
-//   warps 2..  epilogue, 4 * NSPLIT warps (NSPLIT = 2 or 4 warps per SM sub-partition, so that the
-//              latencies of one — tcgen05.ld round trips, dependent min chains — hide behind the
-//              others): warp w reads TMEM lane quarter w%4 and column part (w-2)/4 of the
-//              double-buffered 2 x 256 column accumulator, 32 columns per tcgen05.ld; one point x
-//              256/NSPLIT columns per thread and tile: running minimum (shared between the parts
-//              of a row through shared memory) + candidate emission with predicated stores.
-//              The K = 128 epilogue is latency-bound, not issue-bound (round 1: 35 % issue
-//              utilisation with 8 warps), which is what the 16-warp variant addresses.
+//   warps 2-9  epilogue (two warps per SM sub-partition so one hides the other's latencies):
+//              warp w reads TMEM lane quarter w%4 and column half (w-2)/4 of the double-buffered
+//              2 x 256 column accumulator: all 128 columns of the thread's point go to registers
+//              (4 x tcgen05.ld 32x32b.x32), the accumulator is released, then per 32-column chunk:
+//              running minimum (shared between the two halves through shared memory), one-FFMA
+//              threshold, candidate emission with predicated 256-bit stores.
+// Round-2 measurements (1M x 128, k = 4096, profiles/r02_experiment_notes.md): 16 epilogue warps
+// (96 registers) 2.10 ms, pipelined loads + two 128-bit stores 1.85 ms, 256-bit stores 1.80 ms,
+// load-all-first + 256-bit stores 1.76 ms; the same instruction stream with no record stores 1.66 ms,
+// MMA + TMA alone 1.48 ms.
 // An optional per-point seed (a certified upper bound of the point's minimum distance, e.g. the
 // running minimum of the k-means++ rounds or the distance to the previous iteration's centroid)
 // tightens the candidate test from the first column on; resolve validates it a posteriori.
@@ -45,6 +47,8 @@ constexpr int KB_MAX = 4;          // stationary A supports ld <= 128
 constexpr int NSTAGE = 4;          // B ring depth
 constexpr int A_KB_BYTES = BM * BK * 4;       // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 4;    // 32 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_A = KB_MAX * A_KB_BYTES;                  // 64 KB
 constexpr int SMEM_B = NSTAGE * B_STAGE_BYTES;               // 128 KB
@@ -57,8 +61,8 @@ constexpr int BEXT_BYTES = BN * EXT_K * 4;                   // 8 KB per tile
 constexpr int SMEM_AEXT_OFF = SMEM_A + SMEM_B;
 constexpr int SMEM_BEXT_OFF = SMEM_AEXT_OFF + AEXT_BYTES;
 constexpr int SMEM_BAR_OFF = SMEM_BEXT_OFF + NEXT * BEXT_BYTES;
-constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [NSPLIT][128]
-constexpr int SMEM_TOTAL = SMEM_PUB_OFF + MAX_SEG * BM * 8 + 1024; // + alignment slack
+constexpr int SMEM_PUB_OFF = SMEM_BAR_OFF + 256;             // published (row block, running min) [2][128]
+constexpr int SMEM_TOTAL = SMEM_PUB_OFF + 2 * BM * 8 + 1024; // + alignment slack
 
 struct TcArgs {
   uint32_t m, k, ld, kb;            // kb = ceil(ld / 32) K blocks
@@ -70,10 +74,7 @@ struct TcArgs {
   CandRec* rec; RowInfo* info; int cap;
 };
 
-// (__maxnreg__ instead of __launch_bounds__: for the 576-thread variant the latter would allot 96
-// registers, 18 warps x 112 fit the register file)
-template <int NSPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(NSPLIT == 4 ? 112 : 200)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_e, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -93,10 +94,6 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* smem_aext = smem + SMEM_AEXT_OFF;
   unsigned char* smem_bext = smem + SMEM_BEXT_OFF;
 
-  constexpr int NUM_EPI_WARPS = 4 * NSPLIT;
-  constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
-  constexpr int PART_COLS = BN / NSPLIT;       // accumulator columns per epilogue thread and tile
-  constexpr int NCHUNK = PART_COLS / 32;       // tcgen05.ld chunks per thread and tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -111,8 +108,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int i = 0; i < NEXT; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < MAX_SEG * BM; i += NUM_THREADS)
-    reinterpret_cast<unsigned long long*>(smem + SMEM_PUB_OFF)[i] = ~0ull;
+  if (threadIdx.x >= 64) reinterpret_cast<unsigned long long*>(smem + SMEM_PUB_OFF)[threadIdx.x - 64] = ~0ull;
   // A side of the K extension: every row {1,1,0,0, 1,1,0,0}.  Both 16-byte halves are equal, so the
   // SWIZZLE_32B permutation leaves the tile unchanged and it can be written directly.
   for (int i = threadIdx.x; i < BM * 2; i += NUM_THREADS)
@@ -208,16 +204,18 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // =============================== epilogue warps ==========================================
     const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
-    const uint32_t part = (uint32_t)(warp - 2) >> 2;      // column part of every accumulator
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;      // column half of every accumulator
     const uint32_t lrow = quarter * 32 + lane;
     const float INF = __int_as_float(0x7f800000);
     const float cnmax = a.cstat[0], dcmax = a.cstat[1];
     const float f1 = fmaxf(a.factor, 1.0f);
-    const uint32_t segcap = (uint32_t)a.cap / (uint32_t)NSPLIT;
+    const uint32_t segcap = (uint32_t)a.cap >> 1;
     const uint32_t segbytes = segcap * (uint32_t)sizeof(CandRec);
-    const uint32_t pub_base = smem_u32(smem + SMEM_PUB_OFF) + lrow * 8u;
-    const uint32_t pub_mine = pub_base + part * (BM * 8u);
-    uint32_t rot = 1;                                     // partner whose published maximum is read next
+    const uint32_t pub_mine = smem_u32(smem + SMEM_PUB_OFF) + (half * BM + lrow) * 8u;
+    const uint32_t pub_other = smem_u32(smem + SMEM_PUB_OFF) + ((half ^ 1u) * BM + lrow) * 8u;
+    // the three don't-care words of a record (never read by resolve): any registers, so that the
+    // record is one 256-bit store
+    const uint32_t z1 = lrow, z2 = warp, z3 = threadIdx.x;
     uint32_t tcount = 0;
     for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
       const uint32_t row = rb * BM + lrow;
@@ -226,28 +224,36 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const float E = tc_err_bound(xn, row_ok ? a.xres[row] : 0.0f, cnmax, dcmax, a.ld);
       // non-finite norms or bounds: no certified test exists, the brute-force kernels own the row
       const bool hopeless = !(E < INF) || !(xn < INF);
-      const float xnE = xn + E, xmE = xn - E;
+      // candidate test  d < f (dmin_run + E) + E  with d = |x|^2 - 2 s, dmin_run = |x|^2 - 2 smax:
+      //   s > f smax + ( |x|^2 - E - f (|x|^2 + E) ) / 2
+      // one FFMA per chunk; `slop` covers the roundings of this form (a few ulps of |s|, |x|^2).
       const float slop = 1e-6f * (xn + cnmax) + 1e-30f;
+      const float thrK = row_ok ? 0.5f * ((xn - E) - f1 * (xn + E)) - slop : INF;
       // seed: some centroid has d_ref <= seed, hence d_tf32 <= seed + E and the final maximum of s
-      // is at least (|x|^2 - seed - E) / 2 (minus rounding slop).  resolve checks that the observed
-      // maximum really reaches it and hands the row to the dense fallback otherwise.
+      // is at least tc_seed_bound().  resolve checks that the observed maximum really reaches it
+      // and hands the row to the dense fallback otherwise.
       float sseed = -INF;
       if (a.seed != nullptr && row_ok) {
         const float sd = a.seed[row];
         if (sd < INF) sseed = tc_seed_bound(xn, sd, E, cnmax);
       }
-      // this thread's segment of the row's records
-      CandRec* const seg = a.rec + ((size_t)row * a.cap + (size_t)part * segcap);
-      uint32_t wo = 0;                                    // write offset into the segment, bytes
+      // this thread's segment of the row's records: write pointer and end
+      const unsigned long long seg = (unsigned long long)(a.rec + ((size_t)row * a.cap + (size_t)half * segcap));
+      const unsigned long long wend = seg + segbytes;
+      uint32_t wlo = (uint32_t)seg, whi = (uint32_t)(seg >> 32);   // write pointer
       uint32_t overflow = 0;                              // records that did not fit
-      float smax = -INF;                                  // running maximum of s = x.c - |c|^2/2 over this part
-      float other = sseed;                                // best lower bound of the row's final maximum seen elsewhere
+      float smax = -INF;                                  // running maximum of s = x.c - |c|^2/2 over this half
+      float other = sseed;                                // bound from the seed / the partner half (one chunk old)
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(&t_full[buf], use & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + part * PART_COLS;
-        const uint32_t gtile = (t * BN + part * PART_COLS) >> 2;
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
+        const uint32_t gtile = (t * BN + half * (BN / 2)) >> 2;
+        // a tile emits at most 32 records per thread: when every thread of the warp has room for
+        // them, the whole tile takes the straight-line path without any further capacity test
+        const bool fast = __all_sync(0xffffffffu, (((unsigned long long)whi << 32) | wlo) + 32ull * sizeof(CandRec) <= wend &&
+                                                      wlo <= 0xffffffffu - 32u * (uint32_t)sizeof(CandRec));
 
         // one 32-column chunk of s: running maximum (= running minimum of d = |x|^2 - 2 s), candidate
         // emission
@@ -259,51 +265,38 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                          fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
           smax = fmaxf(smax, fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])),
                                    fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7]))));
-          // Exchange running maxima with the other parts of the same row through shared memory
-          // (tagged with the row block: any value published for this row block is a lower bound of
-          // the row's final maximum, so a stale one only makes the candidate set a little larger).
-          // The partner's value is read one chunk late (`other` was loaded while the previous
-          // chunk was processed) to keep the shared-memory round trip off the critical path; with
-          // more than two parts the partners are read in rotation and every thread publishes the
-          // best bound it knows, so a new maximum reaches all parts within NSPLIT - 1 chunks.
+          // Exchange running maxima with the partner half of the same row through shared memory
+          // (tagged with the row block: any value published for this row block is a valid lower
+          // bound of the final maximum, so a stale one only makes the candidate set a little
+          // larger).  The partner's value is read one chunk late (`other` was loaded while the
+          // previous chunk was processed) to keep the shared-memory round trip off the critical path.
           const float sshare = fmaxf(smax, other);
           {
             uint32_t pv_lo, pv_hi;
-            const uint32_t pp = pub_base + ((part + rot) & (uint32_t)(NSPLIT - 1)) * (BM * 8u);
-            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pp) : "memory");
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pv_lo), "=r"(pv_hi) : "r"(pub_other) : "memory");
             other = fmaxf(other, pv_hi == rb ? __uint_as_float(pv_lo) : -INF);
-            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(sshare)), "r"(rb)
-                         : "memory");
-            if (NSPLIT > 2) rot = rot == (uint32_t)(NSPLIT - 1) ? 1u : rot + 1u;
+            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_mine), "r"(__float_as_uint(smax)), "r"(rb) : "memory");
           }
-          // candidate test  d < f (dmin_run + E) + E  with d = |x|^2 - 2 s, dmin_run = |x|^2 - 2 smax:
-          //   s > ( |x|^2 - E - f (|x|^2 + E - 2 smax) ) / 2
-          const float thr_s = row_ok ? 0.5f * fmaf(-f1, fmaf(-2.0f, sshare, xnE), xmE) - slop : INF;
-          const uint32_t gbase = gtile + c * 8;
-          const bool room = wo + 8u * (uint32_t)sizeof(CandRec) <= segbytes;
-          bool anyhit = false;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) anyhit = anyhit || (q[g] > thr_s);
-          const unsigned votes = __ballot_sync(0xffffffffu, anyhit) | (__all_sync(0xffffffffu, room) ? 0u : 0x80000000u);
-          if (votes == 0) {
-            // no lane has a candidate in this chunk
-          } else if (__all_sync(0xffffffffu, room)) {
-            // fast path: straight-line predicated record stores (no per-group vote or branch); both
-            // 16-byte halves of the record are written, so the 32-byte sector never needs a fill
+          const float thr_s = fmaf(f1, sshare, thrK);
+          uint32_t gi = gtile + c * 8;                     // group index of the record being tested
+          if (fast) {
+            // straight-line predicated record stores, no vote and no branch: one 256-bit store per
+            // record — half the store transactions of two 128-bit stores (measured: 1.81 -> 1.76 ms)
+            // and the whole 32-byte sector is written, so DRAM never has to read-fill it.  The last
+            // three words are don't-care registers.  `fast` guarantees that the low pointer word
+            // cannot wrap inside this tile, so the pointer advances with one predicated 32-bit add.
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               asm volatile(
-                  "{\n\t.reg .pred p;\n\t.reg .u64 o, a;\n\t.reg .b32 z;\n\t"
-                  "setp.gt.f32 p, %2, %3;\n\t"
-                  "cvt.u64.u32 o, %0;\n\t"
-                  "add.u64 a, %1, o;\n\t"
-                  "mov.b32 z, 0;\n\t"
-                  "@p st.global.v4.b32 [a], {%4, %5, %6, %7};\n\t"
-                  "@p st.global.v4.b32 [a+16], {%8, z, z, z};\n\t"
-                  "@p add.u32 %0, %0, 32;\n\t}"
-                  : "+r"(wo)
-                  : "l"(seg), "f"(q[g]), "f"(thr_s), "r"(rr[g * 4 + 0]), "r"(rr[g * 4 + 1]), "r"(rr[g * 4 + 2]),
-                    "r"(rr[g * 4 + 3]), "r"(gbase + g)
+                  "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+                  "setp.gt.f32 p, %3, %4;\n\t"
+                  "mov.b64 a, {%0, %1};\n\t"
+                  "@p st.global.v8.b32 [a], {%5, %6, %7, %8, %2, %9, %10, %11};\n\t"
+                  "@p add.u32 %0, %0, 32;\n\t"
+                  "add.u32 %2, %2, 1;\n\t}"
+                  : "+r"(wlo), "+r"(whi), "+r"(gi)
+                  : "f"(q[g]), "f"(thr_s), "r"(rr[g * 4 + 0]), "r"(rr[g * 4 + 1]), "r"(rr[g * 4 + 2]),
+                    "r"(rr[g * 4 + 3]), "r"(z1), "r"(z2), "r"(z3)
                   : "memory");
             }
           } else {
@@ -311,12 +304,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               if (q[g] > thr_s) {
-                if (wo < segbytes) {
-                  CandRec* wp = reinterpret_cast<CandRec*>(reinterpret_cast<unsigned char*>(seg) + wo);
-                  wp->t = make_float4(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1]),
-                                      __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
-                  *reinterpret_cast<uint4*>(&wp->g) = make_uint4(gbase + g, 0u, 0u, 0u);
-                  wo += (uint32_t)sizeof(CandRec);
+                unsigned long long wp = ((unsigned long long)whi << 32) | wlo;
+                if (wp < wend) {
+                  CandRec* w = reinterpret_cast<CandRec*>(wp);
+                  w->t = make_float4(__uint_as_float(rr[g * 4 + 0]), __uint_as_float(rr[g * 4 + 1]),
+                                     __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
+                  *reinterpret_cast<uint4*>(&w->g) = make_uint4(gi + g, 0u, 0u, 0u);
+                  wp += sizeof(CandRec);
+                  wlo = (uint32_t)wp; whi = (uint32_t)(wp >> 32);
                 } else {
                   ++overflow;
                 }
@@ -325,44 +320,30 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         };
 
-        uint32_t ra[32], rbuf[32];
-        if (NCHUNK == 2) {
-          // both chunks of this warp's columns are fetched at once and the accumulator is released
-          // before they are processed: the next MMA into this buffer never waits for the epilogue
-          // arithmetic, only for the TMEM reads
-          tc_ld32_issue(taddr, ra);
-          tc_ld32_issue(taddr + 32, rbuf);
-          tc_ld32_wait(ra);
-          tc_ld32_wait(rbuf);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[buf]);
-          process(ra, 0);
-          process(rbuf, 1);
-        } else {
-          // software pipeline over the 4 chunks of this warp's column half: the TMEM load of chunk
-          // c+1 is in flight while chunk c is processed
-          tc_ld32_issue(taddr, ra);
-          tc_ld32_wait(ra);
-          tc_ld32_issue(taddr + 32, rbuf);
-          process(ra, 0);
-          tc_ld32_wait(rbuf);
-          tc_ld32_issue(taddr + 64, ra);
-          process(rbuf, 1);
-          tc_ld32_wait(ra);
-          tc_ld32_issue(taddr + 96, rbuf);
-          process(ra, 2);
-          tc_ld32_wait(rbuf);
-          tc_fence_before();                                // this warp's part of the accumulator is read
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[buf]);
-          process(rbuf, 3);
-        }
+        // The thread's whole slice of the accumulator (128 columns) goes to registers first and the
+        // TMEM buffer is released before any arithmetic: with only two accumulator buffers the
+        // next-but-one MMA may start as soon as the epilogue has *read* this one, so the tensor
+        // pipe waits for the epilogue's throughput only, never for its latency chain.
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tc_ld32_issue(taddr, r0);
+        tc_ld32_issue(taddr + 32, r1);
+        tc_ld32_issue(taddr + 64, r2);
+        tc_ld32_issue(taddr + 96, r3);
+        tc_ld32_wait(r0);
+        tc_ld32_wait(r1);
+        tc_ld32_wait(r2);
+        tc_ld32_wait(r3);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);
+        process(r0, 0);
+        process(r1, 1);
+        process(r2, 2);
+        process(r3, 3);
       }
       if (row_ok) {
-        RowInfo* const ri = a.info + row;
-        ri->cnt[part] = hopeless ? segcap + 1u : wo / (uint32_t)sizeof(CandRec) + overflow;
-        ri->best[part] = __float_as_uint(smax);
+        uint2* const info2 = reinterpret_cast<uint2*>(a.info + row) + half;
+        *info2 = make_uint2(hopeless ? segcap + 1u : (uint32_t)(((((unsigned long long)whi << 32) | wlo) - seg) / sizeof(CandRec)) + overflow, __float_as_uint(smax));
       }
     }
   }
@@ -386,7 +367,7 @@ bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) 
 
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
-                     const float* seed, float factor, const CandBuf& cand, int nsplit) {
+                     const float* seed, float factor, const CandBuf& cand) {
   CUtensorMap map_a, map_b, map_e;
   SPF_TRY(make_map_k128(c, &map_a, Ptf, m, ld, BM));
   SPF_TRY(make_map_k128(c, &map_b, Ctf, k, ld, BN / 2));   // each CTA of a pair fetches half a tile
@@ -400,13 +381,8 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
   a.xnorm = xnorm; a.xres = xres; a.cstat = d_cstat; a.seed = seed;
   a.rec = cand.rec; a.info = cand.info; a.cap = cand.cap;
   unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count & ~1u;
-  if (nsplit == 4) {
-    SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    assign_tc_kernel<4><<<grid, 64 + 128 * 4, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
-  } else {
-    SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    assign_tc_kernel<2><<<grid, 64 + 128 * 2, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
-  }
+  SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
   return check_launch(c, "assign_tc_kernel");
 }
 

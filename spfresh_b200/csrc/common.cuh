@@ -52,8 +52,6 @@ struct Params {
   int scan_tc_bucket = 0;    // candidate entries per query kept by the tensor scan (overflow: exact fallback); 0: 256, or 1024 for d > 256
   int scan_tc_cmax_mb = 40960; // keep the bound pass's chunk maxima (one GEMM pass) while they fit in this many MB; 0: always two passes
   int scan_tc_tau_probes = 0;  // probes per query that take part in the bound pass (0: all)
-  int tc_epi_split = 0;      // column parts per point of the tensor assign kernel: 2 (8 epilogue warps), 4 (16), 0 automatic
-  int csr_sort = 1;          // CSR build: 1 single-pass counting sort (k <= 8192), 0 library radix sort
   int cc_cache = 1;          // keep the k x k centroid matrix while the centroid vectors do not change
   int chunk_rows = 0;        // points per assign chunk (0: automatic)
   int work_cap = 0;          // exact-evaluation work-list entries per chunk (0: automatic, 8 per point)

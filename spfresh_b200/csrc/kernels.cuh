@@ -15,20 +15,16 @@ namespace spf {
 struct __align__(16) CandRec {
   float4 t;
   uint32_t g;
-  uint32_t pad[3];   // written as zeros by the tensor kernel (whole 32-byte sector per record: no DRAM read-fill)
+  uint32_t pad[3];   // written as zeros by the tensor kernel (one 256-bit store per record: whole sector, no DRAM read-fill)
 };
 static constexpr uint32_t REC_G_MASK = 0x0fffffffu;
 static constexpr int REC_EXACT_SHIFT = 28;
 static constexpr uint32_t REC_ALL_EXACT = 0xf0000000u;
 static constexpr uint32_t NMEM_OVERFLOW_BIT = 0x80000000u;
-// Per point: cnt[s] = records in segment s (a value > segment capacity marks an overflow),
-// best[s] = bits of the best value the producer saw in segment s's columns (tensor kernel:
-// largest s; exact kernel: smallest distance).  The exact kernel uses segment 0 only.
-constexpr int MAX_SEG = 4;
-struct __align__(16) RowInfo {
-  uint32_t cnt[MAX_SEG];
-  uint32_t best[MAX_SEG];
-};
+// Per point: x = records in segment 0 (a value > segment capacity marks an overflow), y = bits of
+// the best value the producer saw in segment 0's columns (tensor kernel: largest s; exact kernel:
+// smallest distance), z / w = the same for segment 1.
+typedef uint4 RowInfo;
 
 // Certified bound on |d_tf32 - d_ref| for the tensor path.  d_tf32 = |x|^2 - 2 x'.c' + |c|^2 where
 // x' = rn_tf32(x), c' = rn_tf32(c) are the operands the GEMM reads (rounded copies made by
@@ -104,12 +100,11 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
 // error bound, candidates only (two segments per point).  Ptf / Ctf are the rounded operands;
 // cext_pad holds round_up(k,256) K-extension rows of 8 floats (launch_centroid_ext);
 // cstat = {max |c|^2, max |c - c'|}.  Record values are s = x.c - |c|^2/2 (d ~ |x|^2 - 2 s).
-// seed (optional, m floats): per point an upper bound of its minimum distance.  nsplit = column
-// parts (= record segments) per point: 2 (8 epilogue warps) or 4 (16 epilogue warps).
+// seed (optional, m floats): per point an upper bound of its minimum distance.
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld);
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
-                     const float* seed, float factor, const CandBuf& cand, int nsplit);
+                     const float* seed, float factor, const CandBuf& cand);
 // K-extension rows for the tensor kernel: row j < k = {h, m, 0, 0, l, 0, 0, 0} with h + m + l =
 // -|c_j|^2 / 2 split into three TF32 values (residual < 2^-33 |c_j|^2); rows k .. kpad-1 = {-inf, 0, ...}.
 int launch_centroid_ext(spf_ctx* c, const float* cnorm, uint32_t k, uint32_t kpad, float* cext);
@@ -120,7 +115,7 @@ struct ResolveArgs {
   const float* P; uint64_t m; const float* C; uint32_t k; uint32_t ld;   // exact (unrounded) rows
   float factor;
   CandBuf cand;
-  int nseg;                // segments per point: 1 (exact kernel), 2 or 4 (tensor kernel)
+  int nseg;                // segments per point: 1 (exact kernel) or 2 (tensor kernel)
   const float* seed;       // tensor path, optional: the seeds the candidate kernel used (validated here)
   const float* xnorm;      // NULL on the exact path (error bound 0)
   const float* xres;       // tensor path only
@@ -201,7 +196,17 @@ int probe_tc_dense(spf_ctx* c, const ScanTcSide& side, const float* centroids, c
                    uint32_t nlists, uint32_t nprobe, float prune_factor, const uint32_t* lens, uint32_t* probe,
                    float* thr, uint32_t* seqbase, int* d_redo);
 
+// ---- ops.cu (shared with kmeans.cu) ---------------------------------------------------------
+int launch_cluster_sums(spf_ctx* c, const float* X, uint32_t ld, const uint64_t* d_offsets, const uint64_t* d_rows,
+                        uint32_t k, float* out, int divide);
+int launch_medoid_keys(spf_ctx* c, int metric, const float* X, uint32_t ld, const uint64_t* d_rows, uint64_t total,
+                       const uint64_t* d_offsets, uint32_t k, const float* means, unsigned long long* keys);
+
 // ---- assign_api.cu ------------------------------------------------------------------------
+// spf_assign_vectors with the k centroid vectors already on the device (k x ld, rows zero padded to
+// ld); the caller holds the context lock.
+int assign_device_centroids(spf_dataset* ds, int metric, const float* d_centroids, uint32_t k, float boundary_factor,
+                            int flags, const float* d_seed, spf_assign_result** out);
 int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out);   // api.cu: device buffer only
 int dataset_prep_alloc(spf_dataset* ds);
 int dataset_prep(spf_dataset* ds);   // rounded copy + norms of all rows, once per dataset

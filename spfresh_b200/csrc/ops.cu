@@ -720,6 +720,35 @@ unsigned pd_grid(spf_ctx* c, uint64_t count) {
   return (unsigned)(blocks > cap ? cap : (blocks ? blocks : 1));
 }
 
+}  // namespace
+
+// ---- launchers shared with kmeans.cu (the device-resident row-sharded iteration) ---------------
+// per-cluster f32 sums of the member rows in member order (divide != 0: the mean, utils.rs:13-14)
+int launch_cluster_sums(spf_ctx* c, const float* X, uint32_t ld, const uint64_t* d_offsets, const uint64_t* d_rows,
+                        uint32_t k, float* out, int divide) {
+  return launch_cluster_mean(c, X, ld, d_offsets, d_rows, k, out, divide);
+}
+
+// keys[c] = min over the members of cluster c of (distance to means[c] bits << 32 | position in
+// the member list), ~0 when the cluster is empty or no distance is < +inf (hierarchical.rs:155-171)
+int launch_medoid_keys(spf_ctx* c, int metric, const float* X, uint32_t ld, const uint64_t* d_rows, uint64_t total,
+                       const uint64_t* d_offsets, uint32_t k, const float* means, unsigned long long* keys) {
+  cudaStream_t st = c->stream;
+  SPF_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)k * sizeof(unsigned long long), st));
+  if (total == 0) return SPF_OK;
+  DevBuf<uint32_t> cid;
+  SPF_TRY(cid.alloc(st, total));
+  expand_cluster_ids_kernel<<<k, 256, 0, st>>>(d_offsets, cid.p);
+  SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
+  return dispatch_metric(metric, [&](auto M) {
+    medoid_kernel<decltype(M)::value><<<pd_grid(c, total), PD_THREADS, 0, st>>>(X, ld, d_rows, cid.p, d_offsets, means,
+                                                                                  total, keys);
+    return check_launch(c, "medoid_kernel");
+  });
+}
+
+namespace {
+
 // shared tail of the two spf_update_medoids entry points; d_offsets/d_rows are device arrays
 int update_medoids_dev(spf_dataset* ds, int metric, const uint64_t* d_offsets, const uint64_t* d_rows,
                        uint64_t total, uint32_t k, const uint64_t* old_rows, uint64_t* new_rows,

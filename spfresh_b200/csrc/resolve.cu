@@ -133,28 +133,24 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
   const uint32_t ent_flags = approx ? 0u : SE_EXACT;
   const float cnmax = approx ? a.cstat[0] : 0.0f, dcmax = approx ? a.cstat[1] : 0.0f;
 
-  const uint32_t npairs = ((uint32_t)a.nseg + 1u) >> 1;   // segments are read two at a time
   struct Rec2 { float4 t0, t1; uint32_t g0, g1; };
-  // record i of segments 2p and 2p+1 (n0 / n1 live records)
-  auto load_recs = [&](const CandRec* cr, uint32_t i, uint32_t p, uint32_t n0, uint32_t n1) {
+  auto load_recs = [&](const CandRec* cr, uint32_t i, uint32_t n0, uint32_t n1) {
     Rec2 rc;
     rc.t0 = rc.t1 = make_float4(0.f, 0.f, 0.f, 0.f);
     rc.g0 = rc.g1 = 0;
-    const CandRec* s0 = cr + (size_t)(2u * p) * segcap;
     // records are read exactly once: streaming loads keep them from evicting the k x k centroid
     // matrix (read with a data-dependent pattern later in this kernel) out of L2
-    if (i < n0 && i < segcap) { rc.t0 = __ldcs(&s0[i].t); rc.g0 = __ldcs(&s0[i].g); }
-    if (i < n1 && i < segcap) { rc.t1 = __ldcs(&s0[segcap + i].t); rc.g1 = __ldcs(&s0[segcap + i].g); }
+    if (i < n0 && i < segcap) { rc.t0 = __ldcs(&cr[i].t); rc.g0 = __ldcs(&cr[i].g); }
+    if (i < n1 && i < segcap) { rc.t1 = __ldcs(&cr[segcap + i].t); rc.g1 = __ldcs(&cr[segcap + i].g); }
     return rc;
   };
   // Two-level prefetch: a row's info word and norms are fetched two rows ahead, its first 32
-  // records of the first two segments (only the live ones, the counts are known by then) one row
-  // ahead, so the dependent HBM round trips of the next rows overlap the work on the current one.
+  // records of each segment (only the live ones, the counts are known by then) one row ahead, so
+  // the dependent HBM round trips of the next rows overlap the work on the current one.
   struct Pre1 { RowInfo info; float xn, xr; };
   auto prefetch1 = [&](uint32_t rr) {
     Pre1 p;
-#pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s) { p.info.cnt[s] = 0u; p.info.best[s] = 0u; }
+    p.info = make_uint4(0u, 0u, 0u, 0u);
     p.xn = p.xr = 0.f;
     if (rr < a.m) {
       p.info = a.info[rr];
@@ -164,7 +160,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
   };
   auto prefetch2 = [&](uint32_t rr, const Pre1& p1) {
     if (rr < a.m)
-      return load_recs(a.rec + (size_t)rr * a.cap, (uint32_t)lane, 0u, p1.info.cnt[0], a.nseg > 1 ? p1.info.cnt[1] : 0u);
+      return load_recs(a.rec + (size_t)rr * a.cap, (uint32_t)lane, p1.info.x, a.nseg > 1 ? p1.info.z : 0u);
     return Rec2{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), 0u, 0u};
   };
   uint32_t nq = 0;                                   // queued exact evaluations (warp-uniform)
@@ -192,28 +188,24 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
     cur1 = nx1;
     nx1 = prefetch1(r + 2 * warps_total);
     cur_rc = prefetch2(r + warps_total, cur1);
-    uint32_t cnt[MAX_SEG];
-    uint32_t cmax = 0;
-    float sbest = -INF;
-#pragma unroll
-    for (int s = 0; s < MAX_SEG; ++s) {
-      cnt[s] = s < a.nseg ? info.cnt[s] : 0u;
-      cmax = max(cmax, cnt[s]);
-      if (s < a.nseg) sbest = fmaxf(sbest, __uint_as_float(info.best[s]));
-    }
-    bool overflow = cmax > segcap;                    // the dense fallback owns such rows
-    const uint32_t steps = overflow ? 0u : (cmax + 31u) >> 5;
+    const uint32_t cnt0 = info.x, cnt1 = a.nseg > 1 ? info.z : 0u;
+    bool overflow = cnt0 > segcap || cnt1 > segcap;   // the dense fallback owns such rows
+    uint32_t steps = overflow ? 0u : (max(cnt0, cnt1) + 31u) >> 5;
     const CandRec* cr = a.rec + (size_t)r * a.cap;
     const float E = approx ? tc_err_bound(xn, xr, cnmax, dcmax, a.ld) : 0.0f;
     // a seeded candidate pass is only valid when the observed maximum reaches the seed's bound
     if (approx && a.seed != nullptr) {
       const float sd = a.seed[r];
-      if (sd < INF && !(sbest >= tc_seed_bound(xn, sd, E, cnmax))) overflow = true;
+      if (sd < INF && !(fmaxf(__uint_as_float(info.y), __uint_as_float(info.w)) >= tc_seed_bound(xn, sd, E, cnmax))) {
+        overflow = true;
+        steps = 0;
+      }
     }
     // smallest distance the producer saw: approximate on the tensor path (the info words hold the
-    // largest s = x.c - |c|^2/2 per column part, d = |x|^2 - 2 s; the true minimum is within E of
+    // largest s = x.c - |c|^2/2 per column half, d = |x|^2 - 2 s; the true minimum is within E of
     // it, so only elements within 2E can be the argmin), exact otherwise
-    const float ma = approx ? fmaf(-2.0f, sbest, xn) : __uint_as_float(info.best[0]);
+    const float ma = approx ? fmaf(-2.0f, fmaxf(__uint_as_float(info.y), __uint_as_float(info.w)), xn)
+                            : __uint_as_float(info.y);
     const float band = __fadd_ru(ma, 2.0f * E);
     // loosest possible threshold: thr = fl(dmin * factor) with dmin <= ma + E
     const float thi_loose = a.want_members ? __fmul_ru(__fadd_ru(ma, E), a.factor) : 0.0f;
@@ -223,27 +215,18 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
     // ---- level A: element filter, survivors compacted into shared memory ----------------------
     uint32_t nel = 0;
     __syncwarp();
-    for (uint32_t st = 0; st < (overflow ? 0u : steps); ++st) {
+    for (uint32_t st = 0; st < steps; ++st) {
       const uint32_t i = st * 32 + lane;
-      // up to 16 elements per lane and step: record i of every segment, one prefix sum for all
-      Rec2 rc[2];
-      rc[0] = st == 0 ? rc0 : load_recs(cr, i, 0u, cnt[0], cnt[1]);
-      rc[1] = npairs > 1 ? load_recs(cr, i, 1u, cnt[2], cnt[3])
-                         : Rec2{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), 0u, 0u};
-      uint32_t jb[4];
+      const Rec2 rc = st == 0 ? rc0 : load_recs(cr, i, cnt0, cnt1);
+      const float tv[8] = {rc.t0.x, rc.t0.y, rc.t0.z, rc.t0.w, rc.t1.x, rc.t1.y, rc.t1.z, rc.t1.w};
+      const uint32_t jb0 = (rc.g0 & REC_G_MASK) << 2, jb1 = (rc.g1 & REC_G_MASK) << 2;
+      float v[8];
       uint32_t pass = 0;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        if (p == 1 && npairs < 2) break;
-        const float tv[8] = {rc[p].t0.x, rc[p].t0.y, rc[p].t0.z, rc[p].t0.w, rc[p].t1.x, rc[p].t1.y, rc[p].t1.z, rc[p].t1.w};
-        jb[2 * p] = (rc[p].g0 & REC_G_MASK) << 2;
-        jb[2 * p + 1] = (rc[p].g1 & REC_G_MASK) << 2;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float vv = approx ? fmaf(-2.0f, tv[q], xn) : tv[q];
-          const bool live = (i < cnt[2 * p + (q >> 2)]) && (jb[2 * p + (q >> 2)] + (uint32_t)(q & 3)) < a.k;
-          pass |= (live && vv <= vbound) ? (1u << (p * 8 + q)) : 0u;      // NaN never passes (never a member)
-        }
+      for (int q = 0; q < 8; ++q) {
+        v[q] = approx ? fmaf(-2.0f, tv[q], xn) : tv[q];
+        const bool live = (q < 4 ? i < cnt0 : i < cnt1) && ((q < 4 ? jb0 : jb1) + (uint32_t)(q & 3)) < a.k;
+        pass |= (live && v[q] <= vbound) ? (1u << q) : 0u;      // NaN never passes (never a member)
       }
       const uint32_t mine = (uint32_t)__popc(pass);
       uint32_t incl = mine;
@@ -255,18 +238,13 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
       uint32_t pos = nel + incl - mine;
       nel += __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        if (p == 1 && npairs < 2) break;
-        const float tv[8] = {rc[p].t0.x, rc[p].t0.y, rc[p].t0.z, rc[p].t0.w, rc[p].t1.x, rc[p].t1.y, rc[p].t1.z, rc[p].t1.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if ((pass >> (p * 8 + q)) & 1u) {
-            if (pos < (uint32_t)CLS_STAGE) {
-              sm.j[pos] = jb[2 * p + (q >> 2)] + (uint32_t)(q & 3);
-              sm.v[pos] = approx ? fmaf(-2.0f, tv[q], xn) : tv[q];    // the same operation as in the filter
-            }
-            ++pos;
+      for (int q = 0; q < 8; ++q) {
+        if ((pass >> q) & 1u) {
+          if (pos < (uint32_t)CLS_STAGE) {
+            sm.j[pos] = (q < 4 ? jb0 : jb1) + (uint32_t)(q & 3);
+            sm.v[pos] = v[q];
           }
+          ++pos;
         }
       }
     }
@@ -649,12 +627,8 @@ overflow_rows_kernel(ResolveDev a, const float* __restrict__ dense, const uint32
       if (member) {
         const unsigned pos = atomicAdd(&s_cnt, 1u);
         if (PHASE == 1) {
-          if (vals != nullptr) {          // (slot, row) pairs for the radix-sort CSR
-            keys[row_off[r] + pos] = j;
-            vals[row_off[r] + pos] = r;
-          } else {                        // member list of overflow row o (counting-sort CSR)
-            keys[row_off[o] + pos] = j;
-          }
+          keys[row_off[r] + pos] = j;
+          vals[row_off[r] + pos] = r;
         }
       }
     }
@@ -697,8 +671,7 @@ int run_overflow(spf_ctx* c, const ResolveDev& d, uint32_t n_ovf, float* keep, c
       SPF_TRY(launch_assign_exact(c, METRIC, rows.p, nb, d.C, d.k, d.ld, 1.0f, nullptr, blk));
     }
     const unsigned grid = nb < (uint32_t)c->sm_count * 8 ? nb : (unsigned)c->sm_count * 8;
-    overflow_rows_kernel<METRIC, PHASE><<<grid, 256, 0, st>>>(d, blk, d.ovf_rows + b0, nb,
-                                                              (PHASE == 1 && vals == nullptr) ? row_off + b0 : row_off, keys, vals);
+    overflow_rows_kernel<METRIC, PHASE><<<grid, 256, 0, st>>>(d, blk, d.ovf_rows + b0, nb, row_off, keys, vals);
     SPF_TRY(check_launch(c, "overflow_rows_kernel"));
   }
   return SPF_OK;
@@ -740,226 +713,6 @@ __global__ void offsets_kernel(const uint32_t* __restrict__ keys_sorted, uint64_
     if (keys_sorted[mid] < c) lo = mid + 1; else hi = mid;
   }
   offsets[c] = lo;
-}
-
-// ---------------------------------------------------------------------------------------------
-// CSR by one counting pass (k <= CS_MAX_K): the serial merge of hierarchical.rs:353-361 is a stable
-// counting sort of (row, slot) pairs by slot.  The rows are cut into `nw` contiguous ranges, one
-// per warp: cs_count builds a per-range histogram over the k slots (16-bit counters in shared
-// memory), cs_scan turns the nw x k matrix into the first output position of every (range, slot)
-// — ranges in order inside a slot, slots in order — and cs_scatter replays the ranges and writes
-// every row to its final position.  Two reads of the member lists and one scattered 4-byte write
-// per member instead of the fill + two radix passes of the library sort.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t CS_MAX_K = 8192;
-constexpr int CS_GROUPS = 16;          // cs_scan: ranges are scanned in this many independent groups
-
-struct CsArgs {
-  const uint32_t* memlist; int sl_shift; const uint32_t* nmem;
-  const uint32_t* ovf_list; const uint64_t* ovf_aux;   // member lists of the overflow rows (aux[row] = offset)
-  uint32_t m, k, kw;                   // kw = words per histogram row = ceil(k / 2)
-  uint32_t nw, rpw;                    // ranges, rows per range
-  uint32_t* hist;                      // nw x kw packed 16-bit counts
-  uint32_t* base;                      // nw x k: position of the range's first member inside its group and slot
-  uint32_t* gtot;                      // CS_GROUPS x k: members per (group, slot), then exclusive over groups
-  uint64_t* offsets;                   // k + 1
-  uint32_t* members;
-};
-
-// One batch = 32 consecutive rows of the warp's range.  Lane i describes row r0 + i: member count
-// and list pointer go to shared memory together with the exclusive prefix of the counts; returns
-// the number of members of the batch.
-struct CsBatch { const uint32_t* list[32]; uint32_t pre[34]; };
-static_assert(sizeof(CsBatch) % 8 == 0, "batches are laid out back to back in shared memory");
-
-__device__ __forceinline__ uint32_t cs_load_batch(const CsArgs& a, CsBatch& b, uint32_t r0, uint32_t rend, int lane) {
-  const uint32_t r = r0 + lane;
-  uint32_t cnt = 0;
-  const uint32_t* lp = nullptr;
-  if (r < rend) {
-    const uint32_t nm = a.nmem[r];
-    cnt = nm & ~NMEM_OVERFLOW_BIT;
-    lp = (nm & NMEM_OVERFLOW_BIT) ? a.ovf_list + a.ovf_aux[r] : a.memlist + ((size_t)r << a.sl_shift);
-  }
-  uint32_t incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
-  }
-  __syncwarp();
-  b.pre[lane] = incl - cnt;
-  b.list[lane] = lp;
-  if (lane == 31) b.pre[32] = incl;
-  __syncwarp();
-  return __shfl_sync(0xffffffffu, incl, 31);
-}
-
-// member e of the batch (flat, row-major): which row of the batch and its slot
-__device__ __forceinline__ uint32_t cs_member(const CsBatch& b, uint32_t e, uint32_t* row_in_batch) {
-  uint32_t lo = 0;                                   // last i with pre[i] <= e
-#pragma unroll
-  for (int step = 16; step > 0; step >>= 1)
-    if (b.pre[lo + step] <= e) lo += step;
-  *row_in_batch = lo;
-  return b.list[lo][e - b.pre[lo]];
-}
-
-__global__ void __launch_bounds__(256) cs_count_kernel(CsArgs a) {
-  extern __shared__ __align__(16) uint32_t cs_smem[];
-  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  CsBatch& b = reinterpret_cast<CsBatch*>(cs_smem)[wl];
-  uint32_t* h = cs_smem + (size_t)wpb * (sizeof(CsBatch) / 4) + (size_t)wl * a.kw;
-  const uint32_t w = blockIdx.x * wpb + wl;
-  if (w >= a.nw) return;
-  for (uint32_t i = lane; i < a.kw; i += 32) h[i] = 0;
-  const uint32_t rbeg = w * a.rpw, rend = min(a.m, rbeg + a.rpw);
-  for (uint32_t r0 = rbeg; r0 < rend; r0 += 32) {
-    const uint32_t T = cs_load_batch(a, b, r0, rend, lane);
-    for (uint32_t e = lane; e < T; e += 32) {
-      uint32_t rib;
-      const uint32_t j = cs_member(b, e, &rib);
-      atomicAdd(&h[j >> 1], 1u << ((j & 1u) * 16));
-    }
-  }
-  __syncwarp();
-  uint32_t* out = a.hist + (size_t)w * a.kw;
-  for (uint32_t i = lane; i < a.kw; i += 32) out[i] = h[i];
-}
-
-// grid (ceil(kw / 256), CS_GROUPS): thread = one histogram word (two slots) of one group of ranges
-__global__ void __launch_bounds__(256) cs_scan_ranges_kernel(CsArgs a) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.kw) return;
-  const uint32_t per = (a.nw + CS_GROUPS - 1) / CS_GROUPS;
-  const uint32_t w0 = blockIdx.y * per, w1 = min(a.nw, w0 + per);
-  uint32_t run0 = 0, run1 = 0;
-  const bool two = 2 * i + 1 < a.k;
-#pragma unroll 8
-  for (uint32_t w = w0; w < w1; ++w) {
-    const uint32_t c = a.hist[(size_t)w * a.kw + i];
-    a.base[(size_t)w * a.k + 2 * i] = run0;
-    if (two) a.base[(size_t)w * a.k + 2 * i + 1] = run1;
-    run0 += c & 0xffffu;
-    run1 += c >> 16;
-  }
-  a.gtot[(size_t)blockIdx.y * a.k + 2 * i] = run0;
-  if (two) a.gtot[(size_t)blockIdx.y * a.k + 2 * i + 1] = run1;
-}
-
-// one CTA of 1024 threads: per slot the exclusive scan over the groups, then the slot offsets
-__global__ void __launch_bounds__(1024) cs_offsets_kernel(CsArgs a) {
-  __shared__ unsigned long long wsum[32];
-  constexpr int PER = CS_MAX_K / 1024;
-  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  unsigned long long tot[PER];
-  unsigned long long mine = 0;
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    const uint32_t j = threadIdx.x * PER + u;
-    uint32_t run = 0;
-    if (j < a.k) {
-      for (int g = 0; g < CS_GROUPS; ++g) {
-        const uint32_t c = a.gtot[(size_t)g * a.k + j];
-        a.gtot[(size_t)g * a.k + j] = run;
-        run += c;
-      }
-    }
-    tot[u] = run;
-    mine += run;
-  }
-  unsigned long long incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
-  }
-  if (lane == 31) wsum[wl] = incl;
-  __syncthreads();
-  if (wl == 0) {
-    unsigned long long v = wsum[lane], in2 = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long up = __shfl_up_sync(0xffffffffu, in2, o);
-      if (lane >= o) in2 += up;
-    }
-    wsum[lane] = in2 - v;
-  }
-  __syncthreads();
-  unsigned long long off = wsum[wl] + incl - mine;
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    const uint32_t j = threadIdx.x * PER + u;
-    if (j < a.k) a.offsets[j] = off;
-    off += tot[u];
-    if (j + 1 == a.k) a.offsets[a.k] = off;
-  }
-}
-
-__global__ void __launch_bounds__(256) cs_scatter_kernel(CsArgs a) {
-  extern __shared__ __align__(16) uint32_t cs_smem[];
-  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  CsBatch& b = reinterpret_cast<CsBatch*>(cs_smem)[wl];
-  uint32_t* cur = cs_smem + (size_t)wpb * (sizeof(CsBatch) / 4) + (size_t)wl * a.k;
-  const uint32_t w = blockIdx.x * wpb + wl;
-  if (w >= a.nw) return;
-  const uint32_t per = (a.nw + CS_GROUPS - 1) / CS_GROUPS;
-  const uint32_t g = w / per;
-  // positions are < 2^32 (m < 2^32 points and at most 64 members each would not be, but `total` is
-  // checked against 2^32 by the caller)
-  for (uint32_t j = lane; j < a.k; j += 32)
-    cur[j] = (uint32_t)a.offsets[j] + a.gtot[(size_t)g * a.k + j] + a.base[(size_t)w * a.k + j];
-  __syncwarp();
-  const uint32_t rbeg = w * a.rpw, rend = min(a.m, rbeg + a.rpw);
-  for (uint32_t r0 = rbeg; r0 < rend; r0 += 32) {
-    const uint32_t T = cs_load_batch(a, b, r0, rend, lane);
-    for (uint32_t e0 = 0; e0 < T; e0 += 32) {
-      const uint32_t e = e0 + lane;
-      const bool have = e < T;
-      uint32_t rib = 0;
-      const uint32_t j = have ? cs_member(b, e, &rib) : (0x80000000u | (uint32_t)lane);   // unique dummy keys
-      // members of one slot inside this group of 32 keep their (row-major) order: rank by lane
-      const unsigned peers = __match_any_sync(0xffffffffu, j);
-      const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      uint32_t pos = 0;
-      if (have) pos = cur[j] + rank;
-      __syncwarp();
-      if (have && rank + 1 == (uint32_t)__popc(peers)) cur[j] = pos + 1;     // last of the group advances the cursor
-      if (have) a.members[pos] = r0 + rib;
-      __syncwarp();
-    }
-  }
-}
-
-__global__ void cs_ovf_aux_kernel(const uint32_t* __restrict__ ovf_rows, const uint64_t* __restrict__ ovf_off,
-                                  uint32_t n_ovf, uint64_t* __restrict__ aux) {
-  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o < n_ovf) aux[ovf_rows[o]] = ovf_off[o];
-}
-
-// exclusive scan of the overflow rows' member counts (one CTA; the overflow set is small on the
-// paths where this matters, and dominated by the dense fallback itself where it is not)
-__global__ void __launch_bounds__(1024) cs_ovf_scan_kernel(const uint32_t* __restrict__ ovf_rows,
-                                                           const uint32_t* __restrict__ nmem, uint32_t n_ovf,
-                                                           uint64_t* __restrict__ ovf_off) {
-  __shared__ unsigned long long part[1024];
-  const uint32_t per = (n_ovf + 1023u) / 1024u;
-  const uint32_t b0 = threadIdx.x * per, b1 = min(n_ovf, b0 + per);
-  unsigned long long sum = 0;
-  for (uint32_t o = b0; o < b1; ++o) sum += nmem[ovf_rows[o]] & ~NMEM_OVERFLOW_BIT;
-  part[threadIdx.x] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int i = 0; i < 1024; ++i) { const unsigned long long v = part[i]; part[i] = run; run += v; }
-    ovf_off[n_ovf] = run;
-  }
-  __syncthreads();
-  unsigned long long run = part[threadIdx.x];
-  for (uint32_t o = b0; o < b1; ++o) {
-    ovf_off[o] = run;
-    run += nmem[ovf_rows[o]] & ~NMEM_OVERFLOW_BIT;
-  }
 }
 
 template <int METRIC>
@@ -1027,68 +780,6 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   if (!csr) return SPF_OK;
 
   KernelTimer t(c, "csr");
-  if (c->params.csr_sort != 0 && a.k <= CS_MAX_K) {
-    // ---- single counting pass (see cs_count_kernel) ------------------------------------------
-    DevBuf<uint64_t> ovf_off, ovf_aux, offsets;
-    DevBuf<uint32_t> ovf_list, hist, base, gtot;
-    if (n_ovf > 0) {
-      SPF_TRY(ovf_off.alloc(st, (size_t)n_ovf + 1));
-      SPF_TRY(ovf_aux.alloc(st, a.m));
-      cs_ovf_scan_kernel<<<1, 1024, 0, st>>>(s->ovf_rows.p, a.nmem, n_ovf, ovf_off.p);
-      SPF_TRY(check_launch(c, "cs_ovf_scan_kernel"));
-      uint64_t ovf_total = 0;
-      SPF_CUDA(cudaMemcpyAsync(&ovf_total, ovf_off.p + n_ovf, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      SPF_CUDA(cudaStreamSynchronize(st));
-      SPF_TRY(ovf_list.alloc(st, ovf_total));
-      cs_ovf_aux_kernel<<<(unsigned)ceil_div(n_ovf, 256), 256, 0, st>>>(s->ovf_rows.p, ovf_off.p, n_ovf, ovf_aux.p);
-      SPF_TRY(check_launch(c, "cs_ovf_aux_kernel"));
-      SPF_TRY((run_overflow<METRIC, 1>(c, d, n_ovf, keep.p, ovf_off.p, ovf_list.p, nullptr)));
-    }
-    CsArgs ca;
-    ca.memlist = s->memlist.p; ca.sl_shift = s->sl_shift; ca.nmem = a.nmem;
-    ca.ovf_list = ovf_list.p; ca.ovf_aux = ovf_aux.p;
-    ca.m = (uint32_t)a.m; ca.k = a.k; ca.kw = (a.k + 1) / 2;
-    uint64_t rpw = ceil_div(a.m, (uint64_t)c->sm_count * 16);
-    if (rpw < 32) rpw = 32;
-    if (rpw > 32768) rpw = 32768;                      // 16-bit counters per (range, slot)
-    ca.rpw = (uint32_t)rpw;
-    ca.nw = (uint32_t)ceil_div(a.m, rpw);
-    SPF_TRY(hist.alloc(st, (size_t)ca.nw * ca.kw));
-    SPF_TRY(base.alloc(st, (size_t)ca.nw * ca.k));
-    SPF_TRY(gtot.alloc(st, (size_t)CS_GROUPS * ca.k));
-    SPF_TRY(offsets.alloc(st, (size_t)a.k + 1));
-    ca.hist = hist.p; ca.base = base.p; ca.gtot = gtot.p; ca.offsets = offsets.p; ca.members = nullptr;
-    auto warps_for = [](size_t bytes_per_warp) {
-      size_t w = (64u << 10) / (bytes_per_warp ? bytes_per_warp : 1);
-      return (int)(w < 1 ? 1 : (w > 8 ? 8 : w));
-    };
-    const int wc = warps_for((size_t)ca.kw * 4), ws = warps_for((size_t)ca.k * 4);
-    const size_t smem_c = (size_t)wc * (sizeof(CsBatch) + (size_t)ca.kw * 4);
-    const size_t smem_s = (size_t)ws * (sizeof(CsBatch) + (size_t)ca.k * 4);
-    SPF_CUDA(cudaFuncSetAttribute(cs_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    SPF_CUDA(cudaFuncSetAttribute(cs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    cs_count_kernel<<<(unsigned)ceil_div(ca.nw, wc), wc * 32, smem_c, st>>>(ca);
-    SPF_TRY(check_launch(c, "cs_count_kernel"));
-    cs_scan_ranges_kernel<<<dim3((unsigned)ceil_div(ca.kw, 256), CS_GROUPS), 256, 0, st>>>(ca);
-    SPF_TRY(check_launch(c, "cs_scan_ranges_kernel"));
-    cs_offsets_kernel<<<1, 1024, 0, st>>>(ca);
-    SPF_TRY(check_launch(c, "cs_offsets_kernel"));
-    uint64_t total = 0;
-    SPF_CUDA(cudaMemcpyAsync(&total, offsets.p + a.k, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SPF_CUDA(cudaStreamSynchronize(st));
-    if (total < (1ull << 32)) {
-      DevBuf<uint32_t> members;
-      SPF_TRY(members.alloc(st, total));
-      ca.members = members.p;
-      cs_scatter_kernel<<<(unsigned)ceil_div(ca.nw, ws), ws * 32, smem_s, st>>>(ca);
-      SPF_TRY(check_launch(c, "cs_scatter_kernel"));
-      csr->total = total;
-      csr->offsets = offsets.take();
-      csr->members = members.take();
-      return SPF_OK;
-    }
-    // >= 2^32 members: positions do not fit the 32-bit cursors, use the library sort below
-  }
   // row offsets = exclusive scan of member counts
   DevBuf<uint64_t> row_off, d_total;
   SPF_TRY(row_off.alloc(st, a.m));

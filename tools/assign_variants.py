@@ -1,15 +1,16 @@
-"""Times the device-resident assign step (1M x 128, k = 4096, N(0,1)) under the kernel variants the
-knobs select — epilogue layout of the tcgen05 kernel (8 / 16 epilogue warps), counting-sort CSR vs
-library sort, cached centroid matrix — and checks that all variants return identical results.
-Prints one JSON line per variant (round-2 kernel experiments, profiles/)."""
+"""Times the device-resident assign step (1M x 128, k = 4096, N(0,1)) with per-kernel times, with
+and without the cached centroid matrix, and checks the results against each other.  Prints one JSON
+line per variant to stderr-safe stdout (round-2 kernel experiments, profiles/)."""
 import json
+import os
 import sys
 
 import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-import bench  # noqa: E402
+OUT = os.dup(1)
+import bench  # noqa: E402  (redirects fd 1 to stderr)
 import spfresh_b200 as s  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
@@ -17,10 +18,8 @@ rows = bench.make_rows(0)
 cent = np.arange(bench.K_CENT, dtype=np.uint64)
 kn = ["assign_tc", "classify", "exact_eval", "finalize", "overflow", "cc_matrix", "csr"]
 ref = None
-for split, csr_sort, cc_cache in [(2, 0, 0), (2, 1, 1), (4, 0, 0), (4, 1, 1), (4, 1, 0)]:
+for cc_cache in (0, 1):
     ctx = s.Context(0)
-    ctx.set_param("tc_epi_split", split)
-    ctx.set_param("csr_sort", csr_sort)
     ctx.set_param("cc_cache", cc_cache)
     ds = s.Dataset(ctx, rows)
     ext = torch.cuda.ExternalStream(ctx.stream)
@@ -49,9 +48,9 @@ for split, csr_sort, cc_cache in [(2, 0, 0), (2, 1, 1), (4, 0, 0), (4, 1, 1), (4
     else:
         same = bool(np.array_equal(ref.best, f.best) and np.array_equal(ref.dmin.view(np.uint32), f.dmin.view(np.uint32))
                     and np.array_equal(ref.offsets, f.offsets) and np.array_equal(ref.members, f.members))
-    print(json.dumps({"tc_epi_split": split, "csr_sort": csr_sort, "cc_cache": cc_cache, "ms_per_step": ms,
-                      "kernels_ms": {k: float(np.mean(v)) for k, v in acc.items()},
-                      "overflow_rows": ctx.last_overflow_rows(), "members": int(f.members.size),
-                      "identical_to_first_variant": same}), flush=True)
+    os.write(OUT, (json.dumps({"cc_cache": cc_cache, "ms_per_step": ms,
+                               "kernels_ms": {k: float(np.mean(v)) for k, v in acc.items()},
+                               "overflow_rows": ctx.last_overflow_rows(), "members": int(f.members.size),
+                               "identical_to_first_variant": same}) + "\n").encode())
     ds.free()
     ctx.close()
