@@ -60,6 +60,8 @@ typedef struct spf_dataset spf_dataset;          /* n x d f32 rows resident in H
 typedef struct spf_assign_result spf_assign_result;
 typedef struct spf_kmpp spf_kmpp;                /* k-means++ session state in HBM            */
 typedef struct spf_index spf_index;              /* posting lists + centroids resident in HBM */
+typedef struct spf_comm spf_comm;                /* one rank of a multi-GPU group (NCCL)      */
+typedef struct spf_kmeans spf_kmeans;            /* device-resident row-sharded k-means state */
 
 /* ---- library / context ---------------------------------------------------------------- */
 int         spf_abi_version(void);
@@ -165,6 +167,44 @@ int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result
 int spf_cluster_sums(spf_dataset* ds, const spf_assign_result* r, float* sums, uint64_t* counts);
 int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* r, const float* means,
                           float* dist, uint64_t* row);
+
+/* ---- multi-GPU group -------------------------------------------------- *
+ * One process per GPU.  The reference is single-process (rayon, hierarchical.rs:144-303); the
+ * exchange steps below are what north_star adds on one NVLink / NVSwitch box.  libnccl is loaded
+ * at run time (dlopen "libnccl.so.2"), only when a group with world > 1 is created.
+ *   spf_comm_unique_id   rank 0 creates the 128-byte NCCL id; the host passes it to every rank by
+ *                        whatever channel it has (MPI, a TCP store, torch.distributed, a file)
+ *   spf_comm_create      collective over all ranks; world == 1 needs no id and no NCCL */
+#define SPF_COMM_ID_BYTES 128
+int  spf_comm_unique_id(uint8_t* id128);
+int  spf_comm_create(spf_ctx* ctx, int world, int rank, const uint8_t* id128, spf_comm** out);
+void spf_comm_destroy(spf_comm* comm);
+int  spf_comm_world(const spf_comm* comm);
+int  spf_comm_rank(const spf_comm* comm);
+
+/* Device-resident row-sharded k-means iteration: HierarchicalClustering::assign_points +
+ * update_centroids (hierarchical.rs:368-390, 138-181) with the rows sharded contiguously over the
+ * ranks (rank r holds global rows [row0, row0 + n), rank 0 starts at 0) and the k centroid vectors
+ * replicated.  Nothing leaves the device between iterations; per iteration two NCCL all-gathers
+ * on the context stream carry (C1) the per-cluster partial sums + counts, added in rank order and
+ * divided (compute_mean, utils.rs:13-14), and (C2) every rank's best member per cluster for the
+ * new mean with its vector; the (distance, rank) minimum names the new centroid (:155-171), an
+ * empty cluster keeps its centroid (:146-149).  comm == NULL: one GPU, no exchange.
+ *   set_centroids  k global rows + their vectors (k x d, host), e.g. from k-means++
+ *   step           one iteration (collective: every rank of the group must call it)
+ *   fetch          what is non-NULL: centroid rows[k], vectors[k*d], last means[k*d], global
+ *                  cluster sizes[k]
+ *   assignment     the rank's last local assignment (owned by the session, valid until the next
+ *                  step / free), for spf_assign_fetch or spf_index_pack */
+enum { SPF_KMEANS_DEFAULT = 0,
+       SPF_KMEANS_UNSEEDED = 1 /* do not seed the assignment with the previous iteration's result */ };
+int  spf_kmeans_create(spf_dataset* ds, spf_comm* comm, int metric, uint64_t row0, uint32_t k,
+                       float boundary_factor, int flags, spf_kmeans** out);
+int  spf_kmeans_set_centroids(spf_kmeans* s, const uint64_t* global_rows, const float* vectors);
+int  spf_kmeans_step(spf_kmeans* s);
+int  spf_kmeans_fetch(spf_kmeans* s, uint64_t* rows, float* vectors, float* means, uint64_t* counts);
+const spf_assign_result* spf_kmeans_assignment(const spf_kmeans* s);
+void spf_kmeans_free(spf_kmeans* s);
 
 /* ---- k-means++ ------------------------------------------------------------------------- *
  * HierarchicalClustering::initialize_clusters_kmeans_plus_plus, hierarchical.rs:249-293.

@@ -12,7 +12,8 @@ from ._capi import (ASSIGN_DEFAULT, ASSIGN_FORCE_EXACT, ASSIGN_NO_CSR, METRIC_CH
 from .clustering import (BOUNDARY_THRESHOLD, ChebyshevDistance, Cluster, ClusteringParams, DistanceMetric,
                          HierarchicalClustering, InitializationMethod, ManhattanDistance, NumpyRandomSource,
                          RandomSource, ScriptedRandomSource, SquaredEuclideanDistance)
-from .device import AssignResult, Context, Dataset, DeviceIndex, KmppSession, KmppShardSession, topk_merge
+from .device import (AssignResult, Context, Dataset, DeviceComm, DeviceIndex, KMeansSession, KmppSession,
+                     KmppShardSession, topk_merge)
 from .lire import LireError, Reassign, Split, reassign_batch
 from .spann import ClusteringParamsConfig, Config, PointData, SpannIndex, SpannIndexBuilder
 

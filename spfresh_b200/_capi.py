@@ -76,6 +76,17 @@ SIGNATURES = {
     "spf_search_batch": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp, _vp,
                                    _vp, _vp]),
     "spf_index_last_scan_bytes": (C.c_uint64, [_vp]),
+    "spf_comm_unique_id": (C.c_int, [_vp]),
+    "spf_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vpp]),
+    "spf_comm_destroy": (None, [_vp]),
+    "spf_comm_world": (C.c_int, [_vp]),
+    "spf_comm_rank": (C.c_int, [_vp]),
+    "spf_kmeans_create": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_uint32, C.c_float, C.c_int, _vpp]),
+    "spf_kmeans_set_centroids": (C.c_int, [_vp, _vp, _vp]),
+    "spf_kmeans_step": (C.c_int, [_vp]),
+    "spf_kmeans_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "spf_kmeans_assignment": (C.c_void_p, [_vp]),
+    "spf_kmeans_free": (None, [_vp]),
     "spf_topk_merge": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libspfresh_b200.so")
 SOURCES = ["api.cu", "support.cu", "assign_exact.cu", "assign_tc.cu", "resolve.cu", "assign_api.cu",
-           "ops.cu", "search.cu", "scan_tc.cu"]
+           "ops.cu", "search.cu", "scan_tc.cu", "comm.cu", "kmeans.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -437,3 +437,107 @@ def topk_merge(keys, ids, dists, counts):
     o_c = np.empty(nq, np.uint32)
     check(lib().spf_topk_merge(parts, nq, k, ptr(keys), ptr(ids), ptr(dists), ptr(counts), ptr(o_ids), ptr(o_d), ptr(o_c)))
     return o_ids, o_d, o_c
+
+
+class DeviceComm:
+    """spf_comm: this rank's handle of a multi-GPU group (NCCL over NVLink, one process per GPU).
+    `id_bytes` is the 128-byte id rank 0 obtained from `unique_id()` and passed to every rank."""
+
+    def __init__(self, ctx: Context, world: int = 1, rank: int = 0, id_bytes: bytes | None = None):
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        h = C.c_void_p()
+        buf = None
+        if id_bytes is not None:
+            buf = np.frombuffer(bytes(id_bytes), np.uint8).copy()
+            if buf.size != 128:
+                raise ValueError("the communicator id is 128 bytes")
+        check(lib().spf_comm_create(ctx.handle, self.world, self.rank, ptr(buf), C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = np.zeros(128, np.uint8)
+        check(lib().spf_comm_unique_id(ptr(buf)))
+        return buf.tobytes()
+
+    @classmethod
+    def from_torch(cls, ctx: Context) -> "DeviceComm":
+        """Group over the ranks of the initialised torch.distributed process group: rank 0 creates
+        the id, torch broadcasts the 128 bytes (host plumbing only; the data path is the library's
+        own NCCL communicator on the library's stream)."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return cls(ctx, 1, 0, None)
+        box = [cls.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(ctx, dist.get_world_size(), dist.get_rank(), box[0])
+
+    @property
+    def handle(self):
+        return self._h
+
+    def free(self):
+        if self._h:
+            lib().spf_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _BorrowedAssign(AssignResult):
+    """The assignment owned by a KMeansSession (must not be freed by the wrapper)."""
+
+    def free(self):
+        self._h = None
+
+
+class KMeansSession:
+    """spf_kmeans: device-resident row-sharded k-means iterations (assign_points + update_centroids,
+    hierarchical.rs:368-390, 138-181).  `comm` None = one GPU."""
+
+    def __init__(self, ds: Dataset, comm: DeviceComm | None, metric: int, row0: int, k: int,
+                 boundary_factor: float = 1.1, seeded: bool = True):
+        self.ds, self.comm, self.k = ds, comm, int(k)
+        h = C.c_void_p()
+        check(lib().spf_kmeans_create(ds.handle, comm.handle if comm is not None else None, metric, int(row0), self.k,
+                                      boundary_factor, 0 if seeded else 1, C.byref(h)))
+        self._h = h
+
+    def set_centroids(self, global_rows, vectors):
+        rows = as_u64(global_rows)
+        vec = as_f32(vectors).reshape(self.k, self.ds.d)
+        if rows.size != self.k:
+            raise ValueError("k rows expected")
+        check(lib().spf_kmeans_set_centroids(self._h, ptr(rows), ptr(vec)))
+
+    def step(self):
+        check(lib().spf_kmeans_step(self._h))
+
+    def fetch(self, rows=True, vectors=True, means=False, counts=True):
+        r = np.empty(self.k, np.uint64) if rows else None
+        v = np.empty((self.k, self.ds.d), np.float32) if vectors else None
+        m = np.empty((self.k, self.ds.d), np.float32) if means else None
+        c = np.empty(self.k, np.uint64) if counts else None
+        check(lib().spf_kmeans_fetch(self._h, ptr(r), ptr(v), ptr(m), ptr(c)))
+        return r, v, m, c
+
+    def assignment(self) -> AssignResult:
+        h = lib().spf_kmeans_assignment(self._h)
+        if not h:
+            raise RuntimeError("no assignment yet")
+        return _BorrowedAssign(self.ds, C.c_void_p(h))
+
+    def free(self):
+        if self._h:
+            lib().spf_kmeans_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -327,9 +327,47 @@ def clusters_from_assignment(shard, comm: Comm, res, centroid_rows) -> List[Shar
     return [ShardedCluster(int(centroid_rows[c]), lists[c], counts[:, c], 0) for c in range(len(lists))]
 
 
+class DeviceShardedKMeans:
+    """Flat k-means iterations over row shards, device resident (spf_kmeans): assign + the two
+    all-gathers of update_centroids run on the library's stream through the library's own NCCL
+    communicator; no host staging between iterations.  Same results as `ShardedKMeans` below
+    (which stages every exchange through numpy and also runs on the CPU oracle shards)."""
+
+    def __init__(self, dataset, device_comm, metric: int, row0: int, boundary_factor: float = 1.1, seeded: bool = True):
+        self.ds, self.comm, self.metric, self.row0 = dataset, device_comm, metric, int(row0)
+        self.factor, self.seeded = boundary_factor, seeded
+        self.session = None
+
+    def init(self, global_rows, vectors):
+        from .device import KMeansSession
+        rows = np.asarray(global_rows, np.uint64)
+        if self.session is not None:
+            self.session.free()
+        self.session = KMeansSession(self.ds, self.comm, self.metric, self.row0, rows.size, self.factor, self.seeded)
+        self.session.set_centroids(rows, vectors)
+
+    def step(self):
+        self.session.step()
+
+    def centroids(self):
+        """(global rows, vectors, global cluster sizes) after the last step."""
+        rows, vec, _, cnt = self.session.fetch()
+        return rows, vec, cnt
+
+    @property
+    def last(self):
+        return self.session.assignment()
+
+    def free(self):
+        if self.session is not None:
+            self.session.free()
+            self.session = None
+
+
 class ShardedKMeans:
     """Flat k-means iterations over row shards (the part of HierarchicalClustering.fit that is
-    data-parallel: assign_points + update_centroids)."""
+    data-parallel: assign_points + update_centroids), every exchange staged through the host —
+    the portable form (gloo / CPU oracle shards) and the checker of `DeviceShardedKMeans`."""
 
     def __init__(self, shard, comm: Comm, metric: int, boundary_factor: float = 1.1):
         self.shard, self.comm, self.metric, self.factor = shard, comm, metric, boundary_factor

@@ -1031,3 +1031,74 @@ def test_config5_query_sweep_matches_oracle_sample(spf, ctx, oracle, config2, np
         c = int(rc[i])
         assert np.array_equal(ids[qi, :c], rid[i, :c]), (nprobe, qi)
         assert np.array_equal(dists[qi, :c].view(np.uint32), rd[i, :c].view(np.uint32)), (nprobe, qi)
+
+
+# ----------------------------------------------------------------------------------------------
+# device-resident k-means iterations (spf_kmeans) and the NCCL group
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,seeded", [(0, True), (0, False), (1, True), (2, True)])
+def test_kmeans_session_single_gpu_matches_oracle(spf, ctx, oracle, metric, seeded):
+    """One rank, no exchange: three iterations of assign_points + update_centroids stay on the device
+    and reproduce the oracle bit for bit — centroid rows, vectors, means, cluster sizes, and the
+    assignment itself (seeded from the second iteration on for the tensor path)."""
+    n, d, k = (30000, 128, 512) if metric == 0 else (6000, 24, 40)
+    data = clustered(n, d, 64, 500 + metric)
+    rows = np.random.default_rng(metric + 3).choice(n, k, replace=False).astype(np.uint64)
+    ds = spf.Dataset(ctx, data)
+    sess = spf.KMeansSession(ds, None, metric, 0, k, seeded=seeded)
+    sess.set_centroids(rows, data[rows.astype(np.int64)])
+    cur = rows.copy()
+    for it in range(3):
+        sess.step()
+        ref_a = oracle.assign(data, metric, cur)
+        check_assign(sess.assignment().fetch(), ref_a)
+        new_rows, ref_means = oracle.update_medoids(data, metric, ref_a.offsets, ref_a.members, cur, want_means=True)
+        got_rows, got_vec, got_means, got_cnt = sess.fetch(means=True)
+        assert np.array_equal(got_rows, new_rows), it
+        assert np.array_equal(got_vec.view(np.uint32), data[new_rows.astype(np.int64)].view(np.uint32))
+        assert np.array_equal(got_means.view(np.uint32), ref_means.view(np.uint32))
+        assert np.array_equal(got_cnt, np.diff(ref_a.offsets.astype(np.int64)).astype(np.uint64))
+        cur = new_rows
+    sess.free()
+    ds.free()
+
+
+def test_kmeans_session_empty_cluster_and_duplicates(spf, ctx, oracle):
+    """A centroid vector far from every point (it is not a row of this shard, as in the sharded
+    build) attracts nothing: its cluster is empty and keeps its centroid (hierarchical.rs:146-149).
+    Two identical centroids exercise the lowest-slot-wins tie."""
+    data = gauss(5000, 16, 321)
+    data[40] = data[7]
+    far = np.full((1, 16), 1.0e3, np.float32)
+    aug = np.concatenate([data, far])                       # the oracle sees the far vector as row 5000
+    rows = np.array([7, 40, 100, 5000, 900, 2500], np.uint64)
+    ds = spf.Dataset(ctx, data)
+    sess = spf.KMeansSession(ds, None, 0, 0, rows.size)
+    sess.set_centroids(rows, aug[rows.astype(np.int64)])
+    sess.step()
+    ref_a = oracle.assign(aug, 0, rows, point_idx=np.arange(5000, dtype=np.uint64))
+    new_rows = oracle.update_medoids(aug, 0, ref_a.offsets, ref_a.members, rows)
+    got_rows, got_vec, _, got_cnt = sess.fetch()
+    assert got_cnt[3] == 0 and got_rows[3] == 5000
+    assert np.array_equal(got_cnt, np.diff(ref_a.offsets.astype(np.int64)).astype(np.uint64))
+    assert np.array_equal(got_rows, new_rows)
+    assert np.array_equal(got_vec.view(np.uint32), aug[new_rows.astype(np.int64)].view(np.uint32))
+    check_assign(sess.assignment().fetch(), ref_a)
+    sess.free()
+    ds.free()
+
+
+def test_kmeans_session_two_gpus_nccl_matches_host_staged_shards(spf):
+    """N = 2 ranks under torch.distributed.run: the device-resident NCCL iteration == the host-staged
+    exchange over the same shards (tools/check_sharded_nccl.py does the comparison on rank 0)."""
+    import subprocess
+    import sys
+    if spf._capi.lib().spf_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571",
+                        os.path.join(root, "tools", "check_sharded_nccl.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "SHARDED_NCCL_OK" in r.stdout
