@@ -290,6 +290,17 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
  * (sum over queries and probed lists of |L| * d * 4): the roofline numerator of the scan. */
 uint64_t spf_index_last_scan_bytes(const spf_index* idx);
 
+/* The same over a list-sharded index (north_star: "posting lists are sharded for query, with
+ * per-GPU top-k merged at the end"; the per-query work is spann_index.rs:148-197): every rank of
+ * `comm` packed its own lists with spf_index_pack(list_begin, list_end) and brings nq_local queries
+ * of the batch (the same count on every rank).  Collective; on return ids / dists / counts hold the
+ * global top-k of this rank's queries.  Query slices and probe tables are all-gathered over NCCL,
+ * partial top-k are exchanged so that each rank merges its own queries on the device.
+ * comm == NULL: identical to spf_search_batch. */
+int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uint64_t nq_local,
+                       uint32_t k, uint32_t nprobe, float prune_factor, uint64_t* ids, float* dists,
+                       uint32_t* counts);
+
 /* Merge per-rank partial results of spf_search_batch (list-sharded index): `parts` rank-major
  * arrays of nq x k keys / ids / dists, counts per rank and query; writes the global top-k. */
 int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys,

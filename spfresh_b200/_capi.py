@@ -75,6 +75,7 @@ SIGNATURES = {
     "spf_index_vectors": (C.c_uint64, [_vp]),
     "spf_search_batch": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp, _vp,
                                    _vp, _vp]),
+    "spf_search_sharded": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp, _vp]),
     "spf_index_last_scan_bytes": (C.c_uint64, [_vp]),
     "spf_comm_unique_id": (C.c_int, [_vp]),
     "spf_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vpp]),

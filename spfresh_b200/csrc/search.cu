@@ -21,6 +21,7 @@
 
 #include <cub/cub.cuh>
 
+#include "comm.cuh"
 #include "kernels.cuh"
 
 using namespace spf;
@@ -1020,40 +1021,13 @@ uint32_t spf_index_lists(const spf_index* idx) { return idx ? idx->nlists : 0; }
 uint64_t spf_index_vectors(const spf_index* idx) { return idx ? idx->total_vectors : 0; }
 uint64_t spf_index_last_scan_bytes(const spf_index* idx) { return idx ? idx->last_scan_bytes : 0; }
 
-int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t k, uint32_t nprobe,
-                     float prune_factor, uint64_t* ids, float* dists, uint32_t* counts, float* vectors,
-                     uint64_t* keys) {
-  if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_batch: NULL argument");
-  if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
-  if (nq == 0) return SPF_OK;
-  if (nprobe == 0) nprobe = k;                       // spann_index.rs:164 nearest_n(query, k)
-  if (nprobe > idx->nlists) nprobe = idx->nlists;
-  if (nprobe > 1024) return fail(SPF_E_INVALID, "nprobe must be <= 1024");
+// The two phases of a search on device buffers (shared by spf_search_batch and the list-sharded
+// spf_search_sharded).  Qp: nq x ld query rows (zero padded).
+static int search_probe(spf_index* idx, const float* Qp, uint64_t nq, uint32_t nprobe, float prune_factor,
+                        uint32_t* probe, float* thr, uint32_t* seqbase) {
   spf_ctx* c = idx->ctx;
-  std::lock_guard<std::mutex> lk(c->mu);
-  SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  c->kernel_ms.clear();
   const uint32_t ld = idx->ld, d = idx->d, nlists = idx->nlists;
-
-  DevBuf<float> Q, thr, o_dists;
-  DevBuf<uint32_t> probe, seqbase, o_counts;
-  DevBuf<uint64_t> o_ids;
-  DevBuf<unsigned long long> o_keys, o_slots, d_bytes;
-  SPF_TRY(Q.alloc(st, (size_t)nq * ld));
-  SPF_TRY(thr.alloc(st, nq));
-  SPF_TRY(probe.alloc(st, (size_t)nq * nprobe));
-  SPF_TRY(seqbase.alloc(st, (size_t)nq * nprobe));
-  SPF_TRY(o_ids.alloc(st, (size_t)nq * k));
-  SPF_TRY(o_dists.alloc(st, (size_t)nq * k));
-  SPF_TRY(o_keys.alloc(st, (size_t)nq * k));
-  SPF_TRY(o_slots.alloc(st, (size_t)nq * k));
-  SPF_TRY(o_counts.alloc(st, nq));
-  SPF_TRY(d_bytes.alloc(st, 1));
-  SPF_CUDA(cudaMemsetAsync(d_bytes.p, 0, sizeof(unsigned long long), st));
-  if (ld != d) SPF_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)nq * ld * sizeof(float), st));
-  SPF_CUDA(cudaMemcpy2DAsync(Q.p, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq, cudaMemcpyHostToDevice, st));
-
   // centroid probe.  Large batches with nprobe <= 32: the centroids are one posting list that every
   // query probes, so the tensor-core candidate scan (scan_tc.cu) with K = nprobe yields the sorted
   // (distance, list id) keys; otherwise, and for batches with non-finite distances, dense exact
@@ -1084,8 +1058,8 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     DevBuf<int> redo;
     SPF_TRY(redo.alloc(st, 1));
     SPF_CUDA(cudaMemsetAsync(redo.p, 0, sizeof(int), st));
-    SPF_TRY(probe_tc_dense(c, idx->ctc, idx->centroids, Q.p, nq, ld, nlists, nprobe, prune_factor, idx->lens, probe.p,
-                           thr.p, seqbase.p, redo.p));
+    SPF_TRY(probe_tc_dense(c, idx->ctc, idx->centroids, Qp, nq, ld, nlists, nprobe, prune_factor, idx->lens, probe,
+                           thr, seqbase, redo.p));
     int h_redo = 0;
     SPF_CUDA(cudaMemcpyAsync(&h_redo, redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SPF_CUDA(cudaStreamSynchronize(st));
@@ -1120,7 +1094,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     SPF_TRY(check_launch(c, "iota_u32_kernel"));
     ScanTcCall pc;
     pc.s.vecs = idx->cvecs; pc.s.slot_ids = idx->cids; pc.s.grp_off = idx->cgrp; pc.s.lens = idx->clens;
-    pc.s.ld = ld; pc.s.d = d; pc.s.Q = Q.p; pc.s.probe = zero.p; pc.s.thr = thr_inf.p; pc.s.seqbase = zero.p;
+    pc.s.ld = ld; pc.s.d = d; pc.s.Q = Qp; pc.s.probe = zero.p; pc.s.thr = thr_inf.p; pc.s.seqbase = zero.p;
     pc.s.nprobe = 1; pc.s.K = nprobe;
     pc.s.out_ids = p_ids.p; pc.s.out_dists = p_dists.p; pc.s.out_counts = p_counts.p; pc.s.out_keys = p_keys.p;
     pc.s.out_slots = p_slots.p; pc.s.bytes = p_bytes.p; pc.s.only = nullptr;
@@ -1131,7 +1105,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     fa.only = p_flag.p;
     SPF_TRY(launch_scan<1>(c, fa, nq));
     probe_from_keys_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(p_keys.p, p_counts.p, nq, nprobe, prune_factor,
-                                                                        idx->lens, probe.p, thr.p, seqbase.p, redo.p);
+                                                                        idx->lens, probe, thr, seqbase, redo.p);
     SPF_TRY(check_launch(c, "probe_from_keys_kernel"));
     int h_redo = 0;
     SPF_CUDA(cudaMemcpyAsync(&h_redo, redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1147,30 +1121,39 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     KernelTimer t(c, "probe");
     for (uint64_t q0 = 0; q0 < nq; q0 += chunk) {
       const uint64_t nc = (nq - q0) < chunk ? (nq - q0) : chunk;
-      SPF_TRY(launch_assign_exact(c, SPF_METRIC_EUCLIDEAN, Q.p + q0 * ld, nc, idx->centroids, nlists, ld, 1.0f,
+      SPF_TRY(launch_assign_exact(c, SPF_METRIC_EUCLIDEAN, Qp + q0 * ld, nc, idx->centroids, nlists, ld, 1.0f,
                                   nullptr, Dqc.p));
       if (nprobe > 16 && nlists <= 1024) {
         probe_sort_kernel<4><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
-                                                          probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+                                                          probe + q0 * nprobe, thr + q0, seqbase + q0 * nprobe);
       } else if (nprobe > 16 && nprobe <= 256 && nlists <= 4096) {        // select the nprobe smallest, sort only those
         probe_topn_kernel<16, 1><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
-                                                              probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+                                                              probe + q0 * nprobe, thr + q0, seqbase + q0 * nprobe);
       } else if (nprobe > 16 && nlists <= 4096) {
         probe_topn_kernel<16, 4><<<(unsigned)nc, 256, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
-                                                              probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+                                                              probe + q0 * nprobe, thr + q0, seqbase + q0 * nprobe);
       } else {
         probe_select_kernel<<<(unsigned)nc, 128, 0, st>>>(Dqc.p, nlists, nprobe, prune_factor, idx->lens,
-                                                          probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
+                                                          probe + q0 * nprobe, thr + q0, seqbase + q0 * nprobe);
       }
       SPF_TRY(check_launch(c, "probe_select_kernel"));
     }
   }
+  return SPF_OK;
+}
+
+static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k, uint32_t nprobe, uint32_t* probe,
+                       const float* thr, const uint32_t* seqbase, uint64_t* o_ids, float* o_dists, uint32_t* o_counts,
+                       unsigned long long* o_keys, unsigned long long* o_slots, unsigned long long* d_bytes) {
+  spf_ctx* c = idx->ctx;
+  cudaStream_t st = c->stream;
+  const uint32_t ld = idx->ld, d = idx->d, nlists = idx->nlists;
   ScanArgs a;
   a.vecs = idx->vecs; a.slot_ids = idx->slot_ids; a.grp_off = idx->grp_off; a.lens = idx->lens;
-  a.ld = ld; a.d = d; a.Q = Q.p; a.probe = probe.p; a.thr = thr.p; a.seqbase = seqbase.p;
+  a.ld = ld; a.d = d; a.Q = Qp; a.probe = probe; a.thr = thr; a.seqbase = seqbase;
   a.nprobe = nprobe; a.K = k;
-  a.out_ids = o_ids.p; a.out_dists = o_dists.p; a.out_counts = o_counts.p; a.out_keys = o_keys.p;
-  a.out_slots = o_slots.p; a.bytes = d_bytes.p; a.only = nullptr;
+  a.out_ids = o_ids; a.out_dists = o_dists; a.out_counts = o_counts; a.out_keys = o_keys;
+  a.out_slots = o_slots; a.bytes = d_bytes; a.only = nullptr;
   // list-major scan when the batch is large enough for lists to be shared between queries; with
   // tens of probing queries per list the TF32 candidate scan (scan_tc.cu) takes over
   const uint64_t npairs = nq * nprobe;
@@ -1194,9 +1177,9 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     int end_bit = 1;
     while (end_bit < 32 && (1ull << end_bit) < (uint64_t)nlists) ++end_bit;
     size_t sort_bytes = 0;
-    SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, probe.p, pk2.p, pv.p, pv2.p, (int64_t)npairs, 0, end_bit, st));
+    SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, probe, pk2.p, pv.p, pv2.p, (int64_t)npairs, 0, end_bit, st));
     SPF_TRY(stmp.alloc(st, sort_bytes));
-    SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sort_bytes, probe.p, pk2.p, pv.p, pv2.p, (int64_t)npairs, 0, end_bit, st));
+    SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sort_bytes, probe, pk2.p, pv.p, pv2.p, (int64_t)npairs, 0, end_bit, st));
     c->launches += 3;
     list_offsets_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(pk2.p, npairs, nlists, loff.p);
     SPF_TRY(check_launch(c, "list_offsets_kernel"));
@@ -1256,6 +1239,46 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
     else if (k <= 64) SPF_TRY(launch_scan<2>(c, a, nq));
     else SPF_TRY(launch_scan<4>(c, a, nq));
   }
+  return SPF_OK;
+}
+
+int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t k, uint32_t nprobe,
+                     float prune_factor, uint64_t* ids, float* dists, uint32_t* counts, float* vectors,
+                     uint64_t* keys) {
+  if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_batch: NULL argument");
+  if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
+  if (nq == 0) return SPF_OK;
+  if (nprobe == 0) nprobe = k;                       // spann_index.rs:164 nearest_n(query, k)
+  if (nprobe > idx->nlists) nprobe = idx->nlists;
+  if (nprobe > 1024) return fail(SPF_E_INVALID, "nprobe must be <= 1024");
+  spf_ctx* c = idx->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  c->kernel_ms.clear();
+  const uint32_t ld = idx->ld, d = idx->d, nlists = idx->nlists;
+
+  DevBuf<float> Q, thr, o_dists;
+  DevBuf<uint32_t> probe, seqbase, o_counts;
+  DevBuf<uint64_t> o_ids;
+  DevBuf<unsigned long long> o_keys, o_slots, d_bytes;
+  SPF_TRY(Q.alloc(st, (size_t)nq * ld));
+  SPF_TRY(thr.alloc(st, nq));
+  SPF_TRY(probe.alloc(st, (size_t)nq * nprobe));
+  SPF_TRY(seqbase.alloc(st, (size_t)nq * nprobe));
+  SPF_TRY(o_ids.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_dists.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_keys.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_slots.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_counts.alloc(st, nq));
+  SPF_TRY(d_bytes.alloc(st, 1));
+  SPF_CUDA(cudaMemsetAsync(d_bytes.p, 0, sizeof(unsigned long long), st));
+  if (ld != d) SPF_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)nq * ld * sizeof(float), st));
+  SPF_CUDA(cudaMemcpy2DAsync(Q.p, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq, cudaMemcpyHostToDevice, st));
+
+  SPF_TRY(search_probe(idx, Q.p, nq, nprobe, prune_factor, probe.p, thr.p, seqbase.p));
+  SPF_TRY(search_scan(idx, Q.p, nq, k, nprobe, probe.p, thr.p, seqbase.p, o_ids.p, o_dists.p, o_counts.p, o_keys.p, o_slots.p,
+                      d_bytes.p));
   DevBuf<float> o_vec;
   if (vectors) {
     SPF_TRY(o_vec.alloc(st, (size_t)nq * k * d));
@@ -1268,6 +1291,130 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   SPF_CUDA(cudaMemcpyAsync(dists, o_dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaMemcpyAsync(counts, o_counts.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   if (keys) SPF_CUDA(cudaMemcpyAsync(keys, o_keys.p, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  unsigned long long bytes = 0;
+  SPF_CUDA(cudaMemcpyAsync(&bytes, d_bytes.p, sizeof(bytes), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  idx->last_scan_bytes = bytes;
+  return SPF_OK;
+}
+
+// Device-side merge of the ranks' partial top-k for this rank's slice of the batch: per query the k
+// smallest keys (distance bits << 32 | encounter index, globally consistent) over the `parts`
+// sorted partial lists — the reference's final stable sort + truncate (spann_index.rs:188-193)
+// applied across list shards.  One thread per query.
+__global__ void topk_merge_kernel(uint32_t parts, uint64_t nq, uint32_t k, const unsigned long long* __restrict__ keys,
+                                  const uint64_t* __restrict__ ids, const float* __restrict__ dists,
+                                  const uint32_t* __restrict__ counts, uint64_t* __restrict__ out_ids,
+                                  float* __restrict__ out_dists, uint32_t* __restrict__ out_counts) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  constexpr uint32_t MAXP = 16;
+  uint32_t cur[MAXP];
+  for (uint32_t p = 0; p < parts; ++p) cur[p] = 0;
+  uint32_t n = 0;
+  while (n < k) {
+    int bp = -1;
+    unsigned long long bk = 0;
+    for (uint32_t p = 0; p < parts; ++p) {
+      if (cur[p] >= counts[(size_t)p * nq + q]) continue;
+      const unsigned long long kk = keys[((size_t)p * nq + q) * k + cur[p]];
+      if (bp < 0 || kk < bk) { bp = (int)p; bk = kk; }      // strict <: the lower rank wins (keys are unique anyway)
+    }
+    if (bp < 0) break;
+    const size_t src = ((size_t)bp * nq + q) * k + cur[bp];
+    out_ids[q * k + n] = ids[src];
+    out_dists[q * k + n] = dists[src];
+    ++cur[bp];
+    ++n;
+  }
+  out_counts[q] = n;
+  for (uint32_t e = n; e < k; ++e) {
+    out_ids[q * k + e] = ~0ull;
+    out_dists[q * k + e] = __int_as_float(0x7f800000);
+  }
+}
+
+// List-sharded batched search over the ranks of `comm`: every rank holds the
+// posting lists [list_begin, list_end) it packed and all centroids.  Each rank brings nq_local
+// queries of the batch (the same count on every rank); the call returns the global top-k of THOSE
+// queries.  On the device: the query slices are all-gathered, each rank probes its own slice and
+// the probe tables are all-gathered (the probe is computed once, not world times), every rank
+// scans its lists for the whole batch, the partial top-k travel to the rank that owns the query
+// (one personalised exchange), and a device merge produces the result.
+int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uint64_t nq_local, uint32_t k,
+                       uint32_t nprobe, float prune_factor, uint64_t* ids, float* dists, uint32_t* counts) {
+  if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_sharded: NULL argument");
+  if (comm && comm->ctx != idx->ctx) return fail(SPF_E_INVALID, "communicator and index belong to different contexts");
+  if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
+  if (nq_local == 0) return fail(SPF_E_INVALID, "every rank must bring at least one query");
+  if (nprobe == 0) nprobe = k;
+  if (nprobe > idx->nlists) nprobe = idx->nlists;
+  if (nprobe > 1024) return fail(SPF_E_INVALID, "nprobe must be <= 1024");
+  const uint32_t world = comm ? (uint32_t)comm->world : 1u, rank = comm ? (uint32_t)comm->rank : 0u;
+  if (world > 16) return fail(SPF_E_INVALID, "at most 16 ranks");
+  spf_ctx* c = idx->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  c->kernel_ms.clear();
+  const uint32_t ld = idx->ld, d = idx->d;
+  const uint64_t nq = nq_local * world;
+
+  DevBuf<float> Q, thr, o_dists, r_dists, m_dists;
+  DevBuf<uint32_t> probe, seqbase, o_counts, r_counts, m_counts;
+  DevBuf<uint64_t> o_ids, r_ids, m_ids;
+  DevBuf<unsigned long long> o_keys, o_slots, d_bytes, r_keys;
+  SPF_TRY(Q.alloc(st, (size_t)nq * ld));
+  SPF_TRY(thr.alloc(st, nq));
+  SPF_TRY(probe.alloc(st, (size_t)nq * nprobe));
+  SPF_TRY(seqbase.alloc(st, (size_t)nq * nprobe));
+  SPF_TRY(o_ids.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_dists.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_keys.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_slots.alloc(st, (size_t)nq * k));
+  SPF_TRY(o_counts.alloc(st, nq));
+  SPF_TRY(d_bytes.alloc(st, 1));
+  SPF_TRY(r_ids.alloc(st, (size_t)nq * k));
+  SPF_TRY(r_dists.alloc(st, (size_t)nq * k));
+  SPF_TRY(r_keys.alloc(st, (size_t)nq * k));
+  SPF_TRY(r_counts.alloc(st, nq));
+  SPF_TRY(m_ids.alloc(st, (size_t)nq_local * k));
+  SPF_TRY(m_dists.alloc(st, (size_t)nq_local * k));
+  SPF_TRY(m_counts.alloc(st, nq_local));
+  SPF_CUDA(cudaMemsetAsync(d_bytes.p, 0, sizeof(unsigned long long), st));
+  float* Qmine = Q.p + (size_t)rank * nq_local * ld;
+  if (ld != d) SPF_CUDA(cudaMemsetAsync(Qmine, 0, (size_t)nq_local * ld * sizeof(float), st));
+  SPF_CUDA(cudaMemcpy2DAsync(Qmine, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq_local, cudaMemcpyHostToDevice, st));
+  {
+    KernelTimer t(c, "exchange");
+    SPF_TRY(comm_allgather(c, comm, Qmine, Q.p, (size_t)nq_local * ld * sizeof(float)));
+  }
+  SPF_TRY(search_probe(idx, Qmine, nq_local, nprobe, prune_factor, probe.p + (size_t)rank * nq_local * nprobe,
+                       thr.p + (size_t)rank * nq_local, seqbase.p + (size_t)rank * nq_local * nprobe));
+  {
+    KernelTimer t(c, "exchange");
+    SPF_TRY(comm_allgather(c, comm, probe.p + (size_t)rank * nq_local * nprobe, probe.p, (size_t)nq_local * nprobe * 4));
+    SPF_TRY(comm_allgather(c, comm, seqbase.p + (size_t)rank * nq_local * nprobe, seqbase.p, (size_t)nq_local * nprobe * 4));
+    SPF_TRY(comm_allgather(c, comm, thr.p + (size_t)rank * nq_local, thr.p, (size_t)nq_local * 4));
+  }
+  SPF_TRY(search_scan(idx, Q.p, nq, k, nprobe, probe.p, thr.p, seqbase.p, o_ids.p, o_dists.p, o_counts.p, o_keys.p, o_slots.p,
+                      d_bytes.p));
+  {
+    KernelTimer t(c, "exchange");
+    SPF_TRY(comm_alltoall(c, comm, o_keys.p, r_keys.p, (size_t)nq_local * k * 8));
+    SPF_TRY(comm_alltoall(c, comm, o_ids.p, r_ids.p, (size_t)nq_local * k * 8));
+    SPF_TRY(comm_alltoall(c, comm, o_dists.p, r_dists.p, (size_t)nq_local * k * 4));
+    SPF_TRY(comm_alltoall(c, comm, o_counts.p, r_counts.p, (size_t)nq_local * 4));
+  }
+  {
+    KernelTimer t(c, "merge");
+    topk_merge_kernel<<<(unsigned)ceil_div(nq_local, 128), 128, 0, st>>>(world, nq_local, k, r_keys.p, r_ids.p, r_dists.p,
+                                                                         r_counts.p, m_ids.p, m_dists.p, m_counts.p);
+    SPF_TRY(check_launch(c, "topk_merge_kernel"));
+  }
+  SPF_CUDA(cudaMemcpyAsync(ids, m_ids.p, (size_t)nq_local * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(dists, m_dists.p, (size_t)nq_local * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(counts, m_counts.p, (size_t)nq_local * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   unsigned long long bytes = 0;
   SPF_CUDA(cudaMemcpyAsync(&bytes, d_bytes.p, sizeof(bytes), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));

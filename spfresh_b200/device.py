@@ -414,6 +414,21 @@ class DeviceIndex:
             out.append(keys)
         return tuple(out)
 
+    def search_sharded(self, comm, queries, k: int, nprobe: int = 0, prune_factor: float = 1.2, out=None):
+        """spf_search_sharded: this rank's slice of the batch against the list-sharded index of the
+        group; returns the global top-k of these queries (collective)."""
+        q = as_f32(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        if out is not None:
+            ids, dists, counts = out
+        else:
+            ids = np.empty((nq, k), np.uint64)
+            dists = np.empty((nq, k), np.float32)
+            counts = np.empty(nq, np.uint32)
+        check(lib().spf_search_sharded(self._h, comm.handle if comm is not None else None, ptr(q), nq, k, nprobe,
+                                       prune_factor, ptr(ids), ptr(dists), ptr(counts)))
+        return ids, dists, counts
+
     def free(self):
         if self._h:
             lib().spf_index_free(self._h)

@@ -1102,3 +1102,29 @@ def test_kmeans_session_two_gpus_nccl_matches_host_staged_shards(spf):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "SHARDED_NCCL_OK" in r.stdout
+
+
+def test_search_sharded_single_rank_equals_search_batch(spf, ctx, oracle):
+    """comm == NULL: the sharded entry point (probe / scan phases on device buffers + device merge)
+    returns exactly what spf_search_batch and the oracle return."""
+    data = clustered(20000, 64, 64, 4242)
+    cent = np.random.default_rng(42).choice(20000, 256, replace=False)
+    ds = spf.Dataset(ctx, data)
+    res = ds.assign(0, cent)
+    f = res.fetch(best=False, dmin=False)
+    med = ds.update_medoids_from(0, res, cent)
+    res.free()
+    idx = spf.DeviceIndex.pack(ds, f.offsets, f.members, med)
+    q = clustered(3000, 64, 64, 4243)
+    for nprobe in (4, 10, 40):
+        a = idx.search_sharded(None, q, 10, nprobe=nprobe)
+        b = idx.search(q, 10, nprobe=nprobe)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    rid, rd, rc = oracle.search_batch(data, f.offsets, f.members, med, q[:500], 10, nprobe=10)
+    a = idx.search_sharded(None, q[:500], 10, nprobe=10)
+    assert np.array_equal(a[2], rc)
+    for i in range(500):
+        assert np.array_equal(a[0][i, :rc[i]], rid[i, :rc[i]])
+    idx.free()
+    ds.free()

@@ -78,12 +78,9 @@ def main():
     ctx = spf.Context(local)
     comm = spf.DeviceComm.from_torch(ctx)
     rows = check_kmeans(ctx, comm, rank, world, dev)
-    extra = ""
-    try:
-        from check_sharded_query import check_query
-        extra = check_query(ctx, comm, rank, world, dev)
-    except ImportError:
-        pass
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from check_sharded_query import check_query
+    extra = check_query(ctx, comm, rank, world, dev)
     dist.barrier()
     if rank == 0:
         print(f"SHARDED_NCCL_OK world={world} rows={rows} {extra}", flush=True)
