@@ -74,6 +74,10 @@ int  spf_ctx_device(const spf_ctx* ctx);
 /* cudaStream_t all work of this context is enqueued on (for CUDA-event timing by callers). */
 void* spf_ctx_stream(spf_ctx* ctx);
 int  spf_ctx_synchronize(spf_ctx* ctx);
+/* The library keeps freed device temporaries in the stream-ordered pool for reuse; this returns
+ * everything that is currently unused to the driver (after a large one-off call, or before another
+ * allocator in the same process needs the memory). */
+int  spf_ctx_trim(spf_ctx* ctx);
 /* Per-kernel device timing: when enabled, the library brackets its dominant kernels with CUDA
  * events on its stream; spf_ctx_kernel_ms returns the duration of the named kernel's last
  * launch ("assign_tc", "assign_exact", "resolve", "csr", "scan", "probe", ...) or < 0. */

@@ -30,6 +30,7 @@ SIGNATURES = {
     "spf_ctx_device": (C.c_int, [_vp]),
     "spf_ctx_stream": (C.c_void_p, [_vp]),
     "spf_ctx_synchronize": (C.c_int, [_vp]),
+    "spf_ctx_trim": (C.c_int, [_vp]),
     "spf_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
     "spf_ctx_kernel_ms": (C.c_float, [_vp, C.c_char_p]),
     "spf_ctx_launch_count": (C.c_uint64, [_vp]),

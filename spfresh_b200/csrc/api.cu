@@ -112,6 +112,17 @@ int spf_ctx_synchronize(spf_ctx* c) {
   return SPF_OK;
 }
 
+int spf_ctx_trim(spf_ctx* c) {
+  if (!c) return fail(SPF_E_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  SPF_CUDA(cudaStreamSynchronize(c->stream));
+  cudaMemPool_t pool;
+  SPF_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
+  SPF_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return SPF_OK;
+}
+
 int spf_ctx_set_profiling(spf_ctx* c, int enabled) {
   if (!c) return fail(SPF_E_INVALID, "ctx is NULL");
   std::lock_guard<std::mutex> lk(c->mu);

@@ -47,6 +47,10 @@ class Context:
     def synchronize(self):
         check(lib().spf_ctx_synchronize(self._h))
 
+    def trim(self):
+        """Return the unused part of the library's device memory pool to the driver."""
+        check(lib().spf_ctx_trim(self._h))
+
     def set_profiling(self, on: bool):
         check(lib().spf_ctx_set_profiling(self._h, 1 if on else 0))
 
