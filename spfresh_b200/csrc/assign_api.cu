@@ -254,7 +254,6 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
   spf_ctx* c = ds->ctx;
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  c->kernel_ms.clear();
   const uint32_t ld = ds->ld;
 
   DevBuf<uint64_t> d_crow, d_pidx;
@@ -339,6 +338,7 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
                spf_assign_result** out) {
   if (!ds || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
+  ds->ctx->kernel_ms.clear();
   return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, nullptr, k, boundary_factor, flags, nullptr, out);
 }
 
@@ -347,6 +347,7 @@ int spf_assign_vectors(spf_dataset* ds, int metric, const uint64_t* point_idx, u
                        spf_assign_result** out) {
   if (!ds || !centroids) return fail(SPF_E_INVALID, "spf_assign_vectors: NULL argument");
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
+  ds->ctx->kernel_ms.clear();
   return assign_resident(ds, metric, point_idx, m, nullptr, centroids, nullptr, k, boundary_factor, flags, nullptr, out);
 }
 

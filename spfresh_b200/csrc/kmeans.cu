@@ -228,9 +228,11 @@ int spf_kmeans_step(spf_kmeans* s) {
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  c->kernel_ms.clear();
   const float* seed = nullptr;
   if (s->last && s->iterations > 0 && !(s->flags & SPF_KMEANS_UNSEEDED) && s->metric == SPF_METRIC_EUCLIDEAN) {
     // exact distance of every point to the NEW centroid of the slot it was nearest to
+    KernelTimer t(c, "kmeans_seed");
     SPF_TRY(s->seed.alloc(st, ds->n));
     SPF_TRY(launch_pair_dist(c, s->metric, ds->x, ds->ld, nullptr, s->cvec.p, ds->ld, s->last->best, UINT64_MAX, ds->ld,
                              ds->n, s->seed.p));
@@ -238,7 +240,6 @@ int spf_kmeans_step(spf_kmeans* s) {
   }
   spf_assign_result* res = nullptr;
   SPF_TRY(assign_device_centroids(ds, s->metric, s->cvec.p, s->k, s->factor, 0, seed, &res));
-  // assign cleared the per-call timers; keep its figures under their own names
   if (s->last) spf_assign_free(s->last);
   s->last = res;
   SPF_TRY(km_update(s));

@@ -140,7 +140,14 @@ int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t*
   if (threads > 1024) threads = 1024;
   cudaStream_t st = c->stream;
   const size_t row_bytes = (size_t)threads * 16;
-  if (row_bytes * 128 <= 64 * 1024) {
+  // One CTA per cluster: the sum of a dimension is a serial chain over the members, so the machine
+  // is filled by many resident clusters per SM, each with a short ring of rows in flight, rather
+  // than by a deep ring per cluster (16 rows x 512 B per warp, ~28 clusters per SM for d = 128:
+  // 4.6 -> see profiles/r02 for the measured figure).
+  if (row_bytes * 16 <= 8 * 1024) {
+    const size_t smem = row_bytes * 16;
+    cluster_mean_kernel<16><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
+  } else if (row_bytes * 128 <= 64 * 1024) {
     const size_t smem = row_bytes * 128;
     SPF_CUDA(cudaFuncSetAttribute(cluster_mean_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cluster_mean_kernel<128><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
