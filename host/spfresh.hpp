@@ -508,14 +508,29 @@ class SpannIndex {
     f.write(reinterpret_cast<const char*>(centroids_.data()), (std::streamsize)(centroids_.size() * sizeof(float)));
   }
 
-  void load_posting_list(const std::string& path) {    // spann_index.rs:32-43
-    std::ifstream f(path + "/centroids.bin", std::ios::binary);
-    if (!f) throw Error("cannot read " + path + "/centroids.bin");
+  // spann_index.rs:32-43.  The dense centroid matrix of the GPU probe comes from the caller
+  // (`centroids`, nlists x d in list-id order) or from the centroids.bin sidecar build() writes; the
+  // reference keeps centroids only inside output.kdtree (kiddo's private layout, not read here), so a
+  // directory written by the reference alone needs the caller's matrix.  The posting-list files
+  // themselves are compatible in both directions.
+  void load_posting_list(const std::string& path, const std::vector<float>* centroids = nullptr, size_t d = 0) {
     uint64_t shape[2] = {0, 0};
-    f.read(reinterpret_cast<char*>(shape), sizeof(shape));
-    centroids_.resize(shape[0] * shape[1]);
-    f.read(reinterpret_cast<char*>(centroids_.data()), (std::streamsize)(centroids_.size() * sizeof(float)));
-    if (!f) throw Error("truncated centroids.bin");
+    if (centroids) {
+      if (d == 0 || centroids->size() % d) throw Error("load_posting_list: centroids must be nlists x d");
+      centroids_ = *centroids;
+      shape[0] = centroids->size() / d;
+      shape[1] = d;
+    } else {
+      std::ifstream f(path + "/centroids.bin", std::ios::binary);
+      if (!f)
+        throw Error("cannot read " + path + "/centroids.bin: the reference stores centroids only inside output.kdtree; "
+                    "pass the centroid matrix to load_posting_list() or write the sidecar with save_centroids()");
+      f.read(reinterpret_cast<char*>(shape), sizeof(shape));
+      if (!f || shape[1] == 0 || shape[0] > (1ull << 32) || shape[1] > (1ull << 20)) throw Error("corrupt centroids.bin");
+      centroids_.resize(shape[0] * shape[1]);
+      f.read(reinterpret_cast<char*>(centroids_.data()), (std::streamsize)(centroids_.size() * sizeof(float)));
+      if (!f) throw Error("truncated centroids.bin");
+    }
     d_ = shape[1];
     if (idx_) { spf_index_free(idx_); idx_ = nullptr; }
     check(spf_index_load_dir(ctx_->handle(), path.c_str(), centroids_.data(), (uint32_t)shape[0], (uint32_t)d_, &idx_));

@@ -132,9 +132,13 @@ int spf_ctx_set_profiling(spf_ctx* c, int enabled) {
 
 float spf_ctx_kernel_ms(spf_ctx* c, const char* name) {
   if (!c || !name) return -1.0f;
-  std::lock_guard<std::mutex> lk(c->mu);
-  auto it = c->kernel_ms.find(name);
-  return it == c->kernel_ms.end() ? -1.0f : it->second;
+  try {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->kernel_ms.find(name);
+    return it == c->kernel_ms.end() ? -1.0f : it->second;
+  } catch (...) {
+    return -1.0f;
+  }
 }
 
 uint64_t spf_ctx_launch_count(const spf_ctx* c) { return c ? c->launches : 0; }
@@ -142,6 +146,7 @@ uint32_t spf_ctx_last_overflow_rows(const spf_ctx* c) { return c ? c->last_overf
 
 // Internal tuning knobs (tests use them to force the rare paths; not part of the drop-in ABI).
 int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
+  return spf::guarded([&]() -> int {
   if (!c || !name) return fail(SPF_E_INVALID, "ctx/name is NULL");
   std::lock_guard<std::mutex> lk(c->mu);
   std::string s(name);
@@ -168,6 +173,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "cc_cache") c->params.cc_cache = value;
   else return fail(SPF_E_INVALID, "unknown parameter '%s'", name);
   return SPF_OK;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,6 +207,7 @@ extern "C" {
 
 int spf_dataset_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride,
                        spf_dataset** out) {
+  return spf::guarded([&]() -> int {
   if (!rows) return fail(SPF_E_INVALID, "rows is NULL");
   if (row_stride < d) return fail(SPF_E_INVALID, "row_stride (%llu) < d (%u)", (unsigned long long)row_stride, d);
   spf_dataset* ds = nullptr;
@@ -218,6 +225,7 @@ int spf_dataset_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, ui
   }
   *out = ds;
   return SPF_OK;
+  });
 }
 
 int spf_dataset_from_device(spf_ctx* c, const void* dev_rows, uint64_t n, uint32_t d, spf_dataset** out) {

@@ -336,24 +336,29 @@ extern "C" {
 int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
                spf_assign_result** out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
   ds->ctx->kernel_ms.clear();
   return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, nullptr, k, boundary_factor, flags, nullptr, out);
+  });
 }
 
 int spf_assign_vectors(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                        const float* centroids, uint32_t k, float boundary_factor, int flags,
                        spf_assign_result** out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !centroids) return fail(SPF_E_INVALID, "spf_assign_vectors: NULL argument");
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
   ds->ctx->kernel_ms.clear();
   return assign_resident(ds, metric, point_idx, m, nullptr, centroids, nullptr, k, boundary_factor, flags, nullptr, out);
+  });
 }
 
 int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride, int metric,
                     const uint64_t* centroid_rows, uint32_t k, float boundary_factor, int flags,
                     spf_dataset** ds_out, spf_assign_result** out) {
+  return spf::guarded([&]() -> int {
   if (!c || !rows || !out || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign_host: NULL argument");
   *out = nullptr;
   if (ds_out) *ds_out = nullptr;
@@ -443,6 +448,7 @@ int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint6
     guard.d = nullptr;
   }
   return SPF_OK;
+  });
 }
 
 uint64_t spf_assign_points(const spf_assign_result* r) { return r ? r->m : 0; }
@@ -451,6 +457,7 @@ uint64_t spf_assign_total(const spf_assign_result* r) { return r ? r->total : 0;
 
 int spf_assign_fetch(const spf_assign_result* r, uint32_t* best, float* dmin, uint64_t* offsets,
                      uint64_t* members) {
+  return spf::guarded([&]() -> int {
   if (!r) return fail(SPF_E_INVALID, "result is NULL");
   spf_ctx* c = r->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -470,6 +477,7 @@ int spf_assign_fetch(const spf_assign_result* r, uint32_t* best, float* dmin, ui
   }
   SPF_CUDA(cudaStreamSynchronize(st));
   return SPF_OK;
+  });
 }
 
 void spf_assign_free(spf_assign_result* r) {

@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <exception>
 #include <map>
+#include <new>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -28,6 +30,21 @@ int fail(int code, const char* fmt, ...);
                          __LINE__);                                                         \
     }                                                                                       \
   } while (0)
+
+// No exception may cross the C ABI (include/spfresh_b200.h): entry points that touch std containers
+// run their body through this guard.
+template <typename F>
+inline int guarded(F&& f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(SPF_E_OOM, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(SPF_E_INVALID, "unexpected exception: %s", e.what());
+  } catch (...) {
+    return fail(SPF_E_INVALID, "unexpected exception");
+  }
+}
 
 #define SPF_TRY(expr)            \
   do {                           \

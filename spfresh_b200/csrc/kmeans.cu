@@ -173,6 +173,7 @@ extern "C" {
 
 int spf_kmeans_create(spf_dataset* ds, spf_comm* comm, int metric, uint64_t row0, uint32_t k, float boundary_factor,
                       int flags, spf_kmeans** out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !out) return fail(SPF_E_INVALID, "spf_kmeans_create: NULL argument");
   *out = nullptr;
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
@@ -202,9 +203,11 @@ int spf_kmeans_create(spf_dataset* ds, spf_comm* comm, int metric, uint64_t row0
   if (rc < 0) { delete s; return rc; }
   *out = s;
   return SPF_OK;
+  });
 }
 
 int spf_kmeans_set_centroids(spf_kmeans* s, const uint64_t* global_rows, const float* vectors) {
+  return spf::guarded([&]() -> int {
   if (!s || !global_rows || !vectors) return fail(SPF_E_INVALID, "spf_kmeans_set_centroids: NULL argument");
   spf_ctx* c = s->ds->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -218,9 +221,11 @@ int spf_kmeans_set_centroids(spf_kmeans* s, const uint64_t* global_rows, const f
   s->have_centroids = true;
   s->iterations = 0;                                    // the next assignment is unseeded
   return SPF_OK;
+  });
 }
 
 int spf_kmeans_step(spf_kmeans* s) {
+  return spf::guarded([&]() -> int {
   if (!s) return fail(SPF_E_INVALID, "spf_kmeans_step: NULL argument");
   if (!s->have_centroids) return fail(SPF_E_STATE, "spf_kmeans_step: no centroids set");
   spf_dataset* ds = s->ds;
@@ -245,9 +250,11 @@ int spf_kmeans_step(spf_kmeans* s) {
   SPF_TRY(km_update(s));
   ++s->iterations;
   return SPF_OK;
+  });
 }
 
 int spf_kmeans_fetch(spf_kmeans* s, uint64_t* rows, float* vectors, float* means, uint64_t* counts) {
+  return spf::guarded([&]() -> int {
   if (!s) return fail(SPF_E_INVALID, "spf_kmeans_fetch: NULL argument");
   spf_ctx* c = s->ds->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -262,6 +269,7 @@ int spf_kmeans_fetch(spf_kmeans* s, uint64_t* rows, float* vectors, float* means
     SPF_CUDA(cudaMemcpy2DAsync(means, (size_t)d * 4, s->means.p, (size_t)ld * 4, (size_t)d * 4, s->k, cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
   return SPF_OK;
+  });
 }
 
 const spf_assign_result* spf_kmeans_assignment(const spf_kmeans* s) { return s ? s->last : nullptr; }

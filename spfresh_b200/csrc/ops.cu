@@ -805,6 +805,7 @@ extern "C" {
 
 int spf_update_medoids(spf_dataset* ds, int metric, const uint64_t* offsets, const uint64_t* members,
                        uint32_t k, const uint64_t* old_rows, uint64_t* new_rows, float* means_out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !offsets || !old_rows || !new_rows) return fail(SPF_E_INVALID, "spf_update_medoids: NULL argument");
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
   if (k == 0) return SPF_OK;
@@ -824,10 +825,12 @@ int spf_update_medoids(spf_dataset* ds, int metric, const uint64_t* offsets, con
   SPF_CUDA(cudaMemcpyAsync(d_off.p, offsets, ((size_t)k + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   if (total) SPF_CUDA(cudaMemcpyAsync(d_rows.p, members, total * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   return update_medoids_dev(ds, metric, d_off.p, d_rows.p, total, k, old_rows, new_rows, means_out);
+  });
 }
 
 int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result* r,
                             const uint64_t* old_rows, uint64_t* new_rows, float* means_out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !r || !old_rows || !new_rows) return fail(SPF_E_INVALID, "spf_update_medoids_from: NULL argument");
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
   if (!r->has_csr) return fail(SPF_E_STATE, "the assign result has no CSR (SPF_ASSIGN_NO_CSR)");
@@ -839,11 +842,13 @@ int spf_update_medoids_from(spf_dataset* ds, int metric, const spf_assign_result
   SPF_TRY(d_rows.alloc(c->stream, r->total));
   SPF_TRY(assign_members_as_rows(r, d_rows.p));
   return update_medoids_dev(ds, metric, r->offsets, d_rows.p, r->total, r->k, old_rows, new_rows, means_out);
+  });
 }
 
 // ---- sharded build: the two halves of update_centroids, so that the mean can be
 // formed from the partial sums of all row shards and the medoid from the per-shard candidates ----
 int spf_cluster_sums(spf_dataset* ds, const spf_assign_result* r, float* sums, uint64_t* counts) {
+  return spf::guarded([&]() -> int {
   if (!ds || !r || !sums || !counts) return fail(SPF_E_INVALID, "spf_cluster_sums: NULL argument");
   if (!r->has_csr) return fail(SPF_E_STATE, "the assign result has no CSR (SPF_ASSIGN_NO_CSR)");
   if (r->ctx != ds->ctx) return fail(SPF_E_INVALID, "result and dataset belong to different contexts");
@@ -865,10 +870,12 @@ int spf_cluster_sums(spf_dataset* ds, const spf_assign_result* r, float* sums, u
   SPF_CUDA(cudaStreamSynchronize(st));
   for (uint32_t j = 0; j < k; ++j) counts[j] = off[j + 1] - off[j];
   return SPF_OK;
+  });
 }
 
 int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* r, const float* means,
                           float* dist, uint64_t* row) {
+  return spf::guarded([&]() -> int {
   if (!ds || !r || !means || !dist || !row) return fail(SPF_E_INVALID, "spf_medoid_candidates: NULL argument");
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
   if (!r->has_csr) return fail(SPF_E_STATE, "the assign result has no CSR (SPF_ASSIGN_NO_CSR)");
@@ -908,6 +915,7 @@ int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* 
   SPF_CUDA(cudaMemcpyAsync(row, d_row.p, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
   return SPF_OK;
+  });
 }
 
 // Shared by spf_farthest (c1 is a dataset row) and spf_farthest_from (c1 is an explicit vector, the
@@ -1027,6 +1035,7 @@ int spf_seq_sum_f32(spf_ctx* c, const float* values, uint64_t n, int mode, float
 
 // ---- k-means++ session ----------------------------------------------------------------------
 int spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !out) return fail(SPF_E_INVALID, "spf_kmpp_begin: NULL argument");
   *out = nullptr;
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
@@ -1052,9 +1061,11 @@ int spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** o
   }
   *out = s;
   return SPF_OK;
+  });
 }
 
 int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
+  return spf::guarded([&]() -> int {
   if (!s || !chosen) return fail(SPF_E_INVALID, "spf_kmpp_round: NULL argument");
   if (!(u01 >= 0.0 && u01 < 1.0)) return fail(SPF_E_INVALID, "u01 must be in [0,1)");
   if (!s->pending) return fail(SPF_E_STATE, "previous round needs spf_kmpp_push() before the next one");
@@ -1098,6 +1109,7 @@ int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
   s->pending = true;
   *chosen = res[1];
   return SPF_OK;
+  });
 }
 
 // ---- row-sharded k-means++: hierarchical.rs:249-293 split at its reductions ----

@@ -21,6 +21,8 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "comm.cuh"
 #include "kernels.cuh"
 
@@ -789,6 +791,7 @@ extern "C" {
 int spf_index_pack(spf_dataset* ds, const uint64_t* offsets, const uint64_t* members,
                    const uint64_t* centroid_rows, uint32_t nlists, uint32_t list_begin, uint32_t list_end,
                    spf_index** out) {
+  return spf::guarded([&]() -> int {
   if (!ds || !offsets || !centroid_rows || !out) return fail(SPF_E_INVALID, "spf_index_pack: NULL argument");
   *out = nullptr;
   if (nlists == 0) return fail(SPF_E_INVALID, "nlists must be > 0");
@@ -861,10 +864,12 @@ int spf_index_pack(spf_dataset* ds, const uint64_t* offsets, const uint64_t* mem
   if (rc < 0) return cleanup(rc);
   *out = idx;
   return SPF_OK;
+  });
 }
 
 int spf_index_load_dir(spf_ctx* c, const char* dir, const float* centroids, uint32_t nlists, uint32_t d,
                        spf_index** out) {
+  return spf::guarded([&]() -> int {
   if (!c || !dir || !centroids || !out) return fail(SPF_E_INVALID, "spf_index_load_dir: NULL argument");
   *out = nullptr;
   if (nlists == 0 || d == 0) return fail(SPF_E_INVALID, "nlists and d must be > 0");
@@ -905,6 +910,10 @@ int spf_index_load_dir(spf_ctx* c, const char* dir, const float* centroids, uint
     uint64_t len = 0;
     if (!get_u64(buf, o, &len)) return cleanup(fail(SPF_E_IO, "%s is truncated", name));
     if (len >= (1ull << 32)) return cleanup(fail(SPF_E_IO, "%s: list too long", name));
+    // the count comes from the file: check it against the file size before anything is sized by it
+    if (len > (buf.size() - o) / (16ull + 4ull * d))
+      return cleanup(fail(SPF_E_IO, "%s is truncated or corrupt (%llu vectors do not fit %zu bytes)", name,
+                          (unsigned long long)len, buf.size()));
     const uint64_t ng = (len + 31) / 32;
     h_vecs.resize((size_t)(g + ng) * 32 * ld, 0.0f);
     h_ids.resize((size_t)(g + ng) * 32, ~0ull);
@@ -940,9 +949,11 @@ int spf_index_load_dir(spf_ctx* c, const char* dir, const float* centroids, uint
   if (rc < 0) return cleanup(rc);
   *out = idx;
   return SPF_OK;
+  });
 }
 
 int spf_index_save_dir(const spf_index* idx, const char* dir) {
+  return spf::guarded([&]() -> int {
   if (!idx || !dir) return fail(SPF_E_INVALID, "spf_index_save_dir: NULL argument");
   spf_ctx* c = idx->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -987,16 +998,41 @@ int spf_index_save_dir(const spf_index* idx, const char* dir) {
     fclose(f);
     ids_written.push_back(l);
   }
+  // cluster_ids.bin lists every list of the directory.  A list-sharded index holds only the range
+  // [list_begin, list_end): ids already recorded there by another shard are kept (read, merge,
+  // write to a temporary, rename), so shards saved one after the other build up the complete
+  // directory.  Concurrent saves into one directory must be serialised by the caller.
+  std::vector<uint64_t> all_ids;
+  {
+    std::vector<unsigned char> old;
+    if (read_file(base + "/cluster_ids.bin", old)) {
+      size_t o = 0;
+      uint64_t m = 0;
+      if (get_u64(old, o, &m) && m <= (old.size() - o) / 8) {
+        for (uint64_t i = 0; i < m; ++i) {
+          uint64_t id = 0;
+          get_u64(old, o, &id);
+          if (id < idx->list_begin || id >= idx->list_end) all_ids.push_back(id);
+        }
+      }
+    }
+  }
+  all_ids.insert(all_ids.end(), ids_written.begin(), ids_written.end());
+  std::sort(all_ids.begin(), all_ids.end());
+  all_ids.erase(std::unique(all_ids.begin(), all_ids.end()), all_ids.end());
   buf.clear();
-  put_u64(buf, ids_written.size());
-  for (uint64_t id : ids_written) put_u64(buf, id);
-  FILE* f = fopen((base + "/cluster_ids.bin").c_str(), "wb");
+  put_u64(buf, all_ids.size());
+  for (uint64_t id : all_ids) put_u64(buf, id);
+  const std::string tmp = base + "/cluster_ids.bin.tmp", fin = base + "/cluster_ids.bin";
+  FILE* f = fopen(tmp.c_str(), "wb");
   if (!f || fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
     if (f) fclose(f);
     return fail(SPF_E_IO, "cannot write %s/cluster_ids.bin", dir);
   }
   fclose(f);
+  if (rename(tmp.c_str(), fin.c_str()) != 0) return fail(SPF_E_IO, "cannot replace %s/cluster_ids.bin", dir);
   return SPF_OK;
+  });
 }
 
 void spf_index_free(spf_index* idx) {
@@ -1245,6 +1281,7 @@ static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k,
 int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t k, uint32_t nprobe,
                      float prune_factor, uint64_t* ids, float* dists, uint32_t* counts, float* vectors,
                      uint64_t* keys) {
+  return spf::guarded([&]() -> int {
   if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_batch: NULL argument");
   if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
   if (nq == 0) return SPF_OK;
@@ -1296,6 +1333,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   SPF_CUDA(cudaStreamSynchronize(st));
   idx->last_scan_bytes = bytes;
   return SPF_OK;
+  });
 }
 
 // Device-side merge of the ranks' partial top-k for this rank's slice of the batch: per query the k
@@ -1343,6 +1381,7 @@ __global__ void topk_merge_kernel(uint32_t parts, uint64_t nq, uint32_t k, const
 // (one personalised exchange), and a device merge produces the result.
 int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uint64_t nq_local, uint32_t k,
                        uint32_t nprobe, float prune_factor, uint64_t* ids, float* dists, uint32_t* counts) {
+  return spf::guarded([&]() -> int {
   if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_sharded: NULL argument");
   if (comm && comm->ctx != idx->ctx) return fail(SPF_E_INVALID, "communicator and index belong to different contexts");
   if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
@@ -1420,6 +1459,7 @@ int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uin
   SPF_CUDA(cudaStreamSynchronize(st));
   idx->last_scan_bytes = bytes;
   return SPF_OK;
+  });
 }
 
 // Host-side merge of per-rank partial top-k (the reference's final stable sort, spann_index.rs:
@@ -1427,6 +1467,7 @@ int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uin
 int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys, const uint64_t* ids,
                    const float* dists, const uint32_t* counts, uint64_t* out_ids, float* out_dists,
                    uint32_t* out_counts) {
+  return spf::guarded([&]() -> int {
   if (!keys || !ids || !dists || !counts || !out_ids || !out_dists || !out_counts)
     return fail(SPF_E_INVALID, "spf_topk_merge: NULL argument");
   if (parts == 0 || k == 0) return fail(SPF_E_INVALID, "parts and k must be > 0");
@@ -1456,6 +1497,7 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
     }
   }
   return SPF_OK;
+  });
 }
 
 }  // extern "C"

@@ -60,6 +60,55 @@ class Config:                                     # config.rs:14-19
         return ClusteringParams(metric, init, None, self.clustering_params.initial_k, None)
 
 
+def read_posting_list_file(path: str):
+    """posting_list_{id}.bin = bincode 1.x of Vec<PointData{point_id: usize, vector: Vec<f32>}>
+    (posting_lists.rs:7-11, 64-90): u64 n, then n x (u64 id, u64 d, d x f32), little endian."""
+    raw = np.fromfile(path, np.uint8)
+    if raw.size < 8:
+        raise OSError(f"{path} is truncated")
+    n = int(raw[:8].view("<u8")[0])
+    if n == 0:
+        return np.zeros(0, np.uint64), np.zeros((0, 0), np.float32)
+    if raw.size < 24:
+        raise OSError(f"{path} is truncated")
+    d = int(raw[16:24].view("<u8")[0])
+    rec = 16 + 4 * d
+    if raw.size != 8 + n * rec:
+        raise OSError(f"{path}: {raw.size} bytes, expected {8 + n * rec} for {n} vectors of {d} floats")
+    body = raw[8:].reshape(n, rec)
+    ids = np.ascontiguousarray(body[:, :8]).view("<u8").reshape(n)
+    vec = np.ascontiguousarray(body[:, 16:]).view("<f4").reshape(n, d)
+    return ids.astype(np.uint64), vec.astype(np.float32)
+
+
+def centroids_from_lists(path: str) -> np.ndarray:
+    """Fallback navigator for a directory without centroids.bin: per list the medoid of its vectors
+    (mean by row-by-row f32 sum, utils.rs:13-14; nearest member by squared L2, strict <, leftmost,
+    hierarchical.rs:155-171).  Lists are numbered by cluster_ids.bin."""
+    raw = np.fromfile(os.path.join(path, "cluster_ids.bin"), "<u8")
+    ids = np.sort(raw[1:1 + int(raw[0])])
+    nlists = int(ids.max()) + 1 if ids.size else 0
+    cen = None
+    for l in ids:
+        _, vec = read_posting_list_file(os.path.join(path, f"posting_list_{int(l)}.bin"))
+        if vec.shape[0] == 0:
+            continue
+        if cen is None:
+            cen = np.zeros((nlists, vec.shape[1]), np.float32)
+        acc = np.zeros(vec.shape[1], np.float32)
+        for row in vec:                                   # sequential f32 row sum
+            acc = (acc + row).astype(np.float32)
+        mean = (acc / np.float32(vec.shape[0])).astype(np.float32)
+        diff = (vec - mean).astype(np.float32)
+        dist = np.zeros(vec.shape[0], np.float32)
+        for j in range(vec.shape[1]):                     # sequential un-fused f32 chain per member
+            dist = (dist + (diff[:, j] * diff[:, j]).astype(np.float32)).astype(np.float32)
+        cen[int(l)] = vec[int(np.argmin(dist))]           # argmin returns the first minimum
+    if cen is None:
+        raise OSError(f"{path} holds no posting lists")
+    return cen
+
+
 class SpannIndex:
     """spann_index.rs:17-197.  The kd-tree over centroids is replaced by an exact batched probe
     (same result: exact k-NN by squared L2, ascending) and the per-cluster files by lists in HBM."""
@@ -93,11 +142,36 @@ class SpannIndex:
             f.write(np.array(c.shape, "<u8").tobytes())
             f.write(c.astype("<f4").tobytes())
 
-    def load_posting_list(self, path: str, centroids_path: Optional[str] = None):   # spann_index.rs:32-43
+    def load_posting_list(self, path: str, centroids_path: Optional[str] = None, centroids=None,
+                          recompute_centroids: bool = False):                          # spann_index.rs:32-43
+        """Loads posting_list_{id}.bin + cluster_ids.bin (the reference's layout, both directions
+        compatible) and the dense centroid matrix the GPU probe needs.  The reference keeps the
+        centroids only inside output.kdtree (gzip + bincode of kiddo's private tree layout, which
+        is not read here), so the matrix comes from, in this order:
+          1. `centroids` (nlists x d, list-id order) given by the caller;
+          2. the `centroids.bin` sidecar this builder writes next to the lists;
+          3. `recompute_centroids=True`: per list the member nearest (squared L2, leftmost on ties)
+             to the list's mean, i.e. what update_centroids (hierarchical.rs:138-181) produced for
+             a Euclidean build whose clusters were not bisected afterwards.  For other builds this
+             is only an approximation of the reference's navigator: results can differ from it.
+        A directory written by the reference alone therefore needs 1. or 3.; a directory written
+        here lacks output.kdtree, so the reference's own load() cannot query it (one-way format for
+        the navigator, two-way for the lists)."""
         cpath = centroids_path or os.path.join(path, "centroids.bin")
-        with open(cpath, "rb") as f:
-            shape = np.frombuffer(f.read(16), "<u8")
-            cen = np.frombuffer(f.read(), "<f4").reshape(int(shape[0]), int(shape[1]))
+        if centroids is not None:
+            cen = np.ascontiguousarray(centroids, np.float32)
+        elif os.path.exists(cpath):
+            with open(cpath, "rb") as f:
+                shape = np.frombuffer(f.read(16), "<u8")
+                cen = np.frombuffer(f.read(), "<f4").reshape(int(shape[0]), int(shape[1]))
+        elif recompute_centroids:
+            cen = centroids_from_lists(path)
+        else:
+            raise FileNotFoundError(
+                f"{cpath} not found: the reference stores centroids only inside output.kdtree (kiddo's private layout). "
+                "Pass centroids=<nlists x d array>, or recompute_centroids=True to derive them from the lists "
+                "(exact for Euclidean builds without bisected clusters), or write the sidecar with "
+                "SpannIndex.save_centroids().")
         self.centroids = cen
         self.device_index = DeviceIndex.load_dir(self.ctx, path, cen)
 
@@ -158,9 +232,11 @@ class SpannIndexBuilder:
             pass
         return index
 
-    def load(self, N: Optional[int] = None) -> SpannIndex:    # spann_builder.rs:66-75
+    def load(self, N: Optional[int] = None, centroids=None, recompute_centroids: bool = False) -> SpannIndex:
+        """spann_builder.rs:66-75.  See SpannIndex.load_posting_list for where the centroid matrix comes
+        from (the sidecar written by build(), the caller, or the lists themselves)."""
         if self.config.output_path is None:
             raise ValueError("Output path is not specified")
         index = SpannIndex(self.config.output_path, self.ctx or Context.default())
-        index.load_posting_list(self.config.output_path)
+        index.load_posting_list(self.config.output_path, centroids=centroids, recompute_centroids=recompute_centroids)
         return index

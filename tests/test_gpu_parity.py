@@ -877,6 +877,64 @@ def test_index_files_interoperate_with_reference_layout(spf, ctx, oracle, tmp_pa
         assert np.array_equal(x, y)
 
 
+def test_index_shards_saved_into_one_directory_reload_complete(spf, ctx, oracle, tmp_path):
+    """two list shards saved one after the other into the same directory must leave a
+    complete cluster_ids.bin; the reloaded index answers like the unsharded one."""
+    data = gauss(2500, 16, 31)
+    cent, off, mem = build_lists(oracle, data, 11, 2)
+    ds = spf.Dataset(ctx, data)
+    full = spf.DeviceIndex.pack(ds, off, mem, cent)
+    d = tmp_path / "shards"
+    for lo, hi in ((0, 4), (4, 11)):
+        part = spf.DeviceIndex.pack(ds, off, mem, cent, list_range=(lo, hi))
+        part.save_dir(str(d))
+        part.free()
+    ids = np.fromfile(d / "cluster_ids.bin", "<u8")
+    assert ids[0] == 11 and sorted(ids[1:].tolist()) == list(range(11))
+    loaded = spf.DeviceIndex.load_dir(ctx, str(d), data[cent.astype(np.int64)])
+    q = gauss(80, 16, 32)
+    for x, y in zip(full.search(q, 9), loaded.search(q, 9)):
+        assert np.array_equal(x, y)
+
+
+def test_index_load_rejects_corrupt_files_and_finds_centroids(spf, ctx, oracle, tmp_path):
+    """A truncated / corrupt posting-list file is an error code, never an abort (the count in the file
+    is checked against the file size before anything is allocated); a directory without the
+    centroids.bin sidecar loads with caller-supplied or recomputed centroids."""
+    data = clustered(1200, 8, 6, 77)
+    cent = np.random.default_rng(3).choice(1200, 6, replace=False).astype(np.uint64)
+    a = oracle.assign(data, 0, cent)
+    med = oracle.update_medoids(data, 0, a.offsets, a.members, cent)
+    ds = spf.Dataset(ctx, data)
+    idx = spf.DeviceIndex.pack(ds, a.offsets, a.members, med)
+    good = tmp_path / "good"
+    idx.save_dir(str(good))
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    for f in os.listdir(good):
+        raw = open(good / f, "rb").read()
+        if f == "posting_list_2.bin":
+            raw = (2 ** 31).to_bytes(8, "little") + raw[8:]          # an absurd vector count
+        open(bad / f, "wb").write(raw)
+    with pytest.raises(spf.SpfError):
+        spf.DeviceIndex.load_dir(ctx, str(bad), data[med.astype(np.int64)])
+    open(bad / "posting_list_2.bin", "wb").write(open(good / "posting_list_2.bin", "rb").read()[:-5])
+    with pytest.raises(spf.SpfError):
+        spf.DeviceIndex.load_dir(ctx, str(bad), data[med.astype(np.int64)])
+    # no sidecar: explicit error, then the two fallbacks
+    index = spf.SpannIndex(str(good), ctx)
+    with pytest.raises(FileNotFoundError):
+        index.load_posting_list(str(good))
+    index.load_posting_list(str(good), centroids=data[med.astype(np.int64)])
+    q = clustered(50, 8, 6, 78)
+    want = idx.search(q, 5)
+    got = index.device_index.search(q, 5)
+    assert all(np.array_equal(x, y) for x, y in zip(want, got))
+    index2 = spf.SpannIndex(str(good), ctx)
+    index2.load_posting_list(str(good), recompute_centroids=True)     # medoids of the lists == update_centroids' output
+    assert np.array_equal(index2.centroids.view(np.uint32), data[med.astype(np.int64)].view(np.uint32))
+
+
 # ----------------------------------------------------------------------------------------------
 # LIRE operations on the hot-path kernels (src/spann/lire/operations.rs, SURVEY §8(f) rank 4)
 # ----------------------------------------------------------------------------------------------

@@ -183,3 +183,25 @@ def test_posting_list_bincode_roundtrip(oracle, tmp_path):
     oracle.cluster_ids_write(str(tmp_path), [7, 3])
     raw = open(os.path.join(tmp_path, "cluster_ids.bin"), "rb").read()
     assert np.array_equal(np.frombuffer(raw, "<u8"), [2, 7, 3])
+
+
+def test_posting_list_reader_and_centroid_fallback_match_oracle_files(oracle, tmp_path):
+    """spfresh_b200.spann.read_posting_list_file / centroids_from_lists (the loader's fallback when a
+    directory has no centroids.bin) on files written by the oracle's bincode writer."""
+    from spfresh_b200.spann import centroids_from_lists, read_posting_list_file
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((400, 6)).astype(np.float32)
+    cent = rng.choice(400, 5, replace=False).astype(np.uint64)
+    a = oracle.assign(data, 0, cent)
+    med = oracle.update_medoids(data, 0, a.offsets, a.members, cent)
+    for j in range(5):
+        oracle.posting_list_write(str(tmp_path), j, data, a.members[int(a.offsets[j]):int(a.offsets[j + 1])])
+    oracle.cluster_ids_write(str(tmp_path), [3, 0, 4, 1, 2])
+    ids, vec = read_posting_list_file(str(tmp_path / "posting_list_3.bin"))
+    want = a.members[int(a.offsets[3]):int(a.offsets[4])]
+    assert np.array_equal(ids, want) and np.array_equal(vec, data[want.astype(np.int64)])
+    cen = centroids_from_lists(str(tmp_path))
+    assert np.array_equal(cen.view(np.uint32), data[med.astype(np.int64)].view(np.uint32))
+    open(tmp_path / "posting_list_1.bin", "ab").write(b"x")
+    with pytest.raises(OSError):
+        read_posting_list_file(str(tmp_path / "posting_list_1.bin"))
