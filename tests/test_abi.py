@@ -34,6 +34,23 @@ def test_every_declared_symbol_is_exported_and_bound(capi):
     assert L.spf_abi_version() == 1
 
 
+def test_rust_ffi_matches_header_and_ctypes(capi):
+    """spann-cuda-sys/src/ffi.rs is generated from the header (tools/gen_rust_ffi.py): it must be up to
+    date, declare exactly the exported functions, and agree with the ctypes table on arity."""
+    import subprocess
+    import sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"])
+    rs = open(os.path.join(ROOT, "spann-cuda-sys", "src", "ffi.rs")).read()
+    fns = dict(re.findall(r"pub fn (spf_\w+)\(([^)]*)\)", rs))
+    assert sorted(fns) == declared_functions()
+    for name, args in fns.items():
+        arity = 0 if not args.strip() else args.count(":")
+        assert arity == len(capi.SIGNATURES[name][1]), name
+    for f in ("Cargo.toml", "build.rs", "src/lib.rs", "integration/hierarchical_gpu.rs", "integration/spann_index_gpu.rs",
+              "integration/distance_kind.rs"):
+        assert os.path.exists(os.path.join(ROOT, "spann-cuda-sys", f)), f
+
+
 def test_header_compiles_as_c(tmp_path):
     import subprocess
     c = tmp_path / "t.c"
