@@ -30,8 +30,11 @@
 //              threshold, candidate emission with predicated 256-bit stores.
 // Round-2 measurements (1M x 128, k = 4096, profiles/r02_experiment_notes.md): 16 epilogue warps
 // (96 registers) 2.10 ms, pipelined loads + two 128-bit stores 1.85 ms, 256-bit stores 1.80 ms,
-// load-all-first + 256-bit stores 1.76 ms; the same instruction stream with no record stores 1.66 ms,
-// MMA + TMA alone 1.48 ms.
+// load-all-first + 256-bit stores 1.76 ms, + per-chunk capacity vote 1.74 ms; the same instruction
+// stream with no record stores 1.66 ms, MMA + TMA alone 1.48 ms.  Also tried and dropped: records as
+// two parallel arrays (values + indices, 1.79 ms: two store transactions per record cost more than
+// the operand-register wait of the single 256-bit store), two alternating index register quads
+// (1.77 ms: the kernel sits at the 168-register limit of 10 warps per SM).
 // An optional per-point seed (a certified upper bound of the point's minimum distance, e.g. the
 // running minimum of the k-means++ rounds or the distance to the previous iteration's centroid)
 // tightens the candidate test from the first column on; resolve validates it a posteriori.
@@ -279,7 +282,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           const float thr_s = fmaf(f1, sshare, thrK);
           uint32_t gi = gtile + c * 8;                     // group index of the record being tested
-          if (fast) {
+          // room for this chunk's 8 records in every lane of the warp: known for the whole tile
+          // (`fast`), else voted per chunk — the branchy slow path only runs when some lane is
+          // within 8 records of its segment's end (1.78 -> 1.74 ms)
+          const bool fastc = fast || __all_sync(0xffffffffu, (((unsigned long long)whi << 32) | wlo) + 8ull * sizeof(CandRec) <= wend &&
+                                                                 wlo <= 0xffffffffu - 8u * (uint32_t)sizeof(CandRec));
+          if (fastc) {
             // straight-line predicated record stores, no vote and no branch: one 256-bit store per
             // record — half the store transactions of two 128-bit stores (measured: 1.81 -> 1.76 ms)
             // and the whole 32-byte sector is written, so DRAM never has to read-fill it.  The last
