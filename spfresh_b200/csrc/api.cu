@@ -99,6 +99,9 @@ void spf_ctx_destroy(spf_ctx* c) {
   if (c->cc_cache.C) cudaFree(c->cc_cache.C);
   if (c->cc_cache.same) cudaFree(c->cc_cache.same);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->aux_ev[0]) cudaEventDestroy(c->aux_ev[0]);
+  if (c->aux_ev[1]) cudaEventDestroy(c->aux_ev[1]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -82,6 +82,8 @@ struct spf_ctx {
   int cc_major = 0, cc_minor = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // host-streamed assign: uploads overlap the main stream
+  cudaStream_t aux_stream = nullptr;    // independent kernels that may overlap the main stream (hub clusters of the mean)
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
   std::mutex mu;
   bool profiling = false;
   cudaEvent_t ev[2] = {nullptr, nullptr};

@@ -1,5 +1,6 @@
 // ops.cu — centroid update, k-means++ rounds, bisect seed and per-pair distances.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -7,6 +8,7 @@
 
 #include "kernels.cuh"
 #include "pairdist.cuh"
+#include "tc_ptx.cuh"
 
 using namespace spf;
 
@@ -133,21 +135,218 @@ __global__ void cluster_mean_kernel(const float* __restrict__ X, uint32_t ld4, c
   }
 }
 
-// ring depth by row width: as many rows in flight as 64 KB of shared memory hold
+// ---- compute_mean for skewed cluster sizes: warp-specialised producer / consumer ------------
+// High-dimensional data makes hub clusters (1M x 128 N(0,1), k = 4096: the largest cluster holds
+// 90 000 of 5.7 M members), and the ordered sum of a cluster is a serial chain, so the time of the
+// whole update is the time of the largest cluster.  One CTA of four warps per cluster:
+//   producers  (4 warps, or 12 for hub clusters): stages of member rows, copied with cp.async (one
+//              16-byte piece per lane and 128-bit column) into a ring in shared memory; the stage's
+//              mbarrier completes when every producer lane's copies have landed
+//              (cp.async.mbarrier.arrive.noinc); member indices are fetched three stages ahead.  A
+//              warp sustains only ~10 gathered rows per microsecond (its copies in flight / memory
+//              latency), so a hub cluster gets 12 producers and a ring of up to 192 KB
+//   last warp  consumer: waits for a stage, adds its rows in member order — one LDS.128 + four
+//              un-fused FADD per row and 128-bit column, i.e. the chain itself — releases the stage
+// The chain runs at a few cycles per row instead of waiting for a gather round trip per group of
+// rows, and small clusters still fill the machine (<= 64 KB of ring per CTA).  Same operations in the
+// same order as cluster_mean_kernel.  (A TMA variant, one cp.async.bulk per 512-byte row, was
+// measured slower: 83 ns per row against 56 for the single-warp kernel.)
+constexpr int CSB_COLS = 8;            // 128-bit columns per lane: rows up to 32 * 8 * 4 = 1024 floats
+
+// nprod producer warps + one consumer warp; only clusters with min_n <= size < max_n are processed
+// (two launches: a light configuration for the many ordinary clusters, a deep one for the hubs)
+__global__ void __launch_bounds__(512)
+cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t* __restrict__ offsets,
+                      const uint64_t* __restrict__ rows, float* __restrict__ out, int divide, uint32_t stage_rows,
+                      uint32_t nstage, uint32_t nprod, uint64_t min_n, uint64_t max_n) {
+  extern __shared__ __align__(128) unsigned char csb_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(csb_raw);          // [nstage]
+  uint64_t* empty = full + nstage;                                 // [nstage]
+  float4* ring = reinterpret_cast<float4*>(csb_raw + 1024);        // [nstage][stage_rows][ld4]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = blockIdx.x;
+  const uint64_t b = offsets[c], e = offsets[c + 1];
+  const uint64_t n = e - b;
+  if (n < min_n || n >= max_n) return;                            // the other launch owns this cluster
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < nstage; ++s) { tc::mbar_init(&full[s], 32); tc::mbar_init(&empty[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // 32-bit bookkeeping throughout (a cluster has < 2^32 members) and no division in the loops: the
+  // stage index / phase pair is advanced incrementally (64-bit `it % nstage` cost more than the copies)
+  const uint32_t n32 = (uint32_t)n;
+  const uint32_t nit = (n32 + stage_rows - 1) / stage_rows;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  const uint64_t* crow = rows + b;
+  if ((uint32_t)warp < nprod) {
+    // ---------------- producers: stage `it` is filled by warp it % nprod; lane l < stage_rows owns row l of
+    // the stage.  The member indices are fetched three of the warp's stages ahead of their use, so the
+    // dependent index load never sits in front of the copies. ------------------------------------------
+    auto load_idx = [&](uint32_t it) -> uint32_t {          // dataset rows are < 2^32
+      const uint32_t t = it * stage_rows + (uint32_t)lane;
+      return ((uint32_t)lane < stage_rows && it < nit && t < n32) ? (uint32_t)crow[t] : 0u;
+    };
+    uint32_t idx0 = load_idx((uint32_t)warp), idx1 = load_idx((uint32_t)warp + nprod), idx2 = load_idx((uint32_t)warp + 2 * nprod);
+    uint32_t s = (uint32_t)warp % nstage, ph = ((uint32_t)warp / nstage) & 1u;
+    for (uint32_t it = (uint32_t)warp; it < nit; it += nprod) {
+      const uint32_t idx = idx0;
+      idx0 = idx1;
+      idx1 = idx2;
+      idx2 = load_idx(it + 3 * nprod);
+      const uint32_t r0 = it * stage_rows;
+      const uint32_t cnt = (n32 - r0) < stage_rows ? (n32 - r0) : stage_rows;
+      tc::mbar_wait(&empty[s], ph ^ 1);                       // the consumer is done with this stage
+      const uint32_t st = tc::smem_u32(ring + (size_t)s * stage_rows * ld4);
+      for (uint32_t r = 0; r < cnt; ++r) {
+        const uint32_t row = __shfl_sync(0xffffffffu, idx, (int)r);
+        const float4* src = X4 + (size_t)row * ld4;
+        for (uint32_t col = (uint32_t)lane; col < ld4; col += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + (r * ld4 + col) * 16u), "l"(src + col) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&full[s])) : "memory");
+      s += nprod;
+      while (s >= nstage) { s -= nstage; ph ^= 1u; }
+    }
+  } else {
+    // ------------------------------ consumer -------------------------------------------------
+    float4 acc[CSB_COLS];
+#pragma unroll
+    for (int j = 0; j < CSB_COLS; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t s = 0, ph = 0;
+    for (uint32_t it = 0; it < nit; ++it) {
+      const uint32_t r0 = it * stage_rows;
+      const uint32_t cnt = (n32 - r0) < stage_rows ? (n32 - r0) : stage_rows;
+      tc::mbar_wait(&full[s], ph);
+      const float4* st = ring + (size_t)s * stage_rows * ld4 + lane;
+      if (ld4 <= 32) {                                         // one column per lane: groups of 8 rows, loads first
+        if ((uint32_t)lane < ld4) {
+          // software pipeline over groups of 8 rows, two register sets in ping-pong: the next group's
+          // LDS.128 are in flight while the current group's four FADD chains run
+          uint32_t r = 0;
+          float4 v[8], w[8];
+          bool have_v = false;
+          if (cnt >= 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = st[u * ld4];
+            have_v = true;
+          }
+          while (have_v) {
+            const bool have_w = r + 16 <= cnt;
+            if (have_w) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) w[u] = st[(r + 8 + u) * ld4];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc[0].x = __fadd_rn(acc[0].x, v[u].x); acc[0].y = __fadd_rn(acc[0].y, v[u].y);
+              acc[0].z = __fadd_rn(acc[0].z, v[u].z); acc[0].w = __fadd_rn(acc[0].w, v[u].w);
+            }
+            r += 8;
+            if (!have_w) break;
+            have_v = r + 16 <= cnt;
+            if (have_v) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = st[(r + 8 + u) * ld4];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc[0].x = __fadd_rn(acc[0].x, w[u].x); acc[0].y = __fadd_rn(acc[0].y, w[u].y);
+              acc[0].z = __fadd_rn(acc[0].z, w[u].z); acc[0].w = __fadd_rn(acc[0].w, w[u].w);
+            }
+            r += 8;
+          }
+          for (; r < cnt; ++r) {
+            const float4 t = st[r * ld4];
+            acc[0].x = __fadd_rn(acc[0].x, t.x); acc[0].y = __fadd_rn(acc[0].y, t.y);
+            acc[0].z = __fadd_rn(acc[0].z, t.z); acc[0].w = __fadd_rn(acc[0].w, t.w);
+          }
+        }
+      } else {
+        for (uint32_t r = 0; r < cnt; ++r) {
+#pragma unroll
+          for (int j = 0; j < CSB_COLS; ++j) {
+            if ((uint32_t)lane + 32u * j < ld4) {
+              const float4 v = st[r * ld4 + 32u * j];
+              acc[j].x = __fadd_rn(acc[j].x, v.x); acc[j].y = __fadd_rn(acc[j].y, v.y);
+              acc[j].z = __fadd_rn(acc[j].z, v.z); acc[j].w = __fadd_rn(acc[j].w, v.w);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty[s]);
+      if (++s == nstage) { s = 0; ph ^= 1u; }
+    }
+#pragma unroll
+    for (int j = 0; j < CSB_COLS; ++j) {
+      const uint32_t col = (uint32_t)lane + 32u * j;
+      if (col < ld4) {
+        float4 a4 = acc[j];
+        if (divide && n > 0) {
+          const float fm = (float)n;
+          a4.x = __fdiv_rn(a4.x, fm); a4.y = __fdiv_rn(a4.y, fm); a4.z = __fdiv_rn(a4.z, fm); a4.w = __fdiv_rn(a4.w, fm);
+        }
+        reinterpret_cast<float4*>(out)[(size_t)c * ld4 + col] = a4;
+      }
+    }
+  }
+}
+
+// per-cluster ordered row sums (divide != 0: the mean)
 int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t* d_offsets, const uint64_t* d_rows,
                         uint32_t k, float* means, int divide) {
+  cudaStream_t st = c->stream;
+
+  const uint32_t ld4 = ld / 4;
+  if (ld4 <= 32 * CSB_COLS) {
+    SPF_CUDA(cudaFuncSetAttribute(cluster_sum_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+    const uint64_t hub = 8192;          // clusters at least this large get the deep configuration
+    // Every ring slot must always be filled by the same producer warp (the parity waits allow a
+    // producer to be one phase ahead of the consumer, not two), so the number of producers divides
+    // the number of stages.
+    {   // hub clusters: 12 producers, the same stages, up to 192 KB of ring (one CTA per SM); the CTAs of
+        // ordinary clusters return at once.  Runs on the context's auxiliary stream next to the launch
+        // below (disjoint clusters), so the hubs' serial chains overlap the ordinary clusters.
+      uint32_t stage_rows = (16u * 1024u) / (ld4 * 16u);
+      if (stage_rows > 32) stage_rows = 32;
+      if (stage_rows < 1) stage_rows = 1;
+      const size_t stage_bytes = (size_t)stage_rows * ld4 * 16;
+      uint32_t nstage = (uint32_t)((192u * 1024u) / stage_bytes);
+      if (nstage > 12) nstage = 12;
+      if (nstage < 2) nstage = 2;
+      const uint32_t nprod = nstage;                                   // one fixed slot per producer warp
+      const size_t smem = 1024 + (size_t)nstage * stage_bytes;
+      if (!c->aux_stream) SPF_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+      if (!c->aux_ev[0]) {
+        SPF_CUDA(cudaEventCreateWithFlags(&c->aux_ev[0], cudaEventDisableTiming));
+        SPF_CUDA(cudaEventCreateWithFlags(&c->aux_ev[1], cudaEventDisableTiming));
+      }
+      SPF_CUDA(cudaEventRecord(c->aux_ev[0], st));                     // inputs are ready on the main stream
+      SPF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
+      cluster_sum_ws_kernel<<<k, (nprod + 1) * 32, smem, c->aux_stream>>>(X, ld4, d_offsets, d_rows, means, divide, stage_rows,
+                                                                         nstage, nprod, hub, ~0ull);
+      SPF_TRY(check_launch(c, "cluster_sum_ws_kernel"));
+      SPF_CUDA(cudaEventRecord(c->aux_ev[1], c->aux_stream));
+    }
+    {   // ordinary clusters: 4 producers, 8 stages of up to 16 rows and <= 8 KB (64 KB of ring, 3 CTAs per SM)
+      uint32_t stage_rows = (8u * 1024u) / (ld4 * 16u);
+      if (stage_rows > 32) stage_rows = 32;
+      if (stage_rows < 1) stage_rows = 1;
+      const size_t stage_bytes = (size_t)stage_rows * ld4 * 16;
+      const uint32_t nstage = 8, nprod = 4;
+      const size_t smem = 1024 + (size_t)nstage * stage_bytes;       // <= 129 KB for rows of 1024 floats
+      cluster_sum_ws_kernel<<<k, (nprod + 1) * 32, smem, st>>>(X, ld4, d_offsets, d_rows, means, divide, stage_rows, nstage, nprod,
+                                                              0ull, hub);
+      SPF_TRY(check_launch(c, "cluster_sum_ws_kernel"));
+    }
+    SPF_CUDA(cudaStreamWaitEvent(st, c->aux_ev[1], 0));                // both halves done before anything downstream
+    return SPF_OK;
+  }
   unsigned threads = round_up(ld / 4, 32);
   if (threads > 1024) threads = 1024;
-  cudaStream_t st = c->stream;
   const size_t row_bytes = (size_t)threads * 16;
-  // One CTA per cluster: the sum of a dimension is a serial chain over the members, so the machine
-  // is filled by many resident clusters per SM, each with a short ring of rows in flight, rather
-  // than by a deep ring per cluster (16 rows x 512 B per warp, ~28 clusters per SM for d = 128:
-  // 4.6 -> see profiles/r02 for the measured figure).
-  if (row_bytes * 16 <= 8 * 1024) {
-    const size_t smem = row_bytes * 16;
-    cluster_mean_kernel<16><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
-  } else if (row_bytes * 128 <= 64 * 1024) {
+  if (row_bytes * 128 <= 64 * 1024) {
     const size_t smem = row_bytes * 128;
     SPF_CUDA(cudaFuncSetAttribute(cluster_mean_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cluster_mean_kernel<128><<<k, threads, smem, st>>>(X, ld / 4, d_offsets, d_rows, means, divide);
