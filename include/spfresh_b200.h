@@ -201,13 +201,25 @@ int  spf_comm_rank(const spf_comm* comm);
  *   assignment     the rank's last local assignment (owned by the session, valid until the next
  *                  step / free), for spf_assign_fetch or spf_index_pack */
 enum { SPF_KMEANS_DEFAULT = 0,
-       SPF_KMEANS_UNSEEDED = 1 /* do not seed the assignment with the previous iteration's result */ };
+       SPF_KMEANS_UNSEEDED = 1, /* do not seed the assignment with the previous iteration's result */
+       SPF_KMEANS_BALANCED = 2, /* extension: size-balancing penalty in the assignment (see below)  */
+       SPF_KMEANS_MEANS = 4     /* extension: Lloyd iterations, the centroid is the mean itself     */ };
 int  spf_kmeans_create(spf_dataset* ds, spf_comm* comm, int metric, uint64_t row0, uint32_t k,
                        float boundary_factor, int flags, spf_kmeans** out);
 int  spf_kmeans_set_centroids(spf_kmeans* s, const uint64_t* global_rows, const float* vectors);
 int  spf_kmeans_step(spf_kmeans* s);
 int  spf_kmeans_fetch(spf_kmeans* s, uint64_t* rows, float* vectors, float* means, uint64_t* counts);
 const spf_assign_result* spf_kmeans_assignment(const spf_kmeans* s);
+/* EXTENSION beyond the reference (north_star: "the size-balancing penalty is applied in the same
+ * pass"; the reference's fit() is one assign + one update, hierarchical.rs:65-71, so there is no
+ * reference behaviour: the specification is oracle/spf_oracle.h orc_assign_balanced, parity unpinned).
+ * With SPF_KMEANS_BALANCED a point goes to argmin_j fl(d(x, c_j) + lambda * n_j), n_j the global size
+ * of cluster j after the previous iteration, and belongs to that cluster only.  The same assignment
+ * as a single call, with explicit centroid vectors and penalties (k floats >= 0, NULL = zeros): */
+int  spf_kmeans_set_balance(spf_kmeans* s, float lambda);
+int  spf_assign_balanced(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
+                         const float* centroids, const float* penalty, uint32_t k, int flags,
+                         spf_assign_result** out);
 void spf_kmeans_free(spf_kmeans* s);
 
 /* ---- k-means++ ------------------------------------------------------------------------- *

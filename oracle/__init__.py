@@ -93,6 +93,9 @@ def lib():
     L.orc_cluster_ids_write.argtypes = [C.c_char_p, up, C.c_size_t]
     L.orc_posting_list_read.restype = C.c_int
     L.orc_posting_list_read.argtypes = [C.c_char_p, C.c_uint64, up, up, C.POINTER(up), C.POINTER(fp)]
+    L.orc_assign_balanced.restype = C.c_int
+    L.orc_assign_balanced.argtypes = [fp, C.c_size_t, C.c_int, up, C.c_size_t, fp, fp, C.c_size_t, C.c_int,
+                                      C.POINTER(C.c_uint32), fp]
     L.orc_free.argtypes = [C.c_void_p]
     L.orc_online_cpus.restype = C.c_int
     _lib = L
@@ -175,6 +178,33 @@ def assign(data, metric, centroid_rows, point_idx=None, boundary_factor=1.1, thr
     dmin = np.ctypeslib.as_array(res.dmin, (max(m, 1),))[:m].copy()
     lib().orc_assign_free(C.byref(res))
     return AssignResult(offsets, members, best, dmin)
+
+
+def assign_balanced(data, metric, centroids, penalty=None, point_idx=None, threads=0) -> AssignResult:
+    """EXTENSION (parity unpinned — the reference has no balanced assignment): cost = fl(d + penalty[j]),
+    argmin with the reference's fold, every point in exactly its best cluster (CSR in input order)."""
+    data = _f32(data)
+    n, d = data.shape
+    cen = _f32(centroids).reshape(-1, d)
+    k = cen.shape[0]
+    pen = None if penalty is None else _f32(penalty).reshape(k)
+    if point_idx is None:
+        pi, pip, m = None, None, n
+    else:
+        pi = _u64(point_idx)
+        pip, m = _p(pi, C.c_uint64), pi.size
+    best = np.zeros(m, np.uint32)
+    cost = np.zeros(m, np.float32)
+    rc = lib().orc_assign_balanced(_p(data, C.c_float), d, metric, pip, m, _p(cen, C.c_float),
+                                   None if pen is None else _p(pen, C.c_float), k, threads,
+                                   _p(best, C.c_uint32), _p(cost, C.c_float))
+    if rc != 0:
+        raise RuntimeError(f"orc_assign_balanced rc={rc}")
+    order = np.argsort(best, kind="stable")
+    rows = np.arange(m, dtype=np.uint64) if pi is None else pi
+    members = rows[order]
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(best, minlength=k))]).astype(np.uint64)
+    return AssignResult(offsets, members, best, cost)
 
 
 def update_medoids(data, metric, offsets, members, old_rows, want_means=False, threads=0):

@@ -209,6 +209,35 @@ int orc_assign(const float* data, size_t n, size_t d, int metric,
   return 0;
 }
 
+/* EXTENSION (parity unpinned, see spf_oracle.h): balanced assignment */
+typedef struct {
+  const float* data; size_t d; int metric; const uint64_t* point_idx;
+  const float* centroids; const float* penalty; size_t k; uint32_t* best; float* cost;
+} bal_ctx;
+
+static void bal_range(void* p, size_t lo, size_t hi) {
+  bal_ctx* c = (bal_ctx*)p;
+  for (size_t i = lo; i < hi; ++i) {
+    size_t row = c->point_idx ? (size_t)c->point_idx[i] : i;
+    uint32_t bj = 0; float bd = INFINITY;
+    for (size_t j = 0; j < c->k; ++j) {
+      float dd = orc_distance_f32(c->metric, c->data + row * c->d, c->centroids + j * c->d, c->d);
+      float cc = c->penalty ? dd + c->penalty[j] : dd;      /* one f32 add (-ffp-contract=off) */
+      if (cc < bd) { bd = cc; bj = (uint32_t)j; }
+    }
+    c->best[i] = bj; c->cost[i] = bd;
+  }
+}
+
+int orc_assign_balanced(const float* data, size_t d, int metric, const uint64_t* point_idx, size_t m,
+                        const float* centroids, const float* penalty, size_t k, int threads,
+                        uint32_t* best, float* cost) {
+  if (k == 0) return -2;
+  bal_ctx c = { data, d, metric, point_idx, centroids, penalty, k, best, cost };
+  parallel_for(m, threads, 64, bal_range, &c);
+  return 0;
+}
+
 void orc_assign_free(orc_assign_t* a) {
   if (!a) return;
   free(a->offsets); free(a->members); free(a->best); free(a->dmin);

@@ -140,6 +140,17 @@ void orc_free(void* p);
 
 int orc_online_cpus(void);
 
+/* EXTENSION (north_star: "the size-balancing penalty is applied in the same pass"; the reference has
+ * no counterpart — its fit() is one assign + one update, hierarchical.rs:65-71 — so this part of
+ * the oracle is a specification written here, PARITY UNPINNED): balanced assignment against k
+ * explicit centroid vectors.  cost(x, j) = fl(d(x, c_j) + penalty[j]) with d the reference metric
+ * (distance.rs:16-43, sequential f32) and one f32 add; best = argmin cost by the reference's fold
+ * (strict <, identity (0, +inf): lowest slot on ties, :317-326); every point belongs to exactly its
+ * best cluster (no boundary replication).  penalty == NULL means all zeros. */
+int orc_assign_balanced(const float* data, size_t d, int metric, const uint64_t* point_idx, size_t m,
+                        const float* centroids, const float* penalty, size_t k, int threads,
+                        uint32_t* best, float* cost);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ SIGNATURES = {
     "spf_kmeans_step": (C.c_int, [_vp]),
     "spf_kmeans_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "spf_kmeans_assignment": (C.c_void_p, [_vp]),
+    "spf_kmeans_set_balance": (C.c_int, [_vp, C.c_float]),
+    "spf_assign_balanced": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_int, _vpp]),
     "spf_kmeans_free": (None, [_vp]),
     "spf_topk_merge": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

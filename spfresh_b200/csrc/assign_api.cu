@@ -73,6 +73,8 @@ struct AssignCall {
   float factor = 1.0f;
   bool want_members = true, use_tc = false;
   const float* seed = nullptr;   // optional device array (m): upper bounds of the minimum distances
+  const float* penalty = nullptr;   // optional device array (k): balanced assignment, cost = fl(d + penalty[j])
+  uint32_t eld = 0;              // row length entering the certified error bound (ld, + slack with penalties)
   uint64_t m = 0, chunk_rows = 0;
   DevBuf<float> Cg, ctf, cnorm, cres, cstat, cext, cc_own;
   const float* cc = nullptr;     // k x k exact centroid-centroid distances (own buffer or the context's cache)
@@ -118,6 +120,11 @@ int assign_setup(AssignCall& a) {
     SPF_TRY(a.cres.alloc(st, a.k));
     SPF_TRY(a.cstat.alloc(st, 2));
     SPF_TRY(launch_row_prep(c, a.Cg.p, a.ld, nullptr, a.k, a.ctf.p, a.cnorm.p, a.cres.p));
+    // balanced assignment: the penalty rides with |c|^2 in the K extension, s = x.c - (|c|^2 + p)/2, so
+    // the accumulator yields the approximate COST |x|^2 - 2 s.  The two extra roundings (|c|^2 + p,
+    // d + p) are covered by 8 more units of row length in the error bound.
+    a.eld = a.ld + (a.penalty ? 8u : 0u);
+    if (a.penalty) SPF_TRY(launch_add_f32(c, a.cnorm.p, a.penalty, a.k));
     SPF_TRY(launch_max2_f32(c, a.cnorm.p, a.cres.p, a.k, a.cstat.p));
     SPF_TRY(a.cext.alloc(st, (size_t)kpad * 8));
     SPF_TRY(launch_centroid_ext(c, a.cnorm.p, a.k, kpad, a.cext.p));
@@ -174,6 +181,8 @@ ResolveArgs resolve_args(const AssignCall& a, const float* P, uint64_t m, const 
   r.metric = a.metric; r.P = P; r.m = m; r.C = a.Cg.p; r.k = a.k; r.ld = a.ld; r.factor = a.factor;
   r.cand = a.cand; r.nseg = a.use_tc ? 2 : 1;
   r.seed = (a.use_tc && a.seed) ? a.seed + r0 : nullptr;
+  r.penalty = a.penalty;
+  r.eld = a.eld;
   r.xnorm = a.use_tc ? xnorm : nullptr; r.xres = a.use_tc ? xres : nullptr;
   r.d_cstat = a.use_tc ? a.cstat.p : nullptr;
   r.cc = a.cc; r.want_members = a.want_members;
@@ -188,10 +197,10 @@ int assign_rows(AssignCall& a, const float* P, const float* Ptf, const float* xn
   if (a.use_tc) {
     KernelTimer t(c, "assign_tc");
     SPF_TRY(launch_assign_tc(c, Ptf, mc, a.ctf.p, a.k, a.ld, xnorm, xres, a.cext.p, a.cstat.p,
-                             a.seed ? a.seed + r0 : nullptr, a.factor, a.cand));
+                             a.seed ? a.seed + r0 : nullptr, a.factor, a.cand, a.eld));
   } else {
     KernelTimer t(c, "assign_exact");
-    SPF_TRY(launch_assign_exact(c, a.metric, P, mc, a.Cg.p, a.k, a.ld, a.factor, &a.cand, nullptr));
+    SPF_TRY(launch_assign_exact(c, a.metric, P, mc, a.Cg.p, a.k, a.ld, a.factor, &a.cand, nullptr, nullptr, a.penalty));
   }
   return resolve_chunk(c, a.rs, resolve_args(a, P, mc, xnorm, xres, r0), r0);
 }
@@ -240,7 +249,7 @@ int assign_finish(AssignCall& a, const float* P_all, const float* xnorm_all, con
 // m per-point upper bounds of the minimum distance.  The caller holds the context lock.
 static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m,
                            const uint64_t* centroid_rows, const float* centroid_vecs, const float* centroid_dev,
-                           uint32_t k, float boundary_factor, int flags, const float* d_seed,
+                           uint32_t k, float boundary_factor, int flags, const float* d_seed, const float* d_penalty,
                            spf_assign_result** out) {
   if (!ds || !out || (!centroid_rows && !centroid_vecs && !centroid_dev))
     return fail(SPF_E_INVALID, "spf_assign: NULL argument");
@@ -283,6 +292,8 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
              assign_tc_supported(c, m, k, ld);
   a.chunk_rows = pick_chunk_rows(c, m, false, effective_cand_cap(c, a.use_tc, ld));
   a.seed = a.use_tc ? d_seed : nullptr;
+  a.penalty = d_penalty;
+  if (d_penalty) a.factor = 1.0f;             // balanced assignment: exactly one cluster per point
 
   // dense operands: centroids always materialised; points gathered only for a subset
   SPF_TRY(a.Cg.alloc(st, (size_t)k * ld));
@@ -326,9 +337,10 @@ static int assign_resident(spf_dataset* ds, int metric, const uint64_t* point_id
 }
 
 int spf::assign_device_centroids(spf_dataset* ds, int metric, const float* d_centroids, uint32_t k,
-                                 float boundary_factor, int flags, const float* d_seed, spf_assign_result** out) {
+                                 float boundary_factor, int flags, const float* d_seed, const float* d_penalty,
+                                 spf_assign_result** out) {
   return assign_resident(ds, metric, nullptr, ds ? ds->n : 0, nullptr, nullptr, d_centroids, k, boundary_factor, flags,
-                         d_seed, out);
+                         d_seed, d_penalty, out);
 }
 
 extern "C" {
@@ -340,7 +352,7 @@ int spf_assign(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t 
   if (!ds || !centroid_rows) return fail(SPF_E_INVALID, "spf_assign: NULL argument");
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
   ds->ctx->kernel_ms.clear();
-  return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, nullptr, k, boundary_factor, flags, nullptr, out);
+  return assign_resident(ds, metric, point_idx, m, centroid_rows, nullptr, nullptr, k, boundary_factor, flags, nullptr, nullptr, out);
   });
 }
 
@@ -351,7 +363,31 @@ int spf_assign_vectors(spf_dataset* ds, int metric, const uint64_t* point_idx, u
   if (!ds || !centroids) return fail(SPF_E_INVALID, "spf_assign_vectors: NULL argument");
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
   ds->ctx->kernel_ms.clear();
-  return assign_resident(ds, metric, point_idx, m, nullptr, centroids, nullptr, k, boundary_factor, flags, nullptr, out);
+  return assign_resident(ds, metric, point_idx, m, nullptr, centroids, nullptr, k, boundary_factor, flags, nullptr, nullptr, out);
+  });
+}
+
+int spf_assign_balanced(spf_dataset* ds, int metric, const uint64_t* point_idx, uint64_t m, const float* centroids,
+                        const float* penalty, uint32_t k, int flags, spf_assign_result** out) {
+  return spf::guarded([&]() -> int {
+    if (!ds || !centroids || !out) return fail(SPF_E_INVALID, "spf_assign_balanced: NULL argument");
+    if (k == 0) return fail(SPF_E_INVALID, "k must be > 0");
+    spf_ctx* c = ds->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->kernel_ms.clear();
+    SPF_CUDA(cudaSetDevice(c->device));
+    DevBuf<float> d_pen;
+    SPF_TRY(d_pen.alloc(c->stream, k));
+    if (penalty) {
+      for (uint32_t j = 0; j < k; ++j)
+        if (!(penalty[j] >= 0.0f)) return fail(SPF_E_INVALID, "penalty[%u] must be a non-negative number", j);
+      SPF_CUDA(cudaMemcpyAsync(d_pen.p, penalty, (size_t)k * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      SPF_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+      SPF_CUDA(cudaMemsetAsync(d_pen.p, 0, (size_t)k * sizeof(float), c->stream));
+    }
+    return assign_resident(ds, metric, point_idx, m, nullptr, centroids, nullptr, k, 1.0f, flags & ~SPF_ASSIGN_NO_CSR, nullptr,
+                           d_pen.p, out);
   });
 }
 

@@ -25,7 +25,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(NTHREADS)
 assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __restrict__ C, uint32_t k,
                     uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
-                    int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip) {
+                    int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip,
+                    const float* __restrict__ penalty) {
   if (skip != nullptr && *skip != 0) return;   // the caller already holds this result (cached centroid matrix)
   __shared__ __align__(16) float Xs[2][BK][BM + PAD];
   __shared__ __align__(16) float Cs[2][BK][BN + PAD];
@@ -120,6 +121,14 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
       }
     }
     if (cand != nullptr) {
+      if (penalty != nullptr) {             // balanced assignment: candidates are formed on the costs
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float pj = (c0 + tx * 4 + j < k) ? penalty[c0 + tx * 4 + j] : 0.0f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i][j] = __fadd_rn(acc[i][j], pj);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float tmin = __int_as_float(0x7f800000);
@@ -162,7 +171,7 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
 }  // namespace
 
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, const CandBuf* cb, float* dense, const int* d_skip) {
+                        uint32_t ld, float factor, const CandBuf* cb, float* dense, const int* d_skip, const float* penalty) {
   // a dense P x P request is the symmetric centroid matrix: half the tiles
   const int symmetric = (cb == nullptr && dense != nullptr && P == C && m == k) ? 1 : 0;
   if (m == 0 || k == 0) return SPF_OK;
@@ -178,15 +187,15 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   switch (metric) {
     case SPF_METRIC_EUCLIDEAN:
       assign_exact_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
       break;
     case SPF_METRIC_MANHATTAN:
       assign_exact_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
       break;
     case SPF_METRIC_CHEBYSHEV:
       assign_exact_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
       break;
     default:
       return fail(SPF_E_INVALID, "unknown metric %d", metric);

@@ -69,6 +69,7 @@ constexpr int SMEM_TOTAL = SMEM_PUB_OFF + 2 * BM * 8 + 1024; // + alignment slac
 
 struct TcArgs {
   uint32_t m, k, ld, kb;            // kb = ceil(ld / 32) K blocks
+  uint32_t eld;                     // row length entering the certified error bound
   uint32_t ntiles;                  // ceil(k / 256)
   uint32_t nrowblocks;              // ceil(m / 128)
   float factor;
@@ -224,7 +225,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t row = rb * BM + lrow;
       const bool row_ok = row < a.m;
       const float xn = row_ok ? a.xnorm[row] : 0.0f;
-      const float E = tc_err_bound(xn, row_ok ? a.xres[row] : 0.0f, cnmax, dcmax, a.ld);
+      const float E = tc_err_bound(xn, row_ok ? a.xres[row] : 0.0f, cnmax, dcmax, a.eld);
       // non-finite norms or bounds: no certified test exists, the brute-force kernels own the row
       const bool hopeless = !(E < INF) || !(xn < INF);
       // candidate test  d < f (dmin_run + E) + E  with d = |x|^2 - 2 s, dmin_run = |x|^2 - 2 smax:
@@ -375,7 +376,7 @@ bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld) 
 
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
-                     const float* seed, float factor, const CandBuf& cand) {
+                     const float* seed, float factor, const CandBuf& cand, uint32_t eld) {
   CUtensorMap map_a, map_b, map_e;
   SPF_TRY(make_map_k128(c, &map_a, Ptf, m, ld, BM));
   SPF_TRY(make_map_k128(c, &map_b, Ctf, k, ld, BN / 2));   // each CTA of a pair fetches half a tile
@@ -383,6 +384,7 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
   SPF_TRY(make_map_ext(c, &map_e, cext_pad, (uint64_t)((k + BN - 1) / BN) * BN, BN));
   TcArgs a;
   a.m = (uint32_t)m; a.k = k; a.ld = ld; a.kb = (ld + BK - 1) / BK;
+  a.eld = eld ? eld : ld;
   a.ntiles = (k + BN - 1) / BN;
   a.nrowblocks = (uint32_t)(ceil_div(m, 2 * BM) * 2);   // even: the CTAs of a pair walk the tiles in lockstep
   a.factor = factor;

@@ -77,6 +77,8 @@ int launch_gather_rows(spf_ctx* c, const float* src, uint32_t ld, const uint64_t
                        float* dst);
 int launch_row_sqnorm(spf_ctx* c, const float* rows, uint32_t ld, uint64_t m, float* out);
 int launch_fill_f32(spf_ctx* c, float* p, uint64_t n, float v);
+int launch_add_f32(spf_ctx* c, float* dst, const float* src, uint64_t n);          // dst[i] = fl(dst[i] + src[i])
+int launch_scale_u64_f32(spf_ctx* c, const uint64_t* src, float scale, uint64_t n, float* dst);   // dst[i] = fl(scale * (float)src[i])
 int launch_fill_u64(spf_ctx* c, uint64_t* p, uint64_t n, uint64_t v);
 int launch_max_f32(spf_ctx* c, const float* p, uint64_t n, float* out1);   // out1[0] = max
 // dist[i] = metric(A row ai, B row bi): ai = idxA ? idxA[i] : i ;
@@ -92,8 +94,10 @@ int launch_check_rows(spf_ctx* c, const uint64_t* d_idx, uint64_t m, uint64_t n,
 // CUDA-core direct-form kernel: every distance of the m x k problem, exact.  Emits boundary
 // candidates (cand != NULL, one segment, all records exact) and/or the dense m x k matrix.
 // d_skip (optional device flag): when it is non-zero at run time the kernel does nothing.
+// penalty (optional, k floats, candidate mode only): candidates are formed on fl(d + penalty[j]).
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, const CandBuf* cand, float* dense, const int* d_skip = nullptr);
+                        uint32_t ld, float factor, const CandBuf* cand, float* dense, const int* d_skip = nullptr,
+                        const float* penalty = nullptr);
 
 // ---- assign_tc.cu -------------------------------------------------------------------------
 // tcgen05 (TF32) candidate GEMM for squared-Euclidean: approximate distances with a certified
@@ -104,7 +108,7 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
 bool assign_tc_supported(const spf_ctx* c, uint64_t m, uint32_t k, uint32_t ld);
 int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf, uint32_t k, uint32_t ld,
                      const float* xnorm, const float* xres, const float* cext_pad, const float* d_cstat,
-                     const float* seed, float factor, const CandBuf& cand);
+                     const float* seed, float factor, const CandBuf& cand, uint32_t eld = 0);
 // K-extension rows for the tensor kernel: row j < k = {h, m, 0, 0, l, 0, 0, 0} with h + m + l =
 // -|c_j|^2 / 2 split into three TF32 values (residual < 2^-33 |c_j|^2); rows k .. kpad-1 = {-inf, 0, ...}.
 int launch_centroid_ext(spf_ctx* c, const float* cnorm, uint32_t k, uint32_t kpad, float* cext);
@@ -117,6 +121,8 @@ struct ResolveArgs {
   CandBuf cand;
   int nseg;                // segments per point: 1 (exact kernel) or 2 (tensor kernel)
   const float* seed;       // tensor path, optional: the seeds the candidate kernel used (validated here)
+  const float* penalty = nullptr;   // balanced assignment (extension): k per-centroid penalties added to every exact distance
+  uint32_t eld = 0;        // row length entering the certified error bound (0: ld)
   const float* xnorm;      // NULL on the exact path (error bound 0)
   const float* xres;       // tensor path only
   const float* d_cstat;    // device {max |c|^2, max |c - c'|}, tensor path only
@@ -206,7 +212,7 @@ int launch_medoid_keys(spf_ctx* c, int metric, const float* X, uint32_t ld, cons
 // spf_assign_vectors with the k centroid vectors already on the device (k x ld, rows zero padded to
 // ld); the caller holds the context lock.
 int assign_device_centroids(spf_dataset* ds, int metric, const float* d_centroids, uint32_t k, float boundary_factor,
-                            int flags, const float* d_seed, spf_assign_result** out);
+                            int flags, const float* d_seed, const float* d_penalty, spf_assign_result** out);
 int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out);   // api.cu: device buffer only
 int dataset_prep_alloc(spf_dataset* ds);
 int dataset_prep(spf_dataset* ds);   // rounded copy + norms of all rows, once per dataset

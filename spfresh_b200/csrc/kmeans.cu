@@ -16,6 +16,18 @@
 // From the second iteration on the assignment is seeded: d(x, c_new[best_old(x)]) is an exact
 // distance to one of the new centroids, i.e. a certified upper bound of the new minimum distance,
 // which lets the tcgen05 candidate pass emit ~3x fewer candidates (assign_tc.cu).
+//
+// EXTENSION (north_star: "the centroid update is a fused segmented-sum/count kernel, and the
+// size-balancing penalty is applied in the same pass"; the reference's fit() is a single assign +
+// update, hierarchical.rs:65-71, so there is no reference behaviour to match — the oracle's
+// orc_assign_balanced is the specification, PARITY UNPINNED):
+//   SPF_KMEANS_BALANCED  assignment by cost(x, j) = fl(d(x, c_j) + lambda * n_j), n_j the global size
+//                        of cluster j after the previous iteration (0 in the first); every point
+//                        belongs to exactly its best cluster.  On the tensor path the penalty rides
+//                        in the K extension of the GEMM next to |c|^2, so the candidate pass ranks by
+//                        cost at no extra work; exact costs add the penalty with one f32 add.
+//   SPF_KMEANS_MEANS     Lloyd iterations: the new centroid is the mean itself instead of the member
+//                        nearest to it (no medoid pass, no C2 exchange).
 #include "comm.cuh"
 #include "kernels.cuh"
 
@@ -32,7 +44,8 @@ struct spf_kmeans {
   bool have_centroids = false;
   uint64_t iterations = 0;
   spf_assign_result* last = nullptr;
-  DevBuf<float> cvec, means, seed;
+  float lambda = 0.0f;          // balanced mode: penalty[j] = lambda * (float)(members of cluster j after the last iteration)
+  DevBuf<float> cvec, means, seed, penalty;
   DevBuf<uint64_t> crow, gcount;
   DevBuf<uint8_t> msg1, gath1, msg2, gath2;
   size_t msg1_bytes = 0, msg2_bytes = 0;
@@ -120,6 +133,14 @@ __global__ void km_select_kernel(const uint8_t* __restrict__ gath, size_t stride
   for (uint32_t i = threadIdx.x; i < ld; i += blockDim.x) cvec[(size_t)c * ld + i] = src[i];
 }
 
+__global__ void km_take_means_kernel(const float* __restrict__ means, uint32_t ld, const uint64_t* __restrict__ gcount,
+                                     uint64_t* __restrict__ crow, float* __restrict__ cvec) {
+  const uint32_t c = blockIdx.x;
+  if (gcount[c] == 0) return;                                   // empty cluster keeps its centroid
+  if (threadIdx.x == 0) crow[c] = ~0ull;                        // the centroid is no dataset row any more
+  for (uint32_t i = threadIdx.x; i < ld; i += blockDim.x) cvec[(size_t)c * ld + i] = means[(size_t)c * ld + i];
+}
+
 int km_update(spf_kmeans* s) {
   spf_dataset* ds = s->ds;
   spf_ctx* c = ds->ctx;
@@ -148,6 +169,10 @@ int km_update(spf_kmeans* s) {
     km_reduce_means_kernel<<<(unsigned)ceil_div((uint64_t)k * ld, 256), 256, 0, st>>>(s->gath1.p, s->msg1_bytes, world, k, ld,
                                                                                       s->means.p, s->gcount.p);
     SPF_TRY(check_launch(c, "km_reduce_means_kernel"));
+  }
+  if (s->flags & SPF_KMEANS_MEANS) {           // Lloyd: centroid = mean of the non-empty clusters
+    km_take_means_kernel<<<k, 128, 0, st>>>(s->means.p, ld, s->gcount.p, s->crow.p, s->cvec.p);
+    return check_launch(c, "km_take_means_kernel");
   }
   SPF_TRY(keys.alloc(st, k));
   CandMsg* cand = reinterpret_cast<CandMsg*>(s->msg2.p);
@@ -196,6 +221,7 @@ int spf_kmeans_create(spf_dataset* ds, spf_comm* comm, int metric, uint64_t row0
   if (rc >= 0) rc = s->means.alloc(st, (size_t)k * ld);
   if (rc >= 0) rc = s->crow.alloc(st, k);
   if (rc >= 0) rc = s->gcount.alloc(st, k);
+  if (rc >= 0) rc = s->penalty.alloc(st, k);
   if (rc >= 0) rc = s->msg1.alloc(st, s->msg1_bytes);
   if (rc >= 0) rc = s->gath1.alloc(st, s->msg1_bytes * world);
   if (rc >= 0) rc = s->msg2.alloc(st, s->msg2_bytes);
@@ -235,7 +261,14 @@ int spf_kmeans_step(spf_kmeans* s) {
   cudaStream_t st = c->stream;
   c->kernel_ms.clear();
   const float* seed = nullptr;
-  if (s->last && s->iterations > 0 && !(s->flags & SPF_KMEANS_UNSEEDED) && s->metric == SPF_METRIC_EUCLIDEAN) {
+  const float* penalty = nullptr;
+  if (s->flags & SPF_KMEANS_BALANCED) {
+    if (s->iterations == 0) SPF_CUDA(cudaMemsetAsync(s->penalty.p, 0, (size_t)s->k * sizeof(float), st));
+    else SPF_TRY(launch_scale_u64_f32(c, s->gcount.p, s->lambda, s->k, s->penalty.p));
+    penalty = s->penalty.p;
+  }
+  if (s->last && s->iterations > 0 && !(s->flags & (SPF_KMEANS_UNSEEDED | SPF_KMEANS_BALANCED)) &&
+      s->metric == SPF_METRIC_EUCLIDEAN) {
     // exact distance of every point to the NEW centroid of the slot it was nearest to
     KernelTimer t(c, "kmeans_seed");
     SPF_TRY(s->seed.alloc(st, ds->n));
@@ -244,7 +277,7 @@ int spf_kmeans_step(spf_kmeans* s) {
     seed = s->seed.p;
   }
   spf_assign_result* res = nullptr;
-  SPF_TRY(assign_device_centroids(ds, s->metric, s->cvec.p, s->k, s->factor, 0, seed, &res));
+  SPF_TRY(assign_device_centroids(ds, s->metric, s->cvec.p, s->k, s->factor, 0, seed, penalty, &res));
   if (s->last) spf_assign_free(s->last);
   s->last = res;
   SPF_TRY(km_update(s));
@@ -270,6 +303,14 @@ int spf_kmeans_fetch(spf_kmeans* s, uint64_t* rows, float* vectors, float* means
   SPF_CUDA(cudaStreamSynchronize(st));
   return SPF_OK;
   });
+}
+
+int spf_kmeans_set_balance(spf_kmeans* s, float lambda) {
+  if (!s) return fail(SPF_E_INVALID, "spf_kmeans_set_balance: NULL argument");
+  if (!(lambda >= 0.0f)) return fail(SPF_E_INVALID, "lambda must be a non-negative number");
+  if (!(s->flags & SPF_KMEANS_BALANCED)) return fail(SPF_E_STATE, "the session was not created with SPF_KMEANS_BALANCED");
+  s->lambda = lambda;
+  return SPF_OK;
 }
 
 const spf_assign_result* spf_kmeans_assignment(const spf_kmeans* s) { return s ? s->last : nullptr; }

@@ -66,6 +66,8 @@ struct ResolveDev {
   CandRec* rec; const RowInfo* info; int cap; int nseg;
   const float* xnorm; const float* xres; const float* cstat; const float* cc;
   const float* seed;
+  const float* penalty;    // balanced assignment (extension): cost = fl(d + penalty[j]); NULL otherwise
+  uint32_t eld;            // row length entering the certified error bound (ld, plus slack in balanced mode)
   uint32_t* best; float* dmin; uint32_t* nmem;
   uint32_t* ovf_rows; uint32_t* ovf_count;
   int want_members;
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
     bool overflow = cnt0 > segcap || cnt1 > segcap;   // the dense fallback owns such rows
     uint32_t steps = overflow ? 0u : (max(cnt0, cnt1) + 31u) >> 5;
     const CandRec* cr = a.rec + (size_t)r * a.cap;
-    const float E = approx ? tc_err_bound(xn, xr, cnmax, dcmax, a.ld) : 0.0f;
+    const float E = approx ? tc_err_bound(xn, xr, cnmax, dcmax, a.eld) : 0.0f;
     // a seeded candidate pass is only valid when the observed maximum reaches the seed's bound
     if (approx && a.seed != nullptr) {
       const float sd = a.seed[r];
@@ -409,6 +411,7 @@ __device__ __forceinline__ void eval_queue(const ResolveDev& a, EvalSmem& sm, ui
   }
   if ((uint32_t)lane < np) {
     ShortEnt* w = a.sl + sm.qd[lane];
+    if (a.penalty) acc = __fadd_rn(acc, a.penalty[sm.qj[lane] & 0x3fffffffu]);
     w->v = acc;
     w->flags = ((sm.qj[lane] >> 30) << 2) | SE_EXACT;
   }
@@ -485,6 +488,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
       en[u] = cur.en[u];
       if (e < n && (en[u].flags & SE_NEED_EVAL)) {   // did not fit the work list (rare): recompute here
         en[u].v = thread_dist<METRIC>(a.P + (size_t)r * a.ld, a.C + (size_t)en[u].j * a.ld, a.ld);
+        if (a.penalty) en[u].v = __fadd_rn(en[u].v, a.penalty[en[u].j]);
         en[u].flags = (en[u].flags & ~SE_NEED_EVAL) | SE_EXACT;
       }
       if (e < n && (en[u].flags & SE_KIND_MASK) == SE_BAND && lex_less(en[u].v, en[u].j, bd, bj)) { bd = en[u].v; bj = en[u].j; }
@@ -533,11 +537,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
           if (ex) {
             mem = cc >= dv;
           } else {
-            if (E == 0.0f && approx) E = tc_err_bound(a.xnorm[r], a.xres[r], a.cstat[0], a.cstat[1], a.ld);
+            if (E == 0.0f && approx) E = tc_err_bound(a.xnorm[r], a.xres[r], a.cstat[0], a.cstat[1], a.eld);
             const float lo = __fadd_rd(dv, -E), hi = __fadd_ru(dv, E);
             if (cc >= hi) mem = true;
             else if (cc >= lo) {                     // undecidable on the interval: recompute (rare)
               dv = thread_dist<METRIC>(x, a.C + (size_t)j * a.ld, a.ld);
+              if (a.penalty) dv = __fadd_rn(dv, a.penalty[j]);
               mem = dv < thr && cc >= dv;
             }
           }
@@ -589,7 +594,7 @@ overflow_rows_kernel(ResolveDev a, const float* __restrict__ dense, const uint32
     uint32_t bj = 0xffffffffu;
     if (PHASE == 0) {
       for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) {
-        const float dv = drow[j];
+        const float dv = a.penalty ? __fadd_rn(drow[j], a.penalty[j]) : drow[j];
         if (lex_less(dv, j, bd, bj)) { bd = dv; bj = j; }
       }
 #pragma unroll
@@ -617,7 +622,7 @@ overflow_rows_kernel(ResolveDev a, const float* __restrict__ dense, const uint32
     for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) {
       bool member = (j == bj);
       if (!member && a.want_members) {
-        const float dv = drow[j];
+        const float dv = a.penalty ? __fadd_rn(drow[j], a.penalty[j]) : drow[j];
         if (dv < thr) {
           const float cc = a.cc ? a.cc[(size_t)bj * a.k + j]
                                 : thread_dist<METRIC>(cb, a.C + (size_t)j * a.ld, a.ld);
@@ -722,7 +727,8 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   SPF_CUDA(cudaMemsetAsync(s->work_count.p, 0, sizeof(uint32_t), st));
   SPF_CUDA(cudaMemsetAsync(a.nmem, 0, a.m * sizeof(uint32_t), st));
   ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, a.cand.rec, a.cand.info, a.cand.cap, a.nseg,
-               a.xnorm, a.xres, a.d_cstat, a.cc, a.seed, a.best, a.dmin, a.nmem, s->ovf_rows.p, s->ovf_count.p,
+               a.xnorm, a.xres, a.d_cstat, a.cc, a.seed, a.penalty, a.eld ? a.eld : a.ld, a.best, a.dmin, a.nmem, s->ovf_rows.p,
+               s->ovf_count.p,
                a.want_members ? 1 : 0, s->sl.p, s->sl_cnt.p, s->sl_shift,
                a.want_members ? s->memlist.p + ((size_t)r0 << s->sl_shift) : nullptr,
                s->work.p, s->work_count.p, s->work_cap, (uint32_t)r0};
@@ -762,7 +768,8 @@ template <int METRIC>
 int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* csr) {
   cudaStream_t st = c->stream;
   ResolveDev d{a.P, (uint32_t)a.m, a.C, a.k, a.ld, a.factor, nullptr, nullptr, 0, 1,
-               a.xnorm, a.xres, a.d_cstat, a.cc, nullptr, a.best, a.dmin, a.nmem, s->ovf_rows.p, s->ovf_count.p,
+               a.xnorm, a.xres, a.d_cstat, a.cc, nullptr, a.penalty, a.eld ? a.eld : a.ld, a.best, a.dmin, a.nmem, s->ovf_rows.p,
+               s->ovf_count.p,
                a.want_members ? 1 : 0, s->sl.p, s->sl_cnt.p, s->sl_shift, s->memlist.p, s->work.p,
                s->work_count.p, s->work_cap, 0u};
   uint32_t n_ovf = 0;

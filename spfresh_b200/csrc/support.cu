@@ -215,6 +215,28 @@ int launch_fill_f32(spf_ctx* c, float* p, uint64_t n, float v) {
   return check_launch(c, "fill_f32_kernel");
 }
 
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __fadd_rn(dst[i], src[i]);
+}
+
+__global__ void scale_u64_f32_kernel(const uint64_t* __restrict__ src, float scale, uint64_t n, float* __restrict__ dst) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __fmul_rn(scale, __ull2float_rn(src[i]));
+}
+
+int launch_add_f32(spf_ctx* c, float* dst, const float* src, uint64_t n) {
+  if (n == 0) return SPF_OK;
+  add_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(dst, src, n);
+  return check_launch(c, "add_f32_kernel");
+}
+
+int launch_scale_u64_f32(spf_ctx* c, const uint64_t* src, float scale, uint64_t n, float* dst) {
+  if (n == 0) return SPF_OK;
+  scale_u64_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(src, scale, n, dst);
+  return check_launch(c, "scale_u64_f32_kernel");
+}
+
 int launch_fill_u64(spf_ctx* c, uint64_t* p, uint64_t n, uint64_t v) {
   if (n == 0) return SPF_OK;
   fill_u64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(p, n, v);

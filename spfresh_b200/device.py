@@ -181,6 +181,20 @@ class Dataset:
                                        C.byref(h)))
         return AssignResult(self, h)
 
+    def assign_balanced(self, metric: int, centroids, penalty=None, point_idx=None) -> "AssignResult":
+        """spf_assign_balanced (extension, no reference counterpart): argmin_j fl(d(x, c_j) + penalty[j]),
+        one cluster per point."""
+        cv = as_f32(centroids).reshape(-1, self.d)
+        pen = None if penalty is None else as_f32(penalty).reshape(cv.shape[0])
+        if point_idx is None:
+            pi, m = None, self.n
+        else:
+            pi = as_u64(point_idx)
+            m = pi.size
+        h = C.c_void_p()
+        check(lib().spf_assign_balanced(self._h, metric, ptr(pi), m, ptr(cv), ptr(pen), cv.shape[0], 0, C.byref(h)))
+        return AssignResult(self, h)
+
     def cluster_sums(self, result: "AssignResult"):
         sums = np.zeros((result.k, self.d), np.float32)
         counts = np.zeros(result.k, np.uint64)
@@ -519,12 +533,16 @@ class KMeansSession:
     hierarchical.rs:368-390, 138-181).  `comm` None = one GPU."""
 
     def __init__(self, ds: Dataset, comm: DeviceComm | None, metric: int, row0: int, k: int,
-                 boundary_factor: float = 1.1, seeded: bool = True):
+                 boundary_factor: float = 1.1, seeded: bool = True, balance_lambda: float | None = None,
+                 lloyd_means: bool = False):
         self.ds, self.comm, self.k = ds, comm, int(k)
+        flags = (0 if seeded else 1) | (2 if balance_lambda is not None else 0) | (4 if lloyd_means else 0)
         h = C.c_void_p()
         check(lib().spf_kmeans_create(ds.handle, comm.handle if comm is not None else None, metric, int(row0), self.k,
-                                      boundary_factor, 0 if seeded else 1, C.byref(h)))
+                                      boundary_factor, flags, C.byref(h)))
         self._h = h
+        if balance_lambda is not None:
+            check(lib().spf_kmeans_set_balance(self._h, float(balance_lambda)))
 
     def set_centroids(self, global_rows, vectors):
         rows = as_u64(global_rows)

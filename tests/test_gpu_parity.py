@@ -1186,3 +1186,72 @@ def test_search_sharded_single_rank_equals_search_batch(spf, ctx, oracle):
         assert np.array_equal(a[0][i, :rc[i]], rid[i, :rc[i]])
     idx.free()
     ds.free()
+
+
+# ----------------------------------------------------------------------------------------------
+# EXTENSION: balanced assignment / Lloyd iterations (no reference counterpart; the oracle's
+# orc_assign_balanced is the specification — parity unpinned)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,n,d,k", [(0, 20000, 128, 512), (0, 6000, 96, 64), (0, 900, 10, 7), (1, 3000, 24, 40),
+                                          (2, 3000, 24, 40)])
+def test_assign_balanced_matches_oracle(spf, ctx, oracle, metric, n, d, k):
+    """cost = fl(d + penalty[j]): nearest slot, cost bits and the one-cluster-per-point CSR equal the
+    oracle extension — tensor path (penalty folded into the K extension of the GEMM) and CUDA-core
+    path, explicit centroid vectors that are no dataset rows, zero and large penalties, a subset."""
+    data = clustered(n, d, max(k // 4, 2), 900 + n + metric)
+    rng = np.random.default_rng(n + k)
+    cen = np.stack([data[rng.choice(n, 5, replace=False)].mean(0) for _ in range(k)]).astype(np.float32)
+    cen[1] = cen[0]                                       # identical centroids: the lower slot wins unless penalised
+    typical = float(np.median(((data[:200, None, :] - cen[None, :8, :]) ** 2).sum(-1))) if metric == 0 else 1.0
+    for pen in (None, (rng.random(k) * 0.2 * typical).astype(np.float32),
+                np.where(np.arange(k) % 3 == 0, np.float32(1e6), np.float32(0)).astype(np.float32)):
+        ds = spf.Dataset(ctx, data)
+        got = ds.assign_balanced(metric, cen, pen).fetch()
+        ref = oracle.assign_balanced(data, metric, cen, pen)
+        check_assign(got, ref)
+        sub = rng.permutation(n)[: n // 4]
+        check_assign(ds.assign_balanced(metric, cen, pen, point_idx=sub).fetch(),
+                     oracle.assign_balanced(data, metric, cen, pen, point_idx=sub))
+        ds.free()
+    with pytest.raises(spf.SpfError):
+        spf.Dataset(ctx, data).assign_balanced(metric, cen, -np.ones(k, np.float32))
+
+
+@pytest.mark.parametrize("metric,lloyd", [(0, False), (0, True), (1, False)])
+def test_kmeans_balanced_session_matches_oracle(spf, ctx, oracle, metric, lloyd):
+    """Iterated balanced k-means on the device == the same loop on the oracle: penalty = lambda * size
+    of the previous iteration, assignment by cost, medoid (or mean, Lloyd mode) update."""
+    n, d, k = (30000, 128, 256) if metric == 0 else (5000, 16, 24)
+    data = clustered(n, d, 16, 700 + metric)              # few true clusters: sizes are very uneven without a penalty
+    rows = np.random.default_rng(5).choice(n, k, replace=False).astype(np.uint64)
+    dm = float(np.median(oracle.assign(data, metric, rows, boundary_factor=1.0).dmin))
+    lam = np.float32(0.5 * dm / (n / k))
+    ds = spf.Dataset(ctx, data)
+    sess = spf.KMeansSession(ds, None, metric, 0, k, balance_lambda=float(lam), lloyd_means=lloyd)
+    sess.set_centroids(rows, data[rows.astype(np.int64)])
+    vec = data[rows.astype(np.int64)].copy()
+    cur_rows = rows.copy()
+    counts = np.zeros(k, np.uint64)
+    spread = []
+    for it in range(3):
+        sess.step()
+        pen = (lam * counts.astype(np.float32)).astype(np.float32)
+        ref = oracle.assign_balanced(data, metric, vec, pen)
+        check_assign(sess.assignment().fetch(), ref)
+        counts = np.diff(ref.offsets.astype(np.int64)).astype(np.uint64)
+        med, means = oracle.update_medoids(data, metric, ref.offsets, ref.members, np.zeros(k, np.uint64), want_means=True)
+        nz = counts > 0
+        if lloyd:
+            vec[nz] = means[nz]
+        else:
+            cur_rows = np.where(nz, med, cur_rows)
+            vec[nz] = data[med[nz].astype(np.int64)]
+        g_rows, g_vec, _, g_cnt = sess.fetch()
+        assert np.array_equal(g_cnt, counts)
+        assert np.array_equal(g_vec.view(np.uint32), vec.view(np.uint32))
+        if not lloyd:
+            assert np.array_equal(g_rows, cur_rows)
+        spread.append(int(counts.max()))
+    assert len(spread) == 3
+    sess.free()
+    ds.free()
