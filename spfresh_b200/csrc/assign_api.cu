@@ -92,14 +92,18 @@ struct AssignCall {
 // tensor path keeps four times as many records per point there unless the knob was set explicitly.
 int effective_cand_cap(const spf_ctx* c, bool use_tc, uint32_t ld) {
   if (c->params.cand_cap == 128 && use_tc && ld > 256) return 512;
+  // tensor path, short rows: 96 records per segment.  With 64, about 0.1 % of the points of the
+  // 1M x 128 N(0,1) benchmark overflow a segment and go through the dense fallback (0.1 ms per step);
+  // the records are written sparsely, so the larger scratch costs address space, not traffic.
+  if (c->params.cand_cap == 128 && use_tc) return 192;
   return c->params.cand_cap;
 }
 
 uint64_t pick_chunk_rows(const spf_ctx* c, uint64_t m, bool streamed, int cand_cap) {
   // multiples of one full wave of the tensor kernel (one 128-point row block per SM)
   uint64_t rows = (uint64_t)c->sm_count * 128 * (streamed ? 4 : 64);
-  // candidate scratch of a chunk stays below ~5 GB
-  while (rows > (uint64_t)c->sm_count * 128 && rows * (uint64_t)cand_cap * sizeof(CandRec) > (5ull << 30)) rows /= 2;
+  // candidate scratch of a chunk stays below ~8 GB
+  while (rows > (uint64_t)c->sm_count * 128 && rows * (uint64_t)cand_cap * sizeof(CandRec) > (8ull << 30)) rows /= 2;
   if (c->params.chunk_rows > 0) rows = (uint64_t)c->params.chunk_rows;
   return rows < m ? rows : m;
 }
