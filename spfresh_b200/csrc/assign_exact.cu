@@ -7,12 +7,20 @@
 // reference.  It is the production path for Manhattan / Chebyshev (FP32-pipe bound: 2 lane
 // instructions per element-op) and the exact fallback / validator for squared-Euclidean.
 //
-// Tiling: CTA = 64 points x 64 centroids, 256 threads, 4x4 register micro-tile per thread,
-// 16-dimension stages double-buffered through shared memory (stored dimension-major so a
-// thread fetches its 4 points / 4 centroids of one dimension with two LDS.128).  A CTA keeps
-// its 64 points and walks all centroid tiles, so the running row minimum and the candidate
-// counters live in shared memory and no global atomics are needed.
-#include "kernels.cuh"
+// Two kernels:
+//  * assign_exact_tma_kernel (Chebyshev by default; any metric through the "exact_tma" knob):
+//    CTA = 128 points x 128 centroids, 8 compute warps + 1 TMA producer warp, 8 x 8 register tile
+//    per thread.  Point and centroid tiles of 16 dimensions (64-byte rows, SWIZZLE_64B) arrive by
+//    cp.async.bulk.tensor into a 4-stage mbarrier ring; a thread reads its 8 points / 8 centroids
+//    of four dimensions with 16 conflict-free LDS.128 and issues 512 metric instructions on them
+//    (3 % load overhead).  The centroid rows are read through a permuted copy (tile row
+//    tx + 16 j <-> slot 8 tx + j), which makes the swizzled loads conflict-free and gives every
+//    thread 8 consecutive slots = two group records.  The row minimum is folded with warp
+//    shuffles over the 16 lanes that share a point and kept in registers across the centroid
+//    tiles; record slots are handed out by ballot.  No shared-memory atomics, no __syncthreads.
+//  * assign_exact_kernel (Manhattan and squared-L2 by default, and tiny problems): CTA = 64 x 64,
+//    4 x 4 register tile, __ldg staging, shared-memory atomics for the row minimum.
+#include "tc_ptx.cuh"
 
 namespace spf {
 
@@ -168,6 +176,227 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged, register-tiled kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int XT_M = 128, XT_N = 128, XT_K = 16;      // points x centroids x dimensions per stage
+constexpr int XT_STAGES = 4;
+constexpr int XT_TILE_BYTES = XT_M * XT_K * 4;        // 8 KB per operand and stage
+constexpr int XT_THREADS = 256;                       // 8 compute warps; thread 0 also issues the TMA loads
+constexpr int XT_SMEM = 2 * XT_STAGES * XT_TILE_BYTES + 256 + 1024;
+
+// slot (within a 128-centroid tile) held by row r of the permuted centroid copy
+__host__ __device__ inline uint32_t xt_slot_of_row(uint32_t r) { return 8u * (r & 15u) + (r >> 4); }
+
+__global__ void xt_permute_rows_kernel(const float4* __restrict__ C, uint32_t ld4, uint32_t k, uint32_t kpad,
+                                       float4* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)kpad * ld4) return;
+  const uint32_t row = (uint32_t)(t / ld4), col = (uint32_t)(t - (uint64_t)row * ld4);
+  const uint32_t slot = (row & ~127u) + xt_slot_of_row(row & 127u);
+  out[t] = slot < k ? C[(size_t)slot * ld4 + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(XT_THREADS, 2)
+assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, uint32_t m,
+                        uint32_t k, uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
+                        int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip,
+                        const float* __restrict__ penalty) {
+  if (skip != nullptr && *skip != 0) return;
+  // (declared with its alignment instead of aligned by pointer arithmetic: the compiler must keep
+  // seeing a shared-memory address, or the operand loads become generic LD instead of LDS)
+  extern __shared__ __align__(1024) unsigned char xt_raw[];
+  unsigned char* smem = xt_raw;
+  unsigned char* xs = smem;                                        // [XT_STAGES][128 rows][64 B]
+  unsigned char* cs = smem + XT_STAGES * XT_TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * XT_STAGES * XT_TILE_BYTES);
+  uint64_t* empty = full + XT_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t row0 = blockIdx.x * XT_M;
+  const uint32_t ntile = (k + XT_N - 1) / XT_N;
+  const uint32_t nkb = (ld + XT_K - 1) / XT_K;
+  if (tid == 0) {
+    for (int i = 0; i < XT_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // The centroid tiles this CTA visits: t = blockIdx.y, + gridDim.y, ...; symmetric mode skips the
+  // tiles strictly below the diagonal (mirrored from above).  Thread 0 is the TMA producer: it keeps
+  // XT_STAGES - 1 stages in flight ahead of the compute loop (cursor pt / pkb), refilling a stage as
+  // soon as all 8 warps have released it.
+  auto next_tile = [&](uint32_t t) {                    // first visited tile >= t
+    while (t < ntile && symmetric && t < blockIdx.x) t += gridDim.y;
+    return t;
+  };
+  uint32_t pt = next_tile(blockIdx.y), pkb = 0, ps = 0, pph = 0;
+  auto produce = [&]() {                                // thread 0 only: one stage, if any is left
+    if (pt >= ntile) return;
+    tc::mbar_wait(&empty[ps], pph ^ 1);
+    tc::mbar_expect_tx(&full[ps], 2 * XT_TILE_BYTES);
+    tc::tma_load_2d(xs + ps * XT_TILE_BYTES, &map_x, &full[ps], (int)(pkb * XT_K), (int)row0);
+    tc::tma_load_2d(cs + ps * XT_TILE_BYTES, &map_c, &full[ps], (int)(pkb * XT_K), (int)(pt * XT_N));
+    if (++ps == XT_STAGES) { ps = 0; pph ^= 1; }
+    if (++pkb == nkb) { pkb = 0; pt = next_tile(pt + gridDim.y); }
+  };
+  if (tid == 0)
+    for (int i = 0; i < XT_STAGES - 1; ++i) produce();
+  // ------------------------------ compute warps ---------------------------------------------------
+  const uint32_t tx = tid & 15, ty = tid >> 4;                     // centroid / point direction
+  const uint32_t half_mask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;   // the 16 lanes that share this thread's points
+  // SWIZZLE_64B: the 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3); rows tx + 16 j (ty + 16 i)
+  // all share (tx >> 1) & 3 ((ty >> 1) & 3)
+  const uint32_t cbase = tx * 64u, cswz = (tx >> 1) & 3u;
+  const uint32_t xbase = ty * 64u, xswz = (ty >> 1) & 3u;
+  const float INF = __int_as_float(0x7f800000);
+  float runmin[8];
+  uint32_t cnt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { runmin[i] = INF; cnt[i] = 0; }
+  uint32_t s = 0, ph = 0;
+  for (uint32_t t = blockIdx.y; t < ntile; t += gridDim.y) {
+    if (symmetric && t < blockIdx.x) continue;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (uint32_t kb = 0; kb < nkb; ++kb) {
+      if (tid == 0) produce();
+      tc::mbar_wait(&full[s], ph);
+      const unsigned char* xb = xs + s * XT_TILE_BYTES;
+      const unsigned char* cb = cs + s * XT_TILE_BYTES;
+      // the four 16-byte chunks of the stage are a real loop (not unrolled): 512 metric steps per
+      // iteration keep the body inside the instruction cache (fully unrolled, 17 % of the stall
+      // samples were instruction fetches)
+#pragma unroll 1
+      for (uint32_t c = 0; c < 4; ++c) {
+        const unsigned char* cp = cb + cbase + ((c ^ cswz) << 4);
+        const unsigned char* xp = xb + xbase + ((c ^ xswz) << 4);
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {                 // 4 centroids at a time: 16 operand registers
+          float4 cv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const float4*>(cp + (jh * 4 + j) * 1024);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xp + i * 1024);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = acc[i][jh * 4 + j];
+              a = dist_step<METRIC>(a, xv.x, cv[j].x);
+              a = dist_step<METRIC>(a, xv.y, cv[j].y);
+              a = dist_step<METRIC>(a, xv.z, cv[j].z);
+              a = dist_step<METRIC>(a, xv.w, cv[j].w);
+              acc[i][jh * 4 + j] = a;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty[s]);
+      if (++s == XT_STAGES) { s = 0; ph ^= 1; }
+    }
+    // ---- epilogue of this 128 x 128 tile: thread (tx, ty) holds points row0 + ty + 16 i and the
+    // consecutive centroid slots c0 .. c0 + 7 ------------------------------------------------------
+    const uint32_t c0 = t * XT_N + 8u * tx;
+    if (dense != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r = row0 + ty + 16u * i;
+        if (r < m) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t cj = c0 + j;
+            if (cj < k) {
+              dense[(size_t)r * k + cj] = acc[i][j];
+              if (symmetric && t > blockIdx.x) dense[(size_t)cj * k + r] = acc[i][j];   // mirror (off-diagonal tiles)
+            }
+          }
+        }
+      }
+    }
+    if (cand != nullptr) {
+      if (penalty != nullptr) {             // balanced assignment: candidates are formed on the costs
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pj = (c0 + j < k) ? penalty[c0 + j] : 0.0f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i][j] = __fadd_rn(acc[i][j], pj);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float tmin = INF;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < k) tmin = fminf(tmin, acc[i][j]);             // fminf skips NaN
+        // minimum over the 16 lanes that hold the other centroids of this point
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        runmin[i] = fminf(runmin[i], tmin);
+        const float rm = runmin[i];
+        const float thr = __fmul_rn(rm, factor);
+        const uint32_t r = row0 + ty + 16u * i;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          bool hit = false;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float dv = acc[i][g * 4 + q];
+            hit = hit || (c0 + g * 4 + q < k && (dv < thr || dv == rm));
+          }
+          hit = hit && r < m;
+          // record slots by ballot over the lanes of this point (one group record for the thread's 4
+          // consecutive centroids; slots >= k are ignored by index in resolve)
+          const unsigned b = __ballot_sync(0xffffffffu, hit) & half_mask;
+          const uint32_t pos = cnt[i] + (uint32_t)__popc(b & ((1u << lane) - 1u));
+          cnt[i] += (uint32_t)__popc(b);
+          if (hit && pos < (uint32_t)cap) {
+            CandRec* w = cand + (size_t)r * cap + pos;
+            w->t = make_float4(acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
+            w->g = ((c0 + g * 4) >> 2) | REC_ALL_EXACT;
+          }
+        }
+      }
+    }
+  }
+  if (cand != nullptr && tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t r = row0 + ty + 16u * i;
+      if (r < m) info[r] = make_uint4(cnt[i], __float_as_uint(runmin[i]), 0u, 0x7f800000u);
+    }
+  }
+}
+
+// 2-D map over a row-major `rows x ld` f32 matrix: boxes of 128 rows x 16 floats, SWIZZLE_64B
+int xt_make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, uint32_t ld) {
+  cuuint64_t gdim[2] = {ld, rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {XT_K, XT_M};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<tc::EncodeTiledFn>(c->tma_encode)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SPF_E_CUDA, "cuTensorMapEncodeTiled (exact kernel) failed with code %d", (int)r);
+  return SPF_OK;
+}
+
+template <int METRIC>
+int launch_xt(spf_ctx* c, const float* P, uint64_t m, const float* Cperm, uint32_t k, uint32_t ld, float factor,
+              CandRec* cand, RowInfo* info, int cap, float* dense, int symmetric, const int* d_skip, const float* penalty,
+              dim3 grid) {
+  CUtensorMap map_x, map_c;
+  SPF_TRY(xt_make_map(c, &map_x, P, m, ld));
+  SPF_TRY(xt_make_map(c, &map_c, Cperm, (uint64_t)round_up(k, XT_N), ld));
+  SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));
+  assign_exact_tma_kernel<METRIC><<<grid, XT_THREADS, XT_SMEM, c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand, info,
+                                                                          cap, dense, symmetric, d_skip, penalty);
+  return check_launch(c, "assign_exact_tma_kernel");
+}
+
 }  // namespace
 
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
@@ -178,6 +407,40 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   CandRec* cand = cb ? cb->rec : nullptr;
   RowInfo* info = cb ? cb->info : nullptr;
   const int cap = cb ? cb->cap : 0;
+  if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
+  // per-metric choice (bit `metric` of the knob), from measurements at d = 128 and d = 960: Chebyshev
+  // splits its two instructions per element over the FMA and the ALU pipe and is issue-bound — the
+  // 8 x 8 register tile lifts it from 0.58 to 0.74-0.81 of the issue peak; Manhattan and squared-L2
+  // put every instruction on the FMA pipe and run faster on the 4 x 4 kernel (0.69 / 0.76 against
+  // 0.60 / 0.68: the larger tile costs register-bank moves and dispatch stalls there)
+  const bool use_tma = c->tma_encode != nullptr && ((c->params.exact_tma >> metric) & 1) != 0 &&
+                       (uint64_t)m * k >= (uint64_t)c->params.exact_tma_min_pairs && (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+  if (use_tma) {
+    // permuted copy of the centroid rows (tile row tx + 16 j <-> slot 8 tx + j), zero rows beyond k
+    const uint32_t kpad = round_up(k, XT_N), ld4 = ld / 4;
+    DevBuf<float> cperm;
+    SPF_TRY(cperm.alloc(c->stream, (size_t)kpad * ld));
+    xt_permute_rows_kernel<<<(unsigned)ceil_div((uint64_t)kpad * ld4, 256), 256, 0, c->stream>>>(
+        reinterpret_cast<const float4*>(C), ld4, k, kpad, reinterpret_cast<float4*>(cperm.p));
+    SPF_TRY(check_launch(c, "xt_permute_rows_kernel"));
+    dim3 grid((unsigned)ceil_div(m, XT_M));
+    if (cand == nullptr) {   // dense matrix only: fill the machine even when m is small
+      const uint64_t ctiles = ceil_div(k, XT_N);
+      uint64_t want = ceil_div((uint64_t)c->sm_count * 2, grid.x);
+      grid.y = (unsigned)(want < 1 ? 1 : (want > ctiles ? ctiles : want));
+    }
+    switch (metric) {
+      case SPF_METRIC_EUCLIDEAN:
+        return launch_xt<SPF_METRIC_EUCLIDEAN>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip,
+                                               cb ? penalty : nullptr, grid);
+      case SPF_METRIC_MANHATTAN:
+        return launch_xt<SPF_METRIC_MANHATTAN>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip,
+                                               cb ? penalty : nullptr, grid);
+      default:
+        return launch_xt<SPF_METRIC_CHEBYSHEV>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip,
+                                               cb ? penalty : nullptr, grid);
+    }
+  }
   dim3 grid((unsigned)ceil_div(m, BM)), block(NTHREADS);
   if (cand == nullptr) {   // dense matrix only: fill the machine even when m is small
     const uint64_t ctiles = ceil_div(k, BN);
@@ -193,12 +456,10 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
       assign_exact_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(
           P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
       break;
-    case SPF_METRIC_CHEBYSHEV:
+    default:
       assign_exact_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(
           P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
       break;
-    default:
-      return fail(SPF_E_INVALID, "unknown metric %d", metric);
   }
   return check_launch(c, "assign_exact_kernel");
 }
