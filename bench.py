@@ -838,7 +838,7 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
     idx.search(q, TOPK)
     scan_ms, probe_ms = ctx.kernel_ms("scan"), ctx.kernel_ms("probe")
     tc = {n: ctx.kernel_ms("scan_tc_" + n) for n in ("a", "gather", "tau", "b", "refine", "fallback", "candidates", "flagged",
-                                                      "units", "stream_mb", "unique_mb")}
+                                                      "units", "stream_mb", "unique_mb", "flag", "groups")}
     ctx.set_profiling(False)
     bytes_ = idx.last_scan_bytes()
     # the same batch on the exact CUDA-core scan (what the tensor-core candidate scan replaces): identical results
@@ -877,9 +877,9 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
                        "peak_source": hbm_src, "bytes_per_launch": int(unique), "requested_bytes_per_launch": int(stream),
                        "traffic": SCAN_TC_DRAM_BYTES_PER_LAUNCH, "traffic_source": SCAN_TC_DRAM_SOURCE,
                        "kernel_ms": tc["a"],
-                       "passes_ms": {"gather": tc["gather"], "bound": tc["a"], "tau": tc["tau"], "group_refine": tc["b"], "select": tc["refine"],
+                       "passes_ms": {"gather": tc["gather"], "bound": tc["a"], "tau": tc["tau"], "group_refine": tc["b"], "group_refine_flagging": tc["flag"], "select": tc["refine"],
                                      "fallback": tc["fallback"]},
-                       "units": int(tc["units"]), "candidates_per_query": tc["candidates"] / NQ,
+                       "units": int(tc["units"]), "subgroups_refined_per_query": tc["groups"] / NQ, "candidates_per_query": tc["candidates"] / NQ,
                        "queries_on_exact_fallback": int(tc["flagged"]),
                        "query_major_algorithmic_gbs": gbs, "query_major_algorithmic_over_hbm": gbs / hbm_peak,
                        "note": "bytes_per_launch = TF32 rows + K-extension rows of every probed list once (algorithmic HBM "

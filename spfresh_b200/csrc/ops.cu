@@ -154,7 +154,10 @@ __global__ void cluster_mean_kernel(const float* __restrict__ X, uint32_t ld4, c
 constexpr int CSB_COLS = 8;            // 128-bit columns per lane: rows up to 32 * 8 * 4 = 1024 floats
 
 // nprod producer warps + one consumer warp; only clusters with min_n <= size < max_n are processed
-// (two launches: a light configuration for the many ordinary clusters, a deep one for the hubs)
+// (two launches: a light configuration for the many ordinary clusters, a deep one for the hubs).
+// blockIdx.y selects a slice of w4 = ld4 / gridDim.y 128-bit columns: the ordered sum is a chain per
+// DIMENSION, so a hub cluster is split over several CTAs by columns (each gathers only its 16 * w4
+// bytes of every member row) without touching the order of the additions.
 __global__ void __launch_bounds__(512)
 cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t* __restrict__ offsets,
                       const uint64_t* __restrict__ rows, float* __restrict__ out, int divide, uint32_t stage_rows,
@@ -162,12 +165,13 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
   extern __shared__ __align__(128) unsigned char csb_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(csb_raw);          // [nstage]
   uint64_t* empty = full + nstage;                                 // [nstage]
-  float4* ring = reinterpret_cast<float4*>(csb_raw + 1024);        // [nstage][stage_rows][ld4]
+  float4* ring = reinterpret_cast<float4*>(csb_raw + 1024);        // [nstage][stage_rows][w4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t c = blockIdx.x;
   const uint64_t b = offsets[c], e = offsets[c + 1];
   const uint64_t n = e - b;
   if (n < min_n || n >= max_n) return;                            // the other launch owns this cluster
+  const uint32_t w4 = ld4 / gridDim.y, col0 = blockIdx.y * w4;
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nstage; ++s) { tc::mbar_init(&full[s], 32); tc::mbar_init(&empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,7 +181,7 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
   // stage index / phase pair is advanced incrementally (64-bit `it % nstage` cost more than the copies)
   const uint32_t n32 = (uint32_t)n;
   const uint32_t nit = (n32 + stage_rows - 1) / stage_rows;
-  const float4* X4 = reinterpret_cast<const float4*>(X);
+  const float4* X4 = reinterpret_cast<const float4*>(X) + col0;
   const uint64_t* crow = rows + b;
   if ((uint32_t)warp < nprod) {
     // ---------------- producers: stage `it` is filled by warp it % nprod; lane l < stage_rows owns row l of
@@ -189,6 +193,8 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
     };
     uint32_t idx0 = load_idx((uint32_t)warp), idx1 = load_idx((uint32_t)warp + nprod), idx2 = load_idx((uint32_t)warp + 2 * nprod);
     uint32_t s = (uint32_t)warp % nstage, ph = ((uint32_t)warp / nstage) & 1u;
+    const bool narrow = w4 < 32 && (w4 & (w4 - 1)) == 0;   // several rows per copy instruction
+    const uint32_t wsh = narrow ? (uint32_t)__ffs((int)w4) - 1u : 0u;
     for (uint32_t it = (uint32_t)warp; it < nit; it += nprod) {
       const uint32_t idx = idx0;
       idx0 = idx1;
@@ -197,12 +203,23 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
       const uint32_t r0 = it * stage_rows;
       const uint32_t cnt = (n32 - r0) < stage_rows ? (n32 - r0) : stage_rows;
       tc::mbar_wait(&empty[s], ph ^ 1);                       // the consumer is done with this stage
-      const uint32_t st = tc::smem_u32(ring + (size_t)s * stage_rows * ld4);
-      for (uint32_t r = 0; r < cnt; ++r) {
-        const uint32_t row = __shfl_sync(0xffffffffu, idx, (int)r);
-        const float4* src = X4 + (size_t)row * ld4;
-        for (uint32_t col = (uint32_t)lane; col < ld4; col += 32)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + (r * ld4 + col) * 16u), "l"(src + col) : "memory");
+      const uint32_t st = tc::smem_u32(ring + (size_t)s * stage_rows * w4);
+      if (narrow) {
+        const uint32_t pieces = cnt << wsh;
+        for (uint32_t p0 = 0; p0 < pieces; p0 += 32) {
+          const uint32_t p = p0 + (uint32_t)lane;
+          const uint32_t r = p >> wsh, col = p & (w4 - 1u);
+          const uint32_t row = __shfl_sync(0xffffffffu, idx, (int)(r & 31u));
+          if (p < pieces)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + p * 16u), "l"(X4 + (size_t)row * ld4 + col) : "memory");
+        }
+      } else {
+        for (uint32_t r = 0; r < cnt; ++r) {
+          const uint32_t row = __shfl_sync(0xffffffffu, idx, (int)r);
+          const float4* src = X4 + (size_t)row * ld4;
+          for (uint32_t col = (uint32_t)lane; col < w4; col += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + (r * w4 + col) * 16u), "l"(src + col) : "memory");
+        }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&full[s])) : "memory");
       s += nprod;
@@ -218,9 +235,9 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
       const uint32_t r0 = it * stage_rows;
       const uint32_t cnt = (n32 - r0) < stage_rows ? (n32 - r0) : stage_rows;
       tc::mbar_wait(&full[s], ph);
-      const float4* st = ring + (size_t)s * stage_rows * ld4 + lane;
-      if (ld4 <= 32) {                                         // one column per lane: groups of 8 rows, loads first
-        if ((uint32_t)lane < ld4) {
+      const float4* st = ring + (size_t)s * stage_rows * w4 + lane;
+      if (w4 <= 32) {                                          // one column per lane: groups of 8 rows, loads first
+        if ((uint32_t)lane < w4) {
           // software pipeline over groups of 8 rows, two register sets in ping-pong: the next group's
           // LDS.128 are in flight while the current group's four FADD chains run
           uint32_t r = 0;
@@ -228,14 +245,14 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
           bool have_v = false;
           if (cnt >= 8) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = st[u * ld4];
+            for (int u = 0; u < 8; ++u) v[u] = st[u * w4];
             have_v = true;
           }
           while (have_v) {
             const bool have_w = r + 16 <= cnt;
             if (have_w) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) w[u] = st[(r + 8 + u) * ld4];
+              for (int u = 0; u < 8; ++u) w[u] = st[(r + 8 + u) * w4];
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -247,7 +264,7 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
             have_v = r + 16 <= cnt;
             if (have_v) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] = st[(r + 8 + u) * ld4];
+              for (int u = 0; u < 8; ++u) v[u] = st[(r + 8 + u) * w4];
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -257,7 +274,7 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
             r += 8;
           }
           for (; r < cnt; ++r) {
-            const float4 t = st[r * ld4];
+            const float4 t = st[r * w4];
             acc[0].x = __fadd_rn(acc[0].x, t.x); acc[0].y = __fadd_rn(acc[0].y, t.y);
             acc[0].z = __fadd_rn(acc[0].z, t.z); acc[0].w = __fadd_rn(acc[0].w, t.w);
           }
@@ -266,8 +283,8 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
         for (uint32_t r = 0; r < cnt; ++r) {
 #pragma unroll
           for (int j = 0; j < CSB_COLS; ++j) {
-            if ((uint32_t)lane + 32u * j < ld4) {
-              const float4 v = st[r * ld4 + 32u * j];
+            if ((uint32_t)lane + 32u * j < w4) {
+              const float4 v = st[r * w4 + 32u * j];
               acc[j].x = __fadd_rn(acc[j].x, v.x); acc[j].y = __fadd_rn(acc[j].y, v.y);
               acc[j].z = __fadd_rn(acc[j].z, v.z); acc[j].w = __fadd_rn(acc[j].w, v.w);
             }
@@ -281,13 +298,13 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
 #pragma unroll
     for (int j = 0; j < CSB_COLS; ++j) {
       const uint32_t col = (uint32_t)lane + 32u * j;
-      if (col < ld4) {
+      if (col < w4) {
         float4 a4 = acc[j];
         if (divide && n > 0) {
           const float fm = (float)n;
           a4.x = __fdiv_rn(a4.x, fm); a4.y = __fdiv_rn(a4.y, fm); a4.z = __fdiv_rn(a4.z, fm); a4.w = __fdiv_rn(a4.w, fm);
         }
-        reinterpret_cast<float4*>(out)[(size_t)c * ld4 + col] = a4;
+        reinterpret_cast<float4*>(out)[(size_t)c * ld4 + col0 + col] = a4;
       }
     }
   }
@@ -301,17 +318,23 @@ int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t*
   const uint32_t ld4 = ld / 4;
   if (ld4 <= 32 * CSB_COLS) {
     SPF_CUDA(cudaFuncSetAttribute(cluster_sum_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
-    const uint64_t hub = 8192;          // clusters at least this large get the deep configuration
+    const uint64_t hub = c->params.sum_hub > 0 ? (uint64_t)c->params.sum_hub : 8192;   // clusters at least this large get the deep configuration
     // Every ring slot must always be filled by the same producer warp (the parity waits allow a
     // producer to be one phase ahead of the consumer, not two), so the number of producers divides
     // the number of stages.
-    {   // hub clusters: 12 producers, the same stages, up to 192 KB of ring (one CTA per SM); the CTAs of
-        // ordinary clusters return at once.  Runs on the context's auxiliary stream next to the launch
+    {   // hub clusters: 12 producers, the same stages, up to 192 KB of ring (one CTA per SM), optionally split
+        // by columns (sum_slices); the CTAs of ordinary clusters return at once.  Runs on the context's auxiliary stream next to the launch
         // below (disjoint clusters), so the hubs' serial chains overlap the ordinary clusters.
-      uint32_t stage_rows = (16u * 1024u) / (ld4 * 16u);
+      // (measured: slicing does NOT pay — random 128-byte pieces reach 1.2 TB/s of HBM against 2.7 TB/s for
+      // whole 384..512-byte rows, and the gather, not the chain, bounds the launch; it stays a parameter)
+      uint32_t nslice = 1;
+      if (c->params.sum_slices > 0) nslice = (uint32_t)c->params.sum_slices;
+      if (nslice < 1 || ld4 % nslice != 0) nslice = 1;
+      const uint32_t w4 = ld4 / nslice;
+      uint32_t stage_rows = (16u * 1024u) / (w4 * 16u);
       if (stage_rows > 32) stage_rows = 32;
       if (stage_rows < 1) stage_rows = 1;
-      const size_t stage_bytes = (size_t)stage_rows * ld4 * 16;
+      const size_t stage_bytes = (size_t)stage_rows * w4 * 16;
       uint32_t nstage = (uint32_t)((192u * 1024u) / stage_bytes);
       if (nstage > 12) nstage = 12;
       if (nstage < 2) nstage = 2;
@@ -324,8 +347,8 @@ int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t*
       }
       SPF_CUDA(cudaEventRecord(c->aux_ev[0], st));                     // inputs are ready on the main stream
       SPF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
-      cluster_sum_ws_kernel<<<k, (nprod + 1) * 32, smem, c->aux_stream>>>(X, ld4, d_offsets, d_rows, means, divide, stage_rows,
-                                                                         nstage, nprod, hub, ~0ull);
+      cluster_sum_ws_kernel<<<dim3(k, nslice), (nprod + 1) * 32, smem, c->aux_stream>>>(X, ld4, d_offsets, d_rows, means, divide,
+                                                                                      stage_rows, nstage, nprod, hub, ~0ull);
       SPF_TRY(check_launch(c, "cluster_sum_ws_kernel"));
       SPF_CUDA(cudaEventRecord(c->aux_ev[1], c->aux_stream));
     }

@@ -686,19 +686,28 @@ struct CountOp {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)(v & ~NMEM_OVERFLOW_BIT); }
 };
 
+// Thread per row: a row's member slots start on a 16-byte boundary (stride 1 << sl_shift >= 4 slots
+// or a single-slot list), so they are read four at a time; consecutive rows write consecutive
+// ranges of the pair arrays.  (A warp per row left 26 of 32 lanes idle at the usual 1-6 members.)
 __global__ void fill_pairs_kernel(const uint32_t* __restrict__ memlist, int sl_shift, const uint32_t* __restrict__ nmem,
                                   const uint64_t* __restrict__ row_off, uint32_t m,
                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < m; r += warps_total) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
     const uint32_t nm = nmem[r];
     if (nm & NMEM_OVERFLOW_BIT) continue;
     const uint64_t off = row_off[r];
     const uint32_t* mem = memlist + ((size_t)r << sl_shift);
-    for (uint32_t s = lane; s < nm; s += 32) {
-      keys[off + s] = mem[s];
-      vals[off + s] = r;
+    if (sl_shift >= 2) {
+      for (uint32_t s = 0; s < nm; s += 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(mem + s);
+        const uint32_t qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (s + i < nm) { keys[off + s + i] = qv[i]; vals[off + s + i] = r; }
+      }
+    } else {
+      for (uint32_t s = 0; s < nm; ++s) { keys[off + s] = mem[s]; vals[off + s] = r; }
     }
   }
 }
@@ -793,6 +802,9 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   SPF_TRY(d_total.alloc(st, 1));
   cub::TransformInputIterator<uint64_t, CountOp, const uint32_t*> counts(a.nmem, CountOp());
   size_t tmp_bytes = 0;
+  uint64_t total = 0;
+  {
+  KernelTimer ts(c, "csr_scan");
   SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, row_off.p, (int64_t)a.m, st));
   DevBuf<uint8_t> tmp;
   SPF_TRY(tmp.alloc(st, tmp_bytes));
@@ -800,9 +812,9 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   c->launches += 2;
   total_kernel<<<1, 32, 0, st>>>(row_off.p, a.nmem, (uint32_t)a.m, d_total.p);
   SPF_TRY(check_launch(c, "total_kernel"));
-  uint64_t total = 0;
   SPF_CUDA(cudaMemcpyAsync(&total, d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   SPF_CUDA(cudaStreamSynchronize(st));
+  }
 
   DevBuf<uint32_t> keys, vals, keys2, vals2;
   SPF_TRY(keys.alloc(st, total));
@@ -812,7 +824,8 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   DevBuf<uint64_t> offsets;
   SPF_TRY(offsets.alloc(st, (size_t)a.k + 1));
   {
-    uint64_t blocks = ceil_div(a.m * 32, 256);
+    KernelTimer ts(c, "csr_fill");
+    uint64_t blocks = ceil_div(a.m, 256);
     if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
     fill_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->memlist.p, s->sl_shift, a.nmem, row_off.p, (uint32_t)a.m,
                                                         keys.p, vals.p);
@@ -823,6 +836,7 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   int end_bit = 1;
   while (end_bit < 32 && (1ull << end_bit) < (uint64_t)a.k) ++end_bit;
   if (total > 0) {
+    KernelTimer ts(c, "csr_sort");
     size_t sort_bytes = 0;
     SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys2.p, vals.p, vals2.p,
                                              (int64_t)total, 0, end_bit, st));

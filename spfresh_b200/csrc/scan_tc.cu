@@ -72,6 +72,9 @@ struct ScanTcArgs {
   uint32_t u0;                     // rank of this launch's first unit (row scalars are kept for all units)
   const UnitDesc* desc;            // per unit of this launch
   float4* cmax;                    // bound pass out (optional): per (tile, column half, row) its 4 chunk maxima
+  uint32_t* cmask;                 // ... and per chunk 8 bits: which 4-slot subgroups can still pass (see below)
+  const float2* rowes;             // per row: (E, slop) of its query — the running threshold of the masks
+  uint32_t topk;                   // K of the search (<= TOPR)
   const float* rowthr;             // per row: threshold on s (phase B), -inf / +inf = enabled / disabled (phase A)
   const uint32_t* rowseq;          // per row: encounter base of the pair - slot0 (mod 2^32)
   const uint32_t* rowpair;         // per row: q * nprobe + p, NOPAIR for padding rows
@@ -229,6 +232,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool warp_enabled = __any_sync(0xffffffffu, enabled);
       const uint32_t rseq = a.rowseq[row];
       const uint32_t pair = a.rowpair[row];
+      const float2 es = (MODE == 0 && a.cmask != nullptr) ? a.rowes[row] : make_float2(0.f, 0.f);
       float top[TOPR];
 #pragma unroll
       for (int i = 0; i < TOPR; ++i) top[i] = -INF;
@@ -249,6 +253,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // One 32-column chunk of s.  Chunks are aligned with the 32-slot groups of the list, so a
         // chunk lies either inside the list or entirely behind its end (where the tile holds the
         // next list's vectors).
+        // Subgroup masks (bound pass with kept chunk maxima): the final threshold on s of this row's query
+        // is max(by_thr, kth - E) - slop with kth = the K-th largest chunk maximum over ALL of the query's
+        // pairs (tau_kernel), which is at least the K-th largest this row has seen so far.  A 4-slot
+        // subgroup whose maximum does not exceed that running bound (one more slop below, so that the
+        // two evaluations need not round alike) cannot hold a passing element; the group refinement
+        // then evaluates only the marked subgroups of a flagged chunk instead of all 32 vectors.
+        float th_run = -INF;
+        if (MODE == 0 && a.cmask != nullptr) {
+          float kv = top[TOPR - 1];
+#pragma unroll
+          for (int i = 0; i < TOPR - 1; ++i)
+            if ((uint32_t)(i + 1) == a.topk) kv = top[i];
+          th_run = ((kv - es.x) - es.y) - es.y;
+        }
+        uint32_t mword = 0;
         auto process = [&](uint32_t (&rr)[32], int c) -> float {
           const uint32_t cb = colbase + (uint32_t)c * 32u;
           if (cb >= ud.nslots || !enabled) return -INF;
@@ -267,6 +286,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                          fmaxf(__uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3])));
           float m = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
           m = fmaxf(m, -INF);                             // an all-NaN chunk counts as empty
+          if (MODE == 0 && a.cmask != nullptr) {
+            uint32_t mk = 0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) mk |= q[g] > th_run ? (1u << g) : 0u;
+            mword |= mk << (8 * c);
+          }
           if (MODE == 1) {
             if (m > thr_s) {
               // which of the 32 columns pass: straight-line mask, then one iteration per hit (only the
@@ -314,6 +339,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const float m3 = process(rbuf, 3);
         if (MODE == 0 && a.cmax != nullptr)                   // one coalesced 512-byte store per warp and tile
           a.cmax[((size_t)(ud.tile0 + t) * 2 + half) * UNIT_ROWS + lrow] = make_float4(m0, m1, m2, m3);
+        if (MODE == 0 && a.cmask != nullptr)
+          a.cmask[((size_t)(ud.tile0 + t) * 2 + half) * UNIT_ROWS + lrow] = mword;
       }
       if (MODE == 0 && enabled) {
         float4* o = reinterpret_cast<float4*>(a.pairtop + ((size_t)pair * 2 + half) * TOPR);
@@ -439,6 +466,7 @@ struct GatherArgs {
   int copy_rows;                   // 0: the gathered rows of this chunk are already in place
   float* A; UnitDesc* desc; float* rowthr; uint32_t* rowseq; uint32_t* rowpair;
   uint32_t* unit_slot0;            // per unit rank: first slot of its list
+  float2* rowes; const float* qnorm; const float* qres; const float* vstat;   // per row (E, slop) of its query, or NULL
   unsigned long long* bytes;       // algorithmic scan bytes (counted when != NULL)
   unsigned long long* stream_bytes;   // [0] bytes of list tiles one pass requests, [1] the same counting every list once
 };
@@ -494,6 +522,15 @@ __global__ void __launch_bounds__(256) unit_gather_kernel(GatherArgs g) {
       g.rowthr[grow] = th;
       g.rowseq[grow] = pair != NOPAIR ? g.seqbase[pair] - slot0 : 0u;
       g.rowpair[grow] = pair;
+      if (g.rowes) {
+        float2 es = make_float2(INF, INF);
+        if (pair != NOPAIR) {
+          const float qn = g.qnorm[q], cnmax = g.vstat[0];
+          es.x = tc_err_bound(qn, g.qres[q], cnmax, g.vstat[1], g.ld4 * 4);
+          es.y = 1e-6f * (qn + cnmax) + 1e-30f;
+        }
+        g.rowes[grow] = es;
+      }
     }
   }
 }
@@ -564,28 +601,34 @@ __global__ void tc_unit_tiles_kernel(const uint32_t* __restrict__ keys_sorted, u
   ntiles[r] = r < nunits ? ((0xffffffffu - keys_sorted[r]) * 32u + BN - 1) / BN : 0u;
 }
 
-struct WorkItem { uint32_t pair, group; };   // group = 32-slot group of the index
+struct WorkItem { uint32_t pair, group; };   // group = 4-slot subgroup of the index (32-slot group * 8 + subgroup)
 
 struct FlagArgs {
   const uint32_t* keys_sorted;     // unit ranks: 0xffffffff - groups of the list
-  const uint32_t* tile_off; const float4* cmax;
+  const uint32_t* tile_off; const float4* cmax; const uint32_t* cmask;
   const uint32_t* rowpair; const uint32_t* unit_slot0;  // per row: pair; per unit rank: first slot of its list
   const float* qthr; uint32_t nprobe;
   WorkItem* work; uint32_t work_cap; uint32_t* nwork; uint8_t* qflag;
 };
 
-// One CTA per unit rank, thread = (column half, row): walks the unit's chunk maxima and queues
-// every (pair, 32-slot group) whose maximum passes the pair's threshold on s.  Items that do not
-// fit flag their query for the exact fallback.
+// One CTA per unit rank and run of FLAG_TILES tiles (the longest list would otherwise serialise
+// hundreds of dependent loads in one CTA), thread = (column half, row): walks the chunk maxima and queues
+// the marked 4-slot subgroups of every (pair, 32-slot group) whose maximum passes the pair's
+// threshold on s.  Items that do not fit flag their query for the exact fallback.
+constexpr uint32_t FLAG_TILES = 16;
 __global__ void __launch_bounds__(256) chunk_flag_kernel(FlagArgs f) {
   // items are staged in shared memory and appended with one global atomic per CTA (a single
   // global counter bumped once per item serialises in L2)
   constexpr uint32_t SQ = 2048;
   __shared__ WorkItem sq[SQ];
   __shared__ uint32_t sn, sbase;
+  const uint32_t r = blockIdx.x;
+  {
+    const uint32_t nt = ((0xffffffffu - f.keys_sorted[r]) * 32u + BN - 1) / BN;
+    if (blockIdx.y * FLAG_TILES >= nt) return;            // block-uniform
+  }
   if (threadIdx.x == 0) sn = 0;
   __syncthreads();
-  const uint32_t r = blockIdx.x;
   const uint32_t half = threadIdx.x >> 7, lrow = threadIdx.x & 127;
   const size_t row = (size_t)r * UNIT_ROWS + lrow;
   const uint32_t pair = f.rowpair[row];
@@ -595,23 +638,31 @@ __global__ void __launch_bounds__(256) chunk_flag_kernel(FlagArgs f) {
     const uint32_t groups = 0xffffffffu - f.keys_sorted[r];
     const uint32_t ntiles = (groups * 32u + BN - 1) / BN;
     const uint32_t g0 = f.unit_slot0[r] >> 5;
-    const float4* cm = f.cmax + ((size_t)f.tile_off[r] * 2 + half) * UNIT_ROWS + lrow;
+    const size_t e0 = ((size_t)f.tile_off[r] * 2 + half) * UNIT_ROWS + lrow;
+    const float4* cm = f.cmax + e0;
+    const uint32_t* mk = f.cmask + e0;
+    const uint32_t t_end = min(ntiles, (blockIdx.y + 1) * FLAG_TILES);
 #pragma unroll 4
-    for (uint32_t t = 0; t < ntiles; ++t) {
+    for (uint32_t t = blockIdx.y * FLAG_TILES; t < t_end; ++t) {
       const float4 m = cm[(size_t)t * 2 * UNIT_ROWS];
+      const uint32_t mw = mk[(size_t)t * 2 * UNIT_ROWS];
       const float mv[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t grp = t * 8 + half * 4 + c;          // chunk = 32-slot group of the list
         if (grp < groups && mv[c] > th) {
-          WorkItem w;
-          w.pair = pair; w.group = g0 + grp;
-          const uint32_t sp = atomicAdd(&sn, 1u);
-          if (sp < SQ) {
-            sq[sp] = w;
-          } else {                                            // staging full: straight to the global list
-            const uint32_t pos = atomicAdd(f.nwork, 1u);
-            if (pos < f.work_cap) f.work[pos] = w; else f.qflag[q] = 1;
+          uint32_t sub = (mw >> (8 * c)) & 0xffu;           // never empty: the chunk maximum is in a marked subgroup
+          while (sub) {
+            WorkItem w;
+            w.pair = pair; w.group = (g0 + grp) * 8u + (uint32_t)(__ffs(sub) - 1);
+            sub &= sub - 1;
+            const uint32_t sp = atomicAdd(&sn, 1u);
+            if (sp < SQ) {
+              sq[sp] = w;
+            } else {                                          // staging full: straight to the global list
+              const uint32_t pos = atomicAdd(f.nwork, 1u);
+              if (pos < f.work_cap) f.work[pos] = w; else f.qflag[q] = 1;
+            }
           }
         }
       }
@@ -632,24 +683,29 @@ struct GroupArgs {
   const float* qbound; uint32_t cap; uint32_t* qcnt; uint4* ebucket;   // exact entries: key lo, key hi, slot
 };
 
-// One warp per queued (pair, group): the lane's vector against the pair's query, exact (the
-// reference's sequential f32 sum, :172); vectors passing `dist <= threshold` (:176) and the certified
-// bound on the K-th smallest distance go to the query's bucket with their (distance, encounter) key.
+// Eight queued (pair, 4-slot subgroup) items per warp and step, four lanes each: the lane's vector
+// against the pair's query, exact (the reference's sequential f32 sum, :172); vectors passing
+// `dist <= threshold` (:176) and the certified bound on the K-th smallest distance go to the query's
+// bucket with their (distance, encounter) key.
 __global__ void __launch_bounds__(256) group_refine_kernel(GroupArgs g) {
   const ScanArgs& a = g.s;
   const int lane = threadIdx.x & 31;
   const uint32_t nw = min(*g.nwork, g.work_cap);
   const uint32_t ld4 = a.ld / 4;
   const float4* V4 = reinterpret_cast<const float4*>(a.vecs);
-  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nw; w += (gridDim.x * blockDim.x) >> 5) {
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u; w0 < nw; w0 += nwarps * 8u) {
+    const uint32_t w = w0 + ((uint32_t)lane >> 2);
+    if (w >= nw) continue;                                 // no warp-wide operation below
     const WorkItem it = g.work[w];
     const uint32_t q = it.pair / a.nprobe;
+    const uint32_t slot = it.group * 4u + ((uint32_t)lane & 3u);
     const float4* Q4 = reinterpret_cast<const float4*>(a.Q) + (size_t)q * ld4;
-    const float4* base = V4 + (size_t)it.group * ld4 * 32 + lane;
+    const float4* base = V4 + (size_t)(slot >> 5) * ld4 * 32 + (slot & 31u);
     // The sum only grows (or turns NaN), so a lane whose partial sum is already above the bound can
-    // stop reading: it could not pass the tests below anyway.  31 of the 32 vectors of a flagged
-    // group usually drop out this way, and with them most of the group's sectors.
-    const float bound = fminf(a.thr[q], g.qbound[q]);
+    // stop reading: it could not pass the tests below anyway.
+    const float thr = a.thr[q], qb = g.qbound[q];
+    const float bound = fminf(thr, qb);
     float acc = 0.0f;
     for (uint32_t c0 = 0; c0 < ld4; c0 += 4) {
       if (!(acc <= bound)) break;
@@ -666,9 +722,8 @@ __global__ void __launch_bounds__(256) group_refine_kernel(GroupArgs g) {
         }
       }
     }
-    const uint32_t slot = it.group * 32 + lane;
     const bool valid = a.slot_ids[slot] != ~0ull;
-    if (valid && acc <= a.thr[q] && acc <= g.qbound[q]) {
+    if (valid && acc <= thr && acc <= qb) {
       const uint32_t l = a.probe[it.pair];
       // encounter index: base of this probe + position in the list
       const uint32_t seq = a.seqbase[it.pair] + (slot - (uint32_t)(a.grp_off[l] * 32));
@@ -1019,7 +1074,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   // (4 KB per tile) and the candidates come from an exact re-evaluation of the few 32-slot groups
   // whose maximum passes ("group refinement"); otherwise — and for the centroid probe, where every
   // query has nprobe hits in one short list — a second GEMM pass emits the candidates.
-  uint32_t total_tiles = 0;
+  uint32_t total_tiles = 0, max_tiles = 0;
   DevBuf<uint32_t> utiles, tile_off;
   bool keep_cmax = false;
   // (a flagged group costs 32 exact vectors = 128 * ld bytes: beyond ld = 256 the second GEMM pass,
@@ -1036,8 +1091,9 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_CUDA(cub::DeviceScan::ExclusiveSum(stmp.p, sb, utiles.p, tile_off.p, (int)(nunits + 1), st));
     c->launches += 1;
     SPF_CUDA(cudaMemcpyAsync(&total_tiles, tile_off.p + nunits, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaMemcpyAsync(&max_tiles, utiles.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));   // rank 0 = longest list
     SPF_CUDA(cudaStreamSynchronize(st));
-    keep_cmax = (uint64_t)total_tiles * 4096ull <= (uint64_t)c->params.scan_tc_cmax_mb << 20;
+    keep_cmax = (uint64_t)total_tiles * 5120ull <= (uint64_t)c->params.scan_tc_cmax_mb << 20;
   }
 
   if (nunits > 0) {
@@ -1049,6 +1105,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     DevBuf<uint32_t> rowseq, rowpair, unit_slot0;
     DevBuf<UnitDesc> desc;
     DevBuf<float4> cmax;
+    DevBuf<uint32_t> cmask;
+    DevBuf<float2> rowes;
     SPF_TRY(A.alloc(st, (size_t)chunk_units * UNIT_ROWS * ld));
     SPF_TRY(rowthr.alloc(st, (size_t)nunits * UNIT_ROWS));
     SPF_TRY(rowseq.alloc(st, (size_t)nunits * UNIT_ROWS));
@@ -1057,7 +1115,11 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_TRY(desc.alloc(st, chunk_units));
     SPF_TRY(pairtop.alloc(st, npairs * 2 * topr));
     SPF_TRY(qbound.alloc(st, nq));
-    if (keep_cmax) SPF_TRY(cmax.alloc(st, (size_t)total_tiles * 2 * UNIT_ROWS));
+    if (keep_cmax) {
+      SPF_TRY(cmax.alloc(st, (size_t)total_tiles * 2 * UNIT_ROWS));
+      SPF_TRY(cmask.alloc(st, (size_t)total_tiles * 2 * UNIT_ROWS));
+      SPF_TRY(rowes.alloc(st, (size_t)nunits * UNIT_ROWS));
+    }
 
     CUtensorMap map_a, map_b, map_e;
     SPF_TRY(make_map_k128(c, &map_a, A.p, (uint64_t)chunk_units * UNIT_ROWS, ld, BM));
@@ -1075,6 +1137,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     g.tile_off = keep_cmax ? tile_off.p : nullptr;
     g.A = A.p; g.desc = desc.p; g.rowthr = rowthr.p; g.rowseq = rowseq.p; g.rowpair = rowpair.p;
     g.unit_slot0 = unit_slot0.p;
+    g.rowes = keep_cmax ? rowes.p : nullptr; g.qnorm = qnorm.p; g.qres = qres.p; g.vstat = side.vstat;
     g.stream_bytes = stats.p + 2;
 
     ScanTcArgs k;
@@ -1082,6 +1145,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     k.desc = desc.p; k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
     k.pairtop = pairtop.p; k.qcnt = qcnt.p; k.bucket = bucket.p;
     k.cmax = keep_cmax ? cmax.p : nullptr;
+    k.cmask = keep_cmax ? cmask.p : nullptr; k.rowes = rowes.p; k.topk = s.K;
     k.dense = nullptr; k.dense_ld = 0;
 
     for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
@@ -1111,7 +1175,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     if (keep_cmax) {
       // group refinement: queue the (pair, group) items whose chunk maximum passes, evaluate them exactly
       KernelTimer t(c, n_b);
-      const uint64_t want = nq * 64ull > (1ull << 20) ? nq * 64ull : (1ull << 20);
+      const uint64_t want = nq * 128ull > (1ull << 20) ? nq * 128ull : (1ull << 20);
       const uint32_t work_cap = (uint32_t)(want < (1ull << 30) ? want : (1ull << 30));
       DevBuf<WorkItem> work;
       DevBuf<uint32_t> nwork;
@@ -1120,11 +1184,14 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
       SPF_TRY(ebucket.alloc(st, (size_t)nq * cap));
       SPF_CUDA(cudaMemsetAsync(nwork.p, 0, sizeof(uint32_t), st));
       FlagArgs f;
-      f.keys_sorted = ukey2.p; f.tile_off = tile_off.p; f.cmax = cmax.p; f.rowpair = rowpair.p;
+      f.keys_sorted = ukey2.p; f.tile_off = tile_off.p; f.cmax = cmax.p; f.cmask = cmask.p; f.rowpair = rowpair.p;
       f.unit_slot0 = unit_slot0.p; f.qthr = qthr.p; f.nprobe = s.nprobe;
       f.work = work.p; f.work_cap = work_cap; f.nwork = nwork.p; f.qflag = call.qflag;
-      chunk_flag_kernel<<<nunits, 256, 0, st>>>(f);
-      SPF_TRY(check_launch(c, "chunk_flag_kernel"));
+      {
+        KernelTimer tf(c, "scan_tc_flag");
+        chunk_flag_kernel<<<dim3(nunits, (max_tiles + FLAG_TILES - 1) / FLAG_TILES), 256, 0, st>>>(f);
+        SPF_TRY(check_launch(c, "chunk_flag_kernel"));
+      }
       GroupArgs ga;
       ga.s = s; ga.work = work.p; ga.nwork = nwork.p; ga.work_cap = work_cap; ga.qbound = qbound.p; ga.cap = cap;
       ga.qcnt = qcnt.p; ga.ebucket = ebucket.p;
@@ -1208,7 +1275,8 @@ int probe_tc_dense(spf_ctx* c, const ScanTcSide& side, const float* centroids, c
     SPF_TRY(check_launch(c, "dense_setup_kernel"));
     ScanTcArgs k;
     k.nunits = nu; k.kb = (ld + BK - 1) / BK; k.nprobe = 1; k.cap = 0; k.u0 = 0;
-    k.desc = desc.p; k.cmax = nullptr; k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
+    k.desc = desc.p; k.cmax = nullptr; k.cmask = nullptr; k.rowes = nullptr; k.topk = 0;
+    k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
     k.pairtop = nullptr; k.qcnt = nullptr; k.bucket = nullptr;
     k.dense = S.p; k.dense_ld = cslots;
     {

@@ -12,13 +12,16 @@ import bench  # noqa: E402
 import spfresh_b200 as s  # noqa: E402
 
 names = ["assign_tc", "classify", "exact_eval", "finalize", "resolve", "cc_matrix", "csr", "overflow", "kmeans_seed", "kmeans_sums",
-         "kmeans_exchange", "kmeans_means", "kmeans_medoid"]
+         "kmeans_exchange", "kmeans_means", "kmeans_medoid", "csr_scan", "csr_fill", "csr_sort"]
 dev = torch.device("cuda", 0)
 ctx = s.Context(0)
 ext = torch.cuda.ExternalStream(ctx.stream)
 
 
-def run(tag, ds, init_rows, init_vec, steps=5):
+def run(tag, ds, init_rows, init_vec, steps=5, sum_hub=0, sum_slices=0):
+    ctx.set_param("sum_hub", sum_hub)
+    ctx.set_param("sum_slices", sum_slices)
+    tag = f"{tag} hub={sum_hub} slices={sum_slices}"
     sess = s.KMeansSession(ds, None, 0, 0, init_rows.size)
     sess.set_centroids(init_rows, init_vec)
     for it in range(steps):
@@ -46,7 +49,9 @@ def run(tag, ds, init_rows, init_vec, steps=5):
 
 rows = bench.make_rows(0)
 ds = s.Dataset(ctx, rows)
-run("1M x 128 gauss", ds, np.arange(4096, dtype=np.uint64), rows[:4096])
+ref = None
+for hub, sl in ((0, 1), (0, 0), (2048, 0), (512, 0), (2048, 2)):
+    run("1M x 128 gauss", ds, np.arange(4096, dtype=np.uint64), rows[:4096], steps=4, sum_hub=hub, sum_slices=sl)
 ds.free()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 25_000_000
 x = bench.device_clustered(torch, dev, n, 96, 4096, 1234, 99)
@@ -54,4 +59,5 @@ ds = s.Dataset(ctx, device_ptr=x.data_ptr(), n=n, d=96)
 del x
 torch.cuda.empty_cache()
 init = np.sort(np.random.Generator(np.random.Philox(key=7)).choice(n, 4096, replace=False)).astype(np.uint64)
-run(f"{n} x 96 clustered", ds, init, ds.fetch_rows(init), steps=4)
+for hub, sl in ((0, 1), (0, 0)):
+    run(f"{n} x 96 clustered", ds, init, ds.fetch_rows(init), steps=3, sum_hub=hub, sum_slices=sl)
