@@ -541,6 +541,16 @@ def max_over_ranks(torch, dist, dev, world, *vals):
     return out if len(out) > 1 else out[0]
 
 
+def all_ranks(torch, dist, dev, world, val):
+    """The value of every rank, in rank order."""
+    if world == 1:
+        return [float(val)]
+    t = torch.tensor([float(val)], dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return [float(x.item()) for x in parts]
+
+
 def bench_kmeans_iteration(spf, ctx, ds, comm, rank, world, rows_np, torch, dist, dev, ext, iters=4):
     """HierarchicalClustering assign_points + update_centroids (hierarchical.rs:368-390, 138-181), rows
     sharded (1M per GPU, weak), state resident on the device, exchanges over NCCL."""
@@ -737,6 +747,9 @@ def bench_sweep(spf, ctx, comm, rank, world, torch, dist, dev, ext, hbm_peak, wi
     res.free()
     lb, le = balanced_list_ranges(f.offsets, world)[rank]
     idx = spf.DeviceIndex.pack(ds, f.offsets, f.members, med, list_range=(lb, le))
+    # N > 1 and the whole index fits one GPU (4.8 GB here): the other deployment, every rank holds all
+    # lists and answers its own slice of the queries — no exchange at all ("replicas only")
+    idx_full = spf.DeviceIndex.pack(ds, f.offsets, f.members, med) if world > 1 else None
     nq_total = 100_000 // world * world
     nql = nq_total // world
     q_all = np.random.Generator(np.random.Philox(key=46)).standard_normal((nq_total, DIM), dtype=np.float32)
@@ -779,6 +792,25 @@ def bench_sweep(spf, ctx, comm, rank, world, torch, dist, dev, ext, hbm_peak, wi
         rec = {"nprobe": nprobe, "nq": nq_total, "k": TOPK, "qps_e2e": nq_total / (ms * 1e-3), "ms_per_batch": ms,
                "scan_ms_max": scan_ms, "probe_ms": km["probe"], "exchange_ms_max": exch_ms, "merge_ms": km["merge"],
                "h2d_bytes_per_rank": int(q.nbytes), "d2h_bytes_per_rank": int(sum(o.nbytes for o in out_bufs))}
+        if world > 1:
+            rec["scan_ms_all_ranks"] = [round(v, 3) for v in all_ranks(torch, dist, dev, world, km["scan"])]
+            sh = (ids.copy(), dists.copy(), counts.copy())
+            for _ in range(2):
+                idx_full.search(q, TOPK, nprobe=nprobe, out=out_bufs)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            for _ in range(reps):
+                ids, dists, counts = idx_full.search(q, TOPK, nprobe=nprobe, out=out_bufs)
+            e1.record(ext)
+            e1.synchronize()
+            ms_rep = max_over_ranks(torch, dist, dev, world, e0.elapsed_time(e1) / reps)
+            same = bool(np.array_equal(sh[2], counts) and np.array_equal(sh[0], ids)
+                        and np.array_equal(sh[1].view(np.uint32), dists.view(np.uint32)))
+            rec["replicated_lists"] = {"qps_e2e": nq_total / (ms_rep * 1e-3), "ms_per_batch": ms_rep,
+                                       "identical_to_list_sharded": same,
+                                       "what": "every rank holds all lists and searches its own query slice (spf_search_batch), no exchange"}
         if km["scan_tc_a"] > 0 and stream_mb > 0:
             ach = stream_mb * 1e6 / (km["scan_tc_a"] * 1e-3) / 1e9
             rec["bound_pass"] = {"kernel_ms": km["scan_tc_a"], "list_bytes_streamed_once": int(stream_mb * 1e6),
@@ -805,6 +837,8 @@ def bench_sweep(spf, ctx, comm, rank, world, torch, dist, dev, ext, hbm_peak, wi
            "sharding": "posting lists by contiguous list range balanced by vectors; queries sharded for upload / probe / merge",
            "points": points}
     idx.free()
+    if idx_full is not None:
+        idx_full.free()
     ds.free()
     return out
 

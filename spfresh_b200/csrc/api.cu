@@ -175,6 +175,8 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "cc_matrix_max_k") c->params.cc_matrix_max_k = value;
   else if (s == "exact_tma") c->params.exact_tma = value;
   else if (s == "exact_tma_min_pairs") c->params.exact_tma_min_pairs = value;
+  else if (s == "exact_packed") c->params.exact_packed = value;
+  else if (s == "exact_one_cta") c->params.exact_one_cta = value;
   else if (s == "sum_hub") c->params.sum_hub = value;
   else if (s == "sum_slices") c->params.sum_slices = value;
   else if (s == "cc_cache") c->params.cc_cache = value;

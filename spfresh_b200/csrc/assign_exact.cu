@@ -180,10 +180,10 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
 // TMA-staged, register-tiled kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int XT_M = 128, XT_N = 128, XT_K = 16;      // points x centroids x dimensions per stage
-constexpr int XT_STAGES = 4;
+constexpr int xt_stages(int minb) { return minb == 1 ? 8 : 4; }   // one CTA per SM: room for a deeper ring
 constexpr int XT_TILE_BYTES = XT_M * XT_K * 4;        // 8 KB per operand and stage
 constexpr int XT_THREADS = 256;                       // 8 compute warps; thread 0 also issues the TMA loads
-constexpr int XT_SMEM = 2 * XT_STAGES * XT_TILE_BYTES + 256 + 1024;
+constexpr int xt_smem(int minb) { return 2 * xt_stages(minb) * XT_TILE_BYTES + 256 + 1024; }
 
 // slot (within a 128-centroid tile) held by row r of the permuted centroid copy
 __host__ __device__ inline uint32_t xt_slot_of_row(uint32_t r) { return 8u * (r & 15u) + (r >> 4); }
@@ -197,8 +197,11 @@ __global__ void xt_permute_rows_kernel(const float4* __restrict__ C, uint32_t ld
   out[t] = slot < k ? C[(size_t)slot * ld4 + col] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(XT_THREADS, 2)
+// PACKED (Manhattan / Chebyshev): the differences of two consecutive dimensions come from one
+// sub.rn.f32x2 (FADD2: both lanes IEEE round-to-nearest like the scalar FADD), the accumulator chain
+// stays scalar and in dimension order: 6 issue slots per 4 element-ops instead of 8.
+template <int METRIC, bool PACKED, int MINB>
+__global__ void __launch_bounds__(XT_THREADS, MINB)
 assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, uint32_t m,
                         uint32_t k, uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
                         int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip,
@@ -207,6 +210,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   // (declared with its alignment instead of aligned by pointer arithmetic: the compiler must keep
   // seeing a shared-memory address, or the operand loads become generic LD instead of LDS)
   extern __shared__ __align__(1024) unsigned char xt_raw[];
+  constexpr int XT_STAGES = xt_stages(MINB);
   unsigned char* smem = xt_raw;
   unsigned char* xs = smem;                                        // [XT_STAGES][128 rows][64 B]
   unsigned char* cs = smem + XT_STAGES * XT_TILE_BYTES;
@@ -275,6 +279,33 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const unsigned char* xp = xb + xbase + ((c ^ xswz) << 4);
 #pragma unroll
         for (int jh = 0; jh < 2; ++jh) {                 // 4 centroids at a time: 16 operand registers
+          if constexpr (PACKED && METRIC != SPF_METRIC_EUCLIDEAN) {
+            ulonglong2 cv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const ulonglong2*>(cp + (jh * 4 + j) * 1024);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(xp + i * 1024);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                unsigned long long d01, d23;
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(xv.x), "l"(cv[j].x));
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(xv.y), "l"(cv[j].y));
+                float d0, d1, d2, d3;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d01));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(d2), "=f"(d3) : "l"(d23));
+                float a = acc[i][jh * 4 + j];
+                if constexpr (METRIC == SPF_METRIC_MANHATTAN) {
+                  a = __fadd_rn(a, fabsf(d0)); a = __fadd_rn(a, fabsf(d1));
+                  a = __fadd_rn(a, fabsf(d2)); a = __fadd_rn(a, fabsf(d3));
+                } else {
+                  a = fmaxf(a, fabsf(d0)); a = fmaxf(a, fabsf(d1));
+                  a = fmaxf(a, fabsf(d2)); a = fmaxf(a, fabsf(d3));
+                }
+                acc[i][jh * 4 + j] = a;
+              }
+            }
+          } else {
           float4 cv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const float4*>(cp + (jh * 4 + j) * 1024);
@@ -290,6 +321,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
               a = dist_step<METRIC>(a, xv.w, cv[j].w);
               acc[i][jh * 4 + j] = a;
             }
+          }
           }
         }
       }
@@ -384,15 +416,21 @@ int xt_make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, 
   return SPF_OK;
 }
 
-template <int METRIC>
+template <int METRIC, bool PACKED>
 int launch_xt(spf_ctx* c, const float* P, uint64_t m, const float* Cperm, uint32_t k, uint32_t ld, float factor,
               CandRec* cand, RowInfo* info, int cap, float* dense, int symmetric, const int* d_skip, const float* penalty,
               dim3 grid) {
   CUtensorMap map_x, map_c;
   SPF_TRY(xt_make_map(c, &map_x, P, m, ld));
   SPF_TRY(xt_make_map(c, &map_c, Cperm, (uint64_t)round_up(k, XT_N), ld));
-  SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));
-  assign_exact_tma_kernel<METRIC><<<grid, XT_THREADS, XT_SMEM, c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand, info,
+  if (PACKED && ((c->params.exact_one_cta >> METRIC) & 1) != 0) {
+    SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem(1)));
+    assign_exact_tma_kernel<METRIC, PACKED, 1><<<grid, XT_THREADS, xt_smem(1), c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand,
+                                                                                     info, cap, dense, symmetric, d_skip, penalty);
+    return check_launch(c, "assign_exact_tma_kernel");
+  }
+  SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem(2)));
+  assign_exact_tma_kernel<METRIC, PACKED, 2><<<grid, XT_THREADS, xt_smem(2), c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand, info,
                                                                           cap, dense, symmetric, d_skip, penalty);
   return check_launch(c, "assign_exact_tma_kernel");
 }
@@ -408,11 +446,14 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   RowInfo* info = cb ? cb->info : nullptr;
   const int cap = cb ? cb->cap : 0;
   if (metric < 0 || metric > 2) return fail(SPF_E_INVALID, "unknown metric %d", metric);
-  // per-metric choice (bit `metric` of the knob), from measurements at d = 128 and d = 960: Chebyshev
-  // splits its two instructions per element over the FMA and the ALU pipe and is issue-bound — the
-  // 8 x 8 register tile lifts it from 0.58 to 0.74-0.81 of the issue peak; Manhattan and squared-L2
-  // put every instruction on the FMA pipe and run faster on the 4 x 4 kernel (0.69 / 0.76 against
-  // 0.60 / 0.68: the larger tile costs register-bank moves and dispatch stalls there)
+  // per-metric choice (bit `metric` of the knobs), from measurements at d = 128 and d = 960 (fractions of
+  // 2 lane instructions per element-op at one instruction per clock and SM sub-partition):
+  //   Chebyshev  4 x 4 kernel 0.58-0.61 | 8 x 8 TMA kernel 0.74-0.84 | + packed FADD2 differences 0.89-0.92
+  //   Manhattan  4 x 4 kernel 0.69-0.73 | 8 x 8 TMA 0.60-0.68 (dispatch stalls: 0.77 per issued instruction,
+  //              128 registers) | packed 0.73 | packed, compiled for one CTA per SM (236 registers, no
+  //              spills) 0.80-0.81
+  //   squared-L2 stays on the 4 x 4 kernel (0.76 against 0.68); its packed form is not used because ptxas
+  //              contracts mul.f32x2 + add.f32x2 into FFMA2, which changes the rounding
   const bool use_tma = c->tma_encode != nullptr && ((c->params.exact_tma >> metric) & 1) != 0 &&
                        (uint64_t)m * k >= (uint64_t)c->params.exact_tma_min_pairs && (reinterpret_cast<uintptr_t>(P) & 15) == 0;
   if (use_tma) {
@@ -429,16 +470,19 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
       uint64_t want = ceil_div((uint64_t)c->sm_count * 2, grid.x);
       grid.y = (unsigned)(want < 1 ? 1 : (want > ctiles ? ctiles : want));
     }
+    const bool packed = ((c->params.exact_packed >> metric) & 1) != 0;
+    const float* pen = cb ? penalty : nullptr;
     switch (metric) {
       case SPF_METRIC_EUCLIDEAN:
-        return launch_xt<SPF_METRIC_EUCLIDEAN>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip,
-                                               cb ? penalty : nullptr, grid);
+        return launch_xt<SPF_METRIC_EUCLIDEAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
       case SPF_METRIC_MANHATTAN:
-        return launch_xt<SPF_METRIC_MANHATTAN>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip,
-                                               cb ? penalty : nullptr, grid);
+        if (packed)
+          return launch_xt<SPF_METRIC_MANHATTAN, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
+        return launch_xt<SPF_METRIC_MANHATTAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
       default:
-        return launch_xt<SPF_METRIC_CHEBYSHEV>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip,
-                                               cb ? penalty : nullptr, grid);
+        if (packed)
+          return launch_xt<SPF_METRIC_CHEBYSHEV, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
+        return launch_xt<SPF_METRIC_CHEBYSHEV, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
     }
   }
   dim3 grid((unsigned)ceil_div(m, BM)), block(NTHREADS);

@@ -122,6 +122,7 @@ struct ClsSmem {
 // threshold interval, the centroid-centroid test, and the short-list entry of every element that
 // is not certainly out.  Records are either all exact (CUDA-core producer) or all approximate
 // (tensor producer), so exactness is a property of the call, not of the element.
+template <bool APPROX>
 __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a) {
   __shared__ ClsSmem smem[RS_WARPS];
   ClsSmem& sm = smem[threadIdx.x >> 5];
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
   const float INF = __int_as_float(0x7f800000);
   const uint32_t segcap = (uint32_t)a.cap / (uint32_t)a.nseg;
   const uint32_t slcap = 1u << a.sl_shift;
-  const bool approx = a.xnorm != nullptr;
+  constexpr bool approx = APPROX;   // tensor producer (a.xnorm != nullptr): a property of the call
   const uint32_t ent_flags = approx ? 0u : SE_EXACT;
   const float cnmax = approx ? a.cstat[0] : 0.0f, dcmax = approx ? a.cstat[1] : 0.0f;
 
@@ -227,9 +228,13 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         v[q] = approx ? fmaf(-2.0f, tv[q], xn) : tv[q];
-        const bool live = (q < 4 ? i < cnt0 : i < cnt1) && ((q < 4 ? jb0 : jb1) + (uint32_t)(q & 3)) < a.k;
-        pass |= (live && v[q] <= vbound) ? (1u << q) : 0u;      // NaN never passes (never a member)
+        pass |= v[q] <= vbound ? (1u << q) : 0u;                // NaN never passes (never a member)
       }
+      // live elements, per record: the record exists and the slot is a real centroid (only the last
+      // group of four can reach past k)
+      const uint32_t lm0 = i < cnt0 ? (jb0 + 3u < a.k ? 0xfu : (jb0 < a.k ? (1u << (a.k - jb0)) - 1u : 0u)) : 0u;
+      const uint32_t lm1 = i < cnt1 ? (jb1 + 3u < a.k ? 0xfu : (jb1 < a.k ? (1u << (a.k - jb1)) - 1u : 0u)) : 0u;
+      pass &= lm0 | (lm1 << 4);
       const uint32_t mine = (uint32_t)__popc(pass);
       uint32_t incl = mine;
 #pragma unroll
@@ -747,13 +752,15 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   uint64_t blocks = ceil_div(a.m, RS_WARPS);
   uint64_t blocks_cls = blocks, blocks_fin = blocks;
   int cls_per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cls_per_sm, classify_kernel, RS_WARPS * 32, 0);
+  if (a.xnorm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cls_per_sm, classify_kernel<true>, RS_WARPS * 32, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cls_per_sm, classify_kernel<false>, RS_WARPS * 32, 0);
   if (cls_per_sm < 1) cls_per_sm = 1;
   if (blocks_cls > (uint64_t)c->sm_count * cls_per_sm) blocks_cls = (uint64_t)c->sm_count * cls_per_sm;
   if (blocks_fin > (uint64_t)c->sm_count * 8) blocks_fin = (uint64_t)c->sm_count * 8;
   {
     KernelTimer t2(c, "classify");
-    classify_kernel<<<(unsigned)blocks_cls, RS_WARPS * 32, 0, st>>>(d);
+    if (a.xnorm) classify_kernel<true><<<(unsigned)blocks_cls, RS_WARPS * 32, 0, st>>>(d);
+    else classify_kernel<false><<<(unsigned)blocks_cls, RS_WARPS * 32, 0, st>>>(d);
     SPF_TRY(check_launch(c, "classify_kernel"));
   }
   if (a.xnorm) {   // the exact path never queues work

@@ -1022,17 +1022,20 @@ def test_assign_tensor_kernel_variants_match_oracle(spf, oracle, cc_cache):
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("n,d,k", [(700, 7, 9), (5000, 33, 300), (4097, 128, 513), (3000, 200, 130)])
 def test_assign_exact_both_kernels_match_oracle(spf, oracle, metric, n, d, k):
-    """The two CUDA-core kernels (TMA-staged 8 x 8 register tile, 64 x 64 __ldg kernel) for every metric,
-    candidate mode and the dense modes behind the centroid matrix / overflow fallback."""
+    """The CUDA-core kernels (64 x 64 __ldg kernel; TMA-staged 8 x 8 register tile, scalar and with packed
+    FADD2 differences) for every metric, candidate mode and the dense modes behind the centroid matrix /
+    overflow fallback."""
     data = gauss(n, d, 40 + n)
     data[n // 2] = data[1]
     cent = np.random.default_rng(n + k).choice(n, k, replace=False)
     cent[3], cent[4] = 1, n // 2
     ref = oracle.assign(data, metric, cent)
-    for mask in (0, 7):
+    for mask, packed, one_cta in ((0, 0, 0), (7, 0, 0), (7, 7, 0), (7, 7, 7)):
         c2 = spf.Context(0)
         try:
             c2.set_param("exact_tma", mask)
+            c2.set_param("exact_packed", packed)
+            c2.set_param("exact_one_cta", one_cta)
             c2.set_param("exact_tma_min_pairs", 1)
             c2.set_param("cc_cache", 0)
             ds = spf.Dataset(c2, data)
