@@ -700,8 +700,8 @@ def bench_deep(spf, ctx, comm, rank, world, torch, dist, dev, ext, rows_total=10
     km.step()
     ctx.set_profiling(True)
     km.step()
-    names = ["assign_tc", "resolve", "cc_matrix", "csr", "overflow", "kmeans_seed", "kmeans_sums", "kmeans_exchange", "kmeans_means",
-             "kmeans_medoid"]
+    names = ["assign_tc", "classify", "exact_eval", "finalize", "resolve", "cc_matrix", "csr", "csr_scan", "csr_fill", "csr_sort",
+             "overflow", "kmeans_seed", "kmeans_sums", "kmeans_exchange", "kmeans_means", "kmeans_medoid"]
     parts = {nm: max(ctx.kernel_ms(nm), 0.0) for nm in names}
     ctx.set_profiling(False)
     times = []

@@ -95,6 +95,8 @@ void spf_ctx_destroy(spf_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  for (auto& kv : c->scratch)
+    if (kv.second.p) cudaFree(kv.second.p);
   if (c->cc_cache.cc) cudaFree(c->cc_cache.cc);
   if (c->cc_cache.C) cudaFree(c->cc_cache.C);
   if (c->cc_cache.same) cudaFree(c->cc_cache.same);
@@ -119,6 +121,13 @@ int spf_ctx_trim(spf_ctx* c) {
   if (!c) return fail(SPF_E_INVALID, "ctx is NULL");
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
+  SPF_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& kv : c->scratch) {
+    if (kv.second.busy) continue;
+    if (kv.second.p) cudaFreeAsync(kv.second.p, c->stream);
+    kv.second.p = nullptr;
+    kv.second.bytes = 0;
+  }
   SPF_CUDA(cudaStreamSynchronize(c->stream));
   cudaMemPool_t pool;
   SPF_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -176,6 +185,8 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "exact_tma") c->params.exact_tma = value;
   else if (s == "exact_tma_min_pairs") c->params.exact_tma_min_pairs = value;
   else if (s == "exact_packed") c->params.exact_packed = value;
+  else if (s == "scratch_cache") c->params.scratch_cache = value;
+  else if (s == "exact_seed") c->params.exact_seed = value;
   else if (s == "exact_one_cta") c->params.exact_one_cta = value;
   else if (s == "sum_hub") c->params.sum_hub = value;
   else if (s == "sum_slices") c->params.sum_slices = value;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(NTHREADS)
 assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __restrict__ C, uint32_t k,
                     uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
                     int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip,
-                    const float* __restrict__ penalty) {
+                    const float* __restrict__ penalty, const float* __restrict__ seed) {
   if (skip != nullptr && *skip != 0) return;   // the caller already holds this result (cached centroid matrix)
   __shared__ __align__(16) float Xs[2][BK][BM + PAD];
   __shared__ __align__(16) float Cs[2][BK][BN + PAD];
@@ -47,7 +47,10 @@ assign_exact_kernel(const float* __restrict__ P, uint32_t m, const float* __rest
   const uint32_t row0 = blockIdx.x * BM;
 
   if (tid < BM) {
-    rowmin[tid] = 0x7f800000u;   // +inf
+    // seed (optional): the distance of the point to SOME centroid, i.e. an upper bound of its minimum —
+    // the boundary threshold is tight from the first tile on instead of after the nearest one was met
+    rowmin[tid] = (seed != nullptr && row0 + tid < m) ? __float_as_uint(fminf(seed[row0 + tid], __int_as_float(0x7f800000)))
+                                                      : 0x7f800000u;   // +inf
     rowcnt[tid] = 0;
   }
   __syncthreads();
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(XT_THREADS, MINB)
 assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, uint32_t m,
                         uint32_t k, uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
                         int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip,
-                        const float* __restrict__ penalty) {
+                        const float* __restrict__ penalty, const float* __restrict__ seed) {
   if (skip != nullptr && *skip != 0) return;
   // (declared with its alignment instead of aligned by pointer arithmetic: the compiler must keep
   // seeing a shared-memory address, or the operand loads become generic LD instead of LDS)
@@ -256,7 +259,11 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   float runmin[8];
   uint32_t cnt[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { runmin[i] = INF; cnt[i] = 0; }
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t r = row0 + ty + 16u * i;
+    runmin[i] = (seed != nullptr && r < m) ? fminf(seed[r], INF) : INF;   // upper bound of the minimum (NaN -> +inf)
+    cnt[i] = 0;
+  }
   uint32_t s = 0, ph = 0;
   for (uint32_t t = blockIdx.y; t < ntile; t += gridDim.y) {
     if (symmetric && t < blockIdx.x) continue;
@@ -419,26 +426,27 @@ int xt_make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, 
 template <int METRIC, bool PACKED>
 int launch_xt(spf_ctx* c, const float* P, uint64_t m, const float* Cperm, uint32_t k, uint32_t ld, float factor,
               CandRec* cand, RowInfo* info, int cap, float* dense, int symmetric, const int* d_skip, const float* penalty,
-              dim3 grid) {
+              const float* seed, dim3 grid) {
   CUtensorMap map_x, map_c;
   SPF_TRY(xt_make_map(c, &map_x, P, m, ld));
   SPF_TRY(xt_make_map(c, &map_c, Cperm, (uint64_t)round_up(k, XT_N), ld));
   if (PACKED && ((c->params.exact_one_cta >> METRIC) & 1) != 0) {
     SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem(1)));
     assign_exact_tma_kernel<METRIC, PACKED, 1><<<grid, XT_THREADS, xt_smem(1), c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand,
-                                                                                     info, cap, dense, symmetric, d_skip, penalty);
+                                                                                     info, cap, dense, symmetric, d_skip, penalty, seed);
     return check_launch(c, "assign_exact_tma_kernel");
   }
   SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem(2)));
   assign_exact_tma_kernel<METRIC, PACKED, 2><<<grid, XT_THREADS, xt_smem(2), c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand, info,
-                                                                          cap, dense, symmetric, d_skip, penalty);
+                                                                          cap, dense, symmetric, d_skip, penalty, seed);
   return check_launch(c, "assign_exact_tma_kernel");
 }
 
 }  // namespace
 
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
-                        uint32_t ld, float factor, const CandBuf* cb, float* dense, const int* d_skip, const float* penalty) {
+                        uint32_t ld, float factor, const CandBuf* cb, float* dense, const int* d_skip, const float* penalty,
+                        const float* seed) {
   // a dense P x P request is the symmetric centroid matrix: half the tiles
   const int symmetric = (cb == nullptr && dense != nullptr && P == C && m == k) ? 1 : 0;
   if (m == 0 || k == 0) return SPF_OK;
@@ -472,17 +480,18 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
     }
     const bool packed = ((c->params.exact_packed >> metric) & 1) != 0;
     const float* pen = cb ? penalty : nullptr;
+    const float* sd = cb ? seed : nullptr;
     switch (metric) {
       case SPF_METRIC_EUCLIDEAN:
-        return launch_xt<SPF_METRIC_EUCLIDEAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
+        return launch_xt<SPF_METRIC_EUCLIDEAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
       case SPF_METRIC_MANHATTAN:
         if (packed)
-          return launch_xt<SPF_METRIC_MANHATTAN, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
-        return launch_xt<SPF_METRIC_MANHATTAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
+          return launch_xt<SPF_METRIC_MANHATTAN, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
+        return launch_xt<SPF_METRIC_MANHATTAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
       default:
         if (packed)
-          return launch_xt<SPF_METRIC_CHEBYSHEV, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
-        return launch_xt<SPF_METRIC_CHEBYSHEV, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, grid);
+          return launch_xt<SPF_METRIC_CHEBYSHEV, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
+        return launch_xt<SPF_METRIC_CHEBYSHEV, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
     }
   }
   dim3 grid((unsigned)ceil_div(m, BM)), block(NTHREADS);
@@ -494,15 +503,15 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
   switch (metric) {
     case SPF_METRIC_EUCLIDEAN:
       assign_exact_kernel<SPF_METRIC_EUCLIDEAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr, cb ? seed : nullptr);
       break;
     case SPF_METRIC_MANHATTAN:
       assign_exact_kernel<SPF_METRIC_MANHATTAN><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr, cb ? seed : nullptr);
       break;
     default:
       assign_exact_kernel<SPF_METRIC_CHEBYSHEV><<<grid, block, 0, c->stream>>>(
-          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr);
+          P, (uint32_t)m, C, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, cb ? penalty : nullptr, cb ? seed : nullptr);
       break;
   }
   return check_launch(c, "assign_exact_kernel");

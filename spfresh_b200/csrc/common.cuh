@@ -74,6 +74,8 @@ struct Params {
   int sum_slices = 0;        // ... column slices per hub cluster (0: one; measured slower when > 1)
   int exact_packed = 6;      // ... bit per metric: differences of two dimensions from one packed FADD2
   int exact_one_cta = 2;     // ... bit per metric: the packed kernel compiled for one CTA per SM (more registers)
+  int exact_seed = 1;        // Manhattan / Chebyshev: seed the running minimum from a tensor-core L2 pre-pass (0 off, 1 long rows, 2 always)
+  int scratch_cache = 1;     // keep the large temporaries of assign between calls (see spf_ctx::scratch)
   int exact_tma_min_pairs = 1 << 16;   // ... for problems of at least this many (point, centroid) pairs
   int cc_cache = 1;          // keep the k x k centroid matrix while the centroid vectors do not change
   int chunk_rows = 0;        // points per assign chunk (0: automatic)
@@ -108,6 +110,12 @@ struct spf_ctx {
     int metric = -1;
     bool valid = false;
   } cc_cache;
+  // Large per-call temporaries of the assign path (candidate records, short lists, member slots,
+  // sort buffers) are kept between calls, one grow-only slot per name: the multi-GB blocks of a
+  // 100 M-row k-means iteration otherwise make the stream-ordered pool remap memory every
+  // iteration (single iterations of 300 ms were measured at 1.8 s).  Freed by spf_ctx_trim / destroy.
+  struct ScratchSlot { void* p = nullptr; size_t bytes = 0; bool busy = false; };
+  std::map<std::string, ScratchSlot> scratch;
 };
 
 struct spf_dataset {
@@ -143,6 +151,7 @@ struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaStream_t s = nullptr;
+  spf_ctx::ScratchSlot* slot = nullptr;   // set when the memory belongs to the context's scratch cache
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -159,8 +168,44 @@ struct DevBuf {
     }
     return SPF_OK;
   }
+  // The same from the context's named scratch slot (all work of a context is ordered on its stream,
+  // so reusing the block needs no synchronisation).  Small requests and a slot that is in use go
+  // through the pool.  A cached buffer must not be take()n.
+  int alloc_cached(spf_ctx* c, const char* tag, size_t count) {
+    release();
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    if (bytes < (1u << 20) || !c->params.scratch_cache) return alloc(c->stream, count);
+    spf_ctx::ScratchSlot& sl = c->scratch[tag];
+    if (sl.busy) return alloc(c->stream, count);
+    if (sl.bytes < bytes) {
+      if (sl.p) cudaFreeAsync(sl.p, c->stream);
+      sl.p = nullptr;
+      sl.bytes = 0;
+      const size_t want = bytes + bytes / 8;                 // headroom: sizes drift between iterations
+      cudaError_t e = cudaMallocAsync(&sl.p, want, c->stream);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMallocAsync(&sl.p, bytes, c->stream);
+        if (e != cudaSuccess) {
+          sl.p = nullptr;
+          return fail(SPF_E_OOM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+        sl.bytes = bytes;
+      } else {
+        sl.bytes = want;
+      }
+    }
+    sl.busy = true;
+    slot = &sl;
+    s = c->stream;
+    n = count;
+    p = static_cast<T*>(sl.p);
+    return SPF_OK;
+  }
   void release() {
-    if (p) cudaFreeAsync(p, s);
+    if (slot) slot->busy = false;
+    else if (p) cudaFreeAsync(p, s);
+    slot = nullptr;
     p = nullptr;
     n = 0;
   }

@@ -95,9 +95,11 @@ int launch_check_rows(spf_ctx* c, const uint64_t* d_idx, uint64_t m, uint64_t n,
 // candidates (cand != NULL, one segment, all records exact) and/or the dense m x k matrix.
 // d_skip (optional device flag): when it is non-zero at run time the kernel does nothing.
 // penalty (optional, k floats, candidate mode only): candidates are formed on fl(d + penalty[j]).
+// seed (optional, m floats, candidate mode only): per point the exact distance to SOME centroid (an
+// upper bound of its minimum) — the boundary threshold starts tight instead of at +inf.
 int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, const float* C, uint32_t k,
                         uint32_t ld, float factor, const CandBuf* cand, float* dense, const int* d_skip = nullptr,
-                        const float* penalty = nullptr);
+                        const float* penalty = nullptr, const float* seed = nullptr);
 
 // ---- assign_tc.cu -------------------------------------------------------------------------
 // tcgen05 (TF32) candidate GEMM for squared-Euclidean: approximate distances with a certified

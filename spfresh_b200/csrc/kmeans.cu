@@ -150,7 +150,7 @@ int km_update(spf_kmeans* s) {
   const int world = s->comm ? s->comm->world : 1;
   DevBuf<uint64_t> d_rows;
   DevBuf<unsigned long long> keys;
-  SPF_TRY(d_rows.alloc(st, r->total));
+  SPF_TRY(d_rows.alloc_cached(c, "member_rows", r->total));
   SPF_TRY(assign_members_as_rows(r, d_rows.p));
   float* sums = reinterpret_cast<float*>(s->msg1.p);
   uint32_t* counts = reinterpret_cast<uint32_t*>(sums + (size_t)k * ld);
@@ -267,8 +267,7 @@ int spf_kmeans_step(spf_kmeans* s) {
     else SPF_TRY(launch_scale_u64_f32(c, s->gcount.p, s->lambda, s->k, s->penalty.p));
     penalty = s->penalty.p;
   }
-  if (s->last && s->iterations > 0 && !(s->flags & (SPF_KMEANS_UNSEEDED | SPF_KMEANS_BALANCED)) &&
-      s->metric == SPF_METRIC_EUCLIDEAN) {
+  if (s->last && s->iterations > 0 && !(s->flags & (SPF_KMEANS_UNSEEDED | SPF_KMEANS_BALANCED))) {
     // exact distance of every point to the NEW centroid of the slot it was nearest to
     KernelTimer t(c, "kmeans_seed");
     SPF_TRY(s->seed.alloc(st, ds->n));

@@ -286,7 +286,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) classify_kernel(ResolveDev a
         const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
         if (lex_less(od, oj, bd, bj)) { bd = od; bj = oj; }
       }
-      if (!(bd < INF)) { bd = INF; bj = 0; }   // fold identity (0, +inf): nothing was < inf
+      if (!(bd < INF)) {                        // fold identity (0, +inf): nothing was < inf
+        // (a finite producer minimum without a record at it can only come from a seed that was not
+        // the distance of a real centroid: the dense fallback decides such a row)
+        if (ma < INF) overflow = true;
+        bd = INF; bj = 0;
+      }
       best_known = bd_known = true;
     } else if (n_in == 1) {    // a single approximate element can be the argmin: it is the best
       bj = __reduce_max_sync(0xffffffffu, j_any);
@@ -805,7 +810,7 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   KernelTimer t(c, "csr");
   // row offsets = exclusive scan of member counts
   DevBuf<uint64_t> row_off, d_total;
-  SPF_TRY(row_off.alloc(st, a.m));
+  SPF_TRY(row_off.alloc_cached(c, "csr_row_off", a.m));
   SPF_TRY(d_total.alloc(st, 1));
   cub::TransformInputIterator<uint64_t, CountOp, const uint32_t*> counts(a.nmem, CountOp());
   size_t tmp_bytes = 0;
@@ -814,7 +819,7 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   KernelTimer ts(c, "csr_scan");
   SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, row_off.p, (int64_t)a.m, st));
   DevBuf<uint8_t> tmp;
-  SPF_TRY(tmp.alloc(st, tmp_bytes));
+  SPF_TRY(tmp.alloc_cached(c, "csr_scan_tmp", tmp_bytes));
   SPF_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts, row_off.p, (int64_t)a.m, st));
   c->launches += 2;
   total_kernel<<<1, 32, 0, st>>>(row_off.p, a.nmem, (uint32_t)a.m, d_total.p);
@@ -824,9 +829,9 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
   }
 
   DevBuf<uint32_t> keys, vals, keys2, vals2;
-  SPF_TRY(keys.alloc(st, total));
-  SPF_TRY(vals.alloc(st, total));
-  SPF_TRY(keys2.alloc(st, total));
+  SPF_TRY(keys.alloc_cached(c, "csr_keys", total));
+  SPF_TRY(vals.alloc_cached(c, "csr_vals", total));
+  SPF_TRY(keys2.alloc_cached(c, "csr_keys2", total));
   SPF_TRY(vals2.alloc(st, total));
   DevBuf<uint64_t> offsets;
   SPF_TRY(offsets.alloc(st, (size_t)a.k + 1));
@@ -848,7 +853,7 @@ int resolve_finish_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, CsrOut* 
     SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys2.p, vals.p, vals2.p,
                                              (int64_t)total, 0, end_bit, st));
     DevBuf<uint8_t> stmp;
-    SPF_TRY(stmp.alloc(st, sort_bytes));
+    SPF_TRY(stmp.alloc_cached(c, "csr_sort_tmp", sort_bytes));
     SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sort_bytes, keys.p, keys2.p, vals.p, vals2.p,
                                              (int64_t)total, 0, end_bit, st));
     c->launches += 4;
@@ -876,12 +881,12 @@ int resolve_begin(spf_ctx* c, uint64_t m_total, uint64_t chunk_rows, bool approx
   s->work_cap = work_cap64 > 0xffffff00ull ? 0xffffff00u : (uint32_t)work_cap64;
   int rc = SPF_OK;
   if ((chunk_rows << s->sl_shift) >= (1ull << 32)) rc = fail(SPF_E_INVALID, "assign: chunk too large");
-  if (rc >= 0) rc = s->ovf_rows.alloc(st, m_total);
+  if (rc >= 0) rc = s->ovf_rows.alloc_cached(c, "ovf_rows", m_total);
   if (rc >= 0) rc = s->ovf_count.alloc(st, 1);
-  if (rc >= 0) rc = s->sl.alloc(st, (size_t)chunk_rows << s->sl_shift);
-  if (rc >= 0) rc = s->sl_cnt.alloc(st, chunk_rows);
-  if (rc >= 0 && want_members) rc = s->memlist.alloc(st, (size_t)m_total << s->sl_shift);
-  if (rc >= 0) rc = s->work.alloc(st, s->work_cap);
+  if (rc >= 0) rc = s->sl.alloc_cached(c, "short_lists", (size_t)chunk_rows << s->sl_shift);
+  if (rc >= 0) rc = s->sl_cnt.alloc_cached(c, "short_counts", chunk_rows);
+  if (rc >= 0 && want_members) rc = s->memlist.alloc_cached(c, "member_slots", (size_t)m_total << s->sl_shift);
+  if (rc >= 0) rc = s->work.alloc_cached(c, "eval_work", s->work_cap);
   if (rc >= 0) rc = s->work_count.alloc(st, 1);
   if (rc >= 0 && cudaMemsetAsync(s->ovf_count.p, 0, sizeof(uint32_t), st) != cudaSuccess)
     rc = fail(SPF_E_CUDA, "cudaMemsetAsync failed");

@@ -1053,11 +1053,25 @@ def test_assign_l1_linf_gist_dimension_matches_oracle(spf, ctx, oracle, metric):
     cent = np.random.default_rng(960).choice(6000, 256, replace=False)
     cent[0], cent[1] = 7, 100
     ds = spf.Dataset(ctx, data)
-    check_assign(ds.assign(metric, cent).fetch(), oracle.assign(data, metric, cent))
+    ref = oracle.assign(data, metric, cent)
     gdata = gauss(3000, 960, 961)                # N(0,1): the wide boundary band of BASELINE.md 4.3
-    cent = np.random.default_rng(961).choice(3000, 300, replace=False)
+    gcent = np.random.default_rng(961).choice(3000, 300, replace=False)
     ds2 = spf.Dataset(ctx, gdata)
-    check_assign(ds2.assign(metric, cent).fetch(), oracle.assign(gdata, metric, cent))
+    gref = oracle.assign(gdata, metric, gcent)
+    try:
+        # unseeded, and with the running minimum seeded by the tensor-core squared-L2 pre-pass
+        for seed_mode in (0, 2):
+            ctx.set_param("exact_seed", seed_mode)
+            ctx.set_profiling(True)
+            check_assign(ds.assign(metric, cent).fetch(), ref)
+            assert (ctx.kernel_ms("exact_seed") > 0) == (seed_mode == 2)
+            ctx.set_profiling(False)
+            check_assign(ds2.assign(metric, gcent).fetch(), gref)
+            sub = np.random.default_rng(5).permutation(6000)[:2500]
+            check_assign(ds.assign(metric, cent, point_idx=sub).fetch(), oracle.assign(data, metric, cent, point_idx=sub))
+    finally:
+        ctx.set_profiling(False)
+        ctx.set_param("exact_seed", 1)
 
 
 @pytest.fixture(scope="module")

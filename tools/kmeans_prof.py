@@ -37,20 +37,22 @@ def run(tag, ds, init_rows, init_vec, steps=5, sum_hub=0, sum_slices=0):
             rec["parts_ms"] = {n: round(ctx.kernel_ms(n), 3) for n in names if ctx.kernel_ms(n) >= 0}
         os.write(OUT, (json.dumps(rec) + "\n").encode())
     ctx.set_profiling(False)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    for _ in range(3):
+    each = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
         sess.step()
-    e1.record(ext)
-    e1.synchronize()
-    os.write(OUT, (json.dumps({"case": tag, "steady_ms_per_iteration": e0.elapsed_time(e1) / 3}) + "\n").encode())
+        e1.record(ext)
+        e1.synchronize()
+        each.append(round(e0.elapsed_time(e1), 2))
+    os.write(OUT, (json.dumps({"case": tag, "steady_ms_each": each}) + "\n").encode())
     sess.free()
 
 
 rows = bench.make_rows(0)
 ds = s.Dataset(ctx, rows)
 ref = None
-for hub, sl in ((0, 1), (0, 0), (2048, 0), (512, 0), (2048, 2)):
+for hub, sl in ((0, 1),):
     run("1M x 128 gauss", ds, np.arange(4096, dtype=np.uint64), rows[:4096], steps=4, sum_hub=hub, sum_slices=sl)
 ds.free()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 25_000_000
@@ -59,5 +61,8 @@ ds = s.Dataset(ctx, device_ptr=x.data_ptr(), n=n, d=96)
 del x
 torch.cuda.empty_cache()
 init = np.sort(np.random.Generator(np.random.Philox(key=7)).choice(n, 4096, replace=False)).astype(np.uint64)
-for hub, sl in ((0, 1), (0, 0)):
-    run(f"{n} x 96 clustered", ds, init, ds.fetch_rows(init), steps=3, sum_hub=hub, sum_slices=sl)
+for cache in (1, 0):
+    ctx.set_param("scratch_cache", cache)
+    ctx.trim()
+    hub, sl = 0, cache
+    run(f"{n} x 96 clustered cache={cache}", ds, init, ds.fetch_rows(init), steps=3, sum_hub=hub, sum_slices=sl)
