@@ -786,12 +786,14 @@ def bench_sweep(spf, ctx, comm, rank, world, torch, dist, dev, ext, hbm_peak, wi
         ctx.set_profiling(True)
         idx.search_sharded(comm, q, TOPK, nprobe=nprobe, out=out_bufs)
         km = {nm: max(ctx.kernel_ms(nm), 0.0) for nm in ("probe", "scan", "exchange", "merge", "scan_tc_a")}
+        passes = {nm: round(max(ctx.kernel_ms("scan_tc_" + nm), 0.0), 3) for nm in ("gather", "a", "tau", "b", "flag", "refine", "fallback")}
         stream_mb = ctx.kernel_ms("scan_tc_unique_mb")
         ctx.set_profiling(False)
         scan_ms, exch_ms = max_over_ranks(torch, dist, dev, world, km["scan"], km["exchange"])
         rec = {"nprobe": nprobe, "nq": nq_total, "k": TOPK, "qps_e2e": nq_total / (ms * 1e-3), "ms_per_batch": ms,
                "scan_ms_max": scan_ms, "probe_ms": km["probe"], "exchange_ms_max": exch_ms, "merge_ms": km["merge"],
                "h2d_bytes_per_rank": int(q.nbytes), "d2h_bytes_per_rank": int(sum(o.nbytes for o in out_bufs))}
+        rec["scan_passes_ms_this_rank"] = passes
         if world > 1:
             rec["scan_ms_all_ranks"] = [round(v, 3) for v in all_ranks(torch, dist, dev, world, km["scan"])]
             sh = (ids.copy(), dists.copy(), counts.copy())
