@@ -188,6 +188,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "scratch_cache") c->params.scratch_cache = value;
   else if (s == "exact_seed") c->params.exact_seed = value;
   else if (s == "exact_one_cta") c->params.exact_one_cta = value;
+  else if (s == "exact_three_cta") c->params.exact_three_cta = value;
   else if (s == "sum_hub") c->params.sum_hub = value;
   else if (s == "sum_slices") c->params.sum_slices = value;
   else if (s == "cc_cache") c->params.cc_cache = value;

@@ -186,7 +186,10 @@ constexpr int XT_M = 128, XT_N = 128, XT_K = 16;      // points x centroids x di
 constexpr int xt_stages(int minb) { return minb == 1 ? 8 : 4; }   // one CTA per SM: room for a deeper ring
 constexpr int XT_TILE_BYTES = XT_M * XT_K * 4;        // 8 KB per operand and stage
 constexpr int XT_THREADS = 256;                       // 8 compute warps; thread 0 also issues the TMA loads
-constexpr int xt_smem(int minb) { return 2 * xt_stages(minb) * XT_TILE_BYTES + 256 + 1024; }
+// MINB (resident CTAs per SM the kernel is compiled for) also selects the shape: 1 or 2 -> 128 points x 128
+// centroids, 256 threads; 3 -> 64 points x 128 centroids, 128 threads (12 warps per SM at <= 168 registers)
+constexpr int xt_rows(int minb) { return minb == 3 ? 64 : 128; }
+constexpr int xt_smem(int minb) { return xt_stages(minb) * (xt_rows(minb) * XT_K * 4 + XT_TILE_BYTES) + 256 + 1024; }
 
 // slot (within a 128-centroid tile) held by row r of the permuted centroid copy
 __host__ __device__ inline uint32_t xt_slot_of_row(uint32_t r) { return 8u * (r & 15u) + (r >> 4); }
@@ -204,7 +207,7 @@ __global__ void xt_permute_rows_kernel(const float4* __restrict__ C, uint32_t ld
 // sub.rn.f32x2 (FADD2: both lanes IEEE round-to-nearest like the scalar FADD), the accumulator chain
 // stays scalar and in dimension order: 6 issue slots per 4 element-ops instead of 8.
 template <int METRIC, bool PACKED, int MINB>
-__global__ void __launch_bounds__(XT_THREADS, MINB)
+__global__ void __launch_bounds__(2 * xt_rows(MINB), MINB)
 assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, uint32_t m,
                         uint32_t k, uint32_t ld, float factor, CandRec* __restrict__ cand, RowInfo* __restrict__ info,
                         int cap, float* __restrict__ dense, int symmetric, const int* __restrict__ skip,
@@ -214,17 +217,20 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   // seeing a shared-memory address, or the operand loads become generic LD instead of LDS)
   extern __shared__ __align__(1024) unsigned char xt_raw[];
   constexpr int XT_STAGES = xt_stages(MINB);
+  constexpr int M = xt_rows(MINB);                 // points per CTA; a thread owns rows ty + (M / 8) i
+  constexpr int XB = M * XT_K * 4;                 // bytes of a point tile
+  constexpr uint32_t RSTEP = M / 8;
   unsigned char* smem = xt_raw;
   unsigned char* xs = smem;                                        // [XT_STAGES][128 rows][64 B]
-  unsigned char* cs = smem + XT_STAGES * XT_TILE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * XT_STAGES * XT_TILE_BYTES);
+  unsigned char* cs = smem + XT_STAGES * XB;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + XT_STAGES * (XB + XT_TILE_BYTES));
   uint64_t* empty = full + XT_STAGES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t row0 = blockIdx.x * XT_M;
+  const uint32_t row0 = blockIdx.x * M;
   const uint32_t ntile = (k + XT_N - 1) / XT_N;
   const uint32_t nkb = (ld + XT_K - 1) / XT_K;
   if (tid == 0) {
-    for (int i = 0; i < XT_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 8); }
+    for (int i = 0; i < XT_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2 * M / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -240,8 +246,8 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   auto produce = [&]() {                                // thread 0 only: one stage, if any is left
     if (pt >= ntile) return;
     tc::mbar_wait(&empty[ps], pph ^ 1);
-    tc::mbar_expect_tx(&full[ps], 2 * XT_TILE_BYTES);
-    tc::tma_load_2d(xs + ps * XT_TILE_BYTES, &map_x, &full[ps], (int)(pkb * XT_K), (int)row0);
+    tc::mbar_expect_tx(&full[ps], XB + XT_TILE_BYTES);
+    tc::tma_load_2d(xs + ps * XB, &map_x, &full[ps], (int)(pkb * XT_K), (int)row0);
     tc::tma_load_2d(cs + ps * XT_TILE_BYTES, &map_c, &full[ps], (int)(pkb * XT_K), (int)(pt * XT_N));
     if (++ps == XT_STAGES) { ps = 0; pph ^= 1; }
     if (++pkb == nkb) { pkb = 0; pt = next_tile(pt + gridDim.y); }
@@ -260,7 +266,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint32_t cnt[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const uint32_t r = row0 + ty + 16u * i;
+    const uint32_t r = row0 + ty + RSTEP * i;
     runmin[i] = (seed != nullptr && r < m) ? fminf(seed[r], INF) : INF;   // upper bound of the minimum (NaN -> +inf)
     cnt[i] = 0;
   }
@@ -275,7 +281,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     for (uint32_t kb = 0; kb < nkb; ++kb) {
       if (tid == 0) produce();
       tc::mbar_wait(&full[s], ph);
-      const unsigned char* xb = xs + s * XT_TILE_BYTES;
+      const unsigned char* xb = xs + s * XB;
       const unsigned char* cb = cs + s * XT_TILE_BYTES;
       // the four 16-byte chunks of the stage are a real loop (not unrolled): 512 metric steps per
       // iteration keep the body inside the instruction cache (fully unrolled, 17 % of the stall
@@ -292,7 +298,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const ulonglong2*>(cp + (jh * 4 + j) * 1024);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(xp + i * 1024);
+              const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(xp + i * (RSTEP * 64));
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 unsigned long long d01, d23;
@@ -318,7 +324,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const float4*>(cp + (jh * 4 + j) * 1024);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 xv = *reinterpret_cast<const float4*>(xp + i * 1024);
+            const float4 xv = *reinterpret_cast<const float4*>(xp + i * (RSTEP * 64));
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float a = acc[i][jh * 4 + j];
@@ -342,7 +348,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (dense != nullptr) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint32_t r = row0 + ty + 16u * i;
+        const uint32_t r = row0 + ty + RSTEP * i;
         if (r < m) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -376,7 +382,7 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         runmin[i] = fminf(runmin[i], tmin);
         const float rm = runmin[i];
         const float thr = __fmul_rn(rm, factor);
-        const uint32_t r = row0 + ty + 16u * i;
+        const uint32_t r = row0 + ty + RSTEP * i;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           bool hit = false;
@@ -403,17 +409,17 @@ assign_exact_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   if (cand != nullptr && tx == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint32_t r = row0 + ty + 16u * i;
+      const uint32_t r = row0 + ty + RSTEP * i;
       if (r < m) info[r] = make_uint4(cnt[i], __float_as_uint(runmin[i]), 0u, 0x7f800000u);
     }
   }
 }
 
 // 2-D map over a row-major `rows x ld` f32 matrix: boxes of 128 rows x 16 floats, SWIZZLE_64B
-int xt_make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, uint32_t ld) {
+int xt_make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
   cuuint64_t gdim[2] = {ld, rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {XT_K, XT_M};
+  cuuint32_t box[2] = {XT_K, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<tc::EncodeTiledFn>(c->tma_encode)(
       map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
@@ -423,23 +429,37 @@ int xt_make_map(spf_ctx* c, CUtensorMap* map, const float* base, uint64_t rows, 
   return SPF_OK;
 }
 
+template <int METRIC, bool PACKED, int MINB>
+int launch_xt_shape(spf_ctx* c, const float* P, uint64_t m, const float* Cperm, uint32_t k, uint32_t ld, float factor,
+                    CandRec* cand, RowInfo* info, int cap, float* dense, int symmetric, const int* d_skip, const float* penalty,
+                    const float* seed) {
+  constexpr int M = xt_rows(MINB);
+  CUtensorMap map_x, map_c;
+  SPF_TRY(xt_make_map(c, &map_x, P, m, ld, M));
+  SPF_TRY(xt_make_map(c, &map_c, Cperm, (uint64_t)round_up(k, XT_N), ld, XT_N));
+  dim3 grid((unsigned)ceil_div(m, M));
+  if (cand == nullptr) {   // dense matrix only: fill the machine even when m is small
+    const uint64_t ctiles = ceil_div(k, XT_N);
+    uint64_t want = ceil_div((uint64_t)c->sm_count * 2, grid.x);
+    grid.y = (unsigned)(want < 1 ? 1 : (want > ctiles ? ctiles : want));
+  }
+  SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                xt_smem(MINB)));
+  assign_exact_tma_kernel<METRIC, PACKED, MINB><<<grid, 2 * M, xt_smem(MINB), c->stream>>>(
+      map_x, map_c, (uint32_t)m, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, penalty, seed);
+  return check_launch(c, "assign_exact_tma_kernel");
+}
+
 template <int METRIC, bool PACKED>
 int launch_xt(spf_ctx* c, const float* P, uint64_t m, const float* Cperm, uint32_t k, uint32_t ld, float factor,
               CandRec* cand, RowInfo* info, int cap, float* dense, int symmetric, const int* d_skip, const float* penalty,
-              const float* seed, dim3 grid) {
-  CUtensorMap map_x, map_c;
-  SPF_TRY(xt_make_map(c, &map_x, P, m, ld));
-  SPF_TRY(xt_make_map(c, &map_c, Cperm, (uint64_t)round_up(k, XT_N), ld));
-  if (PACKED && ((c->params.exact_one_cta >> METRIC) & 1) != 0) {
-    SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem(1)));
-    assign_exact_tma_kernel<METRIC, PACKED, 1><<<grid, XT_THREADS, xt_smem(1), c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand,
-                                                                                     info, cap, dense, symmetric, d_skip, penalty, seed);
-    return check_launch(c, "assign_exact_tma_kernel");
-  }
-  SPF_CUDA(cudaFuncSetAttribute(assign_exact_tma_kernel<METRIC, PACKED, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem(2)));
-  assign_exact_tma_kernel<METRIC, PACKED, 2><<<grid, XT_THREADS, xt_smem(2), c->stream>>>(map_x, map_c, (uint32_t)m, k, ld, factor, cand, info,
-                                                                          cap, dense, symmetric, d_skip, penalty, seed);
-  return check_launch(c, "assign_exact_tma_kernel");
+              const float* seed) {
+  // the 64-row shape has no symmetric (tile index == row block index) mode: candidate launches only
+  if (PACKED && cand != nullptr && ((c->params.exact_three_cta >> METRIC) & 1) != 0)
+    return launch_xt_shape<METRIC, PACKED, 3>(c, P, m, Cperm, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, penalty, seed);
+  if (PACKED && ((c->params.exact_one_cta >> METRIC) & 1) != 0)
+    return launch_xt_shape<METRIC, PACKED, 1>(c, P, m, Cperm, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, penalty, seed);
+  return launch_xt_shape<METRIC, PACKED, 2>(c, P, m, Cperm, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, penalty, seed);
 }
 
 }  // namespace
@@ -472,26 +492,20 @@ int launch_assign_exact(spf_ctx* c, int metric, const float* P, uint64_t m, cons
     xt_permute_rows_kernel<<<(unsigned)ceil_div((uint64_t)kpad * ld4, 256), 256, 0, c->stream>>>(
         reinterpret_cast<const float4*>(C), ld4, k, kpad, reinterpret_cast<float4*>(cperm.p));
     SPF_TRY(check_launch(c, "xt_permute_rows_kernel"));
-    dim3 grid((unsigned)ceil_div(m, XT_M));
-    if (cand == nullptr) {   // dense matrix only: fill the machine even when m is small
-      const uint64_t ctiles = ceil_div(k, XT_N);
-      uint64_t want = ceil_div((uint64_t)c->sm_count * 2, grid.x);
-      grid.y = (unsigned)(want < 1 ? 1 : (want > ctiles ? ctiles : want));
-    }
     const bool packed = ((c->params.exact_packed >> metric) & 1) != 0;
     const float* pen = cb ? penalty : nullptr;
     const float* sd = cb ? seed : nullptr;
     switch (metric) {
       case SPF_METRIC_EUCLIDEAN:
-        return launch_xt<SPF_METRIC_EUCLIDEAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
+        return launch_xt<SPF_METRIC_EUCLIDEAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd);
       case SPF_METRIC_MANHATTAN:
         if (packed)
-          return launch_xt<SPF_METRIC_MANHATTAN, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
-        return launch_xt<SPF_METRIC_MANHATTAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
+          return launch_xt<SPF_METRIC_MANHATTAN, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd);
+        return launch_xt<SPF_METRIC_MANHATTAN, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd);
       default:
         if (packed)
-          return launch_xt<SPF_METRIC_CHEBYSHEV, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
-        return launch_xt<SPF_METRIC_CHEBYSHEV, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd, grid);
+          return launch_xt<SPF_METRIC_CHEBYSHEV, true>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd);
+        return launch_xt<SPF_METRIC_CHEBYSHEV, false>(c, P, m, cperm.p, k, ld, factor, cand, info, cap, dense, symmetric, d_skip, pen, sd);
     }
   }
   dim3 grid((unsigned)ceil_div(m, BM)), block(NTHREADS);

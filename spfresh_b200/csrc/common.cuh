@@ -73,6 +73,7 @@ struct Params {
   int sum_hub = 0;           // compute_mean: clusters of at least this many members use the deep, column-sliced launch (0: 8192)
   int sum_slices = 0;        // ... column slices per hub cluster (0: one; measured slower when > 1)
   int exact_packed = 6;      // ... bit per metric: differences of two dimensions from one packed FADD2
+  int exact_three_cta = 0;   // ... bit per metric: the packed kernel in its 64-point shape, three CTAs of 128 threads per SM
   int exact_one_cta = 2;     // ... bit per metric: the packed kernel compiled for one CTA per SM (more registers)
   int exact_seed = 1;        // Manhattan / Chebyshev: seed the running minimum from a tensor-core L2 pre-pass (0 off, 1 long rows, 2 always)
   int scratch_cache = 1;     // keep the large temporaries of assign between calls (see spf_ctx::scratch)

@@ -1030,12 +1030,13 @@ def test_assign_exact_both_kernels_match_oracle(spf, oracle, metric, n, d, k):
     cent = np.random.default_rng(n + k).choice(n, k, replace=False)
     cent[3], cent[4] = 1, n // 2
     ref = oracle.assign(data, metric, cent)
-    for mask, packed, one_cta in ((0, 0, 0), (7, 0, 0), (7, 7, 0), (7, 7, 7)):
+    for mask, packed, one_cta, three_cta in ((0, 0, 0, 0), (7, 0, 0, 0), (7, 7, 0, 0), (7, 7, 7, 0), (7, 7, 0, 7)):
         c2 = spf.Context(0)
         try:
             c2.set_param("exact_tma", mask)
             c2.set_param("exact_packed", packed)
             c2.set_param("exact_one_cta", one_cta)
+            c2.set_param("exact_three_cta", three_cta)
             c2.set_param("exact_tma_min_pairs", 1)
             c2.set_param("cc_cache", 0)
             ds = spf.Dataset(c2, data)

@@ -19,10 +19,12 @@ cent = np.random.Generator(np.random.Philox(key=7)).choice(n, 4096, replace=Fals
 ctx.set_profiling(True)
 for metric, name in ((s.METRIC_MANHATTAN, "manhattan"), (s.METRIC_CHEBYSHEV, "chebyshev")):
     ref = None
-    for tag, tma, packed, minb in (("4x4", 0, 0, 2), ("tma 8x8", 7, 0, 2), ("tma 8x8 packed", 7, 7, 2), ("tma 8x8 packed 1 CTA/SM", 7, 7, 1)):
+    for tag, tma, packed, minb in (("4x4", 0, 0, 2), ("tma 8x8", 7, 0, 2), ("tma 8x8 packed", 7, 7, 2), ("tma 8x8 packed 1 CTA/SM", 7, 7, 1), ("tma 8x8 packed 64 rows 3 CTA/SM", 7, 7, 3)):
         ctx.set_param("exact_tma", tma)
         ctx.set_param("exact_packed", packed)
         ctx.set_param("exact_one_cta", 7 if minb == 1 else 0)
+        ctx.set_param("exact_three_cta", 7 if minb == 3 else 0)
+        ctx.set_param("exact_seed", 0)
         r = ds.assign(metric, cent)
         ms = ctx.kernel_ms("assign_exact")
         f = r.fetch()
@@ -34,5 +36,5 @@ for metric, name in ((s.METRIC_MANHATTAN, "manhattan"), (s.METRIC_CHEBYSHEV, "ch
             same = bool(np.array_equal(ref.best, f.best) and np.array_equal(ref.dmin.view(np.uint32), f.dmin.view(np.uint32))
                         and np.array_equal(ref.offsets, f.offsets) and np.array_equal(ref.members, f.members))
         lane = 2.0 * n * 4096 * 960
-        print(f"{name:10s} {tag:24s} assign_exact {ms:8.2f} ms = {lane / (ms * 1e-3) / (148 * 128 * 1.965e9):.3f} of 2 lane-instr/element-op at 1965 MHz"
+        print(f"{name:10s} {tag:33s} assign_exact {ms:8.2f} ms = {lane / (ms * 1e-3) / (148 * 128 * 1.965e9):.3f} of 2 lane-instr/element-op at 1965 MHz"
               f"  identical={same}", flush=True)
