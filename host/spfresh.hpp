@@ -16,6 +16,7 @@
 // `Result::Err` / `expect` / `unwrap` panics become `spfresh::Error`.  Header-only, C++17.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -131,6 +132,7 @@ struct ChebyshevDistance : DistanceMetric {          // distance.rs:36-43
 namespace clustering {
 
 constexpr float BOUNDARY_THRESHOLD = 1.1f;   // hierarchical.rs:55
+constexpr uint32_t KMPP_BATCH = 256;          // k-means++ rounds per spf_kmpp_rounds call (one host sync per batch)
 
 enum class InitializationMethod { Random, KMeansPlusPlus };   // hierarchical.rs:13-16
 
@@ -246,15 +248,24 @@ class HierarchicalClustering {
     spf_kmpp* s = nullptr;
     check(spf_kmpp_begin(dataset_->handle(), metric(), first, &s));
     try {
-      for (size_t i = 1; i < k; ++i) {                                        // :259
-        uint64_t chosen = 0;
-        const int rc = spf_kmpp_round(s, rng->uniform01(), &chosen);          // :260-286 on the device
+      std::vector<double> draws;                                              // drawn ahead, not yet used
+      std::vector<uint64_t> rows(KMPP_BATCH);
+      size_t left = k > 0 ? k - 1 : 0;
+      while (left > 0) {                                                      // :259
+        const size_t want = std::min(left, (size_t)KMPP_BATCH);
+        while (draws.size() < want) draws.push_back(rng->uniform01());
+        uint32_t done = 0;
+        const int rc = spf_kmpp_rounds(s, draws.data(), (uint32_t)want, rows.data(), &done);   // :260-286 on the device
         check(rc);
+        for (uint32_t i = 0; i < done; ++i) clusters.emplace_back((size_t)rows[i], std::vector<uint64_t>(), 0);
+        draws.erase(draws.begin(), draws.begin() + done + (rc > 0 ? 1 : 0));  // the failing round consumed its draw too
+        left -= done;
         if (rc > 0) {                                                         // :287-290 uniform fallback
-          chosen = rng->choose_index(n);
+          const uint64_t chosen = rng->choose_index(n);
           check(spf_kmpp_push(s, chosen));
+          clusters.emplace_back((size_t)chosen, std::vector<uint64_t>(), 0);
+          left -= 1;
         }
-        clusters.emplace_back((size_t)chosen, std::vector<uint64_t>(), 0);
       }
     } catch (...) {
       spf_kmpp_free(s);

@@ -235,6 +235,13 @@ void spf_kmeans_free(spf_kmeans* s);
 int  spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** out);
 int  spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen);
 int  spf_kmpp_push(spf_kmpp* s, uint64_t row);
+/* `count` rounds (:259-291) back to back without a host round trip per round: the draws u01[0..count)
+ * are uploaded once, every round's update kernel reads the row the previous round picked from
+ * device memory, chosen[0..*done) receives the picked rows.  Returns SPF_OK with *done == count, or
+ * 1 when round *done (0-based within the batch) could not pick (its centroid is folded, the later
+ * rounds did not run, draws u01[*done+1..) are unused): the host draws uniformly, calls
+ * spf_kmpp_push() and carries on.  spf_kmpp_round() is this call with count = 1. */
+int  spf_kmpp_rounds(spf_kmpp* s, const double* u01, uint32_t count, uint64_t* chosen, uint32_t* done);
 /* Diagnostics of the last round: the f32 sum (:278) and the f64 weight total. */
 int  spf_kmpp_last_sums(const spf_kmpp* s, float* sum, double* total);
 /* Row-sharded form (one session per rank over its shard): the newest centroid
@@ -334,8 +341,9 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 
 /* Test hook: the strictly sequential f32 fold of hierarchical.rs:278 over n host values.  mode 1 is
- * the scan-based kernel the k-means++ rounds use ("kmpp_exact_sum" = 1), mode 2 the serial add
- * chain it must equal bit for bit. */
+ * the single-CTA scan kernel, mode 3 the thread-block-cluster scan (the k-means++ rounds use it for
+ * more than 16 384 elements when "kmpp_exact_sum" = 1), mode 2 the serial add chain both must equal
+ * bit for bit. */
 int spf_seq_sum_f32(spf_ctx* ctx, const float* values, uint64_t n, int mode, float* out);
 
 #if defined(__GNUC__)

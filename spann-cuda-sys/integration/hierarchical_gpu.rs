@@ -49,7 +49,8 @@ impl<'a> HierarchicalClustering<'a, f32> {
         (c1, c2)
     }
 
-    // reference :249-293 — the host keeps the RNG; one library call per round
+    // reference :249-293 — the host keeps the RNG; up to 256 rounds per library call (spf_kmpp_rounds:
+    // the draws are made ahead, the rounds run back to back on the device, one synchronisation)
     fn initialize_clusters_kmeans_plus_plus(&mut self, rng: &mut impl Rng) {
         use spann_cuda_sys::ffi;
         let g = self.gpu.as_ref().expect("GPU state");
@@ -58,14 +59,20 @@ impl<'a> HierarchicalClustering<'a, f32> {
         let mut rows = vec![first];
         let mut s = std::ptr::null_mut();
         unsafe { ffi::spf_kmpp_begin(g.ds.raw(), g.kind as i32, first as u64, &mut s) };
+        let mut draws: Vec<f64> = Vec::new();
+        let mut picked = vec![0u64; 256];
         while rows.len() < self.params.initial_k {
-            let mut chosen = 0u64;
-            let rc = unsafe { ffi::spf_kmpp_round(s, rng.random::<f64>(), &mut chosen) };
+            let want = (self.params.initial_k - rows.len()).min(256);
+            while draws.len() < want { draws.push(rng.random::<f64>()); }
+            let mut done = 0u32;
+            let rc = unsafe { ffi::spf_kmpp_rounds(s, draws.as_ptr(), want as u32, picked.as_mut_ptr(), &mut done) };
+            rows.extend(picked[..done as usize].iter().map(|&r| r as usize));
+            draws.drain(..(done as usize + (rc == 1) as usize));
             if rc == 1 {                                   // the Err arm of choose_weighted (:287-290)
-                chosen = (0..n).choose(rng).unwrap() as u64;
+                let chosen = (0..n).choose(rng).unwrap() as u64;
                 unsafe { ffi::spf_kmpp_push(s, chosen) };
+                rows.push(chosen as usize);
             }
-            rows.push(chosen as usize);
         }
         unsafe { ffi::spf_kmpp_free(s) };
         self.clusters = rows.into_iter().map(|r| Cluster { centroid_idx: Some(r), points: Vec::new(), depth: 0 }).collect();

@@ -59,6 +59,7 @@ SIGNATURES = {
     "spf_kmpp_begin": (C.c_int, [_vp, C.c_int, C.c_uint64, _vpp]),
     "spf_kmpp_round": (C.c_int, [_vp, C.c_double, _u64p]),
     "spf_kmpp_push": (C.c_int, [_vp, C.c_uint64]),
+    "spf_kmpp_rounds": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_uint32, _u64p, C.POINTER(C.c_uint32)]),
     "spf_kmpp_last_sums": (C.c_int, [_vp, _f32p, C.POINTER(C.c_double)]),
     "spf_kmpp_begin_sharded": (C.c_int, [_vp, C.c_int, _vpp]),
     "spf_kmpp_fold_vector": (C.c_int, [_vp, _vp, _f32p]),

@@ -17,6 +17,7 @@ from . import _capi as capi
 from .device import Context, Dataset
 
 BOUNDARY_THRESHOLD = 1.1   # hierarchical.rs:55
+KMPP_BATCH = 256           # k-means++ rounds per device batch (spf_kmpp_rounds): one host sync per batch
 
 
 class DistanceMetric:
@@ -170,13 +171,24 @@ class HierarchicalClustering:
         first = rng.choose_index(n)                                   # :253-255
         self.clusters.append(Cluster(int(first), np.zeros(0, np.uint64), 0))
         sess = self.dataset.kmeanspp(self._metric, first)
+        draws: List[float] = []                                       # drawn ahead, not yet used
         try:
-            for _ in range(1, k):                                     # :259
-                chosen = sess.round(rng.uniform01())                  # :260-286 on the device
-                if chosen is None:                                    # :287-290 uniform fallback
+            left = k - 1
+            while left > 0:                                           # :259
+                want = min(left, KMPP_BATCH)
+                while len(draws) < want:
+                    draws.append(rng.uniform01())
+                rows, failed = sess.rounds(draws[:want])              # :260-286 on the device, one sync per batch
+                for r in rows:
+                    self.clusters.append(Cluster(int(r), np.zeros(0, np.uint64), 0))
+                used = len(rows) + (1 if failed else 0)               # the failing round consumed its draw too
+                del draws[:used]
+                left -= len(rows)
+                if failed:                                            # :287-290 uniform fallback
                     chosen = rng.choose_index(n)
                     sess.push(chosen)
-                self.clusters.append(Cluster(int(chosen), np.zeros(0, np.uint64), 0))
+                    self.clusters.append(Cluster(int(chosen), np.zeros(0, np.uint64), 0))
+                    left -= 1
         finally:
             sess.free()
 

@@ -29,6 +29,11 @@ struct spf_kmpp {
   float last_sum = 0.f;
   double last_total = 0.0;
   float* d_vec = nullptr;    // sharded sessions: the newest centroid as an explicit vector (ld floats)
+  // batched rounds (spf_kmpp_rounds): draws, picked rows and {stop, done} stay on the device
+  double* d_u01 = nullptr;
+  uint64_t* d_chosen = nullptr;
+  int* d_ctl = nullptr;      // [0] stop flag, [1] rounds completed
+  uint32_t batch_cap = 0;
 };
 
 namespace spf {
@@ -473,8 +478,10 @@ farthest_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __rest
 template <int METRIC>
 __global__ void __launch_bounds__(PD_THREADS)
 kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const float* __restrict__ cvec, int first,
-                   float* __restrict__ mind) {
+                   float* __restrict__ mind, const uint64_t* __restrict__ d_row, const int* __restrict__ stop) {
   __shared__ PairDistSmem sm[PD_THREADS / 32];
+  if (stop && *stop) return;
+  if (d_row) cvec = X + (size_t)d_row[0] * ld;            // batched rounds: the row the previous pick wrote
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
   for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < n; base += nwarps * 32) {
@@ -495,8 +502,10 @@ constexpr int KU_ROWS = 128;
 template <int METRIC>
 __global__ void __launch_bounds__(KU_ROWS)
 kmpp_update_tiled_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const float* __restrict__ cvec, int first,
-                         float* __restrict__ mind) {
+                         float* __restrict__ mind, const uint64_t* __restrict__ d_row, const int* __restrict__ stop) {
   extern __shared__ __align__(16) float ku_smem[];
+  if (stop && *stop) return;
+  if (d_row) cvec = X + (size_t)d_row[0] * ld;            // batched rounds: the row the previous pick wrote
   const uint32_t ld4 = ld / 4, pitch4 = ld4 + 1;           // in float4 units
   float4* s_c = reinterpret_cast<float4*>(ku_smem);         // the centroid, ld4 float4
   float4* s_x = s_c + ld4;                                  // KU_ROWS x pitch4
@@ -536,15 +545,16 @@ unsigned pd_grid(spf_ctx* c, uint64_t count);
 
 // Launches the tiled kernel when the row fits its shared-memory tile, the generic one otherwise.
 template <int METRIC>
-int launch_kmpp_update(spf_ctx* c, const float* X, uint32_t ld, uint64_t n, const float* cvec, int first, float* mind) {
+int launch_kmpp_update(spf_ctx* c, const float* X, uint32_t ld, uint64_t n, const float* cvec, int first, float* mind,
+                       const uint64_t* d_row = nullptr, const int* stop = nullptr) {
   const size_t smem = ((size_t)(ld / 4) + (size_t)KU_ROWS * (ld / 4 + 1)) * sizeof(float4);
   if (smem <= 72 * 1024) {                                  // three CTAs per SM
     SPF_CUDA(cudaFuncSetAttribute(kmpp_update_tiled_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t ntiles = (n + KU_ROWS - 1) / KU_ROWS;
     const uint64_t cap = (uint64_t)c->sm_count * 3 * 4;
-    kmpp_update_tiled_kernel<METRIC><<<(unsigned)(ntiles < cap ? ntiles : cap), KU_ROWS, smem, c->stream>>>(X, ld, n, cvec, first, mind);
+    kmpp_update_tiled_kernel<METRIC><<<(unsigned)(ntiles < cap ? ntiles : cap), KU_ROWS, smem, c->stream>>>(X, ld, n, cvec, first, mind, d_row, stop);
   } else {
-    kmpp_update_kernel<METRIC><<<pd_grid(c, n), PD_THREADS, 0, c->stream>>>(X, ld, n, cvec, first, mind);
+    kmpp_update_kernel<METRIC><<<pd_grid(c, n), PD_THREADS, 0, c->stream>>>(X, ld, n, cvec, first, mind, d_row, stop);
   }
   return check_launch(c, "kmpp_update_kernel");
 }
@@ -555,8 +565,10 @@ int launch_kmpp_update(spf_ctx* c, const float* X, uint32_t ld, uint64_t n, cons
 // latency per element, not a global-memory round trip per 16 elements.
 constexpr int SEQ_TILE = 4096;       // floats per tile
 constexpr int SEQ_THREADS = 256;
-__global__ void __launch_bounds__(SEQ_THREADS) seq_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(SEQ_THREADS) seq_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out,
+                                                              const int* __restrict__ stop = nullptr) {
   __shared__ __align__(16) float buf[2][SEQ_TILE];
+  if (stop && *stop) return;
   const uint64_t ntiles = (n + SEQ_TILE - 1) / SEQ_TILE;
   auto stage = [&](uint64_t t, int b) {            // threads 1.. load tile t (the fold only reads the valid part)
     const uint64_t base = t * SEQ_TILE;
@@ -614,7 +626,8 @@ __device__ __forceinline__ FsSumm fs_compose(const FsSumm& a, const FsSumm& b) {
   return r;
 }
 
-__global__ void __launch_bounds__(FS_THREADS) seq_sum_scan_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(FS_THREADS) seq_sum_scan_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out,
+                                                                  const int* __restrict__ stop = nullptr) {
   extern __shared__ float fs_buf[];                     // FS_WINDOW + FS_WINDOW / 32 staged values
   __shared__ FsSumm s_lane[FS_THREADS];                 // per thread: its exclusive prefix inside the warp
   __shared__ FsSumm s_warp[FS_THREADS / 32];
@@ -626,6 +639,7 @@ __global__ void __launch_bounds__(FS_THREADS) seq_sum_scan_kernel(const float* _
   __shared__ int s_bad;
   const uint32_t LIMIT = 1u << 24;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (stop && *stop) return;
   if (threadIdx.x == 0) { s_pos = 0; s_acc = 0; s_bad = 0; }
   __syncthreads();
   while (true) {
@@ -792,13 +806,335 @@ __global__ void __launch_bounds__(FS_THREADS) seq_sum_scan_kernel(const float* _
 
 int launch_seq_sum_scan(spf_ctx* c, const float* v, uint64_t n, float* out) {
   SPF_CUDA(cudaFuncSetAttribute(seq_sum_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
-  seq_sum_scan_kernel<<<1, FS_THREADS, FS_SMEM, c->stream>>>(v, n, out);
+  seq_sum_scan_kernel<<<1, FS_THREADS, FS_SMEM, c->stream>>>(v, n, out, nullptr);
+  return SPF_OK;
+}
+
+// ---- the same scan over a thread-block cluster ---------------------------------------------------
+// One cluster of CS_MAXC (16, else 8) CTAs owns the fold: a window is C x 8192 elements, thread t of
+// CTA r holds 16 consecutive elements in registers.  An iteration = decode the runs for the current
+// binade, transducer scan inside the warp (shuffles), over the warps (shared memory) and over the
+// CTAs (every warp reads the C CTA summaries through distributed shared memory after ONE cluster
+// barrier), so every CTA knows the sum at the end of the window and which CTA — if any — holds the
+// first element that reaches the next binade.  Only that CTA walks its runs a second time and
+// publishes (new sum, restart position) behind a second cluster barrier.  A restart keeps the
+// window: the elements stay in registers and the ones in front of the restart position are masked
+// to +0 (the identity), so a crossing costs no memory traffic.  1 M elements: 8 windows + ~20
+// crossings = ~28 iterations of ~2 us instead of ~150 single-CTA iterations (0.54 ms -> see
+// profiles/r02_experiment_notes.md).  Same bits as the serial chain for every input; the serial
+// tail (negative / non-finite input, infinite sum) runs on CTA 0 from the current position.
+constexpr int CS_THREADS = 512;
+constexpr int CS_RUN = 16;
+constexpr int CS_SLICE = CS_THREADS * CS_RUN;
+constexpr int CS_MAXC = 16;
+constexpr int CS_WARPS = CS_THREADS / 32;
+constexpr int CS_PREFIX = 4096;      // elements folded by the plain add chain before the scan starts
+constexpr uint32_t CS_SAT = 1u << 26;
+
+// A run's transducer in 8 bytes: k[p] = sum of the rounded quotients when the run is entered with
+// parity p, saturated at 2^26 (anything >= 2^24 means "reached the next binade"; sums in front of
+// the first crossing stay exact).  The parity behind the run is (p + k[p]) & 1, so it needs no field.
+struct CsT { uint32_t k0, k1; };
+__device__ __forceinline__ CsT cs_compose(const CsT& a, const CsT& b) {   // a first, then b
+  CsT r;
+  r.k0 = min(a.k0 + ((a.k0 & 1u) ? b.k1 : b.k0), CS_SAT);
+  r.k1 = min(a.k1 + ((a.k1 & 1u) ? b.k0 : b.k1), CS_SAT);
+  return r;
+}
+__device__ __forceinline__ CsT cs_shfl_up(const CsT& a, int d) {
+  CsT l;
+  l.k0 = __shfl_up_sync(0xffffffffu, a.k0, d);
+  l.k1 = __shfl_up_sync(0xffffffffu, a.k1, d);
+  return l;
+}
+struct CsRes { unsigned long long start; uint32_t acc, pad; };
+
+__device__ __forceinline__ uint32_t cs_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cs_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cs_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cs_map(const void* p, uint32_t rank) {   // shared::cluster address of p in CTA `rank`
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint4 cs_ld128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(CS_THREADS)
+seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out, const int* __restrict__ stop) {
+  __shared__ __align__(16) float s_pre[CS_PREFIX];
+  __shared__ CsT s_warp[CS_WARPS];
+  __shared__ __align__(16) uint4 s_cta[2];                // {k0, k1, bad, -} of this CTA, by iteration parity
+  __shared__ __align__(16) CsRes s_res;
+  __shared__ unsigned long long s_cross;
+  __shared__ uint32_t s_acc0;
+  if (stop && *stop) return;                              // uniform over the cluster (batched k-means++ rounds)
+  const uint32_t LIMIT = 1u << 24;
+  const uint32_t C = cs_cluster_size(), rank = cs_cluster_rank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t W = (uint64_t)C * CS_SLICE;
+  // ---- the first CS_PREFIX elements by the plain add chain, in every CTA alike (no exchange): the
+  // sum doubles about every time the position does, so half of the ~20 binade crossings of a fold
+  // fall into this prefix and would each cost a scan iteration
+  const uint32_t npre = n < (uint64_t)CS_PREFIX ? (uint32_t)n : (uint32_t)CS_PREFIX;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)CS_PREFIX; i += CS_THREADS) s_pre[i] = i < npre ? __ldcg(v + i) : 0.0f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.0f;
+    const float4* b4 = reinterpret_cast<const float4*>(s_pre);
+    uint32_t i = 0;
+#pragma unroll 4
+    for (; i + 4 <= npre; i += 4) {
+      const float4 x = b4[i / 4];
+      acc = __fadd_rn(acc, x.x); acc = __fadd_rn(acc, x.y); acc = __fadd_rn(acc, x.z); acc = __fadd_rn(acc, x.w);
+    }
+    for (; i < npre; ++i) acc = __fadd_rn(acc, s_pre[i]);
+    s_acc0 = __float_as_uint(acc);
+  }
+  __syncthreads();
+  uint64_t wbase = 0, start = npre;
+  uint32_t accb = s_acc0, it = 0;
+  bool fallback = (accb >> 23) == 255u && (accb & 0x7fffffu);   // NaN in the prefix: the chain carries on serially
+  if (accb >> 31) fallback = true;                        // a negative sum so far: not the scan's domain
+  uint32_t cur[CS_RUN];
+  auto load_window = [&]() {
+    const uint64_t i0 = wbase + (uint64_t)rank * CS_SLICE + (uint64_t)threadIdx.x * CS_RUN;
+    if (i0 + CS_RUN <= n && (reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
+#pragma unroll
+      for (int q = 0; q < CS_RUN / 4; ++q) {
+        const uint4 x = __ldcg(reinterpret_cast<const uint4*>(v + i0) + q);
+        cur[4 * q] = x.x; cur[4 * q + 1] = x.y; cur[4 * q + 2] = x.z; cur[4 * q + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < CS_RUN; ++r) cur[r] = i0 + r < n ? __float_as_uint(__ldcg(v + i0 + r)) : 0u;
+    }
+  };
+  if (!fallback && start < n) load_window();
+  while (!fallback && start < n && (accb >> 23) != 255u) {
+    const uint32_t Ea = accb >> 23;
+    const uint32_t Eeff = Ea ? Ea : 1u;
+    const uint32_t A0 = Ea ? ((accb & 0x7fffffu) | 0x800000u) : accb;
+    const uint64_t i0 = wbase + (uint64_t)rank * CS_SLICE + (uint64_t)threadIdx.x * CS_RUN;
+    // elements in front of `start` are already in the sum: masked to +0, the identity
+    const uint32_t live = start <= i0 ? 0xffffu : (start >= i0 + CS_RUN ? 0u : (0xffffu << (uint32_t)(start - i0)) & 0xffffu);
+    // ---- my run for this binade
+    uint32_t F[CS_RUN];
+    uint32_t gt = 0, tie = 0;
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < CS_RUN; ++r) {
+      uint32_t xb = (live >> r) & 1u ? cur[r] : 0u;
+      if (xb == 0x80000000u) xb = 0u;                     // -0 counts as 0
+      if (xb > 0x7f7fffffu) bad = true;                   // negative, inf or NaN
+      const uint32_t Ex = xb >> 23;
+      const uint32_t mx = Ex ? ((xb & 0x7fffffu) | 0x800000u) : xb;
+      const uint32_t Exeff = Ex ? Ex : 1u;
+      uint32_t f = 0;
+      if (Exeff > Eeff) {
+        f = LIMIT;                                        // x alone reaches the next binade
+      } else {
+        const uint32_t sh = Eeff - Exeff;
+        if (sh <= 25u) {
+          f = mx >> sh;
+          const uint32_t rem = mx & ((1u << sh) - 1u), half = (1u << sh) >> 1;   // sh = 0: rem = 0, half = 0 -> no flag
+          gt |= (rem > half ? 1u : 0u) << r;
+          tie |= ((rem == half && sh != 0u) ? 1u : 0u) << r;
+        }
+      }
+      F[r] = f;
+    }
+    CsT me;
+    if (tie == 0) {                                       // no half-way case in the run: k does not depend on the parity
+      uint32_t K = (uint32_t)__popc(gt);
+#pragma unroll
+      for (int r = 0; r < CS_RUN; ++r) K += F[r];
+      me.k0 = me.k1 = min(K, CS_SAT);
+    } else {
+      uint32_t k[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t K = 0, par = (uint32_t)p;
+#pragma unroll
+        for (int r = 0; r < CS_RUN; ++r) {
+          const uint32_t kk = F[r] + (((tie >> r) & 1u) ? ((par + F[r]) & 1u) : ((gt >> r) & 1u));
+          K += kk;
+          par = (par + kk) & 1u;
+        }
+        k[p] = min(K, CS_SAT);
+      }
+      me.k0 = k[0]; me.k1 = k[1];
+    }
+    const bool anybad = __syncthreads_or(bad ? 1 : 0) != 0;   // also orders the previous iteration's shared reads
+    // ---- inside the warp
+    CsT inc = me;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const CsT l = cs_shfl_up(inc, d);
+      if (lane >= d) inc = cs_compose(l, inc);
+    }
+    CsT ex = cs_shfl_up(inc, 1);
+    if (lane == 0) { ex.k0 = 0; ex.k1 = 0; }
+    if (lane == 31) s_warp[warp] = inc;
+    if (threadIdx.x == 0) s_cross = ~0ull;
+    __syncthreads();
+    // ---- over the warps of the CTA (every warp repeats the 16-entry scan: no second barrier)
+    CsT winc = s_warp[lane & (CS_WARPS - 1)];
+#pragma unroll
+    for (int d = 1; d < CS_WARPS; d <<= 1) {
+      const CsT l = cs_shfl_up(winc, d);
+      if (lane >= d) winc = cs_compose(l, winc);
+    }
+    CsT wex;                                              // exclusive prefix of my warp inside the CTA
+    {
+      const int src = warp ? warp - 1 : 0;
+      wex.k0 = __shfl_sync(0xffffffffu, winc.k0, src);
+      wex.k1 = __shfl_sync(0xffffffffu, winc.k1, src);
+      if (warp == 0) { wex.k0 = 0; wex.k1 = 0; }
+    }
+    if (warp == 0 && lane == CS_WARPS - 1) s_cta[it & 1u] = make_uint4(winc.k0, winc.k1, anybad ? 1u : 0u, 0u);
+    cs_cluster_sync();
+    // ---- over the CTAs: lanes 0..C-1 of every warp read the C summaries through DSMEM
+    CsT cinc; cinc.k0 = 0; cinc.k1 = 0;
+    uint32_t cbad = 0;
+    if ((uint32_t)lane < C) {
+      const uint4 t = cs_ld128(cs_map(&s_cta[it & 1u], (uint32_t)lane));
+      cinc.k0 = t.x; cinc.k1 = t.y; cbad = t.z;
+    }
+#pragma unroll
+    for (int d = 1; d < CS_MAXC; d <<= 1) {
+      const CsT l = cs_shfl_up(cinc, d);
+      if (lane >= d) cinc = cs_compose(l, cinc);
+    }
+    if (__any_sync(0xffffffffu, cbad != 0)) { fallback = true; break; }
+    const uint32_t p0 = A0 & 1u;
+    const uint32_t kinc = p0 ? cinc.k1 : cinc.k0;         // inclusive over the CTAs 0..lane, for the actual parity
+    const uint32_t crossers = __ballot_sync(0xffffffffu, (uint32_t)lane < C && A0 + kinc >= LIMIT);
+    const uint32_t ktotal = __shfl_sync(0xffffffffu, kinc, (int)C - 1);
+    const uint32_t kpre = __shfl_sync(0xffffffffu, kinc, rank ? (int)rank - 1 : 0);
+    ++it;
+    if (crossers == 0) {                                  // the whole window stays in this binade
+      const uint32_t A = A0 + ktotal;
+      accb = A < 0x800000u ? A : ((Eeff << 23) | (A & 0x7fffffu));
+      wbase += W;
+      start = wbase;
+      if (start < n) load_window();
+      continue;
+    }
+    const uint32_t rc = (uint32_t)__ffs((int)crossers) - 1u;
+    if (rc == rank) {                                     // the first crossing is in my CTA: second walk
+      uint32_t A = A0 + (rank ? kpre : 0u);
+      A += (A & 1u) ? wex.k1 : wex.k0;
+      A = min(A, CS_SAT);
+      A += (A & 1u) ? ex.k1 : ex.k0;
+      A = min(A, CS_SAT);
+      const uint32_t mine = (A & 1u) ? me.k1 : me.k0;
+      unsigned long long mykey = ~0ull;                   // (index in the CTA, A in front of the element)
+      uint32_t myx = 0;
+      if (A < LIMIT && A + mine >= LIMIT) {
+        bool open = true;
+#pragma unroll
+        for (int r = 0; r < CS_RUN; ++r) {
+          const uint32_t kk = F[r] + (((tie >> r) & 1u) ? ((A + F[r]) & 1u) : ((gt >> r) & 1u));
+          if (open && A + kk >= LIMIT) {
+            mykey = ((unsigned long long)(threadIdx.x * CS_RUN + r) << 32) | A;
+            myx = cur[r];                                 // live: a masked element is +0 and cannot cross
+            open = false;
+          }
+          if (open) A += kk;
+        }
+        if (mykey != ~0ull) atomicMin(&s_cross, mykey);
+      }
+      __syncthreads();
+      if (mykey != ~0ull && s_cross == mykey) {           // the owner of the crossing element adds it in hardware
+        const uint32_t Ab = (uint32_t)(mykey & 0xffffffffull);
+        const float before = __uint_as_float(Ab < 0x800000u ? Ab : ((Eeff << 23) | (Ab & 0x7fffffu)));
+        CsRes t;
+        t.acc = __float_as_uint(__fadd_rn(before, __uint_as_float(myx)));
+        t.start = wbase + (uint64_t)rank * CS_SLICE + (uint32_t)(mykey >> 32) + 1;
+        t.pad = 0;
+        s_res = t;
+      }
+    }
+    cs_cluster_sync();
+    {
+      const uint4 t = cs_ld128(cs_map(&s_res, rc));
+      start = ((unsigned long long)t.y << 32) | t.x;
+      accb = t.z;
+    }
+    if (start >= wbase + W) {
+      wbase += W;
+      if (start < n) load_window();
+    }
+  }
+  cs_cluster_sync();                                      // nobody leaves while a peer may still read its shared memory
+  if (rank == 0 && threadIdx.x == 0) {
+    float acc = __uint_as_float(accb);
+    if (fallback || (accb >> 23) == 255u)
+      for (uint64_t i = start; i < n; ++i) acc = __fadd_rn(acc, v[i]);
+    out[0] = acc;
+  }
+}
+
+// cluster size the device can co-schedule (16 needs the non-portable opt-in), 0 = no cluster launch
+int seq_sum_cluster_size() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int best = 0;
+  for (int C : {CS_MAXC, 8}) {
+    if (C > 8 && cudaFuncSetAttribute(seq_sum_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C);
+    cfg.blockDim = dim3(CS_THREADS);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, seq_sum_cluster_kernel, &cfg) == cudaSuccess && ncl >= 1) { best = C; break; }
+    cudaGetLastError();
+  }
+  cached = best;
+  return best;
+}
+
+int launch_seq_sum_cluster(spf_ctx* c, const float* v, uint64_t n, float* out, const int* stop) {
+  const int C = seq_sum_cluster_size();
+  if (C == 0) return fail(SPF_E_CUDA, "thread-block clusters are not available on this device");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C);
+  cfg.blockDim = dim3(CS_THREADS);
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SPF_CUDA(cudaLaunchKernelEx(&cfg, seq_sum_cluster_kernel, v, n, out, stop));
+  return SPF_OK;
+}
+
+// the k-means++ rounds' sum: the cluster scan for long vectors, the single-CTA scan otherwise
+int launch_kmpp_sum(spf_ctx* c, const float* v, uint64_t n, float* out, const int* stop) {
+  if (n > (uint64_t)FS_WINDOW && seq_sum_cluster_size() > 0) return launch_seq_sum_cluster(c, v, n, out, stop);
+  SPF_CUDA(cudaFuncSetAttribute(seq_sum_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+  seq_sum_scan_kernel<<<1, FS_THREADS, FS_SMEM, c->stream>>>(v, n, out, stop);
   return SPF_OK;
 }
 
 // Deterministic tree sum (fast mode: picks equal the reference's only up to near-ties).
-__global__ void tree_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out) {
+__global__ void tree_sum_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out, const int* __restrict__ stop = nullptr) {
   __shared__ double sm[1024];
+  if (stop && *stop) return;
   double acc = 0.0;
   for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
   sm[threadIdx.x] = acc;
@@ -817,8 +1153,9 @@ __device__ __forceinline__ float kmpp_weight(float d, float denom) {
 // f64 block sums of the weights (rand 0.9 WeightedIndex accumulates f64 weights) + validity.
 __global__ void __launch_bounds__(256)
 kmpp_block_sums_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
-                       double* __restrict__ block_sums, int* __restrict__ bad) {
+                       double* __restrict__ block_sums, int* __restrict__ bad, const int* __restrict__ stop = nullptr) {
   __shared__ double sm[256];
+  if (stop && *stop) return;
   const float denom = fmaxf(d_sum[0], 1e-10f);
   const uint64_t b0 = (uint64_t)blockIdx.x * WBLOCK;
   double acc = 0.0;
@@ -843,94 +1180,122 @@ kmpp_block_sums_kernel(const float* __restrict__ mind, uint64_t n, const float* 
 }
 
 // cumulative_weights.partition_point(|w| w <= u) with u = u01 * total (rand 0.9 WeightedIndex).
-// The three walks (total of the block sums, the block where the cumulative sum crosses u, the
-// element inside that block) are strictly sequential f64 chains on thread 0; the other threads of
-// the block stage what it reads next in shared memory, so no step waits for global memory.
-constexpr int PICK_THREADS = 256;
-constexpr int PICK_TILE = 1024;      // block sums per staged tile
+// One CTA of 1024 threads, no serial walk over the vector: thread t adds its contiguous chunk of block
+// sums in order, the chunk sums are scanned over the CTA (f64 shuffle scan in the warp, then over the
+// 32 warp totals), the first chunk whose inclusive prefix exceeds u is walked by one thread (a chunk
+// is one block sum at 1 M rows, ~100 at 100 M), and inside the block found the 1024 weights are
+// scanned the same way.  The cumulative sums are therefore f64 sums in a fixed tree order — equal to
+// the reference's sequential f64 prefix up to its last bits (documented near-tie deviation).
+constexpr int PICK_THREADS = 1024;
+static_assert(PICK_THREADS == WBLOCK, "one thread per weight of the block that holds the crossing");
+// Device-side control of batched rounds (spf_kmpp_rounds): the draw of round `round` is read from
+// u01[], the picked row goes to chosen[] (and to res[1], where the next round's update reads it), the
+// first round whose weighted pick is impossible raises *stop and every later kernel of the batch
+// returns at once.  All pointers null: single-round mode, the draw is the kernel argument.
+struct KmppBatch {
+  const double* u01 = nullptr;
+  uint64_t* chosen = nullptr;
+  int* stop = nullptr;
+  uint32_t* done = nullptr;
+  uint32_t round = 0;
+};
+
+// inclusive f64 scan over the 1024 threads of the CTA; *total = the last thread's value, *excl = the
+// value of the thread in front (0 for the first)
+__device__ __forceinline__ double pick_scan(double x, double* s_w, double* total, double* excl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  const double up1 = __shfl_up_sync(0xffffffffu, x, 1);
+  __syncthreads();                                        // the previous scan's warp totals are consumed
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  double w = s_w[lane];                                   // 32 warps: every warp scans the totals itself
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, w, d);
+    if (lane >= d) w += y;
+  }
+  *total = __shfl_sync(0xffffffffu, w, 31);
+  const double before = __shfl_sync(0xffffffffu, w, warp ? warp - 1 : 0);
+  *excl = lane ? (warp ? before + up1 : up1) : (warp ? before : 0.0);
+  return warp ? before + x : x;
+}
+
 __global__ void __launch_bounds__(PICK_THREADS)
 kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __restrict__ d_sum,
                  const double* __restrict__ block_sums, uint64_t nblocks,
                  const int* __restrict__ bad, double u01, double target, uint64_t* __restrict__ res,
-                 double* __restrict__ d_total) {
-  __shared__ double sd[2][PICK_TILE];
-  __shared__ float sf[WBLOCK];
-  __shared__ int s_stop;
-  __shared__ double s_u, s_cum;
+                 double* __restrict__ d_total, KmppBatch bt = KmppBatch()) {
+  __shared__ double s_w[32];
+  __shared__ unsigned long long s_first;
+  __shared__ double s_cum;
   __shared__ unsigned long long s_b;
-  const uint64_t ntiles = (nblocks + PICK_TILE - 1) / PICK_TILE;
-  auto stage = [&](uint64_t t, int b) {
-    const uint64_t base = t * PICK_TILE;
-    for (uint32_t i = threadIdx.x; i < (uint32_t)PICK_TILE; i += PICK_THREADS)
-      sd[b][i] = base + i < nblocks ? block_sums[base + i] : 0.0;
-  };
-  // ---- total = block sums added in order
-  double total = 0.0;
-  if (ntiles) stage(0, 0);
-  __syncthreads();
-  for (uint64_t t = 0; t < ntiles; ++t) {
-    const int b = (int)(t & 1);
-    if (t + 1 < ntiles) stage(t + 1, b ^ 1);
+  if (bt.stop && *bt.stop) return;
+  if (bt.u01) u01 = bt.u01[bt.round];
+  // ---- chunk sums and their prefix
+  const uint64_t chunk = (nblocks + PICK_THREADS - 1) / PICK_THREADS;
+  const uint64_t c0 = (uint64_t)threadIdx.x * chunk;
+  const uint64_t c1 = c0 + chunk < nblocks ? c0 + chunk : nblocks;
+  double mine = 0.0;
+  for (uint64_t i = c0; i < c1; ++i) mine += block_sums[i];
+  if (threadIdx.x == 0) s_first = ~0ull;
+  double total, excl;
+  const double incl = pick_scan(mine, s_w, &total, &excl);
+  if (threadIdx.x == 0) d_total[0] = total;
+  if (*bad || total == 0.0 || !isfinite(total)) {         // uniform: every thread sees the same total
     if (threadIdx.x == 0) {
-      const uint64_t left = nblocks - t * PICK_TILE;
-      const uint32_t cnt = left < (uint64_t)PICK_TILE ? (uint32_t)left : (uint32_t)PICK_TILE;
-      for (uint32_t i = 0; i < cnt; ++i) total += sd[b][i];
+      res[0] = 1; res[1] = 0;
+      if (bt.stop) *bt.stop = 1;
     }
-    __syncthreads();
+    return;
   }
-  if (threadIdx.x == 0) {
-    d_total[0] = total;
-    s_stop = 0;
-    if (*bad || total == 0.0 || !isfinite(total)) { res[0] = 1; res[1] = 0; s_stop = 2; }
-    s_u = target >= 0.0 ? target : u01 * total;   // sharded pick: target already relative to this shard
-    s_cum = 0.0;
-    s_b = 0;
+  const double u = target >= 0.0 ? target : u01 * total;   // sharded pick: target already relative to this shard
+  // ---- the chunk, then the block, where the cumulative sum crosses u (the last block takes what is left)
+  if (c0 < nblocks && !(incl <= u)) atomicMin(&s_first, (unsigned long long)threadIdx.x);
+  __syncthreads();
+  const uint64_t nchunks = (nblocks + chunk - 1) / chunk;
+  const uint64_t tc = s_first == ~0ull ? nchunks - 1 : s_first;
+  if (threadIdx.x == tc) {
+    double cum = excl;                                    // everything in front of my chunk
+    uint64_t bi = c0;
+    for (; bi < nblocks; ++bi) {                          // runs past the chunk only if rounding moved the crossing
+      const double b = block_sums[bi];
+      if (bi + 1 >= nblocks || !(cum + b <= u)) break;
+      cum += b;
+    }
+    s_cum = cum;
+    s_b = bi;
+    s_first = ~0ull;
   }
   __syncthreads();
-  if (s_stop == 2) return;
-  const double u = s_u;
-  // ---- the block where the cumulative sum crosses u (the last block takes what is left)
-  if (ntiles) stage(0, 0);
-  __syncthreads();
-  for (uint64_t t = 0; t < ntiles && s_stop == 0; ++t) {
-    const int b = (int)(t & 1);
-    if (t + 1 < ntiles) stage(t + 1, b ^ 1);
-    if (threadIdx.x == 0) {
-      double cum = s_cum;
-      uint64_t bi = t * PICK_TILE;
-      const uint64_t end = bi + PICK_TILE < nblocks ? bi + PICK_TILE : nblocks;
-      for (; bi < end; ++bi) {
-        if (bi + 1 >= nblocks || !(cum + sd[b][bi - t * PICK_TILE] <= u)) { s_stop = 1; break; }
-        cum += sd[b][bi - t * PICK_TILE];
-      }
-      s_cum = cum;
-      s_b = bi;
-    }
-    __syncthreads();
-  }
   // ---- the element inside that block
   const uint64_t lo = (uint64_t)s_b * WBLOCK;
-  uint64_t hi = lo + WBLOCK;
-  if (hi > n) hi = n;
-  for (uint64_t i = lo + threadIdx.x; i < hi; i += PICK_THREADS) sf[i - lo] = mind[i];
+  const double cum0 = s_cum;
+  const float denom = fmaxf(d_sum[0], 1e-10f);
+  const uint64_t i = lo + threadIdx.x;
+  const double w = i < n ? (double)kmpp_weight(mind[i], denom) : 0.0;
+  double tot2, ex2;
+  const double e = cum0 + pick_scan(w, s_w, &tot2, &ex2);
+  if (i + 1 < n && !(e <= u)) atomicMin(&s_first, (unsigned long long)i);
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const float denom = fmaxf(d_sum[0], 1e-10f);
-  double cum = s_cum;
   uint64_t idx = n - 1;
-  bool found = false;
-  for (uint64_t i = lo; i < hi && i + 1 < n; ++i) {
-    cum += (double)kmpp_weight(sf[i - lo], denom);
-    if (!(cum <= u)) { idx = i; found = true; break; }
-  }
-  if (!found) {       // rounding pushed the crossing into a later block: continue sequentially
-    for (uint64_t i = hi; i + 1 < n; ++i) {
-      cum += (double)kmpp_weight(mind[i], denom);
-      if (!(cum <= u)) { idx = i; break; }
+  if (s_first != ~0ull) {
+    idx = s_first;
+  } else {                 // rounding pushed the crossing into a later block: continue sequentially
+    double cum = cum0 + tot2;
+    for (uint64_t j = lo + WBLOCK; j + 1 < n; ++j) {
+      cum += (double)kmpp_weight(mind[j], denom);
+      if (!(cum <= u)) { idx = j; break; }
     }
   }
   res[0] = 0;
   res[1] = idx;
+  if (bt.chosen) { bt.chosen[bt.round] = idx; *bt.done = bt.round + 1u; }
 }
 
 template <typename F>
@@ -1236,7 +1601,7 @@ int spf_distance_pairs(spf_ctx* c, int metric, const float* a, const float* b, u
 // 2 = serial chain.  Both must return the same bits for any input.
 int spf_seq_sum_f32(spf_ctx* c, const float* values, uint64_t n, int mode, float* out) {
   if (!c || !out || (n && !values)) return fail(SPF_E_INVALID, "spf_seq_sum_f32: NULL argument");
-  if (mode != 1 && mode != 2) return fail(SPF_E_INVALID, "mode must be 1 (scan) or 2 (serial)");
+  if (mode < 1 || mode > 3) return fail(SPF_E_INVALID, "mode must be 1 (scan), 2 (serial) or 3 (cluster scan)");
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
@@ -1247,6 +1612,7 @@ int spf_seq_sum_f32(spf_ctx* c, const float* values, uint64_t n, int mode, float
   {
     KernelTimer t(c, "seq_sum");
     if (mode == 1) SPF_TRY(launch_seq_sum_scan(c, d_v.p, n, d_out.p));
+    else if (mode == 3) SPF_TRY(launch_seq_sum_cluster(c, d_v.p, n, d_out.p, nullptr));
     else seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(d_v.p, n, d_out.p);
     SPF_TRY(check_launch(c, "seq_sum kernel"));
   }
@@ -1286,51 +1652,101 @@ int spf_kmpp_begin(spf_dataset* ds, int metric, uint64_t first_row, spf_kmpp** o
   });
 }
 
+// `count` rounds of hierarchical.rs:259-291 back to back on the device: the row a round picks is read
+// by the next round's update kernel from device memory, so the host synchronises once per batch.
+static int kmpp_rounds_locked(spf_kmpp* s, const double* u01, uint32_t count, uint64_t* chosen, uint32_t* done) {
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  cudaStream_t st = c->stream;
+  const uint64_t n = ds->n;
+  if (count > s->batch_cap) {
+    if (s->d_u01) cudaFree(s->d_u01);
+    if (s->d_chosen) cudaFree(s->d_chosen);
+    s->d_u01 = nullptr; s->d_chosen = nullptr; s->batch_cap = 0;
+    const uint32_t cap = count < 64u ? 64u : count;
+    if (cudaMalloc((void**)&s->d_u01, (size_t)cap * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&s->d_chosen, (size_t)cap * sizeof(uint64_t)) != cudaSuccess)
+      return fail(SPF_E_OOM, "k-means++ batch buffers: out of device memory");
+    s->batch_cap = cap;
+  }
+  if (!s->d_ctl && cudaMalloc((void**)&s->d_ctl, 2 * sizeof(int)) != cudaSuccess)
+    return fail(SPF_E_OOM, "k-means++ batch buffers: out of device memory");
+  SPF_CUDA(cudaMemcpyAsync(s->d_u01, u01, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemsetAsync(s->d_ctl, 0, 2 * sizeof(int), st));
+  SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
+  const uint64_t res0[2] = {0, s->newest};
+  SPF_CUDA(cudaMemcpyAsync(s->res, res0, sizeof(res0), cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+  const int* stop = s->d_ctl;
+  for (uint32_t r = 0; r < count; ++r) {
+    {
+      KernelTimer t(c, "kmpp_update");
+      const int first = (s->rounds == 0 && r == 0) ? 1 : 0;
+      SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
+        return launch_kmpp_update<decltype(M)::value>(c, ds->x, ds->ld, n, ds->x, first, s->mind, s->res + 1, stop);
+      }));
+    }
+    {
+      KernelTimer t(c, "kmpp_sum");
+      if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_kmpp_sum(c, s->mind, n, s->d_sum, stop));
+      else if (c->params.kmpp_exact_sum == 2) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum, stop);
+      else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum, stop);
+      SPF_TRY(check_launch(c, "kmpp sum kernel"));
+    }
+    {
+      KernelTimer t(c, "kmpp_pick");
+      kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->bad, stop);
+      SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
+      KmppBatch bt;
+      bt.u01 = s->d_u01; bt.chosen = s->d_chosen; bt.stop = s->d_ctl; bt.done = reinterpret_cast<uint32_t*>(s->d_ctl + 1); bt.round = r;
+      kmpp_pick_kernel<<<1, PICK_THREADS, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, -1.0, s->res, s->d_total, bt);
+      SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
+    }
+  }
+  int ctl[2] = {0, 0};
+  SPF_CUDA(cudaMemcpyAsync(ctl, s->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(chosen, s->d_chosen, (size_t)count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(&s->last_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(&s->last_total, s->d_total, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  const uint32_t ok = (uint32_t)ctl[1];
+  const bool failed = ctl[0] != 0;
+  *done = ok;
+  s->rounds += ok + (failed ? 1u : 0u);                   // the failing round folded its centroid too
+  if (ok) s->newest = chosen[ok - 1];
+  s->pending = !failed;
+  return failed ? 1 : SPF_OK;
+}
+
 int spf_kmpp_round(spf_kmpp* s, double u01, uint64_t* chosen) {
   return spf::guarded([&]() -> int {
   if (!s || !chosen) return fail(SPF_E_INVALID, "spf_kmpp_round: NULL argument");
   if (!(u01 >= 0.0 && u01 < 1.0)) return fail(SPF_E_INVALID, "u01 must be in [0,1)");
   if (!s->pending) return fail(SPF_E_STATE, "previous round needs spf_kmpp_push() before the next one");
-  spf_dataset* ds = s->ds;
-  spf_ctx* c = ds->ctx;
+  spf_ctx* c = s->ds->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
-  cudaStream_t st = c->stream;
-  const uint64_t n = ds->n;
-  {
-    KernelTimer t(c, "kmpp_update");
-    const int first = s->rounds == 0 ? 1 : 0;
-    SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
-      return launch_kmpp_update<decltype(M)::value>(c, ds->x, ds->ld, n, ds->x + (size_t)s->newest * ds->ld, first, s->mind);
-    }));
-  }
-  s->rounds += 1;
-  s->pending = false;
-  {
-    KernelTimer t(c, "kmpp_sum");
-    if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_seq_sum_scan(c, s->mind, n, s->d_sum));
-    else if (c->params.kmpp_exact_sum == 2) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
-    else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
-    SPF_TRY(check_launch(c, "kmpp sum kernel"));
-  }
-  {
-    KernelTimer t(c, "kmpp_pick");
-    SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
-    kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->bad);
-    SPF_TRY(check_launch(c, "kmpp_block_sums_kernel"));
-    kmpp_pick_kernel<<<1, PICK_THREADS, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, u01, -1.0, s->res, s->d_total);
-    SPF_TRY(check_launch(c, "kmpp_pick_kernel"));
-  }
-  uint64_t res[2] = {0, 0};
-  SPF_CUDA(cudaMemcpyAsync(res, s->res, sizeof(res), cudaMemcpyDeviceToHost, st));
-  SPF_CUDA(cudaMemcpyAsync(&s->last_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
-  SPF_CUDA(cudaMemcpyAsync(&s->last_total, s->d_total, sizeof(double), cudaMemcpyDeviceToHost, st));
-  SPF_CUDA(cudaStreamSynchronize(st));
-  if (res[0] != 0) return 1;   // weighted pick impossible → host draws uniformly and pushes
-  s->newest = res[1];
-  s->pending = true;
-  *chosen = res[1];
+  uint32_t done = 0;
+  uint64_t row = 0;
+  const int rc = kmpp_rounds_locked(s, &u01, 1, &row, &done);
+  if (rc != SPF_OK) return rc;   // 1: weighted pick impossible → host draws uniformly and pushes
+  *chosen = row;
   return SPF_OK;
+  });
+}
+
+int spf_kmpp_rounds(spf_kmpp* s, const double* u01, uint32_t count, uint64_t* chosen, uint32_t* done) {
+  return spf::guarded([&]() -> int {
+  if (!s || !u01 || !chosen || !done) return fail(SPF_E_INVALID, "spf_kmpp_rounds: NULL argument");
+  *done = 0;
+  if (count == 0) return SPF_OK;
+  if (count > (1u << 20)) return fail(SPF_E_INVALID, "spf_kmpp_rounds: at most 2^20 rounds per call");
+  for (uint32_t i = 0; i < count; ++i)
+    if (!(u01[i] >= 0.0 && u01[i] < 1.0)) return fail(SPF_E_INVALID, "u01 must be in [0,1)");
+  if (!s->pending) return fail(SPF_E_STATE, "previous round needs spf_kmpp_push() before the next one");
+  spf_ctx* c = s->ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  return kmpp_rounds_locked(s, u01, count, chosen, done);
   });
 }
 
@@ -1362,7 +1778,7 @@ int spf_kmpp_fold_vector(spf_kmpp* s, const float* centroid, float* local_sum) {
     return launch_kmpp_update<decltype(M)::value>(c, ds->x, ds->ld, n, s->d_vec, first, s->mind);
   }));
   s->rounds += 1;
-  if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_seq_sum_scan(c, s->mind, n, s->d_sum));
+  if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_kmpp_sum(c, s->mind, n, s->d_sum, nullptr));
     else if (c->params.kmpp_exact_sum == 2) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, s->d_sum);
   else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, s->d_sum);
   SPF_TRY(check_launch(c, "kmpp sum kernel"));
@@ -1440,6 +1856,9 @@ void spf_kmpp_free(spf_kmpp* s) {
   if (s->d_sum) cudaFree(s->d_sum);
   if (s->d_total) cudaFree(s->d_total);
   if (s->d_vec) cudaFree(s->d_vec);
+  if (s->d_u01) cudaFree(s->d_u01);
+  if (s->d_chosen) cudaFree(s->d_chosen);
+  if (s->d_ctl) cudaFree(s->d_ctl);
   delete s;
 }
 

@@ -307,6 +307,17 @@ class KmppSession:
         rc = check(lib().spf_kmpp_round(self._h, float(u01), C.byref(out)))
         return None if rc == 1 else int(out.value)
 
+    def rounds(self, u01):
+        """spf_kmpp_rounds: len(u01) rounds on the device with one host synchronisation.  Returns
+        (rows picked, failed): failed means round len(rows) could not pick (caller draws uniformly,
+        calls push and carries on with the unused draws)."""
+        u = np.ascontiguousarray(u01, np.float64)
+        chosen = np.zeros(u.size, np.uint64)
+        done = C.c_uint32()
+        rc = check(lib().spf_kmpp_rounds(self._h, u.ctypes.data_as(C.POINTER(C.c_double)), u.size,
+                                         chosen.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(done)))
+        return chosen[:int(done.value)].copy(), rc == 1
+
     def push(self, row: int):
         check(lib().spf_kmpp_push(self._h, int(row)))
 

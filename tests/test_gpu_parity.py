@@ -465,6 +465,50 @@ def test_kmeanspp_matches_oracle(spf, ctx, oracle, metric):
     sess.free()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_kmeanspp_batched_rounds_match_oracle(spf, ctx, oracle, metric):
+    """spf_kmpp_rounds (device-resident rounds, one host sync per batch, cluster scan for the fold:
+    40 000 rows > one single-CTA window) against the oracle and against single rounds."""
+    data = clustered(40000, 24, 30, 9)
+    k = 41
+    u = np.random.default_rng(50 + metric).random(k - 1)
+    ref, fell = oracle.kmeanspp(data, metric, k, 77, u)
+    assert not fell.any()
+    ds = spf.Dataset(ctx, data)
+    sess = ds.kmeanspp(metric, 77)
+    got = [77]
+    for lo, hi in ((0, 1), (1, 18), (18, 40)):             # uneven batches, the state carries over
+        rows, failed = sess.rounds(u[lo:hi])
+        assert not failed and len(rows) == hi - lo
+        got += [int(r) for r in rows]
+    sums = sess.last_sums()
+    sess.free()
+    assert got == ref.tolist()
+    one = ds.kmeanspp(metric, 77)
+    for r in range(k - 1):
+        assert one.round(u[r]) == got[r + 1]
+    assert one.last_sums() == sums
+    one.free()
+    # degenerate: identical points -> the first round of the batch cannot pick, nothing else runs
+    same = np.ones((64, 4), np.float32)
+    sess = spf.Dataset(ctx, same).kmeanspp(0, 3)
+    rows, failed = sess.rounds([0.5, 0.25, 0.125])
+    assert failed and len(rows) == 0
+    sess.push(9)
+    rows, failed = sess.rounds([0.25])
+    assert failed and len(rows) == 0
+    sess.free()
+    # a batch that fails in the middle: two distinct points, the third round has all-zero weights
+    two = np.concatenate([np.zeros((40, 4), np.float32), np.ones((40, 4), np.float32)])
+    sess = spf.Dataset(ctx, two).kmeanspp(0, 0)
+    rows, failed = sess.rounds([0.5, 0.5, 0.5, 0.5])
+    assert failed and len(rows) == 1 and rows[0] >= 40
+    sess.push(5)
+    rows, failed = sess.rounds([0.3])
+    assert failed and len(rows) == 0
+    sess.free()
+
+
 def test_sequential_sum_scan_is_bit_exact(spf, ctx):
     """hierarchical.rs:278 is a strictly sequential f32 fold.  The scan-based kernel (two-state
     transducers per binade) must return the bits of the serial add chain and of numpy's sequential
@@ -492,10 +536,13 @@ def test_sequential_sum_scan_is_bit_exact(spf, ctx):
             want = np.cumsum(v, dtype=np.float32)[-1] if v.size else np.float32(0.0)
         serial = ctx.seq_sum_f32(v, 2)
         scan = ctx.seq_sum_f32(v, 1)
+        cluster = ctx.seq_sum_f32(v, 3)                    # thread-block-cluster scan (the k-means++ rounds' kernel)
         assert np.array_equal(np.array([serial]).view(np.uint32), np.array([want]).view(np.uint32)) or \
             (np.isnan(serial) and np.isnan(want)), (i, serial, want)
         assert np.array_equal(np.array([scan]).view(np.uint32), np.array([serial]).view(np.uint32)) or \
             (np.isnan(scan) and np.isnan(serial)), (i, v.size, scan, serial)
+        assert np.array_equal(np.array([cluster]).view(np.uint32), np.array([serial]).view(np.uint32)) or \
+            (np.isnan(cluster) and np.isnan(serial)), (i, v.size, cluster, serial)
 
 
 # ----------------------------------------------------------------------------------------------

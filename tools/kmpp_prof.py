@@ -27,3 +27,22 @@ for i in range(int(sys.argv[2]) if len(sys.argv) > 2 else 4):
         print(i, r, {n: round(cur[n] - prev[n], 4) for n in prev}, f"call {dt:.3f} ms", flush=True)
     prev = cur
 sess.free()
+
+# batched rounds (spf_kmpp_rounds): no host round trip per round
+ctx.set_profiling(False)
+sess = ds.kmeanspp(0, 12345)
+u = np.random.Generator(np.random.Philox(key=9)).random(1024)
+sess.rounds(u[:8])
+for cnt in (64, 256, 512):
+    t0 = time.perf_counter()
+    rows_, failed = sess.rounds(u[:cnt])
+    dt = (time.perf_counter() - t0) * 1e3
+    print(f"batch of {cnt}: {dt:.2f} ms = {dt / cnt:.4f} ms per round, failed={failed}", flush=True)
+sess.free()
+import ctypes as C  # noqa: E402
+for mode, name in ((1, "single-CTA scan"), (3, "cluster scan"), (2, "serial chain")):
+    v = np.random.default_rng(1).random(1_000_000, dtype=np.float32) * 300
+    ctx.set_profiling(True)
+    ctx.seq_sum_f32(v, mode)
+    ctx.seq_sum_f32(v, mode)
+    print(name, "1M elements:", round(ctx.kernel_ms("seq_sum"), 4), "ms", flush=True)
