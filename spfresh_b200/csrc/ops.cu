@@ -859,18 +859,33 @@ __device__ __forceinline__ uint32_t cs_map(const void* p, uint32_t rank) {   // 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
   return r;
 }
-__device__ __forceinline__ uint4 cs_ld128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-  return v;
+// 16 bytes into a peer CTA's shared memory; the peer's mbarrier counts them (complete_tx): the data is
+// visible to whoever observes the phase flip with acquire.cluster — no cluster barrier, no MEMBAR.GPU
+__device__ __forceinline__ void cs_send16(uint32_t remote_dst, uint4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               :: "r"(remote_dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void cs_bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cs_bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  }
 }
 
 __global__ void __launch_bounds__(CS_THREADS)
-seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out, const int* __restrict__ stop) {
+seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out, const int* __restrict__ stop,
+                       unsigned long long* __restrict__ dbg) {
   __shared__ __align__(16) float s_pre[CS_PREFIX];
   __shared__ CsT s_warp[CS_WARPS];
-  __shared__ __align__(16) uint4 s_cta[2];                // {k0, k1, bad, -} of this CTA, by iteration parity
-  __shared__ __align__(16) CsRes s_res;
+  __shared__ __align__(16) uint4 s_in[2][CS_MAXC];        // {k0, k1, bad, -} of every CTA, by iteration parity
+  __shared__ __align__(16) uint4 s_resin[2];              // {start lo, start hi, acc, -} from the crossing CTA
+  __shared__ __align__(8) uint64_t s_bar[2], s_rbar[2];   // complete_tx barriers of the two exchanges
   __shared__ unsigned long long s_cross;
   __shared__ uint32_t s_acc0;
   if (stop && *stop) return;                              // uniform over the cluster (batched k-means++ rounds)
@@ -878,6 +893,11 @@ seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restric
   const uint32_t C = cs_cluster_size(), rank = cs_cluster_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t W = (uint64_t)C * CS_SLICE;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&s_bar[0], 1); tc::mbar_init(&s_bar[1], 1); tc::mbar_init(&s_rbar[0], 1); tc::mbar_init(&s_rbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cs_cluster_sync();                                      // every CTA's barriers exist before anybody sends
   // ---- the first CS_PREFIX elements by the plain add chain, in every CTA alike (no exchange): the
   // sum doubles about every time the position does, so half of the ~20 binade crossings of a fold
   // fall into this prefix and would each cost a scan iteration
@@ -898,7 +918,7 @@ seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restric
   }
   __syncthreads();
   uint64_t wbase = 0, start = npre;
-  uint32_t accb = s_acc0, it = 0;
+  uint32_t accb = s_acc0, it = 0, xit = 0;                // exchanges so far: summaries / crossing results
   bool fallback = (accb >> 23) == 255u && (accb & 0x7fffffu);   // NaN in the prefix: the chain carries on serially
   if (accb >> 31) fallback = true;                        // a negative sum so far: not the scan's domain
   uint32_t cur[CS_RUN];
@@ -916,7 +936,9 @@ seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restric
     }
   };
   if (!fallback && start < n) load_window();
+  if (dbg && rank == 0 && threadIdx.x == 0) { dbg[0] = C; dbg[2] = clock64(); }
   while (!fallback && start < n && (accb >> 23) != 255u) {
+    if (dbg && rank == 0 && threadIdx.x == 0 && it < 60u) { dbg[3 + 2 * it] = clock64(); dbg[4 + 2 * it] = start; }
     const uint32_t Ea = accb >> 23;
     const uint32_t Eeff = Ea ? Ea : 1u;
     const uint32_t A0 = Ea ? ((accb & 0x7fffffu) | 0x800000u) : accb;
@@ -997,13 +1019,20 @@ seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restric
       wex.k1 = __shfl_sync(0xffffffffu, winc.k1, src);
       if (warp == 0) { wex.k0 = 0; wex.k1 = 0; }
     }
-    if (warp == 0 && lane == CS_WARPS - 1) s_cta[it & 1u] = make_uint4(winc.k0, winc.k1, anybad ? 1u : 0u, 0u);
-    cs_cluster_sync();
-    // ---- over the CTAs: lanes 0..C-1 of every warp read the C summaries through DSMEM
+    // ---- over the CTAs: warp 0 sends this CTA's summary to every CTA (lane r -> CTA r, 16 bytes counted by
+    // the receiver's barrier); every warp then reads the C summaries from its own shared memory
+    if (warp == 0) {
+      const uint32_t tk0 = __shfl_sync(0xffffffffu, winc.k0, CS_WARPS - 1), tk1 = __shfl_sync(0xffffffffu, winc.k1, CS_WARPS - 1);
+      if (lane == 0) cs_bar_expect(&s_bar[it & 1u], C * 16u);
+      if ((uint32_t)lane < C)
+        cs_send16(cs_map(&s_in[it & 1u][rank], (uint32_t)lane), make_uint4(tk0, tk1, anybad ? 1u : 0u, 0u),
+                  cs_map(&s_bar[it & 1u], (uint32_t)lane));
+    }
+    cs_bar_wait(&s_bar[it & 1u], (it >> 1) & 1u);
     CsT cinc; cinc.k0 = 0; cinc.k1 = 0;
     uint32_t cbad = 0;
     if ((uint32_t)lane < C) {
-      const uint4 t = cs_ld128(cs_map(&s_cta[it & 1u], (uint32_t)lane));
+      const uint4 t = s_in[it & 1u][lane];
       cinc.k0 = t.x; cinc.k1 = t.y; cbad = t.z;
     }
 #pragma unroll
@@ -1054,25 +1083,27 @@ seq_sum_cluster_kernel(const float* __restrict__ v, uint64_t n, float* __restric
       if (mykey != ~0ull && s_cross == mykey) {           // the owner of the crossing element adds it in hardware
         const uint32_t Ab = (uint32_t)(mykey & 0xffffffffull);
         const float before = __uint_as_float(Ab < 0x800000u ? Ab : ((Eeff << 23) | (Ab & 0x7fffffu)));
-        CsRes t;
-        t.acc = __float_as_uint(__fadd_rn(before, __uint_as_float(myx)));
-        t.start = wbase + (uint64_t)rank * CS_SLICE + (uint32_t)(mykey >> 32) + 1;
-        t.pad = 0;
-        s_res = t;
+        const unsigned long long st = wbase + (uint64_t)rank * CS_SLICE + (uint32_t)(mykey >> 32) + 1;
+        const uint4 t = make_uint4((uint32_t)st, (uint32_t)(st >> 32), __float_as_uint(__fadd_rn(before, __uint_as_float(myx))), 0u);
+        for (uint32_t r = 0; r < C; ++r)                  // (new sum, restart position) to every CTA
+          cs_send16(cs_map(&s_resin[xit & 1u], r), t, cs_map(&s_rbar[xit & 1u], r));
       }
     }
-    cs_cluster_sync();
+    if (threadIdx.x == 0) cs_bar_expect(&s_rbar[xit & 1u], 16u);
+    cs_bar_wait(&s_rbar[xit & 1u], (xit >> 1) & 1u);
     {
-      const uint4 t = cs_ld128(cs_map(&s_res, rc));
+      const uint4 t = s_resin[xit & 1u];
       start = ((unsigned long long)t.y << 32) | t.x;
       accb = t.z;
     }
+    ++xit;
     if (start >= wbase + W) {
       wbase += W;
       if (start < n) load_window();
     }
   }
   cs_cluster_sync();                                      // nobody leaves while a peer may still read its shared memory
+  if (dbg && rank == 0 && threadIdx.x == 0) { dbg[1] = it; if (it < 60u) dbg[3 + 2 * it] = clock64(); }
   if (rank == 0 && threadIdx.x == 0) {
     float acc = __uint_as_float(accb);
     if (fallback || (accb >> 23) == 255u)
@@ -1086,7 +1117,9 @@ int seq_sum_cluster_size() {
   static int cached = -1;
   if (cached >= 0) return cached;
   int best = 0;
+  const char* force = getenv("SPF_SEQSUM_CLUSTER");        // experiments: force the cluster size (8 or 16)
   for (int C : {CS_MAXC, 8}) {
+    if (force && atoi(force) != C) continue;
     if (C > 8 && cudaFuncSetAttribute(seq_sum_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
       cudaGetLastError();
       continue;
@@ -1107,7 +1140,7 @@ int seq_sum_cluster_size() {
   return best;
 }
 
-int launch_seq_sum_cluster(spf_ctx* c, const float* v, uint64_t n, float* out, const int* stop) {
+int launch_seq_sum_cluster(spf_ctx* c, const float* v, uint64_t n, float* out, const int* stop, unsigned long long* dbg = nullptr) {
   const int C = seq_sum_cluster_size();
   if (C == 0) return fail(SPF_E_CUDA, "thread-block clusters are not available on this device");
   cudaLaunchConfig_t cfg = {};
@@ -1119,7 +1152,7 @@ int launch_seq_sum_cluster(spf_ctx* c, const float* v, uint64_t n, float* out, c
   at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  SPF_CUDA(cudaLaunchKernelEx(&cfg, seq_sum_cluster_kernel, v, n, out, stop));
+  SPF_CUDA(cudaLaunchKernelEx(&cfg, seq_sum_cluster_kernel, v, n, out, stop, dbg));
   return SPF_OK;
 }
 
@@ -1612,7 +1645,23 @@ int spf_seq_sum_f32(spf_ctx* c, const float* values, uint64_t n, int mode, float
   {
     KernelTimer t(c, "seq_sum");
     if (mode == 1) SPF_TRY(launch_seq_sum_scan(c, d_v.p, n, d_out.p));
-    else if (mode == 3) SPF_TRY(launch_seq_sum_cluster(c, d_v.p, n, d_out.p, nullptr));
+    else if (mode == 3) {
+      DevBuf<unsigned long long> d_dbg;
+      const bool dbg = getenv("SPF_SEQSUM_DEBUG") != nullptr;   // iteration count and clocks of the cluster scan on stderr
+      if (dbg) {
+        SPF_TRY(d_dbg.alloc(st, 128));
+        SPF_CUDA(cudaMemsetAsync(d_dbg.p, 0, 128 * sizeof(unsigned long long), st));
+      }
+      SPF_TRY(launch_seq_sum_cluster(c, d_v.p, n, d_out.p, nullptr, dbg ? d_dbg.p : nullptr));
+      if (dbg) {
+        unsigned long long h[128];
+        SPF_CUDA(cudaMemcpyAsync(h, d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        SPF_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "seq_sum_cluster: C=%llu iterations=%llu prefix=%llu cyc;", h[0], h[1], h[3] - h[2]);
+        for (unsigned i = 0; i < h[1] && i < 60; ++i) fprintf(stderr, " [%llu]%llu", h[4 + 2 * i], h[5 + 2 * i] - h[3 + 2 * i]);
+        fprintf(stderr, "\n");
+      }
+    }
     else seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(d_v.p, n, d_out.p);
     SPF_TRY(check_launch(c, "seq_sum kernel"));
   }
