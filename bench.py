@@ -436,6 +436,35 @@ def main():
         h2d_ms = min(h2d_ms, (time.perf_counter() - t0) * 1e3)
     del xdev
     torch.cuda.empty_cache()
+    # the same step with ORDINARY heap memory on both sides (what the reference's ndarray callers hold):
+    # the library stages it through its pinned ring with worker threads; rank 0 only, wall clock
+    pageable = None
+    if rank == 0:
+        pg_best, pg_dmin = np.empty(N_ROWS, np.uint32), np.empty(N_ROWS, np.float32)
+        pg_mem = np.zeros(members_cap["buf"].size, np.uint64)
+        from spfresh_b200._capi import check, lib, ptr
+
+        def step_pageable():
+            d2, r = spf.Dataset.assign_from_host(ctx, rows_np, spf.METRIC_EUCLIDEAN, cent)
+            check(lib().spf_assign_fetch(r.handle, ptr(pg_best), ptr(pg_dmin), ptr(out_off), ptr(pg_mem)))
+            r.free()
+            d2.free()
+        times = {}
+        for name, flag in (("staging_ring", 0), ("driver_staged", 1)):
+            ctx.set_param("no_host_staging", flag)
+            step_pageable()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                step_pageable()
+            times[name] = (time.perf_counter() - t0) / 3 * 1e3
+        ctx.set_param("no_host_staging", 0)
+        pageable = {"value": N_ROWS / (times["staging_ring"] * 1e-3), "unit": "points/s",
+                    "ms_per_step": times["staging_ring"], "ms_per_step_driver_staged": times["driver_staged"],
+                    "same_results_as_pinned": bool(np.array_equal(pg_best, out_best) and
+                                                   np.array_equal(pg_dmin.view(np.uint32), out_dmin.view(np.uint32))),
+                    "note": "rows, best, dmin and member lists in ordinary (pageable) numpy arrays; worker threads copy "
+                            "4 MB blocks through 12 pinned slots in both directions (assign_api.cu: staged_upload / "
+                            "staged_download); driver_staged = the same call with cudaMemcpyAsync on the heap pointers"}
 
     # ---- one full row-sharded k-means iteration, device resident (spf_kmeans): assign + update_centroids,
     # the two exchanges of the update as NCCL all-gathers on the library's stream -----------------------
@@ -549,7 +578,8 @@ def main():
                     "raw_h2d_ms": h2d_ms, "raw_h2d_gbs": N_ROWS * DIM * 4 / (h2d_ms * 1e-3) / 1e9,
                     "note": "spf_assign_host overlaps the chunked upload with the kernels; the step is bound by the "
                             "PCIe copy of the rows (raw_h2d_ms, measured here with all ranks copying at once) plus the "
-                            "device -> host fetch of the CSR"},
+                            "device -> host fetch of the CSR",
+                    "pageable_host_buffers": pageable},
             "gpu_launches": int(launches),
             "host_numa": numa,
             "roofline": roofline,

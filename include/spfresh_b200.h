@@ -337,6 +337,7 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
  * "scan_list_major" (0 query-major, 1 automatic, 2 list-major), "scan_tc" (tensor-core candidate
  * scan: 0 never, 1 automatic, 2 whenever supported), "scan_tc_bucket" (candidates per query, 0 =
  * automatic: 256, or 1024 for d > 256), "scan_tc_tau_probes" (0 = all), "scan_tc_cmax_mb" (budget for the one-pass variant, 0 = two GEMM passes), "force_exact", "tc_min_k", "tc_min_m",
+ * "no_host_staging" (1: pageable host buffers are handed to cudaMemcpyAsync instead of the library's threaded pinned staging ring),
  * "kmpp_exact_sum" (1: sequential f32 sum by scan, 2: by the serial add chain — same bits; 0: tree sum), "cc_matrix_max_k". */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 

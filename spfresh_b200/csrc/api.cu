@@ -100,6 +100,10 @@ void spf_ctx_destroy(spf_ctx* c) {
   if (c->cc_cache.cc) cudaFree(c->cc_cache.cc);
   if (c->cc_cache.C) cudaFree(c->cc_cache.C);
   if (c->cc_cache.same) cudaFree(c->cc_cache.same);
+  if (c->stage.base) {
+    cudaFreeHost(c->stage.base);
+    for (cudaEvent_t e : c->stage.ev) if (e) cudaEventDestroy(e);
+  }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->aux_ev[0]) cudaEventDestroy(c->aux_ev[0]);
@@ -181,6 +185,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
+  else if (s == "no_host_staging") c->params.no_host_staging = value;
   else if (s == "cc_matrix_max_k") c->params.cc_matrix_max_k = value;
   else if (s == "exact_tma") c->params.exact_tma = value;
   else if (s == "exact_tma_min_pairs") c->params.exact_tma_min_pairs = value;
@@ -235,6 +240,17 @@ int spf_dataset_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, ui
   SPF_TRY(spf::dataset_alloc(c, n, d, &ds));
   std::lock_guard<std::mutex> lk(c->mu);
   cudaError_t e = cudaSuccess;
+  if ((size_t)n * d * sizeof(float) >= (8u << 20) && spf::host_pointer_is_pageable(rows) && !c->params.no_host_staging) {
+    // ordinary heap memory: threaded staging through the pinned ring instead of the driver's one-thread path
+    const int rc = spf::staged_upload(c, rows, n, d, row_stride, ds->x, ds->ld, n, c->stream, [](uint64_t) { return SPF_OK; });
+    if (rc == SPF_OK) e = cudaStreamSynchronize(c->stream);
+    if (rc != SPF_OK || e != cudaSuccess) {
+      spf_dataset_free(ds);
+      return rc != SPF_OK ? rc : fail(SPF_E_CUDA, "dataset upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = ds;
+    return SPF_OK;
+  }
   if (ds->ld != d) e = cudaMemsetAsync(ds->x, 0, (size_t)n * ds->ld * sizeof(float), c->stream);
   if (e == cudaSuccess)
     e = cudaMemcpy2DAsync(ds->x, (size_t)ds->ld * sizeof(float), rows, (size_t)row_stride * sizeof(float),

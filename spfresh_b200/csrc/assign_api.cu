@@ -1,6 +1,9 @@
 // assign_api.cu — spf_assign: the batched replacement of
 // HierarchicalClustering::assign_points_to_clusters (src/clustering/hierarchical.rs:295-364).
 #include <string.h>
+#include <atomic>
+#include <functional>
+#include <thread>
 
 #include <vector>
 
@@ -56,6 +59,166 @@ int dataset_prep(spf_dataset* ds) {
   SPF_TRY(launch_row_prep(ds->ctx, ds->x, ds->ld, nullptr, ds->n, ds->xtf, ds->xnorm, ds->xres));
   ds->prepped = true;
   return SPF_OK;
+}
+
+// ---- pageable host buffers -------------------------------------------------------------------------
+// cudaMemcpyAsync from ordinary heap memory is staged by the driver on one thread.  The reference's
+// callers hold ndarray views (heap memory), so the host-facing entry points stage such buffers
+// themselves: worker threads copy 4 MB blocks into a ring of pinned slots (rows already in the padded
+// device pitch), the calling thread hands every filled slot to the copy engine in block order and
+// launches a chunk's kernels as soon as its last block is queued.
+bool host_pointer_is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+int stage_ring(spf_ctx* c) {
+  if (c->stage.base) return SPF_OK;
+  SPF_CUDA(cudaHostAlloc((void**)&c->stage.base, spf_ctx::HostStage::SLOTS * spf_ctx::HostStage::SLOT_BYTES, cudaHostAllocDefault));
+  for (cudaEvent_t& e : c->stage.ev) SPF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return SPF_OK;
+}
+
+int stage_threads() {
+  const unsigned hc = std::thread::hardware_concurrency();
+  unsigned t = hc ? hc / 4 : 4;
+  if (t < 2) t = 2;
+  if (t > 8) t = 8;
+  return (int)t;
+}
+
+struct StageBlock { uint64_t r0; uint32_t rows; uint32_t chunk; bool last_in_chunk; };
+
+// rows [0, n) of a pageable row-major host matrix -> dst (pitch ld floats, zero padded) on `copy`;
+// after_chunk(ci) runs on the calling thread right after chunk ci's last block is queued.
+int staged_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride, float* dst, uint32_t ld,
+                  uint64_t chunk_rows, cudaStream_t copy, const std::function<int(uint64_t)>& after_chunk) {
+  constexpr int SLOTS = spf_ctx::HostStage::SLOTS;
+  constexpr size_t SLOT_BYTES = spf_ctx::HostStage::SLOT_BYTES;
+  SPF_TRY(stage_ring(c));
+  const size_t row_bytes = (size_t)ld * sizeof(float);
+  if (row_bytes > SLOT_BYTES) return fail(SPF_E_INVALID, "row too long for the staging ring");
+  const uint32_t brows = (uint32_t)(SLOT_BYTES / row_bytes);
+  std::vector<StageBlock> blocks;
+  for (uint64_t c0 = 0, ci = 0; c0 < n; c0 += chunk_rows, ++ci) {
+    const uint64_t c1 = c0 + chunk_rows < n ? c0 + chunk_rows : n;
+    for (uint64_t r = c0; r < c1; r += brows) {
+      const uint32_t nr = (uint32_t)(c1 - r < brows ? c1 - r : brows);
+      blocks.push_back({r, nr, (uint32_t)ci, r + nr == c1});
+    }
+  }
+  const size_t nb = blocks.size();
+  std::vector<std::atomic<int>> filled(nb);
+  for (auto& f : filled) f.store(0, std::memory_order_relaxed);
+  std::atomic<size_t> next{0}, submitted{0};
+  std::atomic<int> err{0};
+  const int device = c->device;
+  auto worker = [&]() {
+    cudaSetDevice(device);
+    for (;;) {
+      const size_t b = next.fetch_add(1);
+      if (b >= nb || err.load()) return;
+      const int slot = (int)(b % SLOTS);
+      if (b >= (size_t)SLOTS) {                            // the slot's previous block must have left it
+        while (submitted.load(std::memory_order_acquire) < b - SLOTS + 1) {
+          if (err.load()) return;
+          std::this_thread::yield();
+        }
+        if (cudaEventSynchronize(c->stage.ev[slot]) != cudaSuccess) { err.store(1); return; }
+      }
+      const StageBlock& blk = blocks[b];
+      uint8_t* out = c->stage.base + (size_t)slot * SLOT_BYTES;
+      const float* src = rows + blk.r0 * row_stride;
+      if (ld == d && row_stride == d) {
+        memcpy(out, src, (size_t)blk.rows * row_bytes);
+      } else {
+        for (uint32_t r = 0; r < blk.rows; ++r) {
+          float* o = reinterpret_cast<float*>(out + (size_t)r * row_bytes);
+          memcpy(o, src + (size_t)r * row_stride, (size_t)d * sizeof(float));
+          for (uint32_t j = d; j < ld; ++j) o[j] = 0.0f;
+        }
+      }
+      filled[b].store(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  const int nt = stage_threads();
+  for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+  int rc = SPF_OK;
+  for (size_t b = 0; b < nb && rc == SPF_OK; ++b) {
+    while (!filled[b].load(std::memory_order_acquire)) {
+      if (err.load()) { rc = fail(SPF_E_CUDA, "staged upload: a worker failed"); break; }
+      std::this_thread::yield();
+    }
+    if (rc != SPF_OK) break;
+    const int slot = (int)(b % SLOTS);
+    const StageBlock& blk = blocks[b];
+    cudaError_t e = cudaMemcpyAsync(dst + blk.r0 * ld, c->stage.base + (size_t)slot * SLOT_BYTES, (size_t)blk.rows * row_bytes,
+                                    cudaMemcpyHostToDevice, copy);
+    if (e == cudaSuccess) e = cudaEventRecord(c->stage.ev[slot], copy);
+    if (e != cudaSuccess) { rc = fail(SPF_E_CUDA, "staged upload: %s", cudaGetErrorString(e)); break; }
+    submitted.store(b + 1, std::memory_order_release);
+    if (blk.last_in_chunk) rc = after_chunk(blk.chunk);
+  }
+  if (rc != SPF_OK) err.store(1);
+  for (auto& t : pool) t.join();
+  return rc;
+}
+
+// device -> pageable host through the same ring: the copy engine fills slots, workers copy them out
+int staged_download(spf_ctx* c, void* host, const void* dev, size_t bytes, cudaStream_t st) {
+  constexpr int SLOTS = spf_ctx::HostStage::SLOTS;
+  constexpr size_t SLOT_BYTES = spf_ctx::HostStage::SLOT_BYTES;
+  if (bytes == 0) return SPF_OK;
+  SPF_TRY(stage_ring(c));
+  const size_t nb = (bytes + SLOT_BYTES - 1) / SLOT_BYTES;
+  std::atomic<size_t> queued{0}, next{0};
+  std::vector<std::atomic<int>> drained(nb);
+  for (auto& f : drained) f.store(0, std::memory_order_relaxed);
+  std::atomic<int> err{0};
+  const int device = c->device;
+  auto worker = [&]() {
+    cudaSetDevice(device);
+    for (;;) {
+      const size_t b = next.fetch_add(1);
+      if (b >= nb || err.load()) return;
+      while (queued.load(std::memory_order_acquire) < b + 1) {
+        if (err.load()) return;
+        std::this_thread::yield();
+      }
+      const int slot = (int)(b % SLOTS);
+      if (cudaEventSynchronize(c->stage.ev[slot]) != cudaSuccess) { err.store(1); return; }
+      const size_t off = b * SLOT_BYTES, len = bytes - off < SLOT_BYTES ? bytes - off : SLOT_BYTES;
+      memcpy((uint8_t*)host + off, c->stage.base + (size_t)slot * SLOT_BYTES, len);
+      drained[b].store(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  const int nt = stage_threads();
+  for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+  int rc = SPF_OK;
+  for (size_t b = 0; b < nb; ++b) {
+    const int slot = (int)(b % SLOTS);
+    if (b >= (size_t)SLOTS)
+      while (!drained[b - SLOTS].load(std::memory_order_acquire)) {
+        if (err.load()) break;
+        std::this_thread::yield();
+      }
+    if (err.load()) { rc = fail(SPF_E_CUDA, "staged download: a worker failed"); break; }
+    const size_t off = b * SLOT_BYTES, len = bytes - off < SLOT_BYTES ? bytes - off : SLOT_BYTES;
+    cudaError_t e = cudaMemcpyAsync(c->stage.base + (size_t)slot * SLOT_BYTES, (const uint8_t*)dev + off, len, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(c->stage.ev[slot], st);
+    if (e != cudaSuccess) { rc = fail(SPF_E_CUDA, "staged download: %s", cudaGetErrorString(e)); break; }
+    queued.store(b + 1, std::memory_order_release);
+  }
+  if (rc != SPF_OK) err.store(1);
+  for (auto& t : pool) t.join();
+  if (rc == SPF_OK && err.load()) rc = fail(SPF_E_CUDA, "staged download: a worker failed");
+  return rc;
 }
 
 }  // namespace spf
@@ -479,29 +642,35 @@ int spf_assign_host(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint6
     cudaStreamWaitEvent(c->copy_stream, e0, 0);
     cudaEventDestroy(e0);
   }
-  for (uint64_t ci = 0; ci < nchunks; ++ci) {
+  auto compute_chunk = [&](uint64_t ci) -> int {          // the chunk's kernels follow its upload by one event
     const uint64_t r0 = ci * a.chunk_rows;
     const uint64_t mc = (n - r0) < a.chunk_rows ? (n - r0) : a.chunk_rows;
-    float* dst = ds->x + r0 * ld;
-    const float* src = rows + r0 * row_stride;
-    if (ld == d && row_stride == d) {
-      SPF_CUDA(cudaMemcpyAsync(dst, src, (size_t)mc * d * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
-    } else {
-      if (ld != d) SPF_CUDA(cudaMemsetAsync(dst, 0, (size_t)mc * ld * sizeof(float), c->copy_stream));
-      SPF_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)row_stride * sizeof(float),
-                                 (size_t)d * sizeof(float), (size_t)mc, cudaMemcpyHostToDevice, c->copy_stream));
-    }
     SPF_CUDA(cudaEventCreateWithFlags(&evs[ci], cudaEventDisableTiming));
     SPF_CUDA(cudaEventRecord(evs[ci], c->copy_stream));
-  }
-  for (uint64_t ci = 0; ci < nchunks; ++ci) {
-    const uint64_t r0 = ci * a.chunk_rows;
-    const uint64_t mc = (n - r0) < a.chunk_rows ? (n - r0) : a.chunk_rows;
     SPF_CUDA(cudaStreamWaitEvent(st, evs[ci], 0));
     if (a.use_tc)
       SPF_TRY(launch_row_prep(c, ds->x + r0 * ld, ld, nullptr, mc, ds->xtf + r0 * ld, ds->xnorm + r0, ds->xres + r0));
-    SPF_TRY(assign_rows(a, ds->x + r0 * ld, a.use_tc ? ds->xtf + r0 * ld : nullptr,
-                        a.use_tc ? ds->xnorm + r0 : nullptr, a.use_tc ? ds->xres + r0 : nullptr, r0, mc));
+    return assign_rows(a, ds->x + r0 * ld, a.use_tc ? ds->xtf + r0 * ld : nullptr,
+                       a.use_tc ? ds->xnorm + r0 : nullptr, a.use_tc ? ds->xres + r0 : nullptr, r0, mc);
+  };
+  if (host_pointer_is_pageable(rows) && !c->params.no_host_staging) {
+    // ordinary heap memory (what the reference's callers hold): threaded staging through pinned slots
+    SPF_TRY(staged_upload(c, rows, n, d, row_stride, ds->x, ld, a.chunk_rows, c->copy_stream, compute_chunk));
+  } else {
+    for (uint64_t ci = 0; ci < nchunks; ++ci) {
+      const uint64_t r0 = ci * a.chunk_rows;
+      const uint64_t mc = (n - r0) < a.chunk_rows ? (n - r0) : a.chunk_rows;
+      float* dst = ds->x + r0 * ld;
+      const float* src = rows + r0 * row_stride;
+      if (ld == d && row_stride == d) {
+        SPF_CUDA(cudaMemcpyAsync(dst, src, (size_t)mc * d * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+      } else {
+        if (ld != d) SPF_CUDA(cudaMemsetAsync(dst, 0, (size_t)mc * ld * sizeof(float), c->copy_stream));
+        SPF_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)row_stride * sizeof(float),
+                                   (size_t)d * sizeof(float), (size_t)mc, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      SPF_TRY(compute_chunk(ci));
+    }
   }
   SPF_CUDA(cudaStreamSynchronize(c->copy_stream));   // `rows` is not read after the call returns
   SPF_TRY(assign_finish(a, ds->x, ds->xnorm, ds->xres, nullptr, out));
@@ -525,8 +694,17 @@ int spf_assign_fetch(const spf_assign_result* r, uint32_t* best, float* dmin, ui
   std::lock_guard<std::mutex> lk(c->mu);
   SPF_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  if (best) SPF_CUDA(cudaMemcpyAsync(best, r->best, r->m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  if (dmin) SPF_CUDA(cudaMemcpyAsync(dmin, r->dmin, r->m * sizeof(float), cudaMemcpyDeviceToHost, st));
+  // pinned destinations: plain asynchronous copies; ordinary heap memory: through the staging ring
+  auto d2h = [&](void* host, const void* dev, size_t bytes) -> int {
+    if (bytes >= (8u << 20) && host_pointer_is_pageable(host) && !c->params.no_host_staging) {
+      SPF_CUDA(cudaStreamSynchronize(st));                 // the ring's events are shared: drain what is queued first
+      return staged_download(c, host, dev, bytes, st);
+    }
+    SPF_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+    return SPF_OK;
+  };
+  if (best) SPF_TRY(d2h(best, r->best, r->m * sizeof(uint32_t)));
+  if (dmin) SPF_TRY(d2h(dmin, r->dmin, r->m * sizeof(float)));
   if ((offsets || members) && !r->has_csr)
     return fail(SPF_E_STATE, "the result was computed with SPF_ASSIGN_NO_CSR");
   if (offsets)
@@ -535,7 +713,7 @@ int spf_assign_fetch(const spf_assign_result* r, uint32_t* best, float* dmin, ui
   if (members && r->total) {
     SPF_TRY(rows.alloc(st, r->total));
     SPF_TRY(assign_members_as_rows(r, rows.p));
-    SPF_CUDA(cudaMemcpyAsync(members, rows.p, r->total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SPF_TRY(d2h(members, rows.p, r->total * sizeof(uint64_t)));
   }
   SPF_CUDA(cudaStreamSynchronize(st));
   return SPF_OK;

@@ -61,6 +61,7 @@ struct Params {
   int force_exact = 0;       // 1: never use the tcgen05 candidate GEMM
   int tc_min_k = 64;         // use the tensor path only when k >= this
   int tc_min_m = 1024;       // ... and m >= this
+  int no_host_staging = 0;   // 1: pageable host buffers go to cudaMemcpyAsync directly (driver-staged), for comparison
   int kmpp_exact_sum = 1;    // 1: sequential f32 sum (bit-parity with the reference)
   int cc_matrix_max_k = 16384;  // precompute the k x k centroid-centroid matrix up to this k
   int scan_threads = 256;
@@ -117,6 +118,15 @@ struct spf_ctx {
   // iteration (single iterations of 300 ms were measured at 1.8 s).  Freed by spf_ctx_trim / destroy.
   struct ScratchSlot { void* p = nullptr; size_t bytes = 0; bool busy = false; };
   std::map<std::string, ScratchSlot> scratch;
+  // Pinned staging ring for PAGEABLE host buffers (the reference hands ndarray views, i.e. ordinary
+  // heap memory): worker threads copy blocks into the ring, the copy engine drains it
+  // (assign_api.cu: staged_upload / staged_download).  Allocated on first use, freed with the context.
+  struct HostStage {
+    static constexpr int SLOTS = 12;
+    static constexpr size_t SLOT_BYTES = 4u << 20;
+    uint8_t* base = nullptr;
+    cudaEvent_t ev[SLOTS] = {};
+  } stage;
 };
 
 struct spf_dataset {

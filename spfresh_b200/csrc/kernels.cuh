@@ -1,5 +1,7 @@
 // kernels.cuh — internal launch interface between the translation units of libspfresh_b200.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace spf {
@@ -219,5 +221,11 @@ int dataset_alloc(spf_ctx* c, uint64_t n, uint32_t d, spf_dataset** out);   // a
 int dataset_prep_alloc(spf_dataset* ds);
 int dataset_prep(spf_dataset* ds);   // rounded copy + norms of all rows, once per dataset
 int assign_members_as_rows(const spf_assign_result* r, uint64_t* d_out);   // positions → dataset rows
+
+// pageable host buffers through the context's pinned staging ring (assign_api.cu)
+bool host_pointer_is_pageable(const void* p);
+int staged_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_t row_stride, float* dst, uint32_t ld,
+                  uint64_t chunk_rows, cudaStream_t copy, const std::function<int(uint64_t)>& after_chunk);
+int staged_download(spf_ctx* c, void* host, const void* dev, size_t bytes, cudaStream_t st);
 
 }  // namespace spf

@@ -271,6 +271,36 @@ def test_assign_host_streamed_matches_oracle(spf, oracle, metric):
         c2.close()
 
 
+def test_pageable_host_buffers_go_through_the_staging_ring(spf):
+    """Ordinary heap memory (what the reference's ndarray callers hold) is staged by worker threads
+    through the context's pinned ring (more blocks than slots: the ring wraps), in both directions;
+    results equal the driver-staged copies bit for bit."""
+    rng = np.random.default_rng(21)
+    wide = rng.standard_normal((260_000, 68), dtype=np.float32)
+    data = wide[:, :66]                                # stride 68 > d = 66, ld = 68: rows re-pitched by the workers
+    cent = rng.choice(data.shape[0], 64, replace=False)
+    got = {}
+    for staging in (1, 0):
+        c2 = spf.Context(0)
+        try:
+            c2.set_param("no_host_staging", 0 if staging else 1)
+            ds0 = spf.Dataset(c2, data)                # spf_dataset_upload, 68 MB
+            pick = rng.choice(data.shape[0], 5000, replace=False)
+            assert np.array_equal(ds0.fetch_rows(pick), data[pick])
+            ds0.free()
+            ds, res = spf.Dataset.assign_from_host(c2, data, 0, cent, boundary_factor=1.3)
+            f = res.fetch()                            # members: tens of MB into pageable numpy arrays
+            assert f.members.nbytes > (8 << 20)
+            got[staging] = f
+            res.free()
+            ds.free()
+        finally:
+            c2.close()
+    a, b = got[1], got[0]
+    assert np.array_equal(a.best, b.best) and np.array_equal(a.dmin.view(np.uint32), b.dmin.view(np.uint32))
+    assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.members, b.members)
+
+
 @pytest.mark.parametrize("metric", METRICS)
 def test_sharded_build_step_matches_oracle_shards(spf, oracle, metric):
     """§8(e) build: three row shards on one GPU exchanging partial sums / medoid candidates
