@@ -76,6 +76,30 @@ int comm_alltoall(spf_ctx* c, const spf_comm* comm, const void* send, void* recv
   return SPF_OK;
 }
 
+int comm_allreduce_min_f32(spf_ctx* c, const spf_comm* comm, float* buf, size_t count) {
+  if (!comm || comm->world == 1 || count == 0) return SPF_OK;
+  const NcclApi* api = nccl_api();
+  if (!api) return SPF_E_CUDA;
+  SPF_NCCL(api, api->AllReduce(buf, buf, count, ncclFloat32, ncclMin, comm->nccl, c->stream));
+  return SPF_OK;
+}
+
+int comm_group_start(const spf_comm* comm) {
+  if (!comm || comm->world == 1) return SPF_OK;
+  const NcclApi* api = nccl_api();
+  if (!api) return SPF_E_CUDA;
+  SPF_NCCL(api, api->GroupStart());
+  return SPF_OK;
+}
+
+int comm_group_end(const spf_comm* comm) {
+  if (!comm || comm->world == 1) return SPF_OK;
+  const NcclApi* api = nccl_api();
+  if (!api) return SPF_E_CUDA;
+  SPF_NCCL(api, api->GroupEnd());
+  return SPF_OK;
+}
+
 }  // namespace spf
 
 using namespace spf;

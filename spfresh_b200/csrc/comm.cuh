@@ -45,5 +45,11 @@ int comm_allgather(spf_ctx* c, const spf_comm* comm, const void* send, void* rec
 // Personalised exchange: rank r sends bytes [p * chunk, (p+1) * chunk) of `send` to rank p and
 // receives rank p's chunk for r into recv[p * chunk ...).
 int comm_alltoall(spf_ctx* c, const spf_comm* comm, const void* send, void* recv, size_t chunk);
+// In-place element-wise minimum of `count` floats over the ranks (no-op for one rank).
+int comm_allreduce_min_f32(spf_ctx* c, const spf_comm* comm, float* buf, size_t count);
+// Several exchanges issued between start and end travel as ONE aggregated NCCL operation (one launch
+// instead of one per call).  No-ops for one rank.
+int comm_group_start(const spf_comm* comm);
+int comm_group_end(const spf_comm* comm);
 
 }  // namespace spf

@@ -4,6 +4,8 @@
 
 #include "common.cuh"
 
+struct spf_comm;
+
 namespace spf {
 
 // Candidate records written by the assign kernels.  A record (32 bytes, one HBM sector) covers the
@@ -197,6 +199,12 @@ struct ScanTcCall {
   uint64_t nq;
   uint8_t* qflag;                  // nq, out
   bool is_probe = false;           // the centroid probe (names of the timers only)
+  // list-sharded search: the certified bound on every query's K-th distance is min-reduced over the
+  // ranks before the candidates are flagged (a rank that holds none of a query's near lists would
+  // otherwise refine against its own, much looser bound).  Every rank runs exactly one reduction
+  // per scan, whatever path it takes (search.cu: search_scan).
+  const spf_comm* comm = nullptr;
+  bool* bound_exchanged = nullptr;
 };
 int scan_tc_run(spf_ctx* c, const ScanTcCall& call);
 // Dense tensor-core centroid probe for 32 < nprobe <= 1024, nlists <= 4096: TF32 s of every query

@@ -36,6 +36,7 @@
 //              double-buffered 2 x 256 column accumulator, 32 columns per tcgen05.ld
 #include <cub/cub.cuh>
 
+#include "comm.cuh"
 #include "tc_ptx.cuh"
 
 namespace spf {
@@ -592,6 +593,30 @@ __global__ void __launch_bounds__(256) tau_kernel(TauArgs a) {
     a.qbound[q] = (fmaf(-2.0f, kth, qn) + E) + slop;
     a.qflag[q] = hopeless ? 1 : 0;
   }
+}
+
+// List-sharded search: qbound (this rank's certified bound on the query's K-th distance) is
+// min-reduced over the ranks; the flagging threshold then follows from the global bound B exactly
+// like the pruning threshold does: a candidate matters only if d_ref <= B, and d_ref >= |q|^2 - 2 s - E
+// (E of THIS rank's vectors), i.e. only if s >= (|q|^2 - E - B) / 2.
+__global__ void bound_sanitize_kernel(float* __restrict__ qbound, uint64_t nq) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && !(qbound[q] == qbound[q])) qbound[q] = __int_as_float(0x7f800000);   // NaN never enters the reduction
+}
+__global__ void bound_tighten_kernel(const float* __restrict__ qbound, const float* __restrict__ qnorm,
+                                     const float* __restrict__ qres, const float* __restrict__ vstat, uint32_t ld,
+                                     uint64_t nq, float* __restrict__ qthr) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const float INF = __int_as_float(0x7f800000);
+  const float th = qthr[q];
+  if (!(th < INF)) return;                                 // hopeless query or NaN pruning threshold: stays closed
+  const float qn = qnorm[q];
+  const float cnmax = vstat[0], dcmax = vstat[1];
+  const float E = tc_err_bound(qn, qres[q], cnmax, dcmax, ld);
+  const float slop = 1e-6f * (qn + cnmax) + 1e-30f;
+  const float by_global = 0.5f * ((qn - E) - qbound[q]) - slop;
+  if (by_global > th) qthr[q] = by_global;
 }
 
 // Tiles of every unit rank (from its sort key = 0xffffffff - groups of the list).
@@ -1171,6 +1196,15 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
       ta.thr = s.thr; ta.vstat = side.vstat; ta.qthr = qthr.p; ta.qbound = qbound.p; ta.qflag = call.qflag;
       tau_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(ta);
       SPF_TRY(check_launch(c, "tau_kernel"));
+    }
+    if (call.comm && !call.is_probe) {
+      KernelTimer t(c, "scan_tc_bound_exchange");
+      bound_sanitize_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(qbound.p, nq);
+      SPF_TRY(check_launch(c, "bound_sanitize_kernel"));
+      SPF_TRY(comm_allreduce_min_f32(c, call.comm, qbound.p, nq));
+      if (call.bound_exchanged) *call.bound_exchanged = true;
+      bound_tighten_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(qbound.p, qnorm.p, qres.p, side.vstat, ld, nq, qthr.p);
+      SPF_TRY(check_launch(c, "bound_tighten_kernel"));
     }
     if (keep_cmax) {
       // group refinement: queue the (pair, group) items whose chunk maximum passes, evaluate them exactly

@@ -1180,10 +1180,26 @@ static int search_probe(spf_index* idx, const float* Qp, uint64_t nq, uint32_t n
 
 static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k, uint32_t nprobe, uint32_t* probe,
                        const float* thr, const uint32_t* seqbase, uint64_t* o_ids, float* o_dists, uint32_t* o_counts,
-                       unsigned long long* o_keys, unsigned long long* o_slots, unsigned long long* d_bytes) {
+                       unsigned long long* o_keys, unsigned long long* o_slots, unsigned long long* d_bytes,
+                       const spf_comm* comm = nullptr) {
   spf_ctx* c = idx->ctx;
   cudaStream_t st = c->stream;
   const uint32_t ld = idx->ld, d = idx->d, nlists = idx->nlists;
+  // list-sharded search: exactly one min-reduction of the per-query bound per scan on every rank.  The
+  // tensor scan does it behind its tau pass; a rank on any other path (or without probed lists)
+  // contributes +inf here at the end.
+  bool bound_exchanged = false;
+  struct BoundGuard {
+    spf_ctx* c; const spf_comm* comm; uint64_t nq; bool* done; int rc = SPF_OK;
+    int finish() {
+      if (!comm || comm->world == 1 || *done) return SPF_OK;
+      *done = true;
+      DevBuf<float> inf;
+      SPF_TRY(inf.alloc(c->stream, nq));
+      SPF_CUDA(cudaMemsetAsync(inf.p, 0x7f, nq * sizeof(float), c->stream));   // 0x7f7f7f7f: a huge finite float
+      return comm_allreduce_min_f32(c, comm, inf.p, nq);
+    }
+  } bound_guard{c, comm, nq, &bound_exchanged};
   ScanArgs a;
   a.vecs = idx->vecs; a.slot_ids = idx->slot_ids; a.grp_off = idx->grp_off; a.lens = idx->lens;
   a.ld = ld; a.d = d; a.Q = Qp; a.probe = probe; a.thr = thr; a.seqbase = seqbase;
@@ -1226,7 +1242,10 @@ static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k,
     ScanTcCall tc;
     tc.s = a; tc.side = &idx->tc; tc.pair_sorted = pv2.p; tc.list_off = loff.p; tc.nlists = nlists; tc.nq = nq;
     tc.qflag = qflag.p;
+    tc.comm = (comm && comm->world > 1) ? comm : nullptr;
+    tc.bound_exchanged = &bound_exchanged;
     SPF_TRY(scan_tc_run(c, tc));
+    SPF_TRY(bound_guard.finish());                         // no local units: the tau pass (and its reduction) did not run
     // flagged queries (no certified bound / bucket overflow): exact query-major scan
     KernelTimer t2(c, "scan_tc_fallback");
     ScanArgs fa = a;
@@ -1275,6 +1294,7 @@ static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k,
     else if (k <= 64) SPF_TRY(launch_scan<2>(c, a, nq));
     else SPF_TRY(launch_scan<4>(c, a, nq));
   }
+  SPF_TRY(bound_guard.finish());
   return SPF_OK;
 }
 
@@ -1432,18 +1452,26 @@ int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uin
                        thr.p + (size_t)rank * nq_local, seqbase.p + (size_t)rank * nq_local * nprobe));
   {
     KernelTimer t(c, "exchange");
-    SPF_TRY(comm_allgather(c, comm, probe.p + (size_t)rank * nq_local * nprobe, probe.p, (size_t)nq_local * nprobe * 4));
-    SPF_TRY(comm_allgather(c, comm, seqbase.p + (size_t)rank * nq_local * nprobe, seqbase.p, (size_t)nq_local * nprobe * 4));
-    SPF_TRY(comm_allgather(c, comm, thr.p + (size_t)rank * nq_local, thr.p, (size_t)nq_local * 4));
+    SPF_TRY(comm_group_start(comm));
+    int rc = comm_allgather(c, comm, probe.p + (size_t)rank * nq_local * nprobe, probe.p, (size_t)nq_local * nprobe * 4);
+    if (rc == SPF_OK) rc = comm_allgather(c, comm, seqbase.p + (size_t)rank * nq_local * nprobe, seqbase.p, (size_t)nq_local * nprobe * 4);
+    if (rc == SPF_OK) rc = comm_allgather(c, comm, thr.p + (size_t)rank * nq_local, thr.p, (size_t)nq_local * 4);
+    const int rc2 = comm_group_end(comm);
+    if (rc != SPF_OK) return rc;
+    SPF_TRY(rc2);
   }
   SPF_TRY(search_scan(idx, Q.p, nq, k, nprobe, probe.p, thr.p, seqbase.p, o_ids.p, o_dists.p, o_counts.p, o_keys.p, o_slots.p,
-                      d_bytes.p));
+                      d_bytes.p, comm));
   {
-    KernelTimer t(c, "exchange");
-    SPF_TRY(comm_alltoall(c, comm, o_keys.p, r_keys.p, (size_t)nq_local * k * 8));
-    SPF_TRY(comm_alltoall(c, comm, o_ids.p, r_ids.p, (size_t)nq_local * k * 8));
-    SPF_TRY(comm_alltoall(c, comm, o_dists.p, r_dists.p, (size_t)nq_local * k * 4));
-    SPF_TRY(comm_alltoall(c, comm, o_counts.p, r_counts.p, (size_t)nq_local * 4));
+    KernelTimer t(c, "exchange");                          // the four tables travel as one aggregated operation
+    SPF_TRY(comm_group_start(comm));
+    int rc = comm_alltoall(c, comm, o_keys.p, r_keys.p, (size_t)nq_local * k * 8);
+    if (rc == SPF_OK) rc = comm_alltoall(c, comm, o_ids.p, r_ids.p, (size_t)nq_local * k * 8);
+    if (rc == SPF_OK) rc = comm_alltoall(c, comm, o_dists.p, r_dists.p, (size_t)nq_local * k * 4);
+    if (rc == SPF_OK) rc = comm_alltoall(c, comm, o_counts.p, r_counts.p, (size_t)nq_local * 4);
+    const int rc2 = comm_group_end(comm);
+    if (rc != SPF_OK) return rc;
+    SPF_TRY(rc2);
   }
   {
     KernelTimer t(c, "merge");
