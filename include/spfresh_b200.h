@@ -305,7 +305,10 @@ uint64_t spf_index_vectors(const spf_index* idx);   /* total vectors stored on t
  * Outputs: counts[q] <= k results per query (0 == the reference's None), ids / dists are
  * nq x k (rows padded with UINT64_MAX / +inf), vectors (nq x k x d) may be NULL.
  * keys (nq x k, may be NULL) receives the stable-order key of each result,
- * (distance bits << 32 | encounter index), which is what a multi-GPU merge sorts on. */
+ * (distance bits << 32 | encounter index), which is what a multi-GPU merge sorts on.
+ * Limits (the reference has none): 1 <= k <= 1024 (k > 128 runs the exact query-major scan in
+ * passes of 128 results), nprobe <= 1024 (after clamping to the number of lists), fewer than
+ * 2^32 (query, probe) pairs and 2^32 scanned vectors per query. */
 int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t k,
                      uint32_t nprobe, float prune_factor, uint64_t* ids, float* dists,
                      uint32_t* counts, float* vectors, uint64_t* keys);

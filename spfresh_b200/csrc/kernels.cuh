@@ -169,6 +169,10 @@ struct ScanArgs {
   unsigned long long* out_slots;   // nq x K slot index of each result (vector gather)
   unsigned long long* bytes;
   const uint8_t* only;             // query-major kernel: when set, only queries with only[q] != 0 run
+  // query-major kernel, K > 128 in passes of <= 128 results: this pass writes columns
+  // [out_col, out_col + K) of rows out_stride wide and takes only keys above the previous pass's last
+  // one (keys are unique per query).  out_stride = 0: a single pass, rows K wide.
+  uint32_t out_stride = 0, out_col = 0;
 };
 
 // TF32 side structures of an index for the tensor-core candidate scan (scan_tc.cu), made lazily

@@ -363,11 +363,15 @@ scan_kernel(ScanArgs a) {
       if (ng) bytes += (unsigned long long)a.lens[l] * a.d * 4ull;
     }
     s_gpre[a.nprobe] = acc;
-    if (bytes) atomicAdd(a.bytes, bytes);
+    if (bytes && a.out_col == 0) atomicAdd(a.bytes, bytes);
   }
   __syncthreads();
   const float thr = a.thr[q];
   const uint32_t units = s_gpre[a.nprobe];
+  const uint32_t ostride = a.out_stride ? a.out_stride : a.K;
+  // a later pass of a K > 128 search: only what lies behind the previous pass's last result (~0: it was not full)
+  const unsigned long long after = a.out_col ? a.out_keys[q * ostride + a.out_col - 1] : 0ull;
+  const bool later = a.out_col != 0;
 
   unsigned long long key[R], pay[R];
 #pragma unroll
@@ -396,7 +400,7 @@ scan_kernel(ScanArgs a) {
     const bool valid = pos < a.lens[l];
     const unsigned long long ck =
         ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned long long)(seqb[p] + pos);
-    unsigned bal = __ballot_sync(0xffffffffu, valid && acc <= thr && ck < kth);
+    unsigned bal = __ballot_sync(0xffffffffu, valid && acc <= thr && ck < kth && (!later || ck > after));
     while (bal) {
       const int src = __ffs(bal) - 1;
       bal &= bal - 1;
@@ -430,13 +434,14 @@ scan_kernel(ScanArgs a) {
     const bool ok = e < a.K && key[r] != ~0ull;
     count += __popc(__ballot_sync(0xffffffffu, ok));
     if (e < a.K) {
-      a.out_ids[q * a.K + e] = ok ? a.slot_ids[pay[r]] : ~0ull;
-      a.out_dists[q * a.K + e] = ok ? __uint_as_float((uint32_t)(key[r] >> 32)) : __int_as_float(0x7f800000);
-      a.out_keys[q * a.K + e] = key[r];
-      a.out_slots[q * a.K + e] = ok ? pay[r] : ~0ull;
+      const size_t o = q * ostride + a.out_col + e;
+      a.out_ids[o] = ok ? a.slot_ids[pay[r]] : ~0ull;
+      a.out_dists[o] = ok ? __uint_as_float((uint32_t)(key[r] >> 32)) : __int_as_float(0x7f800000);
+      a.out_keys[o] = key[r];
+      a.out_slots[o] = ok ? pay[r] : ~0ull;
     }
   }
-  if (lane == 0) a.out_counts[q] = count;
+  if (lane == 0) a.out_counts[q] = (later ? a.out_counts[q] : 0u) + count;
 }
 
 // ---- list-major scan ---------------------------------------------------------------------------
@@ -1212,8 +1217,10 @@ static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k,
   const uint32_t nloc = idx->list_end - idx->list_begin;
   const bool use_tc = c->params.scan_tc != 0 && scan_tc_supported(c, ld, idx->total_groups * 32, k, npairs) &&
                       (c->params.scan_tc == 2 || npairs >= 16ull * (nloc ? nloc : 1));
+  // (rows too long for the list-major kernel's shared-memory tiles stay on the query-major kernel)
   const bool list_major = !use_tc && k <= 32 && npairs < (1ull << 32) && c->params.scan_list_major != 0 &&
-                          (c->params.scan_list_major == 2 || npairs >= 2ull * nlists);
+                          (c->params.scan_list_major == 2 || npairs >= 2ull * nlists) &&
+                          (size_t)LS_QB * ld * sizeof(float) + (size_t)LS_WARPS * LS_QB * k * 8 <= 200 * 1024;
   DevBuf<uint32_t> pk, pv, pk2, pv2, loff;
   DevBuf<unsigned long long> ukeys, uslots;
   DevBuf<uint8_t> stmp, qflag;
@@ -1292,7 +1299,17 @@ static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k,
     KernelTimer t(c, "scan");
     if (k <= 32) SPF_TRY(launch_scan<1>(c, a, nq));
     else if (k <= 64) SPF_TRY(launch_scan<2>(c, a, nq));
-    else SPF_TRY(launch_scan<4>(c, a, nq));
+    else if (k <= 128) SPF_TRY(launch_scan<4>(c, a, nq));
+    else {
+      // the reference has no cap on k: passes of 128 results, each taking the keys behind the previous one
+      for (uint32_t col = 0; col < k; col += 128) {
+        ScanArgs pa = a;
+        pa.K = k - col < 128u ? k - col : 128u;
+        pa.out_stride = k;
+        pa.out_col = col;
+        SPF_TRY(launch_scan<4>(c, pa, nq));
+      }
+    }
   }
   SPF_TRY(bound_guard.finish());
   return SPF_OK;
@@ -1303,7 +1320,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
                      uint64_t* keys) {
   return spf::guarded([&]() -> int {
   if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_batch: NULL argument");
-  if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
+  if (k == 0 || k > 1024) return fail(SPF_E_INVALID, "k must be in [1,1024]");
   if (nq == 0) return SPF_OK;
   if (nprobe == 0) nprobe = k;                       // spann_index.rs:164 nearest_n(query, k)
   if (nprobe > idx->nlists) nprobe = idx->nlists;
@@ -1404,7 +1421,7 @@ int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uin
   return spf::guarded([&]() -> int {
   if (!idx || !queries || !ids || !dists || !counts) return fail(SPF_E_INVALID, "spf_search_sharded: NULL argument");
   if (comm && comm->ctx != idx->ctx) return fail(SPF_E_INVALID, "communicator and index belong to different contexts");
-  if (k == 0 || k > 128) return fail(SPF_E_INVALID, "k must be in [1,128]");
+  if (k == 0 || k > 1024) return fail(SPF_E_INVALID, "k must be in [1,1024]");
   if (nq_local == 0) return fail(SPF_E_INVALID, "every rank must bring at least one query");
   if (nprobe == 0) nprobe = k;
   if (nprobe > idx->nlists) nprobe = idx->nlists;

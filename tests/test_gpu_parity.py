@@ -1306,6 +1306,57 @@ def test_search_sharded_single_rank_equals_search_batch(spf, ctx, oracle):
     ds.free()
 
 
+def test_search_more_than_128_results_matches_oracle(spf, ctx, oracle):
+    """The reference has no cap on k (spann_index.rs:188-193): k > 128 runs the exact query-major scan in
+    passes of 128 results (each pass takes the keys behind the previous pass's last one); nprobe = 0
+    means nprobe = k.  ids, distance bits and counts against the oracle, single call and sharded entry."""
+    data = clustered(12000, 48, 40, 515)
+    cent = np.random.default_rng(51).choice(12000, 300, replace=False)
+    ds = spf.Dataset(ctx, data)
+    res = ds.assign(0, cent)
+    f = res.fetch(best=False, dmin=False)
+    med = ds.update_medoids_from(0, res, cent)
+    res.free()
+    idx = spf.DeviceIndex.pack(ds, f.offsets, f.members, med)
+    q = clustered(300, 48, 40, 516)
+    for k, nprobe, prune in ((129, 6, 1.2), (200, 0, 1.2), (300, 20, 3.0), (1000, 12, 50.0)):
+        rid, rd, rc = oracle.search_batch(data, f.offsets, f.members, med, q, k, nprobe=nprobe, prune_factor=prune)
+        for got in (idx.search(q, k, nprobe=nprobe, prune_factor=prune),
+                    idx.search_sharded(None, q, k, nprobe=nprobe, prune_factor=prune)):
+            assert np.array_equal(got[2], rc), (k, nprobe)
+            for i in range(q.shape[0]):
+                assert np.array_equal(got[0][i, :rc[i]], rid[i, :rc[i]]), (k, nprobe, i)
+                assert np.array_equal(got[1][i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32))
+        assert rc.max() > 128 or k == 129
+    with pytest.raises(spf.SpfError):
+        idx.search(q, 1025)
+    idx.free()
+    ds.free()
+
+
+def test_search_very_long_rows_stay_on_the_query_major_scan(spf, ctx, oracle):
+    """a mid-size batch of rows too long for the list-major kernel's shared-memory tiles
+    (ld ~ 6500) must fall back to the query-major scan instead of failing."""
+    rng = np.random.default_rng(77)
+    n, d, nl = 1200, 6500, 12
+    data = rng.standard_normal((n, d), dtype=np.float32)
+    owner = rng.integers(0, nl, n)
+    members = np.concatenate([np.flatnonzero(owner == j) for j in range(nl)]).astype(np.uint64)
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=nl))]).astype(np.uint64)
+    med = np.array([members[int(offsets[j])] for j in range(nl)], np.uint64)
+    ds = spf.Dataset(ctx, data)
+    idx = spf.DeviceIndex.pack(ds, offsets, members, med)
+    q = rng.standard_normal((64, d), dtype=np.float32)
+    rid, rd, rc = oracle.search_batch(data, offsets, members, med, q, 10, nprobe=4, prune_factor=5.0)
+    ids, dists, counts = idx.search(q, 10, nprobe=4, prune_factor=5.0)
+    assert np.array_equal(counts, rc)
+    for i in range(q.shape[0]):
+        assert np.array_equal(ids[i, :rc[i]], rid[i, :rc[i]])
+        assert np.array_equal(dists[i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32))
+    idx.free()
+    ds.free()
+
+
 # ----------------------------------------------------------------------------------------------
 # EXTENSION: balanced assignment / Lloyd iterations (no reference counterpart; the oracle's
 # orc_assign_balanced is the specification — parity unpinned, DESIGN.md)
