@@ -257,6 +257,20 @@ int  spf_kmpp_begin_sharded(spf_dataset* ds, int metric, spf_kmpp** out);
 int  spf_kmpp_fold_vector(spf_kmpp* s, const float* centroid, float* local_sum);
 int  spf_kmpp_weight_total(spf_kmpp* s, float global_sum, double* local_total);
 int  spf_kmpp_pick_local(spf_kmpp* s, double target, uint64_t* row);
+/* Device-resident form of the same rounds over the ranks of `comm` (NULL: one rank): no host round
+ * trip per round.  spf_kmpp_set_vector() places the newest centroid's vector (d floats, the same on
+ * every rank); spf_kmpp_rounds_sharded() then runs `count` rounds: fold, local f32 sum, all-gather of
+ * the sums and rank-ordered add (:278), f64 weight totals all-gathered, the rank whose weight range
+ * holds u01[i] * total picks inside its shard, the picked row's vector reaches every rank by a third
+ * all-gather and becomes the next round's centroid.  Same arithmetic and the same picks as the
+ * fold_vector / weight_total / pick_local sequence.  chosen[0..*done) receives GLOBAL rows (row_base +
+ * the owner's local row; row_base = first global row of this rank's shard).  Returns 1 when round
+ * *done could not pick (invalid or all-zero weights; its draw u01[*done] is NOT consumed): the host
+ * draws uniformly, sets that row's vector with spf_kmpp_set_vector() and carries on.  Collective:
+ * every rank calls it with the same count and draws. */
+int  spf_kmpp_set_vector(spf_kmpp* s, const float* centroid);
+int  spf_kmpp_rounds_sharded(spf_kmpp* s, spf_comm* comm, uint64_t row_base, const double* u01, uint32_t count,
+                             uint64_t* chosen, uint32_t* done);
 void spf_kmpp_free(spf_kmpp* s);
 
 /* ---- bisect seed ----------------------------------------------------------------------- *

@@ -65,6 +65,8 @@ SIGNATURES = {
     "spf_kmpp_fold_vector": (C.c_int, [_vp, _vp, _f32p]),
     "spf_kmpp_weight_total": (C.c_int, [_vp, C.c_float, C.POINTER(C.c_double)]),
     "spf_kmpp_pick_local": (C.c_int, [_vp, C.c_double, _u64p]),
+    "spf_kmpp_set_vector": (C.c_int, [_vp, _vp]),
+    "spf_kmpp_rounds_sharded": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_double), C.c_uint32, _u64p, C.POINTER(C.c_uint32)]),
     "spf_kmpp_free": (None, [_vp]),
     "spf_seq_sum_f32": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _f32p]),
     "spf_farthest": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, _u64p]),

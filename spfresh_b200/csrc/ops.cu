@@ -6,6 +6,7 @@
 
 #include <string.h>
 
+#include "comm.cuh"
 #include "kernels.cuh"
 #include "pairdist.cuh"
 #include "tc_ptx.cuh"
@@ -34,6 +35,14 @@ struct spf_kmpp {
   uint64_t* d_chosen = nullptr;
   int* d_ctl = nullptr;      // [0] stop flag, [1] rounds completed
   uint32_t batch_cap = 0;
+  // device-resident sharded rounds (spf_kmpp_rounds_sharded): exchange buffers, sized for `sh_world` ranks
+  bool vec_pending = false;  // d_vec holds a centroid that is not folded yet
+  int sh_world = 0;
+  float* sh_sums = nullptr;      // world local f32 sums, rank order
+  double* sh_tinfo = nullptr;    // world x {local f64 weight total, 1 = all local weights valid}
+  int* sh_owner = nullptr;       // rank that picks this round, -1: no weighted pick possible
+  double* sh_target = nullptr;   // u * total - totals of the lower ranks
+  uint8_t* sh_cand = nullptr;    // (world + 1) x {u64 global row, ld floats}; slot `world` is this rank's
 };
 
 namespace spf {
@@ -1231,6 +1240,11 @@ struct KmppBatch {
   int* stop = nullptr;
   uint32_t* done = nullptr;
   uint32_t round = 0;
+  // sharded rounds: only the owning rank picks, with the target the owner kernel computed; a failed
+  // pick is reported through the candidate exchange, not through *stop (the other ranks must agree)
+  const int* owner = nullptr;
+  const double* d_target = nullptr;
+  int my_rank = 0;
 };
 
 // inclusive f64 scan over the 1024 threads of the CTA; *total = the last thread's value, *excl = the
@@ -1268,7 +1282,12 @@ kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __rest
   __shared__ double s_cum;
   __shared__ unsigned long long s_b;
   if (bt.stop && *bt.stop) return;
-  if (bt.u01) u01 = bt.u01[bt.round];
+  if (bt.owner) {
+    if (*bt.owner != bt.my_rank) return;
+    target = *bt.d_target;
+  } else if (bt.u01) {
+    u01 = bt.u01[bt.round];
+  }
   // ---- chunk sums and their prefix
   const uint64_t chunk = (nblocks + PICK_THREADS - 1) / PICK_THREADS;
   const uint64_t c0 = (uint64_t)threadIdx.x * chunk;
@@ -1282,7 +1301,7 @@ kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __rest
   if (*bad || total == 0.0 || !isfinite(total)) {         // uniform: every thread sees the same total
     if (threadIdx.x == 0) {
       res[0] = 1; res[1] = 0;
-      if (bt.stop) *bt.stop = 1;
+      if (bt.stop && !bt.owner) *bt.stop = 1;
     }
     return;
   }
@@ -1329,6 +1348,78 @@ kmpp_pick_kernel(const float* __restrict__ mind, uint64_t n, const float* __rest
   res[0] = 0;
   res[1] = idx;
   if (bt.chosen) { bt.chosen[bt.round] = idx; *bt.done = bt.round + 1u; }
+}
+
+// ---- device-resident row-sharded rounds (same arithmetic as the host-staged sequence
+// fold_vector / weight_total / pick_local of sharded.py): small single-CTA kernels between the
+// three all-gathers of a round.
+__global__ void kmpp_combine_sums_kernel(const float* __restrict__ sums, int world, float* __restrict__ gsum, const int* __restrict__ stop) {
+  if (*stop) return;
+  float s = 0.0f;
+  for (int r = 0; r < world; ++r) s = __fadd_rn(s, sums[r]);          // :278 over the ranks, in rank order
+  gsum[0] = s;
+}
+
+// this shard's f64 weight total (the pick kernel's chunk sums + scan, bit for bit) and validity
+__global__ void __launch_bounds__(PICK_THREADS)
+kmpp_total_kernel(const double* __restrict__ block_sums, uint64_t nblocks, const int* __restrict__ bad,
+                  double* __restrict__ my_tinfo, const int* __restrict__ stop) {
+  __shared__ double s_w[32];
+  if (*stop) return;
+  const uint64_t chunk = (nblocks + PICK_THREADS - 1) / PICK_THREADS;
+  const uint64_t c0 = (uint64_t)threadIdx.x * chunk;
+  const uint64_t c1 = c0 + chunk < nblocks ? c0 + chunk : nblocks;
+  double mine = 0.0;
+  for (uint64_t i = c0; i < c1; ++i) mine += block_sums[i];
+  double total, excl;
+  pick_scan(mine, s_w, &total, &excl);
+  if (threadIdx.x == 0) { my_tinfo[0] = total; my_tinfo[1] = *bad ? 0.0 : 1.0; }
+}
+
+__global__ void kmpp_owner_kernel(const double* __restrict__ tinfo, int world, const double* __restrict__ u01, uint32_t round,
+                                  int* __restrict__ owner, double* __restrict__ target, int* __restrict__ stop) {
+  if (*stop) return;
+  double total = 0.0;
+  bool ok = true;
+  for (int r = 0; r < world; ++r) { total += tinfo[2 * r]; ok = ok && tinfo[2 * r + 1] == 1.0; }
+  if (!ok || !(total > 0.0) || !isfinite(total)) { owner[0] = -1; *stop = 1; return; }   // the Err arm of WeightedIndex::new
+  const double u = u01[round] * total;
+  double prefix = 0.0;
+  int own = world - 1;
+  for (int r = 0; r < world - 1; ++r) {
+    if (u < prefix + tinfo[2 * r]) { own = r; break; }
+    prefix += tinfo[2 * r];
+  }
+  owner[0] = own;
+  target[0] = u - prefix;
+}
+
+// this rank's candidate of the round: {global row, vector} on the owner, {~0, -} elsewhere
+__global__ void kmpp_pack_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restrict__ res,
+                                 const int* __restrict__ owner, int my_rank, uint64_t row_base,
+                                 uint8_t* __restrict__ my_cand, const int* __restrict__ stop) {
+  if (*stop) return;
+  const bool mine = owner[0] == my_rank && res[0] == 0;
+  if (threadIdx.x == 0) reinterpret_cast<unsigned long long*>(my_cand)[0] = mine ? row_base + res[1] : ~0ull;
+  float* v = reinterpret_cast<float*>(my_cand + 16);
+  if (mine)
+    for (uint32_t j = threadIdx.x; j < ld; j += blockDim.x) v[j] = X[(size_t)res[1] * ld + j];
+}
+
+__global__ void kmpp_take_kernel(const uint8_t* __restrict__ cand, size_t cand_bytes, const int* __restrict__ owner,
+                                 float* __restrict__ d_vec, uint32_t ld, uint64_t* __restrict__ chosen, uint32_t round,
+                                 uint32_t* __restrict__ done, int* __restrict__ stop) {
+  if (*stop) return;                                      // uniform: read before anybody writes it
+  const uint8_t* slot = cand + (size_t)owner[0] * cand_bytes;
+  const unsigned long long row = reinterpret_cast<const unsigned long long*>(slot)[0];
+  __syncthreads();
+  if (row == ~0ull) {                                     // the owner could not pick inside its shard
+    if (threadIdx.x == 0) *stop = 1;
+    return;
+  }
+  const float* v = reinterpret_cast<const float*>(slot + 16);
+  for (uint32_t j = threadIdx.x; j < ld; j += blockDim.x) d_vec[j] = v[j];
+  if (threadIdx.x == 0) { chosen[round] = row; *done = round + 1u; }
 }
 
 template <typename F>
@@ -1878,6 +1969,135 @@ int spf_kmpp_pick_local(spf_kmpp* s, double target, uint64_t* row) {
   return SPF_OK;
 }
 
+int spf_kmpp_set_vector(spf_kmpp* s, const float* centroid) {
+  return spf::guarded([&]() -> int {
+  if (!s || !centroid || !s->d_vec) return fail(SPF_E_INVALID, "spf_kmpp_set_vector: needs a session of spf_kmpp_begin_sharded");
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  SPF_CUDA(cudaMemsetAsync(s->d_vec, 0, (size_t)ds->ld * sizeof(float), st));
+  SPF_CUDA(cudaMemcpyAsync(s->d_vec, centroid, (size_t)ds->d * sizeof(float), cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  s->vec_pending = true;
+  return SPF_OK;
+  });
+}
+
+int spf_kmpp_rounds_sharded(spf_kmpp* s, spf_comm* comm, uint64_t row_base, const double* u01, uint32_t count,
+                            uint64_t* chosen, uint32_t* done) {
+  return spf::guarded([&]() -> int {
+  if (!s || !u01 || !chosen || !done || !s->d_vec) return fail(SPF_E_INVALID, "spf_kmpp_rounds_sharded: bad argument");
+  *done = 0;
+  if (count == 0) return SPF_OK;
+  if (count > (1u << 20)) return fail(SPF_E_INVALID, "spf_kmpp_rounds_sharded: at most 2^20 rounds per call");
+  for (uint32_t i = 0; i < count; ++i)
+    if (!(u01[i] >= 0.0 && u01[i] < 1.0)) return fail(SPF_E_INVALID, "u01 must be in [0,1)");
+  if (!s->vec_pending) return fail(SPF_E_STATE, "no centroid pending: call spf_kmpp_set_vector() first");
+  spf_dataset* ds = s->ds;
+  spf_ctx* c = ds->ctx;
+  if (comm && comm->ctx != c) return fail(SPF_E_INVALID, "communicator and dataset belong to different contexts");
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SPF_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint64_t n = ds->n;
+  const uint32_t ld = ds->ld;
+  const size_t cb = 16 + (size_t)ld * sizeof(float);     // candidate slot: row, pad, vector
+  if (s->sh_world != world) {
+    for (void* p : {(void*)s->sh_sums, (void*)s->sh_tinfo, (void*)s->sh_owner, (void*)s->sh_target, (void*)s->sh_cand})
+      if (p) cudaFree(p);
+    s->sh_sums = nullptr; s->sh_tinfo = nullptr; s->sh_owner = nullptr; s->sh_target = nullptr; s->sh_cand = nullptr;
+    s->sh_world = 0;
+    if (cudaMalloc((void**)&s->sh_sums, (size_t)(world + 1) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void**)&s->sh_tinfo, (size_t)(world + 1) * 2 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&s->sh_owner, sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void**)&s->sh_target, sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&s->sh_cand, (size_t)(world + 1) * cb) != cudaSuccess)
+      return fail(SPF_E_OOM, "sharded k-means++ buffers: out of device memory");
+    s->sh_world = world;
+  }
+  if (count > s->batch_cap) {
+    if (s->d_u01) cudaFree(s->d_u01);
+    if (s->d_chosen) cudaFree(s->d_chosen);
+    s->d_u01 = nullptr; s->d_chosen = nullptr; s->batch_cap = 0;
+    const uint32_t cap = count < 64u ? 64u : count;
+    if (cudaMalloc((void**)&s->d_u01, (size_t)cap * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&s->d_chosen, (size_t)cap * sizeof(uint64_t)) != cudaSuccess)
+      return fail(SPF_E_OOM, "k-means++ batch buffers: out of device memory");
+    s->batch_cap = cap;
+  }
+  if (!s->d_ctl && cudaMalloc((void**)&s->d_ctl, 2 * sizeof(int)) != cudaSuccess)
+    return fail(SPF_E_OOM, "k-means++ batch buffers: out of device memory");
+  SPF_CUDA(cudaMemcpyAsync(s->d_u01, u01, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st));
+  SPF_CUDA(cudaMemsetAsync(s->d_ctl, 0, 2 * sizeof(int), st));
+  int* stop = s->d_ctl;
+  uint32_t* d_done = reinterpret_cast<uint32_t*>(s->d_ctl + 1);
+  float* my_sum = s->sh_sums + world;                      // slot `world`: this rank's contribution
+  double* my_tinfo = s->sh_tinfo + 2 * (size_t)world;
+  uint8_t* my_cand = s->sh_cand + (size_t)world * cb;
+  for (uint32_t r = 0; r < count; ++r) {
+    {
+      KernelTimer t(c, "kmpp_update");
+      const int first = (s->rounds == 0 && r == 0) ? 1 : 0;
+      SPF_TRY(dispatch_metric(s->metric, [&](auto M) {
+        return launch_kmpp_update<decltype(M)::value>(c, ds->x, ld, n, s->d_vec, first, s->mind, nullptr, stop);
+      }));
+    }
+    {
+      KernelTimer t(c, "kmpp_sum");
+      if (c->params.kmpp_exact_sum == 1) SPF_TRY(launch_kmpp_sum(c, s->mind, n, my_sum, stop));
+      else if (c->params.kmpp_exact_sum == 2) seq_sum_kernel<<<1, SEQ_THREADS, 0, st>>>(s->mind, n, my_sum, stop);
+      else tree_sum_kernel<<<1, 1024, 0, st>>>(s->mind, n, my_sum, stop);
+      SPF_TRY(check_launch(c, "kmpp sum kernel"));
+    }
+    {
+      KernelTimer t(c, "kmpp_exchange");
+      SPF_TRY(comm_allgather(c, comm, my_sum, s->sh_sums, sizeof(float)));
+    }
+    {
+      KernelTimer t(c, "kmpp_pick");
+      kmpp_combine_sums_kernel<<<1, 1, 0, st>>>(s->sh_sums, world, s->d_sum, stop);
+      SPF_CUDA(cudaMemsetAsync(s->bad, 0, sizeof(int), st));
+      kmpp_block_sums_kernel<<<(unsigned)s->nblocks, 256, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->bad, stop);
+      kmpp_total_kernel<<<1, PICK_THREADS, 0, st>>>(s->block_sums, s->nblocks, s->bad, my_tinfo, stop);
+      SPF_TRY(check_launch(c, "kmpp total kernels", 3));
+    }
+    {
+      KernelTimer t(c, "kmpp_exchange");
+      SPF_TRY(comm_allgather(c, comm, my_tinfo, s->sh_tinfo, 2 * sizeof(double)));
+    }
+    {
+      KernelTimer t(c, "kmpp_pick");
+      kmpp_owner_kernel<<<1, 1, 0, st>>>(s->sh_tinfo, world, s->d_u01, r, s->sh_owner, s->sh_target, stop);
+      KmppBatch bt;
+      bt.stop = stop; bt.owner = s->sh_owner; bt.d_target = s->sh_target; bt.my_rank = rank; bt.round = r;
+      kmpp_pick_kernel<<<1, PICK_THREADS, 0, st>>>(s->mind, n, s->d_sum, s->block_sums, s->nblocks, s->bad, 0.0, 0.0, s->res, s->d_total, bt);
+      kmpp_pack_kernel<<<1, 128, 0, st>>>(ds->x, ld, s->res, s->sh_owner, rank, row_base, my_cand, stop);
+      SPF_TRY(check_launch(c, "kmpp pick kernels", 3));
+    }
+    {
+      KernelTimer t(c, "kmpp_exchange");
+      SPF_TRY(comm_allgather(c, comm, my_cand, s->sh_cand, cb));
+    }
+    kmpp_take_kernel<<<1, 128, 0, st>>>(s->sh_cand, cb, s->sh_owner, s->d_vec, ld, s->d_chosen, r, d_done, stop);
+    SPF_TRY(check_launch(c, "kmpp_take_kernel"));
+  }
+  int ctl[2] = {0, 0};
+  SPF_CUDA(cudaMemcpyAsync(ctl, s->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(chosen, s->d_chosen, (size_t)count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaMemcpyAsync(&s->last_sum, s->d_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
+  SPF_CUDA(cudaStreamSynchronize(st));
+  const uint32_t ok = (uint32_t)ctl[1];
+  const bool failed = ctl[0] != 0;
+  *done = ok;
+  s->rounds += ok + (failed ? 1u : 0u);                   // the failing round folded its centroid too
+  s->vec_pending = !failed;
+  return failed ? 1 : SPF_OK;
+  });
+}
+
 int spf_kmpp_push(spf_kmpp* s, uint64_t row) {
   if (!s) return fail(SPF_E_INVALID, "session is NULL");
   if (s->pending) return fail(SPF_E_STATE, "a centroid is already pending");
@@ -1908,6 +2128,8 @@ void spf_kmpp_free(spf_kmpp* s) {
   if (s->d_u01) cudaFree(s->d_u01);
   if (s->d_chosen) cudaFree(s->d_chosen);
   if (s->d_ctl) cudaFree(s->d_ctl);
+  for (void* p : {(void*)s->sh_sums, (void*)s->sh_tinfo, (void*)s->sh_owner, (void*)s->sh_target, (void*)s->sh_cand})
+    if (p) cudaFree(p);
   delete s;
 }
 

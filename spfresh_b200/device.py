@@ -360,6 +360,22 @@ class KmppShardSession:
         rc = check(lib().spf_kmpp_weight_total(self._h, float(np.float32(global_sum)), C.byref(out)))
         return float(out.value), rc == 0
 
+    def set_vector(self, centroid):
+        """spf_kmpp_set_vector: the newest centroid of the device-resident rounds."""
+        v = as_f32(centroid).reshape(self.ds.d)
+        check(lib().spf_kmpp_set_vector(self._h, ptr(v)))
+
+    def rounds_sharded(self, comm, row_base: int, u01):
+        """spf_kmpp_rounds_sharded (collective): len(u01) rounds without a host round trip.  Returns
+        (global rows picked, failed); failed: round len(rows) could not pick and did not use its draw."""
+        u = np.ascontiguousarray(u01, np.float64)
+        chosen = np.zeros(u.size, np.uint64)
+        done = C.c_uint32()
+        rc = check(lib().spf_kmpp_rounds_sharded(self._h, comm.handle if comm is not None else None, int(row_base),
+                                                 u.ctypes.data_as(C.POINTER(C.c_double)), u.size,
+                                                 chosen.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(done)))
+        return chosen[:int(done.value)].copy(), rc == 1
+
     def pick_local(self, target: float):
         out = C.c_uint64()
         rc = check(lib().spf_kmpp_pick_local(self._h, float(target), C.byref(out)))

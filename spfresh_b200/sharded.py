@@ -195,6 +195,37 @@ def update_centroids(shard, comm: Comm, metric: int, res, old_vectors: np.ndarra
     return new_rows, new_vecs, means
 
 
+def kmeans_plus_plus_device(shard, comm: Comm, device_comm, metric: int, k: int, rng,
+                            shard_starts: Optional[np.ndarray] = None, batch: int = 256):
+    """The same initialisation with the rounds resident on the devices (spf_kmpp_rounds_sharded over
+    the library's NCCL group `device_comm`; `comm` only gathers the vector of a uniformly drawn row):
+    three small all-gathers per round on the library stream, one host synchronisation per batch.
+    Same picks as kmeans_plus_plus() for the same draws."""
+    starts = shard_layout(shard, comm) if shard_starts is None else shard_starts
+    sizes = np.array([int(x[0]) for x in comm.allgather(np.array([shard.n], np.int64))], np.int64)
+    n_total = int(sizes.sum())
+    sess = shard.kmpp_session(metric)
+    try:
+        chosen = [int(rng.choose_index(n_total))]
+        sess.set_vector(gather_rows(shard, comm, np.array([chosen[-1]], np.uint64), starts)[0])
+        draws: List[float] = []
+        while len(chosen) < k:
+            want = min(k - len(chosen), batch)
+            while len(draws) < want:
+                draws.append(rng.uniform01())
+            rows, failed = sess.rounds_sharded(device_comm, int(starts[comm.rank]), draws[:want])
+            chosen.extend(int(r) for r in rows)
+            del draws[:len(rows)]                                  # a failing round does not use its draw
+            if failed:                                             # Err arm: uniform draw
+                row = int(rng.choose_index(n_total))
+                chosen.append(row)
+                if len(chosen) < k:
+                    sess.set_vector(gather_rows(shard, comm, np.array([row], np.uint64), starts)[0])
+        return np.array(chosen, np.uint64)
+    finally:
+        sess.free()
+
+
 def kmeans_plus_plus(shard, comm: Comm, metric: int, k: int, rng, shard_starts: Optional[np.ndarray] = None):
     """Row-sharded initialize_clusters_kmeans_plus_plus (hierarchical.rs:249-293).  `rng` is a
     RandomSource (clustering.py) that every rank seeds identically, so the draws need no exchange:

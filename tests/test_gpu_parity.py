@@ -539,6 +539,38 @@ def test_kmeanspp_batched_rounds_match_oracle(spf, ctx, oracle, metric):
     sess.free()
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_kmeanspp_device_resident_sharded_rounds_one_rank(spf, ctx, oracle, metric):
+    """spf_kmpp_set_vector + spf_kmpp_rounds_sharded with one rank (comm NULL: the all-gathers are device
+    copies): the picks of the oracle; two ranks over NCCL are checked by tools/check_sharded_nccl.py."""
+    from spfresh_b200.device import KmppShardSession
+    data = clustered(30000, 20, 30, 19)
+    k = 33
+    u = np.random.default_rng(70 + metric).random(k - 1)
+    ref, fell = oracle.kmeanspp(data, metric, k, 4321, u)
+    assert not fell.any()
+    ds = spf.Dataset(ctx, data)
+    sess = KmppShardSession(ds, metric)
+    with pytest.raises(spf.SpfError):
+        sess.rounds_sharded(None, 0, u[:2])                 # no centroid yet
+    sess.set_vector(data[4321])
+    got = [4321]
+    for lo, hi in ((0, 5), (5, 32)):
+        rows, failed = sess.rounds_sharded(None, 0, u[lo:hi])
+        assert not failed and len(rows) == hi - lo
+        got += [int(r) for r in rows]
+    sess.free()
+    assert got == ref.tolist()
+    same = np.ones((64, 4), np.float32)
+    sess = KmppShardSession(spf.Dataset(ctx, same), 0)
+    sess.set_vector(same[3])
+    rows, failed = sess.rounds_sharded(None, 1000, [0.5, 0.25])
+    assert failed and len(rows) == 0
+    with pytest.raises(spf.SpfError):
+        sess.rounds_sharded(None, 1000, [0.5])              # the host must set the uniformly drawn row first
+    sess.free()
+
+
 def test_sequential_sum_scan_is_bit_exact(spf, ctx):
     """hierarchical.rs:278 is a strictly sequential f32 fold.  The scan-based kernel (two-state
     transducers per binade) must return the bits of the serial add chain and of numpy's sequential

@@ -12,7 +12,9 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import spfresh_b200 as spf  # noqa: E402
-from spfresh_b200.sharded import DeviceShard, DeviceShardedKMeans, ShardedKMeans, ThreadComm  # noqa: E402
+from spfresh_b200.clustering import ScriptedRandomSource  # noqa: E402
+from spfresh_b200.sharded import (DeviceShard, DeviceShardedKMeans, ShardedKMeans, ThreadComm, TorchComm,  # noqa: E402
+                                  kmeans_plus_plus, kmeans_plus_plus_device)
 
 
 def shard_rows(rank, n, d):
@@ -69,6 +71,38 @@ def check_kmeans(ctx, comm, rank, world, dev, n=60_000, d=128, k=512, iters=3):
     return n * world
 
 
+def check_kmpp(ctx, comm, rank, world, dev, n=50_000, d=64, k=40):
+    """Device-resident sharded k-means++ rounds (spf_kmpp_rounds_sharded, three NCCL all-gathers per round)
+    against the host-staged exchange of sharded.kmeans_plus_plus over the same shards and draws, for
+    every metric; also a degenerate shard set (identical rows) that must take the uniform fallback."""
+    import time
+    mine = shard_rows(rank, n, d)
+    ds = spf.Dataset(ctx, mine)
+    shard = DeviceShard(ds, rank * n, mine)
+    host = TorchComm(dev)
+    u = np.random.Generator(np.random.Philox(key=31)).random(k).tolist()
+    times = []
+    for metric in (spf.METRIC_EUCLIDEAN, spf.METRIC_MANHATTAN, spf.METRIC_CHEBYSHEV):
+        mk = lambda: ScriptedRandomSource(index=lambda m: (m * 5) // 7, u01=list(u))   # noqa: E731
+        t0 = time.perf_counter()
+        a = kmeans_plus_plus(shard, host, metric, k, mk())
+        t1 = time.perf_counter()
+        b = kmeans_plus_plus_device(shard, host, comm, metric, k, mk(), batch=16)
+        t2 = time.perf_counter()
+        assert np.array_equal(a, b), f"metric {metric}: device-resident picks differ from the host-staged ones"
+        assert len(set(int(x) for x in b)) == k
+        times.append(((t1 - t0) / (k - 1) * 1e3, (t2 - t1) / (k - 1) * 1e3))
+    ds.free()
+    same = np.ones((500, 8), np.float32)
+    ds2 = spf.Dataset(ctx, same)
+    sh2 = DeviceShard(ds2, rank * 500, same)
+    a = kmeans_plus_plus(sh2, host, 0, 5, ScriptedRandomSource(index=[3, 700 % (500 * world), 11, 12, 13], u01=list(u)))
+    b = kmeans_plus_plus_device(sh2, host, comm, 0, 5, ScriptedRandomSource(index=[3, 700 % (500 * world), 11, 12, 13], u01=list(u)))
+    assert np.array_equal(a, b), (a, b)
+    ds2.free()
+    return "kmpp_ok ms_per_round host-staged/device " + " ".join(f"{x:.2f}/{y:.2f}" for x, y in times)
+
+
 def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -81,9 +115,10 @@ def main():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from check_sharded_query import check_query
     extra = check_query(ctx, comm, rank, world, dev)
+    extra2 = check_kmpp(ctx, comm, rank, world, dev)
     dist.barrier()
     if rank == 0:
-        print(f"SHARDED_NCCL_OK world={world} rows={rows} {extra}", flush=True)
+        print(f"SHARDED_NCCL_OK world={world} rows={rows} {extra} {extra2}", flush=True)
     comm.free()
     dist.destroy_process_group()
 
