@@ -653,6 +653,32 @@ def bench_kmeans_iteration(spf, ctx, ds, comm, rank, world, rows_np, torch, dist
            "kernels_ms": parts, "seeded": "iterations after the first seed the candidate pass with d(x, c_new[best_old])",
            "global_members": int(sizes.sum())}
     km.free()
+    # k-means++ rounds over the same shards, resident on the devices (spf_kmpp_rounds_sharded: three small
+    # all-gathers per round, one host synchronisation per batch); CUDA events on the library stream
+    from spfresh_b200.device import KmppShardSession
+    sess = KmppShardSession(ds, spf.METRIC_EUCLIDEAN)
+    sess.set_vector(rows_np[7] if rank == 0 else make_rows(0, K_CENT)[7])      # row 7 is shared by all ranks
+    u = np.random.Generator(np.random.Philox(key=77)).random(64 + 8)
+    sess.rounds_sharded(comm, rank * N_ROWS, u[:8])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(ext)
+    picked, failed = sess.rounds_sharded(comm, rank * N_ROWS, u[8:])
+    k1.record(ext)
+    k1.synchronize()
+    kms = k0.elapsed_time(k1) / 64
+    if world > 1:
+        t = torch.tensor([kms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kms = float(t.item())
+    sess.free()
+    out["kmeanspp_round"] = {"ms_per_round": kms, "rounds": 64, "rows_per_gpu": N_ROWS, "failed": bool(failed),
+                             "distinct_rows": int(len(set(int(x) for x in picked))),
+                             "note": "hierarchical.rs:259-291 over row shards: running-minimum update at HBM rate, bit-exact "
+                                     "sequential f32 sum per shard (thread-block-cluster scan), sums and f64 weight totals "
+                                     "all-gathered and added in rank order, owner picks, vector all-gathered"}
     return out
 
 
