@@ -85,7 +85,7 @@ int stage_ring(spf_ctx* c) {
 
 int stage_threads() {
   const unsigned hc = std::thread::hardware_concurrency();
-  unsigned t = hc ? hc / 4 : 4;
+  unsigned t = hc ? hc / 2 : 4;                            // the copies are memory bound: a few cores saturate the DRAM channels
   if (t < 2) t = 2;
   if (t > 8) t = 8;
   return (int)t;
@@ -147,7 +147,11 @@ int staged_upload(spf_ctx* c, const float* rows, uint64_t n, uint32_t d, uint64_
   };
   std::vector<std::thread> pool;
   const int nt = stage_threads();
-  for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+  try {
+    for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+  } catch (...) {                                          // thread limit reached: carry on with the ones that started
+    if (pool.empty()) return fail(SPF_E_OOM, "staged upload: cannot start a worker thread");
+  }
   int rc = SPF_OK;
   for (size_t b = 0; b < nb && rc == SPF_OK; ++b) {
     while (!filled[b].load(std::memory_order_acquire)) {
@@ -199,7 +203,11 @@ int staged_download(spf_ctx* c, void* host, const void* dev, size_t bytes, cudaS
   };
   std::vector<std::thread> pool;
   const int nt = stage_threads();
-  for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+  try {
+    for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+  } catch (...) {
+    if (pool.empty()) return fail(SPF_E_OOM, "staged download: cannot start a worker thread");
+  }
   int rc = SPF_OK;
   for (size_t b = 0; b < nb; ++b) {
     const int slot = (int)(b % SLOTS);

@@ -141,15 +141,15 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0, ecount = 0;
       for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x, ++it) {
-        if (!stream_a) {
-          for (uint32_t kb = 0; kb < a.kb; ++kb) {
-            mbar_wait(&a_empty[kb], (it & 1) ^ 1);        // previous row block's MMAs are done with it
-            mbar_expect_tx(&a_full[kb], A_KB_BYTES);
-            tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(rb * BM));
-          }
-        }
         for (uint32_t t = 0; t < a.ntiles; ++t, ++ecount) {
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            if (!stream_a && t == 0) {
+              // the row block's point K block, requested as soon as the previous row block's last tile is
+              // done with THIS block (not with all four), so the centroid ring does not drain in between
+              mbar_wait(&a_empty[kb], (it & 1) ^ 1);
+              mbar_expect_tx(&a_full[kb], A_KB_BYTES);
+              tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(rb * BM));
+            }
             mbar_wait(&b_empty[stage], phase ^ 1);          // both CTAs are done with this stage
             if (stream_a) {                                 // own point K block in the same ring stage (not multicast)
               mbar_expect_tx(&b_full[stage], A_KB_BYTES + B_STAGE_BYTES);

@@ -147,16 +147,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const UnitDesc ud = a.desc[u];
         const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
         if (ntiles == 0) continue;
-        if (!stream_a) {
-          for (uint32_t kb = 0; kb < a.kb; ++kb) {
-            mbar_wait(&a_empty[kb], (it & 1) ^ 1);        // previous unit's MMAs are done with it
-            mbar_expect_tx(&a_full[kb], A_KB_BYTES);
-            tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(u * UNIT_ROWS));
-          }
-        }
         for (uint32_t t = 0; t < ntiles; ++t, ++ecount) {
           const int row0 = (int)(ud.slot0 + t * BN);
           for (uint32_t kb = 0; kb < a.kb; ++kb) {
+            if (!stream_a && t == 0) {
+              // the unit's query K block, requested as soon as the previous unit's last tile is done with
+              // THIS block (not with all four): the first list stages of the new unit are already in
+              // flight while the previous unit's last MMAs and epilogue run, so the ring never drains
+              mbar_wait(&a_empty[kb], (it & 1) ^ 1);
+              mbar_expect_tx(&a_full[kb], A_KB_BYTES);
+              tma_load_2d(smem_a + kb * A_KB_BYTES, &map_a, &a_full[kb], (int)(kb * BK), (int)(u * UNIT_ROWS));
+            }
             mbar_wait(&b_empty[stage], phase ^ 1);
             if (stream_a) {                               // the query K block rides in the same ring stage
               mbar_expect_tx(&b_full[stage], A_KB_BYTES + B_STAGE_BYTES);
