@@ -430,13 +430,31 @@ __global__ void max2_atomic_kernel(const float* __restrict__ a, const float* __r
 // per call: units, gathered query rows, bounds, refinement
 // ---------------------------------------------------------------------------------------------
 // units per list = ceil(pairs probing it / 128), 0 for lists this rank does not hold
+// totals[0] += units, totals[1] += 256-slot tiles over all units, totals[2] = max tiles of a probed list:
+// everything the host needs for its sizing decisions comes back in ONE device -> host copy
 __global__ void tc_unit_counts_kernel(const uint32_t* __restrict__ list_off, const uint64_t* __restrict__ grp_off,
-                                      uint32_t nlists, uint32_t* __restrict__ counts) {
+                                      uint32_t nlists, uint32_t* __restrict__ counts, unsigned long long* __restrict__ totals) {
   const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l > nlists) return;
   uint32_t n = 0;
   if (l < nlists && grp_off[l + 1] != grp_off[l]) n = (list_off[l + 1] - list_off[l] + UNIT_ROWS - 1) / UNIT_ROWS;
   counts[l] = n;
+  if (n) {
+    const unsigned long long tiles = ((unsigned long long)(grp_off[l + 1] - grp_off[l]) * 32ull + BN - 1) / BN;
+    atomicAdd(&totals[0], (unsigned long long)n);
+    atomicAdd(&totals[1], (unsigned long long)n * tiles);
+    atomicMax(&totals[2], tiles);
+  }
+}
+
+// the centroid probe: ONE list probed by every query, so the units are known on the host
+__global__ void tc_probe_units_kernel(const uint64_t* __restrict__ grp_off, uint32_t nunits, uint32_t* __restrict__ unit_off,
+                                      uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ order) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u == 0) { unit_off[0] = 0; unit_off[1] = nunits; }
+  if (u >= nunits) return;
+  keys_sorted[u] = 0xffffffffu - (uint32_t)(grp_off[1] - grp_off[0]);
+  order[u] = u;
 }
 
 // Sort key of a unit: longest list first (stable, so the units of one list stay adjacent and share
@@ -1055,33 +1073,48 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   // units
   DevBuf<uint32_t> ucnt, uoff;
   DevBuf<uint8_t> tmp;
-  SPF_TRY(ucnt.alloc(st, (size_t)nlists + 1));
+  DevBuf<unsigned long long> utot;
   SPF_TRY(uoff.alloc(st, (size_t)nlists + 1));
-  tc_unit_counts_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(call.list_off, s.grp_off, nlists, ucnt.p);
-  SPF_TRY(check_launch(c, "tc_unit_counts_kernel"));
-  size_t tmp_bytes = 0;
-  SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
-  SPF_TRY(tmp.alloc(st, tmp_bytes));
-  SPF_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
-  c->launches += 1;
   uint32_t nunits = 0;
-  SPF_CUDA(cudaMemcpyAsync(&nunits, uoff.p + nlists, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  SPF_CUDA(cudaStreamSynchronize(st));
-
+  unsigned long long h_tot[3] = {0, 0, 0};                 // units, tiles over all units, tiles of the longest probed list
   DevBuf<uint32_t> ukey, uval, ukey2, order;
-  if (nunits > 0) {
-    SPF_TRY(ukey.alloc(st, nunits));
-    SPF_TRY(uval.alloc(st, nunits));
+  const bool one_list = call.is_probe && nlists == 1;
+  if (one_list) {
+    // the centroid probe: every query probes the one list, nothing to count, nothing to sort, no round trip
+    nunits = (uint32_t)ceil_div(nq, (uint64_t)UNIT_ROWS);
     SPF_TRY(ukey2.alloc(st, nunits));
     SPF_TRY(order.alloc(st, nunits));
-    tc_unit_keys_kernel<<<(unsigned)ceil_div(nunits, 256), 256, 0, st>>>(uoff.p, s.grp_off, nlists, nunits, ukey.p, uval.p);
-    SPF_TRY(check_launch(c, "tc_unit_keys_kernel"));
-    size_t sb = 0;
-    SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sb, ukey.p, ukey2.p, uval.p, order.p, (int)nunits, 0, 32, st));
-    DevBuf<uint8_t> stmp;
-    SPF_TRY(stmp.alloc(st, sb));
-    SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sb, ukey.p, ukey2.p, uval.p, order.p, (int)nunits, 0, 32, st));
+    tc_probe_units_kernel<<<(unsigned)ceil_div((uint64_t)nunits, 256), 256, 0, st>>>(s.grp_off, nunits, uoff.p, ukey2.p, order.p);
+    SPF_TRY(check_launch(c, "tc_probe_units_kernel"));
+  } else {
+    SPF_TRY(ucnt.alloc(st, (size_t)nlists + 1));
+    SPF_TRY(utot.alloc(st, 3));
+    SPF_CUDA(cudaMemsetAsync(utot.p, 0, 3 * sizeof(unsigned long long), st));
+    tc_unit_counts_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(call.list_off, s.grp_off, nlists, ucnt.p, utot.p);
+    SPF_TRY(check_launch(c, "tc_unit_counts_kernel"));
+    size_t tmp_bytes = 0;
+    SPF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
+    SPF_TRY(tmp.alloc(st, tmp_bytes));
+    SPF_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, ucnt.p, uoff.p, (int)(nlists + 1), st));
     c->launches += 1;
+    SPF_CUDA(cudaMemcpyAsync(h_tot, utot.p, sizeof(h_tot), cudaMemcpyDeviceToHost, st));
+    SPF_CUDA(cudaStreamSynchronize(st));
+    if (h_tot[0] >= (1ull << 32)) return fail(SPF_E_INVALID, "scan_tc: too many units");
+    nunits = (uint32_t)h_tot[0];
+    if (nunits > 0) {
+      SPF_TRY(ukey.alloc(st, nunits));
+      SPF_TRY(uval.alloc(st, nunits));
+      SPF_TRY(ukey2.alloc(st, nunits));
+      SPF_TRY(order.alloc(st, nunits));
+      tc_unit_keys_kernel<<<(unsigned)ceil_div(nunits, 256), 256, 0, st>>>(uoff.p, s.grp_off, nlists, nunits, ukey.p, uval.p);
+      SPF_TRY(check_launch(c, "tc_unit_keys_kernel"));
+      size_t sb = 0;
+      SPF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sb, ukey.p, ukey2.p, uval.p, order.p, (int)nunits, 0, 32, st));
+      DevBuf<uint8_t> stmp;
+      SPF_TRY(stmp.alloc(st, sb));
+      SPF_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sb, ukey.p, ukey2.p, uval.p, order.p, (int)nunits, 0, 32, st));
+      c->launches += 1;
+    }
   }
 
   DevBuf<uint32_t> qcnt;
@@ -1116,9 +1149,10 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_TRY(stmp.alloc(st, sb));
     SPF_CUDA(cub::DeviceScan::ExclusiveSum(stmp.p, sb, utiles.p, tile_off.p, (int)(nunits + 1), st));
     c->launches += 1;
-    SPF_CUDA(cudaMemcpyAsync(&total_tiles, tile_off.p + nunits, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SPF_CUDA(cudaMemcpyAsync(&max_tiles, utiles.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));   // rank 0 = longest list
-    SPF_CUDA(cudaStreamSynchronize(st));
+    // totals came back with the unit count: no second round trip
+    if (h_tot[1] >= (1ull << 32)) return fail(SPF_E_INVALID, "scan_tc: too many tiles");
+    total_tiles = (uint32_t)h_tot[1];
+    max_tiles = (uint32_t)h_tot[2];
     keep_cmax = (uint64_t)total_tiles * 5120ull <= (uint64_t)c->params.scan_tc_cmax_mb << 20;
   }
 
