@@ -85,6 +85,8 @@ int spf_ctx_create(int device, spf_ctx** out) {
   c->tma_encode = fn;
   const char* env = getenv("SPF_FORCE_EXACT");
   if (env && atoi(env)) c->params.force_exact = 1;
+  env = getenv("SPF_TC_PIPE");                     // experiments: epilogue variant of assign_tc_kernel
+  if (env) c->params.tc_pipe = atoi(env);
   *out = c;
   return SPF_OK;
 }
@@ -184,6 +186,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "scan_tc_cmax_mb") c->params.scan_tc_cmax_mb = value;
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
+  else if (s == "tc_pipe") c->params.tc_pipe = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
   else if (s == "no_host_staging") c->params.no_host_staging = value;
   else if (s == "cc_matrix_max_k") c->params.cc_matrix_max_k = value;

@@ -78,6 +78,13 @@ struct TcArgs {
   CandRec* rec; RowInfo* info; int cap;
 };
 
+// PIPE 0: the thread's 128 accumulator columns are loaded first, the buffer is released, then the
+// arithmetic runs (the load latency of every tile is exposed once).  PIPE 1: two halves of 64 columns
+// in a software pipeline that runs ACROSS tiles — the second half of tile i is in flight while the
+// first is processed, the buffer is released in the middle of the tile, and the first half of tile
+// i + 1 is in flight while the second half of tile i is processed: no tcgen05.ld latency is exposed and
+// the register footprint (128 value registers) is unchanged.
+template <int PIPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_e, TcArgs a) {
@@ -221,6 +228,19 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // record is one 256-bit store
     const uint32_t z1 = lrow, z2 = warp, z3 = threadIdx.x;
     uint32_t tcount = 0;
+    // PIPE 1: tiles this CTA walks in total, and the first half of the first tile
+    const uint32_t total_tiles =
+        blockIdx.x < a.nrowblocks ? ((a.nrowblocks - blockIdx.x + gridDim.x - 1) / gridDim.x) * a.ntiles : 0u;
+    const uint32_t tlane = tmem_base + ((quarter * 32u) << 16) + half * (BN / 2);
+    uint32_t r0[32], r1[32], r2[32], r3[32];
+    if (PIPE == 1 && total_tiles > 0) {
+      mbar_wait(&t_full[0], 0);
+      tc_fence_after();
+      tc_ld32_issue(tlane, r0);
+      tc_ld32_issue(tlane + 32, r1);
+      tc_ld32_wait(r0);
+      tc_ld32_wait(r1);
+    }
     for (uint32_t rb = blockIdx.x; rb < a.nrowblocks; rb += gridDim.x) {
       const uint32_t row = rb * BM + lrow;
       const bool row_ok = row < a.m;
@@ -250,9 +270,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       float other = sseed;                                // bound from the seed / the partner half (one chunk old)
       for (uint32_t t = 0; t < a.ntiles; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
-        mbar_wait(&t_full[buf], use & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN + half * (BN / 2);
+        if (PIPE == 0) {
+          mbar_wait(&t_full[buf], use & 1);
+          tc_fence_after();
+        }
+        const uint32_t taddr = tlane + buf * BN;
         const uint32_t gtile = (t * BN + half * (BN / 2)) >> 2;
         // a tile emits at most 32 records per thread: when every thread of the warp has room for
         // them, the whole tile takes the straight-line path without any further capacity test
@@ -333,22 +355,48 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // TMEM buffer is released before any arithmetic: with only two accumulator buffers the
         // next-but-one MMA may start as soon as the epilogue has *read* this one, so the tensor
         // pipe waits for the epilogue's throughput only, never for its latency chain.
-        uint32_t r0[32], r1[32], r2[32], r3[32];
-        tc_ld32_issue(taddr, r0);
-        tc_ld32_issue(taddr + 32, r1);
-        tc_ld32_issue(taddr + 64, r2);
-        tc_ld32_issue(taddr + 96, r3);
-        tc_ld32_wait(r0);
-        tc_ld32_wait(r1);
-        tc_ld32_wait(r2);
-        tc_ld32_wait(r3);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[buf]);
-        process(r0, 0);
-        process(r1, 1);
-        process(r2, 2);
-        process(r3, 3);
+        if (PIPE == 0) {
+          tc_ld32_issue(taddr, r0);
+          tc_ld32_issue(taddr + 32, r1);
+          tc_ld32_issue(taddr + 64, r2);
+          tc_ld32_issue(taddr + 96, r3);
+          tc_ld32_wait(r0);
+          tc_ld32_wait(r1);
+          tc_ld32_wait(r2);
+          tc_ld32_wait(r3);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+          process(r0, 0);
+          process(r1, 1);
+          process(r2, 2);
+          process(r3, 3);
+        } else {
+          // columns 0..63 of this tile are in r0 / r1 (loaded while the previous tile's second half was processed)
+          tc_ld32_issue(taddr + 64, r2);
+          tc_ld32_issue(taddr + 96, r3);
+          process(r0, 0);
+          process(r1, 1);
+          tc_ld32_wait(r2);
+          tc_ld32_wait(r3);
+          tc_fence_before();                              // the whole slice is in registers: release the buffer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+          const bool more = tcount + 1 < total_tiles;     // uniform over the CTA's epilogue warps
+          if (more) {
+            const uint32_t nt = tcount + 1;
+            mbar_wait(&t_full[nt & 1], (nt >> 1) & 1);
+            tc_fence_after();
+            tc_ld32_issue(tlane + (nt & 1) * BN, r0);
+            tc_ld32_issue(tlane + (nt & 1) * BN + 32, r1);
+          }
+          process(r2, 2);
+          process(r3, 3);
+          if (more) {
+            tc_ld32_wait(r0);
+            tc_ld32_wait(r1);
+          }
+        }
       }
       if (row_ok) {
         uint2* const info2 = reinterpret_cast<uint2*>(a.info + row) + half;
@@ -391,8 +439,13 @@ int launch_assign_tc(spf_ctx* c, const float* Ptf, uint64_t m, const float* Ctf,
   a.xnorm = xnorm; a.xres = xres; a.cstat = d_cstat; a.seed = seed;
   a.rec = cand.rec; a.info = cand.info; a.cap = cand.cap;
   unsigned grid = a.nrowblocks < (uint32_t)c->sm_count ? a.nrowblocks : (unsigned)c->sm_count & ~1u;
-  SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-  assign_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
+  if (c->params.tc_pipe) {
+    SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    assign_tc_kernel<1><<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
+  } else {
+    SPF_CUDA(cudaFuncSetAttribute(assign_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    assign_tc_kernel<0><<<grid, NUM_THREADS, SMEM_TOTAL, c->stream>>>(map_a, map_b, map_e, a);
+  }
   return check_launch(c, "assign_tc_kernel");
 }
 
