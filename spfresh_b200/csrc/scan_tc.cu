@@ -71,6 +71,7 @@ struct UnitDesc { uint32_t slot0, nslots, tile0, pad; };   // tile0: first tile 
 struct ScanTcArgs {
   uint32_t nunits, kb, nprobe, cap;
   uint32_t u0;                     // rank of this launch's first unit (row scalars are kept for all units)
+  uint32_t ubase;                  // first unit of this launch inside `desc` / the gathered rows (split launches)
   const UnitDesc* desc;            // per unit of this launch
   float4* cmax;                    // bound pass out (optional): per (tile, column half, row) its 4 chunk maxima
   uint32_t* cmask;                 // ... and per chunk 8 bits: which 4-slot subgroups can still pass (see below)
@@ -143,7 +144,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // =============================== TMA producer ===========================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0, ecount = 0;
-      for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+      for (uint32_t u = a.ubase + blockIdx.x; u < a.ubase + a.nunits; u += gridDim.x) {
         const UnitDesc ud = a.desc[u];
         const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
         if (ntiles == 0) continue;
@@ -180,7 +181,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // =============================== MMA issuer ==============================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0, tcount = 0;
-      for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+      for (uint32_t u = a.ubase + blockIdx.x; u < a.ubase + a.nunits; u += gridDim.x) {
         const UnitDesc ud = a.desc[u];
         const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
         if (ntiles == 0) continue;
@@ -224,7 +225,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t lrow = quarter * 32 + lane;
     const float INF = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
-    for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+    for (uint32_t u = a.ubase + blockIdx.x; u < a.ubase + a.nunits; u += gridDim.x) {
       const UnitDesc ud = a.desc[u];
       const uint32_t ntiles = (ud.nslots + BN - 1) / BN;
       if (ntiles == 0) continue;
@@ -430,7 +431,8 @@ __global__ void max2_atomic_kernel(const float* __restrict__ a, const float* __r
 // per call: units, gathered query rows, bounds, refinement
 // ---------------------------------------------------------------------------------------------
 // units per list = ceil(pairs probing it / 128), 0 for lists this rank does not hold
-// totals[0] += units, totals[1] += 256-slot tiles over all units, totals[2] = max tiles of a probed list:
+// totals[0] += units, totals[1] += 256-slot tiles over all units, totals[2] = max tiles of a probed list,
+// totals[3] / [4] += units / tiles of the lists with more than one unit:
 // everything the host needs for its sizing decisions comes back in ONE device -> host copy
 __global__ void tc_unit_counts_kernel(const uint32_t* __restrict__ list_off, const uint64_t* __restrict__ grp_off,
                                       uint32_t nlists, uint32_t* __restrict__ counts, unsigned long long* __restrict__ totals) {
@@ -444,8 +446,20 @@ __global__ void tc_unit_counts_kernel(const uint32_t* __restrict__ list_off, con
     atomicAdd(&totals[0], (unsigned long long)n);
     atomicAdd(&totals[1], (unsigned long long)n * tiles);
     atomicMax(&totals[2], tiles);
+    if (n > 1) {
+      atomicAdd(&totals[3], (unsigned long long)n);
+      atomicAdd(&totals[4], (unsigned long long)n * tiles);
+    }
   }
 }
+
+// Sort key of a unit rank: bit 31 = its list has a single unit (at most 128 probing pairs), low bits =
+// 0x7fffffff - 32-slot groups of the list.  Ascending order = units of multi-unit lists first, longest
+// list first within each class.
+__host__ __device__ __forceinline__ uint32_t unit_key(uint32_t groups, bool single_unit) {
+  return (single_unit ? 0x80000000u : 0u) | (0x7fffffffu - (groups < 0x7fffffffu ? groups : 0x7fffffffu));
+}
+__host__ __device__ __forceinline__ uint32_t unit_key_groups(uint32_t key) { return 0x7fffffffu - (key & 0x7fffffffu); }
 
 // the centroid probe: ONE list probed by every query, so the units are known on the host
 __global__ void tc_probe_units_kernel(const uint64_t* __restrict__ grp_off, uint32_t nunits, uint32_t* __restrict__ unit_off,
@@ -453,12 +467,13 @@ __global__ void tc_probe_units_kernel(const uint64_t* __restrict__ grp_off, uint
   const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u == 0) { unit_off[0] = 0; unit_off[1] = nunits; }
   if (u >= nunits) return;
-  keys_sorted[u] = 0xffffffffu - (uint32_t)(grp_off[1] - grp_off[0]);
+  keys_sorted[u] = unit_key((uint32_t)(grp_off[1] - grp_off[0]), false);
   order[u] = u;
 }
 
-// Sort key of a unit: longest list first (stable, so the units of one list stay adjacent and share
-// the list through L2).  Dealing the sorted units round-robin to the persistent CTAs balances them.
+// Sort key of a unit: the units of lists probed by more than 128 pairs first, then longest list first
+// (stable, so the units of one list stay adjacent and share the list through L2).  Dealing the sorted
+// units round-robin to the persistent CTAs balances them.
 __global__ void tc_unit_keys_kernel(const uint32_t* __restrict__ unit_off, const uint64_t* __restrict__ grp_off,
                                     uint32_t nlists, uint32_t nunits, uint32_t* __restrict__ keys,
                                     uint32_t* __restrict__ vals) {
@@ -469,7 +484,7 @@ __global__ void tc_unit_keys_kernel(const uint32_t* __restrict__ unit_off, const
     const uint32_t mid = (lo + hi) >> 1;
     if (unit_off[mid] <= u) lo = mid; else hi = mid;
   }
-  keys[u] = 0xffffffffu - (uint32_t)(grp_off[lo + 1] - grp_off[lo]);
+  keys[u] = unit_key((uint32_t)(grp_off[lo + 1] - grp_off[lo]), unit_off[lo + 1] - unit_off[lo] < 2u);
   vals[u] = u;
 }
 
@@ -638,17 +653,17 @@ __global__ void bound_tighten_kernel(const float* __restrict__ qbound, const flo
   if (by_global > th) qthr[q] = by_global;
 }
 
-// Tiles of every unit rank (from its sort key = 0xffffffff - groups of the list).
+// Tiles of every unit rank (from its sort key).
 __global__ void tc_unit_tiles_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t nunits, uint32_t* __restrict__ ntiles) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > nunits) return;
-  ntiles[r] = r < nunits ? ((0xffffffffu - keys_sorted[r]) * 32u + BN - 1) / BN : 0u;
+  ntiles[r] = r < nunits ? (unit_key_groups(keys_sorted[r]) * 32u + BN - 1) / BN : 0u;
 }
 
 struct WorkItem { uint32_t pair, group; };   // group = 4-slot subgroup of the index (32-slot group * 8 + subgroup)
 
 struct FlagArgs {
-  const uint32_t* keys_sorted;     // unit ranks: 0xffffffff - groups of the list
+  const uint32_t* keys_sorted;     // unit ranks: unit_key() of the list
   const uint32_t* tile_off; const float4* cmax; const uint32_t* cmask;
   const uint32_t* rowpair; const uint32_t* unit_slot0;  // per row: pair; per unit rank: first slot of its list
   const float* qthr; uint32_t nprobe;
@@ -668,7 +683,7 @@ __global__ void __launch_bounds__(256) chunk_flag_kernel(FlagArgs f) {
   __shared__ uint32_t sn, sbase;
   const uint32_t r = blockIdx.x;
   {
-    const uint32_t nt = ((0xffffffffu - f.keys_sorted[r]) * 32u + BN - 1) / BN;
+    const uint32_t nt = (unit_key_groups(f.keys_sorted[r]) * 32u + BN - 1) / BN;
     if (blockIdx.y * FLAG_TILES >= nt) return;            // block-uniform
   }
   if (threadIdx.x == 0) sn = 0;
@@ -679,7 +694,7 @@ __global__ void __launch_bounds__(256) chunk_flag_kernel(FlagArgs f) {
   if (pair != NOPAIR) {
     const uint32_t q = pair / f.nprobe;
     const float th = f.qthr[q];
-    const uint32_t groups = 0xffffffffu - f.keys_sorted[r];
+    const uint32_t groups = unit_key_groups(f.keys_sorted[r]);
     const uint32_t ntiles = (groups * 32u + BN - 1) / BN;
     const uint32_t g0 = f.unit_slot0[r] >> 5;
     const size_t e0 = ((size_t)f.tile_off[r] * 2 + half) * UNIT_ROWS + lrow;
@@ -1076,7 +1091,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
   DevBuf<unsigned long long> utot;
   SPF_TRY(uoff.alloc(st, (size_t)nlists + 1));
   uint32_t nunits = 0;
-  unsigned long long h_tot[3] = {0, 0, 0};                 // units, tiles over all units, tiles of the longest probed list
+  // units, tiles over all units, tiles of the longest probed list, units / tiles of the multi-unit lists
+  unsigned long long h_tot[5] = {0, 0, 0, 0, 0};
   DevBuf<uint32_t> ukey, uval, ukey2, order;
   const bool one_list = call.is_probe && nlists == 1;
   if (one_list) {
@@ -1088,8 +1104,8 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     SPF_TRY(check_launch(c, "tc_probe_units_kernel"));
   } else {
     SPF_TRY(ucnt.alloc(st, (size_t)nlists + 1));
-    SPF_TRY(utot.alloc(st, 3));
-    SPF_CUDA(cudaMemsetAsync(utot.p, 0, 3 * sizeof(unsigned long long), st));
+    SPF_TRY(utot.alloc(st, 5));
+    SPF_CUDA(cudaMemsetAsync(utot.p, 0, 5 * sizeof(unsigned long long), st));
     tc_unit_counts_kernel<<<(unsigned)ceil_div((uint64_t)nlists + 1, 256), 256, 0, st>>>(call.list_off, s.grp_off, nlists, ucnt.p, utot.p);
     SPF_TRY(check_launch(c, "tc_unit_counts_kernel"));
     size_t tmp_bytes = 0;
@@ -1206,7 +1222,7 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     k.pairtop = pairtop.p; k.qcnt = qcnt.p; k.bucket = bucket.p;
     k.cmax = keep_cmax ? cmax.p : nullptr;
     k.cmask = keep_cmax ? cmask.p : nullptr; k.rowes = rowes.p; k.topk = s.K;
-    k.dense = nullptr; k.dense_ld = 0;
+    k.dense = nullptr; k.dense_ld = 0; k.ubase = 0;
 
     for (uint32_t u0 = 0; u0 < nunits; u0 += chunk_units) {
       const uint32_t nu = nunits - u0 < chunk_units ? nunits - u0 : chunk_units;
@@ -1217,11 +1233,56 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
         SPF_TRY(check_launch(c, "unit_gather_kernel"));
       }
       KernelTimer t(c, n_a);                              // the bound pass alone (the roofline's kernel time)
-      k.nunits = nu; k.u0 = u0;
-      const unsigned grid = nu < (uint32_t)c->sm_count ? nu : (unsigned)c->sm_count;
-      if (topr == 16) scan_tc_kernel<0, 16><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
-      else scan_tc_kernel<0, 32><<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(map_a, map_b, map_e, k);
-      SPF_TRY(check_launch(c, "scan_tc_kernel<A>"));
+      k.nunits = nu; k.u0 = u0; k.ubase = 0;
+      auto launch_a = [&](unsigned grid, cudaStream_t on) {
+        if (topr == 16) scan_tc_kernel<0, 16><<<grid, NUM_THREADS, SMEM_TOTAL, on>>>(map_a, map_b, map_e, k);
+        else scan_tc_kernel<0, 32><<<grid, NUM_THREADS, SMEM_TOTAL, on>>>(map_a, map_b, map_e, k);
+        return check_launch(c, "scan_tc_kernel<A>");
+      };
+      // Split launch.  The units of lists probed by more than 128 pairs re-read their list from L2 and are
+      // bound by the tensor pipe; the single-unit lists stream from HBM and leave the tensor pipe half idle.
+      // One after the other (sorted order) the two phases add up; as two persistent kernels on disjoint
+      // SMs they overlap, and each list's units still run side by side.  Measured on the 10 k-query batch
+      // (438 multi-unit units holding 42 % of the 51.5 k tiles): 1.10 ms unsplit, 1.42 / 1.05 / 0.94 / 0.97 /
+      // 1.04 / 1.27 ms with 40 / 61 / 70 / 76 / 84 / 100 SMs on the multi-unit side — a little more than its
+      // share of the tiles, because those units pay a per-unit prologue and the other side is HBM-bound
+      // anyway.  With 30 k queries (82 % of the tiles in multi-unit lists) nothing is left to overlap:
+      // 1.69 ms either way, so the split is used only while the HBM-bound side holds 40 % of the tiles.
+      const uint32_t hub_units = (uint32_t)h_tot[3];
+      const uint32_t sms = (uint32_t)c->sm_count;
+      unsigned grid_hub = 0;
+      if (single && !one_list && hub_units >= 1 && nunits - hub_units >= 1 && h_tot[1] > 0 && sms >= 16) {
+        const double share = (double)h_tot[4] / (double)h_tot[1];
+        if (c->params.scan_tc_split > 1) {                  // tests / experiments: fixed SM count, no size conditions
+          grid_hub = (unsigned)c->params.scan_tc_split < sms - 1 ? (unsigned)c->params.scan_tc_split : sms - 1;
+        } else if (c->params.scan_tc_split == 1 && hub_units >= 8 && nunits - hub_units >= 2 * sms &&
+                   share >= 0.05 && share <= 0.6) {
+          grid_hub = (unsigned)(1.2 * share * sms + 0.5);
+          if (grid_hub < 4) grid_hub = 4;
+          if (grid_hub > sms - 8) grid_hub = sms - 8;
+        }
+        if (grid_hub > hub_units) grid_hub = hub_units;
+      }
+      if (grid_hub == 0) {
+        SPF_TRY(launch_a(nu < sms ? nu : sms, st));
+      } else {
+        if (!c->aux_stream) SPF_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        if (!c->aux_ev[0]) {
+          SPF_CUDA(cudaEventCreateWithFlags(&c->aux_ev[0], cudaEventDisableTiming));
+          SPF_CUDA(cudaEventCreateWithFlags(&c->aux_ev[1], cudaEventDisableTiming));
+        }
+        SPF_CUDA(cudaEventRecord(c->aux_ev[0], st));                     // gathered rows and row scalars are ready
+        SPF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
+        k.ubase = 0; k.nunits = hub_units;
+        SPF_TRY(launch_a(grid_hub, c->aux_stream));
+        SPF_CUDA(cudaEventRecord(c->aux_ev[1], c->aux_stream));
+        k.ubase = hub_units; k.nunits = nunits - hub_units;
+        const int rc_main = launch_a(k.nunits < sms - grid_hub ? k.nunits : sms - grid_hub, st);
+        SPF_CUDA(cudaStreamWaitEvent(st, c->aux_ev[1], 0));              // both halves done before tau (and before any free)
+        SPF_TRY(rc_main);
+        k.ubase = 0; k.nunits = nu;
+        if (c->profiling) c->kernel_ms[pr ? "probe_tc_split" : "scan_tc_split"] = (float)grid_hub;
+      }
     }
     {
       KernelTimer t(c, n_tau);
@@ -1303,6 +1364,9 @@ int scan_tc_run(spf_ctx* c, const ScanTcCall& call) {
     c->kernel_ms[pr ? "probe_tc_candidates" : "scan_tc_candidates"] = (float)h[0];
     c->kernel_ms[pr ? "probe_tc_flagged" : "scan_tc_flagged"] = (float)h[1];
     c->kernel_ms[pr ? "probe_tc_units" : "scan_tc_units"] = (float)nunits;
+    c->kernel_ms[pr ? "probe_tc_hub_units" : "scan_tc_hub_units"] = (float)h_tot[3];
+    c->kernel_ms[pr ? "probe_tc_hub_tiles" : "scan_tc_hub_tiles"] = (float)h_tot[4];
+    c->kernel_ms[pr ? "probe_tc_tiles" : "scan_tc_tiles"] = (float)h_tot[1];
     c->kernel_ms[pr ? "probe_tc_stream_mb" : "scan_tc_stream_mb"] = (float)((double)h[2] / 1e6);
     c->kernel_ms[pr ? "probe_tc_unique_mb" : "scan_tc_unique_mb"] = (float)((double)h[3] / 1e6);
   }
@@ -1343,7 +1407,7 @@ int probe_tc_dense(spf_ctx* c, const ScanTcSide& side, const float* centroids, c
                                                                                           rowseq.p, rowpair.p);
     SPF_TRY(check_launch(c, "dense_setup_kernel"));
     ScanTcArgs k;
-    k.nunits = nu; k.kb = (ld + BK - 1) / BK; k.nprobe = 1; k.cap = 0; k.u0 = 0;
+    k.nunits = nu; k.kb = (ld + BK - 1) / BK; k.nprobe = 1; k.cap = 0; k.u0 = 0; k.ubase = 0;
     k.desc = desc.p; k.cmax = nullptr; k.cmask = nullptr; k.rowes = nullptr; k.topk = 0;
     k.rowthr = rowthr.p; k.rowseq = rowseq.p; k.rowpair = rowpair.p;
     k.pairtop = nullptr; k.qcnt = nullptr; k.bucket = nullptr;

@@ -901,6 +901,44 @@ def test_search_tensor_scan_fallbacks(spf, oracle):
         c2.close()
 
 
+@pytest.mark.parametrize("cmax_mb", [16384, 0])
+def test_search_tensor_scan_split_launch(spf, oracle, cmax_mb):
+    """The bound pass as two concurrent launches (units of multi-unit lists on some SMs, single-unit lists
+    on the others; scan_tc.cu: scan_tc_run) returns what the single launch and the exact scans return."""
+    c2 = spf.Context(0)
+    try:
+        # 60 lists, 3000 queries x 4 probes on clustered data: popular lists get several units of 128
+        # pairs, the rest a single one
+        data = clustered(24000, 32, 40, 11)
+        cent, off, mem = build_lists(oracle, data, 60, 13)
+        ds = spf.Dataset(c2, data)
+        idx = spf.DeviceIndex.pack(ds, off, mem, cent)
+        q = clustered(3000, 32, 40, 11)[::-1].copy()
+        c2.set_param("scan_tc", 0)
+        want = idx.search(q, 10, 4, want_keys=True)
+        c2.set_param("scan_tc", 2)
+        c2.set_param("scan_tc_cmax_mb", cmax_mb)
+        for split in (0, 3, 100):
+            c2.set_param("scan_tc_split", split)
+            c2.set_profiling(True)
+            got = idx.search(q, 10, 4, want_keys=True)
+            hub, units = c2.kernel_ms("scan_tc_hub_units"), c2.kernel_ms("scan_tc_units")
+            assert 0 < hub < units, (hub, units)          # both classes of lists are present
+            assert (c2.kernel_ms("scan_tc_split") > 0) == (split > 0), split
+            c2.set_profiling(False)
+            for x, y in zip(want, got):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), split
+        rid, rd, rc = oracle.search_batch(data, off, mem, cent, q[:100], 10, 4)
+        assert np.array_equal(got[2][:100], rc)
+        for i in range(100):
+            assert np.array_equal(got[0][i, :rc[i]], rid[i, :rc[i]]), i
+            assert np.array_equal(got[1][i, :rc[i]].view(np.uint32), rd[i, :rc[i]].view(np.uint32)), i
+        idx.free()
+        ds.free()
+    finally:
+        c2.close()
+
+
 def test_search_tensor_scan_sharded_lists(spf, oracle):
     """List shards scanned by the tensor path merge to the unsharded exact answer."""
     c2 = spf.Context(0)

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "search or config5 or index or lire" 2>&1 | tail -3
+for sp in 0 1; do
+  echo "== scan_tc_split=$sp"
+  SCAN_TC_SPLIT=$sp timeout 300 python tools/query_prof.py 10000 10 4 1 1 gauss check 2>&1 | grep -v "^$" | tail -4
+done
+timeout 300 python tools/query_wall.py 10000 10 30 2>&1 | tail -2

@@ -22,7 +22,7 @@ if kind == "clustered":
 ctx = s.Context(0)
 ctx.set_param("scan_list_major", mode)
 ctx.set_param("scan_tc", tc)
-for name in ("scan_tc_bucket", "scan_tc_tau_probes", "scan_tc_cmax_mb"):
+for name in ("scan_tc_bucket", "scan_tc_tau_probes", "scan_tc_cmax_mb", "scan_tc_split"):
     import os
     if os.environ.get(name.upper()):
         ctx.set_param(name, int(os.environ[name.upper()]))
@@ -45,7 +45,7 @@ for i in range(reps):
           f"algorithmic {b / 1e9:.1f} GB -> {b / ctx.kernel_ms('scan') / 1e6:.0f} GB/s, mean count {counts.mean():.2f}", flush=True)
     if ctx.kernel_ms("scan_tc_b") > 0:
         print("   tensor scan: " + " ".join(f"{n} {ctx.kernel_ms('scan_tc_' + n):.3f}" for n in
-                                            ("a", "tau", "b", "refine", "fallback", "candidates", "flagged", "units", "groups")), flush=True)
+                                            ("a", "tau", "b", "refine", "fallback", "candidates", "flagged", "units", "groups", "split", "hub_units", "hub_tiles", "tiles")), flush=True)
     if ctx.kernel_ms("probe_tc_b") > 0:
         print("   tensor probe: " + " ".join(f"{n} {ctx.kernel_ms('probe_tc_' + n):.3f}" for n in
                                              ("a", "tau", "b", "refine", "candidates", "flagged", "units")), flush=True)
