@@ -968,7 +968,8 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
     idx.search(q, TOPK)
     scan_ms, probe_ms = ctx.kernel_ms("scan"), ctx.kernel_ms("probe")
     tc = {n: ctx.kernel_ms("scan_tc_" + n) for n in ("a", "gather", "tau", "b", "refine", "fallback", "candidates", "flagged",
-                                                      "units", "stream_mb", "unique_mb", "flag", "groups")}
+                                                      "units", "stream_mb", "unique_mb", "flag", "groups", "split", "hub_units",
+                                                      "hub_tiles", "tiles")}
     ctx.set_profiling(False)
     bytes_ = idx.last_scan_bytes()
     # the same batch on the exact CUDA-core scan (what the tensor-core candidate scan replaces): identical results
@@ -1009,7 +1010,13 @@ def bench_query(spf, ctx, ds, rows_np, cent, torch, dev, ext, hbm_peak, hbm_src)
                        "kernel_ms": tc["a"],
                        "passes_ms": {"gather": tc["gather"], "bound": tc["a"], "tau": tc["tau"], "group_refine": tc["b"], "group_refine_flagging": tc["flag"], "select": tc["refine"],
                                      "fallback": tc["fallback"]},
-                       "units": int(tc["units"]), "subgroups_refined_per_query": tc["groups"] / NQ, "candidates_per_query": tc["candidates"] / NQ,
+                       "units": int(tc["units"]),
+                       "split_launch": {"sms_multi_unit_lists": int(max(tc["split"], 0)), "multi_unit_units": int(max(tc["hub_units"], 0)),
+                                        "multi_unit_tiles": int(max(tc["hub_tiles"], 0)), "tiles": int(max(tc["tiles"], 0)),
+                                        "what": "the bound pass runs as two concurrent persistent launches on disjoint SMs: units of lists "
+                                                "probed by more than 128 pairs (tensor-bound, L2 re-reads) and single-unit lists (HBM-bound); "
+                                                "kernel_ms spans both"},
+                       "subgroups_refined_per_query": tc["groups"] / NQ, "candidates_per_query": tc["candidates"] / NQ,
                        "queries_on_exact_fallback": int(tc["flagged"]),
                        "query_major_algorithmic_gbs": gbs, "query_major_algorithmic_over_hbm": gbs / hbm_peak,
                        "note": "bytes_per_launch = TF32 rows + K-extension rows of every probed list once (algorithmic HBM "

@@ -185,6 +185,10 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   } else if (s == "scan_tc_tau_probes") c->params.scan_tc_tau_probes = value;
   else if (s == "scan_tc_cmax_mb") c->params.scan_tc_cmax_mb = value;
   else if (s == "scan_tc_split") c->params.scan_tc_split = value;
+  else if (s == "search_upload_pieces") {
+    if (value < 1 || value > 8) return fail(SPF_E_INVALID, "search_upload_pieces must be in [1,8]");
+    c->params.search_upload_pieces = value;
+  }
   else if (s == "tc_min_k") c->params.tc_min_k = value;
   else if (s == "tc_min_m") c->params.tc_min_m = value;
   else if (s == "tc_pipe") c->params.tc_pipe = value;

@@ -71,6 +71,7 @@ struct Params {
   int scan_tc_bucket = 0;    // candidate entries per query kept by the tensor scan (overflow: exact fallback); 0: 256, or 1024 for d > 256
   int scan_tc_cmax_mb = 40960; // keep the bound pass's chunk maxima (one GEMM pass) while they fit in this many MB; 0: always two passes
   int scan_tc_tau_probes = 0;  // probes per query that take part in the bound pass (0: all)
+  int search_upload_pieces = 2; // spf_search_batch, >= 32768 queries: upload in this many pieces, probe of a piece under the next upload (<= 8; 1: off)
   int scan_tc_split = 1;       // bound pass as two concurrent launches (multi-unit lists | single-unit lists): 0 off, 1 automatic, > 1 SMs of the first
   int exact_tma = 6;         // CUDA-core direct-form kernel: bit m set = metric m uses the TMA-staged 128 x 128 kernel (default: Manhattan, Chebyshev)
   int sum_hub = 0;           // compute_mean: clusters of at least this many members use the deep, column-sliced launch (0: 8192)

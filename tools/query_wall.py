@@ -1,5 +1,5 @@
 """Wall time per search call of the bench batch (10 k queries, top-10, nprobe 10), profiling off.
-usage: python tools/query_wall.py [nq] [nprobe] [reps]"""
+usage: python tools/query_wall.py [nq] [nprobe] [reps] [param=value ...]"""
 import sys
 import time
 
@@ -15,6 +15,9 @@ nprobe = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 rows = bench.make_rows(0)
 ctx = s.Context(0)
+for kv in sys.argv[4:]:                       # name=value context parameters
+    name, value = kv.split("=")
+    ctx.set_param(name, int(value))
 ds = s.Dataset(ctx, rows)
 cent = np.arange(bench.K_CENT, dtype=np.uint64)
 res = ds.assign(0, cent)
