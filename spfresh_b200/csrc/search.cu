@@ -1347,6 +1347,57 @@ static int search_scan(spf_index* idx, const float* Qp, uint64_t nq, uint32_t k,
   return SPF_OK;
 }
 
+// Host queries -> device rows `Qd` (row pitch ld, padding already zeroed in stream order) and the centroid
+// probe of those queries.
+static int upload_and_probe(spf_index* idx, const float* queries, uint64_t nq, uint32_t nprobe, float prune_factor,
+                            float* Qd, uint32_t* probe, float* thr, uint32_t* seqbase) {
+  spf_ctx* c = idx->ctx;
+  cudaStream_t st = c->stream;
+  const uint32_t ld = idx->ld, d = idx->d;
+  // Large batches: the queries travel in pieces on the auxiliary stream and the centroid probe of a piece
+  // (independent per query) runs while the next piece is still on the bus — 100 k x 128 queries are 0.93 ms
+  // of PCIe time that otherwise sits in front of the first kernel.  Every probe call has ~0.25 ms of fixed
+  // cost (a host round trip, two dozen small kernels), so two pieces are the optimum: 100 k queries, nprobe
+  // 8: 7.81 ms (one piece), 7.55 ms (two), 7.85 ms (four).
+  const uint64_t npieces = c->params.search_upload_pieces > 1 ? (uint64_t)c->params.search_upload_pieces : 1;
+  const uint64_t piece = nq >= 32768 && npieces > 1 ? ((nq + npieces - 1) / npieces + 127) / 128 * 128 : nq;
+  if (piece >= nq) {
+    SPF_CUDA(cudaMemcpy2DAsync(Qd, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq, cudaMemcpyHostToDevice, st));
+    SPF_TRY(search_probe(idx, Qd, nq, nprobe, prune_factor, probe, thr, seqbase));
+  } else {
+    struct Events {
+      cudaEvent_t e[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } ev;
+    if (!c->aux_stream) SPF_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& x : ev.e) SPF_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    SPF_CUDA(cudaEventRecord(ev.e[8], st));                            // Q is allocated (and zeroed) in stream order
+    SPF_CUDA(cudaStreamWaitEvent(c->aux_stream, ev.e[8], 0));
+    int rc = SPF_OK;
+    uint32_t np = 0;
+    for (uint64_t q0 = 0; q0 < nq; q0 += piece, ++np) {
+      const uint64_t n = nq - q0 < piece ? nq - q0 : piece;
+      if (cudaMemcpy2DAsync(Qd + q0 * ld, (size_t)ld * 4, queries + q0 * d, (size_t)d * 4, (size_t)d * 4, n,
+                            cudaMemcpyHostToDevice, c->aux_stream) != cudaSuccess ||
+          cudaEventRecord(ev.e[np], c->aux_stream) != cudaSuccess) {
+        rc = fail(SPF_E_CUDA, "query upload: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      }
+    }
+    uint32_t ip = 0;
+    for (uint64_t q0 = 0; rc == SPF_OK && ip < np; q0 += piece, ++ip) {
+      const uint64_t n = nq - q0 < piece ? nq - q0 : piece;
+      if (cudaStreamWaitEvent(st, ev.e[ip], 0) != cudaSuccess) { rc = fail(SPF_E_CUDA, "cudaStreamWaitEvent failed"); break; }
+      rc = search_probe(idx, Qd + q0 * ld, n, nprobe, prune_factor, probe + q0 * nprobe, thr + q0, seqbase + q0 * nprobe);
+    }
+    if (rc != SPF_OK) {                                                // nothing may still write into Q when it is freed
+      cudaStreamSynchronize(c->aux_stream);
+      return rc;
+    }
+  }
+  return SPF_OK;
+}
+
 int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t k, uint32_t nprobe,
                      float prune_factor, uint64_t* ids, float* dists, uint32_t* counts, float* vectors,
                      uint64_t* keys) {
@@ -1380,47 +1431,7 @@ int spf_search_batch(spf_index* idx, const float* queries, uint64_t nq, uint32_t
   SPF_TRY(d_bytes.alloc(st, 1));
   SPF_CUDA(cudaMemsetAsync(d_bytes.p, 0, sizeof(unsigned long long), st));
   if (ld != d) SPF_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)nq * ld * sizeof(float), st));
-  // Large batches: the queries travel in pieces on the auxiliary stream and the centroid probe of a piece
-  // (independent per query) runs while the next piece is still on the bus — 100 k x 128 queries are 0.93 ms
-  // of PCIe time that otherwise sits in front of the first kernel.  Every probe call has ~0.25 ms of fixed
-  // cost (a host round trip, two dozen small kernels), so two pieces are the optimum: 100 k queries, nprobe
-  // 8: 7.81 ms (one piece), 7.55 ms (two), 7.85 ms (four).
-  const uint64_t npieces = c->params.search_upload_pieces > 1 ? (uint64_t)c->params.search_upload_pieces : 1;
-  const uint64_t piece = nq >= 32768 && npieces > 1 ? ((nq + npieces - 1) / npieces + 127) / 128 * 128 : nq;
-  if (piece >= nq) {
-    SPF_CUDA(cudaMemcpy2DAsync(Q.p, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq, cudaMemcpyHostToDevice, st));
-    SPF_TRY(search_probe(idx, Q.p, nq, nprobe, prune_factor, probe.p, thr.p, seqbase.p));
-  } else {
-    struct Events {
-      cudaEvent_t e[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-      ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
-    } ev;
-    if (!c->aux_stream) SPF_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t& x : ev.e) SPF_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-    SPF_CUDA(cudaEventRecord(ev.e[8], st));                            // Q is allocated (and zeroed) in stream order
-    SPF_CUDA(cudaStreamWaitEvent(c->aux_stream, ev.e[8], 0));
-    int rc = SPF_OK;
-    uint32_t np = 0;
-    for (uint64_t q0 = 0; q0 < nq; q0 += piece, ++np) {
-      const uint64_t n = nq - q0 < piece ? nq - q0 : piece;
-      if (cudaMemcpy2DAsync(Q.p + q0 * ld, (size_t)ld * 4, queries + q0 * d, (size_t)d * 4, (size_t)d * 4, n,
-                            cudaMemcpyHostToDevice, c->aux_stream) != cudaSuccess ||
-          cudaEventRecord(ev.e[np], c->aux_stream) != cudaSuccess) {
-        rc = fail(SPF_E_CUDA, "query upload: %s", cudaGetErrorString(cudaGetLastError()));
-        break;
-      }
-    }
-    uint32_t ip = 0;
-    for (uint64_t q0 = 0; rc == SPF_OK && ip < np; q0 += piece, ++ip) {
-      const uint64_t n = nq - q0 < piece ? nq - q0 : piece;
-      if (cudaStreamWaitEvent(st, ev.e[ip], 0) != cudaSuccess) { rc = fail(SPF_E_CUDA, "cudaStreamWaitEvent failed"); break; }
-      rc = search_probe(idx, Q.p + q0 * ld, n, nprobe, prune_factor, probe.p + q0 * nprobe, thr.p + q0, seqbase.p + q0 * nprobe);
-    }
-    if (rc != SPF_OK) {                                                // nothing may still write into Q when it is freed
-      cudaStreamSynchronize(c->aux_stream);
-      return rc;
-    }
-  }
+  SPF_TRY(upload_and_probe(idx, queries, nq, nprobe, prune_factor, Q.p, probe.p, thr.p, seqbase.p));
   SPF_TRY(search_scan(idx, Q.p, nq, k, nprobe, probe.p, thr.p, seqbase.p, o_ids.p, o_dists.p, o_counts.p, o_keys.p, o_slots.p,
                       d_bytes.p));
   DevBuf<float> o_vec;
@@ -1530,13 +1541,13 @@ int spf_search_sharded(spf_index* idx, spf_comm* comm, const float* queries, uin
   SPF_CUDA(cudaMemsetAsync(d_bytes.p, 0, sizeof(unsigned long long), st));
   float* Qmine = Q.p + (size_t)rank * nq_local * ld;
   if (ld != d) SPF_CUDA(cudaMemsetAsync(Qmine, 0, (size_t)nq_local * ld * sizeof(float), st));
-  SPF_CUDA(cudaMemcpy2DAsync(Qmine, (size_t)ld * 4, queries, (size_t)d * 4, (size_t)d * 4, nq_local, cudaMemcpyHostToDevice, st));
+  // own slice: upload and probe (in pieces for large slices), then the slices travel to every rank
+  SPF_TRY(upload_and_probe(idx, queries, nq_local, nprobe, prune_factor, Qmine, probe.p + (size_t)rank * nq_local * nprobe,
+                           thr.p + (size_t)rank * nq_local, seqbase.p + (size_t)rank * nq_local * nprobe));
   {
     KernelTimer t(c, "exchange");
     SPF_TRY(comm_allgather(c, comm, Qmine, Q.p, (size_t)nq_local * ld * sizeof(float)));
   }
-  SPF_TRY(search_probe(idx, Qmine, nq_local, nprobe, prune_factor, probe.p + (size_t)rank * nq_local * nprobe,
-                       thr.p + (size_t)rank * nq_local, seqbase.p + (size_t)rank * nq_local * nprobe));
   {
     KernelTimer t(c, "exchange");
     SPF_TRY(comm_group_start(comm));
