@@ -453,12 +453,18 @@ __global__ void __launch_bounds__(EV_WARPS * 32) exact_eval_kernel(ResolveDev a)
 // ---------------------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------------------
-constexpr int FN_MAX = 2;             // short-list entries per lane (short list <= 64 entries)
-
-template <int METRIC>
+// A short list has a dozen entries on average (at most 64), so a point gets half a warp: two points
+// per warp, FN_MAX entries per lane.  All warp-wide primitives run with the full mask and stay inside
+// the 16-lane group by construction (xor / up shuffles with offsets < 16, ballots masked per group).
+template <int METRIC, int FN_LANES>    // FN_LANES: lanes per point
 __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
+  constexpr int FN_GROUPS = 32 / FN_LANES;
+  constexpr int FN_MAX = 64 / FN_LANES;  // short-list entries per lane (short list <= 64 entries)
   const int lane = threadIdx.x & 31;
-  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int gl = lane & (FN_LANES - 1);                                  // lane within the point's group
+  const int grp = lane / FN_LANES;                                       // which point of the warp
+  const unsigned gmask = (FN_LANES == 32 ? 0xffffffffu : ((1u << FN_LANES) - 1u)) << (grp * FN_LANES);
+  const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * FN_GROUPS;   // points per grid sweep
   const float INF = __int_as_float(0x7f800000);
   const bool approx = a.xnorm != nullptr;
   // two-level prefetch: a row's entry count and overflow mark two rows ahead, its live entries one
@@ -473,28 +479,31 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
       const ShortEnt* sl = a.sl + ((size_t)rr << a.sl_shift);
 #pragma unroll
       for (int u = 0; u < FN_MAX; ++u)
-        if ((uint32_t)(u * 32 + lane) < n) p.en[u] = sl[u * 32 + lane];
+        if ((uint32_t)(u * FN_LANES + gl) < n) p.en[u] = sl[u * FN_LANES + gl];
     }
     return p;
   };
-  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t r_first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * FN_GROUPS;   // the warp's first point
+  uint32_t r = r_first + grp;
   uint2 cur_n = prefetch_n(r);
-  uint2 nx_n = prefetch_n(r + warps_total);
+  uint2 nx_n = prefetch_n(r + stride);
   PreE cur_e = prefetch_e(r, cur_n.x);
-  for (; r < a.m; r += warps_total) {
-    const uint32_t n = cur_n.x, nm = cur_n.y;
+  for (uint32_t rw = r_first; rw < a.m; rw += stride, r += stride) {      // warp-uniform trip count
+    const uint32_t nm = cur_n.y;
     const PreE cur = cur_e;
+    // a group without a point (past the end) or whose row belongs to the dense fallback idles through
+    // the shuffles with an empty list and writes nothing
+    const bool live = r < a.m && !(nm & NMEM_OVERFLOW_BIT);
+    const uint32_t n = live ? cur_n.x : 0u;
     cur_n = nx_n;
-    nx_n = prefetch_n(r + 2 * warps_total);
-    cur_e = prefetch_e(r + warps_total, cur_n.x);
-    if (nm & NMEM_OVERFLOW_BIT) continue;            // the dense fallback owns this row
-    ShortEnt* sl = a.sl + ((size_t)r << a.sl_shift);
+    nx_n = prefetch_n(r + 2 * stride);
+    cur_e = prefetch_e(r + stride, cur_n.x);
     ShortEnt en[FN_MAX];
     float bd = INF;
     uint32_t bj = 0xffffffffu;
 #pragma unroll
     for (int u = 0; u < FN_MAX; ++u) {
-      const uint32_t e = u * 32 + lane;
+      const uint32_t e = u * FN_LANES + gl;
       en[u] = cur.en[u];
       if (e < n && (en[u].flags & SE_NEED_EVAL)) {   // did not fit the work list (rare): recompute here
         en[u].v = thread_dist<METRIC>(a.P + (size_t)r * a.ld, a.C + (size_t)en[u].j * a.ld, a.ld);
@@ -504,28 +513,28 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
       if (e < n && (en[u].flags & SE_KIND_MASK) == SE_BAND && lex_less(en[u].v, en[u].j, bd, bj)) { bd = en[u].v; bj = en[u].j; }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = FN_LANES / 2; o > 0; o >>= 1) {
       const float od = __shfl_xor_sync(0xffffffffu, bd, o);
       const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
       if (lex_less(od, oj, bd, bj)) { bd = od; bj = oj; }
     }
     if (!(bd < INF)) { bd = INF; bj = 0; }   // fold identity (0, +inf): nothing was < inf
-    if (lane == 0) {
+    if (gl == 0 && live) {
       a.best[r] = bj;
       a.dmin[r] = bd;
     }
-    if (!a.want_members) {
-      if (lane == 0) a.nmem[r] = 1;
+    if (!a.want_members) {                   // uniform over the launch
+      if (gl == 0 && live) a.nmem[r] = 1;
       continue;
     }
     const float thr = __fmul_rn(bd, a.factor);
-    const float* x = a.P + (size_t)r * a.ld;
+    const float* x = a.P + (size_t)(live ? r : 0u) * a.ld;
     float E = 0.0f;
     uint32_t member = 0;
     bool best_listed = false;
 #pragma unroll
     for (int u = 0; u < FN_MAX; ++u) {
-      const uint32_t e = u * 32 + lane;
+      const uint32_t e = u * FN_LANES + gl;
       if (e >= n) continue;
       const uint32_t kind = en[u].flags & SE_KIND_MASK, j = en[u].j;
       const bool ex = (en[u].flags & SE_EXACT) != 0;
@@ -560,27 +569,29 @@ __global__ void __launch_bounds__(RS_WARPS * 32) finalize_kernel(ResolveDev a) {
       }
       member |= mem ? (1u << u) : 0u;
     }
-    // member list (uint32 slots) of the row
+    // member list (uint32 slots) of the row: prefix sum over the group's lanes
+    __syncwarp();
     const uint32_t mine = (uint32_t)__popc(member);
     uint32_t incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < FN_LANES; o <<= 1) {
       const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
+      if (gl >= o) incl += up;
     }
-    uint32_t out = __shfl_sync(0xffffffffu, incl, 31);
-    best_listed = __any_sync(0xffffffffu, best_listed);
-    __syncwarp();
-    uint32_t* memlist = a.memlist + ((size_t)r << a.sl_shift);
-    uint32_t pos = incl - mine;
+    uint32_t out = __shfl_sync(0xffffffffu, incl, grp * FN_LANES + FN_LANES - 1);
+    best_listed = (__ballot_sync(0xffffffffu, best_listed) & gmask) != 0u;
+    if (live) {
+      uint32_t* memlist = a.memlist + ((size_t)r << a.sl_shift);
+      uint32_t pos = incl - mine;
 #pragma unroll
-    for (int u = 0; u < FN_MAX; ++u)
-      if ((member >> u) & 1u) memlist[pos++] = en[u].j;
-    if (!best_listed) {         // only when every distance was inf/NaN: members = {slot 0}
-      if (lane == 0) memlist[0] = 0u;
-      out = 1;
+      for (int u = 0; u < FN_MAX; ++u)
+        if ((member >> u) & 1u) memlist[pos++] = en[u].j;
+      if (!best_listed) {       // only when every distance was inf/NaN: members = {slot 0}
+        if (gl == 0) memlist[0] = 0u;
+        out = 1;
+      }
+      if (gl == 0) a.nmem[r] = out;
     }
-    if (lane == 0) a.nmem[r] = out;
   }
 }
 
@@ -755,7 +766,8 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   // persistent grids sized to exactly one resident wave (classify: 3 CTAs / SM by registers,
   // finalize: 4), rows are taken grid-stride
   uint64_t blocks = ceil_div(a.m, RS_WARPS);
-  uint64_t blocks_cls = blocks, blocks_fin = blocks;
+  const int fn_lanes = c->params.finalize_lanes == 8 ? 8 : (c->params.finalize_lanes == 32 ? 32 : 16);
+  uint64_t blocks_cls = blocks, blocks_fin = ceil_div(a.m, RS_WARPS * (32 / fn_lanes));
   int cls_per_sm = 2;
   if (a.xnorm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cls_per_sm, classify_kernel<true>, RS_WARPS * 32, 0);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cls_per_sm, classify_kernel<false>, RS_WARPS * 32, 0);
@@ -777,7 +789,9 @@ int resolve_chunk_t(spf_ctx* c, ResolveState* s, const ResolveArgs& a, uint64_t 
   }
   {
     KernelTimer t2(c, "finalize");
-    finalize_kernel<METRIC><<<(unsigned)blocks_fin, RS_WARPS * 32, 0, st>>>(d);
+    if (fn_lanes == 8) finalize_kernel<METRIC, 8><<<(unsigned)blocks_fin, RS_WARPS * 32, 0, st>>>(d);
+    else if (fn_lanes == 32) finalize_kernel<METRIC, 32><<<(unsigned)blocks_fin, RS_WARPS * 32, 0, st>>>(d);
+    else finalize_kernel<METRIC, 16><<<(unsigned)blocks_fin, RS_WARPS * 32, 0, st>>>(d);
     SPF_TRY(check_launch(c, "finalize_kernel"));
   }
   return SPF_OK;

@@ -1,5 +1,6 @@
-"""assign_tc_kernel epilogue variants (tc_pipe 0 / 1) on the device-resident assign step (1M x 128,
-k = 4096, N(0,1)): per-kernel times and result identity.  usage: python tools/pipe_variants.py [steps]"""
+"""Kernel variants selected by one context parameter (default tc_pipe: assign_tc_kernel epilogue 0 / 1) on
+the device-resident assign step (1M x 128, k = 4096, N(0,1)): per-kernel times and result identity.
+usage: python tools/pipe_variants.py [steps] [values, comma separated] [parameter name]"""
 import json
 import os
 import sys
@@ -14,13 +15,14 @@ import spfresh_b200 as s  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1]
+pname = sys.argv[3] if len(sys.argv) > 3 else "tc_pipe"
 rows = bench.make_rows(0)
 cent = np.arange(bench.K_CENT, dtype=np.uint64)
 kn = ["assign_tc", "classify", "exact_eval", "finalize", "overflow", "cc_matrix", "csr"]
 ref = None
 for pipe in variants:
     ctx = s.Context(0)
-    ctx.set_param("tc_pipe", pipe)
+    ctx.set_param(pname, pipe)
     ds = s.Dataset(ctx, rows)
     ext = torch.cuda.ExternalStream(ctx.stream)
     for _ in range(3):
@@ -48,7 +50,7 @@ for pipe in variants:
     else:
         same = bool(np.array_equal(ref.best, f.best) and np.array_equal(ref.dmin.view(np.uint32), f.dmin.view(np.uint32))
                     and np.array_equal(ref.offsets, f.offsets) and np.array_equal(ref.members, f.members))
-    os.write(OUT, (json.dumps({"tc_pipe": pipe, "ms_per_step": ms,
+    os.write(OUT, (json.dumps({pname: pipe, "ms_per_step": ms,
                                "kernels_ms": {k: round(float(np.median(v)), 4) for k, v in acc.items()},
                                "overflow_rows": ctx.last_overflow_rows(), "members": int(f.members.size),
                                "identical_to_first_variant": same}) + "\n").encode())
