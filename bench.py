@@ -49,8 +49,9 @@ N_ROWS, DIM, K_CENT = 1_000_000, 128, 4096
 TC_DRAM_BYTES_PER_LAUNCH = 1.88e9
 # the same for one bound-pass launch of scan_tc_kernel on the bench's 10k-query batch (None until captured)
 SCAN_TC_DRAM_BYTES_PER_LAUNCH = 5.76e9
-SCAN_TC_DRAM_SOURCE = ("ncu dram__bytes_read+write.sum of the bound-pass launch on this batch, profiles/r01_ncu_scan_tc_v2.txt "
-                       "(5.61 GB read = lists once + gathered query rows, 0.15 GB chunk maxima written)")
+SCAN_TC_DRAM_SOURCE = ("ncu dram__bytes_read+write.sum of the bound pass's two launches on this batch, "
+                       "profiles/r02_ncu_scan_tc_split_v1.txt (multi-unit lists on 74 SMs: 1.19 GB read + 0.10 GB written; "
+                       "single-unit lists on 74 SMs: 4.40 GB read + 0.08 GB written; under ncu the launches run one after the other)")
 NQ, TOPK = 10_000, 10
 METRIC_NAME = "kmeans_assign_pts_per_s"
 WORKLOAD = "assign_points_to_clusters 1M x 128 f32, k=4096, squared-Euclidean, boundary 1.1, iid N(0,1)"
