@@ -62,6 +62,7 @@ struct Params {
   int tc_min_k = 64;         // use the tensor path only when k >= this
   int tc_min_m = 1024;       // ... and m >= this
   int finalize_lanes = 16;   // finalize_kernel: lanes per point (8, 16 or 32)
+  int medoid_direct = 1;     // medoid_kernel: 1 stage only the member rows and read the cluster mean in place, 0 stage both rows of every pair
   int tc_pipe = 0;           // assign_tc_kernel epilogue: 0 load the whole slice first, 1 half-slice pipeline across tiles
   int no_host_staging = 0;   // 1: pageable host buffers go to cudaMemcpyAsync directly (driver-staged), for comparison
   int kmpp_exact_sum = 1;    // 1: sequential f32 sum (bit-parity with the reference)

@@ -406,12 +406,13 @@ __global__ void expand_cluster_ids_kernel(const uint64_t* __restrict__ offsets, 
 
 // ---- medoid (hierarchical.rs:155-171): argmin over members of d(row, mean), strict <, leftmost
 // wins, identity (0, +inf).  key = dist bits << 32 | position inside the member list.
-template <int METRIC>
+// DIRECT: only the member rows are staged (warp_row_dist), the mean is read in place.
+template <int METRIC, bool DIRECT>
 __global__ void __launch_bounds__(PD_THREADS)
 medoid_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restrict__ rows,
               const uint32_t* __restrict__ cid, const uint64_t* __restrict__ offsets,
               const float* __restrict__ means, uint64_t total, unsigned long long* __restrict__ keys) {
-  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  __shared__ typename std::conditional<DIRECT, RowDistSmem, PairDistSmem>::type sm[PD_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
   for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < total; base += nwarps * 32) {
@@ -425,7 +426,9 @@ medoid_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restri
       pa = X + (size_t)rows[t] * ld;
       pb = means + (size_t)c * ld;
     }
-    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    float dv;
+    if constexpr (DIRECT) dv = warp_row_dist<METRIC>(pa, pb, ld, sm[warp]);
+    else dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
     if (valid && dv < __int_as_float(0x7f800000)) {
       const unsigned long long key = ((unsigned long long)__float_as_uint(dv) << 32) | (uint32_t)(t - offsets[c]);
       atomicMin(&keys[c], key);
@@ -1438,6 +1441,21 @@ unsigned pd_grid(spf_ctx* c, uint64_t count) {
   return (unsigned)(blocks > cap ? cap : (blocks ? blocks : 1));
 }
 
+// the medoid pass of all three entry points (params.medoid_direct picks the staging, results are the same bits)
+int launch_medoid_kernel(spf_ctx* c, int metric, const float* X, uint32_t ld, const uint64_t* d_rows, const uint32_t* cid,
+                         const uint64_t* d_offsets, const float* means, uint64_t total, unsigned long long* keys) {
+  cudaStream_t st = c->stream;
+  return dispatch_metric(metric, [&](auto M) {
+    if (c->params.medoid_direct)
+      medoid_kernel<decltype(M)::value, true><<<pd_grid(c, total), PD_THREADS, 0, st>>>(X, ld, d_rows, cid, d_offsets,
+                                                                                          means, total, keys);
+    else
+      medoid_kernel<decltype(M)::value, false><<<pd_grid(c, total), PD_THREADS, 0, st>>>(X, ld, d_rows, cid, d_offsets,
+                                                                                           means, total, keys);
+    return check_launch(c, "medoid_kernel");
+  });
+}
+
 }  // namespace
 
 // ---- launchers shared with kmeans.cu (the device-resident row-sharded iteration) ---------------
@@ -1458,11 +1476,7 @@ int launch_medoid_keys(spf_ctx* c, int metric, const float* X, uint32_t ld, cons
   SPF_TRY(cid.alloc(st, total));
   expand_cluster_ids_kernel<<<k, 256, 0, st>>>(d_offsets, cid.p);
   SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
-  return dispatch_metric(metric, [&](auto M) {
-    medoid_kernel<decltype(M)::value><<<pd_grid(c, total), PD_THREADS, 0, st>>>(X, ld, d_rows, cid.p, d_offsets, means,
-                                                                                  total, keys);
-    return check_launch(c, "medoid_kernel");
-  });
+  return launch_medoid_kernel(c, metric, X, ld, d_rows, cid.p, d_offsets, means, total, keys);
 }
 
 namespace {
@@ -1493,11 +1507,7 @@ int update_medoids_dev(spf_dataset* ds, int metric, const uint64_t* d_offsets, c
   SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
   if (total) {
     KernelTimer t(c, "medoid");
-    SPF_TRY(dispatch_metric(metric, [&](auto M) {
-      medoid_kernel<decltype(M)::value><<<pd_grid(c, total), PD_THREADS, 0, st>>>(
-          ds->x, ld, d_rows, cid.p, d_offsets, means.p, total, keys.p);
-      return check_launch(c, "medoid_kernel");
-    }));
+    SPF_TRY(launch_medoid_kernel(c, metric, ds->x, ld, d_rows, cid.p, d_offsets, means.p, total, keys.p));
   }
   medoid_finalize_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys.p, d_offsets, d_rows, d_old.p, k, d_new.p);
   SPF_TRY(check_launch(c, "medoid_finalize_kernel"));
@@ -1614,11 +1624,7 @@ int spf_medoid_candidates(spf_dataset* ds, int metric, const spf_assign_result* 
   expand_cluster_ids_kernel<<<k, 256, 0, st>>>(r->offsets, cid.p);
   SPF_TRY(check_launch(c, "expand_cluster_ids_kernel"));
   if (r->total) {
-    SPF_TRY(dispatch_metric(metric, [&](auto M) {
-      medoid_kernel<decltype(M)::value><<<pd_grid(c, r->total), PD_THREADS, 0, st>>>(
-          ds->x, ld, d_rows.p, cid.p, r->offsets, d_means.p, r->total, keys.p);
-      return check_launch(c, "medoid_kernel");
-    }));
+    SPF_TRY(launch_medoid_kernel(c, metric, ds->x, ld, d_rows.p, cid.p, r->offsets, d_means.p, r->total, keys.p));
   }
   medoid_candidates_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys.p, r->offsets, d_rows.p, k, d_dist.p, d_row.p);
   SPF_TRY(check_launch(c, "medoid_candidates_kernel"));

@@ -452,6 +452,28 @@ def test_update_medoids_matches_oracle(spf, ctx, oracle, metric):
                           oracle.update_medoids(data, metric, off, mem, [77, 1]))
 
 
+@pytest.mark.parametrize("direct", [1, 0])
+@pytest.mark.parametrize("d", [3, 130, 300])
+@pytest.mark.parametrize("metric", METRICS)
+def test_medoid_staging_variants_match_oracle(spf, ctx, oracle, metric, d, direct):
+    """medoid_kernel with the member rows staged alone and the cluster mean read in place (medoid_direct = 1,
+    128 dimensions per step: one, two and three steps here) and with both rows of every pair staged (0)."""
+    data = clustered(3000, d, 12, 77 + d)
+    cent = np.random.default_rng(5).choice(3000, 24, replace=False)
+    ds = spf.Dataset(ctx, data)
+    res = ds.assign(metric, cent)
+    f = res.fetch()
+    ref_rows = oracle.update_medoids(data, metric, f.offsets, f.members, cent)
+    ctx.set_param("medoid_direct", direct)
+    try:
+        assert np.array_equal(ds.update_medoids_from(metric, res, cent), ref_rows)
+        assert np.array_equal(ds.update_medoids(metric, f.offsets, f.members, cent), ref_rows)
+    finally:
+        ctx.set_param("medoid_direct", 1)
+        res.free()
+        ds.free()
+
+
 def test_mean_kat_on_device(spf, ctx, kats):
     kat = kats["mean"][0]                          # utils.rs:24-32
     data = np.array(kat["data"], np.float32)

@@ -1,4 +1,4 @@
-"""Where a k-means update goes (1M x 128, k = 4096): python tools/update_prof.py"""
+"""Where a k-means update goes (1M x 128, k = 4096): python tools/update_prof.py [knob=value ...]"""
 import sys
 import time
 
@@ -10,6 +10,9 @@ import spfresh_b200 as s  # noqa: E402
 
 rows = bench.make_rows(0)
 ctx = s.Context(0)
+for arg in sys.argv[1:]:                      # knobs: python tools/update_prof.py medoid_direct=0
+    name, val = arg.split("=")
+    ctx.set_param(name, int(val))
 ds = s.Dataset(ctx, rows)
 cent = np.arange(bench.K_CENT, dtype=np.uint64)
 res = ds.assign(0, cent)
