@@ -469,7 +469,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(PD_THREADS)
 farthest_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __restrict__ members, uint64_t m,
                 const float* __restrict__ c1vec, uint64_t c1, unsigned long long* __restrict__ key) {
-  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  __shared__ RowDistSmem sm[PD_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t nwarps = (uint64_t)gridDim.x * (PD_THREADS / 32);
   for (uint64_t base = ((uint64_t)blockIdx.x * (PD_THREADS / 32) + warp) * 32; base < m; base += nwarps * 32) {
@@ -477,7 +477,9 @@ farthest_kernel(const float* __restrict__ X, uint32_t ld, const uint64_t* __rest
     const bool valid = t < m && members[t] != c1;
     const float* pa = valid ? c1vec : nullptr;      // c1 as a dataset row or an explicit vector (c1 = UINT64_MAX)
     const float* pb = valid ? X + (size_t)members[t] * ld : nullptr;
-    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    // the member row is staged, c1 is read in place by every lane (a broadcast); d(x, c1) has the bits of
+    // d(c1, x) for all three metrics: the difference only changes sign before it is squared / made absolute
+    const float dv = warp_row_dist<METRIC>(pb, pa, ld, sm[warp]);
     if (valid && dv > 0.0f) {
       const unsigned long long kk = ((unsigned long long)__float_as_uint(dv) << 32) | (0xffffffffu - (uint32_t)t);
       atomicMax(key, kk);
@@ -491,7 +493,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(PD_THREADS)
 kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const float* __restrict__ cvec, int first,
                    float* __restrict__ mind, const uint64_t* __restrict__ d_row, const int* __restrict__ stop) {
-  __shared__ PairDistSmem sm[PD_THREADS / 32];
+  __shared__ RowDistSmem sm[PD_THREADS / 32];
   if (stop && *stop) return;
   if (d_row) cvec = X + (size_t)d_row[0] * ld;            // batched rounds: the row the previous pick wrote
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -500,8 +502,8 @@ kmpp_update_kernel(const float* __restrict__ X, uint32_t ld, uint64_t n, const f
     const uint64_t i = base + lane;
     const bool valid = i < n;
     const float* pa = valid ? X + (size_t)i * ld : nullptr;
-    const float* pb = valid ? cvec : nullptr;       // the newest centroid (a dataset row or an explicit vector)
-    const float dv = warp_pair_dist<METRIC>(pa, pb, ld, sm[warp]);
+    const float* pb = valid ? cvec : nullptr;       // the newest centroid (a dataset row or an explicit vector), read in place
+    const float dv = warp_row_dist<METRIC>(pa, pb, ld, sm[warp]);
     if (valid && (first || dv < mind[i])) mind[i] = dv;
   }
 }

@@ -495,6 +495,26 @@ def test_farthest_matches_oracle(spf, ctx, oracle, metric):
 
 
 @pytest.mark.parametrize("metric", METRICS)
+def test_farthest_and_kmeanspp_long_rows_match_oracle(spf, ctx, oracle, metric):
+    """Rows of 600 floats: five staging steps of the row-staged distance (farthest_kernel, and the generic
+    kmpp_update_kernel that serves rows too long for the tiled update)."""
+    data = clustered(2500, 600, 10, 31 + metric)
+    ds = spf.Dataset(ctx, data)
+    mem = np.random.default_rng(2).permutation(2500)[:1200]
+    for c1 in (int(mem[3]), 2499):
+        assert ds.farthest(metric, c1, mem) == oracle.farthest(data, metric, c1, mem)
+    k = 9
+    u = np.random.default_rng(40 + metric).random(k - 1)
+    ref, fell = oracle.kmeanspp(data, metric, k, 77, u)
+    assert not fell.any()
+    sess = ds.kmeanspp(metric, 77)
+    got = [77] + [sess.round(u[r]) for r in range(k - 1)]
+    sess.free()
+    ds.free()
+    assert got == ref.tolist()
+
+
+@pytest.mark.parametrize("metric", METRICS)
 def test_kmeanspp_matches_oracle(spf, ctx, oracle, metric):
     data = clustered(20000, 32, 25, 8)
     k = 24
