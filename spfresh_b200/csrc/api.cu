@@ -194,6 +194,7 @@ int spf_ctx_set_param(spf_ctx* c, const char* name, int value) {
   else if (s == "tc_pipe") c->params.tc_pipe = value;
   else if (s == "finalize_lanes") c->params.finalize_lanes = value;
   else if (s == "medoid_direct") c->params.medoid_direct = value;
+  else if (s == "sum_fast") c->params.sum_fast = value;
   else if (s == "kmpp_exact_sum") c->params.kmpp_exact_sum = value;
   else if (s == "no_host_staging") c->params.no_host_staging = value;
   else if (s == "cc_matrix_max_k") c->params.cc_matrix_max_k = value;

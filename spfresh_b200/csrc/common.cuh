@@ -78,6 +78,7 @@ struct Params {
   int exact_tma = 6;         // CUDA-core direct-form kernel: bit m set = metric m uses the TMA-staged 128 x 128 kernel (default: Manhattan, Chebyshev)
   int sum_hub = 0;           // compute_mean: clusters of at least this many members use the deep, column-sliced launch (0: 8192)
   int sum_slices = 0;        // ... column slices per hub cluster (0: one; measured slower when > 1)
+  int sum_fast = 1;          // compute_mean producers: suspended barrier waits + three-instruction copy loop for 512-byte rows (0: polling waits, generic loop)
   int exact_packed = 6;      // ... bit per metric: differences of two dimensions from one packed FADD2
   int exact_three_cta = 0;   // ... bit per metric: the packed kernel in its 64-point shape, three CTAs of 128 threads per SM
   int exact_one_cta = 2;     // ... bit per metric: the packed kernel compiled for one CTA per SM (more registers)

@@ -172,10 +172,33 @@ constexpr int CSB_COLS = 8;            // 128-bit columns per lane: rows up to 3
 // blockIdx.y selects a slice of w4 = ld4 / gridDim.y 128-bit columns: the ordered sum is a chain per
 // DIMENSION, so a hub cluster is split over several CTAs by columns (each gathers only its 16 * w4
 // bytes of every member row) without touching the order of the additions.
+// Producer-side wait with a suspend-time hint: the warp sleeps in the barrier unit until the phase
+// completes (or ~1 us passes) instead of polling.  ncu of the polling form (profiles/r02_ncu_update_v1.txt):
+// 41 % of the hub launch's warp instructions were the 12 producer warps' poll loops, issued on the
+// consumer warp's schedulers.  Bounded like tc::mbar_wait.
+__device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t parity) {
+  if (tc::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(tc::smem_u32(bar)), "r"(parity), "r"(1000u)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+// fast != 0: producers wait suspended and rows of exactly 32 128-bit columns (d = 125..128) are copied by a
+// three-instruction loop body (the generic column loop compiled to ~55 instructions per row).
 __global__ void __launch_bounds__(512)
 cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t* __restrict__ offsets,
                       const uint64_t* __restrict__ rows, float* __restrict__ out, int divide, uint32_t stage_rows,
-                      uint32_t nstage, uint32_t nprod, uint64_t min_n, uint64_t max_n) {
+                      uint32_t nstage, uint32_t nprod, uint64_t min_n, uint64_t max_n, int fast) {
   extern __shared__ __align__(128) unsigned char csb_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(csb_raw);          // [nstage]
   uint64_t* empty = full + nstage;                                 // [nstage]
@@ -216,9 +239,18 @@ cluster_sum_ws_kernel(const float* __restrict__ X, uint32_t ld4, const uint64_t*
       idx2 = load_idx(it + 3 * nprod);
       const uint32_t r0 = it * stage_rows;
       const uint32_t cnt = (n32 - r0) < stage_rows ? (n32 - r0) : stage_rows;
-      tc::mbar_wait(&empty[s], ph ^ 1);                       // the consumer is done with this stage
+      if (fast) mbar_wait_suspended(&empty[s], ph ^ 1);       // the consumer is done with this stage
+      else tc::mbar_wait(&empty[s], ph ^ 1);
       const uint32_t st = tc::smem_u32(ring + (size_t)s * stage_rows * w4);
-      if (narrow) {
+      if (fast && w4 == 32) {                                 // one 512-byte row per instruction: lane = column
+        const float4* srcl = X4 + lane;
+        const uint32_t dl = st + (uint32_t)lane * 16u;
+#pragma unroll 4
+        for (uint32_t r = 0; r < cnt; ++r) {
+          const uint32_t row = __shfl_sync(0xffffffffu, idx, (int)r);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dl + r * 512u), "l"(srcl + (size_t)row * ld4) : "memory");
+        }
+      } else if (narrow) {
         const uint32_t pieces = cnt << wsh;
         for (uint32_t p0 = 0; p0 < pieces; p0 += 32) {
           const uint32_t p = p0 + (uint32_t)lane;
@@ -362,7 +394,7 @@ int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t*
       SPF_CUDA(cudaEventRecord(c->aux_ev[0], st));                     // inputs are ready on the main stream
       SPF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
       cluster_sum_ws_kernel<<<dim3(k, nslice), (nprod + 1) * 32, smem, c->aux_stream>>>(X, ld4, d_offsets, d_rows, means, divide,
-                                                                                      stage_rows, nstage, nprod, hub, ~0ull);
+                                                                                      stage_rows, nstage, nprod, hub, ~0ull, c->params.sum_fast);
       SPF_TRY(check_launch(c, "cluster_sum_ws_kernel"));
       SPF_CUDA(cudaEventRecord(c->aux_ev[1], c->aux_stream));
     }
@@ -374,7 +406,7 @@ int launch_cluster_mean(spf_ctx* c, const float* X, uint32_t ld, const uint64_t*
       const uint32_t nstage = 8, nprod = 4;
       const size_t smem = 1024 + (size_t)nstage * stage_bytes;       // <= 129 KB for rows of 1024 floats
       cluster_sum_ws_kernel<<<k, (nprod + 1) * 32, smem, st>>>(X, ld4, d_offsets, d_rows, means, divide, stage_rows, nstage, nprod,
-                                                              0ull, hub);
+                                                              0ull, hub, c->params.sum_fast);
       SPF_TRY(check_launch(c, "cluster_sum_ws_kernel"));
     }
     SPF_CUDA(cudaStreamWaitEvent(st, c->aux_ev[1], 0));                // both halves done before anything downstream

@@ -474,6 +474,31 @@ def test_medoid_staging_variants_match_oracle(spf, ctx, oracle, metric, d, direc
         ds.free()
 
 
+@pytest.mark.parametrize("fast", [1, 0])
+@pytest.mark.parametrize("d,hub", [(128, 64), (126, 0), (40, 64), (260, 64)])
+def test_cluster_mean_producer_variants_match_oracle(spf, ctx, oracle, d, hub, fast):
+    """compute_mean with the suspended-wait / short-loop producers (sum_fast = 1; rows of 32 128-bit columns take
+    the short loop) and with the polling producers (0); sum_hub = 64 sends every cluster of >= 64 members through
+    the deep 12-producer configuration that real data reserves for hub clusters."""
+    data = clustered(7000, d, 20, 300 + d)
+    cent = np.random.default_rng(11).choice(7000, 40, replace=False)
+    ds = spf.Dataset(ctx, data)
+    res = ds.assign(0, cent)
+    f = res.fetch()
+    ref_rows, ref_means = oracle.update_medoids(data, 0, f.offsets, f.members, cent, want_means=True)
+    ctx.set_param("sum_fast", fast)
+    ctx.set_param("sum_hub", hub)
+    try:
+        rows, means = ds.update_medoids_from(0, res, cent, want_means=True)
+        assert np.array_equal(means.view(np.uint32), ref_means.view(np.uint32))
+        assert np.array_equal(rows, ref_rows)
+    finally:
+        ctx.set_param("sum_fast", 1)
+        ctx.set_param("sum_hub", 0)
+        res.free()
+        ds.free()
+
+
 def test_mean_kat_on_device(spf, ctx, kats):
     kat = kats["mean"][0]                          # utils.rs:24-32
     data = np.array(kat["data"], np.float32)
