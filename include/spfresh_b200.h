@@ -355,7 +355,11 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
  * scan: 0 never, 1 automatic, 2 whenever supported), "scan_tc_bucket" (candidates per query, 0 =
  * automatic: 256, or 1024 for d > 256), "scan_tc_tau_probes" (0 = all), "scan_tc_cmax_mb" (budget for the one-pass variant, 0 = two GEMM passes), "force_exact", "tc_min_k", "tc_min_m",
  * "no_host_staging" (1: pageable host buffers are handed to cudaMemcpyAsync instead of the library's threaded pinned staging ring),
- * "kmpp_exact_sum" (1: sequential f32 sum by scan, 2: by the serial add chain — same bits; 0: tree sum), "cc_matrix_max_k". */
+ * "kmpp_exact_sum" (1: sequential f32 sum by scan, 2: by the serial add chain — same bits; 0: tree sum), "cc_matrix_max_k",
+ * "medoid_direct" (update_centroids medoid pass: 1 stage the member rows only and read the cluster mean in place, 0 stage both
+ * rows of every pair), "sum_fast" (compute_mean producer warps: 1 suspended barrier waits + short copy loop, 0 polling waits),
+ * "sum_hub" (clusters of at least this many members take the deep producer configuration, 0 = 8192), "finalize_lanes" (8 / 16 / 32).
+ * Every knob value returns the same bits; the knobs exist for A/B timing and to reach rare paths in the tests. */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 
 /* Test hook: the strictly sequential f32 fold of hierarchical.rs:278 over n host values.  mode 1 is
