@@ -359,7 +359,7 @@ int spf_topk_merge(uint32_t parts, uint64_t nq, uint32_t k, const uint64_t* keys
  * "medoid_direct" (update_centroids medoid pass: 1 stage the member rows only and read the cluster mean in place, 0 stage both
  * rows of every pair), "sum_fast" (compute_mean producer warps: 1 suspended barrier waits + short copy loop, 0 polling waits),
  * "sum_hub" (clusters of at least this many members take the deep producer configuration, 0 = 8192), "finalize_lanes" (8 / 16 / 32).
- * Every knob value returns the same bits; the knobs exist for A/B timing and to reach rare paths in the tests. */
+ * Apart from "kmpp_exact_sum" = 0 every knob value returns the same bits; the knobs exist for A/B timing and to reach rare paths in the tests. */
 int spf_ctx_set_param(spf_ctx* ctx, const char* name, int value);
 
 /* Test hook: the strictly sequential f32 fold of hierarchical.rs:278 over n host values.  mode 1 is
